@@ -1,0 +1,744 @@
+"""
+oracle/oracle.py -- TEST INFRASTRUCTURE ONLY (CPU oracle).
+
+numpy restatement of the reference's CPU algorithms for the Krylov hot path.  Every function cites
+the reference lines (relative to /root/reference) that it follows one-to-one.  SpMV on
+SparseMatrixCSC goes through the plain-C column-scatter loop in oracle.c (what Julia's SparseArrays
+stdlib executes); dense BLAS-2/3 pieces go through numpy (OpenBLAS, the same backend family Julia
+calls through libblastrampoline).
+
+PARITY UNPINNED for raw SpMV/dot/norm values: the reference holds no golden vectors for them
+ and cannot be executed in this image (no Julia).  What IS pinned:
+  * the literal Hessenberg fixtures of reference test/hessenberg.jl:10-26 (tests/golden/),
+  * the reference's own property tests, ported in tests/test_oracle_*.py,
+  * analytic known answers (Laplacian spectrum, manufactured solutions), and scipy cross-checks.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    """Compile liboracle.so with the committed Makefile (gcc only)."""
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "oracle.c")):
+            build()
+        _LIB = ctypes.CDLL(so)
+        _LIB.oracle_laplace_nnz.restype = ctypes.c_int64
+        _LIB.oracle_laplace_nnz.argtypes = [ctypes.c_int64, ctypes.c_int32]
+        _LIB.oracle_laplace_csc_f64.restype = ctypes.c_int64
+        _LIB.oracle_num_threads.restype = ctypes.c_int32
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+# --------------------------------------------------------------------------------------------
+# SparseMatrixCSC stand-in
+# --------------------------------------------------------------------------------------------
+@dataclass
+class CSC:
+    """SparseMatrixCSC{Tv,Int64}: colptr (n+1), rowval (nnz), nzval (nnz); `base` = 1 for Julia
+    indexing, 0 for C indexing.  Field names as in reference src/stationary_sparse.jl:14-18."""
+    m: int
+    n: int
+    colptr: np.ndarray
+    rowval: np.ndarray
+    nzval: np.ndarray
+    base: int = 0
+
+    @property
+    def shape(self):
+        return (self.m, self.n)
+
+    @property
+    def dtype(self):
+        return self.nzval.dtype
+
+    @property
+    def nnz(self):
+        return int(self.colptr[-1] - self.base)
+
+    @staticmethod
+    def from_scipy(A, base=0):
+        A = A.tocsc()
+        A.sort_indices()
+        return CSC(A.shape[0], A.shape[1], A.indptr.astype(np.int64) + base,
+                   A.indices.astype(np.int64) + base, np.ascontiguousarray(A.data), base)
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.nzval, self.rowval - self.base, self.colptr - self.base),
+                             shape=(self.m, self.n))
+
+    def diagonal(self):
+        return self.to_scipy().diagonal()
+
+
+def csc_spmv(A: CSC, x: np.ndarray, y: np.ndarray | None = None) -> np.ndarray:
+    """mul!(y, A::SparseMatrixCSC, x) -- SparseArrays stdlib, serial column scatter."""
+    x = np.ascontiguousarray(x, dtype=A.dtype)
+    if y is None:
+        y = np.empty(A.m, dtype=A.dtype)
+    fn = lib().oracle_csc_spmv_f64 if A.dtype == np.float64 else lib().oracle_csc_spmv_f32
+    fn(ctypes.c_int64(A.m), ctypes.c_int64(A.n), _p(A.colptr), _p(A.rowval), _p(A.nzval),
+       ctypes.c_int64(A.base), _p(x), _p(y))
+    return y
+
+
+def csc_spmm(A: CSC, X: np.ndarray, Y: np.ndarray | None = None) -> np.ndarray:
+    """mul!(Y, A, X) on column-major n x bs blocks (Fortran-ordered numpy arrays)."""
+    X = np.asfortranarray(X, dtype=A.dtype)
+    if Y is None:
+        Y = np.empty((A.m, X.shape[1]), dtype=A.dtype, order="F")
+    fn = lib().oracle_csc_spmm_f64 if A.dtype == np.float64 else lib().oracle_csc_spmm_f32
+    fn(ctypes.c_int64(A.m), ctypes.c_int64(A.n), _p(A.colptr), _p(A.rowval), _p(A.nzval),
+       ctypes.c_int64(A.base), _p(X), ctypes.c_int64(X.shape[0]), _p(Y), ctypes.c_int64(Y.shape[0]),
+       ctypes.c_int64(X.shape[1]))
+    return Y
+
+
+def mul(A, x):
+    """A*x for the operator kinds the reference tests use: SparseMatrixCSC, dense Matrix,
+    LinearMap-like callables (test/cg.jl:71-77)."""
+    if isinstance(A, CSC):
+        return csc_spmm(A, x) if x.ndim == 2 else csc_spmv(A, x)
+    if callable(A):
+        return A(x)
+    return A @ x
+
+
+def opsize(A, d=None):
+    s = A.shape
+    return s if d is None else s[d]
+
+
+# --------------------------------------------------------------------------------------------
+# Generators
+# --------------------------------------------------------------------------------------------
+def second_order_central_diff(T, dim):
+    """reference test/laplace_matrix.jl:12 -- SymTridiagonal(fill(2,dim), fill(-1,dim-1))."""
+    import scipy.sparse as sp
+    return sp.diags([np.full(dim - 1, -1, dtype=T), np.full(dim, 2, dtype=T), np.full(dim - 1, -1, dtype=T)],
+                    [-1, 0, 1], format="csc", dtype=T)
+
+
+def laplace_matrix_scipy(T, n, dims):
+    """reference test/laplace_matrix.jl:1-10, literal kron recursion (small sizes)."""
+    import scipy.sparse as sp
+    D = second_order_central_diff(T, n)
+    A = D.copy()
+    for _ in range(2, dims + 1):
+        A = sp.kron(A, sp.identity(n, dtype=T, format="csc"), format="csc") + \
+            sp.kron(sp.identity(A.shape[0], dtype=T, format="csc"), D, format="csc")
+    A = A.tocsc()
+    A.sort_indices()
+    return A
+
+
+def laplace_matrix(T, n, dims, base=0) -> CSC:
+    """laplace_matrix(T, n, dims) as a CSC{T,Int64}; direct C construction (same matrix as the
+    kron recursion, checked against laplace_matrix_scipy in tests)."""
+    T = np.dtype(T)
+    N = int(n) ** dims
+    nnz = lib().oracle_laplace_nnz(n, dims)
+    colptr = np.empty(N + 1, dtype=np.int64)
+    rowval = np.empty(nnz, dtype=np.int64)
+    nzval = np.empty(nnz, dtype=np.float64)
+    got = lib().oracle_laplace_csc_f64(ctypes.c_int64(n), ctypes.c_int32(dims), ctypes.c_int64(base),
+                                       _p(colptr), _p(rowval), _p(nzval))
+    assert got == nnz
+    return CSC(N, N, colptr, rowval, nzval.astype(T, copy=False), base)
+
+
+def advection_dominated(N=50, beta=1000.0):
+    """reference benchmark/advection_diffusion.jl:3-30.  A = laplace/(-h^2) + kron(I_{N^2}, dx),
+    dx = tridiag(-beta/2h, 0, +beta/2h), b = f(x,y,z) on interior points, x fastest.
+    Returns (scipy csc, b)."""
+    import scipy.sparse as sp
+    n = N ** 3
+    h = 1.0 / (N + 1)
+    # xs = range(0, stop=1, length=N+2)[2:N+1]; Julia's twice-precision range gives i/(N+1)
+    xs = np.arange(1, N + 1, dtype=np.float64) / (N + 1)
+    lap = laplace_matrix_scipy(np.float64, N, 3)
+    lap = lap.copy()
+    lap.data = lap.data / -(h ** 2)                     # ./ -h^2
+    lo = np.full(N - 1, -beta / (2 * h))                # -1 => fill(-beta / 2h, N-1)
+    up = np.full(N - 1, beta / (2 * h))                 # +1 => fill( beta / 2h, N-1)
+    dx1 = sp.diags([lo, up], [-1, 1], format="csc")
+    dx = sp.kron(sp.identity(N * N, format="csc"), dx1, format="csc")
+    A = (lap + dx).tocsc()
+    A.sort_indices()
+    X, Y, Z = np.meshgrid(xs, xs, xs, indexing="ij")   # [f(x,y,z) for x, y, z] column-major: x fastest
+    F = np.exp(X * Y * Z) * np.sin(np.pi * X) * np.sin(np.pi * Y) * np.sin(np.pi * Z)
+    b = F.reshape(n, order="F")
+    assert A.shape == (n, n)
+    return A, b
+
+
+# --------------------------------------------------------------------------------------------
+# ConvergenceHistory (reference src/history.jl:54-66, 127-252) -- counts only
+# --------------------------------------------------------------------------------------------
+@dataclass
+class ConvergenceHistory:
+    mvps: int = 0
+    mtvps: int = 0
+    iters: int = 0
+    restart: int | None = None
+    isconverged: bool = False
+    data: dict = field(default_factory=dict)
+
+    def __getitem__(self, k):
+        return self.data[k]
+
+    def __setitem__(self, k, v):
+        self.data[k] = v
+
+    @property
+    def niters(self):
+        return self.iters
+
+    @property
+    def nprods(self):
+        return self.mvps + self.mtvps
+
+    @property
+    def nrests(self):
+        """src/history.jl:252: ceil(iters/restart)."""
+        return int(math.ceil(self.iters / self.restart))
+
+
+class Identity:
+    """reference src/common.jl:28-32."""
+
+    def ldiv(self, x):           # ldiv!(::Identity, x) = x
+        return x
+
+    def ldiv3(self, y, x):       # ldiv!(y, ::Identity, x) = copyto!(y, x)
+        y[...] = x
+        return y
+
+
+class JacobiPrec:
+    """reference test/cg.jl:10-18: ldiv!(y, P, x) = y .= x ./ P.diagonal."""
+
+    def __init__(self, diagonal):
+        self.diagonal = np.asarray(diagonal)
+
+    def ldiv(self, x):
+        x /= self.diagonal
+        return x
+
+    def ldiv3(self, y, x):
+        np.divide(x, self.diagonal, out=y)
+        return y
+
+
+class MatrixPrec:
+    """Factorization-like preconditioner P \\ x with a dense matrix (test/gmres.jl:19,28,33 use lu(A))."""
+
+    def __init__(self, M):
+        import scipy.linalg as sla
+        self.lu = sla.lu_factor(np.asarray(M))
+
+    def ldiv(self, x):
+        import scipy.linalg as sla
+        x[...] = sla.lu_solve(self.lu, x)
+        return x
+
+    def ldiv3(self, y, x):
+        import scipy.linalg as sla
+        y[...] = sla.lu_solve(self.lu, x)
+        return y
+
+
+def _eps(dtype):
+    return np.finfo(np.dtype(dtype)).eps
+
+
+def _real_dtype(dtype):
+    return np.zeros(1, dtype=dtype).real.dtype
+
+
+# --------------------------------------------------------------------------------------------
+# CG (reference src/cg.jl)
+# --------------------------------------------------------------------------------------------
+def cg_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, log=False, Pl=None, initially_zero=False):
+    """cg!(x, A, b; ...) -- reference src/cg.jl:209-242 driving cg_iterator! :120-155 and
+    iterate :43-66 (Identity) / :72-100 (PCG)."""
+    if reltol is None:
+        reltol = math.sqrt(_eps(_real_dtype(b.dtype)))
+    if maxiter is None:
+        maxiter = opsize(A, 1)
+    history = ConvergenceHistory()
+    history["abstol"], history["reltol"] = abstol, reltol
+    resnorm = []
+    # cg_iterator!
+    u = np.zeros_like(x)                                   # :129
+    r = b.astype(x.dtype, copy=True)                       # :130
+    if initially_zero:
+        mv_products = 0
+    else:
+        mv_products = 1
+        c = mul(A, x)                                      # :137
+        r -= c                                             # :138
+    c = np.empty_like(x)
+    residual = float(np.linalg.norm(r))                    # :140
+    tol = max(reltol * residual, abstol)                   # :141
+    identity = Pl is None or isinstance(Pl, Identity)
+    prev_residual = 1.0                                    # :146
+    rho = 1.0                                              # :151
+    if log:
+        history.mvps = mv_products                         # :226-228
+    iteration = 0
+    while True:
+        if iteration >= maxiter or residual <= tol:        # :36
+            break
+        if identity:
+            beta = residual ** 2 / prev_residual ** 2      # :50
+            u[...] = r + beta * u                          # :51
+            c = mul(A, u)                                  # :54
+            alpha = residual ** 2 / float(np.dot(u, c))    # :55
+            x += alpha * u                                 # :58
+            r -= alpha * c                                 # :59
+            prev_residual = residual                       # :61
+            residual = float(np.linalg.norm(r))            # :62
+        else:
+            c = Pl.ldiv3(np.empty_like(r), r)              # :79
+            rho_prev = rho
+            rho = float(np.dot(c, r))                      # :82
+            beta = rho / rho_prev                          # :85
+            u[...] = c + beta * u                          # :86
+            c = mul(A, u)                                  # :89
+            alpha = rho / float(np.dot(u, c))              # :90
+            x += alpha * u                                 # :93
+            r -= alpha * c                                 # :94
+            residual = float(np.linalg.norm(r))            # :96
+        iteration += 1
+        if log:
+            history.iters += 1                             # nextiter!(history, mvps=1) :231
+            history.mvps += 1
+            resnorm.append(residual)                       # :232
+    if log:
+        history.isconverged = residual <= tol              # :238
+        history["resnorm"] = np.array(resnorm)
+        history["tol"] = tol
+        return x, history
+    return x
+
+
+def cg(A, b, **kw):
+    """cg(A, b; kw...) = cg!(zerox(A, b), A, b; initially_zero = true, kw...)  src/cg.jl:162."""
+    x = np.zeros(opsize(A, 1), dtype=np.result_type(b.dtype, np.float32))
+    return cg_(x, A, b, initially_zero=True, **kw)
+
+
+def cg_csc_c(x, A: CSC, b, *, abstol=0.0, reltol=None, maxiter=None, Pl_diag=None, initially_zero=False):
+    """Same algorithm, entirely inside oracle.c (fast path for bigger parity cases)."""
+    if reltol is None:
+        reltol = math.sqrt(_eps(np.float64))
+    if maxiter is None:
+        maxiter = A.n
+
+    class Res(ctypes.Structure):
+        _fields_ = [("iters", ctypes.c_int64), ("mvps", ctypes.c_int64), ("isconverged", ctypes.c_int32),
+                    ("pad", ctypes.c_int32), ("tol", ctypes.c_double), ("residual", ctypes.c_double)]
+
+    res = Res()
+    resnorm = np.zeros(maxiter + 1, dtype=np.float64)      # reserve!(history, :resnorm, maxiter+1) :221
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    diag = None if Pl_diag is None else np.ascontiguousarray(Pl_diag, dtype=np.float64)
+    lib().oracle_cg_f64(ctypes.c_int64(A.n), _p(A.colptr), _p(A.rowval), _p(A.nzval), ctypes.c_int64(A.base),
+                        _p(x), _p(b), ctypes.c_double(abstol), ctypes.c_double(reltol), ctypes.c_int64(maxiter),
+                        ctypes.c_int32(1 if initially_zero else 0),
+                        _p(diag) if diag is not None else ctypes.c_void_p(0), _p(resnorm), ctypes.byref(res))
+    h = ConvergenceHistory(mvps=res.mvps, iters=res.iters, isconverged=bool(res.isconverged))
+    h["abstol"], h["reltol"], h["tol"] = abstol, reltol, res.tol
+    h["resnorm"] = resnorm[: res.iters].copy()             # shrink! :239
+    return x, h
+
+
+# --------------------------------------------------------------------------------------------
+# Givens (LinearAlgebra.givensAlgorithm, external stdlib) + FastHessenberg ldiv!
+# --------------------------------------------------------------------------------------------
+def givens_algorithm(f, g):
+    """LinearAlgebra.givensAlgorithm(f, g) -> (c real, s, r) with [c s; -conj(s) c][f; g] = [r; 0].
+    Restates LAPACK xLARTG as Julia's stdlib does (sign convention: c >= 0 when |f| > |g| for
+    reals; version-dependent, see SURVEY.md section 8c -- all users below are invariant to it)."""
+    if np.iscomplexobj(f) or np.iscomplexobj(g):
+        f = complex(f)
+        g = complex(g)
+        if g == 0:
+            return 1.0, 0j, f
+        if f == 0:
+            ag = abs(g)
+            return 0.0, np.conj(g) / ag, ag
+        f1, g1 = abs(f), abs(g)
+        d = math.hypot(f1, g1)
+        ph = f / f1
+        return f1 / d, ph * np.conj(g) / d, ph * d
+    f = float(f)
+    g = float(g)
+    if g == 0.0:
+        return 1.0, 0.0, f
+    if f == 0.0:
+        return 0.0, 1.0, g
+    r = math.hypot(f, g)
+    c, s = f / r, g / r
+    if abs(f) > abs(g) and c < 0:
+        c, s, r = -c, -s, -r
+    return c, s, r
+
+
+def hessenberg_ldiv(H, rhs):
+    """ldiv!(H::FastHessenberg, rhs) -- reference src/hessenberg.jl:15-46.  H is (m+1) x m,
+    mutated to upper triangular; rhs (m+1) mutated: rhs[:m] = LS solution, rhs[m] = signed residual."""
+    width = H.shape[1]
+    for i in range(width):                                              # :24
+        c, s, _ = givens_algorithm(H[i, i], H[i + 1, i])                # :25
+        H[i, i] = c * H[i, i] + s * H[i + 1, i]                         # :28
+        for j in range(i + 1, width):                                   # :31
+            tmp = -np.conj(s) * H[i, j] + c * H[i + 1, j]               # :32
+            H[i, j] = c * H[i, j] + s * H[i + 1, j]                     # :33
+            H[i + 1, j] = tmp                                           # :34
+        tmp = -np.conj(s) * rhs[i] + c * rhs[i + 1]                     # :38
+        rhs[i] = c * rhs[i] + s * rhs[i + 1]                            # :39
+        rhs[i + 1] = tmp                                                # :40
+    # UpperTriangular back-substitution  :44-45
+    for i in range(width - 1, -1, -1):
+        acc = rhs[i]
+        for j in range(i + 1, width):
+            acc -= H[i, j] * rhs[j]
+        rhs[i] = acc / H[i, i]
+    return rhs
+
+
+# --------------------------------------------------------------------------------------------
+# orthogonalize_and_normalize! (reference src/orthogonalize.jl)
+# --------------------------------------------------------------------------------------------
+def orthogonalize_and_normalize_(V, w, h, method="mgs"):
+    """V: n x k (column views), w: n, h: k; all mutated in place.  Returns nrm.
+    method in {"dgks" :13-39, "cgs" :41-51, "mgs" :67-79}."""
+    if method in ("dgks", "cgs"):
+        h[...] = V.conj().T @ w                                         # :15 / :43
+        w -= V @ h                                                      # :16 / :44
+        nrm = float(np.linalg.norm(w))                                  # :17 / :45
+        if method == "dgks":
+            eta = 1.0 / math.sqrt(2.0)                                  # :20
+            projection_size = float(np.linalg.norm(h))                  # :22
+            while nrm < eta * projection_size:                          # :26
+                correction = V.conj().T @ w                             # :27
+                projection_size = float(np.linalg.norm(correction))     # :28
+                w -= V @ correction                                     # :30
+                h += correction                                         # :31
+                nrm = float(np.linalg.norm(w))                          # :32
+    elif method == "mgs":
+        for i in range(V.shape[1]):                                     # :69
+            column = V[:, i]
+            h[i] = np.vdot(column, w)                                   # :71
+            w -= h[i] * column                                          # :72
+        nrm = float(np.linalg.norm(w))                                  # :75
+    else:
+        raise ValueError(method)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        w *= w.dtype.type(1.0) / w.dtype.type(nrm) if nrm != 0 else np.inf  # w .*= inv(nrm)
+    return nrm
+
+
+# --------------------------------------------------------------------------------------------
+# GMRES (reference src/gmres.jl)
+# --------------------------------------------------------------------------------------------
+def gmres_(x, A, b, *, Pl=None, Pr=None, abstol=0.0, reltol=None, restart=None, maxiter=None, log=False,
+           initially_zero=False, orth_meth="mgs"):
+    """gmres!(x, A, b; ...) -- reference src/gmres.jl:184-222 with gmres_iterable! :108-136,
+    iterate :57-106, update_residual! :224-233, init! :235-255, solve_least_squares! :262-271,
+    update_solution! :273-283, expand! :285-304."""
+    T = x.dtype
+    n = opsize(A, 0)
+    if reltol is None:
+        reltol = math.sqrt(_eps(_real_dtype(b.dtype)))
+    if restart is None:
+        restart = min(20, opsize(A, 1))
+    if maxiter is None:
+        maxiter = opsize(A, 1)
+    Pl = Pl or Identity()
+    Pr = Pr or Identity()
+    history = ConvergenceHistory(restart=restart)
+    history["abstol"], history["reltol"] = abstol, reltol
+    resnorm = []
+
+    V = np.zeros((n, restart + 1), dtype=T, order="F")                  # ArnoldiDecomp :11-15
+    H = np.zeros((restart + 1, restart), dtype=T, order="F")
+    nullvec = np.ones(restart + 1, dtype=T)                             # Residual :24-29
+    state = {"accumulator": 1.0, "current": 1.0, "beta": 1.0}
+    mv_products = 1 if initially_zero else 0                            # :122 (sic)
+
+    def init(initially_zero=False):                                     # init! :235-255
+        first_col = V[:, 0]
+        first_col[...] = b                                              # :241
+        if not initially_zero:
+            first_col -= mul(A, x)                                      # :245-246
+        Pl.ldiv(first_col)                                              # :249
+        beta = float(np.linalg.norm(first_col))                         # :252
+        first_col *= T.type(1.0) / T.type(beta) if beta != 0 else np.inf  # :253
+        return beta
+
+    state["current"] = init(initially_zero)                             # :126
+    state["accumulator"], state["beta"] = 1.0, state["current"]         # init_residual! :257-260
+    tol = max(reltol * state["current"], abstol)                        # :129
+    beta = state["current"]                                             # g.β  :133
+    k = 1
+    iteration = 0
+
+    def done(it):
+        return it >= maxiter or state["current"] <= tol                 # :55
+
+    while True:
+        if done(iteration):                                             # :59
+            break
+        # expand! :285-304
+        if isinstance(Pr, Identity):
+            V[:, k] = mul(A, np.ascontiguousarray(V[:, k - 1]))
+            if not isinstance(Pl, Identity):
+                Pl.ldiv(V[:, k])
+        else:
+            nextV = V[:, k]
+            Pr.ldiv3(nextV, V[:, k - 1])
+            nextV[...] = mul(A, np.ascontiguousarray(nextV))
+            Pl.ldiv(nextV)
+        mv_products += 1                                                # :65
+        H[k, k - 1] = orthogonalize_and_normalize_(V[:, :k], V[:, k], H[:k, k - 1], orth_meth)  # :68-73
+        # update_residual! :224-233
+        if H[k, k - 1] == 0:
+            state["current"] = 0.0
+        else:
+            nullvec[k] = -np.conj(np.vdot(nullvec[:k], H[:k, k - 1]) / H[k, k - 1])
+            state["accumulator"] += abs(nullvec[k]) ** 2
+            state["current"] = state["beta"] / math.sqrt(state["accumulator"])
+        k += 1                                                          # :78
+        if k == restart + 1 or done(iteration + 1):                     # :82
+            rhs = np.zeros(k, dtype=T)                                  # solve_least_squares! :262-271
+            rhs[0] = beta
+            hessenberg_ldiv(H[:k, : k - 1], rhs)
+            y = rhs[: k - 1]
+            if isinstance(Pr, Identity):                                # update_solution! :273-283
+                x += V[:, : k - 1] @ y
+            else:
+                Ax = V[:, : k - 1] @ y
+                Pr.ldiv(Ax)
+                x += Ax
+            k = 1                                                       # :90
+            if not done(iteration):                                     # :93 (sic: iteration, not +1)
+                beta = init()                                           # :96
+                state["accumulator"], state["beta"] = 1.0, beta         # :99 (current NOT reset)
+                mv_products += 1                                        # :101
+        iteration += 1
+        if log:
+            history.iters += 1                                          # nextiter! :209
+            history.mvps = mv_products                                  # :210
+            resnorm.append(state["current"])                            # :211
+    history.isconverged = state["current"] <= tol                       # setconv :218 (always)
+    if log:
+        history["resnorm"] = np.array(resnorm)
+        history["tol"] = tol
+        return x, history
+    return x
+
+
+def gmres(A, b, **kw):
+    """gmres(A, b; kw...) = gmres!(zerox(A, b), A, b; initially_zero = true, kw...)  src/gmres.jl:143."""
+    x = np.zeros(opsize(A, 1), dtype=b.dtype)
+    return gmres_(x, A, b, initially_zero=True, **kw)
+
+
+# --------------------------------------------------------------------------------------------
+# MINRES (reference src/minres.jl)
+# --------------------------------------------------------------------------------------------
+def minres_(x, A, b, *, skew_hermitian=False, log=False, abstol=0.0, reltol=None, maxiter=None,
+            initially_zero=False):
+    """minres!(x, A, b; ...) -- reference src/minres.jl:200-237, minres_iterable! :39-89,
+    iterate :97-159."""
+    T = x.dtype
+    if reltol is None:
+        reltol = math.sqrt(_eps(_real_dtype(b.dtype)))
+    if maxiter is None:
+        maxiter = opsize(A, 1)
+    history = ConvergenceHistory()
+    history["abstol"], history["reltol"] = abstol, reltol
+    resnorms = []
+    HT = T if skew_hermitian else _real_dtype(T)
+    v_prev = np.empty_like(x)
+    v_curr = b.astype(T, copy=True)                                     # :49
+    v_next = np.empty_like(x)
+    w_prev = np.zeros_like(x)   # similar(x): contents unspecified, never read before being written
+    w_curr = np.zeros_like(x)
+    w_next = np.zeros_like(x)
+    mv_products = 0
+    if not initially_zero:                                              # :58-63
+        v_next[...] = mul(A, x)
+        v_curr -= v_next
+        mv_products = 1
+    resnorm = float(np.linalg.norm(v_curr))                             # :65
+    tol = max(reltol * resnorm, abstol)                                 # :66
+    H = np.zeros(4, dtype=HT)                                           # :70
+    rhs = np.array([resnorm, 0], dtype=HT)                              # :71
+    v_curr *= T.type(1.0 / resnorm) if resnorm != 0 else np.inf         # :74
+    c_prev, s_prev, c_curr, s_curr = 1.0, 0.0, 1.0, 0.0                 # :77-78
+    if log:
+        history.mvps = mv_products
+    iteration = 1                                                       # start = 1 :93
+    while True:
+        if iteration > maxiter or resnorm <= tol:                       # :95
+            break
+        v_next[...] = mul(A, v_curr)                                    # :104
+        if iteration > 1:
+            v_next -= H[1] * v_prev                                     # :106
+        proj = np.vdot(v_curr, v_next)                                  # :109
+        H[2] = proj if skew_hermitian else np.real(proj)                # :110
+        v_next -= proj * v_curr                                         # :111
+        H[3] = np.linalg.norm(v_next)                                   # :114
+        with np.errstate(divide="ignore", invalid="ignore"):
+            v_next *= T.type(1.0) / H[3]                                # :115
+        if iteration > 2:                                               # :118-121
+            H[0] = s_prev * H[1]
+            H[1] = c_prev * H[1]
+        if iteration > 1:                                               # :124-128
+            tmp = -np.conj(s_curr) * H[1] + c_curr * H[2]
+            H[1] = c_curr * H[1] + s_curr * H[2]
+            H[2] = tmp
+        c, s, H[2] = givens_algorithm(H[2], H[3])                       # :131
+        rhs[1] = -np.conj(s) * rhs[0]                                   # :134
+        rhs[0] = c * rhs[0]                                             # :135
+        w_next[...] = v_curr                                            # :138
+        if iteration > 1:
+            w_next -= H[1] * w_curr                                     # :139
+        if iteration > 2:
+            w_next -= H[0] * w_prev                                     # :140
+        with np.errstate(divide="ignore", invalid="ignore"):
+            w_next *= T.type(1.0) / H[2]                                # :141
+        x += rhs[0] * w_next                                            # :144
+        v_prev, v_curr, v_next = v_curr, v_next, v_prev                 # :147
+        w_prev, w_curr, w_next = w_curr, w_next, w_prev                 # :148
+        c_prev, s_prev, c_curr, s_curr = c_curr, s_curr, c, s           # :149
+        rhs[0] = rhs[1]                                                 # :150
+        H[1] = -H[3] if skew_hermitian else H[3]                        # :153
+        resnorm = float(abs(rhs[1]))                                    # :156
+        iteration += 1
+        if log:
+            history.iters += 1
+            history.mvps += 1
+            resnorms.append(resnorm)
+    if log:
+        history.isconverged = resnorm <= tol
+        history["resnorm"] = np.array(resnorms)
+        history["tol"] = tol
+        return x, history
+    return x
+
+
+def minres(A, b, **kw):
+    x = np.zeros(opsize(A, 1), dtype=b.dtype)
+    return minres_(x, A, b, initially_zero=True, **kw)
+
+
+# --------------------------------------------------------------------------------------------
+# BiCGStab(l) (reference src/bicgstabl.jl)
+# --------------------------------------------------------------------------------------------
+def bicgstabl_(x, A, b, l=2, *, abstol=0.0, reltol=None, max_mv_products=None, log=False, Pl=None,
+               initial_zero=False, r_shadow=None, rng=None):
+    """bicgstabl!(x, A, b, l; ...) -- reference src/bicgstabl.jl:181-219, bicgstabl_iterator!
+    :27-73, iterate :79-134.  The reference draws r_shadow = rand(T, n) (:38); parity runs inject
+    the same `r_shadow` into both implementations."""
+    import scipy.linalg as sla
+    T = x.dtype
+    n = opsize(A, 0)
+    if reltol is None:
+        reltol = math.sqrt(_eps(_real_dtype(b.dtype)))
+    if max_mv_products is None:
+        max_mv_products = opsize(A, 1)
+    Pl = Pl or Identity()
+    history = ConvergenceHistory()
+    history["abstol"], history["reltol"] = abstol, reltol
+    resnorms = []
+    mv_products = 0
+    if r_shadow is None:
+        rng = rng or np.random.default_rng(0)
+        r_shadow = rng.random(n).astype(T)                              # :38
+    rs = np.zeros((n, l + 1), dtype=T, order="F")                       # :39 (undef)
+    us = np.zeros((n, l + 1), dtype=T, order="F")                       # :40
+    residual = rs[:, 0]
+    if initial_zero:
+        residual[...] = b                                               # :47
+    else:
+        residual[...] = mul(A, x)                                       # :49
+        residual[...] = b - residual                                    # :50
+        mv_products += 1
+    Pl.ldiv(residual)                                                   # :55
+    gamma = np.zeros(l, dtype=T)
+    omega = sigma = T.type(1)                                           # :58
+    nrm = float(np.linalg.norm(residual))                               # :60
+    M = np.zeros((l + 1, l + 1), dtype=T, order="F")
+    tol = max(reltol * nrm, abstol)                                     # :66
+    if log:
+        history.mvps = mv_products
+    res = nrm
+    while True:
+        if mv_products >= max_mv_products or res <= tol:                # :77
+            break
+        sigma = -omega * sigma                                          # :85
+        for j in range(1, l + 1):                                       # :88
+            rho = np.vdot(r_shadow, rs[:, j - 1])                       # :89
+            beta = rho / sigma                                          # :90
+            us[:, :j] = rs[:, :j] - beta * us[:, :j]                    # :93
+            us[:, j] = mul(A, np.ascontiguousarray(us[:, j - 1]))       # :97
+            Pl.ldiv(us[:, j])                                           # :98
+            sigma = np.vdot(r_shadow, us[:, j])                         # :100
+            alpha = rho / sigma                                         # :101
+            rs[:, :j] -= alpha * us[:, 1: j + 1]                        # :103
+            rs[:, j] = mul(A, np.ascontiguousarray(rs[:, j - 1]))       # :107
+            Pl.ldiv(rs[:, j])                                           # :108
+            x += alpha * us[:, 0]                                       # :111
+        mv_products += 2 * l                                            # :115
+        M[...] = rs.conj().T @ rs                                       # :120
+        lu = sla.lu_factor(M[1:, 1:])                                   # :123 (raises on singular, like lu!)
+        gamma[...] = sla.lu_solve(lu, M[1:, 0])                         # :124
+        us[:, 0] -= us[:, 1:] @ gamma                                   # :126
+        x += rs[:, :l] @ gamma                                          # :127
+        rs[:, 0] -= rs[:, 1:] @ gamma                                   # :128
+        omega = gamma[l - 1]                                            # :130
+        res = float(np.linalg.norm(rs[:, 0]))                           # :131
+        if log:
+            history.iters += 1                                          # :206
+            history.mvps = mv_products                                  # :207
+            resnorms.append(res)
+    if log:
+        history.isconverged = res <= tol
+        history["resnorm"] = np.array(resnorms)
+        history["tol"] = tol
+        return x, history
+    return x
+
+
+def bicgstabl(A, b, l=2, **kw):
+    x = np.zeros(opsize(A, 1), dtype=b.dtype)
+    return bicgstabl_(x, A, b, l, initial_zero=True, **kw)
