@@ -1,0 +1,290 @@
+/*
+ * b200krylov.h -- C ABI of the B200-native Krylov inner-loop engine (libb200krylov.so).
+ *
+ * This is the drop-in boundary behind IterativeSolvers.jl's cg!/gmres!/minres!/bicgstabl!/lobpcg!
+ * entry points and its operator/preconditioner contract (mul!, ldiv!).  The reference has no FFI of
+ * its own (it is pure Julia, duck-typed: docs/src/getting_started.md:25-30,
+ * docs/src/preconditioning.md:5-15); every entry point below names the reference interface it
+ * replaces (paths relative to the reference checkout).  INTEGRATION.md shows the Julia `ccall`
+ * shim a maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", opaque handles, plain pointers and sizes; no C++ / torch types.
+ *   - every function returns 0 on success, <0 on error (b200_last_error() has the message);
+ *     nothing throws, nothing calls exit().  Non-convergence is NOT an error (reference
+ *     src/cg.jl:238): it is reported through b200_result.isconverged.
+ *   - all device work is ordered on the context's CUDA stream; one host thread per context.
+ *   - `dtype`: B200_F64 or B200_F32 (the configs of BASELINE.json need no complex types).
+ *   - device pointers are raw CUDA device addresses (cudaMalloc / torch tensor .data_ptr()).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     B200_ERR_CUDA.
+ */
+#ifndef B200KRYLOV_H
+#define B200KRYLOV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_API __attribute__((visibility("default")))
+
+enum { B200_F64 = 0, B200_F32 = 1 };
+
+enum {
+  B200_OK = 0,
+  B200_ERR_INVALID = -1, /* bad argument (reference: throw("...") strings, src/lobpcg.jl:833-834) */
+  B200_ERR_CUDA = -2,    /* CUDA runtime / launch failure, or no device                           */
+  B200_ERR_NCCL = -3,
+  B200_ERR_ALLOC = -4,
+  B200_ERR_BREAKDOWN = -5, /* LAPACK-style failure: PosDefException (src/lobpcg.jl:380),
+                              SingularException (src/bicgstabl.jl:123)                            */
+  B200_ERR_UNSUPPORTED = -6
+};
+
+/* orth_meth of gmres! (reference src/orthogonalize.jl:5-8) */
+enum { B200_ORTH_MGS = 0, B200_ORTH_CGS = 1, B200_ORTH_DGKS = 2 };
+
+/* Pl / Pr kinds.  Identity() = reference src/common.jl:28-32; JACOBI = the diagonal
+ * preconditioner idiom of reference test/cg.jl:14-18 (ldiv!(y,P,x) = y .= x ./ P.diagonal). */
+enum { B200_PREC_IDENTITY = 0, B200_PREC_JACOBI = 1 };
+
+typedef struct b200_ctx b200_ctx;   /* device + stream (+ NCCL communicator)                     */
+typedef struct b200_csr b200_csr;   /* the operator A: CSR int32 on device, row-partitioned       */
+typedef struct b200_halo_plan b200_halo_plan; /* host-side plan of the off-slab columns           */
+
+typedef struct {
+  int32_t kind;       /* B200_PREC_*                                                              */
+  int32_t reserved;
+  const void *diag;   /* JACOBI: device pointer to the (local) diagonal, dtype of the operator    */
+} b200_precond;
+
+/* What the reference returns in ConvergenceHistory (src/history.jl:54-66) + solver exit state. */
+typedef struct {
+  int64_t iters;        /* niters(history)                                                        */
+  int64_t mvps;         /* history.mvps  (quirks of SURVEY.md section 9 reproduced)               */
+  int32_t isconverged;  /* converged(iterable) at exit                                            */
+  int32_t status;       /* 0, or B200_ERR_BREAKDOWN if a NaN/breakdown was detected               */
+  double tol;           /* max(reltol*||r0||, abstol)                                             */
+  double residual;      /* iterable.residual at exit                                              */
+  int64_t n_resnorm;    /* number of :resnorm entries written to the caller's history buffer      */
+} b200_result;
+
+/* ---------------------------------------------------------------- library / context */
+B200_API int b200_version(void);
+B200_API const char *b200_last_error(void);
+B200_API int b200_device_count(int *count);
+
+/* One context per (process, GPU).  world==1: no communicator. */
+B200_API int b200_ctx_create(int device, b200_ctx **out);
+/* Multi-GPU: one process per GPU; `nccl_id` = the 128-byte ncclUniqueId made by rank 0 with
+ * b200_nccl_unique_id() and broadcast by the host program (torch.distributed / MPI / Julia
+ * Distributed).  Row slabs of A and of every vector live on their owning rank. */
+B200_API int b200_nccl_unique_id(void *out128);
+B200_API int b200_ctx_create_dist(int device, int rank, int world, const void *nccl_id128, b200_ctx **out);
+B200_API int b200_ctx_destroy(b200_ctx *ctx);
+B200_API int b200_ctx_set_stream(b200_ctx *ctx, void *cuda_stream); /* borrow the caller's stream */
+B200_API int b200_ctx_sync(b200_ctx *ctx);
+B200_API int b200_ctx_info(const b200_ctx *ctx, int *device, int *rank, int *world, int *sm_count);
+/* number of kernels this library has launched on the context since creation (bench evidence) */
+B200_API int64_t b200_ctx_launch_count(const b200_ctx *ctx);
+/* CUDA-event timing on the context's stream (ms between the two marks) */
+B200_API int b200_ctx_timer_start(b200_ctx *ctx);
+B200_API int b200_ctx_timer_stop(b200_ctx *ctx, float *ms);
+/* Per-kernel-class timing inside the solvers: when enabled, the engines bracket each hot kernel
+ * launch with CUDA events on the context's stream (slot 0: SpMV-class kernel, 1: vector update with
+ * reduction, 2: vector update without reduction, 3: other).  read() synchronises and returns the
+ * accumulated milliseconds and launch counts per slot since the last reset. */
+B200_API int b200_ctx_profile_enable(b200_ctx *ctx, int on);
+B200_API int b200_ctx_profile_read(b200_ctx *ctx, int slot, double *total_ms, int64_t *launches, int reset);
+/* sum over ranks (no-op for world==1); used by hosts for max/sum of small host scalars */
+B200_API int b200_ctx_allreduce_f64(b200_ctx *ctx, double *host_inout, int count, int op_max);
+B200_API int b200_ctx_barrier(b200_ctx *ctx);
+
+/* ---------------------------------------------------------------- device memory (similar / copyto!) */
+B200_API int b200_malloc(b200_ctx *ctx, size_t bytes, void **dptr);
+B200_API int b200_free(b200_ctx *ctx, void *dptr);
+B200_API int b200_upload(b200_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+B200_API int b200_download(b200_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+B200_API int b200_host_alloc_pinned(size_t bytes, void **hptr);
+B200_API int b200_host_free_pinned(void *hptr);
+
+/* ---------------------------------------------------------------- the operator A
+ * replaces: A::SparseMatrixCSC as used by mul!(y, A, x) at reference src/cg.jl:54,137,
+ * src/gmres.jl:245,287, src/minres.jl:61,104, src/bicgstabl.jl:49,97,107, src/lobpcg.jl:125,129.
+ */
+/* From the three arrays of a host SparseMatrixCSC{Tv,Ti} (A.colptr, A.rowval, A.nzval;
+ * idx_bytes = 8 for Int64 / 4 for Int32; base = 1 for Julia).  Single-GPU contexts only.
+ * Uploads, transposes to CSR on the device, sorts columns inside each row. */
+B200_API int b200_csr_from_csc(b200_ctx *ctx, int64_t m, int64_t n, const void *colptr, const void *rowval,
+                               const void *nzval, int idx_bytes, int dtype, int base, b200_csr **out);
+/* From a host CSR row slab: rows [row_begin, row_begin+m_local) of an n_global x n_global operator,
+ * column indices GLOBAL.  world==1: row_begin=0, m_local=n_global, plan=NULL.
+ * world>1: `plan` carries the halo exchange lists (see below). */
+B200_API int b200_csr_from_csr_slab(b200_ctx *ctx, int64_t n_global, int64_t row_begin, int64_t m_local,
+                                    const void *rowptr, const void *colind, const void *vals, int idx_bytes,
+                                    int dtype, int base, const b200_halo_plan *plan, b200_csr **out);
+/* laplace_matrix(T, N, dims) (reference test/laplace_matrix.jl:1-12) rows [row_begin,row_begin+m_local)
+ * built directly on the device (bench input for sizes whose host copy would not fit the timed path). */
+B200_API int b200_csr_laplacian(b200_ctx *ctx, int64_t N, int dims, int dtype, int64_t row_begin, int64_t m_local,
+                                const b200_halo_plan *plan, b200_csr **out);
+B200_API int b200_csr_destroy(b200_csr *A);
+/* size(A,1) local, size(A,2) global, nnz local, eltype */
+B200_API int b200_csr_info(const b200_csr *A, int64_t *m_local, int64_t *n_global, int64_t *nnz_local, int *dtype,
+                           int64_t *row_begin, int64_t *n_halo);
+/* diag(A) of the local rows into a device vector (JacobiPrec(diag(A)), reference test/cg.jl:57) */
+B200_API int b200_csr_diag(b200_ctx *ctx, const b200_csr *A, void *diag_dev);
+/* device CSR arrays back to the host (tests) */
+B200_API int b200_csr_download(b200_ctx *ctx, const b200_csr *A, int32_t *rowptr, int32_t *colind, void *vals);
+
+/* Host-side halo plan for row-partitioned operators (multi-GPU).  Pure host code: usable (and
+ * tested) without a GPU.  row_offsets has world+1 entries (rank r owns [row_offsets[r], row_offsets[r+1])). */
+B200_API int b200_halo_plan_create(int rank, int world, const int64_t *row_offsets, b200_halo_plan **out);
+/* scan the slab's GLOBAL column indices and collect the off-slab columns, sorted, grouped by owner */
+B200_API int b200_halo_plan_scan(b200_halo_plan *plan, int64_t m_local, const void *rowptr, const void *colind,
+                                 int idx_bytes, int base);
+/* analytic version for laplace_matrix(N, dims) slabs (no column array needed) */
+B200_API int b200_halo_plan_scan_laplacian(b200_halo_plan *plan, int64_t N, int dims);
+/* how many / which global columns this rank needs from `owner` (sorted ascending) */
+B200_API int64_t b200_halo_plan_recv_count(const b200_halo_plan *plan, int owner);
+B200_API int b200_halo_plan_recv_cols(const b200_halo_plan *plan, int owner, int64_t *cols_out);
+/* tell the plan which of MY rows `peer` needs (global indices, the peer's recv_cols for me) */
+B200_API int b200_halo_plan_set_send(b200_halo_plan *plan, int peer, const int64_t *cols, int64_t count);
+B200_API int64_t b200_halo_plan_send_count(const b200_halo_plan *plan, int peer);
+B200_API int64_t b200_halo_plan_n_halo(const b200_halo_plan *plan);
+/* global column -> local extended index ([0,m_local) own rows, [m_local, m_local+n_halo) halo) */
+B200_API int64_t b200_halo_plan_local_index(const b200_halo_plan *plan, int64_t global_col);
+B200_API int b200_halo_plan_destroy(b200_halo_plan *plan);
+
+/* Host generators of the reference's test/benchmark matrices (inputs for tests and bench.py):
+ * laplace_matrix(Float64, N, dims) as SparseMatrixCSC{Float64,Int64} arrays (test/laplace_matrix.jl:1-12),
+ * or as a CSR row slab with int32 columns.  Return nnz, or <0. */
+B200_API int64_t b200_gen_laplace_nnz(int64_t N, int dims, int64_t row_begin, int64_t m_local);
+B200_API int64_t b200_gen_laplace_csc_i64(int64_t N, int dims, int base, int64_t *colptr, int64_t *rowval,
+                                          double *nzval);
+B200_API int64_t b200_gen_laplace_csr_slab_i32(int64_t N, int dims, int64_t row_begin, int64_t m_local,
+                                               int32_t *rowptr, int32_t *colind_global, double *vals);
+
+/* ---------------------------------------------------------------- L0: operator / vector algebra
+ * (each Julia op of SURVEY.md section 8b is one call; x,y are LOCAL slabs on multi-GPU contexts,
+ * reductions return the GLOBAL value on every rank)
+ */
+/* mul!(y, A, x)  -- y must not alias x */
+B200_API int b200_spmv(b200_ctx *ctx, const b200_csr *A, const void *x_dev, void *y_dev);
+/* mul!(Y, A, X) on column-major m x bs blocks (reference src/lobpcg.jl:124-131) */
+B200_API int b200_spmm(b200_ctx *ctx, const b200_csr *A, const void *X_dev, int64_t ldx, void *Y_dev, int64_t ldy,
+                       int bs);
+/* dot(x, y), norm(x) (host result, synchronises) */
+B200_API int b200_dot(b200_ctx *ctx, int64_t n, const void *x_dev, const void *y_dev, int dtype, double *result);
+B200_API int b200_nrm2(b200_ctx *ctx, int64_t n, const void *x_dev, int dtype, double *result);
+/* y .= a .* x .+ b .* y  (axpy!: b=1; broadcast update of src/cg.jl:51: a=1,x=r,b=beta) */
+B200_API int b200_axpby(b200_ctx *ctx, int64_t n, double a, const void *x_dev, double b, void *y_dev, int dtype);
+B200_API int b200_scal(b200_ctx *ctx, int64_t n, double a, void *x_dev, int dtype);           /* rmul! */
+B200_API int b200_copy(b200_ctx *ctx, int64_t n, const void *x_dev, void *y_dev, int dtype);  /* copyto! */
+B200_API int b200_fill(b200_ctx *ctx, int64_t n, double a, void *x_dev, int dtype);           /* fill! */
+/* ldiv!(y, P::JacobiPrec, x): y .= x ./ diag  (y may alias x: ldiv!(P, x)) */
+B200_API int b200_jacobi_ldiv(b200_ctx *ctx, int64_t n, const void *diag_dev, const void *x_dev, void *y_dev,
+                              int dtype);
+
+/* ---------------------------------------------------------------- L1: dense helper kernels */
+/* orthogonalize_and_normalize!(V[:,1:k], w, h, method) -> nrm
+ * (reference src/orthogonalize.jl:13-39 DGKS, :41-51 CGS, :67-79 MGS).
+ * V: device, column-major, leading dimension ldv (local rows), k columns; w: device n_local;
+ * h_host: k values out (host).  Fused: the k dots in one launch, the k axpys + norm in one launch. */
+B200_API int b200_orthogonalize_and_normalize(b200_ctx *ctx, int64_t n_local, const void *V_dev, int64_t ldv, int k,
+                                              void *w_dev, double *h_host, int method, int dtype, double *nrm);
+/* ldiv!(FastHessenberg(H), rhs) (reference src/hessenberg.jl:15-46): H (m+1) x m column-major with
+ * leading dimension ldh, rhs m+1; both device-resident fp64; mutated in place (single-block kernel). */
+B200_API int b200_hessenberg_ldiv(b200_ctx *ctx, double *H_dev, int ldh, int m, double *rhs_dev);
+
+/* ---------------------------------------------------------------- L2/L3: solver entry points
+ * x is caller-owned and updated IN PLACE (reference src/cg.jl:241); b and A are never mutated.
+ * resnorm_host (may be NULL) receives history[:resnorm]; capacity in entries.
+ */
+typedef struct {
+  double abstol;            /* zero(real(eltype(b)))      src/cg.jl:210                            */
+  double reltol;            /* sqrt(eps(real(eltype(b)))) src/cg.jl:211 -- pass <0 for that default */
+  int64_t maxiter;          /* size(A,2)                  src/cg.jl:212 -- pass <0 for the default  */
+  int32_t initially_zero;   /* src/cg.jl:125                                                       */
+  int32_t check_every;      /* how many iterations are enqueued between host polls of the device-side
+                               `done` flag (<=0: default).  Results do not depend on it: kernels of
+                               iterations past `done` are no-ops.                                   */
+  b200_precond Pl;          /* Identity -> CGIterable (src/cg.jl:43-66); else PCGIterable (:72-100) */
+  int32_t fixed_iterations; /* bench only: ignore convergence, run exactly maxiter iterations      */
+  int32_t variant;          /* 0 = default engine; other values select experimental kernels        */
+} b200_cg_opts;
+
+/* cg!(x, A, b; ...)  reference src/cg.jl:209-242.  x,b device pointers (local slabs). */
+B200_API int b200_cg_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
+                           const b200_cg_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);
+/* same call with HOST x,b (the end-to-end path: H2D of b and x, solve, D2H of x) */
+B200_API int b200_cg_solve_host(b200_ctx *ctx, const b200_csr *A, void *x_host, const void *b_host,
+                                const b200_cg_opts *opts, b200_result *res, double *resnorm_host,
+                                int64_t resnorm_cap);
+
+typedef struct {
+  double abstol, reltol;    /* src/gmres.jl:187-188                                                */
+  int64_t maxiter;          /* size(A,2)           src/gmres.jl:190                                */
+  int32_t restart;          /* min(20, size(A,2))  src/gmres.jl:189  (<=0: default)                */
+  int32_t initially_zero;   /* src/gmres.jl:192                                                    */
+  int32_t orth_meth;        /* B200_ORTH_*; reference default ModifiedGramSchmidt src/gmres.jl:194 */
+  int32_t reserved;
+  b200_precond Pl, Pr;      /* src/gmres.jl:185-186                                                */
+} b200_gmres_opts;
+/* gmres!(x, A, b; ...)  reference src/gmres.jl:184-222 */
+B200_API int b200_gmres_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
+                              const b200_gmres_opts *opts, b200_result *res, double *resnorm_host,
+                              int64_t resnorm_cap);
+
+typedef struct {
+  double abstol, reltol;    /* src/minres.jl:204-205                                               */
+  int64_t maxiter;          /* src/minres.jl:206                                                   */
+  int32_t initially_zero;   /* src/minres.jl:207                                                   */
+  int32_t skew_hermitian;   /* src/minres.jl:201                                                   */
+} b200_minres_opts;
+/* minres!(x, A, b; ...)  reference src/minres.jl:200-237 */
+B200_API int b200_minres_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
+                               const b200_minres_opts *opts, b200_result *res, double *resnorm_host,
+                               int64_t resnorm_cap);
+
+typedef struct {
+  double abstol, reltol;    /* src/bicgstabl.jl:182-183                                            */
+  int64_t max_mv_products;  /* size(A,2)  src/bicgstabl.jl:184                                     */
+  int32_t l;                /* positional l = 2   src/bicgstabl.jl:181                             */
+  int32_t initial_zero;     /* sic (no "ly")      src/bicgstabl.jl:32                              */
+  b200_precond Pl;          /* src/bicgstabl.jl:187                                                */
+  const void *r_shadow;     /* device vector; the reference draws rand(T,n) (src/bicgstabl.jl:38):
+                               the host passes the draw so that runs are reproducible            */
+} b200_bicgstabl_opts;
+/* bicgstabl!(x, A, b, l; ...)  reference src/bicgstabl.jl:181-219 */
+B200_API int b200_bicgstabl_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
+                                  const b200_bicgstabl_opts *opts, b200_result *res, double *resnorm_host,
+                                  int64_t resnorm_cap);
+
+typedef struct {
+  double tol;               /* default_tolerance(T) = eps(real(T))^(3/10)  src/lobpcg.jl:751       */
+  int64_t maxiter;          /* 200   src/lobpcg.jl:865                                             */
+  int32_t largest;          /* src/lobpcg.jl:787                                                   */
+  int32_t blocksize;        /* size(X0, 2)                                                         */
+  b200_precond P;           /* src/lobpcg.jl:226-242 (RPreconditioner)                             */
+  int32_t fixed_iterations; /* bench only: never soft-lock, run exactly maxiter steps              */
+  int32_t reserved;
+} b200_lobpcg_opts;
+typedef struct {
+  int64_t iterations;       /* results.iterations  src/lobpcg.jl:890                               */
+  int32_t converged;        /* all(residual_norms .<= tol)                                         */
+  int32_t status;
+} b200_lobpcg_result;
+/* lobpcg(A, largest, X0; ...) -> LOBPCGResults  reference src/lobpcg.jl:787-839, 865-893.
+ * X_dev: n_local x blocksize column-major (ld = ldx), overwritten with the Ritz vectors;
+ * lambda_host, resnorm_host: blocksize values each. */
+B200_API int b200_lobpcg_solve(b200_ctx *ctx, const b200_csr *A, void *X_dev, int64_t ldx,
+                               const b200_lobpcg_opts *opts, b200_lobpcg_result *res, double *lambda_host,
+                               double *resnorm_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200KRYLOV_H */

@@ -1,0 +1,19 @@
+"""iterativesolvers.jl_b200 -- host-side mirror of IterativeSolvers.jl's hot-path interface over the
+B200-native C ABI (libb200krylov.so).
+
+Julia is not available in this image, so this Python layer plays the role of the Julia shim
+(INTEGRATION.md): same function names (`cg!` -> `cg_`), keyword arguments, defaults, return shapes
+(`x` or `(x, ConvergenceHistory)`) and error behaviour as reference src/cg.jl, src/gmres.jl,
+src/minres.jl, src/bicgstabl.jl, src/lobpcg.jl.  All arithmetic runs in the CUDA library; this
+package contains no numerical fallback.
+
+The directory name contains a dot, so import it through the repo-root alias module:
+    import iterativesolvers_jl_b200 as isb
+"""
+from ._lib import B200Error, lib  # noqa: F401
+from .device import Context, DeviceArray, default_context  # noqa: F401
+from .operators import B200CSR, HaloPlan, Identity, JacobiPrec  # noqa: F401
+from .history import ConvergenceHistory  # noqa: F401
+from .generators import laplace_matrix, laplace_csr_slab  # noqa: F401
+from .solvers import (cg, cg_, gmres, gmres_, minres, minres_, bicgstabl, bicgstabl_, lobpcg,  # noqa: F401
+                      LOBPCGResults, orthogonalize_and_normalize_, hessenberg_ldiv_)

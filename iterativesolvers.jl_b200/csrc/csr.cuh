@@ -1,0 +1,35 @@
+// csr.cuh -- the device operator (CSR int32, row slab) and the host halo plan.
+#pragma once
+#include "common.cuh"
+
+struct b200_halo_plan {
+  int rank = 0, world = 1;
+  std::vector<int64_t> row_offsets;                // world+1
+  std::vector<std::vector<int64_t>> recv_cols;     // [owner] -> sorted global columns needed from owner
+  std::vector<std::vector<int64_t>> send_cols;     // [peer]  -> my global rows the peer needs
+  std::vector<int64_t> halo_sorted;                // concatenation of recv_cols (globally ascending)
+  std::vector<int64_t> recv_offset;                // world+1 prefix over owners into halo_sorted
+  void rebuild_concat();
+};
+
+struct b200_csr {
+  b200_ctx *ctx = nullptr;
+  int dtype = B200_F64;
+  int64_t m_local = 0, n_global = 0, row_begin = 0, nnz = 0, n_halo = 0;
+  int *rowptr = nullptr;   // m_local+1
+  int *colind = nullptr;   // nnz; local extended index: [0,m_local) own, [m_local,m_local+n_halo) halo
+  void *vals = nullptr;    // nnz
+  int max_row_nnz = 0;
+  double avg_row_nnz = 0.0;
+  // halo exchange state (world > 1)
+  std::vector<int64_t> send_count, send_offset, recv_count, recv_offset;  // per peer
+  int64_t n_send = 0;
+  int *send_idx = nullptr;   // device: local row index to pack, grouped by peer
+  void *send_buf = nullptr;  // device: n_send values
+  void *halo = nullptr;      // device: n_halo values (recv buffer == halo part of the extended vector)
+};
+
+namespace b200 {
+// packs x[send_idx] and exchanges with the peers; after return (stream-ordered) A->halo is valid
+int halo_exchange(b200_ctx *ctx, const b200_csr *A, const void *x_dev);
+}  // namespace b200

@@ -1,0 +1,101 @@
+// gen.cu -- host generators of the reference's test matrices (inputs for tests and bench.py).
+// laplace_matrix(T, N, dims) of reference test/laplace_matrix.jl:1-12: D = tridiag(-1,2,-1),
+// A_d = kron(A_{d-1}, I_N) + kron(I, D)  ==  sum over the dims coordinates of a 1-D second
+// difference: diagonal 2*dims, -1 for every +-1 neighbour along one coordinate.  Row/column index
+// = sum_d coord_d * N^d.  Entries inside a column (row) are emitted in ascending index order, which
+// is the order Julia's sparse kron/+ produce.
+#include <omp.h>
+
+#include "common.cuh"
+
+using namespace b200;
+
+namespace {
+struct Geom {
+  int64_t N, n, stride[8];
+  int dims;
+};
+bool make_geom(int64_t N, int dims, Geom *g) {
+  if (N < 1 || dims < 1 || dims > 6) return false;
+  g->N = N;
+  g->dims = dims;
+  g->n = 1;
+  for (int d = 0; d < dims; ++d) {
+    g->stride[d] = g->n;
+    g->n *= N;
+  }
+  return true;
+}
+inline int row_count(const Geom &g, int64_t q) {
+  int c = 1;
+  int64_t rem = q;
+  for (int d = 0; d < g.dims; ++d) {
+    const int64_t x = rem % g.N;
+    rem /= g.N;
+    c += (x > 0) + (x < g.N - 1);
+  }
+  return c;
+}
+template <typename I, typename F>
+inline void emit_row(const Geom &g, int64_t q, int64_t base, I *idx, F *val) {
+  int64_t coord[8], rem = q;
+  for (int d = 0; d < g.dims; ++d) {
+    coord[d] = rem % g.N;
+    rem /= g.N;
+  }
+  int k = 0;
+  for (int d = g.dims - 1; d >= 0; --d)
+    if (coord[d] > 0) { idx[k] = (I)(q - g.stride[d] + base); val[k] = (F)-1; ++k; }
+  idx[k] = (I)(q + base); val[k] = (F)(2 * g.dims); ++k;
+  for (int d = 0; d < g.dims; ++d)
+    if (coord[d] < g.N - 1) { idx[k] = (I)(q + g.stride[d] + base); val[k] = (F)-1; ++k; }
+}
+}  // namespace
+
+extern "C" {
+
+int64_t b200_gen_laplace_nnz(int64_t N, int dims, int64_t row_begin, int64_t m_local) {
+  Geom g;
+  if (!make_geom(N, dims, &g) || row_begin < 0 || m_local < 0 || row_begin + m_local > g.n) {
+    set_error("b200_gen_laplace_nnz: bad arguments");
+    return B200_ERR_INVALID;
+  }
+  int64_t total = 0;
+#pragma omp parallel for reduction(+ : total) schedule(static)
+  for (int64_t i = 0; i < m_local; ++i) total += row_count(g, row_begin + i);
+  return total;
+}
+
+int64_t b200_gen_laplace_csc_i64(int64_t N, int dims, int base, int64_t *colptr, int64_t *rowval, double *nzval) {
+  Geom g;
+  if (!make_geom(N, dims, &g) || !colptr || !rowval || !nzval) {
+    set_error("b200_gen_laplace_csc_i64: bad arguments");
+    return B200_ERR_INVALID;
+  }
+  colptr[0] = base;
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < g.n; ++q) colptr[q + 1] = row_count(g, q);
+  for (int64_t q = 0; q < g.n; ++q) colptr[q + 1] += colptr[q];
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < g.n; ++q) emit_row<int64_t, double>(g, q, base, rowval + (colptr[q] - base), nzval + (colptr[q] - base));
+  return colptr[g.n] - base;
+}
+
+int64_t b200_gen_laplace_csr_slab_i32(int64_t N, int dims, int64_t row_begin, int64_t m_local, int32_t *rowptr,
+                                      int32_t *colind_global, double *vals) {
+  Geom g;
+  if (!make_geom(N, dims, &g) || !rowptr || !colind_global || !vals || row_begin < 0 || m_local < 0 ||
+      row_begin + m_local > g.n || g.n >= INT32_MAX) {
+    set_error("b200_gen_laplace_csr_slab_i32: bad arguments");
+    return B200_ERR_INVALID;
+  }
+  rowptr[0] = 0;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < m_local; ++i) rowptr[i + 1] = row_count(g, row_begin + i);
+  for (int64_t i = 0; i < m_local; ++i) rowptr[i + 1] += rowptr[i];
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < m_local; ++i) emit_row<int32_t, double>(g, row_begin + i, 0, colind_global + rowptr[i], vals + rowptr[i]);
+  return rowptr[m_local];
+}
+
+}  // extern "C"

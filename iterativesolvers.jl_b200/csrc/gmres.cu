@@ -1,0 +1,467 @@
+// gmres.cu -- orthogonalize_and_normalize! (reference src/orthogonalize.jl), FastHessenberg ldiv!
+// (src/hessenberg.jl) and the restarted GMRES engine (src/gmres.jl:57-304).
+//
+// Data layout: the Arnoldi basis V is n_local x (restart+1), column-major, device-resident (the
+// reference hard-codes a host Matrix, src/gmres.jl:5-15; "drop-in" therefore means the whole iterate
+// runs here).  H ((restart+1) x restart) and the null-vector residual recurrence are O(restart^2)
+// scalars: they live on the host, as in the reference, except for the Givens least-squares solve
+// which runs in a single-warp kernel so that y never leaves the device.
+//
+// Fused classical Gram-Schmidt (CGS / DGKS), 2 launches + 1 scale instead of 2k+3 BLAS calls:
+//   k_block_dots : h = V' w        -- all k dots in ONE pass over V and w   ((k+1) n-passes)
+//   k_block_axpy : w -= V h ; ||w||^2 fused                                  ((k+2) n-passes)
+//   k_scale_dev  : w *= inv(nrm)                                             (2 n-passes)
+// Algorithmic bytes per CGS step k: (2k+5) * n * V.
+#include "blas1.cuh"
+#include "spmv.cuh"
+
+using namespace b200;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int JB = 8;  // columns of V per register block
+
+// h[j0+j] = sum_i V[i, j0+j] * w[i]  for all j < k.  Partials: partials[block * kMaxReduceWidth + j].
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_block_dots(const T *__restrict__ V, int64_t ld, int k,
+                                                         const T *__restrict__ w, int64_t n, double *partials,
+                                                         unsigned int *ticket, double *__restrict__ out) {
+  __shared__ double smem[kThreads / 32][JB];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j0 = 0; j0 < k; j0 += JB) {
+    const int jn = min(JB, k - j0);
+    double acc[JB];
+#pragma unroll
+    for (int j = 0; j < JB; ++j) acc[j] = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+      const double wi = (double)w[i];
+#pragma unroll
+      for (int j = 0; j < JB; ++j)
+        if (j < jn) acc[j] += (double)V[i + (int64_t)(j0 + j) * ld] * wi;
+    }
+#pragma unroll
+    for (int j = 0; j < JB; ++j) acc[j] = warp_sum(acc[j]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < JB; ++j) smem[warp][j] = acc[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < jn) {
+      double s = 0.0;
+      for (int wv = 0; wv < kThreads / 32; ++wv) s += smem[wv][threadIdx.x];
+      partials[(size_t)blockIdx.x * kMaxReduceWidth + j0 + threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int j = threadIdx.x; j < k; j += kThreads) {
+    double s = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * kMaxReduceWidth + j]);
+    out[j] = s;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// out[i] = base[i] + sign * sum_j V[i,j] * y[j] ; optionally sum of out[i]^2 -> nrm2_out[0]
+template <typename T, bool WITH_NORM>
+__global__ void __launch_bounds__(kThreads) k_block_axpy(const T *__restrict__ V, int64_t ld, int k,
+                                                         const double *__restrict__ y, double sign,
+                                                         const T *base, T *out, int64_t n, double *partials,
+                                                         unsigned int *ticket, double *nrm2_out) {
+  __shared__ double sy[kMaxReduceWidth];
+  __shared__ double smem[kThreads / 32];
+  for (int j = threadIdx.x; j < k; j += kThreads) sy[j] = sign * y[j];
+  __syncthreads();
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    T t = base[i];
+    for (int j = 0; j < k; ++j) t += (T)sy[j] * V[i + (int64_t)j * ld];
+    out[i] = t;
+    if (WITH_NORM) acc += (double)t * (double)t;
+  }
+  if (WITH_NORM) {
+    acc = block_sum<kThreads>(acc, smem);
+    double total;
+    if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x == 0) nrm2_out[0] = total;
+  }
+}
+
+// w .*= inv(nrm), nrm = sqrt(*nrm2) read from the device (no host round trip)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_scale_dev(T *__restrict__ w, int64_t n,
+                                                        const double *__restrict__ nrm2) {
+  const T inv = (T)1 / (T)sqrt(nrm2[0]);
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+    w[i] = w[i] * inv;
+}
+
+__global__ void k_add_small(double *h, const double *c, int k) {
+  for (int j = threadIdx.x; j < k; j += blockDim.x) h[j] += c[j];
+}
+
+// LinearAlgebra.givensAlgorithm(f, g) for reals (LAPACK dlartg convention as in Julia's stdlib)
+__device__ __forceinline__ void givens(double f, double g, double &c, double &s, double &r) {
+  if (g == 0.0) { c = 1.0; s = 0.0; r = f; return; }
+  if (f == 0.0) { c = 0.0; s = 1.0; r = g; return; }
+  r = hypot(f, g);
+  c = f / r;
+  s = g / r;
+  if (fabs(f) > fabs(g) && c < 0.0) { c = -c; s = -s; r = -r; }
+}
+
+// ldiv!(FastHessenberg(H), rhs): one warp; lanes run over the columns j of each rotation.
+__global__ void k_hessenberg_ldiv(double *__restrict__ H, int ldh, int m, double *__restrict__ rhs) {
+  const int lane = threadIdx.x;
+  for (int i = 0; i < m; ++i) {                                   // src/hessenberg.jl:24
+    double c, s, r;
+    givens(H[i + i * ldh], H[i + 1 + i * ldh], c, s, r);          // :25
+    __syncwarp();
+    for (int j = i + 1 + lane; j < m; j += 32) {                  // :31-35
+      const double a = H[i + j * ldh], b = H[i + 1 + j * ldh];
+      H[i + j * ldh] = c * a + s * b;
+      H[i + 1 + j * ldh] = -s * a + c * b;
+    }
+    if (lane == 0) {
+      H[i + i * ldh] = c * H[i + i * ldh] + s * H[i + 1 + i * ldh];  // :28
+      const double a = rhs[i], b = rhs[i + 1];                    // :38-40
+      rhs[i] = c * a + s * b;
+      rhs[i + 1] = -s * a + c * b;
+    }
+    __syncwarp();
+  }
+  // UpperTriangular solve (:44-45), column-oriented back substitution
+  for (int j = m - 1; j >= 0; --j) {
+    if (lane == 0) rhs[j] = rhs[j] / H[j + j * ldh];
+    __syncwarp();
+    const double xj = rhs[j];
+    for (int i = lane; i < j; i += 32) rhs[i] -= H[i + j * ldh] * xj;
+    __syncwarp();
+  }
+}
+
+int gridv(const b200_ctx *ctx, int64_t n) { return stream_grid(ctx, n, kThreads * 2, 8); }
+
+template <typename T>
+int block_dots(b200_ctx *ctx, const T *V, int64_t ld, int k, const T *w, int64_t n, double *out_dev) {
+  // chunks of at most kMaxReduceWidth columns
+  for (int j0 = 0; j0 < k; j0 += kMaxReduceWidth) {
+    const int kk = std::min(kMaxReduceWidth, k - j0);
+    ProfScope prof(ctx, 1);
+    k_block_dots<T><<<gridv(ctx, n), kThreads, 0, ctx->stream>>>(V + (int64_t)j0 * ld, ld, kk, w, n, ctx->red.partials,
+                                                                ctx->red.ticket, out_dev + j0);
+    ctx->launches++;
+  }
+  B200_CUDA(cudaPeekAtLastError());
+  return allreduce_sum_dev(ctx, out_dev, k);
+}
+
+template <typename T>
+int block_axpy(b200_ctx *ctx, const T *V, int64_t ld, int k, const double *y_dev, double sign, const T *base, T *out,
+               int64_t n, double *nrm2_dev) {
+  for (int j0 = 0; j0 < k || j0 == 0; j0 += kMaxReduceWidth) {
+    const int kk = std::min(kMaxReduceWidth, k - j0);
+    const bool last = j0 + kMaxReduceWidth >= k;
+    const T *src = j0 == 0 ? base : out;
+    ProfScope prof(ctx, 1);
+    if (last && nrm2_dev)
+      k_block_axpy<T, true><<<gridv(ctx, n), kThreads, 0, ctx->stream>>>(V + (int64_t)j0 * ld, ld, kk, y_dev + j0, sign, src, out, n, ctx->red.partials, ctx->red.ticket, nrm2_dev);
+    else
+      k_block_axpy<T, false><<<gridv(ctx, n), kThreads, 0, ctx->stream>>>(V + (int64_t)j0 * ld, ld, kk, y_dev + j0, sign, src, out, n, nullptr, nullptr, nullptr);
+    ctx->launches++;
+    if (last) break;
+  }
+  B200_CUDA(cudaPeekAtLastError());
+  if (nrm2_dev) B200_TRY(allreduce_sum_dev(ctx, nrm2_dev, 1));
+  return B200_OK;
+}
+
+template <typename T>
+int scale_dev(b200_ctx *ctx, T *w, int64_t n, const double *nrm2_dev) {
+  ProfScope prof(ctx, 2);
+  k_scale_dev<T><<<gridv(ctx, n), kThreads, 0, ctx->stream>>>(w, n, nrm2_dev);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
+// orthogonalize_and_normalize!(V[:,1:k], w, h, method): h_host (k doubles) out, returns nrm.
+// Scratch: ctx->d_scalars[0..63] = h, [64..127] = correction, [200] = ||w||^2
+template <typename T>
+int orth_impl(b200_ctx *ctx, int64_t n, const T *V, int64_t ld, int k, T *w, double *h_host, int method,
+              double *nrm_out) {
+  double *d_h = ctx->d_scalars, *d_c = ctx->d_scalars + 64, *d_n = ctx->d_scalars + 200;
+  B200_REQUIRE(k >= 0 && k <= 64, "orthogonalize_and_normalize!: k=%d exceeds 64 basis vectors", k);
+  double nrm2 = 0.0;
+  if (method == B200_ORTH_MGS) {
+    // reference src/orthogonalize.jl:67-79: k sequential (dot ; axpy) pairs
+    for (int i = 0; i < k; ++i) {
+      B200_TRY(block_dots<T>(ctx, V + (int64_t)i * ld, ld, 1, w, n, d_h + i));                       // :71
+      B200_TRY(block_axpy<T>(ctx, V + (int64_t)i * ld, ld, 1, d_h + i, -1.0, w, w, n, i == k - 1 ? d_n : nullptr));  // :72
+    }
+    if (k == 0) {
+      B200_TRY(dot_dev(ctx, n, w, w, dtype_of<T>::value, d_n));
+      B200_TRY(allreduce_sum_dev(ctx, d_n, 1));
+    }
+    B200_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_h, sizeof(double) * std::max(k, 1), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(ctx->h_scalars + 64, d_n, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int j = 0; j < k; ++j) h_host[j] = ctx->h_scalars[j];
+    nrm2 = ctx->h_scalars[64];
+  } else {
+    if (k > 0) {
+      B200_TRY(block_dots<T>(ctx, V, ld, k, w, n, d_h));                       // mul!(h, V', w)         :15/:43
+      B200_TRY(block_axpy<T>(ctx, V, ld, k, d_h, -1.0, w, w, n, d_n));         // mul!(w, V, h, -1, 1)   :16/:44 + norm :17/:45
+    } else {
+      B200_TRY(dot_dev(ctx, n, w, w, dtype_of<T>::value, d_n));
+      B200_TRY(allreduce_sum_dev(ctx, d_n, 1));
+    }
+    B200_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_h, sizeof(double) * std::max(k, 1), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(ctx->h_scalars + 64, d_n, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int j = 0; j < k; ++j) h_host[j] = ctx->h_scalars[j];
+    nrm2 = ctx->h_scalars[64];
+    if (method == B200_ORTH_DGKS && k > 0) {
+      const double eta = 1.0 / sqrt(2.0);                                      // :20
+      double proj = 0.0;
+      for (int j = 0; j < k; ++j) proj += h_host[j] * h_host[j];
+      proj = sqrt(proj);                                                       // :22
+      int guard = 0;
+      while (sqrt(nrm2) < eta * proj && guard++ < 8) {                          // :26
+        B200_TRY(block_dots<T>(ctx, V, ld, k, w, n, d_c));                     // correction = V' w     :27
+        B200_TRY(block_axpy<T>(ctx, V, ld, k, d_c, -1.0, w, w, n, d_n));       // w -= V correction     :30, norm :32
+        k_add_small<<<1, 64, 0, ctx->stream>>>(d_h, d_c, k);                   // h .+= correction      :31
+        ctx->launches++;
+        B200_CUDA(cudaMemcpyAsync(ctx->h_scalars, d_c, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(cudaMemcpyAsync(ctx->h_scalars + 64, d_n, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        proj = 0.0;
+        for (int j = 0; j < k; ++j) {
+          proj += ctx->h_scalars[j] * ctx->h_scalars[j];
+          h_host[j] += ctx->h_scalars[j];
+        }
+        proj = sqrt(proj);                                                     // :28
+        nrm2 = ctx->h_scalars[64];
+      }
+    }
+  }
+  B200_TRY(scale_dev<T>(ctx, w, n, d_n));                                      // w .*= inv(nrm)  :36/:48/:76
+  *nrm_out = sqrt(nrm2);
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GMRES engine
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct Gmres {
+  b200_ctx *ctx;
+  const b200_csr *A;
+  int64_t n;
+  int restart;
+  T *V;       // n x (restart+1)
+  T *Ax;      // work vector
+  T *x;
+  const T *b;
+  const T *pl, *pr;  // Jacobi diagonals or NULL
+  std::vector<double> H, nullvec;  // host, column-major (restart+1) x restart
+  double *d_H, *d_rhs;             // device copies for the LS solve
+  int ldh;
+
+  T *col(int j) { return V + (int64_t)j * n; }
+
+  // init! (src/gmres.jl:235-255): V[:,1] = Pl \ (b - A x); returns beta and normalises
+  int init(bool initially_zero, double *beta) {
+    const int dt = dtype_of<T>::value;
+    T *v0 = col(0);
+    B200_TRY(copy(ctx, n, b, v0, dt));                                   // :241
+    if (!initially_zero) {
+      B200_TRY(spmv(ctx, A, x, Ax));                                     // :245
+      B200_TRY(axpby(ctx, n, -1.0, Ax, 1.0, v0, dt));                    // :246
+    }
+    if (pl) B200_TRY(jacobi_ldiv(ctx, n, pl, v0, v0, dt));               // :249
+    double *d_n = ctx->d_scalars + 200;
+    B200_TRY(dot_dev(ctx, n, v0, v0, dt, d_n));                          // :252
+    B200_TRY(allreduce_sum_dev(ctx, d_n, 1));
+    B200_TRY(scale_dev<T>(ctx, v0, n, d_n));                             // :253
+    double nn;
+    B200_TRY(read_scalars(ctx, d_n, 1, &nn));
+    *beta = sqrt(nn);
+    return B200_OK;
+  }
+
+  // expand! (src/gmres.jl:285-304)
+  int expand(int k) {  // k is 1-based as in the reference: V[:,k+1] = Pl \ (A (Pr \ V[:,k]))
+    const int dt = dtype_of<T>::value;
+    T *next = col(k), *cur = col(k - 1);
+    if (!pr) {
+      {
+        ProfScope prof(ctx, 0);
+        B200_TRY(spmv(ctx, A, cur, next));                               // :287/:293
+      }
+      if (pl) B200_TRY(jacobi_ldiv(ctx, n, pl, next, next, dt));         // :294
+    } else {
+      B200_TRY(jacobi_ldiv(ctx, n, pr, cur, next, dt));                  // :300
+      B200_TRY(spmv(ctx, A, next, Ax));                                  // :301
+      B200_TRY(copy(ctx, n, Ax, next, dt));                              // :302
+      if (pl) B200_TRY(jacobi_ldiv(ctx, n, pl, next, next, dt));         // :303
+    }
+    return B200_OK;
+  }
+
+  // solve_least_squares! + update_solution! (src/gmres.jl:262-283), k as in the reference (k-1 columns)
+  int solve_and_update(int k, double beta) {
+    const int m = k - 1;
+    if (m <= 0) return B200_OK;
+    std::vector<double> rhs(k, 0.0);
+    rhs[0] = beta;                                                        // :265
+    B200_CUDA(cudaMemcpyAsync(d_H, H.data(), sizeof(double) * ldh * restart, cudaMemcpyHostToDevice, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(d_rhs, rhs.data(), sizeof(double) * k, cudaMemcpyHostToDevice, ctx->stream));
+    k_hessenberg_ldiv<<<1, 32, 0, ctx->stream>>>(d_H, ldh, m, d_rhs);     // :267-268
+    B200_LAUNCH_CHECK(ctx);
+    // the reference's ldiv! mutates arnoldi.H in place; mirror that on the host copy
+    B200_CUDA(cudaMemcpyAsync(H.data(), d_H, sizeof(double) * ldh * restart, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!pr) {
+      B200_TRY(block_axpy<T>(ctx, V, n, m, d_rhs, 1.0, x, x, n, nullptr));    // x += V[:,1:k-1] y   :275
+    } else {
+      B200_TRY(fill(ctx, n, 0.0, Ax, dtype_of<T>::value));
+      B200_TRY(block_axpy<T>(ctx, V, n, m, d_rhs, 1.0, Ax, Ax, n, nullptr));  // :280
+      B200_TRY(jacobi_ldiv(ctx, n, pr, Ax, Ax, dtype_of<T>::value));          // :281
+      B200_TRY(axpby(ctx, n, 1.0, Ax, 1.0, x, dtype_of<T>::value));           // :282
+    }
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+  }
+};
+
+template <typename T>
+int gmres_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200_gmres_opts *o, b200_result *res,
+               double *resnorm_host, int64_t resnorm_cap) {
+  const int64_t n = A->m_local;
+  const double eps = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
+  const double reltol = o->reltol < 0 ? sqrt(eps) : o->reltol;
+  const int64_t maxiter = o->maxiter < 0 ? A->n_global : o->maxiter;
+  const int restart = o->restart > 0 ? o->restart : (int)std::min<int64_t>(20, A->n_global);
+  B200_REQUIRE(restart <= 64, "restart=%d: this version supports restart <= 64", restart);
+  const int method = o->orth_meth;
+
+  Gmres<T> g;
+  g.ctx = ctx;
+  g.A = A;
+  g.n = n;
+  g.restart = restart;
+  g.x = x;
+  g.b = b;
+  g.pl = o->Pl.kind == B200_PREC_JACOBI ? (const T *)o->Pl.diag : nullptr;
+  g.pr = o->Pr.kind == B200_PREC_JACOBI ? (const T *)o->Pr.diag : nullptr;
+  g.ldh = restart + 1;
+  g.H.assign((size_t)g.ldh * restart, 0.0);                               // zeros(T, order+1, order) :14
+  g.nullvec.assign(restart + 1, 1.0);                                     // ones(T, order+1)         :27
+  const size_t vec_bytes = align_up(sizeof(T) * (size_t)std::max<int64_t>(n, 1), 256);
+  void *ws = nullptr;
+  B200_TRY(ws_get(ctx, vec_bytes * (restart + 2) + 65536, &ws));
+  g.V = (T *)ws;
+  // columns must be contiguous with leading dimension n (not the padded size)
+  g.Ax = (T *)((char *)ws + align_up(sizeof(T) * (size_t)n * (restart + 1), 256));
+  g.d_H = (double *)((char *)g.Ax + vec_bytes);
+  g.d_rhs = g.d_H + (size_t)g.ldh * restart;
+  B200_REQUIRE((char *)(g.d_rhs + g.ldh) <= (char *)ws + ctx->ws_bytes, "internal: GMRES workspace too small");
+  B200_CUDA(cudaMemsetAsync(g.V, 0, sizeof(T) * (size_t)n * (restart + 1), ctx->stream));  // zeros(T, n, order+1) :13
+
+  // gmres_iterable! (src/gmres.jl:108-136)
+  int64_t mv_products = o->initially_zero ? 1 : 0;                        // :122 (sic)
+  double current, accumulator = 1.0, beta_res;
+  B200_TRY(g.init(o->initially_zero != 0, &current));                     // :126
+  beta_res = current;                                                     // init_residual! :257-260
+  const double tol = std::max(reltol * current, o->abstol);               // :129
+  double beta = current;                                                  // g.beta  :133
+  int k = 1;
+  int64_t iteration = 0, n_hist = 0;
+  bool breakdown = false;
+  auto done = [&](int64_t it) { return it >= maxiter || current <= tol; };  // :55
+  std::vector<double> h(restart + 1);
+
+  while (!done(iteration)) {                                              // :59
+    B200_TRY(g.expand(k));                                                // :63
+    mv_products += 1;                                                     // :65
+    double nrm = 0.0;
+    B200_TRY(orth_impl<T>(ctx, n, g.V, n, k, g.col(k), h.data(), method, &nrm));  // :68-73
+    for (int j = 0; j < k; ++j) g.H[j + (size_t)(k - 1) * g.ldh] = h[j];
+    g.H[k + (size_t)(k - 1) * g.ldh] = nrm;
+    // update_residual! (:224-233)
+    if (nrm == 0.0) {
+      current = 0.0;
+    } else {
+      double d = 0.0;
+      for (int j = 0; j < k; ++j) d += g.nullvec[j] * g.H[j + (size_t)(k - 1) * g.ldh];
+      g.nullvec[k] = -(d / nrm);
+      accumulator += g.nullvec[k] * g.nullvec[k];
+      current = beta_res / sqrt(accumulator);
+    }
+    if (!(current == current)) breakdown = true;
+    k += 1;                                                               // :78
+    if (k == restart + 1 || done(iteration + 1)) {                        // :82
+      B200_TRY(g.solve_and_update(k, beta));                              // :85-88
+      k = 1;                                                              // :90
+      if (!done(iteration)) {                                             // :93 (sic)
+        B200_TRY(g.init(false, &beta));                                   // :96
+        accumulator = 1.0;                                                // :99 (current is NOT reset)
+        beta_res = beta;
+        mv_products += 1;                                                 // :101
+      }
+    }
+    iteration += 1;
+    if (resnorm_host && n_hist < resnorm_cap) resnorm_host[n_hist++] = current;  // push!(:resnorm) :211
+    if (breakdown) break;
+  }
+  if (res) {
+    res->iters = iteration;
+    res->mvps = mv_products;                                              // history.mvps = iterable.mv_products :210
+    res->isconverged = current <= tol;                                    // :218
+    res->status = breakdown ? B200_ERR_BREAKDOWN : 0;
+    res->tol = tol;
+    res->residual = current;
+    res->n_resnorm = n_hist;
+  }
+  return B200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_orthogonalize_and_normalize(b200_ctx *ctx, int64_t n_local, const void *V_dev, int64_t ldv, int k, void *w_dev,
+                                     double *h_host, int method, int dtype, double *nrm) {
+  B200_REQUIRE(ctx && w_dev && nrm && (k == 0 || (V_dev && h_host)), "NULL argument");
+  B200_REQUIRE(ldv >= n_local && n_local >= 0, "bad leading dimension");
+  B200_REQUIRE(method == B200_ORTH_MGS || method == B200_ORTH_CGS || method == B200_ORTH_DGKS, "bad orth_meth");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return dtype == B200_F64 ? orth_impl<double>(ctx, n_local, (const double *)V_dev, ldv, k, (double *)w_dev, h_host, method, nrm)
+                           : orth_impl<float>(ctx, n_local, (const float *)V_dev, ldv, k, (float *)w_dev, h_host, method, nrm);
+}
+
+int b200_hessenberg_ldiv(b200_ctx *ctx, double *H_dev, int ldh, int m, double *rhs_dev) {
+  B200_REQUIRE(ctx && H_dev && rhs_dev && m >= 0 && ldh >= m + 1, "bad arguments");
+  if (m == 0) return B200_OK;
+  k_hessenberg_ldiv<<<1, 32, 0, ctx->stream>>>(H_dev, ldh, m, rhs_dev);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
+int b200_gmres_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev, const b200_gmres_opts *opts,
+                     b200_result *res, double *resnorm_host, int64_t resnorm_cap) {
+  B200_REQUIRE(ctx && A && x_dev && b_dev && opts, "NULL argument");
+  B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return A->dtype == B200_F64
+             ? gmres_impl<double>(ctx, A, (double *)x_dev, (const double *)b_dev, opts, res, resnorm_host, resnorm_cap)
+             : gmres_impl<float>(ctx, A, (float *)x_dev, (const float *)b_dev, opts, res, resnorm_host, resnorm_cap);
+}
+
+}  // extern "C"

@@ -1,0 +1,295 @@
+"""Solver entry points with the reference's names, keywords, defaults and return shapes.
+
+    cg!(x, A, b; kw...)  ->  cg_(x, A, b, **kw)        (Python has no `!`)
+    cg(A, b; kw...)      ->  cg(A, b, **kw)
+
+`A` is a B200CSR; `x`, `b` are either host numpy arrays (copied to the GPU and back inside the call:
+the end-to-end path) or device arrays (DeviceArray / contiguous torch CUDA tensors, zero-copy).
+`x` is updated in place and returned as the same object (reference src/cg.jl:241).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import B200Error, check, lib
+from .device import DeviceArray, as_device_ptr, is_device
+from .history import ConvergenceHistory
+from .operators import B200CSR, Identity, precond_to_c
+
+
+def _eps(dtype):
+    return float(np.finfo(np.dtype(dtype)).eps)
+
+
+def _check_operator(A):
+    if not isinstance(A, B200CSR):
+        raise TypeError("the device path needs a B200CSR operator (B200CSR.from_scipy / from_csc_arrays)")
+
+
+class _Staged:
+    """host<->device staging of the (x, b) pair of a solve call."""
+
+    def __init__(self, A: B200CSR, x, b):
+        self.host = not is_device(x)
+        self.x, self.b = x, b
+        if self.host:
+            if is_device(b):
+                raise TypeError("x and b must both be host arrays or both be device arrays")
+            if not (isinstance(x, np.ndarray) and x.dtype == A.dtype):
+                raise TypeError(f"x must be a numpy array of eltype {A.dtype} (got {getattr(x, 'dtype', type(x))})")
+            self.xd = DeviceArray.from_numpy(A.ctx, x)
+            self.bd = DeviceArray.from_numpy(A.ctx, np.asarray(b, dtype=A.dtype))
+        else:
+            self.xd, self.bd = x, b
+        if self._len(self.xd) != A.m_local or self._len(self.bd) != A.m_local:
+            raise ValueError("dimension mismatch between A, x and b")
+
+    @staticmethod
+    def _len(v):
+        return v.shape[0]
+
+    def finish(self):
+        if self.host:
+            self.x[...] = self.xd.numpy().reshape(self.x.shape)
+        return self.x
+
+
+def _history(res: _lib.Result, resnorm, abstol, reltol, log, restart=None):
+    h = ConvergenceHistory(restart=restart)
+    h["abstol"], h["reltol"] = abstol, reltol
+    h.isconverged = bool(res.isconverged)
+    if log:
+        h.mvps, h.iters = int(res.mvps), int(res.iters)
+        h["resnorm"] = resnorm[: res.n_resnorm].copy()
+        h["tol"] = res.tol
+    return h
+
+
+# ------------------------------------------------------------------------------------------------
+# CG  (reference src/cg.jl:162, 209-242)
+# ------------------------------------------------------------------------------------------------
+def cg_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, log=False, verbose=False, Pl=None,
+        initially_zero=False, statevars=None, check_every=0, _fixed_iterations=False):
+    """cg!(x, A, b; abstol, reltol, maxiter, log, statevars, verbose, Pl, initially_zero).
+    `statevars` is accepted for signature parity; the engine owns its work vectors."""
+    _check_operator(A)
+    if reltol is None:
+        reltol = math.sqrt(_eps(A.dtype))                     # src/cg.jl:211
+    if maxiter is None:
+        maxiter = A.size(2)                                   # src/cg.jl:212
+    opts = _lib.CgOpts(abstol, reltol, int(maxiter), int(bool(initially_zero)), int(check_every),
+                       precond_to_c(Pl, A), int(bool(_fixed_iterations)), 0)
+    res = _lib.Result()
+    cap = int(maxiter) + 1 if log else 0                      # reserve!(history, :resnorm, maxiter+1)  :221
+    resnorm = np.zeros(max(cap, 1), dtype=np.float64)
+    rp = resnorm.ctypes.data_as(C.c_void_p) if log else None
+    if not is_device(x) and isinstance(x, np.ndarray) and x.ndim == 1 and x.flags.c_contiguous and x.dtype == A.dtype:
+        bh = np.ascontiguousarray(b, dtype=A.dtype)
+        if bh.shape != x.shape or x.shape[0] != A.m_local:
+            raise ValueError("dimension mismatch between A, x and b")
+        check(lib().b200_cg_solve_host(A.ctx._h, A._h, x.ctypes.data_as(C.c_void_p), bh.ctypes.data_as(C.c_void_p),
+                                       C.byref(opts), C.byref(res), rp, cap))
+    else:
+        st = _Staged(A, x, b)
+        check(lib().b200_cg_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
+                                  C.byref(res), rp, cap))
+        st.finish()
+    if verbose:
+        for i, r in enumerate(resnorm[: res.n_resnorm]):
+            print(f"{i + 1:3d}\t{r:1.2e}")
+        print()
+    cg_.last_result = res
+    return (x, _history(res, resnorm, abstol, reltol, log)) if log else x
+
+
+def cg(A, b, **kw):
+    """cg(A, b; kw...) = cg!(zerox(A, b), A, b; initially_zero = true, kw...)  (src/cg.jl:162)."""
+    _check_operator(A)
+    if is_device(b):
+        x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype)
+    else:
+        x = np.zeros(A.m_local, dtype=A.dtype)
+    return cg_(x, A, b, initially_zero=True, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# GMRES  (reference src/gmres.jl:143, 184-222)
+# ------------------------------------------------------------------------------------------------
+_ORTH = {"mgs": _lib.ORTH_MGS, "cgs": _lib.ORTH_CGS, "dgks": _lib.ORTH_DGKS,
+         "ModifiedGramSchmidt": _lib.ORTH_MGS, "ClassicalGramSchmidt": _lib.ORTH_CGS, "DGKS": _lib.ORTH_DGKS}
+
+
+def gmres_(x, A, b, *, Pl=None, Pr=None, abstol=0.0, reltol=None, restart=None, maxiter=None, log=False,
+           initially_zero=False, verbose=False, orth_meth="mgs"):
+    """gmres!(x, A, b; Pl, Pr, abstol, reltol, restart, maxiter, log, initially_zero, verbose, orth_meth)."""
+    _check_operator(A)
+    if reltol is None:
+        reltol = math.sqrt(_eps(A.dtype))
+    if restart is None:
+        restart = min(20, A.size(2))                          # src/gmres.jl:189
+    if maxiter is None:
+        maxiter = A.size(2)
+    opts = _lib.GmresOpts(abstol, reltol, int(maxiter), int(restart), int(bool(initially_zero)), _ORTH[orth_meth], 0,
+                          precond_to_c(Pl, A), precond_to_c(Pr, A))
+    res = _lib.Result()
+    cap = int(maxiter) if log else 0                          # reserve!(history, :resnorm, maxiter)  :198
+    resnorm = np.zeros(max(cap, 1), dtype=np.float64)
+    st = _Staged(A, x, b)
+    check(lib().b200_gmres_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
+                                 C.byref(res), resnorm.ctypes.data_as(C.c_void_p) if log else None, cap))
+    st.finish()
+    if verbose:
+        print("=== gmres ===\nrest\titer\tresnorm")
+        for i, r in enumerate(resnorm[: res.n_resnorm], start=1):
+            print(f"{1 + (i - 1) // restart:3d}\t{1 + (i - 1) % restart:3d}\t{r:1.2e}")
+        print()
+    h = _history(res, resnorm, abstol, reltol, log, restart=restart)   # setconv always (src/gmres.jl:218)
+    return (x, h) if log else x
+
+
+def gmres(A, b, **kw):
+    _check_operator(A)
+    x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
+    return gmres_(x, A, b, initially_zero=True, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# MINRES  (reference src/minres.jl:200-244)
+# ------------------------------------------------------------------------------------------------
+def minres_(x, A, b, *, skew_hermitian=False, verbose=False, log=False, abstol=0.0, reltol=None, maxiter=None,
+            initially_zero=False):
+    _check_operator(A)
+    if reltol is None:
+        reltol = math.sqrt(_eps(A.dtype))
+    if maxiter is None:
+        maxiter = A.size(2)
+    opts = _lib.MinresOpts(abstol, reltol, int(maxiter), int(bool(initially_zero)), int(bool(skew_hermitian)))
+    res = _lib.Result()
+    cap = int(maxiter) if log else 0
+    resnorm = np.zeros(max(cap, 1), dtype=np.float64)
+    st = _Staged(A, x, b)
+    check(lib().b200_minres_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
+                                  C.byref(res), resnorm.ctypes.data_as(C.c_void_p) if log else None, cap))
+    st.finish()
+    if verbose:
+        for i, r in enumerate(resnorm[: res.n_resnorm], start=1):
+            print(f"{i:3d}\t{r:1.2e}")
+        print()
+    return (x, _history(res, resnorm, abstol, reltol, log)) if log else x
+
+
+def minres(A, b, **kw):
+    _check_operator(A)
+    x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
+    return minres_(x, A, b, initially_zero=True, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# BiCGStab(l)  (reference src/bicgstabl.jl:143, 181-219)
+# ------------------------------------------------------------------------------------------------
+def bicgstabl_(x, A, b, l=2, *, abstol=0.0, reltol=None, max_mv_products=None, log=False, verbose=False, Pl=None,
+               initial_zero=False, r_shadow=None, rng=None):
+    """bicgstabl!(x, A, b, l; ...).  The reference draws r_shadow = rand(T, n) (src/bicgstabl.jl:38);
+    here the draw happens on the host (numpy Generator `rng`) unless `r_shadow` is given."""
+    _check_operator(A)
+    if reltol is None:
+        reltol = math.sqrt(_eps(A.dtype))
+    if max_mv_products is None:
+        max_mv_products = A.size(2)
+    if r_shadow is None:
+        rng = rng or np.random.default_rng()
+        r_shadow = rng.random(A.m_local).astype(A.dtype)
+    rs = r_shadow if is_device(r_shadow) else DeviceArray.from_numpy(A.ctx, np.asarray(r_shadow, dtype=A.dtype))
+    opts = _lib.BicgstablOpts(abstol, reltol, int(max_mv_products), int(l), int(bool(initial_zero)),
+                              precond_to_c(Pl, A), as_device_ptr(rs))
+    res = _lib.Result()
+    cap = int(max_mv_products) if log else 0                  # src/bicgstabl.jl:194
+    resnorm = np.zeros(max(cap, 1), dtype=np.float64)
+    st = _Staged(A, x, b)
+    status = lib().b200_bicgstabl_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
+                                        C.byref(res), resnorm.ctypes.data_as(C.c_void_p) if log else None, cap)
+    if status == _lib.ERR_BREAKDOWN:
+        raise np.linalg.LinAlgError("SingularException in BiCGStab(l) MR step (reference src/bicgstabl.jl:123)")
+    check(status)
+    st.finish()
+    if verbose:
+        for i, r in enumerate(resnorm[: res.n_resnorm], start=1):
+            print(f"{i:3d}\t{r:1.2e}")
+        print()
+    return (x, _history(res, resnorm, abstol, reltol, log)) if log else x
+
+
+def bicgstabl(A, b, l=2, **kw):
+    _check_operator(A)
+    x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
+    return bicgstabl_(x, A, b, l, initial_zero=True, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# LOBPCG  (reference src/lobpcg.jl:787-839, 865-893)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class LOBPCGResults:
+    """reference src/lobpcg.jl:56-65."""
+    lam: np.ndarray            # λ
+    X: object
+    tolerance: float
+    residual_norms: np.ndarray
+    iterations: int
+    maxiter: int
+    converged: bool
+    trace: list
+
+
+def lobpcg(A, largest: bool, X0, *, P=None, tol=None, maxiter=200, log=False, _fixed_iterations=False):
+    """lobpcg(A, largest, X0; P, tol, maxiter) -> LOBPCGResults (standard problem, B = I, no constraint).
+    X0: n x blocksize, host (numpy, any order) or DeviceArray (column-major)."""
+    _check_operator(A)
+    if tol is None:
+        tol = _eps(A.dtype) ** 0.3                             # default_tolerance  src/lobpcg.jl:751
+    host = not is_device(X0)
+    Xd = DeviceArray.from_numpy(A.ctx, np.asarray(X0, dtype=A.dtype)) if host else X0
+    n, bs = Xd.shape
+    if n != A.m_local:
+        raise ValueError("X0 has the wrong number of rows")
+    if n < 3 * bs:
+        # src/lobpcg.jl:833: throw("n must be at least 3 times the block size")
+        raise B200Error("The order of the matrix must be at least 3 times the block size")
+    opts = _lib.LobpcgOpts(float(tol), int(maxiter), int(bool(largest)), int(bs), precond_to_c(P, A),
+                           int(bool(_fixed_iterations)), 0)
+    res = _lib.LobpcgResult()
+    lam = np.zeros(bs, dtype=np.float64)
+    rn = np.zeros(bs, dtype=np.float64)
+    status = lib().b200_lobpcg_solve(A.ctx._h, A._h, as_device_ptr(Xd), n, C.byref(opts), C.byref(res),
+                                     lam.ctypes.data_as(C.c_void_p), rn.ctypes.data_as(C.c_void_p))
+    if status == _lib.ERR_BREAKDOWN:
+        raise np.linalg.LinAlgError("PosDefException in CholQR (reference src/lobpcg.jl:380)")
+    check(status)
+    X = Xd.numpy() if host else Xd
+    return LOBPCGResults(lam.astype(A.dtype), X, float(tol), rn.astype(A.dtype), int(res.iterations), int(maxiter),
+                         bool(res.converged), [])
+
+
+# ------------------------------------------------------------------------------------------------
+# L1 helpers exposed for tests / drop-in use
+# ------------------------------------------------------------------------------------------------
+def orthogonalize_and_normalize_(V: DeviceArray, w: DeviceArray, h: np.ndarray, method="mgs", k=None):
+    """orthogonalize_and_normalize!(V[:, 1:k], w, h, method) -> nrm  (reference src/orthogonalize.jl)."""
+    k = V.shape[1] if k is None else k
+    nrm = C.c_double()
+    hh = np.zeros(k, dtype=np.float64)
+    check(lib().b200_orthogonalize_and_normalize(V.ctx._h, V.shape[0], V._p, V.shape[0], k, w._p,
+                                                 hh.ctypes.data_as(C.c_void_p), _ORTH[method], V.code, C.byref(nrm)))
+    h[:k] = hh
+    return float(nrm.value)
+
+
+def hessenberg_ldiv_(H: DeviceArray, rhs: DeviceArray):
+    """ldiv!(FastHessenberg(H), rhs)  (reference src/hessenberg.jl:15-46); H (m+1) x m fp64 on device."""
+    check(lib().b200_hessenberg_ldiv(H.ctx._h, H._p, H.shape[0], H.shape[1], rhs._p))
+    return rhs

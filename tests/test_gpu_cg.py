@@ -1,0 +1,291 @@
+"""GPU parity tests for the operator construction, SpMV and the CG engine -- all through the C ABI.
+
+The oracle (oracle/) is the checker only.  Tolerances (fp64): SpMV 1e-13 relative (different
+summation order inside a row), CG residual history and solution 1e-10 relative
+(BASELINE.json north_star).  fp32: 2e-5 on SpMV, 1e-3 on CG histories.
+"""
+import math
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+SEED = 1234321
+
+
+@pytest.fixture(scope="module")
+def isb():
+    import iterativesolvers_jl_b200 as m
+    m.default_context()
+    return m
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+# ------------------------------------------------------------------ operator construction
+@pytest.mark.parametrize("idx", [np.int64, np.int32])
+@pytest.mark.parametrize("base", [0, 1])
+def test_csr_from_csc_is_the_sorted_transpose(isb, idx, base):
+    M = sp.random(301, 301, density=0.03, random_state=5, format="csc", dtype=np.float64) + sp.identity(301, format="csc")
+    M = M.tocsc()
+    M.sort_indices()
+    A = isb.B200CSR.from_csc_arrays(M.indptr.astype(idx) + base, M.indices.astype(idx) + base, M.data, M.shape, base)
+    rowptr, colind, vals = A.download()
+    R = M.tocsr()
+    R.sort_indices()
+    assert np.array_equal(rowptr, R.indptr) and np.array_equal(colind, R.indices) and np.array_equal(vals, R.data)
+
+
+def test_empty_rows_and_duplicates_free_matrix(isb):
+    M = sp.csc_matrix((np.array([1.0, 2.0, 3.0]), (np.array([0, 3, 3]), np.array([0, 1, 3]))), shape=(5, 5))
+    A = isb.B200CSR.from_scipy(M)
+    x = np.arange(1.0, 6.0)
+    np.testing.assert_array_equal(A @ x, M @ x)
+
+
+def test_device_laplacian_equals_host_generator(isb, oracle):
+    for N, dims in [(9, 1), (12, 2), (7, 3)]:
+        A = isb.B200CSR.laplacian(N, dims)
+        rowptr, colind, vals = A.download()
+        O = oracle.laplace_matrix(np.float64, N, dims)          # symmetric: CSC arrays == CSR arrays
+        assert np.array_equal(rowptr, O.colptr) and np.array_equal(colind, O.rowval) and np.array_equal(vals, O.nzval)
+        cp, rv, nz, _ = isb.laplace_matrix(np.float64, N, dims)
+        assert np.array_equal(cp, O.colptr) and np.array_equal(rv, O.rowval) and np.array_equal(nz, O.nzval)
+
+
+# ------------------------------------------------------------------ SpMV
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 2e-5)])
+def test_spmv_vs_oracle_laplacian(isb, oracle, dtype, tol):
+    rng = np.random.default_rng(SEED)
+    O = oracle.laplace_matrix(dtype, 24, 3, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    x = rng.standard_normal(O.n).astype(dtype)
+    assert relerr(A @ x, oracle.csc_spmv(O, x)) <= tol
+
+
+def test_spmv_nonsymmetric_advection(isb, oracle):
+    rng = np.random.default_rng(SEED)
+    M, _ = oracle.advection_dominated(10, 1000.0)
+    O = oracle.CSC.from_scipy(M, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    x = rng.standard_normal(O.n)
+    assert relerr(A @ x, oracle.csc_spmv(O, x)) <= 1e-13
+
+
+@pytest.mark.parametrize("density", [0.002, 0.05, 0.4])
+def test_spmv_random_rows_of_all_lengths(isb, oracle, density):
+    rng = np.random.default_rng(SEED)
+    M = sp.random(700, 700, density=density, random_state=11, format="csc", dtype=np.float64)
+    O = oracle.CSC.from_scipy(M, base=0)
+    A = isb.B200CSR.from_scipy(M)
+    x = rng.standard_normal(700)
+    assert relerr(A @ x, oracle.csc_spmv(O, x)) <= 1e-13
+
+
+def test_spmm_block(isb, oracle):
+    rng = np.random.default_rng(SEED)
+    O = oracle.laplace_matrix(np.float32, 12, 3)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape)
+    for bs in (1, 3, 16, 21):
+        X = np.asfortranarray(rng.standard_normal((O.n, bs)).astype(np.float32))
+        assert relerr(A @ X, oracle.csc_spmm(O, X)) <= 2e-5
+
+
+# ------------------------------------------------------------------ BLAS-1 through the C ABI
+def test_blas1(isb):
+    import ctypes as C
+    rng = np.random.default_rng(SEED)
+    ctx = isb.default_context()
+    n = 100003
+    x, y = rng.standard_normal(n), rng.standard_normal(n)
+    xd, yd = isb.DeviceArray.from_numpy(ctx, x), isb.DeviceArray.from_numpy(ctx, y)
+    out = C.c_double()
+    L = isb.lib()
+    assert L.b200_dot(ctx._h, n, xd._p, yd._p, 0, C.byref(out)) == 0
+    assert out.value == pytest.approx(float(np.dot(x, y)), rel=1e-12)
+    assert L.b200_nrm2(ctx._h, n, xd._p, 0, C.byref(out)) == 0
+    assert out.value == pytest.approx(float(np.linalg.norm(x)), rel=1e-13)
+    assert L.b200_axpby(ctx._h, n, 2.5, xd._p, -0.5, yd._p, 0) == 0
+    np.testing.assert_allclose(yd.numpy(), 2.5 * x - 0.5 * y, rtol=1e-15)
+    assert L.b200_scal(ctx._h, n, 3.0, xd._p, 0) == 0
+    np.testing.assert_array_equal(xd.numpy(), 3.0 * x)
+    # determinism of the reduction
+    v1, v2 = C.c_double(), C.c_double()
+    L.b200_dot(ctx._h, n, xd._p, yd._p, 0, C.byref(v1))
+    L.b200_dot(ctx._h, n, xd._p, yd._p, 0, C.byref(v2))
+    assert v1.value == v2.value
+
+
+# ------------------------------------------------------------------ CG: parity with the oracle
+def _rhs(n, dtype=np.float64):
+    rng = np.random.default_rng(SEED)
+    b = rng.standard_normal(n)
+    b /= np.linalg.norm(b)                                   # rmul!(rhs, inv(norm(rhs)))  test/cg.jl:59-60
+    return b.astype(dtype)
+
+
+def test_cg_config1_2d_poisson_128(isb, oracle):
+    """BASELINE.json configs[0]: cg! on the 5-pt 2-D Poisson SparseMatrixCSC n=128^2 fp64."""
+    O = oracle.laplace_matrix(np.float64, 128, 2, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    b = _rhs(O.n)
+    xo, ho = oracle.cg_csc_c(np.zeros(O.n), O, b, initially_zero=True)
+    x, h = isb.cg(A, b, log=True)
+    assert h.isconverged and h.niters == ho.niters and h.mvps == ho.mvps
+    assert np.max(np.abs(h["resnorm"] - ho["resnorm"]) / ho["resnorm"]) <= 1e-10
+    assert relerr(x, xo) <= 1e-10
+    assert h["tol"] == pytest.approx(ho["tol"], rel=1e-14)
+
+
+@pytest.mark.parametrize("N", [32, 64])
+def test_cg_3d_laplacian_vs_oracle(isb, oracle, N):
+    O = oracle.laplace_matrix(np.float64, N, 3, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    b = _rhs(O.n)
+    xo, ho = oracle.cg_csc_c(np.zeros(O.n), O, b, initially_zero=True)
+    x, h = isb.cg(A, b, log=True)
+    assert h.isconverged and h.niters == ho.niters
+    assert np.max(np.abs(h["resnorm"] - ho["resnorm"]) / ho["resnorm"]) <= 1e-10
+    assert relerr(x, xo) <= 1e-10
+
+
+def test_cg_check_every_does_not_change_results(isb, oracle):
+    O = oracle.laplace_matrix(np.float64, 20, 3)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape)
+    b = _rhs(O.n)
+    x1, h1 = isb.cg(A, b, log=True, check_every=1)
+    x2, h2 = isb.cg(A, b, log=True, check_every=7)
+    x3, h3 = isb.cg(A, b, log=True, check_every=1000)
+    assert h1.niters == h2.niters == h3.niters
+    assert np.array_equal(x1, x2) and np.array_equal(x1, x3)
+    assert np.array_equal(h1["resnorm"], h3["resnorm"])
+
+
+def test_cg_jacobi_pcg_and_initial_guess(isb, oracle):
+    """reference test/cg.jl:55-87 through the device engine, checked against the oracle."""
+    rng = np.random.default_rng(SEED)
+    O = oracle.laplace_matrix(np.float64, 10, 2, base=1)
+    S = O.to_scipy()
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    P = isb.JacobiPrec(A.diag())
+    np.testing.assert_array_equal(P.diagonal.numpy(), O.diagonal())
+    rhs = _rhs(O.n)
+    reltol = abstol = 1e-5
+    xCG = isb.cg(A, rhs, reltol=reltol, maxiter=100)
+    xJAC = isb.cg(A, rhs, Pl=P, reltol=reltol, maxiter=100)
+    assert np.linalg.norm(S @ xCG - rhs) <= reltol and np.linalg.norm(S @ xJAC - rhs) <= reltol
+    x0 = rng.standard_normal(O.n)
+    xCG, hCG = isb.cg_(x0.copy(), A, rhs, abstol=abstol, reltol=0.0, maxiter=100, log=True)
+    xJAC, hJAC = isb.cg_(x0.copy(), A, rhs, Pl=P, abstol=abstol, reltol=0.0, maxiter=100, log=True)
+    assert np.linalg.norm(S @ xCG - rhs) <= reltol and np.linalg.norm(S @ xJAC - rhs) <= reltol
+    assert hJAC.niters == hCG.niters
+    xo, ho = oracle.cg_csc_c(x0.copy(), O, rhs, abstol=abstol, reltol=0.0, maxiter=100)
+    assert ho.niters == hCG.niters and ho.mvps == hCG.mvps
+    assert relerr(xCG, xo) <= 1e-10
+    xo2, ho2 = oracle.cg_csc_c(x0.copy(), O, rhs, abstol=abstol, reltol=0.0, maxiter=100, Pl_diag=O.diagonal())
+    assert ho2.niters == hJAC.niters and relerr(xJAC, xo2) <= 1e-10
+    np.testing.assert_allclose(hJAC["resnorm"], ho2["resnorm"], rtol=1e-10)
+
+
+def test_cg_nonconstant_diagonal_pcg_vs_oracle(isb, oracle):
+    rng = np.random.default_rng(SEED)
+    L = oracle.laplace_matrix_scipy(np.float64, 14, 2)
+    M = (L + sp.diags(rng.random(L.shape[0]) * 3.0)).tocsc()
+    O = oracle.CSC.from_scipy(M, base=1)
+    A = isb.B200CSR.from_scipy(M)
+    b = _rhs(O.n)
+    xo, ho = oracle.cg_csc_c(np.zeros(O.n), O, b, initially_zero=True, Pl_diag=O.diagonal())
+    x, h = isb.cg(A, b, Pl=isb.JacobiPrec(A.diag()), log=True)
+    assert h.niters == ho.niters and relerr(x, xo) <= 1e-10
+    np.testing.assert_allclose(h["resnorm"], ho["resnorm"], rtol=1e-10)
+
+
+def test_cg_x_is_updated_in_place_and_zero_rhs(isb, oracle):
+    O = oracle.laplace_matrix(np.float64, 8, 2)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape)
+    x0 = np.zeros(O.n)
+    x = isb.cg_(x0, A, _rhs(O.n))
+    assert x is x0 and np.linalg.norm(x0) > 0
+    xz = isb.cg(A, np.zeros(O.n))                              # test/cg.jl:50-51
+    assert np.array_equal(xz, np.zeros(O.n))
+    # device-resident arrays: same object back, zero-copy
+    ctx = isb.default_context()
+    xd = isb.DeviceArray.zeros(ctx, O.n)
+    bd = isb.DeviceArray.from_numpy(ctx, _rhs(O.n))
+    out = isb.cg_(xd, A, bd, initially_zero=True)
+    assert out is xd and relerr(xd.numpy(), x0) <= 1e-13
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_cg_termination_criterion(isb, dtype):
+    """reference test/cg.jl:98-122 (real types)."""
+    D = np.array([[2, -1, 0], [-1, 2, -1], [0, -1, 2]], dtype=dtype)
+    A = isb.B200CSR.from_scipy(sp.csc_matrix(D))
+    n = 3
+    b = np.ones(n, dtype=dtype)
+    x0 = np.linalg.solve(D.astype(np.float64), b.astype(np.float64)).astype(dtype)
+    pert = (10 * math.sqrt(np.finfo(dtype).eps) * np.array([-1.0, 1.0, -1.0])).astype(dtype)
+    x, ch = isb.cg_(x0 + pert, A, b, log=True)
+    assert 2 <= ch.niters <= n
+    x = x0 + pert
+    r0 = np.linalg.norm(D @ x - b)
+    x, ch = isb.cg_(x, A, b, abstol=2 * float(r0), reltol=0.0, log=True)
+    assert ch.niters == 0 and ch.mvps == 1
+
+
+def test_cg_float32_vs_oracle(isb, oracle):
+    O = oracle.laplace_matrix(np.float32, 16, 3, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    b = _rhs(O.n, np.float32)
+    x, h = isb.cg(A, b, log=True)
+    xo, ho = oracle.cg_(np.zeros(O.n, dtype=np.float32), O, b, initially_zero=True, log=True)
+    assert h.isconverged and abs(h.niters - ho.niters) <= 2
+    k = min(h.niters, ho.niters)
+    assert np.max(np.abs(h["resnorm"][:k] - ho["resnorm"][:k]) / ho["resnorm"][:k]) <= 1e-3
+    assert relerr(x, xo) <= 1e-4
+
+
+def test_cg_maxiter_and_not_converged_is_not_an_error(isb, oracle):
+    O = oracle.laplace_matrix(np.float64, 16, 3)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape)
+    x, h = isb.cg(A, _rhs(O.n), maxiter=5, log=True)
+    assert h.niters == 5 and not h.isconverged and len(h["resnorm"]) == 5
+
+
+# ------------------------------------------------------------------ full-size properties (config #2)
+def test_cg_256cubed_properties(isb):
+    """BASELINE.json configs[1]: cg! on the 7-pt 3-D Laplacian n=256^3 fp64 on one B200.
+    Size-independent properties: manufactured solution (b = A x*), the recurrence residual equals the
+    true residual, residual history is reproduced run-to-run bit-for-bit."""
+    import ctypes as C
+    ctx = isb.default_context()
+    N = 256
+    n = N ** 3
+    A = isb.B200CSR.laplacian(N, 3)
+    assert A.nnz == 7 * N ** 3 - 6 * N ** 2
+    rng = np.random.default_rng(SEED)
+    xstar = rng.standard_normal(n)
+    xs = isb.DeviceArray.from_numpy(ctx, xstar)
+    b = isb.DeviceArray(ctx, n)
+    A.mul_(b, xs)
+    x = isb.DeviceArray.zeros(ctx, n)
+    x, h = isb.cg_(x, A, b, initially_zero=True, log=True, reltol=1e-8)
+    assert h.isconverged and 300 < h.niters < 1500
+    r = isb.DeviceArray(ctx, n)
+    A.mul_(r, x)
+    L = isb.lib()
+    assert L.b200_axpby(ctx._h, n, 1.0, b._p, -1.0, r._p, 0) == 0          # r = b - A x
+    nr, nb = C.c_double(), C.c_double()
+    L.b200_nrm2(ctx._h, n, r._p, 0, C.byref(nr))
+    L.b200_nrm2(ctx._h, n, b._p, 0, C.byref(nb))
+    assert nr.value / nb.value <= 1.01e-8
+    assert nr.value == pytest.approx(h["resnorm"][-1], rel=1e-4)           # recurrence residual == true residual
+    err = np.linalg.norm(x.numpy() - xstar) / np.linalg.norm(xstar)
+    assert err < 1e-4                                                       # cond(A) ~ 2.7e4
+    x2 = isb.DeviceArray.zeros(ctx, n)
+    x2, h2 = isb.cg_(x2, A, b, initially_zero=True, log=True, reltol=1e-8)
+    assert np.array_equal(h["resnorm"], h2["resnorm"])
