@@ -99,6 +99,9 @@ B200_API int b200_ctx_timer_stop(b200_ctx *ctx, float *ms);
  * accumulated milliseconds and launch counts per slot since the last reset. */
 B200_API int b200_ctx_profile_enable(b200_ctx *ctx, int on);
 B200_API int b200_ctx_profile_read(b200_ctx *ctx, int slot, double *total_ms, int64_t *launches, int reset);
+/* Tuning knobs (do not change results beyond floating-point summation order):
+ *   "spmv_kernel": 0 = auto, 1 = sub-warp-per-row kernel, 2 = TMA-streamed kernel (when the tiles fit) */
+B200_API int b200_ctx_set_option(b200_ctx *ctx, const char *name, int64_t value);
 /* sum over ranks (no-op for world==1); used by hosts for max/sum of small host scalars */
 B200_API int b200_ctx_allreduce_f64(b200_ctx *ctx, double *host_inout, int count, int op_max);
 B200_API int b200_ctx_barrier(b200_ctx *ctx);

@@ -81,6 +81,7 @@ SIGNATURES = {
     "b200_ctx_launch_count": (_I64, [_P]),
     "b200_ctx_timer_start": (_INT, [_P]),
     "b200_ctx_timer_stop": (_INT, [_P, C.POINTER(C.c_float)]),
+    "b200_ctx_set_option": (_INT, [_P, C.c_char_p, _I64]),
     "b200_ctx_profile_enable": (_INT, [_P, _INT]),
     "b200_ctx_profile_read": (_INT, [_P, _INT, C.POINTER(_DBL), C.POINTER(_I64), _INT]),
     "b200_ctx_allreduce_f64": (_INT, [_P, C.POINTER(_DBL), _INT, _INT]),
@@ -141,7 +142,13 @@ def lib():
         if not os.path.exists(_SO):
             raise B200Error(f"{_SO} is missing: build it with `make -C iterativesolvers.jl_b200/csrc` "
                             "(there is no CPU or PyTorch fallback)")
-        _lib = C.CDLL(_SO, mode=C.RTLD_GLOBAL)
+        # libb200krylov.so needs libnccl.so.2.  If PyTorch's bundled NCCL exists, load THAT copy first so
+        # that a later `import torch` (which needs its own, newer NCCL under the same soname) still works.
+        import sysconfig
+        bundled = os.path.join(sysconfig.get_paths()["purelib"], "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(bundled):
+            C.CDLL(bundled, mode=C.RTLD_GLOBAL)
+        _lib = C.CDLL(_SO)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(_lib, name)     # AttributeError if the library does not export it
             fn.restype = res

@@ -13,7 +13,7 @@
 // Multi-GPU: the two sums are ncclAllReduce'd (one double each) and a 1-thread kernel does the
 // bookkeeping; the halo exchange precedes K2.
 #include "blas1.cuh"
-#include "spmv.cuh"
+#include "spmv_stream.cuh"
 
 using namespace b200;
 
@@ -151,6 +151,33 @@ __global__ void __launch_bounds__(kThreads) k_cg_spmv_dot(const int *__restrict_
     cg_finish(FIN_DOT, s, total, nullptr, single_gpu);
 }
 
+// K2, TMA-streamed form (spmv_stream.cuh): same result contract as k_cg_spmv_dot
+template <typename T>
+struct CgDotEpi {
+  T *__restrict__ c;
+  const T *__restrict__ u;
+  double acc;
+  __device__ __forceinline__ void operator()(int64_t row, T v) {
+    c[row] = v;
+    acc += (double)u[row] * (double)v;
+  }
+};
+template <typename T, int LPR>
+__global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
+    k_cg_spmv_dot_stream(const int *__restrict__ rowptr, const int *__restrict__ colind, const T *__restrict__ vals,
+                         XView<T> xv, int64_t m, int W, T *__restrict__ c, CgScal *s, double *partials,
+                         unsigned int *ticket, int single_gpu) {
+  if (s->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double red[kStreamThreads / 32];
+  CgDotEpi<T> epi{c, xv.x, 0.0};
+  spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, m, W, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw));
+  const double acc = block_sum<kStreamThreads>(epi.acc, red);
+  double total;
+  if (grid_reduce_finish<kStreamThreads>(acc, partials, ticket, red, &total) && threadIdx.x == 0)
+    cg_finish(FIN_DOT, s, total, nullptr, single_gpu);
+}
+
 // K3: x += alpha*u ; r -= alpha*c ; ||r||^2
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_update_xr(T *__restrict__ x, T *__restrict__ r,
@@ -225,7 +252,32 @@ struct CgEngine {
   int spmv_dot() {
     B200_TRY(halo_exchange(ctx, A, u));
     XView<T> xv = make_xview<T>(A, u);
-    {
+    if (use_stream(ctx, A)) {
+      const int grid = stream_grid_size(ctx, A);
+      const size_t smem = sizeof(StreamSmem<T>);
+      const int W = stream_window_w(ctx, A, u);
+      ProfScope prof(ctx, 0);
+#define LAUNCH(L)                                                                                                    \
+  do {                                                                                                               \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      B200_CUDA(cudaFuncSetAttribute(k_cg_spmv_dot_stream<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                     (int)smem));                                                                    \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    k_cg_spmv_dot_stream<T, L><<<grid, kStreamThreads, smem, ctx->stream>>>(                                        \
+        A->rowptr, A->colind, (const T *)A->vals, xv, n, W, c, s, ctx->red.partials, ctx->red.ticket, single);       \
+  } while (0)
+      switch (A->stream_lpr) {
+        case 1: LAUNCH(1); break;
+        case 2: LAUNCH(2); break;
+        case 4: LAUNCH(4); break;
+        case 8: LAUNCH(8); break;
+        case 16: LAUNCH(16); break;
+        default: LAUNCH(32); break;
+      }
+#undef LAUNCH
+    } else {
     ProfScope prof(ctx, 0);
 #define LAUNCH(L)                                                                                               \
   k_cg_spmv_dot<T, L><<<grid_spmv, kThreads, 0, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals, xv, n, \

@@ -301,6 +301,41 @@ __global__ void k_row_stats(const int *__restrict__ rowptr, int64_t m, int *__re
   if ((threadIdx.x & 31) == 0) atomicMax(max_len, local);
 }
 
+// max over uniform tiles of R rows of the tile's nonzero count
+__global__ void k_tile_max(const int *__restrict__ rowptr, int64_t m, int R, int *__restrict__ out) {
+  const int64_t ntiles = (m + R - 1) / R;
+  int local = 0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < ntiles; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r0 = t * R, r1 = (r0 + R < m) ? r0 + R : m;
+    local = max(local, rowptr[r1] - rowptr[r0]);
+  }
+  for (int o = 16; o > 0; o >>= 1) local = max(local, __shfl_xor_sync(0xffffffffu, local, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, local);
+}
+
+// out[i] = number of nonzeros with |col - row| <= {16, 64, 256, 512}[i] (own columns only)
+__global__ void k_band_profile(const int *__restrict__ rowptr, const int *__restrict__ colind, int64_t m,
+                               unsigned long long *__restrict__ out) {
+  unsigned int c[4] = {0, 0, 0, 0};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+      const int64_t d = (int64_t)colind[k] - i;
+      const int64_t a = d < 0 ? -d : d;
+      if (colind[k] < m) {
+        c[0] += a <= 16;
+        c[1] += a <= 64;
+        c[2] += a <= 256;
+        c[3] += a <= 512;
+      }
+    }
+  }
+  for (int j = 0; j < 4; ++j) {
+    unsigned int v = c[j];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&out[j], (unsigned long long)v);
+  }
+}
+
 template <typename T>
 __global__ void k_pack(const int *__restrict__ idx, const T *__restrict__ x, int64_t n, T *__restrict__ out) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
@@ -326,7 +361,48 @@ int finish_operator(b200_ctx *ctx, b200_csr *A, const b200_halo_plan *plan) {
   B200_CUDA(cudaStreamSynchronize(ctx->stream));
   A->max_row_nnz = ctx->h_flags[0];
   A->avg_row_nnz = A->m_local ? (double)A->nnz / (double)A->m_local : 0.0;
-  B200_CUDA(cudaMemsetAsync(d_max, 0, sizeof(double), ctx->stream));
+  // TMA-streamed kernel (spmv_stream.cuh): smallest lanes-per-row whose 512/LPR-row tiles hold <= 4096
+  // nonzeros, and the half-width W of the x window staged in shared memory
+  A->stream_lpr = 0;
+  A->stream_w = 0;
+  if (A->m_local > 0) {
+    for (int l = 0; l < 6; ++l) {
+      B200_CUDA(cudaMemsetAsync(d_max + 1 + l, 0, sizeof(int), ctx->stream));
+      k_tile_max<<<grid_for(ctx, (A->m_local + 15) / 16), 256, 0, ctx->stream>>>(A->rowptr, A->m_local, 512 >> l, d_max + 1 + l);
+      B200_LAUNCH_CHECK(ctx);
+    }
+    B200_CUDA(cudaMemcpyAsync(ctx->h_flags, d_max + 1, sizeof(int) * 6, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int l = 0; l < 6; ++l)
+      if (ctx->h_flags[l] <= 4096) {
+        A->stream_lpr = 1 << l;
+        break;
+      }
+  }
+  if (A->stream_lpr > 0 && A->nnz > 0) {
+    // band profile: how many nonzeros lie within w of the diagonal, w in {16, 64, 256, 512}
+    unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(ctx->d_scalars + 16);
+    B200_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 4, ctx->stream));
+    k_band_profile<<<grid_for(ctx, A->m_local), 256, 0, ctx->stream>>>(A->rowptr, A->colind, A->m_local, d_cnt);
+    B200_LAUNCH_CHECK(ctx);
+    unsigned long long cnt[4];
+    B200_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int cand[4] = {16, 64, 256, 512};
+    const int R = 512 / A->stream_lpr;
+    int best = -1;
+    for (int i = 0; i < 4; ++i)
+      if (R + 2 * cand[i] <= 1536) best = i;
+    if (best >= 0 && (double)cnt[best] >= 0.3 * (double)A->nnz) {
+      // smallest window that captures (almost) as much as the largest admissible one
+      int pick = best;
+      for (int i = best; i >= 0; --i)
+        if ((double)cnt[i] >= 0.98 * (double)cnt[best]) pick = i;
+      A->stream_w = cand[pick];
+    }
+    B200_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 4, ctx->stream));
+  }
+  B200_CUDA(cudaMemsetAsync(d_max, 0, sizeof(double) * 8, ctx->stream));
   // halo exchange lists
   const int W = ctx->world;
   A->send_count.assign(W, 0);
@@ -414,11 +490,11 @@ static int csr_from_csc_impl(b200_ctx *ctx, int64_t m, int64_t n, const I *colpt
   CK(cudaMemcpyAsync(d_colptr, colptr, sizeof(I) * (n + 1), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_rowval, rowval, sizeof(I) * nnz, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(d_nz, nzval, sizeof(TI) * nnz, cudaMemcpyHostToDevice, st));
-  CK(cudaMalloc(&A->rowptr, sizeof(int) * (m + 2)));
-  CK(cudaMalloc(&A->colind, sizeof(int) * (nnz ? nnz : 1)));
-  CK(cudaMalloc(&A->vals, sizeof(T) * (nnz ? nnz : 1)));
+  CK(cudaMalloc(&A->rowptr, sizeof(int) * (m + kRowptrPad)));
+  CK(cudaMalloc(&A->colind, sizeof(int) * (nnz + kNnzPad)));
+  CK(cudaMalloc(&A->vals, sizeof(T) * (nnz + kNnzPad)));
   // rowptr: histogram of row ids, exclusive scan
-  CK(cudaMemsetAsync(A->rowptr, 0, sizeof(int) * (m + 2), st));
+  CK(cudaMemsetAsync(A->rowptr, 0, sizeof(int) * (m + kRowptrPad), st));
   if (nnz) {
     k_count_rows<I><<<grid_for(ctx, nnz), 256, 0, st>>>(d_rowval, nnz, base, m, A->rowptr, d_err);
     ctx->launches++;
@@ -430,9 +506,9 @@ static int csr_from_csc_impl(b200_ctx *ctx, int64_t m, int64_t n, const I *colpt
   while (end_bit < 32 && (1ull << end_bit) < (unsigned long long)(m > 1 ? m : 2)) ++end_bit;
   CK(cudaMalloc(&key_in, sizeof(unsigned int) * (nnz ? nnz : 1)));
   CK(cudaMalloc(&key_out, sizeof(unsigned int) * (nnz ? nnz : 1)));
-  CK(cudaMalloc(&col_of, sizeof(int) * (nnz ? nnz : 1)));
-  CK(cudaMalloc(&perm_in, sizeof(int) * (nnz ? nnz : 1)));
-  CK(cudaMalloc(&perm_out, sizeof(int) * (nnz ? nnz : 1)));
+  CK(cudaMalloc(&col_of, sizeof(int) * (nnz + kNnzPad)));
+  CK(cudaMalloc(&perm_in, sizeof(int) * (nnz + kNnzPad)));
+  CK(cudaMalloc(&perm_out, sizeof(int) * (nnz + kNnzPad)));
   CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, key_in, key_out, perm_in, perm_out, (int)nnz, 0, end_bit, st));
   tmp_bytes = std::max(tmp_bytes, tmp2);
   CK(cudaMalloc(&d_tmp, tmp_bytes ? tmp_bytes : 16));
@@ -527,9 +603,10 @@ int b200_csr_from_csr_slab(b200_ctx *ctx, int64_t n_global, int64_t row_begin, i
       return fail(B200_ERR_CUDA);                                                       \
     }                                                                                   \
   } while (0)
-  CK(cudaMalloc(&A->rowptr, sizeof(int) * (m_local + 1)));
-  CK(cudaMalloc(&A->colind, sizeof(int) * (nnz ? nnz : 1)));
-  CK(cudaMalloc(&A->vals, vs * (nnz ? nnz : 1)));
+  CK(cudaMalloc(&A->rowptr, sizeof(int) * (m_local + kRowptrPad)));
+  CK(cudaMemsetAsync(A->rowptr, 0, sizeof(int) * (m_local + kRowptrPad), st));
+  CK(cudaMalloc(&A->colind, sizeof(int) * (nnz + kNnzPad)));
+  CK(cudaMalloc(&A->vals, vs * (nnz + kNnzPad)));
   CK(cudaMalloc(&d_rp, (size_t)idx_bytes * (m_local + 1)));
   CK(cudaMalloc(&d_ci, (size_t)idx_bytes * (nnz ? nnz : 1)));
   CK(cudaMalloc(&d_halo, sizeof(int64_t) * (A->n_halo ? A->n_halo : 1)));
@@ -607,8 +684,8 @@ int b200_csr_laplacian(b200_ctx *ctx, int64_t N, int dims, int dtype, int64_t ro
       return fail(B200_ERR_CUDA);                                                       \
     }                                                                                   \
   } while (0)
-  CK(cudaMalloc(&A->rowptr, sizeof(int) * (m_local + 2)));
-  CK(cudaMemsetAsync(A->rowptr, 0, sizeof(int) * (m_local + 2), st));
+  CK(cudaMalloc(&A->rowptr, sizeof(int) * (m_local + kRowptrPad)));
+  CK(cudaMemsetAsync(A->rowptr, 0, sizeof(int) * (m_local + kRowptrPad), st));
   CK(cudaMalloc(&d_halo, sizeof(int64_t) * (A->n_halo ? A->n_halo : 1)));
   if (A->n_halo)
     CK(cudaMemcpyAsync(d_halo, plan->halo_sorted.data(), sizeof(int64_t) * A->n_halo, cudaMemcpyHostToDevice, st));
@@ -621,8 +698,8 @@ int b200_csr_laplacian(b200_ctx *ctx, int64_t N, int dims, int dtype, int64_t ro
   CK(cudaStreamSynchronize(st));
   A->nnz = nnz32;
   const size_t vs = dtype_size(dtype);
-  CK(cudaMalloc(&A->colind, sizeof(int) * (A->nnz ? A->nnz : 1)));
-  CK(cudaMalloc(&A->vals, vs * (A->nnz ? A->nnz : 1)));
+  CK(cudaMalloc(&A->colind, sizeof(int) * (A->nnz + kNnzPad)));
+  CK(cudaMalloc(&A->vals, vs * (A->nnz + kNnzPad)));
   if (m_local) {
     if (dtype == B200_F64)
       k_lap_fill<double><<<grid_for(ctx, m_local), 256, 0, st>>>(g, row_begin, m_local, A->rowptr, d_halo, A->n_halo, A->colind, (double *)A->vals);

@@ -172,6 +172,21 @@ int b200_ctx_timer_stop(b200_ctx *c, float *ms) {
   return B200_OK;
 }
 
+int b200_ctx_set_option(b200_ctx *c, const char *name, int64_t value) {
+  B200_REQUIRE(c && name, "NULL argument");
+  if (strcmp(name, "spmv_kernel") == 0) {
+    B200_REQUIRE(value >= 0 && value <= 2, "spmv_kernel must be 0, 1 or 2");
+    c->opt_spmv_kernel = (int)value;
+    return B200_OK;
+  }
+  if (strcmp(name, "stream_window") == 0) {
+    c->opt_stream_window = value != 0;
+    return B200_OK;
+  }
+  set_error("unknown option `%s`", name);
+  return B200_ERR_INVALID;
+}
+
 int b200_ctx_profile_enable(b200_ctx *c, int on) {
   B200_REQUIRE(c, "ctx is NULL");
   if (!on && c->prof_on) prof_flush(c);

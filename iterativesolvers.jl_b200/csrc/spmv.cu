@@ -1,5 +1,5 @@
 // spmv.cu -- mul!(y, A, x) and mul!(Y, A, X) (block SpMM) on the device CSR.
-#include "spmv.cuh"
+#include "spmv_stream.cuh"
 
 using namespace b200;
 
@@ -63,9 +63,54 @@ __global__ void __launch_bounds__(kThreads) k_spmm(const int *__restrict__ rowpt
   }
 }
 
+// TMA-streamed y = A x (spmv_stream.cuh)
+template <typename T>
+struct StoreEpi {
+  T *__restrict__ y;
+  __device__ __forceinline__ void operator()(int64_t row, T v) { y[row] = v; }
+};
+template <typename T, int LPR>
+__global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
+    k_spmv_stream(const int *__restrict__ rowptr, const int *__restrict__ colind, const T *__restrict__ vals,
+                  XView<T> xv, int64_t m, int W, T *__restrict__ y) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  StoreEpi<T> epi{y};
+  spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, m, W, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw));
+}
+
+template <typename T>
+int launch_spmv_stream(b200_ctx *ctx, const b200_csr *A, const void *x, void *y) {
+  XView<T> xv = make_xview<T>(A, x);
+  const int grid = stream_grid_size(ctx, A);
+  const size_t smem = sizeof(StreamSmem<T>);
+  const int W = stream_window_w(ctx, A, x);
+#define LAUNCH(L)                                                                                                 \
+  do {                                                                                                            \
+    static bool attr_set = false;                                                                                 \
+    if (!attr_set) {                                                                                              \
+      B200_CUDA(cudaFuncSetAttribute(k_spmv_stream<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    k_spmv_stream<T, L><<<grid, kStreamThreads, smem, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals,   \
+                                                                     xv, A->m_local, W, (T *)y);                 \
+  } while (0)
+  switch (A->stream_lpr) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 4: LAUNCH(4); break;
+    case 8: LAUNCH(8); break;
+    case 16: LAUNCH(16); break;
+    default: LAUNCH(32); break;
+  }
+#undef LAUNCH
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
+
 template <typename T>
 int launch_spmv(b200_ctx *ctx, const b200_csr *A, const void *x, void *y) {
   if (A->m_local == 0) return B200_OK;
+  if (use_stream(ctx, A)) return launch_spmv_stream<T>(ctx, A, x, y);
   XView<T> xv = make_xview<T>(A, x);
   const int lpr = pick_lpr(A->avg_row_nnz);
   const int rows = kThreads / lpr;

@@ -742,3 +742,180 @@ def bicgstabl_(x, A, b, l=2, *, abstol=0.0, reltol=None, max_mv_products=None, l
 def bicgstabl(A, b, l=2, **kw):
     x = np.zeros(opsize(A, 1), dtype=b.dtype)
     return bicgstabl_(x, A, b, l, initial_zero=True, **kw)
+
+
+# --------------------------------------------------------------------------------------------
+# LOBPCG (reference src/lobpcg.jl) -- standard and generalized problem, optional preconditioner,
+# no constraint (C = nothing), the path of BASELINE.json configs[4].
+# --------------------------------------------------------------------------------------------
+@dataclass
+class LOBPCGResults:
+    lam: np.ndarray
+    X: np.ndarray
+    tolerance: float
+    residual_norms: np.ndarray
+    iterations: int
+    maxiter: int
+    converged: bool
+    trace: list
+
+
+def _rdiv_upper(Ablk, R):
+    """rdiv!(A, B::UpperTriangular) -- reference src/lobpcg.jl:345-355 (column sweeps)."""
+    s = Ablk.shape[1]
+    Ablk[:, 0] = Ablk[:, 0] / R[0, 0]
+    for i in range(1, s):
+        for j in range(i):
+            Ablk[:, i] = Ablk[:, i] - Ablk[:, j] * R[j, i]
+        Ablk[:, i] = Ablk[:, i] / R[i, i]
+    return Ablk
+
+
+def _cholqr(X, BX, AX=None, update_AX=False, update_BX=False, generalized=False):
+    """CholQR functor -- reference src/lobpcg.jl:365-393."""
+    gram = X.conj().T @ BX                                              # :376-379
+    R = np.linalg.cholesky(gram.astype(gram.dtype)).conj().T            # cholesky!(Hermitian(gram)) :381 (upper factor)
+    _rdiv_upper(X, R)                                                   # :384/:388
+    if update_AX:
+        _rdiv_upper(AX, R)
+    if generalized and update_BX:
+        _rdiv_upper(BX, R)
+
+
+def lobpcg(A, largest, X0, *, B=None, P=None, tol=None, maxiter=200, log=False, not_zeros=False, rng=None,
+           fixed_iterations=False):
+    """lobpcg(A, [B,] largest, X0; P, tol, maxiter, log) -- reference src/lobpcg.jl:827-839 +
+    lobpcg!(iterator) :865-893 + the step functor :692-749.  `fixed_iterations` (not in the
+    reference) disables soft-locking and the early exit so that throughput runs do constant work."""
+    import scipy.linalg as sla
+    T = X0.dtype
+    if tol is None:
+        tol = float(np.finfo(T).eps) ** 0.3                             # default_tolerance :751
+    X = np.array(X0, dtype=T, order="F", copy=True)                     # X = copy(X0) :830
+    n, sizeX = X.shape
+    if sizeX > n:
+        raise ValueError("X column dimension exceeds the row dimension")            # :833
+    if 3 * sizeX > n:
+        raise ValueError("The LOBPCG algorithms is not stable to use when the matrix size is less than 3 times "
+                         "the block size. Please use a dense solver instead.")       # :834
+    generalized = B is not None
+    if not not_zeros:                                                   # :868-876
+        rng = rng or np.random.default_rng(0)
+        for j in range(sizeX):
+            if np.all(X[:, j] == 0):
+                X[:, j] = rng.random(n).astype(T)
+    AXb = np.zeros_like(X)
+    BXb = np.zeros_like(X) if generalized else X
+    R = np.zeros_like(X); AR = np.zeros_like(X); BR = np.zeros_like(X) if generalized else None
+    Pb = np.zeros_like(X); AP = np.zeros_like(X); BP = np.zeros_like(X) if generalized else None
+    ritz = np.zeros(3 * sizeX, dtype=T)
+    residuals = np.full(sizeX, np.nan, dtype=_real_dtype(T))            # :477
+    mask = np.ones(sizeX, dtype=bool)
+    trace = []
+    iteration = 1
+    bs = sizeX
+
+    def precond(blk):                                                   # RPreconditioner :236-242
+        if P is not None and not isinstance(P, Identity):
+            for j in range(blk.shape[1]):
+                col = np.ascontiguousarray(blk[:, j])
+                blk[:, j] = P.ldiv3(np.empty_like(col), col)
+
+    def eig_select(gA, gB, subdim):                                     # sub_problem! :607-627
+        if gB is None:
+            vals, vecs = sla.eigh(gA[:subdim, :subdim])
+        else:
+            vals, vecs = sla.eigh(gA[:subdim, :subdim], gB[:subdim, :subdim])
+        perm = np.argsort(-vals if largest else vals, kind="stable")[:sizeX]   # partialsortperm!(...; rev=largest)
+        ritz[:sizeX] = vals[perm]
+        return vecs[:, perm].astype(T)
+
+    def residuals_():                                                   # residuals! :533-547
+        nonlocal R
+        R = AXb - BXb * ritz[:sizeX][None, :]
+        for j in range(sizeX):
+            residuals[j] = np.sqrt(np.sum((R[:, j] * R[:, j].conj()).real, dtype=R.dtype))
+
+    while iteration <= maxiter:                                         # :880
+        if iteration == 1:                                              # :695-703
+            if generalized:
+                BXb = np.asfortranarray(mul(B, X))
+            _cholqr(X, BXb, update_BX=True, generalized=generalized)
+            if not generalized:
+                BXb = X
+            AXb = np.asfortranarray(mul(A, X))
+            XAX = X.conj().T @ AXb
+            V = eig_select(XAX, None, sizeX)
+            X[...] = X @ V                                              # update_X_P!(0, 0) :629-690
+            AXb = AXb @ V
+            if generalized:
+                BXb = BXb @ V
+            else:
+                BXb = X
+            residuals_()
+        else:
+            aR = np.array(R[:, mask], order="F")                        # update_active! :557-562
+            if iteration > 2:
+                aP = np.array(Pb[:, mask], order="F")
+                aAP = np.array(AP[:, mask], order="F")
+                aBP = np.array(BP[:, mask], order="F") if generalized else aP
+            precond(aR)                                                 # precond_constr! :564-569
+            aBR = np.asfortranarray(mul(B, aR)) if generalized else aR  # ortho_AB_mul_X! :524-532
+            _cholqr(aR, aBR, update_BX=True, generalized=generalized)
+            aAR = np.asfortranarray(mul(A, aR))
+            if iteration > 2:
+                _cholqr(aP, aBP, AX=aAP, update_AX=True, update_BX=True, generalized=generalized)   # :733
+            n1, n2 = sizeX, bs
+            n3 = bs if iteration > 2 else 0
+            sub = n1 + n2 + n3
+            gA = np.zeros((sub, sub), dtype=T)
+            gB = np.zeros((sub, sub), dtype=T)
+            xr, rr, pr = slice(0, n1), slice(n1, n1 + n2), slice(n1 + n2, sub)
+            gA[xr, xr] = np.diag(ritz[:n1])                             # BlockGram functor :282-307
+            gA[rr, rr] = aR.conj().T @ aAR                              # RAR :266
+            gA[xr, rr] = X.conj().T @ aAR                               # XAR :265
+            gA[rr, xr] = gA[xr, rr].conj().T
+            gB[xr, xr] = np.eye(n1)                                     # normalized :308-338
+            gB[rr, rr] = np.eye(n2)
+            gB[xr, rr] = X.conj().T @ aBR                               # XBR :270
+            gB[rr, xr] = gB[xr, rr].conj().T
+            if n3:
+                gA[pr, pr] = aP.conj().T @ aAP                          # PAP :268
+                gA[rr, pr] = aAR.conj().T @ aP                          # RAP :267
+                gA[xr, pr] = X.conj().T @ aAP                           # XAP :264
+                gA[pr, rr] = gA[rr, pr].conj().T
+                gA[pr, xr] = gA[xr, pr].conj().T
+                gB[pr, pr] = np.eye(n3)
+                gB[rr, pr] = aBR.conj().T @ aP                          # RBP :271
+                gB[xr, pr] = X.conj().T @ aBP                           # XBP :269
+                gB[pr, rr] = gB[rr, pr].conj().T
+                gB[pr, xr] = gB[xr, pr].conj().T
+            V = eig_select(gA, gB, sub)
+            Vx, Vr, Vp = V[xr, :], V[rr, :], V[pr, :]
+            Pb = aR @ Vr                                                # update_X_P! :645-651
+            AP = aAR @ Vr
+            if generalized:
+                BP = aBR @ Vr
+            if n3:
+                Pb = Pb + aP @ Vp                                       # :652-663
+                AP = AP + aAP @ Vp
+                if generalized:
+                    BP = BP + aBP @ Vp
+            X[...] = X @ Vx + Pb                                        # :664-689
+            AXb = AXb @ Vx + AP
+            if generalized:
+                BXb = BXb @ Vx + BP
+            else:
+                BXb = X
+            residuals_()
+        mask = residuals > tol                                          # update_mask! :549-555
+        if fixed_iterations:
+            mask[:] = True
+        bs = int(mask.sum())
+        if log:
+            trace.append((iteration, residuals.copy(), ritz[:sizeX].copy()))
+        if bs == 0:                                                     # :885
+            break
+        iteration += 1                                                  # :886
+    lam = ritz[:sizeX].copy()
+    return LOBPCGResults(lam, X, tol, residuals.copy(), iteration, maxiter, bool(np.all(residuals <= tol)), trace)

@@ -1,0 +1,79 @@
+"""Worker for the multi-GPU parity test; launched by tests/test_gpu_multi.py through torchrun
+(one process per GPU, NCCL).  Every rank owns a z-slab of laplace_matrix(Float64, N, 3); the
+row-partitioned cg! must reproduce the single-GPU cg! (run on rank 0 on the global matrix):
+same iteration count, residual history and solution within 1e-10 relative (only the summation order
+of the two global dots and of the halo rows differs)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 48
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import iterativesolvers_jl_b200 as isb
+    ctx = isb.Context.distributed(local)
+    n = N ** 3
+    # uneven slabs on purpose
+    cuts = [0] + [int(round(N * (r + 1) / world + (0.3 if r % 2 == 0 and r + 1 < world else 0))) for r in range(world)]
+    cuts[-1] = N
+    offs = np.array([c * N * N for c in cuts], dtype=np.int64)
+    lo, m = int(offs[rank]), int(offs[rank + 1] - offs[rank])
+    rng = np.random.default_rng(1234321)
+    b_global = rng.standard_normal(n)
+    b_global /= np.linalg.norm(b_global)
+
+    # (1) operator from a host CSR slab with global columns (general path), (2) on-device generator
+    rp, ci, va = isb.laplace_csr_slab(np.float64, N, 3, lo, m)
+    plan = isb.HaloPlan(rank, world, offs).scan_csr(rp, ci).exchange()
+    A1 = isb.B200CSR.from_csr_slab(rp, ci, va, n, lo, 0, plan, ctx)
+    plan2 = isb.HaloPlan(rank, world, offs).scan_laplacian(N, 3).exchange()
+    A2 = isb.B200CSR.laplacian(N, 3, np.float64, lo, m, plan2, ctx)
+    assert A1.n_halo == A2.n_halo and A1.nnz == A2.nnz
+    r1, c1, v1 = A1.download()
+    r2, c2, v2 = A2.download()
+    assert np.array_equal(r1, r2) and np.array_equal(c1, c2) and np.array_equal(v1, v2)
+
+    # distributed SpMV == slab of the global SpMV (bitwise: same per-row order)
+    xg = rng.standard_normal(n)
+    y_loc = A1 @ xg[lo:lo + m]
+    results = {}
+    for name, A in (("slab", A1), ("generated", A2)):
+        x_loc = np.zeros(m)
+        x_loc, h = isb.cg_(x_loc, A, b_global[lo:lo + m].copy(), initially_zero=True, log=True, reltol=1e-9)
+        results[name] = (x_loc, h)
+
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (y_loc, results["slab"][0], results["generated"][0]))
+    if rank == 0:
+        ctx1 = isb.Context(local)
+        cp, rv, nz, shape = isb.laplace_matrix(np.float64, N, 3, base=1)
+        Ag = isb.B200CSR.from_csc_arrays(cp, rv, nz, shape, base=1, ctx=ctx1)
+        y_ref = Ag @ xg
+        y_dist = np.concatenate([g[0] for g in gathered])
+        assert np.array_equal(y_dist, y_ref), np.abs(y_dist - y_ref).max()
+        xs, hs = isb.cg(Ag, b_global, log=True, reltol=1e-9)
+        for idx, name in ((1, "slab"), (2, "generated")):
+            xd = np.concatenate([g[idx] for g in gathered])
+            h = results[name][1]
+            assert h.isconverged and h.niters == hs.niters and h.mvps == hs.mvps, (h.niters, hs.niters)
+            hist_err = float(np.max(np.abs(h["resnorm"] - hs["resnorm"]) / hs["resnorm"]))
+            x_err = float(np.linalg.norm(xd - xs) / np.linalg.norm(xs))
+            assert hist_err <= 1e-10 and x_err <= 1e-10, (name, hist_err, x_err)
+            print(f"{name}: world={world} N={N} iters={h.niters} hist_err={hist_err:.2e} x_err={x_err:.2e}")
+        print("DIST_OK")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

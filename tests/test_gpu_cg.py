@@ -110,7 +110,7 @@ def test_blas1(isb):
     assert L.b200_nrm2(ctx._h, n, xd._p, 0, C.byref(out)) == 0
     assert out.value == pytest.approx(float(np.linalg.norm(x)), rel=1e-13)
     assert L.b200_axpby(ctx._h, n, 2.5, xd._p, -0.5, yd._p, 0) == 0
-    np.testing.assert_allclose(yd.numpy(), 2.5 * x - 0.5 * y, rtol=1e-15)
+    np.testing.assert_allclose(yd.numpy(), 2.5 * x - 0.5 * y, rtol=1e-15, atol=1e-15)   # FMA contraction
     assert L.b200_scal(ctx._h, n, 3.0, xd._p, 0) == 0
     np.testing.assert_array_equal(xd.numpy(), 3.0 * x)
     # determinism of the reduction
