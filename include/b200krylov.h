@@ -287,6 +287,13 @@ B200_API int b200_lobpcg_solve(b200_ctx *ctx, const b200_csr *A, void *X_dev, in
                                const b200_lobpcg_opts *opts, b200_lobpcg_result *res, double *lambda_host,
                                double *resnorm_host);
 
+/* Host-side dense helpers used by the engines for their O(blocksize^3) pieces (fp64, column-major,
+ * n <= 64): eigen!(Hermitian(A)[, Hermitian(B)]) -- eigenvalues ascending in w, eigenvectors in the
+ * columns of Z with Z'BZ = I (reference src/lobpcg.jl:615,622 -> LAPACK syevd / sygvd).  B may be NULL.
+ * Returns 0; B200_ERR_BREAKDOWN if B is not positive definite or the iteration does not converge.
+ * Exposed so that the CPU test-suite can pin them against LAPACK. */
+B200_API int b200_dense_sygv_host(int n, const double *A, const double *B, double *w, double *Z);
+
 #ifdef __cplusplus
 }
 #endif

@@ -165,13 +165,13 @@ struct CgDotEpi {
 template <typename T, int LPR>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
     k_cg_spmv_dot_stream(const int *__restrict__ rowptr, const int *__restrict__ colind, const T *__restrict__ vals,
-                         XView<T> xv, int64_t m, int W, T *__restrict__ c, CgScal *s, double *partials,
+                         XView<T> xv, int64_t m, T *__restrict__ c, CgScal *s, double *partials,
                          unsigned int *ticket, int single_gpu) {
   if (s->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double red[kStreamThreads / 32];
   CgDotEpi<T> epi{c, xv.x, 0.0};
-  spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, m, W, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw));
+  spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, m, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw));
   const double acc = block_sum<kStreamThreads>(epi.acc, red);
   double total;
   if (grid_reduce_finish<kStreamThreads>(acc, partials, ticket, red, &total) && threadIdx.x == 0)
@@ -255,7 +255,6 @@ struct CgEngine {
     if (use_stream(ctx, A)) {
       const int grid = stream_grid_size(ctx, A);
       const size_t smem = sizeof(StreamSmem<T>);
-      const int W = stream_window_w(ctx, A, u);
       ProfScope prof(ctx, 0);
 #define LAUNCH(L)                                                                                                    \
   do {                                                                                                               \
@@ -266,7 +265,7 @@ struct CgEngine {
       attr_set = true;                                                                                               \
     }                                                                                                                \
     k_cg_spmv_dot_stream<T, L><<<grid, kStreamThreads, smem, ctx->stream>>>(                                        \
-        A->rowptr, A->colind, (const T *)A->vals, xv, n, W, c, s, ctx->red.partials, ctx->red.ticket, single);       \
+        A->rowptr, A->colind, (const T *)A->vals, xv, n, c, s, ctx->red.partials, ctx->red.ticket, single);          \
   } while (0)
       switch (A->stream_lpr) {
         case 1: LAUNCH(1); break;

@@ -82,9 +82,7 @@ struct b200_ctx {
   double *d_scalars = nullptr;   // small device scratch for scalar results (64 doubles)
   double *h_scalars = nullptr;   // pinned host mirror (64 doubles)
   int *h_flags = nullptr;        // pinned host flags (16 ints)
-  int opt_spmv_kernel = 0;       // b200_ctx_set_option("spmv_kernel"): 0 auto, 1 sub-warp per row, 2 TMA stream
-  int opt_stream_window = 1;     // b200_ctx_set_option("stream_window"): stage the x window in shared memory
-  // optional per-kernel-class event timing (b200_ctx_profile_*)
+  int opt_spmv_kernel = 0;       // b200_ctx_set_option("spmv_kernel"): 0 auto, 1 sub-warp per row, 2 TMA stream  // optional per-kernel-class event timing (b200_ctx_profile_*)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;     // pool of event pairs
   std::vector<int> prof_slot;           // slot of each recorded pair

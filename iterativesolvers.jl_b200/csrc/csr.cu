@@ -313,29 +313,6 @@ __global__ void k_tile_max(const int *__restrict__ rowptr, int64_t m, int R, int
   if ((threadIdx.x & 31) == 0) atomicMax(out, local);
 }
 
-// out[i] = number of nonzeros with |col - row| <= {16, 64, 256, 512}[i] (own columns only)
-__global__ void k_band_profile(const int *__restrict__ rowptr, const int *__restrict__ colind, int64_t m,
-                               unsigned long long *__restrict__ out) {
-  unsigned int c[4] = {0, 0, 0, 0};
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
-    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
-      const int64_t d = (int64_t)colind[k] - i;
-      const int64_t a = d < 0 ? -d : d;
-      if (colind[k] < m) {
-        c[0] += a <= 16;
-        c[1] += a <= 64;
-        c[2] += a <= 256;
-        c[3] += a <= 512;
-      }
-    }
-  }
-  for (int j = 0; j < 4; ++j) {
-    unsigned int v = c[j];
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&out[j], (unsigned long long)v);
-  }
-}
-
 template <typename T>
 __global__ void k_pack(const int *__restrict__ idx, const T *__restrict__ x, int64_t n, T *__restrict__ out) {
   for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
@@ -361,10 +338,8 @@ int finish_operator(b200_ctx *ctx, b200_csr *A, const b200_halo_plan *plan) {
   B200_CUDA(cudaStreamSynchronize(ctx->stream));
   A->max_row_nnz = ctx->h_flags[0];
   A->avg_row_nnz = A->m_local ? (double)A->nnz / (double)A->m_local : 0.0;
-  // TMA-streamed kernel (spmv_stream.cuh): smallest lanes-per-row whose 512/LPR-row tiles hold <= 4096
-  // nonzeros, and the half-width W of the x window staged in shared memory
+  // TMA-streamed kernel (spmv_stream.cuh): smallest lanes-per-row whose 512/LPR-row tiles hold <= 4096 nonzeros
   A->stream_lpr = 0;
-  A->stream_w = 0;
   if (A->m_local > 0) {
     for (int l = 0; l < 6; ++l) {
       B200_CUDA(cudaMemsetAsync(d_max + 1 + l, 0, sizeof(int), ctx->stream));
@@ -378,29 +353,6 @@ int finish_operator(b200_ctx *ctx, b200_csr *A, const b200_halo_plan *plan) {
         A->stream_lpr = 1 << l;
         break;
       }
-  }
-  if (A->stream_lpr > 0 && A->nnz > 0) {
-    // band profile: how many nonzeros lie within w of the diagonal, w in {16, 64, 256, 512}
-    unsigned long long *d_cnt = reinterpret_cast<unsigned long long *>(ctx->d_scalars + 16);
-    B200_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 4, ctx->stream));
-    k_band_profile<<<grid_for(ctx, A->m_local), 256, 0, ctx->stream>>>(A->rowptr, A->colind, A->m_local, d_cnt);
-    B200_LAUNCH_CHECK(ctx);
-    unsigned long long cnt[4];
-    B200_CUDA(cudaMemcpyAsync(cnt, d_cnt, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream));
-    B200_CUDA(cudaStreamSynchronize(ctx->stream));
-    const int cand[4] = {16, 64, 256, 512};
-    const int R = 512 / A->stream_lpr;
-    int best = -1;
-    for (int i = 0; i < 4; ++i)
-      if (R + 2 * cand[i] <= 1536) best = i;
-    if (best >= 0 && (double)cnt[best] >= 0.3 * (double)A->nnz) {
-      // smallest window that captures (almost) as much as the largest admissible one
-      int pick = best;
-      for (int i = best; i >= 0; --i)
-        if ((double)cnt[i] >= 0.98 * (double)cnt[best]) pick = i;
-      A->stream_w = cand[pick];
-    }
-    B200_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 4, ctx->stream));
   }
   B200_CUDA(cudaMemsetAsync(d_max, 0, sizeof(double) * 8, ctx->stream));
   // halo exchange lists

@@ -24,7 +24,6 @@ using b200::kRowptrPad;
 struct b200_csr {
   b200_ctx *ctx = nullptr;
   int stream_lpr = 0;      // lanes per row of the TMA-streamed kernel; 0 = tiles do not fit, use the sub-warp kernel
-  int stream_w = 0;        // half-width of the x window staged in shared memory (0 = no window)
   int dtype = B200_F64;
   int64_t m_local = 0, n_global = 0, row_begin = 0, nnz = 0, n_halo = 0;
   int *rowptr = nullptr;   // m_local+1

@@ -179,10 +179,6 @@ int b200_ctx_set_option(b200_ctx *c, const char *name, int64_t value) {
     c->opt_spmv_kernel = (int)value;
     return B200_OK;
   }
-  if (strcmp(name, "stream_window") == 0) {
-    c->opt_stream_window = value != 0;
-    return B200_OK;
-  }
   set_error("unknown option `%s`", name);
   return B200_ERR_INVALID;
 }

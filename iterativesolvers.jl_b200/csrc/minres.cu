@@ -8,7 +8,7 @@
 // The vector "rotation" of :147-148 is a pointer swap done by the host (it is unconditional).
 // Algorithmic bytes per iteration: nnz*(V+4) + (n+1)*4 + 14*n*V.
 #include "blas1.cuh"
-#include "spmv.cuh"
+#include "spmv_stream.cuh"
 
 using namespace b200;
 
@@ -164,6 +164,37 @@ __global__ void __launch_bounds__(kThreads) k_mr_spmv(const int *__restrict__ ro
     mr_finish(MR_PROJ, m, total, nullptr, single);
 }
 
+// Ka, TMA-streamed form (spmv_stream.cuh)
+template <typename T>
+struct MrEpi {
+  T *__restrict__ v_next;
+  const T *__restrict__ v_prev;
+  const T *__restrict__ v_curr;
+  T h2;
+  bool use_prev;
+  double acc;
+  __device__ __forceinline__ void operator()(int64_t row, T t) {
+    if (use_prev) t = t - h2 * v_prev[row];
+    v_next[row] = t;
+    acc += (double)v_curr[row] * (double)t;
+  }
+};
+template <typename T, int LPR>
+__global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
+    k_mr_spmv_stream(const int *__restrict__ rowptr, const int *__restrict__ colind, const T *__restrict__ vals,
+                     XView<T> xv, const T *__restrict__ v_prev, T *__restrict__ v_next, int64_t n, MrScal *m,
+                     double *partials, unsigned int *ticket, int single) {
+  if (m->done) return;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double red[kStreamThreads / 32];
+  MrEpi<T> epi{v_next, v_prev, xv.x, (T)m->H[1], m->iteration > 1, 0.0};
+  spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, n, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw));
+  const double acc = block_sum<kStreamThreads>(epi.acc, red);
+  double total;
+  if (grid_reduce_finish<kStreamThreads>(acc, partials, ticket, red, &total) && threadIdx.x == 0)
+    mr_finish(MR_PROJ, m, total, nullptr, single);
+}
+
 // Kb
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_mr_orth(const T *__restrict__ v_curr, T *__restrict__ v_next, int64_t n,
@@ -281,9 +312,34 @@ int minres_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200_m
     for (int64_t it = 0; it < batch; ++it) {
       B200_TRY(halo_exchange(ctx, A, v_curr));
       XView<T> xv = make_xview<T>(A, v_curr);
-      {
+      if (use_stream(ctx, A)) {
+        const int grid = stream_grid_size(ctx, A);
+        const size_t smem = sizeof(StreamSmem<T>);
         ProfScope prof(ctx, 0);
-#define LAUNCH(L)                                                                                             \
+#define LAUNCH(L)                                                                                                  \
+  do {                                                                                                             \
+    static bool attr_set = false;                                                                                  \
+    if (!attr_set) {                                                                                               \
+      B200_CUDA(cudaFuncSetAttribute(k_mr_spmv_stream<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                     (int)smem));                                                                  \
+      attr_set = true;                                                                                             \
+    }                                                                                                              \
+    k_mr_spmv_stream<T, L><<<grid, kStreamThreads, smem, st>>>(A->rowptr, A->colind, (const T *)A->vals, xv,       \
+                                                                v_prev, v_next, n, m, ctx->red.partials,           \
+                                                                ctx->red.ticket, single);                          \
+  } while (0)
+        switch (A->stream_lpr) {
+          case 1: LAUNCH(1); break;
+          case 2: LAUNCH(2); break;
+          case 4: LAUNCH(4); break;
+          case 8: LAUNCH(8); break;
+          case 16: LAUNCH(16); break;
+          default: LAUNCH(32); break;
+        }
+#undef LAUNCH
+      } else {
+        ProfScope prof(ctx, 0);
+#define LAUNCH(L)                                                                                            \
   k_mr_spmv<T, L><<<gs, kThreads, 0, st>>>(A->rowptr, A->colind, (const T *)A->vals, xv, v_prev, v_next, n, m, \
                                            ctx->red.partials, ctx->red.ticket, single)
         switch (lpr) {

@@ -72,10 +72,10 @@ struct StoreEpi {
 template <typename T, int LPR>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
     k_spmv_stream(const int *__restrict__ rowptr, const int *__restrict__ colind, const T *__restrict__ vals,
-                  XView<T> xv, int64_t m, int W, T *__restrict__ y) {
+                  XView<T> xv, int64_t m, T *__restrict__ y) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StoreEpi<T> epi{y};
-  spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, m, W, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw));
+  spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, m, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw));
 }
 
 template <typename T>
@@ -83,7 +83,6 @@ int launch_spmv_stream(b200_ctx *ctx, const b200_csr *A, const void *x, void *y)
   XView<T> xv = make_xview<T>(A, x);
   const int grid = stream_grid_size(ctx, A);
   const size_t smem = sizeof(StreamSmem<T>);
-  const int W = stream_window_w(ctx, A, x);
 #define LAUNCH(L)                                                                                                 \
   do {                                                                                                            \
     static bool attr_set = false;                                                                                 \
@@ -92,7 +91,7 @@ int launch_spmv_stream(b200_ctx *ctx, const b200_csr *A, const void *x, void *y)
       attr_set = true;                                                                                            \
     }                                                                                                             \
     k_spmv_stream<T, L><<<grid, kStreamThreads, smem, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals,   \
-                                                                     xv, A->m_local, W, (T *)y);                 \
+                                                                     xv, A->m_local, (T *)y);                    \
   } while (0)
   switch (A->stream_lpr) {
     case 1: LAUNCH(1); break;

@@ -3,24 +3,25 @@
 // Why: with ~7 nonzeros per row a "warp(-slice) per row" kernel is latency-bound: every row costs a
 // dependent chain rowptr -> (colind, vals) -> x[col] with one row in flight per lane group
 // (measured: 2.3 TB/s = 35 % of the B200's HBM peak).  Here the matrix is consumed as what it is in
-// HBM -- three contiguous streams -- and the x gather is served from shared memory where possible:
+// HBM -- three contiguous streams -- and only the x gather stays a per-thread load:
 //
 //   * rows are cut into uniform tiles of R = 512/LPR rows; the nonzeros of a tile are one contiguous
 //     range of vals/colind, the row pointers one contiguous range of rowptr;
-//   * a producer warp (one elected lane) moves the three ranges of tile t+STAGES-1 into a shared-memory
-//     ring with cp.async.bulk (the TMA engine; SASS: UBLKCP) while the 16 consumer warps work on tile t;
-//     completion is tracked by mbarriers (full[stage]: expect_tx bytes; empty[stage]: one arrive per
-//     consumer warp).  The matrix copies carry an L2 evict-first policy so the 12 B/nnz stream does not
+//   * a producer warp (one elected lane) moves the three ranges of the next tiles into a 4-stage
+//     shared-memory ring with cp.async.bulk (the TMA engine; SASS: UBLKCP); completion is tracked by
+//     mbarriers (full[stage]: expect_tx bytes; empty[stage]: one arrive per consumer warp of the group
+//     that owns the tile).  The copies carry an L2 evict-first policy so the 12 B/nnz stream does not
 //     evict x from L2;
-//   * the same stage also receives the x WINDOW [r0-W, r1+W) of the tile by TMA: every column within W
-//     of the diagonal (for a 7-point stencil with N <= 512: the +-1 and +-N neighbours, 5 of 7 gathers)
-//     is then a shared-memory read; columns outside the window (the +-N^2 planes, halo columns) are
-//     global loads that hit L1/L2.  W is picked per operator from the band profile of the matrix
-//     (first ncu capture without the window: L2->SM traffic 2.2 GB per SpMV for x alone, L2-bound);
 //   * consumers read rowptr/colind/vals from shared memory (no dependent global loads) and issue all x
-//     gathers of a row back to back (8 in flight per thread);
-//   * the grid is persistent: 1 CTA per SM, tiles interleaved across CTAs (t = blockIdx, +gridDim, ..)
-//     so that all resident CTAs sweep neighbouring rows and the far x planes stay in L2.
+//     gathers of their rows back to back; x comes from L1/L2;
+//   * the x gather of a row ends in a DRAM miss roughly once per row (first touch of the leading stencil
+//     plane), so a tile's consumer latency is a loaded DRAM round trip (~2500 clk): the first streamed
+//     version (one tile in consumer flight per CTA, 512 rows per SM) was bound by exactly that --
+//     ncu: DRAM 65 %, L2 44 %, issue 40 %, "long scoreboard" the top stall.  Therefore the 16 consumer
+//     warps form TWO groups that work on alternate tiles concurrently and every thread owns TWO rows:
+//     1024 rows (7168 gathers) in flight per SM while two more tiles are landing;
+//   * the grid is persistent: 1 CTA per SM, tiles interleaved across CTAs (k-th tile of CTA b is
+//     b + k*gridDim) so that all resident CTAs sweep neighbouring rows and the x planes stay in L2.
 //
 // LPR (lanes per row) = 1 for matrices whose tiles of 512 rows hold <= 4096 nonzeros (the 5/7-point
 // stencils), 2/4/../32 for denser rows; operators whose 16-row tiles exceed 4096 nonzeros fall back to
@@ -32,19 +33,20 @@
 
 namespace b200 {
 
-constexpr int kStreamConsumers = 512;                     // consumer threads (16 warps)
+constexpr int kStreamGroupThreads = 256;                  // consumer threads per group (8 warps)
+constexpr int kStreamGroups = 2;                          // groups working on alternate tiles
+constexpr int kStreamConsumers = kStreamGroupThreads * kStreamGroups;
 constexpr int kStreamThreads = kStreamConsumers + 32;     // + producer warp
+constexpr int kStreamTileRows = 512;                      // rows per tile at LPR == 1 (2 per thread)
 constexpr int kStreamNnzCap = 4096;                       // nonzeros per tile
-constexpr int kStreamXwCap = 1536;                        // elements of x staged per tile (R + 2W <= cap)
-constexpr int kStreamStages = 3;
+constexpr int kStreamStages = 4;
 constexpr int kStreamCtasPerSm = 1;
 
 template <typename T>
 struct alignas(128) StreamStage {
   T val[kStreamNnzCap + 8];
-  T xw[kStreamXwCap];
   int col[kStreamNnzCap + 8];
-  int rp[kStreamConsumers + 8];
+  int rp[kStreamTileRows + 8];
 };
 template <typename T>
 struct StreamSmem {
@@ -87,33 +89,20 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
       : "memory");
 }
 
-// x window of tile [r0, r1): elements [lo, lo+cnt) of the own slab; cnt is a multiple of 4 (16 B)
-__device__ __forceinline__ void stream_window(int64_t r0, int64_t r1, int64_t m, int W, int &lo, int &cnt) {
-  if (W < 0) {
-    lo = 0;
-    cnt = 0;
-    return;
-  }
-  const int64_t a = r0 - W > 0 ? r0 - W : 0;
-  const int64_t b = r1 + W < m ? r1 + W : m;
-  lo = (int)a;
-  cnt = (int)((b - a) & ~(int64_t)3);
-}
-
 // Runs over all tiles of this CTA.  `epi(row, value)` is called once per row by the lane that owns
 // the row result.  Must be called by all kStreamThreads threads of the block.
-// W: half-width of the x window (multiple of 4, R + 2W <= kStreamXwCap), or -1 for "no window".
 template <typename T, int LPR, typename XV, typename Epi>
 __device__ __forceinline__ void spmv_stream_tiles(const int *__restrict__ rowptr, const int *__restrict__ colind,
-                                                  const T *__restrict__ vals, const XV &xv, int64_t m, int W,
-                                                  Epi &epi, StreamSmem<T> *sm) {
-  constexpr int R = kStreamConsumers / LPR;     // rows per tile
+                                                  const T *__restrict__ vals, const XV &xv, int64_t m, Epi &epi,
+                                                  StreamSmem<T> *sm) {
+  constexpr int R = kStreamTileRows / LPR;          // rows per tile
+  constexpr int SLOTS = kStreamGroupThreads / LPR;  // row slots per group; each slot owns rows s and s+SLOTS
   const int tid = threadIdx.x;
   const int64_t ntiles = (m + R - 1) / R;
   if (tid == 0) {
     for (int s = 0; s < kStreamStages; ++s) {
       mbar_init(&sm->full[s], 1);
-      mbar_init(&sm->empty[s], kStreamConsumers / 32);
+      mbar_init(&sm->empty[s], kStreamGroupThreads / 32);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -121,96 +110,124 @@ __device__ __forceinline__ void spmv_stream_tiles(const int *__restrict__ rowptr
 
   if (tid >= kStreamConsumers) {
     // ------------------------------------------------------------ producer warp
-    const uint64_t pol_stream = policy_evict_first();
-    const uint64_t pol_keep = policy_evict_last();
-    int it = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const int s = it % kStreamStages;
-      const uint32_t ph = (uint32_t)((it / kStreamStages) & 1);
-      if (tid == kStreamConsumers) {
-        mbar_wait(&sm->empty[s], ph ^ 1u);
+    if (tid == kStreamConsumers) {
+      const uint64_t pol_stream = policy_evict_first();
+      int64_t t = blockIdx.x;
+      // bounds of the next tile are fetched one iteration ahead (off the critical path)
+      int k0 = 0, k1 = 0;
+      if (t < ntiles) {
+        const int64_t r0 = t * R, r1 = (r0 + R < m) ? (r0 + R) : m;
+        k0 = __ldg(rowptr + r0);
+        k1 = __ldg(rowptr + r1);
+      }
+      for (int it = 0; t < ntiles; ++it) {
+        const int s = it % kStreamStages;
+        const uint32_t ph = (uint32_t)((it / kStreamStages) & 1);
         const int64_t r0 = t * R;
-        const int64_t r1 = (r0 + R < m) ? (r0 + R) : m;
-        const int k0 = __ldg(rowptr + r0), k1 = __ldg(rowptr + r1);
+        const int64_t tn = t + gridDim.x;
+        int nk0 = 0, nk1 = 0;
+        if (tn < ntiles) {
+          const int64_t nr0 = tn * R, nr1 = (nr0 + R < m) ? (nr0 + R) : m;
+          nk0 = __ldg(rowptr + nr0);
+          nk1 = __ldg(rowptr + nr1);
+        }
+        mbar_wait(&sm->empty[s], ph ^ 1u);
         const int k0a = k0 & ~3;
         const uint32_t cnt = (uint32_t)(((k1 - k0a) + 3) & ~3);
         const uint32_t b_val = cnt * (uint32_t)sizeof(T), b_col = cnt * 4u, b_rp = (uint32_t)(R + 4) * 4u;
-        int wlo, wcnt;
-        stream_window(r0, r1, m, W, wlo, wcnt);
-        const uint32_t b_xw = (uint32_t)wcnt * (uint32_t)sizeof(T);
         StreamStage<T> *st = &sm->stage[s];
-        mbar_expect_tx(&sm->full[s], b_val + b_col + b_rp + b_xw);
+        mbar_expect_tx(&sm->full[s], b_val + b_col + b_rp);
         bulk_g2s(st->rp, rowptr + r0, b_rp, &sm->full[s], pol_stream);
         bulk_g2s(st->col, colind + k0a, b_col, &sm->full[s], pol_stream);
-        if (b_xw) bulk_g2s(st->xw, xv.x + wlo, b_xw, &sm->full[s], pol_keep);
         bulk_g2s(st->val, vals + k0a, b_val, &sm->full[s], pol_stream);
+        t = tn;
+        k0 = nk0;
+        k1 = nk1;
       }
-      __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------ consumers
-    const int sub = tid % LPR, rib = tid / LPR;
-    int it = 0;
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const int s = it % kStreamStages;
-      const uint32_t ph = (uint32_t)((it / kStreamStages) & 1);
+    // ------------------------------------------------------------ consumers: group g takes tiles k = g, g+2, ...
+    const int grp = tid / kStreamGroupThreads;
+    const int lt = tid % kStreamGroupThreads;
+    const int sub = lt % LPR, slot = lt / LPR;
+    for (int64_t k = grp;; k += kStreamGroups) {
+      const int64_t t = (int64_t)blockIdx.x + k * gridDim.x;
+      if (t >= ntiles) break;
+      const int s = (int)(k % kStreamStages);
+      const uint32_t ph = (uint32_t)((k / kStreamStages) & 1);
       const int64_t r0 = t * R;
-      const int64_t r1 = (r0 + R < m) ? (r0 + R) : m;
-      int wlo, wcnt;
-      stream_window(r0, r1, m, W, wlo, wcnt);
       mbar_wait(&sm->full[s], ph);
       const StreamStage<T> *st = &sm->stage[s];
-      const int64_t row = r0 + rib;
-      const bool valid = row < m;
       const int k0a = st->rp[0] & ~3;
-      int b = 0, e = 0;
-      if (valid) {
-        b = st->rp[rib] - k0a;
-        e = st->rp[rib + 1] - k0a;
+      int b[2], e[2];
+      bool valid[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int rib = slot + q * SLOTS;
+        valid[q] = r0 + rib < m;
+        b[q] = valid[q] ? st->rp[rib] - k0a : 0;
+        e[q] = valid[q] ? st->rp[rib + 1] - k0a : 0;
       }
-      // x[c]: shared-memory window first, L1/L2 otherwise
-      auto xget = [&](int c) -> T {
-        const unsigned d = (unsigned)(c - wlo);
-        return d < (unsigned)wcnt ? st->xw[d] : xv(c);
-      };
-      T acc = (T)0;
+      T acc[2] = {(T)0, (T)0};
       if constexpr (LPR == 1) {
-        // up to 8 gathers in flight; left-to-right, unfused multiply-add (see header comment)
-        for (int k = b; k < e; k += 8) {
-          T xa[8], va[8];
+        // 2 rows x up to 8 gathers in flight; left-to-right, unfused multiply-add (see header comment)
+        int kk0 = b[0], kk1 = b[1];
+        while (kk0 < e[0] || kk1 < e[1]) {
+          T xa[2][8];   // the gathers; vals are re-read from shared memory at multiply time (registers)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const bool on = k + j < e;
-            const int c = on ? st->col[k + j] : wlo;
-            va[j] = on ? st->val[k + j] : (T)0;
-            xa[j] = on ? xget(c) : (T)0;
+            const bool on0 = kk0 + j < e[0], on1 = kk1 + j < e[1];
+            const int c0 = on0 ? st->col[kk0 + j] : 0;
+            const int c1 = on1 ? st->col[kk1 + j] : 0;
+            xa[0][j] = on0 ? xv(c0) : (T)0;
+            xa[1][j] = on1 ? xv(c1) : (T)0;
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (k + j < e) {
-              if constexpr (sizeof(T) == 8) acc = __dadd_rn(acc, __dmul_rn(va[j], xa[j]));
-              else acc = __fadd_rn(acc, __fmul_rn(va[j], xa[j]));
+            if (kk0 + j < e[0]) {
+              if constexpr (sizeof(T) == 8) acc[0] = __dadd_rn(acc[0], __dmul_rn(st->val[kk0 + j], xa[0][j]));
+              else acc[0] = __fadd_rn(acc[0], __fmul_rn(st->val[kk0 + j], xa[0][j]));
+            }
+            if (kk1 + j < e[1]) {
+              if constexpr (sizeof(T) == 8) acc[1] = __dadd_rn(acc[1], __dmul_rn(st->val[kk1 + j], xa[1][j]));
+              else acc[1] = __fadd_rn(acc[1], __fmul_rn(st->val[kk1 + j], xa[1][j]));
             }
           }
+          kk0 += 8;
+          kk1 += 8;
         }
       } else {
-        for (int k = b + sub; k < e; k += 4 * LPR) {
-          T xa[4], va[4];
+        int kk0 = b[0] + sub, kk1 = b[1] + sub;
+        while (kk0 < e[0] || kk1 < e[1]) {
+          T xa[2][4], va[2][4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int kk = k + j * LPR;
-            const bool on = kk < e;
-            const int c = on ? st->col[kk] : wlo;
-            va[j] = on ? st->val[kk] : (T)0;
-            xa[j] = on ? xget(c) : (T)0;
+            const bool on0 = kk0 + j * LPR < e[0], on1 = kk1 + j * LPR < e[1];
+            const int c0 = on0 ? st->col[kk0 + j * LPR] : 0;
+            const int c1 = on1 ? st->col[kk1 + j * LPR] : 0;
+            va[0][j] = on0 ? st->val[kk0 + j * LPR] : (T)0;
+            va[1][j] = on1 ? st->val[kk1 + j * LPR] : (T)0;
+            xa[0][j] = on0 ? xv(c0) : (T)0;
+            xa[1][j] = on1 ? xv(c1) : (T)0;
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc += va[j] * xa[j];
+          for (int j = 0; j < 4; ++j) {
+            acc[0] += va[0][j] * xa[0][j];
+            acc[1] += va[1][j] * xa[1][j];
+          }
+          kk0 += 4 * LPR;
+          kk1 += 4 * LPR;
         }
 #pragma unroll
-        for (int o = LPR >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, LPR);
+        for (int o = LPR >> 1; o > 0; o >>= 1) {
+          acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], o, LPR);
+          acc[1] += __shfl_xor_sync(0xffffffffu, acc[1], o, LPR);
+        }
       }
-      if (valid && sub == 0) epi(row, acc);
+      if (sub == 0) {
+        if (valid[0]) epi(r0 + slot, acc[0]);
+        if (valid[1]) epi(r0 + slot + SLOTS, acc[1]);
+      }
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&sm->empty[s]);
     }
@@ -224,17 +241,10 @@ inline bool use_stream(const b200_ctx *ctx, const b200_csr *A) {
   return A->stream_lpr > 0 && ctx->opt_spmv_kernel != 1;
 }
 inline int stream_grid_size(const b200_ctx *ctx, const b200_csr *A) {
-  const int R = kStreamConsumers / A->stream_lpr;
+  const int R = kStreamTileRows / A->stream_lpr;
   const int64_t ntiles = (A->m_local + R - 1) / R;
   const int64_t cap = (int64_t)ctx->sm_count * kStreamCtasPerSm;
   return (int)(ntiles < cap ? ntiles : cap);
-}
-// half-width of the x window for a launch on vector x: the operator's choice, or -1 when the window
-// is disabled (option, or x not 16-byte aligned as the bulk copy requires)
-inline int stream_window_w(const b200_ctx *ctx, const b200_csr *A, const void *x) {
-  if (ctx->opt_stream_window == 0 || A->stream_w <= 0) return -1;
-  if ((reinterpret_cast<uintptr_t>(x) & 15u) != 0) return -1;
-  return A->stream_w;
 }
 
 }  // namespace b200
