@@ -1,0 +1,168 @@
+#!/usr/bin/env python
+"""bench_configs.py -- single-GPU throughput of the other BASELINE.json configs (not the driver's bench):
+
+    gmres     configs[2]: gmres!(restart=30) on advection_dominated(N=256), fp64, CGS and DGKS, fixed maxiter
+    lobpcg    configs[4]: lobpcg block=16 on laplace_matrix(Float32, 256, 3), fixed number of steps
+    minres    minres! on laplace_matrix(Float64, 256, 3), fixed maxiter
+    bicgstabl bicgstabl!(l=2) on advection_dominated(N=256), fixed max_mv_products
+    cg256     configs[1]: cg! on laplace_matrix(Float64, 256, 3)
+
+Each line is a JSON object with iterations/s, per-kernel-class CUDA-event times recorded inside the run
+(b200_ctx_profile_*), the algorithmic bytes and the achieved fraction of the measured
+HBM peak.  Used for profiles/ (ncu launch lists are taken with the same commands).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def prof_reset(L, ctx):
+    L.b200_ctx_profile_enable(ctx._h, 1)
+    for s in range(4):
+        L.b200_ctx_profile_read(ctx._h, s, None, None, 1)
+
+
+def prof_read(L, ctx):
+    out = {}
+    names = ["spmv_class", "vector_with_reduction", "vector_no_reduction", "other"]
+    for s in range(4):
+        t, c = C.c_double(), C.c_int64()
+        L.b200_ctx_profile_read(ctx._h, s, C.byref(t), C.byref(c), 1)
+        out[names[s]] = {"total_ms": t.value, "launches": c.value}
+    L.b200_ctx_profile_enable(ctx._h, 0)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", choices=["gmres", "lobpcg", "minres", "bicgstabl", "cg256"])
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=None)
+    ap.add_argument("--orth", default="cgs")
+    ap.add_argument("--reps", type=int, default=2)
+    args = ap.parse_args()
+    import torch
+    torch.cuda.set_device(0)
+    import iterativesolvers_jl_b200 as isb
+    ctx = isb.default_context()
+    L = isb.lib()
+    N = args.grid
+    n = N ** 3
+    nnz = 7 * N ** 3 - 6 * N ** 2
+    pk = peak()
+    rng = np.random.default_rng(1234321)
+    out = {"config": args.which, "grid": N, "n": n, "nnz": nnz, "peak_gbs": pk}
+
+    if args.which in ("gmres", "bicgstabl"):
+        cp, rv, nz, shape, b = isb.advection_dominated(N, 1000.0, base=1)
+        A = isb.B200CSR.from_csc_arrays(cp, rv, nz, shape, base=1, ctx=ctx)
+        del cp, rv, nz
+        bd = isb.DeviceArray.from_numpy(ctx, b)
+        xd = isb.DeviceArray.zeros(ctx, n)
+    if args.which == "gmres":
+        restart = 30
+        iters = args.iters or 90
+        V = 8
+        spmv_b = nnz * 12 + (n + 1) * 4 + 2 * n * V
+        # per cycle of `restart` inner iterations: sum_k (B_spmv + (2k+5) n V) + restart solution update + init!
+        cyc = sum(spmv_b + (2 * k + 5) * n * V for k in range(1, restart + 1)) + (restart + 2) * n * V + spmv_b + 6 * n * V
+        for rep in range(args.reps + 1):
+            L.b200_fill(ctx._h, n, 0.0, xd._p, 0)
+            if rep == 1:
+                prof_reset(L, ctx)
+            ctx.sync()
+            t0 = time.perf_counter()
+            x, h = isb.gmres_(xd, A, bd, restart=restart, maxiter=iters, orth_meth=args.orth, initially_zero=True,
+                              log=True, reltol=0.0)
+            ctx.sync()
+            dt = time.perf_counter() - t0
+        pr = prof_read(L, ctx)
+        out.update({"solver": f"gmres!(restart=30, orth_meth={args.orth})", "iters": h.niters, "seconds": dt,
+                    "iters_per_s": h.niters / dt, "mvps": h.mvps, "resnorm_first_last": [float(h["resnorm"][0]), float(h["resnorm"][-1])],
+                    "algorithmic_gb_per_cycle": cyc / 1e9,
+                    "achieved_gbs": cyc * (h.niters / restart) / dt / 1e9, "profile": pr})
+    elif args.which == "bicgstabl":
+        l = 2
+        mv = args.iters or 80
+        rsh = isb.DeviceArray.from_numpy(ctx, rng.random(n))
+        for rep in range(args.reps + 1):
+            L.b200_fill(ctx._h, n, 0.0, xd._p, 0)
+            if rep == 1:
+                prof_reset(L, ctx)
+            ctx.sync()
+            t0 = time.perf_counter()
+            x, h = isb.bicgstabl_(xd, A, bd, l, max_mv_products=mv, initial_zero=True, log=True, reltol=0.0, r_shadow=rsh)
+            ctx.sync()
+            dt = time.perf_counter() - t0
+        pr = prof_read(L, ctx)
+        out.update({"solver": "bicgstabl!(l=2)", "outer_iters": h.niters, "mvps": h.mvps, "seconds": dt,
+                    "mv_products_per_s": h.mvps / dt, "profile": pr})
+    elif args.which in ("minres", "cg256"):
+        A = isb.B200CSR.laplacian(N, 3, np.float64, ctx=ctx)
+        b = rng.standard_normal(n)
+        b /= np.linalg.norm(b)
+        bd = isb.DeviceArray.from_numpy(ctx, b)
+        xd = isb.DeviceArray.zeros(ctx, n)
+        iters = args.iters or 200
+        V = 8
+        per_it = nnz * 12 + (n + 1) * 4 + (14 if args.which == "minres" else 11) * n * V
+        for rep in range(args.reps + 1):
+            L.b200_fill(ctx._h, n, 0.0, xd._p, 0)
+            if rep == 1:
+                prof_reset(L, ctx)
+            ctx.sync()
+            t0 = time.perf_counter()
+            if args.which == "minres":
+                x, h = isb.minres_(xd, A, bd, maxiter=iters, initially_zero=True, log=True, reltol=0.0)
+            else:
+                x, h = isb.cg_(xd, A, bd, maxiter=iters, initially_zero=True, log=True, reltol=0.0, _fixed_iterations=True)
+            ctx.sync()
+            dt = time.perf_counter() - t0
+        pr = prof_read(L, ctx)
+        out.update({"solver": args.which, "iters": h.niters, "seconds": dt, "iters_per_s": h.niters / dt,
+                    "algorithmic_gb_per_iter": per_it / 1e9, "achieved_gbs": per_it * h.niters / dt / 1e9,
+                    "profile": pr})
+    else:  # lobpcg
+        bs = 16
+        A = isb.B200CSR.laplacian(N, 3, np.float32, ctx=ctx)
+        X0 = rng.random((n, bs), dtype=np.float32)
+        steps = args.iters or 10
+        V = 4
+        per_step = nnz * (V + 4) + (n + 1) * 4 + 26 * n * bs * V        # SURVEY 8d ideal
+        for rep in range(args.reps + 1):
+            Xd = isb.DeviceArray.from_numpy(ctx, X0)
+            if rep == 1:
+                prof_reset(L, ctx)
+            ctx.sync()
+            t0 = time.perf_counter()
+            r = isb.lobpcg(A, False, Xd, maxiter=steps, _fixed_iterations=True)
+            ctx.sync()
+            dt = time.perf_counter() - t0
+            Xd.free()
+        pr = prof_read(L, ctx)
+        out.update({"solver": "lobpcg(block=16, fp32, smallest)", "steps": steps, "seconds": dt, "steps_per_s": steps / dt,
+                    "lambda_min": float(np.min(r.lam)), "max_resnorm": float(np.max(r.residual_norms)),
+                    "algorithmic_gb_per_step_ideal": per_step / 1e9, "achieved_gbs_vs_ideal_bytes": per_step * steps / dt / 1e9,
+                    "profile": pr})
+    if "achieved_gbs" in out:
+        out["frac_of_measured_peak"] = out["achieved_gbs"] / pk
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -100,8 +100,13 @@ B200_API int b200_ctx_timer_stop(b200_ctx *ctx, float *ms);
 B200_API int b200_ctx_profile_enable(b200_ctx *ctx, int on);
 B200_API int b200_ctx_profile_read(b200_ctx *ctx, int slot, double *total_ms, int64_t *launches, int reset);
 /* Tuning knobs (do not change results beyond floating-point summation order):
- *   "spmv_kernel": 0 = auto, 1 = sub-warp-per-row kernel, 2 = TMA-streamed kernel (when the tiles fit) */
+ *   "spmv_kernel": 0 = auto, 1 = sub-warp-per-row kernel, 2 = TMA-streamed kernel (when the tiles fit)
+ *   "snake": 1 (default) = consecutive hot kernels of a solver sweep the rows in alternating directions so
+ *           that each starts on the data the previous one touched last (L2 reuse); 0 = always ascending
+ *   "comm": 0 = auto, 1 = NCCL collectives, 2 = NVLink peer-memory collectives fused into the kernels
+ *           (multi-GPU contexts; get "peer_ok" tells whether the peer buffers could be mapped) */
 B200_API int b200_ctx_set_option(b200_ctx *ctx, const char *name, int64_t value);
+B200_API int b200_ctx_get_option(const b200_ctx *ctx, const char *name, int64_t *value);
 /* sum over ranks (no-op for world==1); used by hosts for max/sum of small host scalars */
 B200_API int b200_ctx_allreduce_f64(b200_ctx *ctx, double *host_inout, int count, int op_max);
 B200_API int b200_ctx_barrier(b200_ctx *ctx);
@@ -167,6 +172,10 @@ B200_API int b200_halo_plan_destroy(b200_halo_plan *plan);
 B200_API int64_t b200_gen_laplace_nnz(int64_t N, int dims, int64_t row_begin, int64_t m_local);
 B200_API int64_t b200_gen_laplace_csc_i64(int64_t N, int dims, int base, int64_t *colptr, int64_t *rowval,
                                           double *nzval);
+/* advection_dominated(N, beta) of reference benchmark/advection_diffusion.jl:3-30 (matrix as CSC Int64 arrays and
+ * the right-hand side b, which may be NULL).  Returns nnz, or <0. */
+B200_API int64_t b200_gen_advection_csc_i64(int64_t N, double beta, int base, int64_t *colptr, int64_t *rowval,
+                                            double *nzval, double *b);
 B200_API int64_t b200_gen_laplace_csr_slab_i32(int64_t N, int dims, int64_t row_begin, int64_t m_local,
                                                int32_t *rowptr, int32_t *colind_global, double *vals);
 

@@ -82,6 +82,7 @@ SIGNATURES = {
     "b200_ctx_timer_start": (_INT, [_P]),
     "b200_ctx_timer_stop": (_INT, [_P, C.POINTER(C.c_float)]),
     "b200_ctx_set_option": (_INT, [_P, C.c_char_p, _I64]),
+    "b200_ctx_get_option": (_INT, [_P, C.c_char_p, C.POINTER(_I64)]),
     "b200_ctx_profile_enable": (_INT, [_P, _INT]),
     "b200_ctx_profile_read": (_INT, [_P, _INT, C.POINTER(_DBL), C.POINTER(_I64), _INT]),
     "b200_ctx_allreduce_f64": (_INT, [_P, C.POINTER(_DBL), _INT, _INT]),
@@ -112,6 +113,7 @@ SIGNATURES = {
     "b200_halo_plan_destroy": (_INT, [_P]),
     "b200_gen_laplace_nnz": (_I64, [_I64, _INT, _I64, _I64]),
     "b200_gen_laplace_csc_i64": (_I64, [_I64, _INT, _INT, _P, _P, _P]),
+    "b200_gen_advection_csc_i64": (_I64, [_I64, _DBL, _INT, _P, _P, _P, _P]),
     "b200_gen_laplace_csr_slab_i32": (_I64, [_I64, _INT, _I64, _I64, _P, _P, _P]),
     "b200_spmv": (_INT, [_P, _P, _P, _P]),
     "b200_spmm": (_INT, [_P, _P, _P, _I64, _P, _I64, _INT]),

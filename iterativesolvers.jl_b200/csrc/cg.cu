@@ -1,17 +1,26 @@
 // cg.cu -- the (P)CG engine: cg!(x, A, b; ...) of reference src/cg.jl:209-242 as fused device kernels.
 //
 // One CG iteration (reference src/cg.jl:43-66) = three stream-ordered launches, no host round trip:
-//   K1  u = r + beta*u                         (beta = residual^2/prev_residual^2, src/cg.jl:50-51)
-//   K2  c = A*u  fused with  dot(u,c)          (src/cg.jl:54-55)     <- the HBM-dominant kernel
-//   K3  x += alpha*u ; r -= alpha*c ; ||r||^2  (src/cg.jl:58-62)
+//   K1  x += alpha_prev*u ; u = r + beta*u     (src/cg.jl:58 of the previous step, :50-51; 5 vector passes)
+//   K2  c = A*u  fused with  dot(u,c), alpha   (src/cg.jl:54-55)     <- the HBM-dominant kernel
+//   K3  r -= alpha*c ; ||r||^2                 (src/cg.jl:59-62; 3 vector passes)
+// (the x update rides in the next K1 because that kernel streams u anyway: 10 vector passes + A per
+// iteration instead of the 11 of the algorithmic accounting below; values are identical to the reference
+// order of operations, x is just completed one launch later -- k_cg_flush_x closes the last step)
 // All scalars (residual, prev_residual, alpha, beta, tol, iteration, done) live in device memory
 // (struct CgScal); the reductions finish on the device (last-block ticket) and the same block does
 // the scalar bookkeeping, including the reference's termination test (src/cg.jl:36).  Kernels of
-// iterations enqueued after `done` is set return immediately, so the host only polls the flag every
+// iterations enqueued after `done` return immediately, so the host only polls the flag every
 // `check_every` iterations and results do not depend on that period.
 // Algorithmic bytes per iteration: nnz*(V+4) + (n+1)*4 + 11*n*V.
-// Multi-GPU: the two sums are ncclAllReduce'd (one double each) and a 1-thread kernel does the
-// bookkeeping; the halo exchange precedes K2.
+//
+// Multi-GPU (row slabs, one process per GPU), two interchangeable transports (option "comm"):
+//   * peer memory (default when the IPC mapping succeeded, peer.cuh): K1 is followed by k_halo_push
+//     (boundary values stored straight into the neighbours' halo segments over NVLink), K2 waits on the
+//     halo flags before its first gather, and the block that finishes a reduction performs the one-shot
+//     all-to-all allreduce itself -- 4 launches per iteration, no NCCL call, no scalar kernel;
+//   * NCCL: halo = pack kernel + grouped ncclSend/ncclRecv, each sum = ncclAllReduce of one double followed
+//     by a 1-thread bookkeeping kernel.
 #include "blas1.cuh"
 #include "spmv_stream.cuh"
 
@@ -27,8 +36,8 @@ struct CgScal {
   double rho;            // it.rho (PCGIterable)
   double rho_prev;
   double tol;
-  double sum;            // scratch: local/global sum of the reduction in flight
-  double sum2;
+  double sum;            // NCCL path: local/global sum of the reduction in flight
+  double alpha;          // alpha of the current iteration (set when dot(u,c) is known)
   double dot_uc;
   double abstol, reltol;
   long long iter;        // iterations completed
@@ -37,7 +46,20 @@ struct CgScal {
   int done;
   int fixed;             // bench: ignore convergence
   int breakdown;
+  int comm_error;
+  int pcg;               // PCGIterable (Jacobi Pl) instead of CGIterable
   int pad;
+};
+
+// how the grid-wide sum of one GPU becomes the global sum
+enum { COMM_SINGLE = 0, COMM_NCCL = 1, COMM_PEER = 2 };
+struct Comm {
+  int mode;
+  unsigned long long seq;        // allreduce sequence number (COMM_PEER)
+  unsigned long long halo_seq;   // halo sequence to wait for before the first gather (COMM_PEER, K2 only)
+  unsigned int halo_mask;        // ranks this GPU receives halo values from
+  int rev;                       // sweep the rows from the end (consecutive kernels alternate: L2 reuse)
+  PeerView pv;
 };
 
 // bookkeeping after ||r||^2 is known (src/cg.jl:61-62 + done() :36); single thread
@@ -68,14 +90,13 @@ __device__ __forceinline__ void cg_after_init_norm(CgScal *s, double rr) {
 
 enum { FIN_NONE = 0, FIN_INIT = 1, FIN_DOT = 2, FIN_NORM = 3, FIN_NORM_PCG = 4, FIN_RHO = 5 };
 
-__device__ __forceinline__ void cg_finish(int kind, CgScal *s, double total, double *hist, bool single_gpu) {
-  if (!single_gpu) {  // multi-GPU: leave the local sum for the allreduce + k_cg_scalar
-    s->sum = total;
-    return;
-  }
+__device__ __forceinline__ void cg_apply(int kind, CgScal *s, double total, double *hist) {
   switch (kind) {
     case FIN_INIT: cg_after_init_norm(s, total); break;
-    case FIN_DOT: s->dot_uc = total; break;
+    case FIN_DOT:                                    // alpha = residual^2 / dot(u,c)  (src/cg.jl:55; PCG :90)
+      s->dot_uc = total;
+      s->alpha = s->pcg ? s->rho / total : (s->residual * s->residual) / total;
+      break;
     case FIN_NORM: cg_after_norm(s, total, hist, false); break;
     case FIN_NORM_PCG: cg_after_norm(s, total, hist, true); break;
     case FIN_RHO: s->rho_prev = s->rho; s->rho = total; break;
@@ -83,16 +104,29 @@ __device__ __forceinline__ void cg_finish(int kind, CgScal *s, double total, dou
   }
 }
 
+// called by the single thread that holds the grid-wide sum of this GPU
+__device__ __forceinline__ void cg_finish(int kind, CgScal *s, double total, double *hist, const Comm &cm) {
+  if (cm.mode == COMM_NCCL) {   // the host enqueues ncclAllReduce(&s->sum) + k_cg_scalar next
+    s->sum = total;
+    return;
+  }
+  if (cm.mode == COMM_PEER) {
+    peer_allreduce_sum(cm.pv, &total, 1, cm.seq);
+    if (cm.pv.hdr[cm.pv.rank]->error) s->comm_error = 1;
+  }
+  cg_apply(kind, s, total, hist);
+}
+
 __global__ void k_cg_scalar(int kind, CgScal *s, double *hist) {
   if (kind != FIN_INIT && s->done) return;  // kernels of iterations past `done` did not produce a sum
-  cg_finish(kind, s, s->sum, hist, true);
+  cg_apply(kind, s, s->sum, hist);
 }
 
 // r = b - c (c = A*x) or r = b; u = 0; ||r||^2     (src/cg.jl:129-140)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_init(const T *__restrict__ b, const T *__restrict__ c, int has_c,
                                                       T *__restrict__ r, T *__restrict__ u, int64_t n, CgScal *s,
-                                                      double *partials, unsigned int *ticket, int single_gpu) {
+                                                      double *partials, unsigned int *ticket, Comm cm) {
   __shared__ double smem[kThreads / 32];
   double acc = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
@@ -105,33 +139,68 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(const T *__restrict__ b, c
   acc = block_sum<kThreads>(acc, smem);
   double total;
   if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x == 0)
-    cg_finish(FIN_INIT, s, total, nullptr, single_gpu);
+    cg_finish(FIN_INIT, s, total, nullptr, cm);
 }
 
-// K1: u = r + beta*u   (CG: beta = residual^2/prev_residual^2 ; PCG: u = c + (rho/rho_prev)*u)
+// K1: x += alpha_prev*u (the x update of the PREVIOUS iteration, src/cg.jl:58) ; u = r + beta*u (src/cg.jl:51)
+//     (CG: beta = residual^2/prev_residual^2 ; PCG: u = c + (rho/rho_prev)*u)
+// The x update is deferred by one kernel so that u is streamed once for both updates (10 instead of 11
+// vector passes per iteration); x_k is formed from the same operands as in the reference, one launch later,
+// and k_cg_flush_x applies the last one when the loop ends.
 template <typename T>
-__global__ void __launch_bounds__(kThreads) k_cg_update_u(const T *__restrict__ r, T *__restrict__ u, int64_t n,
-                                                          const CgScal *__restrict__ s, int pcg) {
+__global__ void __launch_bounds__(kThreads) k_cg_update_u(const T *__restrict__ r, T *__restrict__ u,
+                                                          T *__restrict__ x, int64_t n,
+                                                          const CgScal *__restrict__ s, int pcg, int rev) {
   if (s->done) return;
   const double beta_d = pcg ? s->rho / s->rho_prev
                             : (s->residual * s->residual) / (s->prev_residual * s->prev_residual);
   const T beta = (T)beta_d;
-  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    // r .+ beta .* u  -- no FMA contraction, as the reference's broadcast computes it
-    if constexpr (sizeof(T) == 8) u[i] = __dadd_rn(r[i], __dmul_rn(beta, u[i]));
-    else u[i] = __fadd_rn(r[i], __fmul_rn(beta, u[i]));
+  const T alpha = (T)s->alpha;
+  const bool upd_x = s->iter > 0;
+  for (int64_t j = blockIdx.x * (int64_t)kThreads + threadIdx.x; j < n; j += (int64_t)gridDim.x * kThreads) {
+    const int64_t i = rev ? n - 1 - j : j;
+    const T ui = u[i];
+    // x .+= alpha .* u ; r .+ beta .* u  -- no FMA contraction, as the reference's broadcasts compute them
+    if constexpr (sizeof(T) == 8) {
+      if (upd_x) x[i] = __dadd_rn(x[i], __dmul_rn(alpha, ui));
+      u[i] = __dadd_rn(r[i], __dmul_rn(beta, ui));
+    } else {
+      if (upd_x) x[i] = __fadd_rn(x[i], __fmul_rn(alpha, ui));
+      u[i] = __fadd_rn(r[i], __fmul_rn(beta, ui));
+    }
   }
 }
 
-// K2: c = A*u ; sum u.*c
+// the deferred x update of the last completed iteration
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_cg_flush_x(const T *__restrict__ u, T *__restrict__ x, int64_t n,
+                                                         const CgScal *__restrict__ s) {
+  if (s->iter <= 0) return;
+  const T alpha = (T)s->alpha;
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    if constexpr (sizeof(T) == 8) x[i] = __dadd_rn(x[i], __dmul_rn(alpha, u[i]));
+    else x[i] = __fadd_rn(x[i], __fmul_rn(alpha, u[i]));
+  }
+}
+
+// every CTA makes sure the neighbours' halo values of this iteration have landed (peer path)
+__device__ __forceinline__ void wait_halo(const Comm &cm) {
+  if (cm.mode == COMM_PEER && cm.halo_mask) {
+    if (threadIdx.x == 0) peer_wait_halo(cm.pv, cm.halo_mask, cm.halo_seq);
+    __syncthreads();
+  }
+}
+
+// K2 (sub-warp-per-row fallback): c = A*u ; sum u.*c
 template <typename T, int LPR>
 __global__ void __launch_bounds__(kThreads) k_cg_spmv_dot(const int *__restrict__ rowptr,
                                                           const int *__restrict__ colind,
                                                           const T *__restrict__ vals, XView<T> xv, int64_t m,
                                                           T *__restrict__ c, CgScal *s, double *partials,
-                                                          unsigned int *ticket, int single_gpu) {
+                                                          unsigned int *ticket, Comm cm) {
   if (s->done) return;
   __shared__ double smem[kThreads / 32];
+  wait_halo(cm);
   constexpr int ROWS = kThreads / LPR;
   const int sub = threadIdx.x % LPR;
   const int rib = threadIdx.x / LPR;
@@ -148,7 +217,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_spmv_dot(const int *__restrict_
   acc = block_sum<kThreads>(acc, smem);
   double total;
   if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x == 0)
-    cg_finish(FIN_DOT, s, total, nullptr, single_gpu);
+    cg_finish(FIN_DOT, s, total, nullptr, cm);
 }
 
 // K2, TMA-streamed form (spmv_stream.cuh): same result contract as k_cg_spmv_dot
@@ -166,53 +235,47 @@ template <typename T, int LPR>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
     k_cg_spmv_dot_stream(const int *__restrict__ rowptr, const int *__restrict__ colind, const T *__restrict__ vals,
                          XView<T> xv, int64_t m, T *__restrict__ c, CgScal *s, double *partials,
-                         unsigned int *ticket, int single_gpu) {
+                         unsigned int *ticket, Comm cm) {
   if (s->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double red[kStreamThreads / 32];
+  wait_halo(cm);
   CgDotEpi<T> epi{c, xv.x, 0.0};
-  spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, m, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw));
+  spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, m, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw), cm.rev != 0);
   const double acc = block_sum<kStreamThreads>(epi.acc, red);
   double total;
   if (grid_reduce_finish<kStreamThreads>(acc, partials, ticket, red, &total) && threadIdx.x == 0)
-    cg_finish(FIN_DOT, s, total, nullptr, single_gpu);
+    cg_finish(FIN_DOT, s, total, nullptr, cm);
 }
 
-// K3: x += alpha*u ; r -= alpha*c ; ||r||^2
+// K3: r -= alpha*c ; ||r||^2   (x += alpha*u is applied by the next K1 / k_cg_flush_x)
 template <typename T>
-__global__ void __launch_bounds__(kThreads) k_cg_update_xr(T *__restrict__ x, T *__restrict__ r,
-                                                           const T *__restrict__ u, const T *__restrict__ c,
-                                                           int64_t n, CgScal *s, double *hist, double *partials,
-                                                           unsigned int *ticket, int pcg, int single_gpu) {
+__global__ void __launch_bounds__(kThreads) k_cg_update_r(T *__restrict__ r, const T *__restrict__ c, int64_t n,
+                                                          CgScal *s, double *hist, double *partials,
+                                                          unsigned int *ticket, int pcg, Comm cm) {
   if (s->done) return;
   __shared__ double smem[kThreads / 32];
-  const double alpha_d = pcg ? s->rho / s->dot_uc : (s->residual * s->residual) / s->dot_uc;
-  const T alpha = (T)alpha_d;
+  const T alpha = (T)s->alpha;
   double acc = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    T xi, ri;
-    if constexpr (sizeof(T) == 8) {
-      xi = __dadd_rn(x[i], __dmul_rn(alpha, u[i]));
-      ri = __dsub_rn(r[i], __dmul_rn(alpha, c[i]));
-    } else {
-      xi = __fadd_rn(x[i], __fmul_rn(alpha, u[i]));
-      ri = __fsub_rn(r[i], __fmul_rn(alpha, c[i]));
-    }
-    x[i] = xi;
+  for (int64_t j = blockIdx.x * (int64_t)kThreads + threadIdx.x; j < n; j += (int64_t)gridDim.x * kThreads) {
+    const int64_t i = cm.rev ? n - 1 - j : j;
+    T ri;
+    if constexpr (sizeof(T) == 8) ri = __dsub_rn(r[i], __dmul_rn(alpha, c[i]));
+    else ri = __fsub_rn(r[i], __fmul_rn(alpha, c[i]));
     r[i] = ri;
     acc += (double)ri * (double)ri;
   }
   acc = block_sum<kThreads>(acc, smem);
   double total;
   if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x == 0)
-    cg_finish(pcg ? FIN_NORM_PCG : FIN_NORM, s, total, hist, single_gpu);
+    cg_finish(pcg ? FIN_NORM_PCG : FIN_NORM, s, total, hist, cm);
 }
 
 // PCG: c = r ./ d ; rho = dot(c, r)    (src/cg.jl:79-82, Jacobi ldiv!)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_pcg_precond(const T *__restrict__ d, const T *__restrict__ r,
                                                           T *__restrict__ c, int64_t n, CgScal *s, double *partials,
-                                                          unsigned int *ticket, int single_gpu) {
+                                                          unsigned int *ticket, Comm cm) {
   if (s->done) return;
   __shared__ double smem[kThreads / 32];
   double acc = 0.0;
@@ -225,7 +288,7 @@ __global__ void __launch_bounds__(kThreads) k_pcg_precond(const T *__restrict__ 
   acc = block_sum<kThreads>(acc, smem);
   double total;
   if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x == 0)
-    cg_finish(FIN_RHO, s, total, nullptr, single_gpu);
+    cg_finish(FIN_RHO, s, total, nullptr, cm);
 }
 
 template <typename T>
@@ -238,11 +301,37 @@ struct CgEngine {
   const T *jac;  // NULL => Identity
   CgScal *s;
   double *hist;
-  int single;
+  int mode;      // COMM_*
   int lpr, grid_vec, grid_spmv;
+  int sweep = 0;   // direction of the next hot kernel (toggled per launch when ctx->opt_snake)
+
+  int next_sweep() {
+    const int d = ctx->opt_snake ? sweep : 0;
+    sweep ^= 1;
+    return d;
+  }
+
+  // Comm descriptor for the next reduction (peer path: consumes one sequence number on every rank)
+  Comm comm(bool with_halo = false, int rev = 0) {
+    Comm cm;
+    cm.mode = mode;
+    cm.seq = 0;
+    cm.halo_seq = 0;
+    cm.halo_mask = 0;
+    cm.rev = rev;
+    if (mode == COMM_PEER) {
+      cm.pv = ctx->peer_view;
+      cm.seq = ++ctx->ar_seq;
+      if (with_halo) {
+        cm.halo_seq = ctx->halo_seq;
+        cm.halo_mask = A->recv_mask;
+      }
+    }
+    return cm;
+  }
 
   int after_reduce(int kind) {
-    if (single) return B200_OK;
+    if (mode != COMM_NCCL) return B200_OK;
     B200_TRY(allreduce_sum_dev(ctx, &s->sum, 1));
     k_cg_scalar<<<1, 1, 0, ctx->stream>>>(kind, s, hist);
     B200_LAUNCH_CHECK(ctx);
@@ -250,8 +339,15 @@ struct CgEngine {
   }
 
   int spmv_dot() {
-    B200_TRY(halo_exchange(ctx, A, u));
-    XView<T> xv = make_xview<T>(A, u);
+    const bool peer = mode == COMM_PEER;
+    if (peer) {
+      ctx->halo_seq += 1;
+      B200_TRY(halo_push(ctx, A, u, ctx->halo_seq, &s->done));
+    } else {
+      B200_TRY(halo_exchange(ctx, A, u));
+    }
+    XView<T> xv = make_xview<T>(A, u, peer);
+    const Comm cm = comm(true, next_sweep());
     if (use_stream(ctx, A)) {
       const int grid = stream_grid_size(ctx, A);
       const size_t smem = sizeof(StreamSmem<T>);
@@ -265,7 +361,7 @@ struct CgEngine {
       attr_set = true;                                                                                               \
     }                                                                                                                \
     k_cg_spmv_dot_stream<T, L><<<grid, kStreamThreads, smem, ctx->stream>>>(                                        \
-        A->rowptr, A->colind, (const T *)A->vals, xv, n, c, s, ctx->red.partials, ctx->red.ticket, single);          \
+        A->rowptr, A->colind, (const T *)A->vals, xv, n, c, s, ctx->red.partials, ctx->red.ticket, cm);              \
   } while (0)
       switch (A->stream_lpr) {
         case 1: LAUNCH(1); break;
@@ -277,17 +373,17 @@ struct CgEngine {
       }
 #undef LAUNCH
     } else {
-    ProfScope prof(ctx, 0);
+      ProfScope prof(ctx, 0);
 #define LAUNCH(L)                                                                                               \
   k_cg_spmv_dot<T, L><<<grid_spmv, kThreads, 0, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals, xv, n, \
-                                                               c, s, ctx->red.partials, ctx->red.ticket, single)
-    switch (lpr) {
-      case 2: LAUNCH(2); break;
-      case 4: LAUNCH(4); break;
-      case 8: LAUNCH(8); break;
-      case 16: LAUNCH(16); break;
-      default: LAUNCH(32); break;
-    }
+                                                               c, s, ctx->red.partials, ctx->red.ticket, cm)
+      switch (lpr) {
+        case 2: LAUNCH(2); break;
+        case 4: LAUNCH(4); break;
+        case 8: LAUNCH(8); break;
+        case 16: LAUNCH(16); break;
+        default: LAUNCH(32); break;
+      }
 #undef LAUNCH
     }
     B200_LAUNCH_CHECK(ctx);
@@ -298,19 +394,20 @@ struct CgEngine {
     cudaStream_t st = ctx->stream;
     const int pcg = jac != nullptr;
     if (pcg) {
-      k_pcg_precond<T><<<grid_vec, kThreads, 0, st>>>(jac, r, c, n, s, ctx->red.partials, ctx->red.ticket, single);
+      k_pcg_precond<T><<<grid_vec, kThreads, 0, st>>>(jac, r, c, n, s, ctx->red.partials, ctx->red.ticket, comm());
       B200_LAUNCH_CHECK(ctx);
       B200_TRY(after_reduce(FIN_RHO));
     }
     {
       ProfScope prof(ctx, 2);
-      k_cg_update_u<T><<<grid_vec, kThreads, 0, st>>>(pcg ? c : r, u, n, s, pcg);
+      k_cg_update_u<T><<<grid_vec, kThreads, 0, st>>>(pcg ? c : r, u, x, n, s, pcg, next_sweep());
     }
     B200_LAUNCH_CHECK(ctx);
     B200_TRY(spmv_dot());
     {
       ProfScope prof(ctx, 1);
-      k_cg_update_xr<T><<<grid_vec, kThreads, 0, st>>>(x, r, u, c, n, s, hist, ctx->red.partials, ctx->red.ticket, pcg, single);
+      k_cg_update_r<T><<<grid_vec, kThreads, 0, st>>>(r, c, n, s, hist, ctx->red.partials, ctx->red.ticket, pcg,
+                                                      comm(false, next_sweep()));
     }
     B200_LAUNCH_CHECK(ctx);
     return after_reduce(pcg ? FIN_NORM_PCG : FIN_NORM);
@@ -344,9 +441,10 @@ int cg_solve_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200
   e.r = (T *)p; p += vec_bytes;
   e.c = (T *)p; p += vec_bytes;
   e.s = (CgScal *)p; p += 256;
+  static_assert(sizeof(CgScal) <= 256, "CgScal too large");
   e.hist = hist_cap ? (double *)p : nullptr;
   e.jac = o->Pl.kind == B200_PREC_JACOBI ? (const T *)o->Pl.diag : nullptr;
-  e.single = ctx->world == 1;
+  e.mode = ctx->world == 1 ? COMM_SINGLE : (use_peer(ctx, A) ? COMM_PEER : COMM_NCCL);
   e.lpr = pick_lpr(A->avg_row_nnz);
   e.grid_vec = stream_grid(ctx, n, kThreads * 2, 8);
   e.grid_spmv = stream_grid(ctx, n, kThreads / e.lpr, 8);
@@ -358,6 +456,7 @@ int cg_solve_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200
   h.maxiter = maxiter;
   h.hist_cap = hist_cap;
   h.fixed = o->fixed_iterations;
+  h.pcg = e.jac != nullptr;
   B200_CUDA(cudaMemcpyAsync(e.s, &h, sizeof(h), cudaMemcpyHostToDevice, st));
 
   // cg_iterator! (src/cg.jl:120-155)
@@ -367,7 +466,7 @@ int cg_solve_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200
     B200_TRY(spmv(ctx, A, x, e.c));
   }
   k_cg_init<T><<<e.grid_vec, kThreads, 0, st>>>(b, e.c, o->initially_zero ? 0 : 1, e.r, e.u, n, e.s, ctx->red.partials,
-                                                 ctx->red.ticket, e.single);
+                                                 ctx->red.ticket, e.comm());
   B200_LAUNCH_CHECK(ctx);
   B200_TRY(e.after_reduce(FIN_INIT));
 
@@ -382,8 +481,14 @@ int cg_solve_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200
     for (int64_t i = 0; i < batch; ++i) B200_TRY(e.iterate());
     enqueued += batch;
   }
+  k_cg_flush_x<T><<<e.grid_vec, kThreads, 0, st>>>(e.u, x, n, e.s);   // x += alpha*u of the last iteration
+  B200_LAUNCH_CHECK(ctx);
   B200_CUDA(cudaMemcpyAsync(&h, e.s, sizeof(h), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
+  if (h.comm_error) {
+    set_error("peer-memory collective timed out (a rank did not reach the same point of the CG loop)");
+    return B200_ERR_NCCL;
+  }
   if (res) {
     res->iters = h.iter;
     res->mvps = mv_products + h.iter;  // history.mvps (src/cg.jl:226-231)

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/b200krylov.h"
+#include "peer.cuh"
 
 namespace b200 {
 
@@ -82,7 +83,16 @@ struct b200_ctx {
   double *d_scalars = nullptr;   // small device scratch for scalar results (64 doubles)
   double *h_scalars = nullptr;   // pinned host mirror (64 doubles)
   int *h_flags = nullptr;        // pinned host flags (16 ints)
-  int opt_spmv_kernel = 0;       // b200_ctx_set_option("spmv_kernel"): 0 auto, 1 sub-warp per row, 2 TMA stream  // optional per-kernel-class event timing (b200_ctx_profile_*)
+  int opt_spmv_kernel = 0;       // b200_ctx_set_option("spmv_kernel"): 0 auto, 1 sub-warp per row, 2 TMA stream
+  int opt_comm = 0;              // b200_ctx_set_option("comm"): 0 auto (peer memory if mapped), 1 NCCL, 2 peer memory
+  int opt_snake = 1;             // b200_ctx_set_option("snake"): consecutive hot kernels sweep the rows in alternating directions
+  // peer-memory collectives (peer.cuh), multi-GPU contexts only
+  bool peer_ok = false;
+  void *peer_local = nullptr;                          // this rank's comm buffer
+  void *peer_ptr[b200::kPeerMaxWorld] = {nullptr};     // all ranks' buffers mapped here (peer_ptr[rank] == peer_local)
+  b200::PeerView peer_view;
+  unsigned long long ar_seq = 0, halo_seq = 0;         // sequence numbers (identical on all ranks)
+  // optional per-kernel-class event timing (b200_ctx_profile_*)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;     // pool of event pairs
   std::vector<int> prof_slot;           // slot of each recorded pair

@@ -382,6 +382,34 @@ int finish_operator(b200_ctx *ctx, b200_csr *A, const b200_halo_plan *plan) {
     }
     if (A->n_halo) B200_CUDA(cudaMalloc(&A->halo, vs * A->n_halo));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    // peer-memory path: my halo segment lives in my comm buffer; learn where my values go in each peer's segment
+    A->peer_halo = false;
+    A->peer_dst_offset.assign(W, 0);
+    {
+      std::vector<long long> mine(W + 1), all((size_t)W * (W + 1));
+      for (int p = 0; p <= W; ++p) mine[p] = A->recv_offset[p];
+      long long *d_all = nullptr;
+      B200_CUDA(cudaMalloc(&d_all, sizeof(long long) * all.size()));
+      B200_CUDA(cudaMemcpy(d_all + (size_t)ctx->rank * (W + 1), mine.data(), sizeof(long long) * (W + 1), cudaMemcpyHostToDevice));
+      B200_NCCL(ncclAllGather(d_all + (size_t)ctx->rank * (W + 1), d_all, W + 1, ncclInt64, ctx->comm, ctx->stream));
+      B200_CUDA(cudaStreamSynchronize(ctx->stream));
+      B200_CUDA(cudaMemcpy(all.data(), d_all, sizeof(long long) * all.size(), cudaMemcpyDeviceToHost));
+      cudaFree(d_all);
+      bool fits = true;
+      for (int p = 0; p < W; ++p) {
+        A->peer_dst_offset[p] = all[(size_t)p * (W + 1) + ctx->rank];          // peer p's recv_offset[me]
+        fits = fits && (size_t)all[(size_t)p * (W + 1) + W] * vs + kPeerHeaderBytes <= kPeerBufferBytes;
+      }
+      A->recv_mask = A->send_mask = 0;
+      for (int p = 0; p < W; ++p) {
+        if (A->recv_count[p]) A->recv_mask |= 1u << p;
+        if (A->send_count[p]) A->send_mask |= 1u << p;
+      }
+      if (ctx->peer_ok && fits) {
+        A->peer_halo = true;
+        A->halo_peer = (char *)ctx->peer_local + kPeerHeaderBytes;
+      }
+    }
   }
   return B200_OK;
 }
@@ -721,6 +749,63 @@ int b200_csr_download(b200_ctx *ctx, const b200_csr *A, int32_t *rowptr, int32_t
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------
+// halo push over NVLink peer memory (peer.cuh): x[send_idx[k]] -> the peer's halo segment, then flags
+// ------------------------------------------------------------------------------------------
+namespace {
+struct PushArgs {
+  int world, rank;
+  long long start[kPeerMaxWorld + 1];   // send_offset per peer
+  void *dst[kPeerMaxWorld];             // peer halo segment + my offset inside it
+  unsigned int send_mask;
+};
+template <typename T>
+__global__ void __launch_bounds__(256) k_halo_push(PushArgs a, const int *__restrict__ idx, const T *__restrict__ x,
+                                                   PeerView pv, unsigned long long seq, unsigned int *ticket,
+                                                   const int *__restrict__ done_flag) {
+  if (done_flag && *done_flag) return;
+  const long long n = a.start[a.world];
+  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+    int p = 0;
+    while (k >= a.start[p + 1]) ++p;
+    ((T *)a.dst[p])[k - a.start[p]] = x[idx[k]];      // store to mapped peer memory (NVLink)
+  }
+  __threadfence_system();
+  __shared__ bool is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int p = 0; p < a.world; ++p)
+      if ((a.send_mask >> p) & 1u) st_release_sys(&pv.hdr[p]->halo_flag[a.rank], seq);
+    *ticket = 0u;
+  }
+}
+}  // namespace
+
+int b200::halo_push(b200_ctx *ctx, const b200_csr *A, const void *x_dev, unsigned long long seq,
+                    const int *done_flag) {
+  if (A->send_mask == 0) return B200_OK;
+  PushArgs a;
+  a.world = ctx->world;
+  a.rank = ctx->rank;
+  a.send_mask = A->send_mask;
+  const size_t vs = dtype_size(A->dtype);
+  for (int p = 0; p <= ctx->world; ++p) a.start[p] = A->send_offset[p];
+  for (int p = 0; p < ctx->world; ++p)
+    a.dst[p] = (char *)ctx->peer_ptr[p] + kPeerHeaderBytes + vs * (size_t)A->peer_dst_offset[p];
+  const int grid = std::max(1, std::min(ctx->sm_count, (int)((A->n_send + 1023) / 1024)));
+  unsigned int *ticket = ctx->red.ticket + 1;   // own counter: must not interfere with a reduction in flight
+  if (A->dtype == B200_F64)
+    k_halo_push<double><<<grid, 256, 0, ctx->stream>>>(a, A->send_idx, (const double *)x_dev, ctx->peer_view, seq, ticket, done_flag);
+  else
+    k_halo_push<float><<<grid, 256, 0, ctx->stream>>>(a, A->send_idx, (const float *)x_dev, ctx->peer_view, seq, ticket, done_flag);
+  B200_LAUNCH_CHECK(ctx);
+  return B200_OK;
+}
 
 // ------------------------------------------------------------------------------------------
 // halo exchange: pack boundary values, grouped ncclSend/ncclRecv with every peer that shares rows

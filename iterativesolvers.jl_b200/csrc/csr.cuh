@@ -36,10 +36,21 @@ struct b200_csr {
   int64_t n_send = 0;
   int *send_idx = nullptr;   // device: local row index to pack, grouped by peer
   void *send_buf = nullptr;  // device: n_send values
-  void *halo = nullptr;      // device: n_halo values (recv buffer == halo part of the extended vector)
+  void *halo = nullptr;      // device: n_halo values (recv buffer == halo part of the extended vector), NCCL path
+  // peer-memory path (peer.cuh): the halo segment lives in this rank's comm buffer, neighbours store into it
+  bool peer_halo = false;
+  void *halo_peer = nullptr;               // = ctx->peer_local + kPeerHeaderBytes
+  std::vector<int64_t> peer_dst_offset;    // [peer] element offset of MY values inside the peer's halo segment
+  unsigned int recv_mask = 0, send_mask = 0;
 };
 
 namespace b200 {
 // packs x[send_idx] and exchanges with the peers; after return (stream-ordered) A->halo is valid
 int halo_exchange(b200_ctx *ctx, const b200_csr *A, const void *x_dev);
+// peer-memory variant: stores x[send_idx] into the neighbours' halo segments and raises halo flag `seq`
+// (skipped on the device when *done_flag != 0); consumers wait with peer_wait_halo(.., A->recv_mask, seq)
+int halo_push(b200_ctx *ctx, const b200_csr *A, const void *x_dev, unsigned long long seq, const int *done_flag);
+inline bool use_peer(const b200_ctx *ctx, const b200_csr *A) {
+  return ctx->world > 1 && ctx->peer_ok && A->peer_halo && ctx->opt_comm != 1;
+}
 }  // namespace b200

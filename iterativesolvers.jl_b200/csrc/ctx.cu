@@ -68,6 +68,61 @@ static int ctx_init_common(b200_ctx *c) {
   return B200_OK;
 }
 
+// Map every rank's comm buffer into this process (CUDA IPC; handles all-gathered over NCCL).  If the
+// platform refuses (no P2P between the two devices, IPC disabled), peer_ok stays false and the engines
+// keep using NCCL for the collectives.
+static int peer_setup(b200_ctx *c) {
+  c->peer_ok = false;
+  if (c->world > kPeerMaxWorld) return B200_OK;
+  B200_CUDA(cudaMalloc(&c->peer_local, kPeerBufferBytes));
+  B200_CUDA(cudaMemset(c->peer_local, 0, kPeerBufferBytes));
+  cudaIpcMemHandle_t mine;
+  cudaError_t e = cudaIpcGetMemHandle(&mine, c->peer_local);
+  int ok = (e == cudaSuccess);
+  if (!ok) cudaGetLastError();
+  // all-gather {ok flag, handle} through NCCL (device staging in the comm buffer's tail is not needed: d_scalars is 2 KB)
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  unsigned char *d_stage = nullptr;
+  const size_t rec = 128;
+  B200_CUDA(cudaMalloc(&d_stage, rec * c->world));
+  unsigned char h_rec[128];
+  memset(h_rec, 0, sizeof(h_rec));
+  h_rec[0] = (unsigned char)ok;
+  memcpy(h_rec + 64, &mine, 64);
+  B200_CUDA(cudaMemcpy(d_stage + rec * c->rank, h_rec, rec, cudaMemcpyHostToDevice));
+  B200_NCCL(ncclAllGather(d_stage + rec * c->rank, d_stage, rec, ncclChar, c->comm, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  std::vector<unsigned char> all(rec * c->world);
+  B200_CUDA(cudaMemcpy(all.data(), d_stage, all.size(), cudaMemcpyDeviceToHost));
+  cudaFree(d_stage);
+  for (int r = 0; r < c->world && ok; ++r) ok = ok && all[rec * r] == 1;
+  for (int r = 0; r < c->world && ok; ++r) {
+    if (r == c->rank) {
+      c->peer_ptr[r] = c->peer_local;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, all.data() + rec * r + 64, 64);
+    e = cudaIpcOpenMemHandle(&c->peer_ptr[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+    }
+  }
+  // every rank must agree, otherwise nobody uses the peer path
+  double flag = ok ? 0.0 : 1.0;
+  double *d = c->d_scalars + 128;
+  B200_CUDA(cudaMemcpy(d, &flag, sizeof(double), cudaMemcpyHostToDevice));
+  B200_NCCL(ncclAllReduce(d, d, 1, ncclDouble, ncclSum, c->comm, c->stream));
+  B200_CUDA(cudaMemcpyAsync(&flag, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  B200_CUDA(cudaStreamSynchronize(c->stream));
+  c->peer_ok = (flag == 0.0);
+  c->peer_view.world = c->world;
+  c->peer_view.rank = c->rank;
+  for (int r = 0; r < c->world; ++r) c->peer_view.hdr[r] = c->peer_ok ? (PeerHeader *)c->peer_ptr[r] : nullptr;
+  return B200_OK;
+}
+
 int b200_ctx_create(int device, b200_ctx **out) {
   B200_REQUIRE(out, "out is NULL");
   b200_ctx *c = new b200_ctx();
@@ -106,6 +161,11 @@ int b200_ctx_create_dist(int device, int rank, int world, const void *nccl_id128
     ncclUniqueId id;
     memcpy(&id, nccl_id128, sizeof(id));
     B200_NCCL(ncclCommInitRank(&c->comm, world, id, rank));
+    int s2 = peer_setup(c);
+    if (s2 != B200_OK) {
+      delete c;
+      return s2;
+    }
   }
   *out = c;
   return B200_OK;
@@ -115,6 +175,9 @@ int b200_ctx_destroy(b200_ctx *c) {
   if (!c) return B200_OK;
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  for (int r = 0; r < c->world && r < kPeerMaxWorld; ++r)
+    if (r != c->rank && c->peer_ptr[r]) cudaIpcCloseMemHandle(c->peer_ptr[r]);
+  if (c->peer_local) cudaFree(c->peer_local);
   if (c->comm) ncclCommDestroy(c->comm);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
@@ -179,8 +242,30 @@ int b200_ctx_set_option(b200_ctx *c, const char *name, int64_t value) {
     c->opt_spmv_kernel = (int)value;
     return B200_OK;
   }
+  if (strcmp(name, "snake") == 0) {
+    c->opt_snake = value != 0;
+    return B200_OK;
+  }
+  if (strcmp(name, "comm") == 0) {
+    B200_REQUIRE(value >= 0 && value <= 2, "comm must be 0 (auto), 1 (NCCL) or 2 (peer memory)");
+    B200_REQUIRE(value != 2 || c->peer_ok || c->world == 1, "peer-memory collectives are not available on this context");
+    c->opt_comm = (int)value;
+    return B200_OK;
+  }
   set_error("unknown option `%s`", name);
   return B200_ERR_INVALID;
+}
+
+int b200_ctx_get_option(const b200_ctx *c, const char *name, int64_t *value) {
+  B200_REQUIRE(c && name && value, "NULL argument");
+  if (strcmp(name, "spmv_kernel") == 0) *value = c->opt_spmv_kernel;
+  else if (strcmp(name, "comm") == 0) *value = c->opt_comm;
+  else if (strcmp(name, "peer_ok") == 0) *value = c->peer_ok ? 1 : 0;
+  else {
+    set_error("unknown option `%s`", name);
+    return B200_ERR_INVALID;
+  }
+  return B200_OK;
 }
 
 int b200_ctx_profile_enable(b200_ctx *c, int on) {

@@ -4,6 +4,7 @@
 // difference: diagonal 2*dims, -1 for every +-1 neighbour along one coordinate.  Row/column index
 // = sum_d coord_d * N^d.  Entries inside a column (row) are emitted in ascending index order, which
 // is the order Julia's sparse kron/+ produce.
+#include <math.h>
 #include <omp.h>
 
 #include "common.cuh"
@@ -78,6 +79,49 @@ int64_t b200_gen_laplace_csc_i64(int64_t N, int dims, int base, int64_t *colptr,
   for (int64_t q = 0; q < g.n; ++q) colptr[q + 1] += colptr[q];
 #pragma omp parallel for schedule(static)
   for (int64_t q = 0; q < g.n; ++q) emit_row<int64_t, double>(g, q, base, rowval + (colptr[q] - base), nzval + (colptr[q] - base));
+  return colptr[g.n] - base;
+}
+
+// advection_dominated(N, beta) of reference benchmark/advection_diffusion.jl:3-30 as SparseMatrixCSC{Float64,Int64}:
+//   A = laplace_matrix(Float64, N, 3) ./ -h^2 + kron(I_{N^2}, spdiagm(-1 => -beta/2h, 1 => beta/2h)),  h = 1/(N+1)
+// and the right-hand side b = f(x,y,z) = exp(xyz) sin(pi x) sin(pi y) sin(pi z) on the interior points
+// (x fastest).  Values are formed with the same floating-point operations as the reference expression
+// (stored value / -(h*h), then + the first-derivative coefficient on the x-neighbours).
+int64_t b200_gen_advection_csc_i64(int64_t N, double beta, int base, int64_t *colptr, int64_t *rowval, double *nzval,
+                                   double *b) {
+  Geom g;
+  if (!make_geom(N, 3, &g) || !colptr || !rowval || !nzval) {
+    set_error("b200_gen_advection_csc_i64: bad arguments");
+    return B200_ERR_INVALID;
+  }
+  const double h = 1.0 / (double)(N + 1);
+  const double mh2 = -(h * h);
+  const double lo = -beta / (2 * h), up = beta / (2 * h);
+  const double v_diag = 6.0 / mh2, v_off = -1.0 / mh2;
+  colptr[0] = base;
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < g.n; ++q) colptr[q + 1] = row_count(g, q);
+  for (int64_t q = 0; q < g.n; ++q) colptr[q + 1] += colptr[q];
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < g.n; ++q) {
+    int64_t *idx = rowval + (colptr[q] - base);
+    double *val = nzval + (colptr[q] - base);
+    const int64_t cx = q % N, cy = (q / N) % N, cz = q / (N * N);
+    int k = 0;
+    if (cz > 0) { idx[k] = q - N * N + base; val[k++] = v_off; }
+    if (cy > 0) { idx[k] = q - N + base; val[k++] = v_off; }
+    if (cx > 0) { idx[k] = q - 1 + base; val[k++] = v_off + up; }       // A[q-1, q]: super-diagonal of row q-1
+    idx[k] = q + base; val[k++] = v_diag;
+    if (cx < N - 1) { idx[k] = q + 1 + base; val[k++] = v_off + lo; }   // A[q+1, q]: sub-diagonal of row q+1
+    if (cy < N - 1) { idx[k] = q + N + base; val[k++] = v_off; }
+    if (cz < N - 1) { idx[k] = q + N * N + base; val[k++] = v_off; }
+    if (b) {
+      const double x = (double)(cx + 1) / (double)(N + 1), y = (double)(cy + 1) / (double)(N + 1),
+                   z = (double)(cz + 1) / (double)(N + 1);
+      const double pi = 3.141592653589793;
+      b[q] = exp(x * y * z) * sin(pi * x) * sin(pi * y) * sin(pi * z);
+    }
+  }
   return colptr[g.n] - base;
 }
 

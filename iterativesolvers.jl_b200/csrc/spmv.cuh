@@ -28,10 +28,11 @@ struct XView {
   __device__ __forceinline__ T operator()(int col) const { return col < m ? __ldg(x + col) : __ldg(halo + col); }
 };
 template <typename T>
-inline XView<T> make_xview(const b200_csr *A, const void *x_dev) {
+inline XView<T> make_xview(const b200_csr *A, const void *x_dev, bool peer_halo = false) {
   XView<T> v;
   v.x = (const T *)x_dev;
-  v.halo = A->halo ? (const T *)A->halo - A->m_local : (const T *)x_dev;
+  const void *h = peer_halo ? A->halo_peer : A->halo;   // which halo buffer the preceding exchange filled
+  v.halo = h ? (const T *)h - A->m_local : (const T *)x_dev;
   v.m = (int)A->m_local;
   return v;
 }

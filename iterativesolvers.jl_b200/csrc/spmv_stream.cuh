@@ -94,11 +94,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 template <typename T, int LPR, typename XV, typename Epi>
 __device__ __forceinline__ void spmv_stream_tiles(const int *__restrict__ rowptr, const int *__restrict__ colind,
                                                   const T *__restrict__ vals, const XV &xv, int64_t m, Epi &epi,
-                                                  StreamSmem<T> *sm) {
+                                                  StreamSmem<T> *sm, bool rev = false) {
   constexpr int R = kStreamTileRows / LPR;          // rows per tile
   constexpr int SLOTS = kStreamGroupThreads / LPR;  // row slots per group; each slot owns rows s and s+SLOTS
   const int tid = threadIdx.x;
   const int64_t ntiles = (m + R - 1) / R;
+  // `rev`: sweep the tiles from the last to the first.  Consecutive kernels of a solver alternate the sweep
+  // direction so that each one starts on the rows the previous kernel touched last (still in the 126 MB L2).
+  auto phys = [&](int64_t seq) -> int64_t { return rev ? ntiles - 1 - seq : seq; };
   if (tid == 0) {
     for (int s = 0; s < kStreamStages; ++s) {
       mbar_init(&sm->full[s], 1);
@@ -116,18 +119,18 @@ __device__ __forceinline__ void spmv_stream_tiles(const int *__restrict__ rowptr
       // bounds of the next tile are fetched one iteration ahead (off the critical path)
       int k0 = 0, k1 = 0;
       if (t < ntiles) {
-        const int64_t r0 = t * R, r1 = (r0 + R < m) ? (r0 + R) : m;
+        const int64_t r0 = phys(t) * R, r1 = (r0 + R < m) ? (r0 + R) : m;
         k0 = __ldg(rowptr + r0);
         k1 = __ldg(rowptr + r1);
       }
       for (int it = 0; t < ntiles; ++it) {
         const int s = it % kStreamStages;
         const uint32_t ph = (uint32_t)((it / kStreamStages) & 1);
-        const int64_t r0 = t * R;
+        const int64_t r0 = phys(t) * R;
         const int64_t tn = t + gridDim.x;
         int nk0 = 0, nk1 = 0;
         if (tn < ntiles) {
-          const int64_t nr0 = tn * R, nr1 = (nr0 + R < m) ? (nr0 + R) : m;
+          const int64_t nr0 = phys(tn) * R, nr1 = (nr0 + R < m) ? (nr0 + R) : m;
           nk0 = __ldg(rowptr + nr0);
           nk1 = __ldg(rowptr + nr1);
         }
@@ -155,7 +158,7 @@ __device__ __forceinline__ void spmv_stream_tiles(const int *__restrict__ rowptr
       if (t >= ntiles) break;
       const int s = (int)(k % kStreamStages);
       const uint32_t ph = (uint32_t)((k / kStreamStages) & 1);
-      const int64_t r0 = t * R;
+      const int64_t r0 = phys(t) * R;
       mbar_wait(&sm->full[s], ph);
       const StreamStage<T> *st = &sm->stage[s];
       const int k0a = st->rp[0] & ~3;

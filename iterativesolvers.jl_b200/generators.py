@@ -39,3 +39,17 @@ def laplace_csr_slab(T, N: int, dims: int, row_begin: int, m_local: int):
     got = lib().b200_gen_laplace_csr_slab_i32(N, dims, row_begin, m_local, _vp(rowptr), _vp(colind), _vp(vals))
     assert got == nnz
     return rowptr, colind, vals.astype(np.dtype(T), copy=False)
+
+
+def advection_dominated(N: int = 50, beta: float = 1000.0, base: int = 0):
+    """advection_dominated(N, beta) of reference benchmark/advection_diffusion.jl:3-30:
+    returns (colptr, rowval, nzval, (n, n), b) -- SparseMatrixCSC{Float64,Int64} arrays and the rhs."""
+    n = int(N) ** 3
+    nnz = lib().b200_gen_laplace_nnz(N, 3, 0, n)
+    colptr = np.empty(n + 1, dtype=np.int64)
+    rowval = np.empty(nnz, dtype=np.int64)
+    nzval = np.empty(nnz, dtype=np.float64)
+    b = np.empty(n, dtype=np.float64)
+    got = lib().b200_gen_advection_csc_i64(N, float(beta), base, _vp(colptr), _vp(rowval), _vp(nzval), _vp(b))
+    assert got == nnz
+    return colptr, rowval, nzval, (n, n), b

@@ -46,14 +46,28 @@ def main():
     # distributed SpMV == slab of the global SpMV (bitwise: same per-row order)
     xg = rng.standard_normal(n)
     y_loc = A1 @ xg[lo:lo + m]
+    # both transports of the collectives: NCCL (comm=1) and NVLink peer memory fused into the kernels (comm=2)
+    import ctypes as C
+    L = isb.lib()
+    peer_ok = C.c_int64()
+    assert L.b200_ctx_get_option(ctx._h, b"peer_ok", C.byref(peer_ok)) == 0
     results = {}
-    for name, A in (("slab", A1), ("generated", A2)):
+    for name, A, comm in (("slab", A1, 1), ("generated", A2, 2 if peer_ok.value else 1)):
+        assert L.b200_ctx_set_option(ctx._h, b"comm", comm) == 0
         x_loc = np.zeros(m)
         x_loc, h = isb.cg_(x_loc, A, b_global[lo:lo + m].copy(), initially_zero=True, log=True, reltol=1e-9)
         results[name] = (x_loc, h)
+        # Jacobi-PCG and a nonzero initial guess on the same transport
+        xp = np.full(m, 0.25)
+        xp, hp = isb.cg_(xp, A, b_global[lo:lo + m].copy(), Pl=isb.JacobiPrec(A.diag(), ctx), log=True, reltol=1e-9)
+        results[name + "_pcg"] = (xp, hp)
+    L.b200_ctx_set_option(ctx._h, b"comm", 0)
+    if rank == 0:
+        print(f"peer_ok={peer_ok.value}")
 
     gathered = [None] * world
-    dist.all_gather_object(gathered, (y_loc, results["slab"][0], results["generated"][0]))
+    dist.all_gather_object(gathered, (y_loc, results["slab"][0], results["generated"][0],
+                                      results["slab_pcg"][0], results["generated_pcg"][0]))
     if rank == 0:
         ctx1 = isb.Context(local)
         cp, rv, nz, shape = isb.laplace_matrix(np.float64, N, 3, base=1)
@@ -70,6 +84,15 @@ def main():
             x_err = float(np.linalg.norm(xd - xs) / np.linalg.norm(xs))
             assert hist_err <= 1e-10 and x_err <= 1e-10, (name, hist_err, x_err)
             print(f"{name}: world={world} N={N} iters={h.niters} hist_err={hist_err:.2e} x_err={x_err:.2e}")
+        xs, hs = isb.cg_(np.full(n, 0.25), Ag, b_global, Pl=isb.JacobiPrec(Ag.diag(), ctx1), log=True, reltol=1e-9)
+        for idx, name in ((3, "slab_pcg"), (4, "generated_pcg")):
+            xd = np.concatenate([g[idx] for g in gathered])
+            h = results[name][1]
+            assert h.niters == hs.niters and h.mvps == hs.mvps, (name, h.niters, hs.niters)
+            hist_err = float(np.max(np.abs(h["resnorm"] - hs["resnorm"]) / hs["resnorm"]))
+            x_err = float(np.linalg.norm(xd - xs) / np.linalg.norm(xs))
+            assert hist_err <= 1e-10 and x_err <= 1e-10, (name, hist_err, x_err)
+            print(f"{name}: iters={h.niters} hist_err={hist_err:.2e} x_err={x_err:.2e}")
         print("DIST_OK")
     dist.barrier()
     dist.destroy_process_group()

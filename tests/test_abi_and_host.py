@@ -66,6 +66,17 @@ def test_host_generators_match_oracle(isb, oracle):
         assert np.array_equal(rp, S.indptr) and np.array_equal(ci, S.indices) and np.array_equal(va, S.data)
 
 
+def test_advection_generator_matches_oracle(isb, oracle):
+    """reference benchmark/advection_diffusion.jl:3-30: library generator == scipy restatement (matrix bitwise)."""
+    for N in (5, 12):
+        cp, rv, nz, shape, b = isb.advection_dominated(N, 1000.0, base=1)
+        M, bo = oracle.advection_dominated(N, 1000.0)
+        O = oracle.CSC.from_scipy(M, base=1)
+        assert shape == O.shape and np.array_equal(cp, O.colptr) and np.array_equal(rv, O.rowval)
+        assert np.array_equal(nz, O.nzval)
+        np.testing.assert_allclose(b, bo, rtol=4e-16, atol=1e-300)       # libm vs numpy: 1 ulp
+
+
 def test_halo_plan_single_process(isb, oracle):
     """plan of rank 1 of 3 for a 2-D Laplacian slab, scanned from the CSR columns and analytically."""
     N, dims = 8, 2
