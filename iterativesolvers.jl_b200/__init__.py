@@ -11,7 +11,7 @@ The directory name contains a dot, so import it through the repo-root alias modu
     import iterativesolvers_jl_b200 as isb
 """
 from ._lib import B200Error, lib  # noqa: F401
-from .device import Context, DeviceArray, default_context  # noqa: F401
+from .device import Context, DeviceArray, default_context, pinned_empty  # noqa: F401
 from .operators import B200CSR, HaloPlan, Identity, JacobiPrec  # noqa: F401
 from .history import ConvergenceHistory  # noqa: F401
 from .generators import laplace_matrix, laplace_csr_slab, advection_dominated  # noqa: F401

@@ -163,6 +163,17 @@ class DeviceArray:
             pass
 
 
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by page-locked host memory (cudaMallocHost through the C ABI): host<->device
+    copies of such arrays run at full PCIe/C2C bandwidth.  The memory lives until process exit."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    check(lib().b200_host_alloc_pinned(max(n * dtype.itemsize, 16), C.byref(p)))
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+
 def as_device_ptr(v):
     """raw device address of a DeviceArray or of a torch CUDA tensor (zero-copy)."""
     if isinstance(v, DeviceArray):

@@ -13,29 +13,30 @@ def _vp(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def laplace_matrix(T, N: int, dims: int, base: int = 0):
+def laplace_matrix(T, N: int, dims: int, base: int = 0, empty=np.empty):
     """laplace_matrix(T, N, dims) of reference test/laplace_matrix.jl:1-12 as the three arrays of a
-    SparseMatrixCSC{T,Int64}: returns (colptr, rowval, nzval, (n, n))."""
+    SparseMatrixCSC{T,Int64}: returns (colptr, rowval, nzval, (n, n)).  `empty(shape, dtype=...)` allocates
+    the arrays (pass device.pinned_empty for page-locked host memory)."""
     n = int(N) ** dims
     nnz = lib().b200_gen_laplace_nnz(N, dims, 0, n)
     if nnz < 0:
         raise B200Error("bad laplace_matrix arguments")
-    colptr = np.empty(n + 1, dtype=np.int64)
-    rowval = np.empty(nnz, dtype=np.int64)
-    nzval = np.empty(nnz, dtype=np.float64)
+    colptr = empty(n + 1, dtype=np.int64)
+    rowval = empty(nnz, dtype=np.int64)
+    nzval = empty(nnz, dtype=np.float64)
     got = lib().b200_gen_laplace_csc_i64(N, dims, base, _vp(colptr), _vp(rowval), _vp(nzval))
     assert got == nnz
     return colptr, rowval, nzval.astype(np.dtype(T), copy=False), (n, n)
 
 
-def laplace_csr_slab(T, N: int, dims: int, row_begin: int, m_local: int):
+def laplace_csr_slab(T, N: int, dims: int, row_begin: int, m_local: int, empty=np.empty):
     """rows [row_begin, row_begin+m_local) of laplace_matrix(T, N, dims) as CSR (int32, global columns)."""
     nnz = lib().b200_gen_laplace_nnz(N, dims, row_begin, m_local)
     if nnz < 0:
         raise B200Error("bad laplace slab arguments")
-    rowptr = np.empty(m_local + 1, dtype=np.int32)
-    colind = np.empty(nnz, dtype=np.int32)
-    vals = np.empty(nnz, dtype=np.float64)
+    rowptr = empty(m_local + 1, dtype=np.int32)
+    colind = empty(nnz, dtype=np.int32)
+    vals = empty(nnz, dtype=np.float64)
     got = lib().b200_gen_laplace_csr_slab_i32(N, dims, row_begin, m_local, _vp(rowptr), _vp(colind), _vp(vals))
     assert got == nnz
     return rowptr, colind, vals.astype(np.dtype(T), copy=False)
