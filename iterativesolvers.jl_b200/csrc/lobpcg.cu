@@ -2,55 +2,161 @@
 // the step functor :692-749, for the standard problem (B = nothing) without constraint -- the path of
 // BASELINE.json configs[4] (block = 16, fp32, 3-D Laplacian).
 //
-// Blocks are n x bs column-major (the reference's layout), device-resident.  Per step (it >= 3):
-//   CholQR(R)  : k_gram (R'R, one pass) -> host Cholesky -> k_rdiv (the reference's column sweeps of
-//                rdiv! :345-355, done per row in registers)                              (:365-393)
-//   AR = A*R   : block SpMM, A streamed ONCE for the 16 columns (the CPU path re-reads A per column) (:124-131)
-//   CholQR(P)  : same, AP updated in the same launch                                      (:733)
-//   Gram blocks: X'[AR AP R P], R'[AR P], AR'P, P'AP -- 4 launches, each left block is read once for
-//                all its right blocks                                                     (:586-605)
-//   Rayleigh-Ritz: (3bs x 3bs) generalized symmetric eigenproblem on the host in fp64     (:607-627)
+// Layout: the caller's X is n x bs column-major (the reference's layout).  Inside the engine every block
+// (X, AX, R, AR, P, AP) is ROW-major, n rows x 16 values (zero-padded beyond bs): one row = 64 B (fp32) /
+// 128 B (fp64) contiguous.  That makes the SpMM gather one aligned 64-byte read per nonzero, turns every
+// block operand of the dense kernels into a plain contiguous stream, and lets the Gram kernel pull its
+// operands with TMA bulk copies.  X is transposed in at the start and out at the end (2 passes per solve).
+//
+// Per step (it >= 3), all HBM-bound:
+//   CholQR(R)  : k_gram (R'R) -> host Cholesky (fp64) -> k_rdiv (the reference's column sweeps of rdiv!
+//                :345-355, done per row in registers)                                        (:365-393)
+//   AR = A*R   : k_spmm_rm, A streamed ONCE for the 16 columns (the CPU path re-reads A per column) (:124-131)
+//   CholQR(P)  : same, AP updated in the same launch                                          (:733)
+//   Gram blocks: X'[AR R AP P], R'[AR P], AR'P, P'AP -- 4 launches of k_gram: a producer warp streams the
+//                row chunks of the operands into a shared-memory ring with cp.async.bulk + mbarriers, 256
+//                consumer threads accumulate 4x4 register tiles (16 row groups x 16 tiles)      (:586-605)
+//   Rayleigh-Ritz: (3bs x 3bs) generalized symmetric eigenproblem on the host in fp64 (dense_small.h) (:607-627)
 //   update     : ONE launch computes P = R Vr + P Vp, X = X Vx + P, the same for AP/AX, the residual
-//                block R = AX - X diag(lambda) and its column norms                        (:629-690, :533-547)
+//                block R = AX - X diag(lambda) and its column norms                            (:629-690, :533-547)
 // Soft locking (activeMask, :549-562) gathers the active columns into scratch blocks; with a full mask the
 // active blocks alias R/P/AP (no copies).
-// The dense contractions are fp32/fp64 FMA on CUDA cores (register-tiled 4x4 per thread): at bs = 16 they
-// are HBM-bound (4 flop/byte); routing them through TF32 tensor cores would cost the fp32 parity the
-// reference's own tolerance (eps^0.3) does not require but its eigenvalue accuracy does.
+// The contractions are fp32/fp64 FMA on CUDA cores: at bs = 16 they are HBM-bound (4 flop/byte) and TF32
+// tensor cores would cost the fp32 eigenvalue parity.
 #include "blas1.cuh"
 #include "dense_small.h"
-#include "spmv.cuh"
+#include "spmv_stream.cuh"
 
 using namespace b200;
-
-extern "C" int b200_spmm(b200_ctx *ctx, const b200_csr *A, const void *X_dev, int64_t ldx, void *Y_dev, int64_t ldy,
-                         int bs);
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int BSMAX = 16;
-constexpr int RC = 64;       // rows per shared-memory chunk in the Gram kernel
-constexpr int NRMAX = 4;     // right-hand blocks per Gram launch
+constexpr int BS = 16;             // padded block width
+constexpr int RC = 128;            // rows per Gram chunk
+constexpr int GSTAGES = 4;
+constexpr int kGramThreads = kThreads + 32;
 
-// G_b = L' * R_b for b < NR (all n x <=16 column-major, ld = n).  partials: [gridDim][NR*256] doubles.
+template <typename T>
+__device__ __forceinline__ void load_row(const T *__restrict__ p, T (&v)[BS]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 *q = reinterpret_cast<const float4 *>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = q[i];
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  } else {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double2 t = q[i];
+      v[2 * i] = t.x; v[2 * i + 1] = t.y;
+    }
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_row(T *__restrict__ p, const T (&v)[BS]) {
+  if constexpr (sizeof(T) == 4) {
+    float4 *q = reinterpret_cast<float4 *>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) q[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    double2 *q = reinterpret_cast<double2 *>(p);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) q[i] = make_double2(v[2 * i], v[2 * i + 1]);
+  }
+}
+
+// column-major n x bs (ld = n)  <->  row-major n x 16
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_to_rowmajor(const T *__restrict__ cm, T *__restrict__ rm, int64_t n,
+                                                          int bs) {
+  for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
+    T v[BS];
+#pragma unroll
+    for (int j = 0; j < BS; ++j) v[j] = j < bs ? cm[r + (int64_t)j * n] : (T)0;
+    store_row<T>(rm + r * BS, v);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_to_colmajor(const T *__restrict__ rm, T *__restrict__ cm, int64_t n,
+                                                          int bs) {
+  for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
+    T v[BS];
+    load_row<T>(rm + r * BS, v);
+#pragma unroll
+    for (int j = 0; j < BS; ++j)
+      if (j < bs) cm[r + (int64_t)j * n] = v[j];
+  }
+}
+
+// Y = A X on row-major blocks: 4 lanes per row, each lane owns 4 of the 16 columns, so every nonzero is one
+// coalesced 64-byte (fp32) read of the X row.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_spmm_rm(const int *__restrict__ rowptr, const int *__restrict__ colind,
+                                                      const T *__restrict__ vals, const T *__restrict__ X,
+                                                      int64_t m, T *__restrict__ Y) {
+  const int sub = threadIdx.x & 3;
+  const int rib = threadIdx.x >> 2;
+  const uint64_t pol = policy_evict_first();
+  for (int64_t base = (int64_t)blockIdx.x * (kThreads / 4); base < m; base += (int64_t)gridDim.x * (kThreads / 4)) {
+    const int64_t row = base + rib;
+    if (row >= m) continue;
+    const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
+    T acc[4] = {(T)0, (T)0, (T)0, (T)0};
+    for (int k = b; k < e; ++k) {
+      const int c = ld_stream<int>(colind + k, pol);
+      const T a = ld_stream<T>(vals + k, pol);
+      const T *xr = X + (int64_t)c * BS + 4 * sub;
+      if constexpr (sizeof(T) == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(xr));
+        acc[0] += a * t.x; acc[1] += a * t.y; acc[2] += a * t.z; acc[3] += a * t.w;
+      } else {
+        const double2 t0 = __ldg(reinterpret_cast<const double2 *>(xr));
+        const double2 t1 = __ldg(reinterpret_cast<const double2 *>(xr) + 1);
+        acc[0] += a * t0.x; acc[1] += a * t0.y; acc[2] += a * t1.x; acc[3] += a * t1.y;
+      }
+    }
+    T *yr = Y + row * BS + 4 * sub;
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<float4 *>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    else {
+      reinterpret_cast<double2 *>(yr)[0] = make_double2(acc[0], acc[1]);
+      reinterpret_cast<double2 *>(yr)[1] = make_double2(acc[2], acc[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// G_b = L' * R_b  (b < NR), all blocks row-major n x 16.  TMA-fed: see file header.
+// ---------------------------------------------------------------------------------------------------------
 template <typename T, int NR>
-__global__ void __launch_bounds__(kThreads) k_gram(const T *__restrict__ L, int bl, const T *__restrict__ R0,
-                                                   const T *__restrict__ R1, const T *__restrict__ R2,
-                                                   const T *__restrict__ R3, int br, int64_t n, double *partials,
-                                                   unsigned int *ticket, double *__restrict__ out) {
-  // staging chunk and the final cross-group reduction share the same shared memory
-  constexpr size_t kStageBytes = sizeof(T) * (1 + NR) * BSMAX * RC;
-  constexpr size_t kRedBytes = sizeof(double) * 16 * 257;
-  __shared__ __align__(16) unsigned char raw[kStageBytes > kRedBytes ? kStageBytes : kRedBytes];
-  T(*Ls)[RC] = reinterpret_cast<T(*)[RC]>(raw);
-  T(*Rs)[BSMAX][RC] = reinterpret_cast<T(*)[BSMAX][RC]>(raw + sizeof(T) * BSMAX * RC);
-  double(*red)[257] = reinterpret_cast<double(*)[257]>(raw);
+struct GramSmem {
+  alignas(128) T buf[GSTAGES][1 + NR][RC * BS];
+  alignas(8) unsigned long long full[GSTAGES];
+  alignas(8) unsigned long long empty[GSTAGES];
+};
+
+template <typename T, int NR>
+__global__ void __launch_bounds__(kGramThreads, 1)
+    k_gram(const T *__restrict__ L, const T *__restrict__ R0, const T *__restrict__ R1, const T *__restrict__ R2,
+           const T *__restrict__ R3, int64_t n, double *partials, unsigned int *ticket, double *__restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  GramSmem<T, NR> *sm = reinterpret_cast<GramSmem<T, NR> *>(smem_raw);
   __shared__ bool is_last;
   const T *Rp[4] = {R0, R1, R2, R3};
-  const int t = threadIdx.x;
-  const int g = t >> 4;                 // row group 0..15
-  const int ti = (t & 15) >> 2, tj = t & 3;
+  const int tid = threadIdx.x;
+  const int64_t nchunks = (n + RC - 1) / RC;
+  if (tid == 0) {
+    for (int s = 0; s < GSTAGES; ++s) {
+      mbar_init(&sm->full[s], 1);
+      mbar_init(&sm->empty[s], kThreads / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int g = tid >> 4;                       // row group 0..15 (consumers)
+  const int ti = (tid & 15) >> 2, tj = tid & 3;
   double accd[NR][4][4];
 #pragma unroll
   for (int b = 0; b < NR; ++b)
@@ -59,224 +165,238 @@ __global__ void __launch_bounds__(kThreads) k_gram(const T *__restrict__ L, int 
 #pragma unroll
       for (int c = 0; c < 4; ++c) accd[b][a][c] = 0.0;
 
-  for (int64_t row0 = (int64_t)blockIdx.x * RC; row0 < n; row0 += (int64_t)gridDim.x * RC) {
-    // stage the chunk: thread t loads row (t % RC) of columns t/RC, t/RC+4, ...
-    const int rr = t % RC;
-    const int64_t grow = row0 + rr;
-    for (int j = t / RC; j < BSMAX; j += kThreads / RC) {
-      Ls[j][rr] = (j < bl && grow < n) ? L[grow + (int64_t)j * n] : (T)0;
+  if (tid >= kThreads) {
+    if (tid == kThreads) {                      // producer
+      const uint64_t pol = policy_evict_first();
+      int it = 0;
+      for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+        const int s = it % GSTAGES;
+        const uint32_t ph = (uint32_t)((it / GSTAGES) & 1);
+        mbar_wait(&sm->empty[s], ph ^ 1u);
+        const int64_t r0 = c * RC;
+        const int rows = (int)((n - r0 < RC) ? (n - r0) : RC);
+        const uint32_t bytes = (uint32_t)rows * BS * (uint32_t)sizeof(T);
+        mbar_expect_tx(&sm->full[s], bytes * (1 + NR));
+        bulk_g2s(sm->buf[s][0], L + r0 * BS, bytes, &sm->full[s], pol);
 #pragma unroll
-      for (int b = 0; b < NR; ++b) Rs[b][j][rr] = (j < br && grow < n) ? Rp[b][grow + (int64_t)j * n] : (T)0;
+        for (int b = 0; b < NR; ++b) bulk_g2s(sm->buf[s][1 + b], Rp[b] + r0 * BS, bytes, &sm->full[s], pol);
+      }
     }
-    __syncthreads();
-    T acc[NR][4][4];
+  } else {
+    int it = 0;
+    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+      const int s = it % GSTAGES;
+      const uint32_t ph = (uint32_t)((it / GSTAGES) & 1);
+      const int64_t r0 = c * RC;
+      const int rows = (int)((n - r0 < RC) ? (n - r0) : RC);
+      mbar_wait(&sm->full[s], ph);
+      T acc[NR][4][4];
 #pragma unroll
-    for (int b = 0; b < NR; ++b)
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[b][a][c] = (T)0;
-#pragma unroll
-    for (int q = 0; q < RC / 16; ++q) {
-      const int r = g + 16 * q;
-      T l[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) l[a] = Ls[4 * ti + a][r];
-#pragma unroll
-      for (int b = 0; b < NR; ++b) {
-        T rv[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) rv[c] = Rs[b][4 * tj + c][r];
+      for (int b = 0; b < NR; ++b)
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[b][a][c] += l[a] * rv[c];
-      }
-    }
+          for (int cc = 0; cc < 4; ++cc) acc[b][a][cc] = (T)0;
 #pragma unroll
-    for (int b = 0; b < NR; ++b)
+      for (int q = 0; q < RC / 16; ++q) {
+        const int r = g + 16 * q;
+        if (r < rows) {
+          T l[4];
+          const T *lp = &sm->buf[s][0][r * BS + 4 * ti];
+#pragma unroll
+          for (int a = 0; a < 4; ++a) l[a] = lp[a];
+#pragma unroll
+          for (int b = 0; b < NR; ++b) {
+            const T *rp = &sm->buf[s][1 + b][r * BS + 4 * tj];
+            T rv[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) rv[cc] = rp[cc];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc) acc[b][a][cc] += l[a] * rv[cc];
+          }
+        }
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) mbar_arrive(&sm->empty[s]);
+#pragma unroll
+      for (int b = 0; b < NR; ++b)
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) accd[b][a][cc] += (double)acc[b][a][cc];
+    }
+  }
+  __syncthreads();   // all TMA data consumed: the ring memory is reused for the cross-group reduction
+  double(*red)[257] = reinterpret_cast<double(*)[257]>(smem_raw);
+  static_assert(sizeof(GramSmem<T, NR>) >= sizeof(double) * 16 * 257, "reduction scratch does not fit");
+  for (int b = 0; b < NR; ++b) {
+    if (tid < kThreads) {
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) accd[b][a][c] += (double)acc[b][a][c];
+        for (int c = 0; c < 4; ++c) red[g][(4 * ti + a) * 16 + 4 * tj + c] = accd[b][a][c];
+    }
+    __syncthreads();
+    if (tid < kThreads) {
+      double s = 0.0;
+      for (int gg = 0; gg < 16; ++gg) s += red[gg][tid];
+      partials[((size_t)blockIdx.x * NR + b) * 256 + tid] = s;
+    }
     __syncthreads();
   }
-  // reduce the 16 row groups, one right block at a time
-  for (int b = 0; b < NR; ++b) {
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) red[g][(4 * ti + a) * 16 + 4 * tj + c] = accd[b][a][c];
-    __syncthreads();
-    double s = 0.0;
-    for (int gg = 0; gg < 16; ++gg) s += red[gg][t];
-    partials[((size_t)blockIdx.x * NR + b) * 256 + t] = s;
-    __syncthreads();
-  }
-  if (t == 0) {
+  if (tid == 0) {
     __threadfence();
     is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  for (int b = 0; b < NR; ++b) {
-    double s = 0.0;
-    for (unsigned int blk = 0; blk < gridDim.x; ++blk) s += __ldcg(&partials[((size_t)blk * NR + b) * 256 + t]);
-    out[b * 256 + t] = s;      // out[b][i*16 + j] = G_b[i][j]
+  if (tid < kThreads) {
+    for (int b = 0; b < NR; ++b) {
+      double s = 0.0;
+      for (unsigned int blk = 0; blk < gridDim.x; ++blk) s += __ldcg(&partials[((size_t)blk * NR + b) * 256 + tid]);
+      out[b * 256 + tid] = s;      // out[b][i*16 + j] = G_b[i][j]
+    }
   }
-  if (t == 0) *ticket = 0u;
+  if (tid == 0) *ticket = 0u;
 }
 
 // rdiv!(A, U::UpperTriangular) row by row (reference src/lobpcg.jl:345-355), up to 2 blocks per launch
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_rdiv(T *__restrict__ X0, T *__restrict__ X1, int nblk, int bs,
                                                    int64_t n, const T *__restrict__ Ufac /* bs x bs col-major */) {
-  __shared__ T U[BSMAX][BSMAX];
-  for (int q = threadIdx.x; q < BSMAX * BSMAX; q += kThreads) {
-    const int i = q % BSMAX, j = q / BSMAX;
+  __shared__ T U[BS][BS];
+  for (int q = threadIdx.x; q < BS * BS; q += kThreads) {
+    const int i = q % BS, j = q / BS;
     U[i][j] = (i < bs && j < bs) ? Ufac[i + j * bs] : (T)(i == j);
   }
   __syncthreads();
   for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
     for (int blk = 0; blk < nblk; ++blk) {
-      T *X = blk == 0 ? X0 : X1;
-      T a[BSMAX];
-#pragma unroll
-      for (int j = 0; j < BSMAX; ++j) a[j] = j < bs ? X[r + (int64_t)j * n] : (T)0;
+      T *X = (blk == 0 ? X0 : X1) + r * BS;
+      T a[BS];
+      load_row<T>(X, a);
       a[0] = a[0] / U[0][0];                                         // :347
 #pragma unroll
-      for (int i = 1; i < BSMAX; ++i) {
+      for (int i = 1; i < BS; ++i) {
         if (i < bs) {
 #pragma unroll
           for (int j = 0; j < i; ++j) a[i] = a[i] - a[j] * U[j][i];   // :350
           a[i] = a[i] / U[i][i];                                      // :352
         }
       }
-#pragma unroll
-      for (int j = 0; j < BSMAX; ++j)
-        if (j < bs) X[r + (int64_t)j * n] = a[j];
+      store_row<T>(X, a);
     }
   }
 }
 
-// out[j] (16 per row) = sum_i in[i] * V[i][j]
+// out[j] += sum_i in[i] * V[i][j]
 template <typename T>
-__device__ __forceinline__ void row_times_v(const T (&in)[BSMAX], int nin, const T (*V)[BSMAX], T (&out)[BSMAX]) {
+__device__ __forceinline__ void row_times_v(const T (&in)[BS], int nin, const T (*V)[BS], T (&out)[BS]) {
 #pragma unroll
-  for (int i = 0; i < BSMAX; ++i) {
+  for (int i = 0; i < BS; ++i) {
     if (i < nin) {
 #pragma unroll
-      for (int j = 0; j < BSMAX; ++j) out[j] += in[i] * V[i][j];
+      for (int j = 0; j < BS; ++j) out[j] += in[i] * V[i][j];
     }
   }
 }
 
 struct UpdateArgs {
-  void *X, *AX, *P, *AP, *R;          // in/out blocks, sizeX columns
-  const void *aR, *aAR, *aP, *aAP;    // active blocks, bs1 / bs2 columns
+  void *X, *AX, *P, *AP, *R;          // in/out blocks
+  const void *aR, *aAR, *aP, *aAP;    // active blocks, bs1 / bs2 columns used
   int sizeX, bs1, bs2;
   int64_t n;
 };
 
-// update_X_P! (:629-690) + residuals! (:533-547) in one pass.  Vx: sizeX x sizeX, Vr: bs1 x sizeX, Vp: bs2 x sizeX
-// (row-major [i][j] in the staging buffer, zero padded to 16 x 16); lambda: sizeX.
+// update_X_P! (:629-690) + residuals! (:533-547) in one pass.  Vbuf: Vx | Vr | Vp as 16x16 row-major [i][j]
+// (zero padded), lambda: 16.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_update(UpdateArgs a, const T *__restrict__ Vbuf,
                                                      const T *__restrict__ lambda, double *partials,
                                                      unsigned int *ticket, double *__restrict__ norms2) {
-  __shared__ T Vx[BSMAX][BSMAX], Vr[BSMAX][BSMAX], Vp[BSMAX][BSMAX];
-  __shared__ T lam[BSMAX];
-  __shared__ double smem[kThreads / 32][BSMAX];
+  __shared__ T Vx[BS][BS], Vr[BS][BS], Vp[BS][BS];
+  __shared__ T lam[BS];
+  __shared__ double smem[kThreads / 32][BS];
   __shared__ bool is_last;
-  for (int q = threadIdx.x; q < BSMAX * BSMAX; q += kThreads) {
+  for (int q = threadIdx.x; q < BS * BS; q += kThreads) {
     (&Vx[0][0])[q] = Vbuf[q];
     (&Vr[0][0])[q] = Vbuf[256 + q];
     (&Vp[0][0])[q] = Vbuf[512 + q];
   }
-  if (threadIdx.x < BSMAX) lam[threadIdx.x] = threadIdx.x < a.sizeX ? lambda[threadIdx.x] : (T)0;
+  if (threadIdx.x < BS) lam[threadIdx.x] = threadIdx.x < a.sizeX ? lambda[threadIdx.x] : (T)0;
   __syncthreads();
   T *X = (T *)a.X, *AX = (T *)a.AX, *P = (T *)a.P, *AP = (T *)a.AP, *R = (T *)a.R;
   const T *aR = (const T *)a.aR, *aAR = (const T *)a.aAR, *aP = (const T *)a.aP, *aAP = (const T *)a.aAP;
   const int64_t n = a.n;
-  double nrm[BSMAX];
+  double nrm[BS];
 #pragma unroll
-  for (int j = 0; j < BSMAX; ++j) nrm[j] = 0.0;
+  for (int j = 0; j < BS; ++j) nrm[j] = 0.0;
   for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
-    T in[BSMAX], pn[BSMAX], xn[BSMAX];
+    const int64_t o = r * BS;
+    T in[BS], pn[BS], xn[BS];
     // ---- block: P = aR Vr + aP Vp ; X = X Vx + P
 #pragma unroll
-    for (int j = 0; j < BSMAX; ++j) pn[j] = (T)0;
+    for (int j = 0; j < BS; ++j) pn[j] = (T)0;
     if (a.bs1 > 0) {
-#pragma unroll
-      for (int j = 0; j < BSMAX; ++j) in[j] = j < a.bs1 ? aR[r + (int64_t)j * n] : (T)0;
+      load_row<T>(aR + o, in);
       row_times_v<T>(in, a.bs1, Vr, pn);
     }
     if (a.bs2 > 0) {
-#pragma unroll
-      for (int j = 0; j < BSMAX; ++j) in[j] = j < a.bs2 ? aP[r + (int64_t)j * n] : (T)0;
-      row_times_v<T>(in, a.bs2, Vp, pn);                                     // + aP Vp  (:652-658)
+      load_row<T>(aP + o, in);
+      row_times_v<T>(in, a.bs2, Vp, pn);                                    // + aP Vp  (:652-658)
     }
+    load_row<T>(X + o, in);
 #pragma unroll
-    for (int j = 0; j < BSMAX; ++j) in[j] = j < a.sizeX ? X[r + (int64_t)j * n] : (T)0;
-#pragma unroll
-    for (int j = 0; j < BSMAX; ++j) xn[j] = (T)0;
+    for (int j = 0; j < BS; ++j) xn[j] = (T)0;
     row_times_v<T>(in, a.sizeX, Vx, xn);
     if (a.bs1 > 0) {
 #pragma unroll
-      for (int j = 0; j < BSMAX; ++j) {
-        xn[j] = xn[j] + pn[j];                                              // tempX .+ P  :675
-        if (j < a.sizeX) P[r + (int64_t)j * n] = pn[j];
-      }
+      for (int j = 0; j < BS; ++j) xn[j] = xn[j] + pn[j];                   // tempX .+ P  (:675)
+      store_row<T>(P + o, pn);
     }
-#pragma unroll
-    for (int j = 0; j < BSMAX; ++j)
-      if (j < a.sizeX) X[r + (int64_t)j * n] = xn[j];
+    store_row<T>(X + o, xn);
     // ---- A block: AP = aAR Vr + aAP Vp ; AX = AX Vx + AP
-    T an[BSMAX];
 #pragma unroll
-    for (int j = 0; j < BSMAX; ++j) pn[j] = (T)0;
+    for (int j = 0; j < BS; ++j) pn[j] = (T)0;
     if (a.bs1 > 0) {
-#pragma unroll
-      for (int j = 0; j < BSMAX; ++j) in[j] = j < a.bs1 ? aAR[r + (int64_t)j * n] : (T)0;
+      load_row<T>(aAR + o, in);
       row_times_v<T>(in, a.bs1, Vr, pn);
     }
     if (a.bs2 > 0) {
-#pragma unroll
-      for (int j = 0; j < BSMAX; ++j) in[j] = j < a.bs2 ? aAP[r + (int64_t)j * n] : (T)0;
+      load_row<T>(aAP + o, in);
       row_times_v<T>(in, a.bs2, Vp, pn);
     }
+    load_row<T>(AX + o, in);
+    T an[BS];
 #pragma unroll
-    for (int j = 0; j < BSMAX; ++j) in[j] = j < a.sizeX ? AX[r + (int64_t)j * n] : (T)0;
-#pragma unroll
-    for (int j = 0; j < BSMAX; ++j) an[j] = (T)0;
+    for (int j = 0; j < BS; ++j) an[j] = (T)0;
     row_times_v<T>(in, a.sizeX, Vx, an);
     if (a.bs1 > 0) {
 #pragma unroll
-      for (int j = 0; j < BSMAX; ++j) {
-        an[j] = an[j] + pn[j];
-        if (j < a.sizeX) AP[r + (int64_t)j * n] = pn[j];
-      }
+      for (int j = 0; j < BS; ++j) an[j] = an[j] + pn[j];
+      store_row<T>(AP + o, pn);
     }
+    store_row<T>(AX + o, an);
     // ---- residuals!: R = AX - X * Diagonal(lambda)  (:535-536) and column norms (:538-545)
 #pragma unroll
-    for (int j = 0; j < BSMAX; ++j) {
-      if (j < a.sizeX) {
-        AX[r + (int64_t)j * n] = an[j];
-        const T res = an[j] - xn[j] * lam[j];
-        R[r + (int64_t)j * n] = res;
-        nrm[j] += (double)res * (double)res;
-      }
+    for (int j = 0; j < BS; ++j) {
+      const T res = j < a.sizeX ? an[j] - xn[j] * lam[j] : (T)0;
+      pn[j] = res;
+      nrm[j] += (double)res * (double)res;
     }
+    store_row<T>(R + o, pn);
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < BSMAX; ++j) {
+  for (int j = 0; j < BS; ++j) {
     const double v = warp_sum(nrm[j]);
     if (lane == 0) smem[warp][j] = v;
   }
   __syncthreads();
-  if (threadIdx.x < BSMAX) {
+  if (threadIdx.x < BS) {
     double s = 0.0;
     for (int w = 0; w < kThreads / 32; ++w) s += smem[w][threadIdx.x];
     partials[(size_t)blockIdx.x * kMaxReduceWidth + threadIdx.x] = s;
@@ -289,7 +409,7 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateArgs a, const T *__re
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (threadIdx.x < BSMAX) {
+  if (threadIdx.x < BS) {
     double s = 0.0;
     for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * kMaxReduceWidth + threadIdx.x]);
     norms2[threadIdx.x] = s;
@@ -297,21 +417,38 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateArgs a, const T *__re
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
-// dst[:, k] = src[:, idx[k]]  (update_active! :557-562)
+// dst[:, k] = src[:, idx[k]] for k < bs, zero beyond  (update_active! :557-562)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_gather_cols(T *__restrict__ dst, const T *__restrict__ src, int64_t n,
                                                           int bs, const int *__restrict__ idx) {
-  for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads)
-    for (int k = 0; k < bs; ++k) dst[r + (int64_t)k * n] = src[r + (int64_t)idx[k] * n];
+  __shared__ int sidx[BS];
+  if (threadIdx.x < BS) sidx[threadIdx.x] = threadIdx.x < bs ? idx[threadIdx.x] : -1;
+  __syncthreads();
+  for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
+    T in[BS], out[BS];
+    load_row<T>(src + r * BS, in);
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+      T v = (T)0;
+#pragma unroll
+      for (int j = 0; j < BS; ++j)
+        if (sidx[k] == j) v = in[j];
+      out[k] = v;
+    }
+    store_row<T>(dst + r * BS, out);
+  }
 }
 
 // precond!(R[:,1:bs]) with a Jacobi M: R[:,j] ./= d  (:236-242)
 template <typename T>
-__global__ void __launch_bounds__(kThreads) k_block_jacobi(T *__restrict__ X, int64_t n, int bs,
-                                                           const T *__restrict__ d) {
+__global__ void __launch_bounds__(kThreads) k_block_jacobi(T *__restrict__ X, int64_t n, const T *__restrict__ d) {
   for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
+    T v[BS];
+    load_row<T>(X + r * BS, v);
     const T di = d[r];
-    for (int k = 0; k < bs; ++k) X[r + (int64_t)k * n] = X[r + (int64_t)k * n] / di;
+#pragma unroll
+    for (int j = 0; j < BS; ++j) v[j] = v[j] / di;
+    store_row<T>(X + r * BS, v);
   }
 }
 
@@ -321,36 +458,44 @@ struct Lobpcg {
   const b200_csr *A;
   int64_t n;
   int sizeX;
-  T *X, *AX, *R, *AR, *P, *AP, *gR, *gP, *gAP;   // g*: gather scratch (allocated on first partial mask)
-  double *gram_partials, *d_gram;                // device Gram output: NRMAX * 256 doubles
+  T *X, *AX, *R, *AR, *P, *AP, *gR, *gP, *gAP;   // row-major blocks; g*: gather scratch (first partial mask)
+  double *gram_partials, *d_gram;                // device Gram output: 4 * 256 doubles
   T *d_small;                                    // V (3*256) + lambda (16) + U (256)
   int *d_idx;
   DevBuf scratch;
-  int grid_gram, grid_vec;
+  int grid_gram, grid_vec, grid_spmm;
 
-  int gram(const T *L, int bl, const T *const *Rb, int nr, int br, double *host_out /* nr*256 */) {
-    cudaStream_t st = ctx->stream;
-    const T *r0 = Rb[0], *r1 = nr > 1 ? Rb[1] : Rb[0], *r2 = nr > 2 ? Rb[2] : Rb[0], *r3 = nr > 3 ? Rb[3] : Rb[0];
-    {
-      ProfScope prof(ctx, 1);
-      switch (nr) {
-        case 1: k_gram<T, 1><<<grid_gram, kThreads, 0, st>>>(L, bl, r0, r1, r2, r3, br, n, gram_partials, ctx->red.ticket, d_gram); break;
-        case 2: k_gram<T, 2><<<grid_gram, kThreads, 0, st>>>(L, bl, r0, r1, r2, r3, br, n, gram_partials, ctx->red.ticket, d_gram); break;
-        case 3: k_gram<T, 3><<<grid_gram, kThreads, 0, st>>>(L, bl, r0, r1, r2, r3, br, n, gram_partials, ctx->red.ticket, d_gram); break;
-        default: k_gram<T, 4><<<grid_gram, kThreads, 0, st>>>(L, bl, r0, r1, r2, r3, br, n, gram_partials, ctx->red.ticket, d_gram); break;
-      }
+  template <int NR>
+  int gram_launch(const T *L, const T *const *Rb) {
+    const size_t smem = sizeof(GramSmem<T, NR>);
+    static bool attr_set = false;
+    if (!attr_set) {
+      B200_CUDA(cudaFuncSetAttribute(k_gram<T, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
     }
-    B200_LAUNCH_CHECK(ctx);
-    B200_CUDA(cudaMemcpyAsync(host_out, d_gram, sizeof(double) * 256 * nr, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaStreamSynchronize(st));
+    k_gram<T, NR><<<grid_gram, kGramThreads, smem, ctx->stream>>>(L, Rb[0], Rb[NR > 1 ? 1 : 0], Rb[NR > 2 ? 2 : 0],
+                                                                  Rb[NR > 3 ? 3 : 0], n, gram_partials,
+                                                                  ctx->red.ticket, d_gram);
     return B200_OK;
   }
 
-  // CholQR (:365-393): blocks[0] is orthonormalised, blocks[1] (A-block) follows if given
+  int gram(const T *L, const T *const *Rb, int nr, double *host_out /* nr*256 */) {
+    {
+      ProfScope prof(ctx, 1);
+      if (nr == 1) B200_TRY(gram_launch<1>(L, Rb));
+      else B200_TRY(gram_launch<2>(L, Rb));
+    }
+    B200_LAUNCH_CHECK(ctx);
+    B200_CUDA(cudaMemcpyAsync(host_out, d_gram, sizeof(double) * 256 * nr, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+  }
+
+  // CholQR (:365-393): blk is orthonormalised, ablk (its A-block) follows if given
   int cholqr(T *blk, T *ablk, int bs) {
     double G[256];
     const T *rb[1] = {blk};
-    B200_TRY(gram(blk, bs, rb, 1, bs, G));
+    B200_TRY(gram(blk, rb, 1, G));
     std::vector<double> U((size_t)bs * bs);
     for (int i = 0; i < bs; ++i)
       for (int j = 0; j < bs; ++j) U[i + (size_t)j * bs] = i <= j ? G[i * 16 + j] : G[j * 16 + i];  // Hermitian(gram): upper
@@ -371,19 +516,21 @@ struct Lobpcg {
     return B200_OK;
   }
 
-  int spmm(const T *Xin, T *Yout, int bs) {
+  int spmm(const T *Xin, T *Yout) {
     ProfScope prof(ctx, 0);
-    return b200_spmm(ctx, A, Xin, n, Yout, n, bs);
+    k_spmm_rm<T><<<grid_spmm, kThreads, 0, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals, Xin, n, Yout);
+    B200_LAUNCH_CHECK(ctx);
+    return B200_OK;
   }
 };
 
 template <typename T>
-int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *X, int64_t ldx, const b200_lobpcg_opts *o,
+int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b200_lobpcg_opts *o,
                 b200_lobpcg_result *res, double *lambda_host, double *resnorm_host) {
   cudaStream_t st = ctx->stream;
   const int64_t n = A->m_local;
   const int sizeX = o->blocksize;
-  B200_REQUIRE(sizeX >= 1 && sizeX <= BSMAX, "lobpcg: block size %d not in 1..%d", sizeX, BSMAX);
+  B200_REQUIRE(sizeX >= 1 && sizeX <= BS, "lobpcg: block size %d not in 1..%d", sizeX, BS);
   B200_REQUIRE(ldx == n, "lobpcg: X must be n x blocksize with leading dimension n");
   B200_REQUIRE(sizeX <= n, "X column dimension exceeds the row dimension");                        // :833
   B200_REQUIRE(3 * (int64_t)sizeX <= n, "The LOBPCG algorithms is not stable to use when the matrix size is less "
@@ -398,26 +545,29 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *X, int64_t ldx, const b200_
   L.A = A;
   L.n = n;
   L.sizeX = sizeX;
-  L.X = X;
-  L.grid_gram = stream_grid(ctx, n, RC, 4);
+  L.grid_gram = (int)std::min<int64_t>(ctx->sm_count, (n + RC - 1) / RC);
   L.grid_vec = stream_grid(ctx, n, kThreads, 4);
-  const size_t blk_bytes = align_up(sizeof(T) * (size_t)n * sizeX, 256);
+  L.grid_spmm = stream_grid(ctx, n, kThreads / 4, 8);
+  const size_t blk_bytes = align_up(sizeof(T) * (size_t)n * BS, 256);
   const size_t small_bytes = align_up(sizeof(T) * (3 * 256 + 16 + 256), 256);
-  const size_t gram_bytes = sizeof(double) * ((size_t)L.grid_gram * NRMAX * 256 + NRMAX * 256 + 64);
+  const size_t gram_bytes = sizeof(double) * ((size_t)L.grid_gram * 4 * 256 + 4 * 256 + 64);
   void *ws = nullptr;
-  B200_TRY(ws_get(ctx, 5 * blk_bytes + small_bytes + gram_bytes + 1024, &ws));
+  B200_TRY(ws_get(ctx, 6 * blk_bytes + small_bytes + gram_bytes + 1024, &ws));
   char *p = (char *)ws;
+  L.X = (T *)p; p += blk_bytes;
   L.AX = (T *)p; p += blk_bytes;
   L.R = (T *)p; p += blk_bytes;
   L.AR = (T *)p; p += blk_bytes;
   L.P = (T *)p; p += blk_bytes;
   L.AP = (T *)p; p += blk_bytes;
   L.d_small = (T *)p; p += small_bytes;
-  L.gram_partials = (double *)p; p += sizeof(double) * (size_t)L.grid_gram * NRMAX * 256;
-  L.d_gram = (double *)p; p += sizeof(double) * NRMAX * 256;
+  L.gram_partials = (double *)p; p += sizeof(double) * (size_t)L.grid_gram * 4 * 256;
+  L.d_gram = (double *)p; p += sizeof(double) * 4 * 256;
   double *d_norms = (double *)p; p += sizeof(double) * 64;
   L.d_idx = (int *)p;
   L.gR = L.gP = L.gAP = nullptr;
+  k_to_rowmajor<T><<<L.grid_vec, kThreads, 0, st>>>(Xcm, L.X, n, sizeX);
+  B200_LAUNCH_CHECK(ctx);
 
   std::vector<double> ritz(3 * sizeX, 0.0), residuals(sizeX, NAN);                                  // :473-477
   std::vector<char> mask(sizeX, 1);
@@ -442,12 +592,12 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *X, int64_t ldx, const b200_
     ua.aR = aR; ua.aAR = aAR; ua.aP = aP; ua.aAP = aAP;
     ua.sizeX = sizeX; ua.bs1 = bs1; ua.bs2 = bs2; ua.n = n;
     {
-      ProfScope prof(ctx, 1);
+      ProfScope prof(ctx, 3);
       k_update<T><<<L.grid_vec, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, ctx->red.partials, ctx->red.ticket, d_norms);
     }
     B200_LAUNCH_CHECK(ctx);
-    double nn[BSMAX];
-    B200_CUDA(cudaMemcpyAsync(nn, d_norms, sizeof(double) * BSMAX, cudaMemcpyDeviceToHost, st));
+    double nn[BS];
+    B200_CUDA(cudaMemcpyAsync(nn, d_norms, sizeof(double) * BS, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     for (int j = 0; j < sizeX; ++j) residuals[j] = sqrt(nn[j]);                                     // :545
     return B200_OK;
@@ -463,10 +613,10 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *X, int64_t ldx, const b200_
     if (iteration == 1) {                                                                           // :695-703
       status = L.cholqr(L.X, nullptr, sizeX);                                                       // ortho_AB_mul_X! :524-532
       if (status) break;
-      B200_TRY(L.spmm(L.X, L.AX, sizeX));
+      B200_TRY(L.spmm(L.X, L.AX));
       double G[256];
       const T *rb[1] = {L.AX};
-      B200_TRY(L.gram(L.X, sizeX, rb, 1, sizeX, G));                                                // XAX :262
+      B200_TRY(L.gram(L.X, rb, 1, G));                                                              // XAX :262
       std::vector<double> Am((size_t)sizeX * sizeX), w, Z;
       for (int i = 0; i < sizeX; ++i)
         for (int j = 0; j < sizeX; ++j) Am[i + (size_t)j * sizeX] = i <= j ? G[i * 16 + j] : G[j * 16 + i];
@@ -485,7 +635,7 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *X, int64_t ldx, const b200_
           L.gP = (T *)((char *)L.scratch.p + blk_bytes);
           L.gAP = (T *)((char *)L.scratch.p + 2 * blk_bytes);
         }
-        int idx[BSMAX], k = 0;
+        int idx[BS], k = 0;
         for (int j = 0; j < sizeX; ++j)
           if (mask[j]) idx[k++] = j;
         B200_CUDA(cudaMemcpyAsync(L.d_idx, idx, sizeof(int) * bs, cudaMemcpyHostToDevice, st));
@@ -499,12 +649,12 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *X, int64_t ldx, const b200_
         aR = L.gR; aP = L.gP; aAP = L.gAP;
       }
       if (jac) {                                                                                    // precond_constr! :564-569
-        k_block_jacobi<T><<<L.grid_vec, kThreads, 0, st>>>(aR, n, bs, jac);
+        k_block_jacobi<T><<<L.grid_vec, kThreads, 0, st>>>(aR, n, jac);
         B200_LAUNCH_CHECK(ctx);
       }
       status = L.cholqr(aR, nullptr, bs);                                                           // :524-532
       if (status) break;
-      B200_TRY(L.spmm(aR, L.AR, bs));
+      B200_TRY(L.spmm(aR, L.AR));
       if (with_p) {
         status = L.cholqr(aP, aAP, bs);                                                             // :733
         if (status) break;
@@ -515,36 +665,42 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *X, int64_t ldx, const b200_
       auto setB = [&](int i, int j, double v) { gB[i + (size_t)j * sub] = v; gB[j + (size_t)i * sub] = v; };
       for (int i = 0; i < n1; ++i) setA(i, i, ritz[i]);                                             // Diagonal(lambda) :289
       for (int i = 0; i < sub; ++i) setB(i, i, 1.0);                                                // I! :315,322,331
-      double G[NRMAX * 256];
-      {   // X' [AR, R, AP, P]
-        const T *rb[4] = {L.AR, aR, aAP, aP};
-        B200_TRY(L.gram(L.X, n1, rb, with_p ? 4 : 2, n2, G));
-        for (int i = 0; i < n1; ++i)
-          for (int j = 0; j < n2; ++j) {
-            setA(i, n1 + j, G[i * 16 + j]);                                                         // XAR :265
-            setB(i, n1 + j, G[256 + i * 16 + j]);                                                   // XBR :270
-            if (with_p) {
-              setA(i, n1 + n2 + j, G[512 + i * 16 + j]);                                            // XAP :264
-              setB(i, n1 + n2 + j, G[768 + i * 16 + j]);                                            // XBP :269
-            }
+      double G[4 * 256];
+      {               // X' [AR, R]  (and X' [AP, P]): two right blocks per launch keeps the 4x4 tiles in registers
+        const T *rb[2] = {L.AR, aR};
+        B200_TRY(L.gram(L.X, rb, 2, G));
+        if (with_p) {
+          const T *rb2[2] = {aAP, aP};
+          B200_TRY(L.gram(L.X, rb2, 2, G + 512));
+        }
+      }
+      for (int i = 0; i < n1; ++i)
+        for (int j = 0; j < n2; ++j) {
+          setA(i, n1 + j, G[i * 16 + j]);                                                           // XAR :265
+          setB(i, n1 + j, G[256 + i * 16 + j]);                                                     // XBR :270
+          if (with_p) {
+            setA(i, n1 + n2 + j, G[512 + i * 16 + j]);                                              // XAP :264
+            setB(i, n1 + n2 + j, G[768 + i * 16 + j]);                                              // XBP :269
           }
-      }
-      {   // R' [AR, P]
+        }
+      if (with_p) {   // R' [AR, P]
         const T *rb[2] = {L.AR, aP};
-        B200_TRY(L.gram(aR, n2, rb, with_p ? 2 : 1, n2, G));
+        B200_TRY(L.gram(aR, rb, 2, G));
         for (int i = 0; i < n2; ++i)
-          for (int j = i; j < n2; ++j) setA(n1 + i, n1 + j, G[i * 16 + j]);                         // RAR :266 (upper triangle)
-        if (with_p)
-          for (int i = 0; i < n2; ++i)
-            for (int j = 0; j < n3; ++j) setB(n1 + i, n1 + n2 + j, G[256 + i * 16 + j]);            // RBP :271
+          for (int j = 0; j < n3; ++j) setB(n1 + i, n1 + n2 + j, G[256 + i * 16 + j]);              // RBP :271
+      } else {
+        const T *rb[1] = {L.AR};
+        B200_TRY(L.gram(aR, rb, 1, G));
       }
+      for (int i = 0; i < n2; ++i)
+        for (int j = i; j < n2; ++j) setA(n1 + i, n1 + j, G[i * 16 + j]);                           // RAR :266 (upper triangle)
       if (with_p) {
         const T *rb1[1] = {aP};
-        B200_TRY(L.gram(L.AR, n2, rb1, 1, n3, G));                                                  // RAP = AR' P :267
+        B200_TRY(L.gram(L.AR, rb1, 1, G));                                                          // RAP = AR' P :267
         for (int i = 0; i < n2; ++i)
           for (int j = 0; j < n3; ++j) setA(n1 + i, n1 + n2 + j, G[i * 16 + j]);
         const T *rb2[1] = {aAP};
-        B200_TRY(L.gram(aP, n3, rb2, 1, n3, G));                                                    // PAP :268
+        B200_TRY(L.gram(aP, rb2, 1, G));                                                            // PAP :268
         for (int i = 0; i < n3; ++i)
           for (int j = i; j < n3; ++j) setA(n1 + n2 + i, n1 + n2 + j, G[i * 16 + j]);
       }
@@ -567,6 +723,8 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *X, int64_t ldx, const b200_
     if (bs == 0) break;                                                                             // :885
     iteration += 1;                                                                                 // :886
   }
+  k_to_colmajor<T><<<L.grid_vec, kThreads, 0, st>>>(L.X, Xcm, n, sizeX);
+  B200_LAUNCH_CHECK(ctx);
   bool conv = true;
   for (int j = 0; j < sizeX; ++j) {
     if (lambda_host) lambda_host[j] = ritz[j];
