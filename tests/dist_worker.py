@@ -64,6 +64,15 @@ def main():
     L.b200_ctx_set_option(ctx._h, b"comm", 0)
     if rank == 0:
         print(f"peer_ok={peer_ok.value}")
+    # the other solvers on the same row partition (halo exchange + NCCL allreduce of their reductions)
+    b_loc = b_global[lo:lo + m].copy()
+    xm, hm = isb.minres_(np.zeros(m), A1, b_loc, initially_zero=True, log=True, reltol=1e-9)
+    xg, hg = isb.gmres_(np.zeros(m), A1, b_loc, initially_zero=True, log=True, restart=20, maxiter=60, orth_meth="dgks")
+    rsh = np.random.default_rng(7).random(n)
+    xb, hb = isb.bicgstabl_(np.zeros(m), A1, b_loc, 2, initial_zero=True, log=True, max_mv_products=120,
+                            r_shadow=rsh[lo:lo + m].copy(), reltol=1e-9)
+    others = [None] * world
+    dist.all_gather_object(others, (xm, xg, xb))
 
     gathered = [None] * world
     dist.all_gather_object(gathered, (y_loc, results["slab"][0], results["generated"][0],
@@ -93,6 +102,23 @@ def main():
             x_err = float(np.linalg.norm(xd - xs) / np.linalg.norm(xs))
             assert hist_err <= 1e-10 and x_err <= 1e-10, (name, hist_err, x_err)
             print(f"{name}: iters={h.niters} hist_err={hist_err:.2e} x_err={x_err:.2e}")
+        # minres / gmres / bicgstabl: partitioned == single GPU
+        xs, hs = isb.minres_(np.zeros(n), Ag, b_global, initially_zero=True, log=True, reltol=1e-9)
+        xd = np.concatenate([o[0] for o in others])
+        assert hm.niters == hs.niters and np.max(np.abs(hm["resnorm"] - hs["resnorm"]) / hs["resnorm"]) <= 1e-8
+        assert np.linalg.norm(xd - xs) <= 1e-8 * np.linalg.norm(xs)
+        xs, hs = isb.gmres_(np.zeros(n), Ag, b_global, initially_zero=True, log=True, restart=20, maxiter=60, orth_meth="dgks")
+        xd = np.concatenate([o[1] for o in others])
+        assert hg.niters == hs.niters and hg.mvps == hs.mvps
+        assert np.max(np.abs(hg["resnorm"] - hs["resnorm"]) / hs["resnorm"]) <= 1e-8
+        assert np.linalg.norm(xd - xs) <= 1e-8 * np.linalg.norm(xs)
+        xs, hs = isb.bicgstabl_(np.zeros(n), Ag, b_global, 2, initial_zero=True, log=True, max_mv_products=120,
+                                r_shadow=rsh.copy(), reltol=1e-9)
+        xd = np.concatenate([o[2] for o in others])
+        assert hb.niters == hs.niters and hb.mvps == hs.mvps
+        k = min(5, hs.niters)
+        assert np.max(np.abs(hb["resnorm"][:k] - hs["resnorm"][:k]) / hs["resnorm"][:k]) <= 1e-7
+        print(f"minres/gmres/bicgstabl partitioned == single: iters {hm.niters}/{hg.niters}/{hb.niters}")
         print("DIST_OK")
     dist.barrier()
     dist.destroy_process_group()
