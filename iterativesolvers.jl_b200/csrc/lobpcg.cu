@@ -140,7 +140,8 @@ struct GramSmem {
 template <typename T, int NR>
 __global__ void __launch_bounds__(kGramThreads, 1)
     k_gram(const T *__restrict__ L, const T *__restrict__ R0, const T *__restrict__ R1, const T *__restrict__ R2,
-           const T *__restrict__ R3, int64_t n, double *partials, unsigned int *ticket, double *__restrict__ out) {
+           const T *__restrict__ R3, int same0 /* R0 is L itself: stream it once */, int64_t n, double *partials,
+           unsigned int *ticket, double *__restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   GramSmem<T, NR> *sm = reinterpret_cast<GramSmem<T, NR> *>(smem_raw);
   __shared__ bool is_last;
@@ -176,10 +177,11 @@ __global__ void __launch_bounds__(kGramThreads, 1)
         const int64_t r0 = c * RC;
         const int rows = (int)((n - r0 < RC) ? (n - r0) : RC);
         const uint32_t bytes = (uint32_t)rows * BS * (uint32_t)sizeof(T);
-        mbar_expect_tx(&sm->full[s], bytes * (1 + NR));
+        mbar_expect_tx(&sm->full[s], bytes * (1 + NR - (same0 ? 1 : 0)));
         bulk_g2s(sm->buf[s][0], L + r0 * BS, bytes, &sm->full[s], pol);
 #pragma unroll
-        for (int b = 0; b < NR; ++b) bulk_g2s(sm->buf[s][1 + b], Rp[b] + r0 * BS, bytes, &sm->full[s], pol);
+        for (int b = 0; b < NR; ++b)
+          if (!(same0 && b == 0)) bulk_g2s(sm->buf[s][1 + b], Rp[b] + r0 * BS, bytes, &sm->full[s], pol);
       }
     }
   } else {
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(kGramThreads, 1)
           for (int a = 0; a < 4; ++a) l[a] = lp[a];
 #pragma unroll
           for (int b = 0; b < NR; ++b) {
-            const T *rp = &sm->buf[s][1 + b][r * BS + 4 * tj];
+            const T *rp = &sm->buf[s][(same0 && b == 0) ? 0 : 1 + b][r * BS + 4 * tj];
             T rv[4];
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) rv[cc] = rp[cc];
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(kGramThreads, 1)
 
 // rdiv!(A, U::UpperTriangular) row by row (reference src/lobpcg.jl:345-355), up to 2 blocks per launch
 template <typename T>
-__global__ void __launch_bounds__(kThreads) k_rdiv(T *__restrict__ X0, T *__restrict__ X1, int nblk, int bs,
+__global__ void __launch_bounds__(kThreads, 4) k_rdiv(T *__restrict__ X0, T *__restrict__ X1, int nblk, int bs,
                                                    int64_t n, const T *__restrict__ Ufac /* bs x bs col-major */) {
   __shared__ T U[BS][BS];
   for (int q = threadIdx.x; q < BS * BS; q += kThreads) {
@@ -311,12 +313,15 @@ struct UpdateArgs {
   int64_t n;
 };
 
-// update_X_P! (:629-690) + residuals! (:533-547) in one pass.  Vbuf: Vx | Vr | Vp as 16x16 row-major [i][j]
-// (zero padded), lambda: 16.
-template <typename T>
-__global__ void __launch_bounds__(kThreads) k_update(UpdateArgs a, const T *__restrict__ Vbuf,
-                                                     const T *__restrict__ lambda, double *partials,
-                                                     unsigned int *ticket, double *__restrict__ norms2) {
+// update_X_P! (:629-690) + residuals! (:533-547).  Vbuf: Vx | Vr | Vp as 16x16 row-major [i][j] (zero padded),
+// lambda: 16.  Two launches so that each keeps two CTAs per SM (the fused single kernel needed 228 registers):
+//   PHASE 0: P = aR Vr + aP Vp ; X = X Vx + P                                  (reads 3 blocks, writes 2)
+//   PHASE 1: AP = aAR Vr + aAP Vp ; AX = AX Vx + AP ; R = AX - X diag(lambda) ; column norms of R
+//                                                                               (reads 4 blocks, writes 3)
+template <typename T, int PHASE>
+__global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a, const T *__restrict__ Vbuf,
+                                                        const T *__restrict__ lambda, double *partials,
+                                                        unsigned int *ticket, double *__restrict__ norms2) {
   __shared__ T Vx[BS][BS], Vr[BS][BS], Vp[BS][BS];
   __shared__ T lam[BS];
   __shared__ double smem[kThreads / 32][BS];
@@ -328,8 +333,10 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateArgs a, const T *__re
   }
   if (threadIdx.x < BS) lam[threadIdx.x] = threadIdx.x < a.sizeX ? lambda[threadIdx.x] : (T)0;
   __syncthreads();
-  T *X = (T *)a.X, *AX = (T *)a.AX, *P = (T *)a.P, *AP = (T *)a.AP, *R = (T *)a.R;
-  const T *aR = (const T *)a.aR, *aAR = (const T *)a.aAR, *aP = (const T *)a.aP, *aAP = (const T *)a.aAP;
+  // PHASE 0 works on the blocks themselves, PHASE 1 on their A-images
+  T *Xb = (T *)(PHASE == 0 ? a.X : a.AX), *Pb = (T *)(PHASE == 0 ? a.P : a.AP), *R = (T *)a.R;
+  const T *Xnew = (const T *)a.X;
+  const T *aRb = (const T *)(PHASE == 0 ? a.aR : a.aAR), *aPb = (const T *)(PHASE == 0 ? a.aP : a.aAP);
   const int64_t n = a.n;
   double nrm[BS];
 #pragma unroll
@@ -337,58 +344,39 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateArgs a, const T *__re
   for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
     const int64_t o = r * BS;
     T in[BS], pn[BS], xn[BS];
-    // ---- block: P = aR Vr + aP Vp ; X = X Vx + P
 #pragma unroll
     for (int j = 0; j < BS; ++j) pn[j] = (T)0;
     if (a.bs1 > 0) {
-      load_row<T>(aR + o, in);
+      load_row<T>(aRb + o, in);
       row_times_v<T>(in, a.bs1, Vr, pn);
     }
     if (a.bs2 > 0) {
-      load_row<T>(aP + o, in);
+      load_row<T>(aPb + o, in);
       row_times_v<T>(in, a.bs2, Vp, pn);                                    // + aP Vp  (:652-658)
     }
-    load_row<T>(X + o, in);
+    load_row<T>(Xb + o, in);
 #pragma unroll
     for (int j = 0; j < BS; ++j) xn[j] = (T)0;
     row_times_v<T>(in, a.sizeX, Vx, xn);
     if (a.bs1 > 0) {
 #pragma unroll
       for (int j = 0; j < BS; ++j) xn[j] = xn[j] + pn[j];                   // tempX .+ P  (:675)
-      store_row<T>(P + o, pn);
+      store_row<T>(Pb + o, pn);
     }
-    store_row<T>(X + o, xn);
-    // ---- A block: AP = aAR Vr + aAP Vp ; AX = AX Vx + AP
+    store_row<T>(Xb + o, xn);
+    if constexpr (PHASE == 1) {
+      // residuals!: R = AX - X * Diagonal(lambda)  (:535-536) and column norms (:538-545); X is already updated
+      load_row<T>(Xnew + o, in);
 #pragma unroll
-    for (int j = 0; j < BS; ++j) pn[j] = (T)0;
-    if (a.bs1 > 0) {
-      load_row<T>(aAR + o, in);
-      row_times_v<T>(in, a.bs1, Vr, pn);
+      for (int j = 0; j < BS; ++j) {
+        const T res = j < a.sizeX ? xn[j] - in[j] * lam[j] : (T)0;
+        pn[j] = res;
+        nrm[j] += (double)res * (double)res;
+      }
+      store_row<T>(R + o, pn);
     }
-    if (a.bs2 > 0) {
-      load_row<T>(aAP + o, in);
-      row_times_v<T>(in, a.bs2, Vp, pn);
-    }
-    load_row<T>(AX + o, in);
-    T an[BS];
-#pragma unroll
-    for (int j = 0; j < BS; ++j) an[j] = (T)0;
-    row_times_v<T>(in, a.sizeX, Vx, an);
-    if (a.bs1 > 0) {
-#pragma unroll
-      for (int j = 0; j < BS; ++j) an[j] = an[j] + pn[j];
-      store_row<T>(AP + o, pn);
-    }
-    store_row<T>(AX + o, an);
-    // ---- residuals!: R = AX - X * Diagonal(lambda)  (:535-536) and column norms (:538-545)
-#pragma unroll
-    for (int j = 0; j < BS; ++j) {
-      const T res = j < a.sizeX ? an[j] - xn[j] * lam[j] : (T)0;
-      pn[j] = res;
-      nrm[j] += (double)res * (double)res;
-    }
-    store_row<T>(R + o, pn);
   }
+  if constexpr (PHASE == 0) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int j = 0; j < BS; ++j) {
@@ -474,8 +462,8 @@ struct Lobpcg {
       attr_set = true;
     }
     k_gram<T, NR><<<grid_gram, kGramThreads, smem, ctx->stream>>>(L, Rb[0], Rb[NR > 1 ? 1 : 0], Rb[NR > 2 ? 2 : 0],
-                                                                  Rb[NR > 3 ? 3 : 0], n, gram_partials,
-                                                                  ctx->red.ticket, d_gram);
+                                                                  Rb[NR > 3 ? 3 : 0], Rb[0] == L ? 1 : 0, n,
+                                                                  gram_partials, ctx->red.ticket, d_gram);
     return B200_OK;
   }
 
@@ -593,7 +581,9 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
     ua.sizeX = sizeX; ua.bs1 = bs1; ua.bs2 = bs2; ua.n = n;
     {
       ProfScope prof(ctx, 3);
-      k_update<T><<<L.grid_vec, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, ctx->red.partials, ctx->red.ticket, d_norms);
+      k_update<T, 0><<<L.grid_vec, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, nullptr, nullptr, nullptr);
+      k_update<T, 1><<<L.grid_vec, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, ctx->red.partials, ctx->red.ticket, d_norms);
+      ctx->launches++;
     }
     B200_LAUNCH_CHECK(ctx);
     double nn[BS];
