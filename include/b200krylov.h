@@ -236,6 +236,12 @@ B200_API int b200_cg_solve_host(b200_ctx *ctx, const b200_csr *A, void *x_host, 
                                 const b200_cg_opts *opts, b200_result *res, double *resnorm_host,
                                 int64_t resnorm_cap);
 
+/* chebyshev!(x, A, b, lmin, lmax; abstol, reltol, Pl, maxiter, initially_zero)  reference src/chebyshev.jl:131-160
+ * (SURVEY.md section 8f item 2).  Uses the cg option block (abstol, reltol, maxiter, initially_zero, Pl). */
+B200_API int b200_chebyshev_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
+                                  double lambda_min, double lambda_max, const b200_cg_opts *opts, b200_result *res,
+                                  double *resnorm_host, int64_t resnorm_cap);
+
 typedef struct {
   double abstol, reltol;    /* src/gmres.jl:187-188                                                */
   int64_t maxiter;          /* size(A,2)           src/gmres.jl:190                                */

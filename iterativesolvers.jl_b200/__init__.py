@@ -15,5 +15,5 @@ from .device import Context, DeviceArray, default_context, pinned_empty  # noqa:
 from .operators import B200CSR, HaloPlan, Identity, JacobiPrec  # noqa: F401
 from .history import ConvergenceHistory  # noqa: F401
 from .generators import laplace_matrix, laplace_csr_slab, advection_dominated  # noqa: F401
-from .solvers import (cg, cg_, gmres, gmres_, minres, minres_, bicgstabl, bicgstabl_, lobpcg,  # noqa: F401
+from .solvers import (cg, cg_, chebyshev, chebyshev_, gmres, gmres_, minres, minres_, bicgstabl, bicgstabl_, lobpcg,  # noqa: F401
                       LOBPCGResults, orthogonalize_and_normalize_, hessenberg_ldiv_)

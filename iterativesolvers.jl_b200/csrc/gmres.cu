@@ -22,24 +22,54 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int JB = 8;  // columns of V per register block
 
+// VEC consecutive rows per thread: VEC = 2 uses 128-bit (fp64) / 64-bit (fp32) accesses.  The first ncu capture of
+// the scalar versions showed both orthogonalisation kernels latency-bound ("long scoreboard" 34-95 per issue,
+// 5.2 TB/s): wider accesses and explicitly independent column loads double the bytes in flight per thread.
+template <typename T, int VEC>
+__device__ __forceinline__ void ldv(const T *p, T (&v)[VEC]) {
+  if constexpr (VEC == 1) v[0] = *p;
+  else if constexpr (sizeof(T) == 8) {
+    const double2 t = *reinterpret_cast<const double2 *>(p);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    const float2 t = *reinterpret_cast<const float2 *>(p);
+    v[0] = t.x; v[1] = t.y;
+  }
+}
+template <typename T, int VEC>
+__device__ __forceinline__ void stv(T *p, const T (&v)[VEC]) {
+  if constexpr (VEC == 1) *p = v[0];
+  else if constexpr (sizeof(T) == 8) *reinterpret_cast<double2 *>(p) = make_double2(v[0], v[1]);
+  else *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+}
+
 // h[j0+j] = sum_i V[i, j0+j] * w[i]  for all j < k.  Partials: partials[block * kMaxReduceWidth + j].
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads) k_block_dots(const T *__restrict__ V, int64_t ld, int k,
                                                          const T *__restrict__ w, int64_t n, double *partials,
                                                          unsigned int *ticket, double *__restrict__ out) {
   __shared__ double smem[kThreads / 32][JB];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nv = n / VEC;   // VEC == 2 is only launched when n is even
   for (int j0 = 0; j0 < k; j0 += JB) {
     const int jn = min(JB, k - j0);
     double acc[JB];
 #pragma unroll
     for (int j = 0; j < JB; ++j) acc[j] = 0.0;
-    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-      const double wi = (double)w[i];
+    for (int64_t iv = blockIdx.x * (int64_t)kThreads + threadIdx.x; iv < nv; iv += (int64_t)gridDim.x * kThreads) {
+      const int64_t i = iv * VEC;
+      T wv[VEC], vv[JB][VEC];
+      ldv<T, VEC>(w + i, wv);
 #pragma unroll
       for (int j = 0; j < JB; ++j)
-        if (j < jn) acc[j] += (double)V[i + (int64_t)(j0 + j) * ld] * wi;
+        if (j < jn) ldv<T, VEC>(V + i + (int64_t)(j0 + j) * ld, vv[j]);
+#pragma unroll
+      for (int j = 0; j < JB; ++j)
+        if (j < jn) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) acc[j] += (double)vv[j][e] * (double)wv[e];
+        }
     }
 #pragma unroll
     for (int j = 0; j < JB; ++j) acc[j] = warp_sum(acc[j]);
@@ -71,21 +101,49 @@ __global__ void __launch_bounds__(kThreads) k_block_dots(const T *__restrict__ V
 }
 
 // out[i] = base[i] + sign * sum_j V[i,j] * y[j] ; optionally sum of out[i]^2 -> nrm2_out[0]
-template <typename T, bool WITH_NORM>
+template <typename T, bool WITH_NORM, int VEC>
 __global__ void __launch_bounds__(kThreads) k_block_axpy(const T *__restrict__ V, int64_t ld, int k,
                                                          const double *__restrict__ y, double sign,
                                                          const T *base, T *out, int64_t n, double *partials,
                                                          unsigned int *ticket, double *nrm2_out) {
-  __shared__ double sy[kMaxReduceWidth];
+  __shared__ T sy[kMaxReduceWidth];
   __shared__ double smem[kThreads / 32];
-  for (int j = threadIdx.x; j < k; j += kThreads) sy[j] = sign * y[j];
+  for (int j = threadIdx.x; j < k; j += kThreads) sy[j] = (T)(sign * y[j]);
   __syncthreads();
   double acc = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    T t = base[i];
-    for (int j = 0; j < k; ++j) t += (T)sy[j] * V[i + (int64_t)j * ld];
-    out[i] = t;
-    if (WITH_NORM) acc += (double)t * (double)t;
+  const int64_t nv = n / VEC;
+  for (int64_t iv = blockIdx.x * (int64_t)kThreads + threadIdx.x; iv < nv; iv += (int64_t)gridDim.x * kThreads) {
+    const int64_t i = iv * VEC;
+    T t[VEC];
+    ldv<T, VEC>(base + i, t);
+    int j = 0;
+    for (; j + JB <= k; j += JB) {       // JB independent column loads in flight, then the ordered accumulation
+      T vv[JB][VEC];
+#pragma unroll
+      for (int u = 0; u < JB; ++u) ldv<T, VEC>(V + i + (int64_t)(j + u) * ld, vv[u]);
+#pragma unroll
+      for (int u = 0; u < JB; ++u) {
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) t[e] += sy[j + u] * vv[u][e];
+      }
+    }
+    if (j < k) {
+      T vv[JB][VEC];
+#pragma unroll
+      for (int u = 0; u < JB; ++u)
+        if (j + u < k) ldv<T, VEC>(V + i + (int64_t)(j + u) * ld, vv[u]);
+#pragma unroll
+      for (int u = 0; u < JB; ++u)
+        if (j + u < k) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) t[e] += sy[j + u] * vv[u][e];
+        }
+    }
+    stv<T, VEC>(out + i, t);
+    if (WITH_NORM) {
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) acc += (double)t[e] * (double)t[e];
+    }
   }
   if (WITH_NORM) {
     acc = block_sum<kThreads>(acc, smem);
@@ -149,14 +207,34 @@ __global__ void k_hessenberg_ldiv(double *__restrict__ H, int ldh, int m, double
 
 int gridv(const b200_ctx *ctx, int64_t n) { return stream_grid(ctx, n, kThreads * 2, 8); }
 
+// grid = one full wave of the kernel's real occupancy (grid-stride loops: a partial last wave is pure tail)
+template <typename K>
+int grid_one_wave(const b200_ctx *ctx, K kernel, int64_t n) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 2;
+  return stream_grid(ctx, n, kThreads * 2, per_sm);
+}
+
+// two rows per thread when every column start stays 2*sizeof(T)-aligned
+template <typename T>
+bool can_vec2(int64_t n, int64_t ld, std::initializer_list<const void *> ptrs) {
+  if ((n & 1) || (ld & 1)) return false;
+  for (const void *p : ptrs)
+    if (reinterpret_cast<uintptr_t>(p) % (2 * sizeof(T))) return false;
+  return true;
+}
+
 template <typename T>
 int block_dots(b200_ctx *ctx, const T *V, int64_t ld, int k, const T *w, int64_t n, double *out_dev) {
+  const bool v2 = can_vec2<T>(n, ld, {V, w});
   // chunks of at most kMaxReduceWidth columns
   for (int j0 = 0; j0 < k; j0 += kMaxReduceWidth) {
     const int kk = std::min(kMaxReduceWidth, k - j0);
     ProfScope prof(ctx, 1);
-    k_block_dots<T><<<gridv(ctx, n), kThreads, 0, ctx->stream>>>(V + (int64_t)j0 * ld, ld, kk, w, n, ctx->red.partials,
-                                                                ctx->red.ticket, out_dev + j0);
+    auto kern = v2 ? k_block_dots<T, 2> : k_block_dots<T, 1>;
+    kern<<<grid_one_wave(ctx, kern, n), kThreads, 0, ctx->stream>>>(V + (int64_t)j0 * ld, ld, kk, w, n,
+                                                                    ctx->red.partials, ctx->red.ticket, out_dev + j0);
     ctx->launches++;
   }
   B200_CUDA(cudaPeekAtLastError());
@@ -171,10 +249,17 @@ int block_axpy(b200_ctx *ctx, const T *V, int64_t ld, int k, const double *y_dev
     const bool last = j0 + kMaxReduceWidth >= k;
     const T *src = j0 == 0 ? base : out;
     ProfScope prof(ctx, 1);
-    if (last && nrm2_dev)
-      k_block_axpy<T, true><<<gridv(ctx, n), kThreads, 0, ctx->stream>>>(V + (int64_t)j0 * ld, ld, kk, y_dev + j0, sign, src, out, n, ctx->red.partials, ctx->red.ticket, nrm2_dev);
-    else
-      k_block_axpy<T, false><<<gridv(ctx, n), kThreads, 0, ctx->stream>>>(V + (int64_t)j0 * ld, ld, kk, y_dev + j0, sign, src, out, n, nullptr, nullptr, nullptr);
+    const bool v2 = can_vec2<T>(n, ld, {V, src, out});
+    const T *Vj = V + (int64_t)j0 * ld;
+    if (last && nrm2_dev) {
+      auto kern = v2 ? k_block_axpy<T, true, 2> : k_block_axpy<T, true, 1>;
+      kern<<<grid_one_wave(ctx, kern, n), kThreads, 0, ctx->stream>>>(Vj, ld, kk, y_dev + j0, sign, src, out, n,
+                                                                      ctx->red.partials, ctx->red.ticket, nrm2_dev);
+    } else {
+      auto kern = v2 ? k_block_axpy<T, false, 2> : k_block_axpy<T, false, 1>;
+      kern<<<grid_one_wave(ctx, kern, n), kThreads, 0, ctx->stream>>>(Vj, ld, kk, y_dev + j0, sign, src, out, n,
+                                                                      nullptr, nullptr, nullptr);
+    }
     ctx->launches++;
     if (last) break;
   }

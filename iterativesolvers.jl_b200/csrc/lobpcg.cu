@@ -35,7 +35,20 @@ constexpr int kThreads = 256;
 constexpr int BS = 16;             // padded block width
 constexpr int RC = 128;            // rows per Gram chunk
 constexpr int GSTAGES = 4;
-constexpr int kGramThreads = kThreads + 32;
+constexpr int kGramConsumers = 2 * kThreads;      // two consumer groups of 256 threads
+constexpr int kGramThreads = kGramConsumers + 32; // + producer warp
+
+// 4 consecutive values from shared memory as one (fp32) or two (fp64) 128-bit loads
+template <typename T>
+__device__ __forceinline__ void lds4(const T *p, T (&v)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    const float4 t = *reinterpret_cast<const float4 *>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  } else {
+    const double2 a = reinterpret_cast<const double2 *>(p)[0], b = reinterpret_cast<const double2 *>(p)[1];
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+}
 
 template <typename T>
 __device__ __forceinline__ void load_row(const T *__restrict__ p, T (&v)[BS]) {
@@ -156,18 +169,24 @@ __global__ void __launch_bounds__(kGramThreads, 1)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  const int g = tid >> 4;                       // row group 0..15 (consumers)
-  const int ti = (tid & 15) >> 2, tj = tid & 3;
-  double accd[NR][4][4];
+  // consumers: two groups of 256 threads work on alternate chunks (first ncu capture with one group:
+  // issue 43 %, 9 warps resident -> dependency-bound); inside a group 16 row groups x 16 (4x4) tiles.
+  const int grp = tid / kThreads;               // 0, 1 (consumers), 2 (producer warp)
+  const int lt = tid % kThreads;
+  const int g = lt >> 4;                        // row group 0..15 inside the consumer group
+  const int ti = (lt & 15) >> 2, tj = lt & 3;
+  // accumulators in the operand precision over the thread's whole run (<= n/(148*32) rows per thread: fp32
+  // rounding stays ~1e-6 relative per partial); the cross-thread and cross-CTA sums are fp64
+  T acc[NR][4][4];
 #pragma unroll
   for (int b = 0; b < NR; ++b)
 #pragma unroll
     for (int a = 0; a < 4; ++a)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) accd[b][a][c] = 0.0;
+      for (int c = 0; c < 4; ++c) acc[b][a][c] = (T)0;
 
-  if (tid >= kThreads) {
-    if (tid == kThreads) {                      // producer
+  if (tid >= kGramConsumers) {
+    if (tid == kGramConsumers) {                // producer
       const uint64_t pol = policy_evict_first();
       int it = 0;
       for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
@@ -185,34 +204,24 @@ __global__ void __launch_bounds__(kGramThreads, 1)
       }
     }
   } else {
-    int it = 0;
-    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
-      const int s = it % GSTAGES;
-      const uint32_t ph = (uint32_t)((it / GSTAGES) & 1);
+    for (int64_t k = grp;; k += 2) {
+      const int64_t c = (int64_t)blockIdx.x + k * gridDim.x;
+      if (c >= nchunks) break;
+      const int s = (int)(k % GSTAGES);
+      const uint32_t ph = (uint32_t)((k / GSTAGES) & 1);
       const int64_t r0 = c * RC;
       const int rows = (int)((n - r0 < RC) ? (n - r0) : RC);
       mbar_wait(&sm->full[s], ph);
-      T acc[NR][4][4];
-#pragma unroll
-      for (int b = 0; b < NR; ++b)
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) acc[b][a][cc] = (T)0;
-#pragma unroll
+#pragma unroll 2
       for (int q = 0; q < RC / 16; ++q) {
         const int r = g + 16 * q;
         if (r < rows) {
           T l[4];
-          const T *lp = &sm->buf[s][0][r * BS + 4 * ti];
-#pragma unroll
-          for (int a = 0; a < 4; ++a) l[a] = lp[a];
+          lds4<T>(&sm->buf[s][0][r * BS + 4 * ti], l);
 #pragma unroll
           for (int b = 0; b < NR; ++b) {
-            const T *rp = &sm->buf[s][(same0 && b == 0) ? 0 : 1 + b][r * BS + 4 * tj];
             T rv[4];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) rv[cc] = rp[cc];
+            lds4<T>(&sm->buf[s][(same0 && b == 0) ? 0 : 1 + b][r * BS + 4 * tj], rv);
 #pragma unroll
             for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -222,28 +231,22 @@ __global__ void __launch_bounds__(kGramThreads, 1)
       }
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&sm->empty[s]);
-#pragma unroll
-      for (int b = 0; b < NR; ++b)
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) accd[b][a][cc] += (double)acc[b][a][cc];
     }
   }
   __syncthreads();   // all TMA data consumed: the ring memory is reused for the cross-group reduction
-  double(*red)[257] = reinterpret_cast<double(*)[257]>(smem_raw);
-  static_assert(sizeof(GramSmem<T, NR>) >= sizeof(double) * 16 * 257, "reduction scratch does not fit");
+  double(*red)[256] = reinterpret_cast<double(*)[256]>(smem_raw);
+  static_assert(sizeof(GramSmem<T, NR>) >= sizeof(double) * 32 * 256, "reduction scratch does not fit");
   for (int b = 0; b < NR; ++b) {
-    if (tid < kThreads) {
+    if (tid < kGramConsumers) {
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) red[g][(4 * ti + a) * 16 + 4 * tj + c] = accd[b][a][c];
+        for (int c = 0; c < 4; ++c) red[grp * 16 + g][(4 * ti + a) * 16 + 4 * tj + c] = (double)acc[b][a][c];
     }
     __syncthreads();
     if (tid < kThreads) {
       double s = 0.0;
-      for (int gg = 0; gg < 16; ++gg) s += red[gg][tid];
+      for (int gg = 0; gg < 32; ++gg) s += red[gg][tid];
       partials[((size_t)blockIdx.x * NR + b) * 256 + tid] = s;
     }
     __syncthreads();
@@ -319,7 +322,7 @@ struct UpdateArgs {
 //   PHASE 1: AP = aAR Vr + aAP Vp ; AX = AX Vx + AP ; R = AX - X diag(lambda) ; column norms of R
 //                                                                               (reads 4 blocks, writes 3)
 template <typename T, int PHASE>
-__global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a, const T *__restrict__ Vbuf,
+__global__ void __launch_bounds__(kThreads) k_update(UpdateArgs a, const T *__restrict__ Vbuf,
                                                         const T *__restrict__ lambda, double *partials,
                                                         unsigned int *ticket, double *__restrict__ norms2) {
   __shared__ T Vx[BS][BS], Vr[BS][BS], Vp[BS][BS];
@@ -343,18 +346,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_update(UpdateArgs a, const T *_
   for (int j = 0; j < BS; ++j) nrm[j] = 0.0;
   for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
     const int64_t o = r * BS;
-    T in[BS], pn[BS], xn[BS];
+    T in[BS], in2[BS], in3[BS], pn[BS], xn[BS];
+    // all row loads first (up to 12 x 128-bit loads in flight per thread), then the FMAs
+    if (a.bs1 > 0) load_row<T>(aRb + o, in2);
+    if (a.bs2 > 0) load_row<T>(aPb + o, in3);
+    load_row<T>(Xb + o, in);
 #pragma unroll
     for (int j = 0; j < BS; ++j) pn[j] = (T)0;
-    if (a.bs1 > 0) {
-      load_row<T>(aRb + o, in);
-      row_times_v<T>(in, a.bs1, Vr, pn);
-    }
-    if (a.bs2 > 0) {
-      load_row<T>(aPb + o, in);
-      row_times_v<T>(in, a.bs2, Vp, pn);                                    // + aP Vp  (:652-658)
-    }
-    load_row<T>(Xb + o, in);
+    if (a.bs1 > 0) row_times_v<T>(in2, a.bs1, Vr, pn);
+    if (a.bs2 > 0) row_times_v<T>(in3, a.bs2, Vp, pn);                      // + aP Vp  (:652-658)
 #pragma unroll
     for (int j = 0; j < BS; ++j) xn[j] = (T)0;
     row_times_v<T>(in, a.sizeX, Vx, xn);

@@ -118,6 +118,41 @@ def cg(A, b, **kw):
 
 
 # ------------------------------------------------------------------------------------------------
+# Chebyshev iteration  (reference src/chebyshev.jl:117-160)
+# ------------------------------------------------------------------------------------------------
+def chebyshev_(x, A, b, lmin, lmax, *, abstol=0.0, reltol=None, Pl=None, maxiter=None, log=False, verbose=False,
+               initially_zero=False):
+    """chebyshev!(x, A, b, λmin, λmax; abstol, reltol, Pl, maxiter, log, verbose, initially_zero)."""
+    _check_operator(A)
+    if reltol is None:
+        reltol = math.sqrt(_eps(A.dtype))
+    if maxiter is None:
+        maxiter = A.size(2)
+    opts = _lib.CgOpts(abstol, reltol, int(maxiter), int(bool(initially_zero)), 0, precond_to_c(Pl, A), 0, 0)
+    res = _lib.Result()
+    cap = int(maxiter)                                          # reserve!(history, :resnorm, maxiter)  :144
+    resnorm = np.zeros(max(cap, 1), dtype=np.float64)
+    st = _Staged(A, x, b)
+    check(lib().b200_chebyshev_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), float(lmin),
+                                     float(lmax), C.byref(opts), C.byref(res),
+                                     resnorm.ctypes.data_as(C.c_void_p), cap))
+    st.finish()
+    if verbose:
+        print("=== chebyshev ===\niter\tresnorm")
+        for i, r in enumerate(resnorm[: res.n_resnorm], start=1):
+            print(f"{i:3d}\t{r:1.2e}")
+        print()
+    h = _history(res, resnorm, abstol, reltol, True)            # mvps / setconv are always recorded (:146-155)
+    return (x, h) if log else x
+
+
+def chebyshev(A, b, lmin, lmax, **kw):
+    _check_operator(A)
+    x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
+    return chebyshev_(x, A, b, lmin, lmax, initially_zero=True, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
 # GMRES  (reference src/gmres.jl:143, 184-222)
 # ------------------------------------------------------------------------------------------------
 _ORTH = {"mgs": _lib.ORTH_MGS, "cgs": _lib.ORTH_CGS, "dgks": _lib.ORTH_DGKS,

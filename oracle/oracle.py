@@ -379,6 +379,69 @@ def cg_csc_c(x, A: CSC, b, *, abstol=0.0, reltol=None, maxiter=None, Pl_diag=Non
 
 
 # --------------------------------------------------------------------------------------------
+# Chebyshev iteration (reference src/chebyshev.jl) -- SURVEY.md section 8(f) item 2
+# --------------------------------------------------------------------------------------------
+def chebyshev_(x, A, b, lmin, lmax, *, abstol=0.0, reltol=None, Pl=None, maxiter=None, log=False,
+               initially_zero=False):
+    """chebyshev!(x, A, b, λmin, λmax; ...) -- reference src/chebyshev.jl:131-160, iterate :29-57,
+    chebyshev_iterable! :59-92.  Restated literally, including `iteration == 1` being the SECOND call
+    (start = 0, :26) and `u .= c .+ β .* c` (:45)."""
+    T = x.dtype
+    if reltol is None:
+        reltol = math.sqrt(_eps(_real_dtype(b.dtype)))
+    if maxiter is None:
+        maxiter = opsize(A, 1)
+    Pl = Pl or Identity()
+    l_avg = (lmax + lmin) / 2                                           # :65
+    l_diff = (lmax - lmin) / 2                                          # :66
+    r = b.astype(T, copy=True)                                          # :70
+    u = np.zeros_like(x)
+    if initially_zero:
+        mv_products = 0
+    else:
+        mv_products = 1
+        r -= mul(A, x)                                                  # :80-81
+    resnorm = float(np.linalg.norm(r))                                  # :83
+    tol = max(reltol * resnorm, abstol)                                 # :84
+    alpha = _real_dtype(T).type(0)                                      # :89
+    history = ConvergenceHistory()
+    history["abstol"], history["reltol"] = abstol, reltol
+    history.mvps = mv_products                                          # :148
+    resnorms = []
+    iteration = 0                                                       # start :26
+    RT = _real_dtype(T).type
+    while True:
+        if iteration >= maxiter or resnorm <= tol:                      # :27
+            break
+        c = Pl.ldiv3(np.empty_like(r), r)                               # :37
+        if iteration == 1:                                              # :39
+            alpha = RT(2) / RT(l_avg)
+            u[...] = c
+        else:
+            beta = (RT(l_diff) * alpha / 2) ** 2                        # :43
+            alpha = RT(1) / (RT(l_avg) - beta)                          # :44
+            u[...] = c + T.type(beta) * c                               # :45 (sic)
+        c = mul(A, u)                                                   # :48
+        mv_products += 1
+        x += T.type(alpha) * u                                          # :51
+        r -= T.type(alpha) * c                                          # :52
+        resnorm = float(np.linalg.norm(r))                              # :54
+        iteration += 1
+        history.iters += 1                                              # :150-152
+        history.mvps = mv_products
+        resnorms.append(resnorm)
+    history.isconverged = resnorm <= tol                                # :157
+    history["resnorm"] = np.array(resnorms)
+    history["tol"] = tol
+    return (x, history) if log else x
+
+
+def chebyshev(A, b, lmin, lmax, **kw):
+    x = np.zeros(opsize(A, 1), dtype=b.dtype)
+    return chebyshev_(x, A, b, lmin, lmax, initially_zero=True, **kw)
+
+
+# --------------------------------------------------------------------------------------------
 # Givens (LinearAlgebra.givensAlgorithm, external stdlib) + FastHessenberg ldiv!
 # --------------------------------------------------------------------------------------------
 def givens_algorithm(f, g):

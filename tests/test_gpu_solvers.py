@@ -295,3 +295,60 @@ def test_bicgstabl_jacobi_inplace_and_termination(isb, oracle):
     r0 = np.linalg.norm(T3 @ x - b3)
     x, ch = isb.bicgstabl_(x, A3, b3, 1, abstol=2 * r0, reltol=0.0, log=True)
     assert ch.niters == 0
+
+
+# ------------------------------------------------------------------ full-size properties (configs #3 and MINRES)
+def _true_residual(isb, ctx, A, x, b, n):
+    import ctypes as C
+    L = isb.lib()
+    r = isb.DeviceArray(ctx, n)
+    A.mul_(r, x)
+    assert L.b200_axpby(ctx._h, n, 1.0, b._p, -1.0, r._p, 0) == 0
+    nr = C.c_double()
+    L.b200_nrm2(ctx._h, n, r._p, 0, C.byref(nr))
+    r.free()
+    return nr.value
+
+
+@pytest.mark.parametrize("orth", ["cgs", "dgks"])
+def test_gmres_256cubed_advection_properties(isb, orth):
+    """BASELINE.json configs[2]: gmres!(restart=30) on advection_dominated(N=256) fp64, fixed horizon of two
+    cycles.  Size-independent properties: non-increasing implicit residual (GMRES optimality), the implicit
+    residual at the end of a cycle equals the true residual ||b - A x||, history counts of the reference."""
+    ctx = isb.default_context()
+    N = 256
+    n = N ** 3
+    cp, rv, nz, shape, b = isb.advection_dominated(N, 1000.0, base=1)
+    A = isb.B200CSR.from_csc_arrays(cp, rv, nz, shape, base=1)
+    del cp, rv, nz
+    bd = isb.DeviceArray.from_numpy(ctx, b)
+    xd = isb.DeviceArray.zeros(ctx, n)
+    x, h = isb.gmres_(xd, A, bd, restart=30, maxiter=60, orth_meth=orth, initially_zero=True, log=True, reltol=0.0)
+    assert h.niters == 60 and h.mvps == 60 + 1 + 2 and not h.isconverged      # src/gmres.jl:122,101 quirks
+    res = h["resnorm"]
+    assert np.all(np.diff(res) <= 1e-12 * res[0])
+    assert _true_residual(isb, ctx, A, x, bd, n) == pytest.approx(res[-1], rel=1e-8)
+    assert res[-1] < res[0]
+    for v in (xd, bd):
+        v.free()
+    A.close()
+
+
+def test_minres_256cubed_properties(isb):
+    """minres! on laplace_matrix(Float64, 256, 3): implicit residual == true residual, monotone history."""
+    ctx = isb.default_context()
+    N = 256
+    n = N ** 3
+    A = isb.B200CSR.laplacian(N, 3)
+    rng = np.random.default_rng(SEED)
+    xs = isb.DeviceArray.from_numpy(ctx, rng.standard_normal(n))
+    b = isb.DeviceArray(ctx, n)
+    A.mul_(b, xs)
+    x = isb.DeviceArray.zeros(ctx, n)
+    x, h = isb.minres_(x, A, b, initially_zero=True, log=True, maxiter=300, reltol=1e-6)
+    res = h["resnorm"]
+    assert np.all(np.diff(res) <= 1e-12 * res[0])
+    assert _true_residual(isb, ctx, A, x, b, n) == pytest.approx(res[-1], rel=1e-6)
+    for v in (xs, b, x):
+        v.free()
+    A.close()
