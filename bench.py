@@ -125,6 +125,19 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def ncu_traffic(grid, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE K2 launch, from the committed `ncu --set full` capture
+    (profiles/k2_traffic.json names the .ncu-rep).  Only valid for the workload it was captured on."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k2_traffic.json")) as f:
+            t = json.load(f)
+        if int(t["grid"]) == grid and int(t["n_gpus"]) == world:
+            return int(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------------------------
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm for this path (oracle restatement of
@@ -339,7 +352,7 @@ def main():
             "cg_step_frac_of_peak": cg_bytes / (it_ms / 1e3) / 1e9 / peak,
             "roofline": {"bound": "hbm", "kernel": "k_cg_spmv_dot (c = A*u fused with dot(u,c))",
                          "achieved": spmv_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": (spmv_gbs / peak) if spmv_gbs else None, "traffic": None,
+                         "frac": (spmv_gbs / peak) if spmv_gbs else None, "traffic": ncu_traffic(N, world),
                          "peak_source": peak_src, "avg_launch_ms": k2_ms, "launches": prof[0][1],
                          "algorithmic_bytes_per_launch": spmv_bytes,
                          "other_kernels_ms": {"k3_r_update_nrm2": prof[1][0] / max(prof[1][1], 1),

@@ -226,9 +226,10 @@ struct CgDotEpi {
   T *__restrict__ c;
   const T *__restrict__ u;
   double acc;
-  __device__ __forceinline__ void operator()(int64_t row, T v) {
+  __device__ __forceinline__ T pre(int64_t row) const { return u[row]; }
+  __device__ __forceinline__ void operator()(int64_t row, T v, T ur) {
     c[row] = v;
-    acc += (double)u[row] * (double)v;
+    acc += (double)ur * (double)v;
   }
 };
 template <typename T, int LPR>

@@ -85,7 +85,8 @@ struct b200_ctx {
   int *h_flags = nullptr;        // pinned host flags (16 ints)
   int opt_spmv_kernel = 0;       // b200_ctx_set_option("spmv_kernel"): 0 auto, 1 sub-warp per row, 2 TMA stream
   int opt_comm = 0;              // b200_ctx_set_option("comm"): 0 auto (peer memory if mapped), 1 NCCL, 2 peer memory
-  int opt_snake = 1;             // b200_ctx_set_option("snake"): consecutive hot kernels sweep the rows in alternating directions
+  int opt_lobpcg_mma = 1;        // b200_ctx_set_option("lobpcg_mma"): fp32 LOBPCG blocks on the tensor pipe (3xTF32); 0 = SIMT kernels
+  int opt_snake = 1;            // b200_ctx_set_option("snake"): consecutive hot kernels sweep the rows in alternating directions
   // peer-memory collectives (peer.cuh), multi-GPU contexts only
   bool peer_ok = false;
   void *peer_local = nullptr;                          // this rank's comm buffer

@@ -246,6 +246,10 @@ int b200_ctx_set_option(b200_ctx *c, const char *name, int64_t value) {
     c->opt_snake = value != 0;
     return B200_OK;
   }
+  if (strcmp(name, "lobpcg_mma") == 0) {
+    c->opt_lobpcg_mma = value != 0;
+    return B200_OK;
+  }
   if (strcmp(name, "comm") == 0) {
     B200_REQUIRE(value >= 0 && value <= 2, "comm must be 0 (auto), 1 (NCCL) or 2 (peer memory)");
     B200_REQUIRE(value != 2 || c->peer_ok || c->world == 1, "peer-memory collectives are not available on this context");
@@ -260,6 +264,8 @@ int b200_ctx_get_option(const b200_ctx *c, const char *name, int64_t *value) {
   B200_REQUIRE(c && name && value, "NULL argument");
   if (strcmp(name, "spmv_kernel") == 0) *value = c->opt_spmv_kernel;
   else if (strcmp(name, "comm") == 0) *value = c->opt_comm;
+  else if (strcmp(name, "lobpcg_mma") == 0) *value = c->opt_lobpcg_mma;
+  else if (strcmp(name, "snake") == 0) *value = c->opt_snake;
   else if (strcmp(name, "peer_ok") == 0) *value = c->peer_ok ? 1 : 0;
   else {
     set_error("unknown option `%s`", name);

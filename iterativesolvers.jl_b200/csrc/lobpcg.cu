@@ -297,14 +297,42 @@ __global__ void __launch_bounds__(kThreads, 4) k_rdiv(T *__restrict__ X0, T *__r
   }
 }
 
-// out[j] += sum_i in[i] * V[i][j]
+// ---- quad layout for the dense row-block kernels ---------------------------------------------------------------
+// A warp works on 8 consecutive rows at a time: lanes 4q..4q+3 form the quad of row q and lane c of the quad owns
+// columns 4c..4c+3, so every global load/store instruction of the warp covers 8 x 64 B contiguous bytes (fp32).
+// The first row-per-thread version issued 32 sectors per request and sat at 78 % L1/LSU throughput (ncu,
+// profiles/r1_lobpcg_kernels_v3.ncu-rep); the other three chunks of a row now come from the quad by shuffle.
 template <typename T>
-__device__ __forceinline__ void row_times_v(const T (&in)[BS], int nin, const T (*V)[BS], T (&out)[BS]) {
+__device__ __forceinline__ void st4(T *p, const T (&v)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void quad_gather(const T (&mine)[4], T (&row)[BS]) {
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) row[4 * cc + e] = __shfl_sync(0xffffffffu, mine[e], cc, 4);
+  }
+}
+// o0[e] += sum_i r0[i] * V[i][4c+e], o1 likewise for a second row (the V loads are shared by the two rows)
+template <typename T>
+__device__ __forceinline__ void rows2_times_vchunk(const T (&r0)[BS], const T (&r1)[BS], int nin, const T (*V)[BS],
+                                                   int c, T (&o0)[4], T (&o1)[4]) {
 #pragma unroll
   for (int i = 0; i < BS; ++i) {
     if (i < nin) {
+      T v[4];
+      lds4<T>(&V[i][4 * c], v);
 #pragma unroll
-      for (int j = 0; j < BS; ++j) out[j] += in[i] * V[i][j];
+      for (int e = 0; e < 4; ++e) {
+        o0[e] += r0[i] * v[e];
+        o1[e] += r1[i] * v[e];
+      }
     }
   }
 }
@@ -317,15 +345,16 @@ struct UpdateArgs {
 };
 
 // update_X_P! (:629-690) + residuals! (:533-547).  Vbuf: Vx | Vr | Vp as 16x16 row-major [i][j] (zero padded),
-// lambda: 16.  Two launches so that each keeps two CTAs per SM (the fused single kernel needed 228 registers):
+// lambda: 16.  Two launches (the fused single kernel needed 228 registers):
 //   PHASE 0: P = aR Vr + aP Vp ; X = X Vx + P                                  (reads 3 blocks, writes 2)
 //   PHASE 1: AP = aAR Vr + aAP Vp ; AX = AX Vx + AP ; R = AX - X diag(lambda) ; column norms of R
 //                                                                               (reads 4 blocks, writes 3)
+// Quad layout, two rows (q and q+8 of a 16-row group) per thread.
 template <typename T, int PHASE>
 __global__ void __launch_bounds__(kThreads) k_update(UpdateArgs a, const T *__restrict__ Vbuf,
                                                         const T *__restrict__ lambda, double *partials,
                                                         unsigned int *ticket, double *__restrict__ norms2) {
-  __shared__ T Vx[BS][BS], Vr[BS][BS], Vp[BS][BS];
+  __shared__ __align__(16) T Vx[BS][BS], Vr[BS][BS], Vp[BS][BS];
   __shared__ T lam[BS];
   __shared__ double smem[kThreads / 32][BS];
   __shared__ bool is_last;
@@ -341,47 +370,73 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateArgs a, const T *__re
   const T *Xnew = (const T *)a.X;
   const T *aRb = (const T *)(PHASE == 0 ? a.aR : a.aAR), *aPb = (const T *)(PHASE == 0 ? a.aP : a.aAP);
   const int64_t n = a.n;
-  double nrm[BS];
-#pragma unroll
-  for (int j = 0; j < BS; ++j) nrm[j] = 0.0;
-  for (int64_t r = blockIdx.x * (int64_t)kThreads + threadIdx.x; r < n; r += (int64_t)gridDim.x * kThreads) {
-    const int64_t o = r * BS;
-    T in[BS], in2[BS], in3[BS], pn[BS], xn[BS];
-    // all row loads first (up to 12 x 128-bit loads in flight per thread), then the FMAs
-    if (a.bs1 > 0) load_row<T>(aRb + o, in2);
-    if (a.bs2 > 0) load_row<T>(aPb + o, in3);
-    load_row<T>(Xb + o, in);
-#pragma unroll
-    for (int j = 0; j < BS; ++j) pn[j] = (T)0;
-    if (a.bs1 > 0) row_times_v<T>(in2, a.bs1, Vr, pn);
-    if (a.bs2 > 0) row_times_v<T>(in3, a.bs2, Vp, pn);                      // + aP Vp  (:652-658)
-#pragma unroll
-    for (int j = 0; j < BS; ++j) xn[j] = (T)0;
-    row_times_v<T>(in, a.sizeX, Vx, xn);
-    if (a.bs1 > 0) {
-#pragma unroll
-      for (int j = 0; j < BS; ++j) xn[j] = xn[j] + pn[j];                   // tempX .+ P  (:675)
-      store_row<T>(Pb + o, pn);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = lane & 3, q = lane >> 2;
+  const bool has1 = a.bs1 > 0, has2 = a.bs2 > 0;
+  double nrm[4] = {0.0, 0.0, 0.0, 0.0};
+  const int64_t warps_total = (int64_t)gridDim.x * (kThreads / 32);
+  for (int64_t base = ((int64_t)blockIdx.x * (kThreads / 32) + warp) * 16; base < n; base += warps_total * 16) {
+    const int64_t r0 = base + q, r1 = base + 8 + q;
+    const bool ok0 = r0 < n, ok1 = r1 < n;
+    const int64_t o0 = (ok0 ? r0 : 0) * BS + 4 * c, o1 = (ok1 ? r1 : 0) * BS + 4 * c;   // clamped: shuffles need all lanes
+    T x0[4], x1[4], p0[4], p1[4], q0[4], q1[4];
+    // all chunk loads first (up to 6 x 128-bit loads in flight per thread), then the shuffles and FMAs
+    if (has1) { lds4<T>(aRb + o0, p0); lds4<T>(aRb + o1, p1); }
+    if (has2) { lds4<T>(aPb + o0, q0); lds4<T>(aPb + o1, q1); }
+    lds4<T>(Xb + o0, x0);
+    lds4<T>(Xb + o1, x1);
+    T pn0[4] = {(T)0, (T)0, (T)0, (T)0}, pn1[4] = {(T)0, (T)0, (T)0, (T)0};
+    T xn0[4] = {(T)0, (T)0, (T)0, (T)0}, xn1[4] = {(T)0, (T)0, (T)0, (T)0};
+    T w0[BS], w1[BS];
+    if (has1) {
+      quad_gather<T>(p0, w0);
+      quad_gather<T>(p1, w1);
+      rows2_times_vchunk<T>(w0, w1, a.bs1, Vr, c, pn0, pn1);
     }
-    store_row<T>(Xb + o, xn);
+    if (has2) {                                                             // + aP Vp  (:652-658)
+      quad_gather<T>(q0, w0);
+      quad_gather<T>(q1, w1);
+      rows2_times_vchunk<T>(w0, w1, a.bs2, Vp, c, pn0, pn1);
+    }
+    quad_gather<T>(x0, w0);
+    quad_gather<T>(x1, w1);
+    rows2_times_vchunk<T>(w0, w1, a.sizeX, Vx, c, xn0, xn1);
+    if (has1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {                                         // tempX .+ P  (:675)
+        xn0[e] = xn0[e] + pn0[e];
+        xn1[e] = xn1[e] + pn1[e];
+      }
+      if (ok0) st4<T>(Pb + o0, pn0);
+      if (ok1) st4<T>(Pb + o1, pn1);
+    }
+    if (ok0) st4<T>(Xb + o0, xn0);
+    if (ok1) st4<T>(Xb + o1, xn1);
     if constexpr (PHASE == 1) {
       // residuals!: R = AX - X * Diagonal(lambda)  (:535-536) and column norms (:538-545); X is already updated
-      load_row<T>(Xnew + o, in);
+      lds4<T>(Xnew + o0, x0);
+      lds4<T>(Xnew + o1, x1);
 #pragma unroll
-      for (int j = 0; j < BS; ++j) {
-        const T res = j < a.sizeX ? xn[j] - in[j] * lam[j] : (T)0;
-        pn[j] = res;
-        nrm[j] += (double)res * (double)res;
+      for (int e = 0; e < 4; ++e) {
+        const int j = 4 * c + e;
+        const T res0 = (j < a.sizeX && ok0) ? xn0[e] - x0[e] * lam[j] : (T)0;
+        const T res1 = (j < a.sizeX && ok1) ? xn1[e] - x1[e] * lam[j] : (T)0;
+        pn0[e] = res0;
+        pn1[e] = res1;
+        nrm[e] += (double)res0 * (double)res0 + (double)res1 * (double)res1;
       }
-      store_row<T>(R + o, pn);
+      if (ok0) st4<T>(R + o0, pn0);
+      if (ok1) st4<T>(R + o1, pn1);
     }
   }
   if constexpr (PHASE == 0) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < BS; ++j) {
-    const double v = warp_sum(nrm[j]);
-    if (lane == 0) smem[warp][j] = v;
+  for (int e = 0; e < 4; ++e) {
+    double v = nrm[e];
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (lane < 4) smem[warp][4 * lane + e] = v;
   }
   __syncthreads();
   if (threadIdx.x < BS) {
@@ -403,6 +458,383 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateArgs a, const T *__re
     norms2[threadIdx.x] = s;
   }
   if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fp32 blocks on the tensor pipe ("3xTF32": a = a_hi + a_lo in TF32, a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi,
+// fp32 accumulate; products are exact, the dropped a_lo*b_lo term is 2^-22 relative).  The SIMT versions of the
+// update and of the Rayleigh-Ritz Gram products are bound by shared-memory operand traffic / FMA issue, not by
+// HBM (ncu: 78 % LSU, 27 % issue); as m16n8k8 MMAs the same arithmetic is ~6 % of the tensor pipe and the kernels
+// become bandwidth-bound.  These are tall-skinny products (K or N = 16): one warp-level mma.sync per 16 rows is
+// the natural tile, a 128-row tcgen05 tile with TMEM round trips would not move fewer bytes.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_3xtf32(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                           uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1) {
+  mma_tf32(d, al, bh0, bh1);   // small terms first
+  mma_tf32(d, ah, bl0, bl1);
+  mma_tf32(d, ah, bh0, bh1);
+}
+
+// B operand (16x16 coefficient matrix V, shared memory) as loop-invariant register fragments.  With lane = 4g + t
+// the two k8 halves p of a 16-wide K use the column permutation  logical k = t (t+4)  <->  physical 4t+2p (+1),
+// so that the A fragment is exactly the lane's own 16-byte chunk of the row (quad layout, coalesced).
+struct BFrag {
+  uint32_t h[2][2][2], l[2][2][2];   // [p][n-tile][b0/b1]
+};
+__device__ __forceinline__ void load_bfrag(const float (*V)[BS], int g, int t, BFrag &f) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) split_tf32(V[4 * t + 2 * p + h][8 * nt + g], f.h[p][nt][h], f.l[p][nt][h]);
+}
+// acc[nt] += [x0 ; x1] * V   (x0: row g, x1: row g+8, both the lane's columns 4t..4t+3; columns >= nin are skipped)
+// acc[nt] = {(g, 8nt+2t), (g, 8nt+2t+1), (g+8, 8nt+2t), (g+8, 8nt+2t+1)}
+__device__ __forceinline__ void chunk_mma(const float (&x0)[4], const float (&x1)[4], int nin, int t, const BFrag &f,
+                                          float (&acc)[2][4]) {
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const bool on0 = 4 * t + 2 * p < nin, on1 = 4 * t + 2 * p + 1 < nin;
+    uint32_t ah[4], al[4];
+    split_tf32(on0 ? x0[2 * p] : 0.f, ah[0], al[0]);
+    split_tf32(on0 ? x1[2 * p] : 0.f, ah[1], al[1]);
+    split_tf32(on1 ? x0[2 * p + 1] : 0.f, ah[2], al[2]);
+    split_tf32(on1 ? x1[2 * p + 1] : 0.f, ah[3], al[3]);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+      mma_3xtf32(acc[nt], ah, al, f.h[p][nt][0], f.h[p][nt][1], f.l[p][nt][0], f.l[p][nt][1]);
+  }
+}
+
+// k_update for fp32 blocks on the tensor pipe; same phases, same memory behaviour as k_update<float, PHASE>.
+template <int PHASE>
+__global__ void __launch_bounds__(kThreads, 2) k_update_tc(UpdateArgs a, const float *__restrict__ Vbuf,
+                                                            const float *__restrict__ lambda, double *partials,
+                                                            unsigned int *ticket, double *__restrict__ norms2) {
+  __shared__ float V3[3][BS][BS];
+  __shared__ float lam[BS];
+  __shared__ double smem[kThreads / 32][BS];
+  __shared__ bool is_last;
+  for (int q = threadIdx.x; q < 3 * BS * BS; q += kThreads) (&V3[0][0][0])[q] = Vbuf[q];
+  if (threadIdx.x < BS) lam[threadIdx.x] = threadIdx.x < a.sizeX ? lambda[threadIdx.x] : 0.f;
+  __syncthreads();
+  float *Xb = (float *)(PHASE == 0 ? a.X : a.AX), *Pb = (float *)(PHASE == 0 ? a.P : a.AP), *R = (float *)a.R;
+  const float *Xnew = (const float *)a.X;
+  const float *aRb = (const float *)(PHASE == 0 ? a.aR : a.aAR), *aPb = (const float *)(PHASE == 0 ? a.aP : a.aAP);
+  const int64_t n = a.n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int t = lane & 3, g = lane >> 2;
+  const bool has1 = a.bs1 > 0, has2 = a.bs2 > 0;
+  BFrag fx, fr, fp;
+  load_bfrag(V3[0], g, t, fx);
+  if (has1) load_bfrag(V3[1], g, t, fr);
+  if (has2) load_bfrag(V3[2], g, t, fp);
+  double nrm[4] = {0.0, 0.0, 0.0, 0.0};   // columns 2t, 2t+1, 8+2t, 8+2t+1
+  const int64_t warps_total = (int64_t)gridDim.x * (kThreads / 32);
+  for (int64_t base = ((int64_t)blockIdx.x * (kThreads / 32) + warp) * 16; base < n; base += warps_total * 16) {
+    const int64_t r0 = base + g, r1 = base + 8 + g;
+    const bool ok0 = r0 < n, ok1 = r1 < n;
+    const int64_t b0 = (ok0 ? r0 : 0) * BS, b1 = (ok1 ? r1 : 0) * BS;   // clamped: the MMAs need all lanes
+    float x0[4], x1[4], p0[4], p1[4], q0[4], q1[4];
+    if (has1) { lds4<float>(aRb + b0 + 4 * t, p0); lds4<float>(aRb + b1 + 4 * t, p1); }
+    if (has2) { lds4<float>(aPb + b0 + 4 * t, q0); lds4<float>(aPb + b1 + 4 * t, q1); }
+    lds4<float>(Xb + b0 + 4 * t, x0);
+    lds4<float>(Xb + b1 + 4 * t, x1);
+    float2 xw[2][2];
+    if constexpr (PHASE == 1) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        xw[nt][0] = *reinterpret_cast<const float2 *>(Xnew + b0 + 8 * nt + 2 * t);
+        xw[nt][1] = *reinterpret_cast<const float2 *>(Xnew + b1 + 8 * nt + 2 * t);
+      }
+    }
+    float pn[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, xn[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    if (has1) chunk_mma(p0, p1, a.bs1, t, fr, pn);
+    if (has2) chunk_mma(q0, q1, a.bs2, t, fp, pn);                          // + aP Vp  (:652-658)
+    chunk_mma(x0, x1, a.sizeX, t, fx, xn);
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const int col = 8 * nt + 2 * t;
+      if (has1) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) xn[nt][e] = xn[nt][e] + pn[nt][e];      // tempX .+ P  (:675)
+        if (ok0) *reinterpret_cast<float2 *>(Pb + b0 + col) = make_float2(pn[nt][0], pn[nt][1]);
+        if (ok1) *reinterpret_cast<float2 *>(Pb + b1 + col) = make_float2(pn[nt][2], pn[nt][3]);
+      }
+      if (ok0) *reinterpret_cast<float2 *>(Xb + b0 + col) = make_float2(xn[nt][0], xn[nt][1]);
+      if (ok1) *reinterpret_cast<float2 *>(Xb + b1 + col) = make_float2(xn[nt][2], xn[nt][3]);
+      if constexpr (PHASE == 1) {
+        // residuals!: R = AX - X * Diagonal(lambda)  (:535-536) and column norms (:538-545); X is already updated
+        const bool c0 = col < a.sizeX, c1 = col + 1 < a.sizeX;
+        const float l0 = lam[col], l1 = lam[col + 1];
+        const float ra = (c0 && ok0) ? xn[nt][0] - xw[nt][0].x * l0 : 0.f;
+        const float rb = (c1 && ok0) ? xn[nt][1] - xw[nt][0].y * l1 : 0.f;
+        const float rc = (c0 && ok1) ? xn[nt][2] - xw[nt][1].x * l0 : 0.f;
+        const float rd = (c1 && ok1) ? xn[nt][3] - xw[nt][1].y * l1 : 0.f;
+        nrm[2 * nt] += (double)ra * (double)ra + (double)rc * (double)rc;
+        nrm[2 * nt + 1] += (double)rb * (double)rb + (double)rd * (double)rd;
+        if (ok0) *reinterpret_cast<float2 *>(R + b0 + col) = make_float2(ra, rb);
+        if (ok1) *reinterpret_cast<float2 *>(R + b1 + col) = make_float2(rc, rd);
+      }
+    }
+  }
+  if constexpr (PHASE == 0) return;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    double v = nrm[e];
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    if (lane < 4) smem[warp][8 * (e >> 1) + 2 * lane + (e & 1)] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < BS) {
+    double s = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) s += smem[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * kMaxReduceWidth + threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < BS) {
+    double s = 0.0;
+    for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * kMaxReduceWidth + threadIdx.x]);
+    norms2[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+}
+
+// All Gram blocks of one Rayleigh-Ritz step in ONE pass over the blocks (reference src/lobpcg.jl:262-271 computes
+// them as eight separate mul! calls; the SIMT path above needs five launches that stream 13 blocks):
+//   MODE 1: blocks X, R, AR        -> X'AR, X'R, R'AR                                (3 products, no P yet)
+//   MODE 2: blocks X, R, AR, P, AP -> X'AR, X'R, R'AR, X'AP, X'P, R'P, AR'P, P'AP    (8 products)
+//   MODE 0: one block B -> B'B  (the CholQR Gram matrix, :378)
+// out[p*256 + i*16 + j] = G_p[i][j].  TMA ring as k_gram; each consumer warp turns 8 staged rows into one k8 step:
+// the lane's two 64-bit shared loads (rows k0+t, k0+t+4, columns 2g, 2g+1) are at once the A fragment of the block
+// as a left factor (m = g <-> column 2g, m = g+8 <-> column 2g+1) and its B fragments as a right factor
+// (n-tile nt, n = g <-> column 2g+nt) -- conflict-free, no transposition.
+constexpr int kRrRows = 128;
+constexpr int rr_blocks(int mode) { return mode == 2 ? 5 : (mode == 1 ? 3 : 1); }
+constexpr int rr_stages(int mode) { return mode == 2 ? 3 : (mode == 1 ? 4 : 8); }   // 120 / 96 / 64 KB in flight
+constexpr int kRrConsumerWarps = 16;
+constexpr int kRrThreads = kRrConsumerWarps * 32 + 32;
+template <int MODE>
+struct RrSmem {
+  alignas(128) float buf[rr_stages(MODE)][rr_blocks(MODE)][kRrRows * BS];
+  alignas(8) unsigned long long full[rr_stages(MODE)];
+  alignas(8) unsigned long long empty[rr_stages(MODE)];
+};
+struct RrArgs {
+  const float *blk[5];   // X, R, AR, P, AP
+  int64_t n;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kRrThreads, 1) k_gram_rr_tc(RrArgs a, double *partials, unsigned int *ticket,
+                                                              double *__restrict__ out) {
+  constexpr bool WITH_P = MODE == 2;
+  constexpr int NB = rr_blocks(MODE);
+  constexpr int NP = MODE == 2 ? 8 : (MODE == 1 ? 3 : 1);
+  constexpr int kRrStages = rr_stages(MODE);
+  // (left, right) block of each product; block order X=0, R=1, AR=2, P=3, AP=4
+  constexpr int kL[8] = {0, 0, 1, 0, 0, 1, 2, 3};
+  constexpr int kR[8] = {MODE == 0 ? 0 : 2, 1, 2, 4, 3, 3, 3, 4};
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  RrSmem<MODE> *sm = reinterpret_cast<RrSmem<MODE> *>(smem_raw);
+  __shared__ bool is_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t = lane & 3, g = lane >> 2;
+  const int64_t n = a.n;
+  const int64_t nchunks = (n + kRrRows - 1) / kRrRows;
+  if (tid == 0) {
+    for (int s = 0; s < kRrStages; ++s) {
+      mbar_init(&sm->full[s], 1);
+      mbar_init(&sm->empty[s], kRrConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // WITH_P: warps 0-7 own products 0-3, warps 8-15 products 4-7 (32 accumulator registers per lane instead of 64),
+  // each over 16 of the chunk's 128 rows; without P all 16 warps own the three products over 8 rows each.
+  constexpr int NPW = WITH_P ? 4 : NP;
+  constexpr int kSteps = WITH_P ? 2 : 1;
+  const int half = WITH_P ? (warp >> 3) & 1 : 0;
+  const int wrow = (WITH_P ? (warp & 7) : warp) * 8 * kSteps;
+  float acc[NPW][2][4];
+#pragma unroll
+  for (int p = 0; p < NPW; ++p)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[p][nt][e] = 0.f;
+  float acc_small[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // MODE 0: the three small product terms
+
+  if (warp == kRrConsumerWarps) {
+    if (lane == 0) {                                   // producer
+      const uint64_t pol = policy_evict_first();
+      int it = 0;
+      for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+        const int s = it % kRrStages;
+        const uint32_t ph = (uint32_t)((it / kRrStages) & 1);
+        mbar_wait(&sm->empty[s], ph ^ 1u);
+        const int64_t r0 = c * kRrRows;
+        const int rows = (int)((n - r0 < kRrRows) ? (n - r0) : kRrRows);
+        const uint32_t bytes = (uint32_t)rows * BS * (uint32_t)sizeof(float);
+        mbar_expect_tx(&sm->full[s], bytes * NB);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) bulk_g2s(sm->buf[s][b], a.blk[b] + r0 * BS, bytes, &sm->full[s], pol);
+      }
+    }
+  } else {
+    int it = 0;
+    for (int64_t c = blockIdx.x; c < nchunks; c += gridDim.x, ++it) {
+      const int s = it % kRrStages;
+      const uint32_t ph = (uint32_t)((it / kRrStages) & 1);
+      const int64_t r0 = c * kRrRows;
+      const int rows = (int)((n - r0 < kRrRows) ? (n - r0) : kRrRows);
+      mbar_wait(&sm->full[s], ph);
+#pragma unroll
+      for (int step = 0; step < kSteps; ++step) {
+        const int k0 = wrow + 8 * step;
+        const bool v0 = k0 + t < rows, v1 = k0 + t + 4 < rows;
+        uint32_t fh[NB][4], fl[NB][4];                  // {row k0+t: col 2g, 2g+1 ; row k0+t+4: col 2g, 2g+1}
+        float raw0[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+          const float2 u = *reinterpret_cast<const float2 *>(&sm->buf[s][b][(k0 + t) * BS + 2 * g]);
+          const float2 w = *reinterpret_cast<const float2 *>(&sm->buf[s][b][(k0 + t + 4) * BS + 2 * g]);
+          if (MODE == 0 && b == 0) { raw0[0] = u.x; raw0[1] = u.y; raw0[2] = w.x; raw0[3] = w.y; }
+          split_tf32(v0 ? u.x : 0.f, fh[b][0], fl[b][0]);
+          split_tf32(v0 ? u.y : 0.f, fh[b][1], fl[b][1]);
+          split_tf32(v1 ? w.x : 0.f, fh[b][2], fl[b][2]);
+          split_tf32(v1 ? w.y : 0.f, fh[b][3], fl[b][3]);
+        }
+        if (step == kSteps - 1) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm->empty[s]);    // operands are in registers: release the stage early
+        }
+        if constexpr (MODE == 0) {
+          // CholQR squares the condition number of the block, so B'B gets fp32-exact products: a third TF32 term
+          // (11 + 11 + 2 mantissa bits represent an fp32 value exactly) and the six products above 2^-33.
+          uint32_t fm[4], fs[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x = (e < 2 ? v0 : v1) ? raw0[e] : 0.f;
+            const float r1 = x - __uint_as_float(fh[0][e]);
+            fm[e] = to_tf32(r1);                                   // == fl[0][e]
+            fs[e] = to_tf32(r1 - __uint_as_float(fm[e]));
+          }
+          // two independent accumulator chains per n-tile (small terms / leading terms), interleaved over nt
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) mma_tf32(acc_small[nt], fs, fh[0][nt], fh[0][2 + nt]);
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[0][nt], fm, fh[0][nt], fh[0][2 + nt]);
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) mma_tf32(acc_small[nt], fh[0], fs[nt], fs[2 + nt]);
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[0][nt], fh[0], fm[nt], fm[2 + nt]);
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) mma_tf32(acc_small[nt], fm, fm[nt], fm[2 + nt]);
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) mma_tf32(acc[0][nt], fh[0], fh[0][nt], fh[0][2 + nt]);
+        } else if (half == 0) {
+          // term by term over all (product, n-tile) accumulators: consecutive MMAs are independent
+#pragma unroll
+          for (int term = 0; term < 3; ++term)
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) {
+              const int lb = kL[q], rb = kR[q];
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                if (term == 0) mma_tf32(acc[q][nt], fl[lb], fh[rb][nt], fh[rb][2 + nt]);       // small terms first
+                else if (term == 1) mma_tf32(acc[q][nt], fh[lb], fl[rb][nt], fl[rb][2 + nt]);
+                else mma_tf32(acc[q][nt], fh[lb], fh[rb][nt], fh[rb][2 + nt]);
+              }
+            }
+        } else if constexpr (WITH_P) {
+#pragma unroll
+          for (int term = 0; term < 3; ++term)
+#pragma unroll
+            for (int q = 0; q < NPW; ++q) {
+              const int lb = kL[4 + q], rb = kR[4 + q];
+#pragma unroll
+              for (int nt = 0; nt < 2; ++nt) {
+                if (term == 0) mma_tf32(acc[q][nt], fl[lb], fh[rb][nt], fh[rb][2 + nt]);
+                else if (term == 1) mma_tf32(acc[q][nt], fh[lb], fl[rb][nt], fl[rb][2 + nt]);
+                else mma_tf32(acc[q][nt], fh[lb], fh[rb][nt], fh[rb][2 + nt]);
+              }
+            }
+        }
+      }
+    }
+  }
+  if constexpr (MODE == 0) {
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[0][nt][e] += acc_small[nt][e];
+  }
+  __syncthreads();   // all TMA data consumed: the ring memory is reused for the cross-warp reduction
+  double(*red)[256] = reinterpret_cast<double(*)[256]>(smem_raw);
+  static_assert(sizeof(RrSmem<MODE>) >= sizeof(double) * kRrConsumerWarps * 256, "reduction scratch does not fit");
+  constexpr int kOwners = WITH_P ? 8 : kRrConsumerWarps;   // warps that hold a partial of a given product
+  for (int q = 0; q < NPW; ++q) {
+    // round q publishes product q (warps of half 0) and, with P, product 4+q (half 1) side by side
+    if (warp < kRrConsumerWarps) {
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 2 * g + (e >> 1);               // m = g (+8)  <-> column 2g (+1) of the left block
+          const int j = 2 * (2 * t + (e & 1)) + nt;     // n = 2t (+1) <-> column 2n + nt of the right block
+          red[warp][i * 16 + j] = (double)acc[q][nt][e];
+        }
+    }
+    __syncthreads();
+    if (tid < 256 * (WITH_P ? 2 : 1)) {
+      const int h = tid >> 8, el = tid & 255;
+      double s = 0.0;
+      for (int w = 0; w < kOwners; ++w) s += red[h * 8 + w][el];
+      partials[((size_t)blockIdx.x * NP + 4 * h + q) * 256 + el] = s;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    __threadfence();
+    is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid < 256) {
+    for (int p = 0; p < NP; ++p) {
+      double s = 0.0;
+      for (unsigned int blk = 0; blk < gridDim.x; ++blk) s += __ldcg(&partials[((size_t)blk * NP + p) * 256 + tid]);
+      out[p * 256 + tid] = s;
+    }
+  }
+  if (tid == 0) *ticket = 0u;
 }
 
 // dst[:, k] = src[:, idx[k]] for k < bs, zero beyond  (update_active! :557-562)
@@ -479,11 +911,79 @@ struct Lobpcg {
     return B200_OK;
   }
 
+  // fp32 blocks go through the tensor-pipe kernels unless the option "lobpcg_mma" is 0
+  bool use_tc() const { return sizeof(T) == 4 && ctx->opt_lobpcg_mma != 0; }
+
+  int gram_rr(bool with_p, const T *X_, const T *R_, const T *AR_, const T *P_, const T *AP_, double *host_out) {
+    if constexpr (sizeof(T) == 4) {
+      RrArgs ra;
+      ra.blk[0] = X_; ra.blk[1] = R_; ra.blk[2] = AR_;
+      ra.blk[3] = with_p ? P_ : X_; ra.blk[4] = with_p ? AP_ : X_;
+      ra.n = n;
+      static bool attr_set = false;
+      if (!attr_set) {
+        B200_CUDA(cudaFuncSetAttribute(k_gram_rr_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(RrSmem<2>)));
+        B200_CUDA(cudaFuncSetAttribute(k_gram_rr_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(RrSmem<1>)));
+        attr_set = true;
+      }
+      {
+        ProfScope prof(ctx, 1);
+        if (with_p)
+          k_gram_rr_tc<2><<<grid_gram, kRrThreads, sizeof(RrSmem<2>), ctx->stream>>>(ra, gram_partials,
+                                                                                     ctx->red.ticket, d_gram);
+        else
+          k_gram_rr_tc<1><<<grid_gram, kRrThreads, sizeof(RrSmem<1>), ctx->stream>>>(ra, gram_partials,
+                                                                                     ctx->red.ticket, d_gram);
+      }
+      B200_LAUNCH_CHECK(ctx);
+      B200_CUDA(cudaMemcpyAsync(host_out, d_gram, sizeof(double) * 256 * (with_p ? 8 : 3), cudaMemcpyDeviceToHost,
+                                ctx->stream));
+      B200_CUDA(cudaStreamSynchronize(ctx->stream));
+      return B200_OK;
+    } else {
+      (void)with_p; (void)X_; (void)R_; (void)AR_; (void)P_; (void)AP_; (void)host_out;
+      B200_REQUIRE(false, "gram_rr: fp32 only");
+    }
+  }
+
+  // G = B' B on the tensor pipe (fp32 blocks)
+  int gram_self(const T *B_, double *host_out) {
+    if constexpr (sizeof(T) == 4) {
+      RrArgs ra;
+      for (int b = 0; b < 5; ++b) ra.blk[b] = B_;
+      ra.n = n;
+      static bool attr_set = false;
+      if (!attr_set) {
+        B200_CUDA(cudaFuncSetAttribute(k_gram_rr_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)sizeof(RrSmem<0>)));
+        attr_set = true;
+      }
+      {
+        ProfScope prof(ctx, 1);
+        k_gram_rr_tc<0><<<grid_gram, kRrThreads, sizeof(RrSmem<0>), ctx->stream>>>(ra, gram_partials, ctx->red.ticket,
+                                                                                   d_gram);
+      }
+      B200_LAUNCH_CHECK(ctx);
+      B200_CUDA(cudaMemcpyAsync(host_out, d_gram, sizeof(double) * 256, cudaMemcpyDeviceToHost, ctx->stream));
+      B200_CUDA(cudaStreamSynchronize(ctx->stream));
+      return B200_OK;
+    } else {
+      (void)B_; (void)host_out;
+      B200_REQUIRE(false, "gram_self: fp32 only");
+    }
+  }
+
   // CholQR (:365-393): blk is orthonormalised, ablk (its A-block) follows if given
   int cholqr(T *blk, T *ablk, int bs) {
     double G[256];
-    const T *rb[1] = {blk};
-    B200_TRY(gram(blk, rb, 1, G));
+    if (use_tc()) {
+      B200_TRY(gram_self(blk, G));
+    } else {
+      const T *rb[1] = {blk};
+      B200_TRY(gram(blk, rb, 1, G));
+    }
     std::vector<double> U((size_t)bs * bs);
     for (int i = 0; i < bs; ++i)
       for (int j = 0; j < bs; ++j) U[i + (size_t)j * bs] = i <= j ? G[i * 16 + j] : G[j * 16 + i];  // Hermitian(gram): upper
@@ -538,7 +1038,7 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
   L.grid_spmm = stream_grid(ctx, n, kThreads / 4, 8);
   const size_t blk_bytes = align_up(sizeof(T) * (size_t)n * BS, 256);
   const size_t small_bytes = align_up(sizeof(T) * (3 * 256 + 16 + 256), 256);
-  const size_t gram_bytes = sizeof(double) * ((size_t)L.grid_gram * 4 * 256 + 4 * 256 + 64);
+  const size_t gram_bytes = sizeof(double) * ((size_t)L.grid_gram * 8 * 256 + 8 * 256 + 64);
   void *ws = nullptr;
   B200_TRY(ws_get(ctx, 6 * blk_bytes + small_bytes + gram_bytes + 1024, &ws));
   char *p = (char *)ws;
@@ -549,8 +1049,8 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
   L.P = (T *)p; p += blk_bytes;
   L.AP = (T *)p; p += blk_bytes;
   L.d_small = (T *)p; p += small_bytes;
-  L.gram_partials = (double *)p; p += sizeof(double) * (size_t)L.grid_gram * 4 * 256;
-  L.d_gram = (double *)p; p += sizeof(double) * 4 * 256;
+  L.gram_partials = (double *)p; p += sizeof(double) * (size_t)L.grid_gram * 8 * 256;
+  L.d_gram = (double *)p; p += sizeof(double) * 8 * 256;
   double *d_norms = (double *)p; p += sizeof(double) * 64;
   L.d_idx = (int *)p;
   L.gR = L.gP = L.gAP = nullptr;
@@ -581,9 +1081,20 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
     ua.sizeX = sizeX; ua.bs1 = bs1; ua.bs2 = bs2; ua.n = n;
     {
       ProfScope prof(ctx, 3);
-      k_update<T, 0><<<L.grid_vec, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, nullptr, nullptr, nullptr);
-      k_update<T, 1><<<L.grid_vec, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, ctx->red.partials, ctx->red.ticket, d_norms);
-      ctx->launches++;
+      if constexpr (sizeof(T) == 4) {
+        if (L.use_tc()) {
+          const int gtc = stream_grid(ctx, n, kThreads / 2, 2);
+          k_update_tc<0><<<gtc, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, nullptr, nullptr, nullptr);
+          k_update_tc<1><<<gtc, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, ctx->red.partials, ctx->red.ticket, d_norms);
+        } else {
+          k_update<T, 0><<<L.grid_vec, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, nullptr, nullptr, nullptr);
+          k_update<T, 1><<<L.grid_vec, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, ctx->red.partials, ctx->red.ticket, d_norms);
+        }
+      } else {
+        k_update<T, 0><<<L.grid_vec, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, nullptr, nullptr, nullptr);
+        k_update<T, 1><<<L.grid_vec, kThreads, 0, st>>>(ua, L.d_small, L.d_small + 768, ctx->red.partials, ctx->red.ticket, d_norms);
+      }
+      ctx->launches++;   // two launches: the second is counted by B200_LAUNCH_CHECK below
     }
     B200_LAUNCH_CHECK(ctx);
     double nn[BS];
@@ -655,13 +1166,32 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
       auto setB = [&](int i, int j, double v) { gB[i + (size_t)j * sub] = v; gB[j + (size_t)i * sub] = v; };
       for (int i = 0; i < n1; ++i) setA(i, i, ritz[i]);                                             // Diagonal(lambda) :289
       for (int i = 0; i < sub; ++i) setB(i, i, 1.0);                                                // I! :315,322,331
-      double G[4 * 256];
-      {               // X' [AR, R]  (and X' [AP, P]): two right blocks per launch keeps the 4x4 tiles in registers
-        const T *rb[2] = {L.AR, aR};
-        B200_TRY(L.gram(L.X, rb, 2, G));
-        if (with_p) {
-          const T *rb2[2] = {aAP, aP};
-          B200_TRY(L.gram(L.X, rb2, 2, G + 512));
+      // Gram blocks, slot p at G + 256 p:  0 X'AR  1 X'R  2 R'AR  3 X'AP  4 X'P  5 R'P  6 AR'P  7 P'AP
+      double G[8 * 256];
+      if (L.use_tc()) {
+        B200_TRY(L.gram_rr(with_p, L.X, aR, L.AR, aP, aAP, G));                                     // one pass
+      } else {
+        {             // X' [AR, R]  (and X' [AP, P]): two right blocks per launch keeps the 4x4 tiles in registers
+          const T *rb[2] = {L.AR, aR};
+          B200_TRY(L.gram(L.X, rb, 2, G));
+          if (with_p) {
+            const T *rb2[2] = {aAP, aP};
+            B200_TRY(L.gram(L.X, rb2, 2, G + 3 * 256));
+          }
+        }
+        double G2[2 * 256];
+        if (with_p) {   // R' [AR, P]
+          const T *rb[2] = {L.AR, aP};
+          B200_TRY(L.gram(aR, rb, 2, G2));
+          memcpy(G + 2 * 256, G2, sizeof(double) * 256);
+          memcpy(G + 5 * 256, G2 + 256, sizeof(double) * 256);
+          const T *rb1[1] = {aP};
+          B200_TRY(L.gram(L.AR, rb1, 1, G + 6 * 256));                                              // AR' P
+          const T *rb2[1] = {aAP};
+          B200_TRY(L.gram(aP, rb2, 1, G + 7 * 256));                                                // P' AP
+        } else {
+          const T *rb[1] = {L.AR};
+          B200_TRY(L.gram(aR, rb, 1, G + 2 * 256));
         }
       }
       for (int i = 0; i < n1; ++i)
@@ -669,30 +1199,20 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
           setA(i, n1 + j, G[i * 16 + j]);                                                           // XAR :265
           setB(i, n1 + j, G[256 + i * 16 + j]);                                                     // XBR :270
           if (with_p) {
-            setA(i, n1 + n2 + j, G[512 + i * 16 + j]);                                              // XAP :264
-            setB(i, n1 + n2 + j, G[768 + i * 16 + j]);                                              // XBP :269
+            setA(i, n1 + n2 + j, G[3 * 256 + i * 16 + j]);                                          // XAP :264
+            setB(i, n1 + n2 + j, G[4 * 256 + i * 16 + j]);                                          // XBP :269
           }
         }
-      if (with_p) {   // R' [AR, P]
-        const T *rb[2] = {L.AR, aP};
-        B200_TRY(L.gram(aR, rb, 2, G));
-        for (int i = 0; i < n2; ++i)
-          for (int j = 0; j < n3; ++j) setB(n1 + i, n1 + n2 + j, G[256 + i * 16 + j]);              // RBP :271
-      } else {
-        const T *rb[1] = {L.AR};
-        B200_TRY(L.gram(aR, rb, 1, G));
-      }
       for (int i = 0; i < n2; ++i)
-        for (int j = i; j < n2; ++j) setA(n1 + i, n1 + j, G[i * 16 + j]);                           // RAR :266 (upper triangle)
+        for (int j = i; j < n2; ++j) setA(n1 + i, n1 + j, G[2 * 256 + i * 16 + j]);                 // RAR :266 (upper triangle)
       if (with_p) {
-        const T *rb1[1] = {aP};
-        B200_TRY(L.gram(L.AR, rb1, 1, G));                                                          // RAP = AR' P :267
         for (int i = 0; i < n2; ++i)
-          for (int j = 0; j < n3; ++j) setA(n1 + i, n1 + n2 + j, G[i * 16 + j]);
-        const T *rb2[1] = {aAP};
-        B200_TRY(L.gram(aP, rb2, 1, G));                                                            // PAP :268
+          for (int j = 0; j < n3; ++j) {
+            setB(n1 + i, n1 + n2 + j, G[5 * 256 + i * 16 + j]);                                     // RBP :271
+            setA(n1 + i, n1 + n2 + j, G[6 * 256 + i * 16 + j]);                                     // RAP :267
+          }
         for (int i = 0; i < n3; ++i)
-          for (int j = i; j < n3; ++j) setA(n1 + n2 + i, n1 + n2 + j, G[i * 16 + j]);
+          for (int j = i; j < n3; ++j) setA(n1 + n2 + i, n1 + n2 + j, G[7 * 256 + i * 16 + j]);     // PAP :268
       }
       std::vector<double> w, Z;
       const int info = dense::sym_eig_generalized(gA, gB, sub, w, Z);                               // :622

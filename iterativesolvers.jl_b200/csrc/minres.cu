@@ -173,8 +173,9 @@ struct MrEpi {
   T h2;
   bool use_prev;
   double acc;
-  __device__ __forceinline__ void operator()(int64_t row, T t) {
-    if (use_prev) t = t - h2 * v_prev[row];
+  __device__ __forceinline__ T pre(int64_t row) const { return use_prev ? v_prev[row] : (T)0; }
+  __device__ __forceinline__ void operator()(int64_t row, T t, T vp) {
+    if (use_prev) t = t - h2 * vp;
     v_next[row] = t;
     acc += (double)v_curr[row] * (double)t;
   }

@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(kThreads) k_spmm(const int *__restrict__ rowpt
 template <typename T>
 struct StoreEpi {
   T *__restrict__ y;
-  __device__ __forceinline__ void operator()(int64_t row, T v) { y[row] = v; }
+  __device__ __forceinline__ T pre(int64_t) const { return (T)0; }
+  __device__ __forceinline__ void operator()(int64_t row, T v, T) { y[row] = v; }
 };
 template <typename T, int LPR>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)

@@ -172,6 +172,13 @@ __device__ __forceinline__ void spmv_stream_tiles(const int *__restrict__ rowptr
         e[q] = valid[q] ? st->rp[rib + 1] - k0a : 0;
       }
       T acc[2] = {(T)0, (T)0};
+      // the epilogue's own per-row operand (e.g. MINRES' v_prev[row]) is requested BEFORE the gathers so that its
+      // DRAM latency overlaps theirs; loaded after them it doubled the time a tile occupies its stage
+      T pre[2] = {(T)0, (T)0};
+      if (sub == 0) {
+        if (valid[0]) pre[0] = epi.pre(r0 + slot);
+        if (valid[1]) pre[1] = epi.pre(r0 + slot + SLOTS);
+      }
       if constexpr (LPR == 1) {
         // 2 rows x up to 8 gathers in flight; left-to-right, unfused multiply-add (see header comment)
         int kk0 = b[0], kk1 = b[1];
@@ -228,8 +235,8 @@ __device__ __forceinline__ void spmv_stream_tiles(const int *__restrict__ rowptr
         }
       }
       if (sub == 0) {
-        if (valid[0]) epi(r0 + slot, acc[0]);
-        if (valid[1]) epi(r0 + slot + SLOTS, acc[1]);
+        if (valid[0]) epi(r0 + slot, acc[0], pre[0]);
+        if (valid[1]) epi(r0 + slot + SLOTS, acc[1], pre[1]);
       }
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&sm->empty[s]);

@@ -119,6 +119,34 @@ def test_lobpcg_fp32_config5_shape(isb, oracle):
     np.testing.assert_allclose(rn.lam, ex, rtol=2e-3)
 
 
+@pytest.mark.parametrize("bs", [16, 5])
+def test_lobpcg_fp32_tensor_pipe_vs_simt(isb, oracle, bs):
+    """fp32 blocks run the update and the Rayleigh-Ritz Gram products as 3xTF32 MMAs by default; option
+    lobpcg_mma = 0 selects the SIMT kernels.  Both must agree with each other and with the oracle to fp32
+    accuracy.  n = 24^3 is a multiple of the 128-row chunk and of the 16-row MMA tile, n = 23^3 is neither."""
+    import ctypes as C
+    L = isb.lib()
+    ctx = isb.default_context()
+    rng = np.random.default_rng(SEED + bs)
+    for N in (24, 23):
+        O = oracle.laplace_matrix(np.float32, N, 3)
+        A = _op(isb, O)
+        X0 = rng.random((O.n, bs)).astype(np.float32)
+        ro = oracle.lobpcg(O, False, X0, maxiter=6, fixed_iterations=True)
+        out = {}
+        try:
+            for mode in (1, 0):
+                assert L.b200_ctx_set_option(ctx._h, b"lobpcg_mma", mode) == 0
+                out[mode] = isb.lobpcg(A, False, X0, maxiter=6, _fixed_iterations=True)
+        finally:
+            L.b200_ctx_set_option(ctx._h, b"lobpcg_mma", 1)
+        for mode in (1, 0):
+            np.testing.assert_allclose(out[mode].lam, ro.lam, rtol=1e-4)
+            np.testing.assert_allclose(out[mode].residual_norms, ro.residual_norms, rtol=5e-3)
+        np.testing.assert_allclose(out[1].lam, out[0].lam, rtol=2e-5)
+        np.testing.assert_allclose(out[1].X.T @ out[1].X, np.eye(bs), atol=2e-5)
+
+
 def test_lobpcg_256cubed_fp32_properties(isb):
     """configs[4] full size: lobpcg block=16 on laplace_matrix(Float32, 256, 3), 4 steps: Ritz values
     decrease monotonically (Rayleigh-Ritz optimality), stay above the analytic lambda_min, X'X = I."""
