@@ -236,6 +236,21 @@ B200_API int b200_cg_solve_host(b200_ctx *ctx, const b200_csr *A, void *x_host, 
                                 const b200_cg_opts *opts, b200_result *res, double *resnorm_host,
                                 int64_t resnorm_cap);
 
+/* cg_iterator!(x, A, b; abstol, reltol, maxiter, statevars, Pl, initially_zero)  reference src/cg.jl:120-155:
+ * the resumable form of the same engine.  u_dev, r_dev, c_dev are the caller-owned CGStateVariables
+ * (src/cg.jl:114-118) or NULL (owned by the iterator).  Creation forms r = b - A x, u = 0, the residual and tol.
+ * b200_cg_iter_next performs up to k calls of iterate(it) (src/cg.jl:43-66 / :72-100), stopping at done()
+ * (src/cg.jl:36); on return x is complete, res->iters / mvps / residual / tol / isconverged describe the iterator,
+ * res->status is 1 once done() holds, and resnorm_host (may be NULL; at most 4096 entries per call) receives the
+ * residual after each iteration performed by this call. */
+typedef struct b200_cg_iter b200_cg_iter;
+B200_API int b200_cg_iter_create(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
+                                 const b200_cg_opts *opts, void *u_dev, void *r_dev, void *c_dev,
+                                 b200_cg_iter **out);
+B200_API int b200_cg_iter_next(b200_cg_iter *it, int64_t k, b200_result *res, double *resnorm_host,
+                               int64_t resnorm_cap);
+B200_API int b200_cg_iter_destroy(b200_cg_iter *it);
+
 /* chebyshev!(x, A, b, lmin, lmax; abstol, reltol, Pl, maxiter, initially_zero)  reference src/chebyshev.jl:131-160
  * (SURVEY.md section 8f item 2).  Uses the cg option block (abstol, reltol, maxiter, initially_zero, Pl). */
 B200_API int b200_chebyshev_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,

@@ -128,6 +128,9 @@ SIGNATURES = {
     "b200_hessenberg_ldiv": (_INT, [_P, _P, _INT, _INT, _P]),
     "b200_cg_solve": (_INT, [_P, _P, _P, _P, C.POINTER(CgOpts), C.POINTER(Result), _P, _I64]),
     "b200_cg_solve_host": (_INT, [_P, _P, _P, _P, C.POINTER(CgOpts), C.POINTER(Result), _P, _I64]),
+    "b200_cg_iter_create": (_INT, [_P, _P, _P, _P, C.POINTER(CgOpts), _P, _P, _P, C.POINTER(_P)]),
+    "b200_cg_iter_next": (_INT, [_P, _I64, C.POINTER(Result), _P, _I64]),
+    "b200_cg_iter_destroy": (_INT, [_P]),
     "b200_chebyshev_solve": (_INT, [_P, _P, _P, _P, _DBL, _DBL, C.POINTER(CgOpts), C.POINTER(Result), _P, _I64]),
     "b200_gmres_solve": (_INT, [_P, _P, _P, _P, C.POINTER(GmresOpts), C.POINTER(Result), _P, _I64]),
     "b200_minres_solve": (_INT, [_P, _P, _P, _P, C.POINTER(MinresOpts), C.POINTER(Result), _P, _I64]),

@@ -142,6 +142,14 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(const T *__restrict__ b, c
     cg_finish(FIN_INIT, s, total, nullptr, cm);
 }
 
+// every CTA makes sure the neighbours' halo values of this iteration have landed (peer path)
+__device__ __forceinline__ void wait_halo(const Comm &cm) {
+  if (cm.mode == COMM_PEER && cm.halo_mask) {
+    if (threadIdx.x == 0) peer_wait_halo(cm.pv, cm.halo_mask, cm.halo_seq);
+    __syncthreads();
+  }
+}
+
 // K1: x += alpha_prev*u (the x update of the PREVIOUS iteration, src/cg.jl:58) ; u = r + beta*u (src/cg.jl:51)
 //     (CG: beta = residual^2/prev_residual^2 ; PCG: u = c + (rho/rho_prev)*u)
 // The x update is deferred by one kernel so that u is streamed once for both updates (10 instead of 11
@@ -150,7 +158,9 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(const T *__restrict__ b, c
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_update_u(const T *__restrict__ r, T *__restrict__ u,
                                                           T *__restrict__ x, int64_t n,
-                                                          const CgScal *__restrict__ s, int pcg, int rev) {
+                                                          const CgScal *__restrict__ s, int pcg, int rev,
+                                                          const T *r_halo, T *__restrict__ u_halo, int n_halo,
+                                                          Comm cm) {
   if (s->done) return;
   const double beta_d = pcg ? s->rho / s->rho_prev
                             : (s->residual * s->residual) / (s->prev_residual * s->prev_residual);
@@ -169,6 +179,18 @@ __global__ void __launch_bounds__(kThreads) k_cg_update_u(const T *__restrict__ 
       u[i] = __fadd_rn(r[i], __fmul_rn(beta, ui));
     }
   }
+  // Peer-memory path (CG, Identity): the neighbours pushed the boundary values of r right after their K3 -- one
+  // kernel earlier than u exists -- and every GPU forms the halo part of u itself from the same operands
+  // (r_halo, beta, previous u_halo): bit-identical to the owner's values, and the NVLink latency of the push is
+  // hidden behind this kernel instead of stalling the first gathers of K2.
+  if (r_halo && (int64_t)blockIdx.x * kThreads < n_halo) {
+    wait_halo(cm);
+    for (int64_t h = blockIdx.x * (int64_t)kThreads + threadIdx.x; h < n_halo; h += (int64_t)gridDim.x * kThreads) {
+      const T rh = __ldcg(r_halo + h);
+      if constexpr (sizeof(T) == 8) u_halo[h] = __dadd_rn(rh, __dmul_rn(beta, u_halo[h]));
+      else u_halo[h] = __fadd_rn(rh, __fmul_rn(beta, u_halo[h]));
+    }
+  }
 }
 
 // the deferred x update of the last completed iteration
@@ -183,13 +205,6 @@ __global__ void __launch_bounds__(kThreads) k_cg_flush_x(const T *__restrict__ u
   }
 }
 
-// every CTA makes sure the neighbours' halo values of this iteration have landed (peer path)
-__device__ __forceinline__ void wait_halo(const Comm &cm) {
-  if (cm.mode == COMM_PEER && cm.halo_mask) {
-    if (threadIdx.x == 0) peer_wait_halo(cm.pv, cm.halo_mask, cm.halo_seq);
-    __syncthreads();
-  }
-}
 
 // K2 (sub-warp-per-row fallback): c = A*u ; sum u.*c
 template <typename T, int LPR>
@@ -305,6 +320,7 @@ struct CgEngine {
   int mode;      // COMM_*
   int lpr, grid_vec, grid_spmv;
   int sweep = 0;   // direction of the next hot kernel (toggled per launch when ctx->opt_snake)
+  bool fold_halo = false;   // peer path, Identity: r's boundary is pushed after K3 and K1 forms u's halo locally
 
   int next_sweep() {
     const int d = ctx->opt_snake ? sweep : 0;
@@ -341,14 +357,16 @@ struct CgEngine {
 
   int spmv_dot() {
     const bool peer = mode == COMM_PEER;
-    if (peer) {
+    if (fold_halo) {
+      // u's halo was formed by K1 in A->halo: nothing to exchange, nothing to wait for
+    } else if (peer) {
       ctx->halo_seq += 1;
       B200_TRY(halo_push(ctx, A, u, ctx->halo_seq, &s->done));
     } else {
       B200_TRY(halo_exchange(ctx, A, u));
     }
-    XView<T> xv = make_xview<T>(A, u, peer);
-    const Comm cm = comm(true, next_sweep());
+    XView<T> xv = make_xview<T>(A, u, peer && !fold_halo);
+    const Comm cm = comm(!fold_halo, next_sweep());
     if (use_stream(ctx, A)) {
       const int grid = stream_grid_size(ctx, A);
       const size_t smem = sizeof(StreamSmem<T>);
@@ -401,7 +419,17 @@ struct CgEngine {
     }
     {
       ProfScope prof(ctx, 2);
-      k_cg_update_u<T><<<grid_vec, kThreads, 0, st>>>(pcg ? c : r, u, x, n, s, pcg, next_sweep());
+      Comm hc;
+      hc.mode = mode;
+      hc.seq = 0;
+      hc.halo_seq = ctx->halo_seq;
+      hc.halo_mask = fold_halo ? A->recv_mask : 0;
+      hc.rev = 0;
+      if (mode == COMM_PEER) hc.pv = ctx->peer_view;
+      k_cg_update_u<T><<<grid_vec, kThreads, 0, st>>>(pcg ? c : r, u, x, n, s, pcg, next_sweep(),
+                                                      fold_halo ? (const T *)A->halo_peer : nullptr,
+                                                      fold_halo ? (T *)A->halo : nullptr, fold_halo ? (int)A->n_halo : 0,
+                                                      hc);
     }
     B200_LAUNCH_CHECK(ctx);
     B200_TRY(spmv_dot());
@@ -411,17 +439,75 @@ struct CgEngine {
                                                       comm(false, next_sweep()));
     }
     B200_LAUNCH_CHECK(ctx);
-    return after_reduce(pcg ? FIN_NORM_PCG : FIN_NORM);
+    B200_TRY(after_reduce(pcg ? FIN_NORM_PCG : FIN_NORM));
+    return push_r_halo();
+  }
+
+  // boundary values of the new r go to the neighbours now; they are consumed by the next K1
+  int push_r_halo() {
+    if (!fold_halo) return B200_OK;
+    ctx->halo_seq += 1;
+    return halo_push(ctx, A, r, ctx->halo_seq, &s->done);
   }
 };
+
+// cg_iterator! (src/cg.jl:120-155): fills the engine, uploads the scalars, forms r = b - A x (unless
+// initially_zero), u = 0, ||r||, tol.  u/r/c/scal/hist are provided by the caller (solve: context arena;
+// iterator: its own buffers or the user's CGStateVariables).
+template <typename T>
+int cg_setup(CgEngine<T> &e, b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200_cg_opts *o, T *u, T *r,
+             T *c, CgScal *scal, double *hist, int64_t hist_cap, int64_t *mv_products) {
+  cudaStream_t st = ctx->stream;
+  const int64_t n = A->m_local;
+  const double eps = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
+  const double reltol = o->reltol < 0 ? sqrt(eps) : o->reltol;
+  const int64_t maxiter = o->maxiter < 0 ? A->n_global : o->maxiter;
+  e.ctx = ctx;
+  e.A = A;
+  e.n = n;
+  e.x = x;
+  e.b = b;
+  e.u = u;
+  e.r = r;
+  e.c = c;
+  e.s = scal;
+  static_assert(sizeof(CgScal) <= 256, "CgScal too large");
+  e.hist = hist_cap ? hist : nullptr;
+  e.jac = o->Pl.kind == B200_PREC_JACOBI ? (const T *)o->Pl.diag : nullptr;
+  e.mode = ctx->world == 1 ? COMM_SINGLE : (use_peer(ctx, A) ? COMM_PEER : COMM_NCCL);
+  e.lpr = pick_lpr(A->avg_row_nnz);
+  e.grid_vec = stream_grid(ctx, n, kThreads * 2, 8);
+  e.grid_spmv = stream_grid(ctx, n, kThreads / e.lpr, 8);
+  e.fold_halo = e.mode == COMM_PEER && !e.jac && A->halo && A->halo_peer && A->n_halo > 0;
+  if (e.fold_halo) B200_CUDA(cudaMemsetAsync(A->halo, 0, sizeof(T) * (size_t)A->n_halo, st));   // u_0 = 0
+
+  CgScal h;
+  memset(&h, 0, sizeof(h));
+  h.abstol = o->abstol;
+  h.reltol = reltol;
+  h.maxiter = maxiter;
+  h.hist_cap = hist_cap;
+  h.fixed = o->fixed_iterations;
+  h.pcg = e.jac != nullptr;
+  B200_CUDA(cudaMemcpyAsync(e.s, &h, sizeof(h), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+
+  *mv_products = 0;
+  if (!o->initially_zero) {
+    *mv_products = 1;
+    B200_TRY(spmv(ctx, A, x, e.c));
+  }
+  k_cg_init<T><<<e.grid_vec, kThreads, 0, st>>>(b, e.c, o->initially_zero ? 0 : 1, e.r, e.u, n, e.s, ctx->red.partials,
+                                                 ctx->red.ticket, e.comm());
+  B200_LAUNCH_CHECK(ctx);
+  B200_TRY(e.after_reduce(FIN_INIT));
+  return e.push_r_halo();
+}
 
 template <typename T>
 int cg_solve_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200_cg_opts *o, b200_result *res,
                   double *resnorm_host, int64_t resnorm_cap) {
   cudaStream_t st = ctx->stream;
   const int64_t n = A->m_local;
-  const double eps = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
-  const double reltol = o->reltol < 0 ? sqrt(eps) : o->reltol;
   const int64_t maxiter = o->maxiter < 0 ? A->n_global : o->maxiter;
   const int check_every = o->check_every > 0 ? o->check_every : 32;
   const int64_t hist_cap = resnorm_host ? std::min<int64_t>(resnorm_cap, maxiter) : 0;
@@ -433,43 +519,9 @@ int cg_solve_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200
   B200_TRY(ws_get(ctx, 3 * vec_bytes + 256 + hist_bytes, &ws));
   char *p = (char *)ws;
   CgEngine<T> e;
-  e.ctx = ctx;
-  e.A = A;
-  e.n = n;
-  e.x = x;
-  e.b = b;
-  e.u = (T *)p; p += vec_bytes;
-  e.r = (T *)p; p += vec_bytes;
-  e.c = (T *)p; p += vec_bytes;
-  e.s = (CgScal *)p; p += 256;
-  static_assert(sizeof(CgScal) <= 256, "CgScal too large");
-  e.hist = hist_cap ? (double *)p : nullptr;
-  e.jac = o->Pl.kind == B200_PREC_JACOBI ? (const T *)o->Pl.diag : nullptr;
-  e.mode = ctx->world == 1 ? COMM_SINGLE : (use_peer(ctx, A) ? COMM_PEER : COMM_NCCL);
-  e.lpr = pick_lpr(A->avg_row_nnz);
-  e.grid_vec = stream_grid(ctx, n, kThreads * 2, 8);
-  e.grid_spmv = stream_grid(ctx, n, kThreads / e.lpr, 8);
-
-  CgScal h;
-  memset(&h, 0, sizeof(h));
-  h.abstol = o->abstol;
-  h.reltol = reltol;
-  h.maxiter = maxiter;
-  h.hist_cap = hist_cap;
-  h.fixed = o->fixed_iterations;
-  h.pcg = e.jac != nullptr;
-  B200_CUDA(cudaMemcpyAsync(e.s, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-
-  // cg_iterator! (src/cg.jl:120-155)
   int64_t mv_products = 0;
-  if (!o->initially_zero) {
-    mv_products = 1;
-    B200_TRY(spmv(ctx, A, x, e.c));
-  }
-  k_cg_init<T><<<e.grid_vec, kThreads, 0, st>>>(b, e.c, o->initially_zero ? 0 : 1, e.r, e.u, n, e.s, ctx->red.partials,
-                                                 ctx->red.ticket, e.comm());
-  B200_LAUNCH_CHECK(ctx);
-  B200_TRY(e.after_reduce(FIN_INIT));
+  B200_TRY(cg_setup<T>(e, ctx, A, x, b, o, (T *)p, (T *)(p + vec_bytes), (T *)(p + 2 * vec_bytes),
+                       (CgScal *)(p + 3 * vec_bytes), (double *)(p + 3 * vec_bytes + 256), hist_cap, &mv_products));
 
   // the hot loop (src/cg.jl:229): enqueue check_every iterations, poll the device flag
   int64_t enqueued = 0;
@@ -484,6 +536,7 @@ int cg_solve_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200
   }
   k_cg_flush_x<T><<<e.grid_vec, kThreads, 0, st>>>(e.u, x, n, e.s);   // x += alpha*u of the last iteration
   B200_LAUNCH_CHECK(ctx);
+  CgScal h;
   B200_CUDA(cudaMemcpyAsync(&h, e.s, sizeof(h), cudaMemcpyDeviceToHost, st));
   B200_CUDA(cudaStreamSynchronize(st));
   if (h.comm_error) {
@@ -501,6 +554,84 @@ int cg_solve_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200
   }
   if (hist_cap && h.iter > 0) {
     B200_CUDA(cudaMemcpyAsync(resnorm_host, e.hist, sizeof(double) * std::min<int64_t>(h.iter, hist_cap),
+                              cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+  }
+  return B200_OK;
+}
+
+// per-call control of an iterator: history window for the coming batch; alpha = 0 after x was completed, so that
+// the deferred `x += alpha*u` of the next K1 adds exactly nothing
+__global__ void k_cg_iter_ctl(CgScal *s, long long hist_cap, int zero_alpha) {
+  if (hist_cap >= 0) s->hist_cap = hist_cap;
+  if (zero_alpha) s->alpha = 0.0;
+}
+
+constexpr int64_t kIterHistWindow = 4096;   // residuals recorded per b200_cg_iter_next call
+
+template <typename T>
+struct CgIterState {
+  CgEngine<T> e;
+  DevBuf own_vec[3], scal, hist;
+  int64_t mv_products = 0, maxiter = 0;
+};
+
+template <typename T>
+int cg_iter_create_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200_cg_opts *o, T *u, T *r, T *c,
+                        CgIterState<T> *it) {
+  const size_t vec_bytes = sizeof(T) * (size_t)std::max<int64_t>(A->m_local, 1);
+  T *v[3] = {u, r, c};
+  for (int k = 0; k < 3; ++k)
+    if (!v[k]) {
+      B200_TRY(it->own_vec[k].alloc(vec_bytes));
+      v[k] = (T *)it->own_vec[k].p;
+    }
+  B200_TRY(it->scal.alloc(256));
+  B200_TRY(it->hist.alloc(sizeof(double) * kIterHistWindow));
+  it->maxiter = o->maxiter < 0 ? A->n_global : o->maxiter;
+  return cg_setup<T>(it->e, ctx, A, x, b, o, v[0], v[1], v[2], (CgScal *)it->scal.p, (double *)it->hist.p, 0,
+                     &it->mv_products);
+}
+
+template <typename T>
+int cg_iter_next_impl(CgIterState<T> *it, int64_t k, b200_result *res, double *resnorm_host, int64_t cap) {
+  CgEngine<T> &e = it->e;
+  b200_ctx *ctx = e.ctx;
+  cudaStream_t st = ctx->stream;
+  CgScal h;
+  B200_CUDA(cudaMemcpyAsync(&h, e.s, sizeof(h), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  const int64_t start = h.iter;
+  k = std::max<int64_t>(0, std::min<int64_t>(k, it->maxiter - start));
+  const int64_t window = resnorm_host ? std::min<int64_t>(std::min<int64_t>(cap, k), kIterHistWindow) : 0;
+  // history slots of this batch: hist[iter] lands in the window for iter in [start, start + window)
+  e.hist = window ? (double *)it->hist.p - start : nullptr;
+  k_cg_iter_ctl<<<1, 1, 0, st>>>(e.s, start + window, 0);
+  B200_LAUNCH_CHECK(ctx);
+  if (!h.done)
+    for (int64_t i = 0; i < k; ++i) B200_TRY(e.iterate());          // iterate(it) x k  (src/cg.jl:43-66 / :72-100)
+  k_cg_flush_x<T><<<e.grid_vec, kThreads, 0, st>>>(e.u, e.x, e.n, e.s);
+  B200_LAUNCH_CHECK(ctx);
+  k_cg_iter_ctl<<<1, 1, 0, st>>>(e.s, -1, 1);
+  B200_LAUNCH_CHECK(ctx);
+  B200_CUDA(cudaMemcpyAsync(&h, e.s, sizeof(h), cudaMemcpyDeviceToHost, st));
+  B200_CUDA(cudaStreamSynchronize(st));
+  if (h.comm_error) {
+    set_error("peer-memory collective timed out (a rank did not reach the same point of the CG loop)");
+    return B200_ERR_NCCL;
+  }
+  const int64_t performed = h.iter - start;
+  if (res) {
+    res->iters = h.iter;
+    res->mvps = it->mv_products + h.iter;
+    res->isconverged = h.residual <= h.tol;
+    res->status = h.breakdown ? B200_ERR_BREAKDOWN : (h.done ? 1 : 0);   // 1: done() is true (src/cg.jl:36)
+    res->tol = h.tol;
+    res->residual = h.residual;
+    res->n_resnorm = std::min<int64_t>(performed, window);
+  }
+  if (window && performed > 0) {
+    B200_CUDA(cudaMemcpyAsync(resnorm_host, it->hist.p, sizeof(double) * std::min<int64_t>(performed, window),
                               cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
   }
@@ -542,6 +673,48 @@ int b200_cg_solve_host(b200_ctx *ctx, const b200_csr *A, void *x_host, const voi
   if (s != B200_OK) return s;
   B200_CUDA(cudaMemcpyAsync(x_host, dx.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
+}
+
+struct b200_cg_iter {
+  int dtype;
+  CgIterState<double> d;
+  CgIterState<float> f;
+};
+
+int b200_cg_iter_create(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev, const b200_cg_opts *opts,
+                        void *u_dev, void *r_dev, void *c_dev, b200_cg_iter **out) {
+  B200_TRY(check_cg_args(ctx, A, x_dev, b_dev, opts));
+  B200_REQUIRE(out, "NULL argument");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  b200_cg_iter *it = new b200_cg_iter();
+  it->dtype = A->dtype;
+  const int st = A->dtype == B200_F64
+                     ? cg_iter_create_impl<double>(ctx, A, (double *)x_dev, (const double *)b_dev, opts, (double *)u_dev,
+                                                   (double *)r_dev, (double *)c_dev, &it->d)
+                     : cg_iter_create_impl<float>(ctx, A, (float *)x_dev, (const float *)b_dev, opts, (float *)u_dev,
+                                                  (float *)r_dev, (float *)c_dev, &it->f);
+  if (st != B200_OK) {
+    delete it;
+    return st;
+  }
+  *out = it;
+  return B200_OK;
+}
+
+int b200_cg_iter_next(b200_cg_iter *it, int64_t k, b200_result *res, double *resnorm_host, int64_t resnorm_cap) {
+  B200_REQUIRE(it, "NULL argument");
+  b200_ctx *ctx = it->dtype == B200_F64 ? it->d.e.ctx : it->f.e.ctx;
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return it->dtype == B200_F64 ? cg_iter_next_impl<double>(&it->d, k, res, resnorm_host, resnorm_cap)
+                               : cg_iter_next_impl<float>(&it->f, k, res, resnorm_host, resnorm_cap);
+}
+
+int b200_cg_iter_destroy(b200_cg_iter *it) {
+  if (!it) return B200_OK;
+  b200_ctx *ctx = it->dtype == B200_F64 ? it->d.e.ctx : it->f.e.ctx;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  delete it;
   return B200_OK;
 }
 

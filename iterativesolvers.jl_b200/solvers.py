@@ -76,12 +76,30 @@ def _history(res: _lib.Result, resnorm, abstol, reltol, log, restart=None):
 def cg_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, log=False, verbose=False, Pl=None,
         initially_zero=False, statevars=None, check_every=0, _fixed_iterations=False):
     """cg!(x, A, b; abstol, reltol, maxiter, log, statevars, verbose, Pl, initially_zero).
-    `statevars` is accepted for signature parity; the engine owns its work vectors."""
+    With `statevars` (CGStateVariables of three device vectors) the solve runs through the iterator form of the
+    engine on the caller's u, r, c -- exactly `cg_iterator!(...; statevars)` driven to done() (src/cg.jl:224-236)."""
     _check_operator(A)
     if reltol is None:
         reltol = math.sqrt(_eps(A.dtype))                     # src/cg.jl:211
     if maxiter is None:
         maxiter = A.size(2)                                   # src/cg.jl:212
+    if statevars is not None:
+        it = cg_iterator_(x, A, b, abstol=abstol, reltol=reltol, maxiter=maxiter, statevars=statevars, Pl=Pl,
+                          initially_zero=initially_zero)
+        resnorm = []
+        while not it.done:
+            resnorm.extend(it.step(4096))
+        res = it.result
+        it.close()
+        cg_.last_result = res
+        h = ConvergenceHistory()
+        h["abstol"], h["reltol"] = abstol, reltol
+        h.isconverged = bool(res.isconverged)
+        if log:
+            h.mvps, h.iters = int(res.mvps), int(res.iters)
+            h["resnorm"] = np.array(resnorm, dtype=np.float64)
+            h["tol"] = res.tol
+        return (x, h) if log else x
     opts = _lib.CgOpts(abstol, reltol, int(maxiter), int(bool(initially_zero)), int(check_every),
                        precond_to_c(Pl, A), int(bool(_fixed_iterations)), 0)
     res = _lib.Result()
@@ -105,6 +123,116 @@ def cg_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, log=False, verbose=Fa
         print()
     cg_.last_result = res
     return (x, _history(res, resnorm, abstol, reltol, log)) if log else x
+
+
+class CGStateVariables:
+    """CGStateVariables(u, r, c) -- reference src/cg.jl:114-118: three vectors similar to x that hold the
+    intermediate results of the iteration; here three DeviceArrays of the operator's eltype and local length."""
+
+    def __init__(self, u, r, c):
+        for v in (u, r, c):
+            if not is_device(v):
+                raise TypeError("CGStateVariables holds device vectors (DeviceArray)")
+        self.u, self.r, self.c = u, r, c
+
+
+class CGIterable:
+    """The object `cg_iterator!` returns (CGIterable / PCGIterable, reference src/cg.jl:5-30): iterating it yields
+    the residual norm after each step (src/cg.jl:65, :99) and leaves x updated in place; `step(k)` performs up to k
+    steps in one call (one launch batch, one host synchronisation)."""
+
+    def __init__(self, x, A, b, opts, statevars):
+        self._A, self._x = A, x
+        self._st = _Staged(A, x, b)
+        self._sv = statevars                                   # keep the state vectors alive
+        sv = statevars
+        self._h = C.c_void_p()
+        check(lib().b200_cg_iter_create(A.ctx._h, A._h, as_device_ptr(self._st.xd), as_device_ptr(self._st.bd),
+                                        C.byref(opts), as_device_ptr(sv.u) if sv else None,
+                                        as_device_ptr(sv.r) if sv else None, as_device_ptr(sv.c) if sv else None,
+                                        C.byref(self._h)))
+        self.result = _lib.Result()
+        self._buf = np.zeros(4096, dtype=np.float64)
+        self.step(0)                                           # residual / tol of the initial state
+
+    # -- reference field names -------------------------------------------------------------------
+    @property
+    def residual(self):
+        return float(self.result.residual)
+
+    @property
+    def tol(self):
+        return float(self.result.tol)
+
+    @property
+    def iteration(self):
+        return int(self.result.iters)
+
+    @property
+    def mv_products(self):
+        return int(self.result.mvps)
+
+    @property
+    def converged(self):                                       # converged(it)  src/cg.jl:32-34
+        return bool(self.result.isconverged)
+
+    @property
+    def done(self):                                            # done(it, iteration)  src/cg.jl:36
+        return self.result.status == 1
+
+    @property
+    def x(self):
+        return self._x
+
+    def step(self, k=1):
+        """up to k calls of iterate(it); returns the residual norms of the steps performed."""
+        if self._h is None:
+            raise RuntimeError("iterator is closed")
+        k = int(k)
+        out = []
+        while True:
+            kk = min(k, 4096)
+            check(lib().b200_cg_iter_next(self._h, kk, C.byref(self.result), self._buf.ctypes.data_as(C.c_void_p), 4096))
+            out.extend(self._buf[: self.result.n_resnorm].tolist())
+            k -= kk
+            if k <= 0 or self.done:
+                break
+        self._st.finish()                                      # host x: copy the completed iterate back
+        return out
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.done:
+            raise StopIteration
+        r = self.step(1)
+        if not r:
+            raise StopIteration
+        return r[0]
+
+    def close(self):
+        if self._h is not None:
+            lib().b200_cg_iter_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def cg_iterator_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, statevars=None, Pl=None, initially_zero=False):
+    """cg_iterator!(x, A, b, Pl = Identity(); abstol, reltol, maxiter, statevars, initially_zero)
+    -- reference src/cg.jl:120-155."""
+    _check_operator(A)
+    if reltol is None:
+        reltol = math.sqrt(_eps(A.dtype))
+    if maxiter is None:
+        maxiter = A.size(2)
+    opts = _lib.CgOpts(abstol, reltol, int(maxiter), int(bool(initially_zero)), 0, precond_to_c(Pl, A), 0, 0)
+    return CGIterable(x, A, b, opts, statevars)
 
 
 def cg(A, b, **kw):

@@ -67,12 +67,12 @@ def main():
     # the other solvers on the same row partition (halo exchange + NCCL allreduce of their reductions)
     b_loc = b_global[lo:lo + m].copy()
     xm, hm = isb.minres_(np.zeros(m), A1, b_loc, initially_zero=True, log=True, reltol=1e-9)
-    xg, hg = isb.gmres_(np.zeros(m), A1, b_loc, initially_zero=True, log=True, restart=20, maxiter=60, orth_meth="dgks")
+    xgm, hg = isb.gmres_(np.zeros(m), A1, b_loc, initially_zero=True, log=True, restart=20, maxiter=60, orth_meth="dgks")
     rsh = np.random.default_rng(7).random(n)
     xb, hb = isb.bicgstabl_(np.zeros(m), A1, b_loc, 2, initial_zero=True, log=True, max_mv_products=120,
                             r_shadow=rsh[lo:lo + m].copy(), reltol=1e-9)
     others = [None] * world
-    dist.all_gather_object(others, (xm, xg, xb))
+    dist.all_gather_object(others, (xm, xgm, xb))
 
     gathered = [None] * world
     dist.all_gather_object(gathered, (y_loc, results["slab"][0], results["generated"][0],

@@ -289,3 +289,65 @@ def test_cg_256cubed_properties(isb):
     x2 = isb.DeviceArray.zeros(ctx, n)
     x2, h2 = isb.cg_(x2, A, b, initially_zero=True, log=True, reltol=1e-8)
     assert np.array_equal(h["resnorm"], h2["resnorm"])
+
+
+# ------------------------------------------------------------------ iterator form (cg_iterator!, src/cg.jl:120-155)
+@pytest.mark.parametrize("jacobi", [False, True])
+def test_cg_iterator_steps_match_oracle(isb, oracle, jacobi):
+    rng = np.random.default_rng(SEED)
+    O = oracle.laplace_matrix(np.float64, 12, 3, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    b = rng.standard_normal(O.n)
+    x0 = rng.standard_normal(O.n)
+    kw_o = {"Pl": oracle.JacobiPrec(O.diagonal())} if jacobi else {}
+    kw_d = {"Pl": isb.JacobiPrec(A.diag())} if jacobi else {}
+    xo, ho = oracle.cg_(x0.copy(), O, b, log=True, **kw_o)
+    # one iterate() at a time: the iterable yields the residual after each step and x is complete after each
+    x = x0.copy()
+    it = isb.cg_iterator_(x, A, b, **kw_d)
+    r0 = np.linalg.norm(b - O.to_scipy() @ x0) if hasattr(O, "to_scipy") else None
+    assert it.iteration == 0 and not it.done and it.tol == pytest.approx(math.sqrt(np.finfo(np.float64).eps) * it.residual)
+    if r0 is not None:
+        assert it.residual == pytest.approx(r0, rel=1e-12)
+    res = []
+    for k, r in enumerate(it, start=1):
+        res.append(r)
+        assert it.iteration == k and it.residual == r
+        if k == 5:                                              # x_5 of the reference recurrence
+            x5, _ = oracle.cg_(x0.copy(), O, b, log=True, maxiter=5, **kw_o)
+            assert relerr(x, x5) <= 1e-12
+    assert it.done and it.converged and it.mv_products == ho.mvps and len(res) == ho.niters
+    np.testing.assert_allclose(res, ho["resnorm"], rtol=1e-10)
+    assert relerr(x, xo) <= 1e-10
+    assert it.step(3) == [] and it.iteration == ho.niters      # iterate past done() returns nothing
+    it.close()
+    # batches of 7 give the same sequence; device-resident x and b
+    xd = isb.DeviceArray.from_numpy(A.ctx, x0)
+    bd = isb.DeviceArray.from_numpy(A.ctx, b)
+    it = isb.cg_iterator_(xd, A, bd, **kw_d)
+    res2 = []
+    while not it.done:
+        res2.extend(it.step(7))
+    np.testing.assert_array_equal(res2, res)
+    np.testing.assert_array_equal(xd.numpy(), x)
+    it.close()
+
+
+def test_cg_statevars_are_used_and_hold_the_state(isb, oracle):
+    rng = np.random.default_rng(SEED + 1)
+    O = oracle.laplace_matrix(np.float64, 10, 3, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    b = rng.standard_normal(O.n)
+    x_ref, h_ref = isb.cg(A, b, log=True)
+    sv = isb.CGStateVariables(*(isb.DeviceArray.zeros(A.ctx, O.n) for _ in range(3)))
+    x = np.zeros(O.n)
+    x2, h = isb.cg_(x, A, b, statevars=sv, initially_zero=True, log=True)
+    assert x2 is x and h.isconverged and h.niters == h_ref.niters and h.mvps == h_ref.mvps
+    np.testing.assert_array_equal(h["resnorm"], h_ref["resnorm"])
+    np.testing.assert_array_equal(x, x_ref)
+    # the caller's vectors hold the final state: r is the recurrence residual, c = A u
+    r = sv.r.numpy()
+    assert np.linalg.norm(r) == pytest.approx(h["resnorm"][-1], rel=1e-12)
+    assert relerr(sv.c.numpy(), A @ sv.u.numpy()) <= 1e-13
+    with pytest.raises(TypeError):
+        isb.CGStateVariables(np.zeros(3), np.zeros(3), np.zeros(3))
