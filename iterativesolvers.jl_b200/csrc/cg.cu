@@ -15,10 +15,11 @@
 // Algorithmic bytes per iteration: nnz*(V+4) + (n+1)*4 + 11*n*V.
 //
 // Multi-GPU (row slabs, one process per GPU), two interchangeable transports (option "comm"):
-//   * peer memory (default when the IPC mapping succeeded, peer.cuh): K1 is followed by k_halo_push
-//     (boundary values stored straight into the neighbours' halo segments over NVLink), K2 waits on the
-//     halo flags before its first gather, and the block that finishes a reduction performs the one-shot
-//     all-to-all allreduce itself -- 4 launches per iteration, no NCCL call, no scalar kernel;
+//   * peer memory (default when the IPC mapping succeeded, peer.cuh): K3 is followed by k_halo_push of r's
+//     boundary values (stored straight into the neighbours' halo segments over NVLink), the next K1 forms the
+//     halo part of u locally from them (so K2 never waits; PCG keeps the push of u after K1 and the wait in
+//     K2), and the block that finishes a reduction performs the one-shot all-to-all allreduce itself --
+//     4 launches per iteration, no NCCL call, no scalar kernel;
 //   * NCCL: halo = pack kernel + grouped ncclSend/ncclRecv, each sum = ncclAllReduce of one double followed
 //     by a 1-thread bookkeeping kernel.
 #include "blas1.cuh"

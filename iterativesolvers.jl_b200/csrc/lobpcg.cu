@@ -51,6 +51,16 @@ __device__ __forceinline__ void lds4(const T *p, T (&v)[4]) {
 }
 
 template <typename T>
+__device__ __forceinline__ void st4(T *p, const T (&v)[4]) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+    reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
+    reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
+  }
+}
+
+template <typename T>
 __device__ __forceinline__ void load_row(const T *__restrict__ p, T (&v)[BS]) {
   if constexpr (sizeof(T) == 4) {
     const float4 *q = reinterpret_cast<const float4 *>(p);
@@ -104,12 +114,25 @@ __global__ void __launch_bounds__(kThreads) k_to_colmajor(const T *__restrict__ 
   }
 }
 
+// multi-GPU: rows idx[k] of a row-major block -> contiguous send buffer (4 lanes per row)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_pack_rows(const int *__restrict__ idx, const T *__restrict__ X,
+                                                        int64_t nrows, T *__restrict__ out) {
+  const int sub = threadIdx.x & 3;
+  for (int64_t k = (blockIdx.x * (int64_t)kThreads + threadIdx.x) >> 2; k < nrows;
+       k += ((int64_t)gridDim.x * kThreads) >> 2) {
+    T v[4];
+    lds4<T>(X + (int64_t)idx[k] * BS + 4 * sub, v);
+    st4<T>(out + k * BS + 4 * sub, v);
+  }
+}
+
 // Y = A X on row-major blocks: 4 lanes per row, each lane owns 4 of the 16 columns, so every nonzero is one
 // coalesced 64-byte (fp32) read of the X row.
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_spmm_rm(const int *__restrict__ rowptr, const int *__restrict__ colind,
                                                       const T *__restrict__ vals, const T *__restrict__ X,
-                                                      int64_t m, T *__restrict__ Y) {
+                                                      const T *__restrict__ Xhalo, int64_t m, T *__restrict__ Y) {
   const int sub = threadIdx.x & 3;
   const int rib = threadIdx.x >> 2;
   const uint64_t pol = policy_evict_first();
@@ -121,7 +144,8 @@ __global__ void __launch_bounds__(kThreads) k_spmm_rm(const int *__restrict__ ro
     for (int k = b; k < e; ++k) {
       const int c = ld_stream<int>(colind + k, pol);
       const T a = ld_stream<T>(vals + k, pol);
-      const T *xr = X + (int64_t)c * BS + 4 * sub;
+      // local extended index: [0, m) own rows, [m, m + n_halo) rows received from the neighbours
+      const T *xr = (c < m ? X + (int64_t)c * BS : Xhalo + (int64_t)(c - m) * BS) + 4 * sub;
       if constexpr (sizeof(T) == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4 *>(xr));
         acc[0] += a * t.x; acc[1] += a * t.y; acc[2] += a * t.z; acc[3] += a * t.w;
@@ -302,15 +326,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_rdiv(T *__restrict__ X0, T *__r
 // columns 4c..4c+3, so every global load/store instruction of the warp covers 8 x 64 B contiguous bytes (fp32).
 // The first row-per-thread version issued 32 sectors per request and sat at 78 % L1/LSU throughput (ncu,
 // profiles/r1_lobpcg_kernels_v3.ncu-rep); the other three chunks of a row now come from the quad by shuffle.
-template <typename T>
-__device__ __forceinline__ void st4(T *p, const T (&v)[4]) {
-  if constexpr (sizeof(T) == 4) {
-    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  } else {
-    reinterpret_cast<double2 *>(p)[0] = make_double2(v[0], v[1]);
-    reinterpret_cast<double2 *>(p)[1] = make_double2(v[2], v[3]);
-  }
-}
 template <typename T>
 __device__ __forceinline__ void quad_gather(const T (&mine)[4], T (&row)[BS]) {
 #pragma unroll
@@ -882,7 +897,7 @@ struct Lobpcg {
   double *gram_partials, *d_gram;                // device Gram output: 4 * 256 doubles
   T *d_small;                                    // V (3*256) + lambda (16) + U (256)
   int *d_idx;
-  DevBuf scratch;
+  DevBuf scratch, send_blk, halo_blk;              // multi-GPU: packed boundary rows out / halo rows in (n x 16)
   int grid_gram, grid_vec, grid_spmm;
 
   template <int NR>
@@ -906,6 +921,7 @@ struct Lobpcg {
       else B200_TRY(gram_launch<2>(L, Rb));
     }
     B200_LAUNCH_CHECK(ctx);
+    B200_TRY(allreduce_sum_dev(ctx, d_gram, 256 * nr));   // row slabs: global Gram = sum of the slabs' Grams
     B200_CUDA(cudaMemcpyAsync(host_out, d_gram, sizeof(double) * 256 * nr, cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     return B200_OK;
@@ -938,6 +954,7 @@ struct Lobpcg {
                                                                                      ctx->red.ticket, d_gram);
       }
       B200_LAUNCH_CHECK(ctx);
+      B200_TRY(allreduce_sum_dev(ctx, d_gram, 256 * (with_p ? 8 : 3)));
       B200_CUDA(cudaMemcpyAsync(host_out, d_gram, sizeof(double) * 256 * (with_p ? 8 : 3), cudaMemcpyDeviceToHost,
                                 ctx->stream));
       B200_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -966,6 +983,7 @@ struct Lobpcg {
                                                                                    d_gram);
       }
       B200_LAUNCH_CHECK(ctx);
+      B200_TRY(allreduce_sum_dev(ctx, d_gram, 256));
       B200_CUDA(cudaMemcpyAsync(host_out, d_gram, sizeof(double) * 256, cudaMemcpyDeviceToHost, ctx->stream));
       B200_CUDA(cudaStreamSynchronize(ctx->stream));
       return B200_OK;
@@ -1004,9 +1022,35 @@ struct Lobpcg {
     return B200_OK;
   }
 
+  // multi-GPU: the rows of Xin the neighbours' SpMM needs (the operator's send lists) -> their halo blocks
+  int halo_block(const T *Xin) {
+    if (ctx->world == 1 || (A->n_send == 0 && A->n_halo == 0)) return B200_OK;
+    cudaStream_t st = ctx->stream;
+    if (A->n_send) {
+      k_pack_rows<T><<<stream_grid(ctx, A->n_send, kThreads / 4, 8), kThreads, 0, st>>>(A->send_idx, Xin, A->n_send,
+                                                                                       (T *)send_blk.p);
+      B200_LAUNCH_CHECK(ctx);
+    }
+    const ncclDataType_t nt = sizeof(T) == 8 ? ncclDouble : ncclFloat;
+    B200_NCCL(ncclGroupStart());
+    for (int p = 0; p < ctx->world; ++p) {
+      if (p == ctx->rank) continue;
+      if (A->send_count[p])
+        B200_NCCL(ncclSend((const T *)send_blk.p + (size_t)BS * A->send_offset[p], (size_t)BS * A->send_count[p], nt, p,
+                           ctx->comm, st));
+      if (A->recv_count[p])
+        B200_NCCL(ncclRecv((T *)halo_blk.p + (size_t)BS * A->recv_offset[p], (size_t)BS * A->recv_count[p], nt, p,
+                           ctx->comm, st));
+    }
+    B200_NCCL(ncclGroupEnd());
+    return B200_OK;
+  }
+
   int spmm(const T *Xin, T *Yout) {
+    B200_TRY(halo_block(Xin));
     ProfScope prof(ctx, 0);
-    k_spmm_rm<T><<<grid_spmm, kThreads, 0, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals, Xin, n, Yout);
+    k_spmm_rm<T><<<grid_spmm, kThreads, 0, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals, Xin,
+                                                          (const T *)halo_blk.p, n, Yout);
     B200_LAUNCH_CHECK(ctx);
     return B200_OK;
   }
@@ -1020,8 +1064,8 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
   const int sizeX = o->blocksize;
   B200_REQUIRE(sizeX >= 1 && sizeX <= BS, "lobpcg: block size %d not in 1..%d", sizeX, BS);
   B200_REQUIRE(ldx == n, "lobpcg: X must be n x blocksize with leading dimension n");
-  B200_REQUIRE(sizeX <= n, "X column dimension exceeds the row dimension");                        // :833
-  B200_REQUIRE(3 * (int64_t)sizeX <= n, "The LOBPCG algorithms is not stable to use when the matrix size is less "
+  B200_REQUIRE(sizeX <= A->n_global, "X column dimension exceeds the row dimension");              // :833
+  B200_REQUIRE(3 * (int64_t)sizeX <= A->n_global, "The LOBPCG algorithms is not stable to use when the matrix size is less "
                "than 3 times the block size. Please use a dense solver instead.");                 // :834
   const double eps = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
   const double tol = o->tol < 0 ? pow(eps, 0.3) : o->tol;                                           // :751
@@ -1054,6 +1098,10 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
   double *d_norms = (double *)p; p += sizeof(double) * 64;
   L.d_idx = (int *)p;
   L.gR = L.gP = L.gAP = nullptr;
+  if (ctx->world > 1) {
+    B200_TRY(L.send_blk.alloc(sizeof(T) * BS * (size_t)std::max<int64_t>(A->n_send, 1)));
+    B200_TRY(L.halo_blk.alloc(sizeof(T) * BS * (size_t)std::max<int64_t>(A->n_halo, 1)));
+  }
   k_to_rowmajor<T><<<L.grid_vec, kThreads, 0, st>>>(Xcm, L.X, n, sizeX);
   B200_LAUNCH_CHECK(ctx);
 
@@ -1097,6 +1145,7 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
       ctx->launches++;   // two launches: the second is counted by B200_LAUNCH_CHECK below
     }
     B200_LAUNCH_CHECK(ctx);
+    B200_TRY(allreduce_sum_dev(ctx, d_norms, BS));
     double nn[BS];
     B200_CUDA(cudaMemcpyAsync(nn, d_norms, sizeof(double) * BS, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
@@ -1258,7 +1307,6 @@ int b200_lobpcg_solve(b200_ctx *ctx, const b200_csr *A, void *X_dev, int64_t ldx
                       b200_lobpcg_result *res, double *lambda_host, double *resnorm_host) {
   B200_REQUIRE(ctx && A && X_dev && opts, "NULL argument");
   B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
-  B200_REQUIRE(ctx->world == 1, "lobpcg is single-GPU in this version");
   B200_CUDA(cudaSetDevice(ctx->device));
   return A->dtype == B200_F64 ? lobpcg_impl<double>(ctx, A, (double *)X_dev, ldx, opts, res, lambda_host, resnorm_host)
                               : lobpcg_impl<float>(ctx, A, (float *)X_dev, ldx, opts, res, lambda_host, resnorm_host);

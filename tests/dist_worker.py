@@ -71,8 +71,11 @@ def main():
     rsh = np.random.default_rng(7).random(n)
     xb, hb = isb.bicgstabl_(np.zeros(m), A1, b_loc, 2, initial_zero=True, log=True, max_mv_products=120,
                             r_shadow=rsh[lo:lo + m].copy(), reltol=1e-9)
+    # lobpcg on the row partition: block halo exchange in the SpMM, allreduce of the Gram blocks and norms
+    X0 = np.random.default_rng(11).random((n, 4))
+    rl = isb.lobpcg(A1, False, X0[lo:lo + m].copy(), maxiter=6, _fixed_iterations=True)
     others = [None] * world
-    dist.all_gather_object(others, (xm, xgm, xb))
+    dist.all_gather_object(others, (xm, xgm, xb, rl.X))
 
     gathered = [None] * world
     dist.all_gather_object(gathered, (y_loc, results["slab"][0], results["generated"][0],
@@ -118,7 +121,15 @@ def main():
         assert hb.niters == hs.niters and hb.mvps == hs.mvps
         k = min(5, hs.niters)
         assert np.max(np.abs(hb["resnorm"][:k] - hs["resnorm"][:k]) / hs["resnorm"][:k]) <= 1e-7
-        print(f"minres/gmres/bicgstabl partitioned == single: iters {hm.niters}/{hg.niters}/{hb.niters}")
+        rs = isb.lobpcg(Ag, False, X0.copy(), maxiter=6, _fixed_iterations=True)
+        Xd = np.concatenate([o[3] for o in others], axis=0)
+        assert rl.iterations == rs.iterations
+        assert np.max(np.abs(rl.lam - rs.lam) / np.abs(rs.lam)) <= 1e-9
+        assert np.max(np.abs(rl.residual_norms - rs.residual_norms) / rs.residual_norms) <= 1e-6
+        assert np.max(np.abs(Xd.T @ Xd - np.eye(4))) <= 1e-10
+        sgn = np.sign(np.sum(Xd * rs.X, axis=0))
+        assert np.max(np.abs(Xd * sgn[None, :] - rs.X)) <= 1e-6
+        print(f"minres/gmres/bicgstabl/lobpcg partitioned == single: iters {hm.niters}/{hg.niters}/{hb.niters}/{rl.iterations}")
         print("DIST_OK")
     dist.barrier()
     dist.destroy_process_group()

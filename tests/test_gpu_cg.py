@@ -291,6 +291,49 @@ def test_cg_256cubed_properties(isb):
     assert np.array_equal(h["resnorm"], h2["resnorm"])
 
 
+def test_cg_512cubed_properties(isb):
+    """BASELINE.json configs[3] on one GPU: n = 512^3 (nnz = 937 951 232, the int32 CSR limit case).  Same
+    size-independent properties as above plus: the TMA-streamed and the sub-warp SpMV kernels give the same
+    history to 1e-9, and 40 iterations through the iterator form reproduce the first 40 residuals bit-for-bit."""
+    import ctypes as C
+    ctx = isb.default_context()
+    N = 512
+    n = N ** 3
+    A = isb.B200CSR.laplacian(N, 3)
+    assert A.nnz == 7 * N ** 3 - 6 * N ** 2
+    L = isb.lib()
+    # x* = smooth + rough part, generated on the host once (1 GB)
+    rng = np.random.default_rng(SEED)
+    xstar = rng.standard_normal(n)
+    xs = isb.DeviceArray.from_numpy(ctx, xstar)
+    b = isb.DeviceArray(ctx, n)
+    A.mul_(b, xs)
+    x = isb.DeviceArray.zeros(ctx, n)
+    x, h = isb.cg_(x, A, b, initially_zero=True, log=True, reltol=1e-6)
+    assert h.isconverged and 300 < h.niters < 3000 and h.mvps == h.niters
+    r = isb.DeviceArray(ctx, n)
+    A.mul_(r, x)
+    assert L.b200_axpby(ctx._h, n, 1.0, b._p, -1.0, r._p, 0) == 0          # r = b - A x
+    nr, nb = C.c_double(), C.c_double()
+    L.b200_nrm2(ctx._h, n, r._p, 0, C.byref(nr))
+    L.b200_nrm2(ctx._h, n, b._p, 0, C.byref(nb))
+    assert nr.value / nb.value <= 1.01e-6
+    assert nr.value == pytest.approx(h["resnorm"][-1], rel=1e-4)
+    del r, xs
+    try:
+        assert L.b200_ctx_set_option(ctx._h, b"spmv_kernel", 1) == 0      # sub-warp-per-row kernel
+        x1 = isb.DeviceArray.zeros(ctx, n)
+        x1, h1 = isb.cg_(x1, A, b, initially_zero=True, log=True, maxiter=40, reltol=0.0)
+    finally:
+        L.b200_ctx_set_option(ctx._h, b"spmv_kernel", 0)
+    np.testing.assert_allclose(h1["resnorm"], h["resnorm"][:40], rtol=1e-9)   # different in-row summation order
+    x2 = isb.DeviceArray.zeros(ctx, n)
+    it = isb.cg_iterator_(x2, A, b, initially_zero=True, reltol=1e-6)
+    res = it.step(25) + it.step(15)
+    assert np.array_equal(res, h["resnorm"][:40]) and it.iteration == 40 and not it.done
+    it.close()
+
+
 # ------------------------------------------------------------------ iterator form (cg_iterator!, src/cg.jl:120-155)
 @pytest.mark.parametrize("jacobi", [False, True])
 def test_cg_iterator_steps_match_oracle(isb, oracle, jacobi):
