@@ -66,7 +66,8 @@ typedef struct {
   int64_t iters;        /* niters(history)                                                        */
   int64_t mvps;         /* history.mvps  (quirks of SURVEY.md section 9 reproduced)               */
   int32_t isconverged;  /* converged(iterable) at exit                                            */
-  int32_t status;       /* 0, or B200_ERR_BREAKDOWN if a NaN/breakdown was detected               */
+  int32_t status;       /* 0, or B200_ERR_BREAKDOWN if a NaN/breakdown was detected
+                           (b200_cg_iter_next: 1 once done(it) holds)                             */
   double tol;           /* max(reltol*||r0||, abstol)                                             */
   double residual;      /* iterable.residual at exit                                              */
   int64_t n_resnorm;    /* number of :resnorm entries written to the caller's history buffer      */
@@ -104,7 +105,9 @@ B200_API int b200_ctx_profile_read(b200_ctx *ctx, int slot, double *total_ms, in
  *   "snake": 1 (default) = consecutive hot kernels of a solver sweep the rows in alternating directions so
  *           that each starts on the data the previous one touched last (L2 reuse); 0 = always ascending
  *   "comm": 0 = auto, 1 = NCCL collectives, 2 = NVLink peer-memory collectives fused into the kernels
- *           (multi-GPU contexts; get "peer_ok" tells whether the peer buffers could be mapped) */
+ *           (multi-GPU contexts; get "peer_ok" tells whether the peer buffers could be mapped)
+ *   "lobpcg_mma": 1 (default) = fp32 LOBPCG blocks run the update and the Gram products as 3xTF32 tensor-core
+ *           MMAs (fp32-level products, fp32 accumulate); 0 = CUDA-core kernels (always used for fp64) */
 B200_API int b200_ctx_set_option(b200_ctx *ctx, const char *name, int64_t value);
 B200_API int b200_ctx_get_option(const b200_ctx *ctx, const char *name, int64_t *value);
 /* sum over ranks (no-op for world==1); used by hosts for max/sum of small host scalars */
@@ -225,7 +228,7 @@ typedef struct {
                                iterations past `done` are no-ops.                                   */
   b200_precond Pl;          /* Identity -> CGIterable (src/cg.jl:43-66); else PCGIterable (:72-100) */
   int32_t fixed_iterations; /* bench only: ignore convergence, run exactly maxiter iterations      */
-  int32_t variant;          /* 0 = default engine; other values select experimental kernels        */
+  int32_t variant;          /* reserved, must be 0                                                 */
 } b200_cg_opts;
 
 /* cg!(x, A, b; ...)  reference src/cg.jl:209-242.  x,b device pointers (local slabs). */

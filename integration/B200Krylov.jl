@@ -1,0 +1,309 @@
+# B200Krylov.jl -- the reference-side binding of libb200krylov.so (INTEGRATION.md).
+#
+# SOURCE ONLY: Julia is not installed in the build image, so this file has never been executed there.  It
+# is the file a maintainer of IterativeSolvers.jl would add (or ship as a package extension): device
+# operator / vector types plus methods of the five solver entry points that dispatch on them.  Every ccall
+# below is exercised, with the same argument meaning, by the Python harness (iterativesolvers.jl_b200/_lib.py,
+# whose signature table tests/test_abi_and_host.py checks against include/b200krylov.h).
+#
+# Keyword names, defaults and return shapes are the reference's: src/cg.jl:209-217, src/chebyshev.jl:131-139,
+# src/gmres.jl:184-194, src/minres.jl:200-207, src/bicgstabl.jl:181-188, src/lobpcg.jl:827-829.
+module B200Krylov
+
+using SparseArrays, LinearAlgebra
+import IterativeSolvers
+import IterativeSolvers: cg!, chebyshev!, gmres!, minres!, bicgstabl!, lobpcg, ConvergenceHistory, Identity,
+                         ClassicalGramSchmidt, ModifiedGramSchmidt, DGKS, OrthogonalizationMethod, LOBPCGResults
+import LinearAlgebra: mul!, ldiv!
+
+const LIB = "libb200krylov.so"
+
+check(status::Integer) =
+    status == 0 ? nothing : error(unsafe_string(ccall((:b200_last_error, LIB), Cstring, ())))
+
+# ------------------------------------------------------------------------------------------- context
+mutable struct Ctx
+    h::Ptr{Cvoid}
+    function Ctx(device::Integer = 0)
+        r = Ref{Ptr{Cvoid}}()
+        check(ccall((:b200_ctx_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r))
+        finalizer(c -> ccall((:b200_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), new(r[]))
+    end
+end
+const DEFAULT_CTX = Ref{Union{Nothing,Ctx}}(nothing)
+default_ctx() = something(DEFAULT_CTX[], (DEFAULT_CTX[] = Ctx(0)))
+
+dtype_code(::Type{Float64}) = Cint(0)
+dtype_code(::Type{Float32}) = Cint(1)
+const BlasReal = Union{Float32,Float64}
+
+# ------------------------------------------------------------------------------------------- vectors
+mutable struct B200Vector{T<:BlasReal} <: AbstractVector{T}
+    p::Ptr{T}
+    n::Int
+    ctx::Ctx
+    function B200Vector{T}(ctx::Ctx, n::Integer) where {T}
+        r = Ref{Ptr{Cvoid}}()
+        check(ccall((:b200_malloc, LIB), Cint, (Ptr{Cvoid}, Csize_t, Ref{Ptr{Cvoid}}), ctx.h, n * sizeof(T), r))
+        finalizer(v -> ccall((:b200_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), v.ctx.h, v.p),
+                  new{T}(Ptr{T}(r[]), n, ctx))
+    end
+end
+Base.size(v::B200Vector) = (v.n,)
+Base.similar(v::B200Vector{T}) where {T} = B200Vector{T}(v.ctx, v.n)
+function B200Vector(ctx::Ctx, x::Vector{T}) where {T<:BlasReal}
+    v = B200Vector{T}(ctx, length(x))
+    check(ccall((:b200_upload, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), ctx.h, v.p, x, sizeof(x)))
+    v
+end
+function Base.Array(v::B200Vector{T}) where {T}
+    x = Vector{T}(undef, v.n)
+    check(ccall((:b200_download, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Csize_t), v.ctx.h, x, v.p, sizeof(x)))
+    x
+end
+# operator-level BLAS-1: lets the UNMODIFIED reference loops (src/cg.jl:43-66, src/minres.jl:97-159) run on
+# device vectors, one ccall per Julia operation
+LinearAlgebra.dot(x::B200Vector{T}, y::B200Vector{T}) where {T} = (r = Ref{Cdouble}();
+    check(ccall((:b200_dot, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ref{Cdouble}),
+                x.ctx.h, x.n, x.p, y.p, dtype_code(T), r)); T(r[]))
+LinearAlgebra.norm(x::B200Vector{T}) where {T} = (r = Ref{Cdouble}();
+    check(ccall((:b200_nrm2, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Cint, Ref{Cdouble}),
+                x.ctx.h, x.n, x.p, dtype_code(T), r)); T(r[]))
+# y = a*x + b*y
+axpby!(a, x::B200Vector{T}, b, y::B200Vector{T}) where {T} =
+    (check(ccall((:b200_axpby, LIB), Cint, (Ptr{Cvoid}, Int64, Cdouble, Ptr{Cvoid}, Cdouble, Ptr{Cvoid}, Cint),
+                 x.ctx.h, x.n, a, x.p, b, y.p, dtype_code(T))); y)
+LinearAlgebra.axpy!(a, x::B200Vector, y::B200Vector) = axpby!(a, x, 1, y)
+LinearAlgebra.rmul!(x::B200Vector{T}, a::Number) where {T} =
+    (check(ccall((:b200_scal, LIB), Cint, (Ptr{Cvoid}, Int64, Cdouble, Ptr{Cvoid}, Cint), x.ctx.h, x.n, a, x.p, dtype_code(T))); x)
+Base.copyto!(y::B200Vector{T}, x::B200Vector{T}) where {T} =
+    (check(ccall((:b200_copy, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Cint), x.ctx.h, x.n, x.p, y.p, dtype_code(T))); y)
+Base.fill!(x::B200Vector{T}, a::Number) where {T} =
+    (check(ccall((:b200_fill, LIB), Cint, (Ptr{Cvoid}, Int64, Cdouble, Ptr{Cvoid}, Cint), x.ctx.h, x.n, a, x.p, dtype_code(T))); x)
+
+# ------------------------------------------------------------------------------------------- operator
+mutable struct B200CSR{T<:BlasReal}
+    h::Ptr{Cvoid}
+    ctx::Ctx
+    n::Int
+end
+# stands where a SparseMatrixCSC is passed today (src/cg.jl:54, src/gmres.jl:287, ...): CSC -> device CSR int32
+function B200CSR(A::SparseMatrixCSC{T,Ti}; ctx::Ctx = default_ctx()) where {T<:BlasReal,Ti<:Union{Int32,Int64}}
+    size(A, 1) == size(A, 2) || throw(DimensionMismatch("square operators only"))
+    r = Ref{Ptr{Cvoid}}()
+    check(ccall((:b200_csr_from_csc, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Int64, Ptr{Ti}, Ptr{Ti}, Ptr{T}, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
+                ctx.h, size(A, 1), size(A, 2), A.colptr, A.rowval, A.nzval, sizeof(Ti), dtype_code(T), 1, r))
+    finalizer(a -> ccall((:b200_csr_destroy, LIB), Cint, (Ptr{Cvoid},), a.h), B200CSR{T}(r[], ctx, size(A, 1)))
+end
+Base.size(A::B200CSR) = (A.n, A.n)
+Base.size(A::B200CSR, d::Integer) = d <= 2 ? A.n : 1
+Base.eltype(::B200CSR{T}) where {T} = T
+mul!(y::B200Vector{T}, A::B200CSR{T}, x::B200Vector{T}) where {T} =
+    (check(ccall((:b200_spmv, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), A.ctx.h, A.h, x.p, y.p)); y)
+
+# the diagonal preconditioner of test/cg.jl:14-18
+struct JacobiPrec{T}
+    d::B200Vector{T}
+end
+function JacobiPrec(A::B200CSR{T}) where {T}
+    d = B200Vector{T}(A.ctx, A.n)
+    check(ccall((:b200_csr_diag, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), A.ctx.h, A.h, d.p))
+    JacobiPrec{T}(d)
+end
+ldiv!(y::B200Vector{T}, P::JacobiPrec{T}, x::B200Vector{T}) where {T} =
+    (check(ccall((:b200_jacobi_ldiv, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint),
+                 x.ctx.h, x.n, P.d.p, x.p, y.p, dtype_code(T))); y)
+ldiv!(P::JacobiPrec, x::B200Vector) = ldiv!(x, P, x)
+
+# ------------------------------------------------------------------------------------------- C structs
+struct Precond
+    kind::Int32
+    reserved::Int32
+    diag::Ptr{Cvoid}
+end
+prec(::Identity) = Precond(0, 0, C_NULL)
+prec(P::JacobiPrec) = Precond(1, 0, P.d.p)
+prec(P) = throw(ArgumentError("the device path supports Identity() and JacobiPrec; got $(typeof(P))"))
+
+mutable struct Result
+    iters::Int64
+    mvps::Int64
+    isconverged::Int32
+    status::Int32
+    tol::Float64
+    residual::Float64
+    n_resnorm::Int64
+    Result() = new(0, 0, 0, 0, 0.0, 0.0, 0)
+end
+struct CgOpts
+    abstol::Float64; reltol::Float64; maxiter::Int64; initially_zero::Int32; check_every::Int32
+    Pl::Precond; fixed_iterations::Int32; variant::Int32
+end
+struct GmresOpts
+    abstol::Float64; reltol::Float64; maxiter::Int64; restart::Int32; initially_zero::Int32
+    orth_meth::Int32; reserved::Int32; Pl::Precond; Pr::Precond
+end
+struct MinresOpts
+    abstol::Float64; reltol::Float64; maxiter::Int64; initially_zero::Int32; skew_hermitian::Int32
+end
+struct BicgstablOpts
+    abstol::Float64; reltol::Float64; max_mv_products::Int64; l::Int32; initial_zero::Int32
+    Pl::Precond; r_shadow::Ptr{Cvoid}
+end
+struct LobpcgOpts
+    tol::Float64; maxiter::Int64; largest::Int32; blocksize::Int32; P::Precond
+    fixed_iterations::Int32; reserved::Int32
+end
+mutable struct LobpcgResult
+    iterations::Int64; converged::Int32; status::Int32
+    LobpcgResult() = new(0, 0, 0)
+end
+orth_code(::ModifiedGramSchmidt) = Int32(0); orth_code(::ClassicalGramSchmidt) = Int32(1); orth_code(::DGKS) = Int32(2)   # B200_ORTH_*
+
+function history(res::Result, resnorm, abstol, reltol; restart = nothing)
+    h = ConvergenceHistory(partial = false, restart = restart)
+    h[:abstol] = abstol; h[:reltol] = reltol; h[:tol] = res.tol
+    h.mvps = res.mvps; h.iters = res.iters; h.isconverged = res.isconverged != 0
+    h.data[:resnorm] = resnorm[1:res.n_resnorm]
+    h
+end
+
+# host x, b: upload, solve on the device, download x into the caller's array (in place, src/cg.jl:241)
+function staged(f, A::B200CSR{T}, x::Vector{T}, b::Vector{T}) where {T}
+    xd, bd = B200Vector(A.ctx, x), B200Vector(A.ctx, b)
+    f(xd, bd)
+    copyto!(x, Array(xd))
+    x
+end
+
+# ------------------------------------------------------------------------------------------- cg!
+function cg!(x::B200Vector{T}, A::B200CSR{T}, b::B200Vector{T};
+             abstol::Real = zero(T), reltol::Real = sqrt(eps(T)), maxiter::Int = size(A, 2), log::Bool = false,
+             verbose::Bool = false, Pl = Identity(), initially_zero::Bool = false, kwargs...) where {T}
+    res = Result(); hist = Vector{Float64}(undef, log ? maxiter + 1 : 0)
+    o = CgOpts(abstol, reltol, maxiter, initially_zero, 0, prec(Pl), 0, 0)
+    check(ccall((:b200_cg_solve, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{CgOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                A.ctx.h, A.h, x.p, b.p, o, res, hist, length(hist)))
+    log ? (x, history(res, hist, abstol, reltol)) : x
+end
+# host arrays: one call does H2D of b and x, the solve, D2H of x
+function cg!(x::Vector{T}, A::B200CSR{T}, b::Vector{T};
+             abstol::Real = zero(T), reltol::Real = sqrt(eps(T)), maxiter::Int = size(A, 2), log::Bool = false,
+             verbose::Bool = false, Pl = Identity(), initially_zero::Bool = false, kwargs...) where {T}
+    res = Result(); hist = Vector{Float64}(undef, log ? maxiter + 1 : 0)
+    o = CgOpts(abstol, reltol, maxiter, initially_zero, 0, prec(Pl), 0, 0)
+    check(ccall((:b200_cg_solve_host, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ref{CgOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                A.ctx.h, A.h, x, b, o, res, hist, length(hist)))
+    log ? (x, history(res, hist, abstol, reltol)) : x
+end
+
+# cg_iterator! (src/cg.jl:120-155): `for (k, residual) in enumerate(it)` as in docs/src/iterators.md
+mutable struct B200CGIterable{T}
+    h::Ptr{Cvoid}
+    x::B200Vector{T}
+    res::Result
+end
+function IterativeSolvers.cg_iterator!(x::B200Vector{T}, A::B200CSR{T}, b::B200Vector{T}, Pl = Identity();
+                                       abstol::Real = zero(T), reltol::Real = sqrt(eps(T)), maxiter::Int = size(A, 2),
+                                       statevars = nothing, initially_zero::Bool = false) where {T}
+    o = CgOpts(abstol, reltol, maxiter, initially_zero, 0, prec(Pl), 0, 0)
+    r = Ref{Ptr{Cvoid}}()
+    u, rr, c = statevars === nothing ? (C_NULL, C_NULL, C_NULL) : (statevars.u.p, statevars.r.p, statevars.c.p)
+    check(ccall((:b200_cg_iter_create, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{CgOpts}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}),
+                A.ctx.h, A.h, x.p, b.p, o, u, rr, c, r))
+    it = B200CGIterable{T}(r[], x, Result())
+    step!(it, 0)
+    finalizer(i -> ccall((:b200_cg_iter_destroy, LIB), Cint, (Ptr{Cvoid},), i.h), it)
+end
+step!(it::B200CGIterable, k::Integer) =
+    check(ccall((:b200_cg_iter_next, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{Result}, Ptr{Float64}, Int64), it.h, k, it.res, C_NULL, 0))
+function Base.iterate(it::B200CGIterable, iteration::Int = 0)
+    it.res.status == 1 && return nothing                    # done(it, iteration)  src/cg.jl:36
+    step!(it, 1)
+    it.res.residual, iteration + 1                           # src/cg.jl:65
+end
+
+# ------------------------------------------------------------------------------------------- chebyshev!
+function chebyshev!(x::Vector{T}, A::B200CSR{T}, b::Vector{T}, λmin::Real, λmax::Real;
+                    abstol::Real = zero(T), reltol::Real = sqrt(eps(T)), Pl = Identity(), maxiter::Int = size(A, 2),
+                    log::Bool = false, verbose::Bool = false, initially_zero::Bool = false) where {T}
+    res = Result(); hist = Vector{Float64}(undef, maxiter)
+    o = CgOpts(abstol, reltol, maxiter, initially_zero, 0, prec(Pl), 0, 0)
+    staged(A, x, b) do xd, bd
+        check(ccall((:b200_chebyshev_solve, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cdouble, Ref{CgOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                    A.ctx.h, A.h, xd.p, bd.p, λmin, λmax, o, res, hist, length(hist)))
+    end
+    log ? (x, history(res, hist, abstol, reltol)) : x
+end
+
+# ------------------------------------------------------------------------------------------- gmres!
+function gmres!(x::Vector{T}, A::B200CSR{T}, b::Vector{T};
+                Pl = Identity(), Pr = Identity(), abstol::Real = zero(T), reltol::Real = sqrt(eps(T)),
+                restart::Int = min(20, size(A, 2)), maxiter::Int = size(A, 2), log::Bool = false,
+                initially_zero::Bool = false, verbose::Bool = false,
+                orth_meth::OrthogonalizationMethod = ModifiedGramSchmidt()) where {T}
+    res = Result(); hist = Vector{Float64}(undef, log ? maxiter : 0)
+    o = GmresOpts(abstol, reltol, maxiter, restart, initially_zero, orth_code(orth_meth), 0, prec(Pl), prec(Pr))
+    staged(A, x, b) do xd, bd
+        check(ccall((:b200_gmres_solve, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{GmresOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                    A.ctx.h, A.h, xd.p, bd.p, o, res, hist, length(hist)))
+    end
+    log ? (x, history(res, hist, abstol, reltol; restart = restart)) : x
+end
+
+# ------------------------------------------------------------------------------------------- minres!
+function minres!(x::Vector{T}, A::B200CSR{T}, b::Vector{T};
+                 skew_hermitian::Bool = false, verbose::Bool = false, log::Bool = false, abstol::Real = zero(T),
+                 reltol::Real = sqrt(eps(T)), maxiter::Int = size(A, 2), initially_zero::Bool = false) where {T}
+    res = Result(); hist = Vector{Float64}(undef, log ? maxiter : 0)
+    o = MinresOpts(abstol, reltol, maxiter, initially_zero, skew_hermitian)
+    staged(A, x, b) do xd, bd
+        check(ccall((:b200_minres_solve, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{MinresOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                    A.ctx.h, A.h, xd.p, bd.p, o, res, hist, length(hist)))
+    end
+    log ? (x, history(res, hist, abstol, reltol)) : x
+end
+
+# ------------------------------------------------------------------------------------------- bicgstabl!
+function bicgstabl!(x::Vector{T}, A::B200CSR{T}, b::Vector{T}, l::Int = 2;
+                    abstol::Real = zero(T), reltol::Real = sqrt(eps(T)), max_mv_products::Int = size(A, 2),
+                    log::Bool = false, verbose::Bool = false, Pl = Identity(), initial_zero::Bool = false) where {T}
+    res = Result(); hist = Vector{Float64}(undef, log ? max_mv_products : 0)
+    shadow = B200Vector(A.ctx, rand(T, length(b)))            # r_shadow = rand(T, n)  src/bicgstabl.jl:38
+    o = BicgstablOpts(abstol, reltol, max_mv_products, l, initial_zero, prec(Pl), shadow.p)
+    GC.@preserve shadow staged(A, x, b) do xd, bd
+        status = ccall((:b200_bicgstabl_solve, LIB), Cint,
+                       (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{BicgstablOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                       A.ctx.h, A.h, xd.p, bd.p, o, res, hist, length(hist))
+        status == -5 && throw(SingularException(0))           # lu! of the MR matrix, src/bicgstabl.jl:123
+        check(status)
+    end
+    log ? (x, history(res, hist, abstol, reltol)) : x
+end
+
+# ------------------------------------------------------------------------------------------- lobpcg
+function lobpcg(A::B200CSR{T}, largest::Bool, X0::Matrix{T}; P = nothing, tol::Real = eps(T)^(3 / 10),
+                maxiter::Integer = 200, log::Bool = false) where {T}
+    n, bs = size(X0)
+    n == size(A, 1) || throw(DimensionMismatch("X0 has $n rows, A has $(size(A, 1))"))
+    Xd = B200Vector(A.ctx, vec(copy(X0)))                     # X0 is copied  src/lobpcg.jl:830
+    λ = Vector{Float64}(undef, bs); rn = Vector{Float64}(undef, bs)
+    res = LobpcgResult()
+    o = LobpcgOpts(tol, maxiter, largest, bs, P === nothing ? prec(Identity()) : prec(P), 0, 0)
+    status = ccall((:b200_lobpcg_solve, LIB), Cint,
+                   (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{LobpcgOpts}, Ref{LobpcgResult}, Ptr{Float64}, Ptr{Float64}),
+                   A.ctx.h, A.h, Xd.p, n, o, res, λ, rn)
+    status == -5 && throw(PosDefException(0))                 # cholesky! in CholQR  src/lobpcg.jl:380
+    check(status)
+    X = reshape(Array(Xd), n, bs)
+    LOBPCGResults(T.(λ), X, T(tol), T.(rn), Int(res.iterations), Int(maxiter), res.converged != 0, nothing)
+end
+
+end # module

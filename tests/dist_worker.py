@@ -74,8 +74,12 @@ def main():
     # lobpcg on the row partition: block halo exchange in the SpMM, allreduce of the Gram blocks and norms
     X0 = np.random.default_rng(11).random((n, 4))
     rl = isb.lobpcg(A1, False, X0[lo:lo + m].copy(), maxiter=6, _fixed_iterations=True)
+    # chebyshev: one global reduction per step; 12 steps with the analytic spectral bounds (fixed horizon)
+    lam1 = 2.0 - 2.0 * np.cos(np.arange(1, N + 1) * np.pi / (N + 1))
+    xc, hc = isb.chebyshev_(np.zeros(m), A1, b_loc, 3 * lam1[0], 3 * lam1[-1], initially_zero=True, log=True,
+                            maxiter=12, reltol=1e-12)
     others = [None] * world
-    dist.all_gather_object(others, (xm, xgm, xb, rl.X))
+    dist.all_gather_object(others, (xm, xgm, xb, rl.X, xc))
 
     gathered = [None] * world
     dist.all_gather_object(gathered, (y_loc, results["slab"][0], results["generated"][0],
@@ -121,6 +125,11 @@ def main():
         assert hb.niters == hs.niters and hb.mvps == hs.mvps
         k = min(5, hs.niters)
         assert np.max(np.abs(hb["resnorm"][:k] - hs["resnorm"][:k]) / hs["resnorm"][:k]) <= 1e-7
+        xs, hs = isb.chebyshev_(np.zeros(n), Ag, b_global, 3 * lam1[0], 3 * lam1[-1], initially_zero=True, log=True,
+                                maxiter=12, reltol=1e-12)
+        xd = np.concatenate([o[4] for o in others])
+        assert hc.niters == hs.niters == 12 and np.max(np.abs(hc["resnorm"] - hs["resnorm"]) / hs["resnorm"]) <= 1e-10
+        assert np.linalg.norm(xd - xs) <= 1e-10 * np.linalg.norm(xs)
         rs = isb.lobpcg(Ag, False, X0.copy(), maxiter=6, _fixed_iterations=True)
         Xd = np.concatenate([o[3] for o in others], axis=0)
         assert rl.iterations == rs.iterations
