@@ -166,6 +166,44 @@ EXPORT void oracle_cg_steps_f64(int64_t n, const int64_t *colptr, const int64_t 
   *prev_residual_io = prev_residual;
 }
 
+/* NOT reference behaviour -- a stronger CPU baseline for bench.py only: the same CGIterable steps with every
+ * loop spread over the host's threads.  Only valid for a SYMMETRIC matrix: the CSC arrays are then read as the
+ * CSR of A, which turns the reference's serial column scatter into a row-parallel gather (the reference itself
+ * cannot thread its SpMV: SparseArrays' mul! is serial).  Reductions are OpenMP reductions, so the summation
+ * order differs from the serial path (checked to 1e-12 in tests/test_oracle.py). */
+EXPORT void oracle_cg_steps_f64_omp(int64_t n, const int64_t *colptr, const int64_t *rowval,
+                                    const double *nzval, int64_t base, double *x, double *r, double *u,
+                                    double *c, double *residual_io, double *prev_residual_io,
+                                    int64_t iters) {
+  double residual = *residual_io, prev_residual = *prev_residual_io;
+  for (int64_t it = 0; it < iters; ++it) {
+    const double beta = (residual * residual) / (prev_residual * prev_residual);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) u[i] = r[i] + beta * u[i];
+    double uc = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : uc)
+    for (int64_t i = 0; i < n; ++i) {
+      double s = 0.0;
+      for (int64_t k = colptr[i] - base; k < colptr[i + 1] - base; ++k) s += nzval[k] * u[rowval[k] - base];
+      c[i] = s;
+      uc += u[i] * s;
+    }
+    const double alpha = (residual * residual) / uc;
+    double rr = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : rr)
+    for (int64_t i = 0; i < n; ++i) {
+      x[i] += alpha * u[i];
+      const double ri = r[i] - alpha * c[i];
+      r[i] = ri;
+      rr += ri * ri;
+    }
+    prev_residual = residual;
+    residual = sqrt(rr);
+  }
+  *residual_io = residual;
+  *prev_residual_io = prev_residual;
+}
+
 /*
  * laplace_matrix(T, N, dims) as SparseMatrixCSC{T,Int64} (reference test/laplace_matrix.jl:1-12):
  *   A_1 = D = tridiag(-1, 2, -1);  A_d = kron(A_{d-1}, I_N) + kron(I, D)

@@ -378,3 +378,24 @@ def test_bicgstabl_termination(oracle):
     r0 = np.linalg.norm(A @ x - b)
     x, ch = oracle.bicgstabl_(x, A, b, 1, abstol=2 * r0, reltol=0.0, log=True)
     assert ch.niters == 0
+
+
+def test_threaded_bench_variant_equals_serial_steps(oracle):
+    """bench.py's `threaded_variant_not_reference_behaviour` (oracle_cg_steps_f64_omp) performs the same CG
+    steps as the serial restatement; only the summation order of the reductions differs."""
+    import ctypes as C
+    A = oracle.laplace_matrix(np.float64, 14, 3, base=1)
+    n = A.n
+    rng = np.random.default_rng(5)
+    b = rng.standard_normal(n)
+    out = []
+    for fn in ("oracle_cg_steps_f64", "oracle_cg_steps_f64_omp"):
+        x, u, c = np.zeros(n), np.zeros(n), np.zeros(n)
+        r = b.copy()
+        res, prev = C.c_double(float(np.linalg.norm(r))), C.c_double(1.0)
+        getattr(oracle.lib(), fn)(C.c_int64(n), oracle._p(A.colptr), oracle._p(A.rowval), oracle._p(A.nzval),
+                                  C.c_int64(1), oracle._p(x), oracle._p(r), oracle._p(u), oracle._p(c),
+                                  C.byref(res), C.byref(prev), C.c_int64(25))
+        out.append((x, res.value))
+    assert abs(out[0][1] - out[1][1]) <= 1e-12 * out[0][1]
+    assert np.linalg.norm(out[0][0] - out[1][0]) <= 1e-12 * np.linalg.norm(out[0][0])
