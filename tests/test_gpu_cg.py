@@ -310,7 +310,7 @@ def test_cg_512cubed_properties(isb):
     A.mul_(b, xs)
     x = isb.DeviceArray.zeros(ctx, n)
     x, h = isb.cg_(x, A, b, initially_zero=True, log=True, reltol=1e-6)
-    assert h.isconverged and 300 < h.niters < 3000 and h.mvps == h.niters
+    assert h.isconverged and 50 < h.niters < 3000 and h.mvps == h.niters
     r = isb.DeviceArray(ctx, n)
     A.mul_(r, x)
     assert L.b200_axpby(ctx._h, n, 1.0, b._p, -1.0, r._p, 0) == 0          # r = b - A x
