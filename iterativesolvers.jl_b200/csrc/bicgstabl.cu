@@ -125,33 +125,39 @@ __global__ void __launch_bounds__(kThreads) k_bc_update_r(T *__restrict__ rs, co
   }
 }
 
-// upper triangle of rs'rs in one pass
-template <typename T>
+// upper triangle of rs'rs in one pass.  LC = compile-time column count (l + 1 for the common l, LMAX + 1 with
+// zero-padded columns otherwise): the generic 9-column version carried 45 fp64 accumulators at 128 registers and
+// ran at 1.7 TB/s (ncu, profiles/r1_bicgstabl_kernels.ncu-rep); l = 2 needs 6.
+// Output slots keep the static (p,q) numbering over LMAX+1 columns that k_bc_mr_solve reads.
+__host__ __device__ constexpr int pair_slot(int p, int q) { return p * (2 * (LMAX + 1) + 1 - p) / 2 + (q - p); }
+
+template <typename T, int LC>
 __global__ void __launch_bounds__(kThreads) k_bc_gram(const T *__restrict__ rs, int64_t n, int L, double *partials,
                                                       unsigned int *ticket, double *__restrict__ out) {
-  __shared__ double smem[kThreads / 32][NPAIR];
+  constexpr int NPL = LC * (LC + 1) / 2;
+  __shared__ double smem[kThreads / 32][NPL];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int npair = NPAIR;  // static (p,q) indexing over LMAX+1 columns; columns >= L contribute zeros
-  double acc[NPAIR];
+  double acc[NPL];
 #pragma unroll
-  for (int p = 0; p < NPAIR; ++p) acc[p] = 0.0;
+  for (int p = 0; p < NPL; ++p) acc[p] = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    double r[LMAX + 1];
+    double r[LC];
 #pragma unroll
-    for (int c = 0; c <= LMAX; ++c) r[c] = c < L ? (double)rs[i + c * n] : 0.0;
+    for (int c = 0; c < LC; ++c) r[c] = c < L ? (double)rs[i + c * n] : 0.0;
+    int k = 0;
 #pragma unroll
-    for (int p = 0; p <= LMAX; ++p)
+    for (int p = 0; p < LC; ++p)
 #pragma unroll
-      for (int q = p; q <= LMAX; ++q) acc[p * (2 * (LMAX + 1) + 1 - p) / 2 + (q - p)] += r[p] * r[q];
+      for (int q = p; q < LC; ++q, ++k) acc[k] += r[p] * r[q];
   }
 #pragma unroll
-  for (int p = 0; p < npair; ++p) {
+  for (int p = 0; p < NPL; ++p) {
     const double v = warp_sum(acc[p]);
     if (lane == 0) smem[warp][p] = v;
   }
   __syncthreads();
-  if (threadIdx.x < npair) {
+  if (threadIdx.x < NPL) {
     double sacc = 0.0;
     for (int wv = 0; wv < kThreads / 32; ++wv) sacc += smem[wv][threadIdx.x];
     partials[(size_t)blockIdx.x * kMaxReduceWidth + threadIdx.x] = sacc;
@@ -164,36 +170,67 @@ __global__ void __launch_bounds__(kThreads) k_bc_gram(const T *__restrict__ rs, 
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  for (int p = threadIdx.x; p < npair; p += kThreads) {
+  if (threadIdx.x < NPAIR) out[threadIdx.x] = 0.0;      // pairs with a column >= LC
+  __syncthreads();
+  if (threadIdx.x < NPL) {
     double sacc = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) sacc += __ldcg(&partials[(size_t)b * kMaxReduceWidth + p]);
-    out[p] = sacc;
+    for (unsigned int b = 0; b < gridDim.x; ++b)
+      sacc += __ldcg(&partials[(size_t)b * kMaxReduceWidth + threadIdx.x]);
+    int p = 0, k = threadIdx.x;                           // local pair index -> (p, q)
+    while (k >= LC - p) { k -= LC - p; ++p; }
+    out[pair_slot(p, p + k)] = sacc;
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
 // us[:,0] -= us[:,1:L) g ; x += rs[:,0:l) g ; rs[:,0] -= rs[:,1:L) g ; sum rs[:,0]^2   (:126-131)
-template <typename T>
+// LCOL = compile-time l (0: runtime loops).  All 2l + 3 loads of a row are issued before the arithmetic.
+template <typename T, int LCOL>
 __global__ void __launch_bounds__(kThreads) k_bc_mr_update(T *__restrict__ rs, T *__restrict__ us, T *__restrict__ x,
                                                            int64_t n, int l, BcScal *s, double *partials,
                                                            unsigned int *ticket) {
   __shared__ double smem[kThreads / 32];
-  T g[LMAX];
-  for (int c = 0; c < LMAX; ++c) g[c] = c < l ? (T)s->gamma[c] : (T)0;
   double acc = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    T r[LMAX + 1];
-    for (int c = 0; c <= l; ++c) r[c] = rs[i + c * n];
-    T u0 = us[i], xi = x[i], r0 = r[0];
-    for (int c = 0; c < l; ++c) {
-      u0 -= us[i + (c + 1) * n] * g[c];
-      xi += r[c] * g[c];
-      r0 -= r[c + 1] * g[c];
+  if constexpr (LCOL > 0) {
+    T g[LCOL];
+#pragma unroll
+    for (int c = 0; c < LCOL; ++c) g[c] = (T)s->gamma[c];
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+      T r[LCOL + 1], u[LCOL + 1];
+#pragma unroll
+      for (int c = 0; c <= LCOL; ++c) {
+        r[c] = rs[i + c * n];
+        u[c] = us[i + c * n];
+      }
+      T u0 = u[0], xi = x[i], r0 = r[0];
+#pragma unroll
+      for (int c = 0; c < LCOL; ++c) {
+        u0 -= u[c + 1] * g[c];
+        xi += r[c] * g[c];
+        r0 -= r[c + 1] * g[c];
+      }
+      us[i] = u0;
+      x[i] = xi;
+      rs[i] = r0;
+      acc += (double)r0 * (double)r0;
     }
-    us[i] = u0;
-    x[i] = xi;
-    rs[i] = r0;
-    acc += (double)r0 * (double)r0;
+  } else {
+    T g[LMAX];
+    for (int c = 0; c < LMAX; ++c) g[c] = c < l ? (T)s->gamma[c] : (T)0;
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+      T r[LMAX + 1];
+      for (int c = 0; c <= l; ++c) r[c] = rs[i + c * n];
+      T u0 = us[i], xi = x[i], r0 = r[0];
+      for (int c = 0; c < l; ++c) {
+        u0 -= us[i + (c + 1) * n] * g[c];
+        xi += r[c] * g[c];
+        r0 -= r[c + 1] * g[c];
+      }
+      us[i] = u0;
+      x[i] = xi;
+      rs[i] = r0;
+      acc += (double)r0 * (double)r0;
+    }
   }
   acc = block_sum<kThreads>(acc, smem);
   double total;
@@ -290,7 +327,13 @@ int bicgstabl_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b20
     }
     {
       ProfScope prof(ctx, 1);
-      k_bc_gram<T><<<gv, kThreads, 0, st>>>(rs, n, l + 1, ctx->red.partials, ctx->red.ticket, s->gram);  // :120
+      switch (l) {                                                               // rs' rs  :120
+        case 1: k_bc_gram<T, 2><<<gv, kThreads, 0, st>>>(rs, n, 2, ctx->red.partials, ctx->red.ticket, s->gram); break;
+        case 2: k_bc_gram<T, 3><<<gv, kThreads, 0, st>>>(rs, n, 3, ctx->red.partials, ctx->red.ticket, s->gram); break;
+        case 4: k_bc_gram<T, 5><<<gv, kThreads, 0, st>>>(rs, n, 5, ctx->red.partials, ctx->red.ticket, s->gram); break;
+        default:
+          k_bc_gram<T, LMAX + 1><<<gv, kThreads, 0, st>>>(rs, n, l + 1, ctx->red.partials, ctx->red.ticket, s->gram);
+      }
     }
     B200_LAUNCH_CHECK(ctx);
     B200_TRY(allreduce_sum_dev(ctx, s->gram, NPAIR));
@@ -298,7 +341,12 @@ int bicgstabl_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b20
     B200_LAUNCH_CHECK(ctx);
     {
       ProfScope prof(ctx, 1);
-      k_bc_mr_update<T><<<gv, kThreads, 0, st>>>(rs, us, x, n, l, s, ctx->red.partials, ctx->red.ticket);  // :126-131
+      switch (l) {                                                               // :126-131
+        case 1: k_bc_mr_update<T, 1><<<gv, kThreads, 0, st>>>(rs, us, x, n, l, s, ctx->red.partials, ctx->red.ticket); break;
+        case 2: k_bc_mr_update<T, 2><<<gv, kThreads, 0, st>>>(rs, us, x, n, l, s, ctx->red.partials, ctx->red.ticket); break;
+        case 4: k_bc_mr_update<T, 4><<<gv, kThreads, 0, st>>>(rs, us, x, n, l, s, ctx->red.partials, ctx->red.ticket); break;
+        default: k_bc_mr_update<T, 0><<<gv, kThreads, 0, st>>>(rs, us, x, n, l, s, ctx->red.partials, ctx->red.ticket);
+      }
     }
     B200_LAUNCH_CHECK(ctx);
     B200_TRY(scalar(BC_END));
