@@ -198,3 +198,40 @@ def test_halo_plan_and_partitioned_cg_world2_gloo(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o[-3000:]}"
         assert f"rank {r} ok" in o
+
+
+def test_julia_binding_source_uses_only_declared_symbols_and_matching_structs():
+    """integration/B200Krylov.jl (the reference-side binding; Julia is absent here, so the file is source only):
+    every ccall names a symbol the header declares, and its struct definitions list the header's fields in
+    order (names as in the ctypes mirror, which test_signature_table_matches_header pins to the header)."""
+    import re
+    src = open(os.path.join(ROOT, "integration", "B200Krylov.jl")).read()
+    hdr = open(os.path.join(ROOT, "include", "b200krylov.h")).read()
+    declared = set(re.findall(r"B200_API\s+[\w\s\*]+?\b(b200_\w+)\s*\(", hdr))
+    used = set(re.findall(r"\(:(b200_\w+),\s*LIB\)", src))
+    assert used and used <= declared, sorted(used - declared)
+    from importlib import import_module
+    L = import_module("iterativesolvers_jl_b200")._lib
+
+    def julia_fields(name):
+        body = re.search(r"struct\s+" + name + r"\b(.*?)\n\s*end", src, re.S).group(1)
+        body = re.sub(r"#.*", "", body)
+        return [f for f in re.findall(r"\b(\w+)::", body)]
+
+    for jl, ct in (("Precond", L.Precond), ("Result", L.Result), ("CgOpts", L.CgOpts), ("GmresOpts", L.GmresOpts),
+                   ("MinresOpts", L.MinresOpts), ("BicgstablOpts", L.BicgstablOpts), ("LobpcgOpts", L.LobpcgOpts),
+                   ("LobpcgResult", L.LobpcgResult)):
+        assert julia_fields(jl) == [f[0] for f in ct._fields_], jl
+
+
+def test_committed_ncu_traffic_matches_the_algorithmic_bytes():
+    """profiles/k2_traffic.json (echoed by bench.py as roofline.traffic) is the DRAM traffic of one launch of the
+    dominant kernel from an `ncu --set full` capture; it must be within 2 % of SURVEY 8(d)'s SpMV bytes."""
+    import json
+    t = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))
+    N = t["grid"]
+    n, nnz = N ** 3, 7 * N ** 3 - 6 * N ** 2
+    algorithmic = nnz * 12 + (n + 1) * 4 + 2 * n * 8
+    assert t["dram_bytes_per_launch"] == t["dram_bytes_read"] + t["dram_bytes_write"]
+    assert abs(t["dram_bytes_per_launch"] - algorithmic) <= 0.02 * algorithmic
+    assert os.path.exists(os.path.join(ROOT, t["source"].split(" ")[0]))
