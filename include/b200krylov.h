@@ -145,6 +145,11 @@ B200_API int b200_csr_destroy(b200_csr *A);
 /* size(A,1) local, size(A,2) global, nnz local, eltype */
 B200_API int b200_csr_info(const b200_csr *A, int64_t *m_local, int64_t *n_global, int64_t *nnz_local, int *dtype,
                            int64_t *row_begin, int64_t *n_halo);
+/* adjoint(A) as an operator (reference: `adjoint(A)` stored by LanczosDecomp src/qmr.jl:54 and used by
+ * mul!(y, A', x) at src/qmr.jl:76, src/lsqr.jl:128,152, src/lsmr.jl:116,175).  Built on the device from the CSR of A
+ * (real element types: adjoint == transpose).  Single-GPU contexts; on multi-GPU contexts pass the row slabs of A'
+ * to b200_csr_from_csr_slab. */
+B200_API int b200_csr_transpose(b200_ctx *ctx, const b200_csr *A, b200_csr **out);
 /* diag(A) of the local rows into a device vector (JacobiPrec(diag(A)), reference test/cg.jl:57) */
 B200_API int b200_csr_diag(b200_ctx *ctx, const b200_csr *A, void *diag_dev);
 /* device CSR arrays back to the host (tests) */
@@ -259,6 +264,20 @@ B200_API int b200_cg_iter_destroy(b200_cg_iter *it);
 B200_API int b200_chebyshev_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
                                   double lambda_min, double lambda_max, const b200_cg_opts *opts, b200_result *res,
                                   double *resnorm_host, int64_t resnorm_cap);
+
+typedef struct {
+  double abstol;            /* zero(real(eltype(b)))       src/qmr.jl:266                           */
+  double reltol;            /* sqrt(eps(real(eltype(b))))  src/qmr.jl:267 -- pass <0 for that default */
+  int64_t maxiter;          /* size(A, 2)                  src/qmr.jl:268 -- pass <0 for the default  */
+  int32_t initially_zero;   /* src/qmr.jl:271                                                        */
+  int32_t check_every;      /* iterations enqueued between host polls of the device-side done flag (<=0: 16) */
+} b200_qmr_opts;
+/* qmr!(x, A, b; abstol, reltol, maxiter, initially_zero)  reference src/qmr.jl:262-297.
+ * At = adjoint(A) (b200_csr_transpose, or the adjoint's own row slabs on multi-GPU contexts).  res->mvps counts the
+ * products with A and A' together; res->status = B200_ERR_BREAKDOWN after an exact Lanczos breakdown (delta == 0,
+ * src/qmr.jl:84-86; see DESIGN.md for the one documented deviation there). */
+B200_API int b200_qmr_solve(b200_ctx *ctx, const b200_csr *A, const b200_csr *At, void *x_dev, const void *b_dev,
+                            const b200_qmr_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);
 
 typedef struct {
   double abstol, reltol;    /* src/gmres.jl:187-188                                                */

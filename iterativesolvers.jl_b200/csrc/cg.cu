@@ -642,6 +642,8 @@ int cg_iter_next_impl(CgIterState<T> *it, int64_t k, b200_result *res, double *r
 int check_cg_args(b200_ctx *ctx, const b200_csr *A, const void *x, const void *b, const b200_cg_opts *o) {
   B200_REQUIRE(ctx && A && x && b && o, "NULL argument");
   B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
+  B200_REQUIRE(is_square(A), "this solver needs a square operator (got %lld x %lld)", (long long)A->m_global,
+               (long long)A->n_global);
   B200_REQUIRE(o->Pl.kind == B200_PREC_IDENTITY || (o->Pl.kind == B200_PREC_JACOBI && o->Pl.diag),
                "unsupported preconditioner");
   return B200_OK;

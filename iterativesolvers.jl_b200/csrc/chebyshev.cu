@@ -223,6 +223,8 @@ int b200_chebyshev_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const vo
                          int64_t resnorm_cap) {
   B200_REQUIRE(ctx && A && x_dev && b_dev && opts, "NULL argument");
   B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
+  B200_REQUIRE(is_square(A), "this solver needs a square operator (got %lld x %lld)", (long long)A->m_global,
+               (long long)A->n_global);
   B200_REQUIRE(opts->Pl.kind == B200_PREC_IDENTITY || (opts->Pl.kind == B200_PREC_JACOBI && opts->Pl.diag),
                "unsupported preconditioner");
   B200_CUDA(cudaSetDevice(ctx->device));

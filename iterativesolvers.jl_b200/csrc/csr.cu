@@ -437,9 +437,10 @@ int check_dist_args(b200_ctx *ctx, int64_t n_global, int64_t row_begin, int64_t 
 // ------------------------------------------------------------------------------------------
 template <typename I, typename TI, typename T>
 static int csr_from_csc_impl(b200_ctx *ctx, int64_t m, int64_t n, const I *colptr, const I *rowval, const TI *nzval,
-                             int base, b200_csr *A) {
+                             int base, int64_t nnz, cudaMemcpyKind src_kind, b200_csr *A) {
+  // colptr/rowval/nzval: host arrays (src_kind = cudaMemcpyHostToDevice; nnz = colptr[n] - base read by the caller)
+  // or device arrays (cudaMemcpyDeviceToDevice: b200_csr_transpose feeds the CSR arrays of A as the CSC of A')
   cudaStream_t st = ctx->stream;
-  const int64_t nnz = (int64_t)colptr[n] - base;
   B200_REQUIRE(nnz >= 0 && nnz < (int64_t)INT32_MAX, "nnz=%lld does not fit int32 CSR", (long long)nnz);
   A->nnz = nnz;
   I *d_colptr = nullptr, *d_rowval = nullptr;
@@ -467,9 +468,9 @@ static int csr_from_csc_impl(b200_ctx *ctx, int64_t m, int64_t n, const I *colpt
   CK(cudaMalloc(&d_nz, sizeof(TI) * (nnz ? nnz : 1)));
   CK(cudaMalloc(&d_err, sizeof(int)));
   CK(cudaMemsetAsync(d_err, 0, sizeof(int), st));
-  CK(cudaMemcpyAsync(d_colptr, colptr, sizeof(I) * (n + 1), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_rowval, rowval, sizeof(I) * nnz, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d_nz, nzval, sizeof(TI) * nnz, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_colptr, colptr, sizeof(I) * (n + 1), src_kind, st));
+  CK(cudaMemcpyAsync(d_rowval, rowval, sizeof(I) * nnz, src_kind, st));
+  CK(cudaMemcpyAsync(d_nz, nzval, sizeof(TI) * nnz, src_kind, st));
   CK(cudaMalloc(&A->rowptr, sizeof(int) * (m + kRowptrPad)));
   CK(cudaMalloc(&A->colind, sizeof(int) * (nnz + kNnzPad)));
   CK(cudaMalloc(&A->vals, sizeof(T) * (nnz + kNnzPad)));
@@ -522,20 +523,23 @@ int b200_csr_from_csc(b200_ctx *ctx, int64_t m, int64_t n, const void *colptr, c
   B200_REQUIRE(dtype == B200_F64 || dtype == B200_F32, "bad dtype");
   B200_REQUIRE(ctx->world == 1, "b200_csr_from_csc is single-GPU; use b200_csr_from_csr_slab on multi-GPU contexts");
   B200_REQUIRE(m >= 0 && n >= 0 && m < INT32_MAX && n < INT32_MAX, "dimensions must fit int32");
-  B200_REQUIRE(m == n, "the Krylov solvers need a square operator");
+  // rectangular operators are accepted (lsqr!/lsmr!); the square-system solvers check is_square(A) themselves
   B200_CUDA(cudaSetDevice(ctx->device));
   auto *A = new b200_csr();
   A->ctx = ctx;
   A->dtype = dtype;
   A->m_local = m;
+  A->m_global = m;
   A->n_global = n;
+  const int64_t nnz = (idx_bytes == 8 ? (int64_t)((const int64_t *)colptr)[n] : (int64_t)((const int32_t *)colptr)[n]) - base;
+  const cudaMemcpyKind h2d = cudaMemcpyHostToDevice;
   int s;
   if (idx_bytes == 8) {
-    s = dtype == B200_F64 ? csr_from_csc_impl<int64_t, double, double>(ctx, m, n, (const int64_t *)colptr, (const int64_t *)rowval, (const double *)nzval, base, A)
-                          : csr_from_csc_impl<int64_t, float, float>(ctx, m, n, (const int64_t *)colptr, (const int64_t *)rowval, (const float *)nzval, base, A);
+    s = dtype == B200_F64 ? csr_from_csc_impl<int64_t, double, double>(ctx, m, n, (const int64_t *)colptr, (const int64_t *)rowval, (const double *)nzval, base, nnz, h2d, A)
+                          : csr_from_csc_impl<int64_t, float, float>(ctx, m, n, (const int64_t *)colptr, (const int64_t *)rowval, (const float *)nzval, base, nnz, h2d, A);
   } else {
-    s = dtype == B200_F64 ? csr_from_csc_impl<int32_t, double, double>(ctx, m, n, (const int32_t *)colptr, (const int32_t *)rowval, (const double *)nzval, base, A)
-                          : csr_from_csc_impl<int32_t, float, float>(ctx, m, n, (const int32_t *)colptr, (const int32_t *)rowval, (const float *)nzval, base, A);
+    s = dtype == B200_F64 ? csr_from_csc_impl<int32_t, double, double>(ctx, m, n, (const int32_t *)colptr, (const int32_t *)rowval, (const double *)nzval, base, nnz, h2d, A)
+                          : csr_from_csc_impl<int32_t, float, float>(ctx, m, n, (const int32_t *)colptr, (const int32_t *)rowval, (const float *)nzval, base, nnz, h2d, A);
   }
   if (s == B200_OK) s = finish_operator(ctx, A, nullptr);
   if (s != B200_OK) {
@@ -543,6 +547,36 @@ int b200_csr_from_csc(b200_ctx *ctx, int64_t m, int64_t n, const void *colptr, c
     return s;
   }
   *out = A;
+  return B200_OK;
+}
+
+/* adjoint(A) as an operator of its own (reference: LanczosDecomp stores `adjoint(A)`, src/qmr.jl:54; lsqr src/lsqr.jl:120,
+ * lsmr src/lsmr.jl:116): the device CSR arrays of A are the CSC arrays of A', so the CSC->CSR conversion above builds
+ * the CSR of A' without leaving the GPU.  Real element types: adjoint == transpose. */
+int b200_csr_transpose(b200_ctx *ctx, const b200_csr *A, b200_csr **out) {
+  B200_REQUIRE(ctx && A && out, "NULL argument");
+  B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
+  B200_REQUIRE(ctx->world == 1, "b200_csr_transpose is single-GPU; on multi-GPU contexts build the adjoint from its own "
+                                "row slabs with b200_csr_from_csr_slab");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  auto *At = new b200_csr();
+  At->ctx = ctx;
+  At->dtype = A->dtype;
+  At->m_local = A->n_global;
+  At->m_global = A->n_global;
+  At->n_global = A->m_local;
+  const cudaMemcpyKind d2d = cudaMemcpyDeviceToDevice;
+  int s = A->dtype == B200_F64
+              ? csr_from_csc_impl<int32_t, double, double>(ctx, At->m_local, At->n_global, A->rowptr, A->colind,
+                                                           (const double *)A->vals, 0, A->nnz, d2d, At)
+              : csr_from_csc_impl<int32_t, float, float>(ctx, At->m_local, At->n_global, A->rowptr, A->colind,
+                                                         (const float *)A->vals, 0, A->nnz, d2d, At);
+  if (s == B200_OK) s = finish_operator(ctx, At, nullptr);
+  if (s != B200_OK) {
+    b200_csr_destroy(At);
+    return s;
+  }
+  *out = At;
   return B200_OK;
 }
 
@@ -561,6 +595,7 @@ int b200_csr_from_csr_slab(b200_ctx *ctx, int64_t n_global, int64_t row_begin, i
   A->ctx = ctx;
   A->dtype = dtype;
   A->m_local = m_local;
+  A->m_global = n_global;   // row-partitioned operators are square
   A->n_global = n_global;
   A->row_begin = row_begin;
   A->nnz = nnz;
@@ -645,6 +680,7 @@ int b200_csr_laplacian(b200_ctx *ctx, int64_t N, int dims, int dtype, int64_t ro
   A->ctx = ctx;
   A->dtype = dtype;
   A->m_local = m_local;
+  A->m_global = n;
   A->n_global = n;
   A->row_begin = row_begin;
   A->n_halo = plan ? (int64_t)plan->halo_sorted.size() : 0;

@@ -26,6 +26,7 @@ struct b200_csr {
   int stream_lpr = 0;      // lanes per row of the TMA-streamed kernel; 0 = tiles do not fit, use the sub-warp kernel
   int dtype = B200_F64;
   int64_t m_local = 0, n_global = 0, row_begin = 0, nnz = 0, n_halo = 0;
+  int64_t m_global = 0;    // size(A,1); != n_global only for single-GPU rectangular operators (lsqr!/lsmr!)
   int *rowptr = nullptr;   // m_local+1
   int *colind = nullptr;   // nnz; local extended index: [0,m_local) own, [m_local,m_local+n_halo) halo
   void *vals = nullptr;    // nnz
@@ -50,6 +51,7 @@ int halo_exchange(b200_ctx *ctx, const b200_csr *A, const void *x_dev);
 // peer-memory variant: stores x[send_idx] into the neighbours' halo segments and raises halo flag `seq`
 // (skipped on the device when *done_flag != 0); consumers wait with peer_wait_halo(.., A->recv_mask, seq)
 int halo_push(b200_ctx *ctx, const b200_csr *A, const void *x_dev, unsigned long long seq, const int *done_flag);
+inline bool is_square(const b200_csr *A) { return A->m_global == A->n_global; }
 inline bool use_peer(const b200_ctx *ctx, const b200_csr *A) {
   return ctx->world > 1 && ctx->peer_ok && A->peer_halo && ctx->opt_comm != 1;
 }

@@ -543,6 +543,8 @@ int b200_gmres_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *
                      b200_result *res, double *resnorm_host, int64_t resnorm_cap) {
   B200_REQUIRE(ctx && A && x_dev && b_dev && opts, "NULL argument");
   B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
+  B200_REQUIRE(is_square(A), "this solver needs a square operator (got %lld x %lld)", (long long)A->m_global,
+               (long long)A->n_global);
   B200_CUDA(cudaSetDevice(ctx->device));
   return A->dtype == B200_F64
              ? gmres_impl<double>(ctx, A, (double *)x_dev, (const double *)b_dev, opts, res, resnorm_host, resnorm_cap)

@@ -1307,6 +1307,8 @@ int b200_lobpcg_solve(b200_ctx *ctx, const b200_csr *A, void *X_dev, int64_t ldx
                       b200_lobpcg_result *res, double *lambda_host, double *resnorm_host) {
   B200_REQUIRE(ctx && A && X_dev && opts, "NULL argument");
   B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
+  B200_REQUIRE(is_square(A), "this solver needs a square operator (got %lld x %lld)", (long long)A->m_global,
+               (long long)A->n_global);
   B200_CUDA(cudaSetDevice(ctx->device));
   return A->dtype == B200_F64 ? lobpcg_impl<double>(ctx, A, (double *)X_dev, ldx, opts, res, lambda_host, resnorm_host)
                               : lobpcg_impl<float>(ctx, A, (float *)X_dev, ldx, opts, res, lambda_host, resnorm_host);

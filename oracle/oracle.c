@@ -49,6 +49,32 @@ EXPORT void oracle_csc_spmv_f32(int64_t n_rows, int64_t n_cols, const int64_t *c
   }
 }
 
+/* ---- SparseArrays mul!(y, adjoint(A)::Adjoint{SparseMatrixCSC}, x): one gather dot per column,
+ *      y[col] = sum_k conj(nzval[k]) * x[rowval[k]]   (real eltypes: adjoint == transpose).
+ *      Call sites in the reference: src/qmr.jl:76, src/lsqr.jl:128,152, src/lsmr.jl:116,175. ---- */
+EXPORT void oracle_csc_spmv_adj_f64(int64_t n_rows, int64_t n_cols, const int64_t *colptr,
+                                    const int64_t *rowval, const double *nzval, int64_t base,
+                                    const double *x, double *y) {
+  (void)n_rows;
+  for (int64_t col = 0; col < n_cols; ++col) {
+    double t = 0.0;
+    for (int64_t k = colptr[col] - base; k < colptr[col + 1] - base; ++k)
+      t += nzval[k] * x[rowval[k] - base];
+    y[col] = t;
+  }
+}
+EXPORT void oracle_csc_spmv_adj_f32(int64_t n_rows, int64_t n_cols, const int64_t *colptr,
+                                    const int64_t *rowval, const float *nzval, int64_t base,
+                                    const float *x, float *y) {
+  (void)n_rows;
+  for (int64_t col = 0; col < n_cols; ++col) {
+    float t = 0.0f;
+    for (int64_t k = colptr[col] - base; k < colptr[col + 1] - base; ++k)
+      t += nzval[k] * x[rowval[k] - base];
+    y[col] = t;
+  }
+}
+
 /* SparseArrays mul!(Y, A, X) on n x bs column-major blocks: the stdlib loops the block column
  * outermost, i.e. re-streams A once per column. */
 EXPORT void oracle_csc_spmm_f32(int64_t n_rows, int64_t n_cols, const int64_t *colptr,

@@ -106,6 +106,18 @@ def csc_spmv(A: CSC, x: np.ndarray, y: np.ndarray | None = None) -> np.ndarray:
     return y
 
 
+def csc_spmv_adjoint(A: CSC, x: np.ndarray, y: np.ndarray | None = None) -> np.ndarray:
+    """mul!(y, adjoint(A), x) for A::SparseMatrixCSC -- SparseArrays stdlib, one gather dot per column
+    (call sites: reference src/qmr.jl:76, src/lsqr.jl:128,152, src/lsmr.jl:116,175)."""
+    x = np.ascontiguousarray(x, dtype=A.dtype)
+    if y is None:
+        y = np.empty(A.n, dtype=A.dtype)
+    fn = lib().oracle_csc_spmv_adj_f64 if A.dtype == np.float64 else lib().oracle_csc_spmv_adj_f32
+    fn(ctypes.c_int64(A.m), ctypes.c_int64(A.n), _p(A.colptr), _p(A.rowval), _p(A.nzval),
+       ctypes.c_int64(A.base), _p(x), _p(y))
+    return y
+
+
 def csc_spmm(A: CSC, X: np.ndarray, Y: np.ndarray | None = None) -> np.ndarray:
     """mul!(Y, A, X) on column-major n x bs blocks (Fortran-ordered numpy arrays)."""
     X = np.asfortranarray(X, dtype=A.dtype)
@@ -126,6 +138,13 @@ def mul(A, x):
     if callable(A):
         return A(x)
     return A @ x
+
+
+def mul_adjoint(A, x):
+    """adjoint(A)*x for SparseMatrixCSC and dense Matrix operators."""
+    if isinstance(A, CSC):
+        return csc_spmv_adjoint(A, x)
+    return A.conj().T @ x
 
 
 def opsize(A, d=None):
@@ -982,3 +1001,527 @@ def lobpcg(A, largest, X0, *, B=None, P=None, tol=None, maxiter=200, log=False, 
         iteration += 1                                                  # :886
     lam = ritz[:sizeX].copy()
     return LOBPCGResults(lam, X, tol, residuals.copy(), iteration, maxiter, bool(np.all(residuals <= tol)), trace)
+
+
+# ============================================================================================
+# the solvers that need A' (QMR, LSQR, LSMR) and IDR(s)
+# ============================================================================================
+# --------------------------------------------------------------------------------------------
+# QMR (reference src/qmr.jl)
+# --------------------------------------------------------------------------------------------
+def qmr_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, log=False, initially_zero=False):
+    """qmr!(x, A, b; ...) -- reference src/qmr.jl:262-297; LanczosDecomp constructor :24-60 and
+    iterate :63-100; qmr_iterable! :119-151; QMRIterable iterate :157-215.  Restated literally,
+    including the early return of the Lanczos step at delta == 0 (:84-86) BEFORE the vector rotation."""
+    T = x.dtype
+    if reltol is None:
+        reltol = math.sqrt(_eps(_real_dtype(b.dtype)))                   # :267
+    if maxiter is None:
+        maxiter = opsize(A, 1)                                          # :268
+    history = ConvergenceHistory()
+    history["abstol"], history["reltol"] = abstol, reltol
+    resnorms = []
+    # LanczosDecomp(x, A, b) :24-60
+    v_prev = np.zeros_like(x)                                           # :32
+    v_curr = b.astype(T, copy=True)                                     # :33
+    v_next = np.empty_like(x)                                           # :34
+    if not initially_zero:                                              # :35-39
+        v_next[...] = mul(A, x)
+        v_curr -= v_next
+    resnorm = float(np.linalg.norm(v_curr))                             # :40
+    with np.errstate(divide="ignore", invalid="ignore"):
+        v_curr *= T.type(1.0) / T.type(resnorm)                         # :41
+    w_prev = np.zeros_like(x)                                           # :43
+    w_curr = v_curr.copy()                                              # :44
+    w_next = np.empty_like(x)                                           # :45
+    alpha = beta_prev = beta_curr = delta = T.type(0)                   # :47-50
+    # qmr_iterable! :119-151
+    g = np.array([resnorm, 0], dtype=T)                                 # :131
+    H = np.zeros(4, dtype=T)                                            # :132
+    c_prev, s_prev, c_curr, s_curr = T.type(1), T.type(0), T.type(1), T.type(0)   # :135-136
+    p_prev = np.zeros_like(x)                                           # :139
+    p_curr = np.zeros_like(x)                                           # :140
+    tol = max(reltol * resnorm, abstol)                                 # :142
+    iteration = 1                                                       # start :154
+    while True:
+        if iteration > maxiter or resnorm <= tol:                       # done :155
+            break
+        # iterate(::LanczosDecomp, iteration) :63-100
+        v_next[...] = mul(A, v_curr)                                    # :68
+        alpha = np.vdot(v_next, w_curr)                                 # dot(v_next, w_curr) :70 (conj on the 1st)
+        v_next -= np.conj(alpha) * v_curr                               # :71
+        if iteration > 1:
+            v_next -= np.conj(beta_curr) * v_prev                       # :72-74
+        w_next[...] = mul_adjoint(A, w_curr)                            # :76
+        w_next -= alpha * w_curr                                        # :77
+        if iteration > 1:
+            w_next -= delta * w_prev                                    # :78-80
+        vw = np.vdot(v_next, w_next)                                    # :82
+        delta = math.sqrt(abs(vw))                                      # :83
+        if delta != 0:                                                  # :84-86 (early return otherwise)
+            beta_prev = beta_curr                                       # :88
+            beta_curr = vw / delta                                      # :89
+            v_next *= T.type(1.0) / T.type(delta)                       # :91
+            w_next *= T.type(1.0) / beta_curr                           # :92
+            w_next, w_curr, w_prev = w_prev, w_next, w_curr             # :94
+            v_next, v_curr, v_prev = v_prev, v_next, v_curr             # :95
+        # QMRIterable iterate :165-212
+        H[1] = np.conj(beta_prev)                                       # :168
+        H[2] = np.conj(alpha)                                           # :169
+        H[3] = delta                                                    # :170
+        if iteration > 2:                                               # :173-176
+            H[0] = s_prev * H[1]
+            H[1] = c_prev * H[1]
+        if iteration > 1:                                               # :179-183
+            tmp = -np.conj(s_curr) * H[1] + c_curr * H[2]
+            H[1] = c_curr * H[1] + s_curr * H[2]
+            H[2] = tmp
+        c, s, H[2] = givens_algorithm(H[2], H[3])                       # :187
+        g[1] = -np.conj(s) * g[0]                                       # :190
+        g[0] = c * g[0]                                                 # :191
+        v_next[...] = v_prev                                            # :196
+        if iteration > 1:
+            v_next -= H[1] * p_curr                                     # :197
+        if iteration > 2:
+            v_next -= H[0] * p_prev                                     # :198
+        with np.errstate(divide="ignore", invalid="ignore"):
+            v_next *= T.type(1.0) / H[2]                                # :199
+        x += g[0] * v_next                                              # :202
+        c_prev, s_prev, c_curr, s_curr = c_curr, s_curr, c, s           # :205
+        p_prev[...] = p_curr                                            # :206
+        p_curr[...] = v_next                                            # :207
+        g[0] = g[1]                                                     # :208
+        resnorm = float(abs(g[1]))                                      # :212
+        iteration += 1
+        if log:
+            history.iters += 1                                          # nextiter!(history) :285 (mvps not counted)
+            resnorms.append(resnorm)
+    if log:
+        history.isconverged = resnorm <= tol                            # :293
+        history["resnorm"] = np.array(resnorms)
+        history["tol"] = tol
+        return x, history
+    return x
+
+
+def qmr(A, b, **kw):
+    """qmr(A, b; kwargs...) = qmr!(zerox(A, b), A, b; initially_zero = true, kwargs...) -- src/qmr.jl:222."""
+    x = np.zeros(opsize(A, 1), dtype=b.dtype)
+    return qmr_(x, A, b, initially_zero=True, **kw)
+
+
+# --------------------------------------------------------------------------------------------
+# LSQR (reference src/lsqr.jl)
+# --------------------------------------------------------------------------------------------
+def lsqr_(x, A, b, *, damp=0.0, atol=None, btol=None, conlim=None, maxiter=None, log=False):
+    """lsqr!(x, A, b; ...) -- reference src/lsqr.jl:66-77 and lsqr_method! :90-275, restated literally
+    (including `ddnorm += norm(wrho)` :206 and isconverged = istop > 0 :271, which is true for istop = 7)."""
+    T = np.result_type(x.dtype, b.dtype).type                           # Adivtype(A, b) :108
+    Tr = _real_dtype(np.dtype(T)).type
+    m, n = opsize(A, 0), opsize(A, 1)
+    eps = _eps(np.dtype(Tr))
+    if atol is None:
+        atol = math.sqrt(eps)                                           # :91
+    if btol is None:
+        btol = math.sqrt(eps)
+    if conlim is None:
+        conlim = 1.0 / math.sqrt(eps)                                   # :92
+    if maxiter is None:
+        maxiter = max(m, n)                                             # :67
+    history = ConvergenceHistory()
+    hist = {"resnorm": [], "anorm": [], "rnorm": [], "cnorm": []}
+    if len(x) != n:
+        raise ValueError(f"x should be of length {n}")                  # :99
+    if len(b) != m:
+        raise ValueError(f"b should be of length {m}")                  # :100
+    if not np.all(np.isfinite(x)):
+        raise ValueError("Initial guess for x must be finite")          # :102-104
+    itn = istop = 0                                                     # :110
+    ctol = Tr(1 / conlim) if conlim > 0 else Tr(0)                      # :111
+    Anorm = Acond = ddnorm = res2 = xnorm = xxnorm = z = sn2 = Tr(0)    # :112
+    cs2 = Tr(-1)                                                        # :113
+    damp = Tr(damp)
+    dampsq = damp * damp                                                # :114
+    history["atol"], history["btol"], history["ctol"] = atol, btol, ctol
+
+    def finish():
+        for k, v_ in hist.items():
+            history[k] = np.array(v_, dtype=np.float64)
+        return (x, history) if log else x
+
+    u = (b - mul(A, x)).astype(T)                                       # :124
+    v = x.astype(T, copy=True)                                          # :125
+    beta = Tr(np.linalg.norm(u))                                        # :126
+    alpha = Tr(0)                                                       # :127
+    if beta > 0:                                                        # :129-134
+        history.mtvps = 1
+        u *= Tr(1) / beta
+        v[...] = mul_adjoint(A, u)
+        alpha = Tr(np.linalg.norm(v))
+    if alpha > 0:                                                       # :135-137
+        v *= Tr(1) / alpha
+    w = v.copy()                                                        # :138
+    Arnorm = alpha * beta                                               # :141
+    if Arnorm == 0:                                                     # :142-144
+        return finish()
+    rhobar = alpha                                                      # :146
+    phibar = bnorm = rnorm = beta                                       # :147
+    while itn < maxiter and not history.isconverged:                    # :152
+        history.iters += 1                                              # nextiter!(log, mvps=1) :153
+        history.mvps += 1
+        itn += 1                                                        # :154
+        tmpm = mul(A, v)                                                # :163
+        u[...] = -alpha * u + tmpm                                      # :164
+        beta = Tr(np.linalg.norm(u))                                    # :165
+        if beta > 0:                                                    # :166-178
+            history.mtvps += 1
+            u *= Tr(1) / beta
+            Anorm = Tr(math.sqrt(Anorm * Anorm + alpha * alpha + beta * beta + dampsq))   # :169
+            tmpn = mul_adjoint(A, u)                                    # :172
+            v[...] = -beta * v + tmpn                                   # :173
+            alpha = Tr(np.linalg.norm(v))                               # :174
+            if alpha > 0:
+                v *= Tr(1) / alpha                                      # :176
+        rhobar1 = Tr(math.sqrt(rhobar * rhobar + dampsq))               # :182
+        cs1 = rhobar / rhobar1                                          # :183
+        sn1 = damp / rhobar1                                            # :184
+        psi = sn1 * phibar                                              # :185
+        phibar = cs1 * phibar                                           # :186
+        rho = Tr(math.sqrt(rhobar1 * rhobar1 + beta * beta))            # :190
+        cs = rhobar1 / rho                                              # :191
+        sn = beta / rho                                                 # :192
+        theta = sn * alpha                                              # :193
+        rhobar = -cs * alpha                                            # :194
+        phi = cs * phibar                                               # :195
+        phibar = sn * phibar                                            # :196
+        tau = sn * phi                                                  # :197
+        t1 = phi / rho                                                  # :200
+        t2 = -theta / rho                                               # :201
+        x += T(t1) * w                                                  # :203
+        w = T(t2) * w + v                                               # :204
+        wrho = w * (Tr(1) / rho)                                        # :205
+        ddnorm = ddnorm + Tr(np.linalg.norm(wrho))                      # :206
+        delta = sn2 * rho                                               # :211
+        gambar = -cs2 * rho                                             # :212
+        rhs = phi - delta * z                                           # :213
+        zbar = rhs / gambar                                             # :214
+        xnorm = Tr(math.sqrt(xxnorm + zbar * zbar))                     # :215
+        gamma = Tr(math.sqrt(gambar * gambar + theta * theta))          # :216
+        cs2 = gambar / gamma                                            # :217
+        sn2 = theta / gamma                                             # :218
+        z = rhs / gamma                                                 # :219
+        xxnorm = xxnorm + z * z                                         # :220
+        Acond = Anorm * Tr(math.sqrt(ddnorm))                           # :225
+        res1 = phibar * phibar                                          # :226
+        res2 = res2 + psi * psi                                         # :227
+        rnorm = Tr(math.sqrt(res1 + res2))                              # :228
+        Arnorm = alpha * abs(tau)                                       # :229
+        r1sq = rnorm * rnorm - dampsq * xxnorm                          # :239
+        r1norm = Tr(math.sqrt(abs(r1sq)))                               # :240
+        if r1sq < 0:
+            r1norm = -r1norm
+        hist["resnorm"].append(float(r1norm))                           # :242
+        with np.errstate(divide="ignore", invalid="ignore"):
+            test1 = rnorm / bnorm                                       # :246
+            test2 = Arnorm / (Anorm * rnorm)                            # :247
+            test3 = Tr(1) / Acond                                       # :248
+            t1 = test1 / (1 + Anorm * xnorm / bnorm)                    # :249
+            rtol = btol + atol * Anorm * xnorm / bnorm                  # :250
+        hist["cnorm"].append(float(test3))                              # :251
+        hist["anorm"].append(float(test2))                              # :252
+        hist["rnorm"].append(float(test1))                              # :253
+        if itn >= maxiter:
+            istop = 7                                                   # :261
+        if Tr(1) + test3 <= 1:
+            istop = 6                                                   # :262
+        if Tr(1) + test2 <= 1:
+            istop = 5                                                   # :263
+        if Tr(1) + t1 <= 1:
+            istop = 4                                                   # :264
+        if test3 <= ctol:
+            istop = 3                                                   # :267
+        if test2 <= atol:
+            istop = 2                                                   # :268
+        if test1 <= rtol:
+            istop = 1                                                   # :269
+        history.isconverged = istop > 0                                 # :271
+    history["istop"] = istop
+    return finish()
+
+
+def lsqr(A, b, **kw):
+    """lsqr(A, b; kwargs...) = lsqr!(zerox(A, b), A, b; kwargs...) -- src/lsqr.jl:8."""
+    x = np.zeros(opsize(A, 1), dtype=b.dtype)
+    return lsqr_(x, A, b, **kw)
+
+
+# --------------------------------------------------------------------------------------------
+# LSMR (reference src/lsmr.jl)
+# --------------------------------------------------------------------------------------------
+def lsmr_(x, A, b, *, atol=1e-6, btol=1e-6, conlim=1e8, maxiter=None, lam=0.0, log=False):
+    """lsmr!(x, A, b; atol, btol, conlim, maxiter, λ) -- reference src/lsmr.jl:67-82 and lsmr_method! :88-287,
+    restated literally (first-match stopping tests with `break` :274-281, isconverged = istop ∉ (3, 6, 7) :285,
+    minrbar = 1e100 :150, unguarded divisions by the norms :116, :120, :175)."""
+    T = np.result_type(x.dtype, b.dtype).type                           # Adivtype(A, b) :104
+    Tr = _real_dtype(np.dtype(T)).type
+    m, n = opsize(A, 0), opsize(A, 1)
+    if maxiter is None:
+        maxiter = max(m, n)                                             # :68
+    if len(x) != n:
+        raise ValueError(f"x has length {len(x)} but should have length {n}")   # :98
+    if len(b) != m:
+        raise ValueError(f"b has length {len(b)} but should have length {m}")   # :102
+    history = ConvergenceHistory()
+    hist = {"anorm": [], "rnorm": [], "cnorm": []}
+    ctol = Tr(1 / conlim) if conlim > 0 else Tr(0)                      # :108
+    lam = Tr(lam)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        u = (b.astype(T) - mul(A, x)).astype(T)                         # :112-114 (on the copy btmp :76-77)
+        beta = Tr(np.linalg.norm(u))                                    # :115
+        u *= Tr(1) / beta                                               # :116
+        v = mul_adjoint(A, u).astype(T)                                 # :118
+        alpha = Tr(np.linalg.norm(v))                                   # :119
+        v *= Tr(1) / alpha                                              # :120
+    history["atol"], history["btol"], history["ctol"] = atol, btol, ctol
+    zetabar = alpha * beta                                              # :127
+    alphabar = alpha                                                    # :128
+    rho = rhobar = cbar = Tr(1)                                         # :129-131
+    sbar = Tr(0)                                                        # :132
+    h = v.copy()                                                        # :134
+    hbar = np.zeros_like(v)                                             # :135
+    betadd = beta                                                       # :138
+    betad = Tr(0)
+    rhodold = Tr(1)
+    tautildeold = thetatilde = zeta = d = Tr(0)                         # :141-144
+    normA2 = alpha * alpha                                              # :148
+    maxrbar = Tr(0)                                                     # :149
+    minrbar = 1e100                                                     # :150
+    normb = beta                                                        # :153
+    istop = 0
+    normAr = alpha * beta                                               # :156
+    it = 0
+    history.mvps = 1                                                    # :160
+    history.mtvps = 1                                                   # :161
+    if normAr != 0:                                                     # :162
+        while it < maxiter:                                             # :163
+            history.iters += 1                                          # nextiter!(log, mvps=1) :164
+            history.mvps += 1
+            it += 1
+            with np.errstate(divide="ignore", invalid="ignore"):
+                tmp_u = mul(A, v)                                       # :166
+                u[...] = tmp_u + u * (-alpha)                           # :167
+                beta = Tr(np.linalg.norm(u))                            # :168
+                if beta > 0:                                            # :169-176
+                    history.mtvps += 1
+                    u *= Tr(1) / beta
+                    tmp_v = mul_adjoint(A, u)                           # :172
+                    v[...] = tmp_v + v * (-beta)                        # :173
+                    alpha = Tr(np.linalg.norm(v))                       # :174
+                    v *= Tr(1) / alpha                                  # :175
+                alphahat = Tr(math.hypot(alphabar, lam))                # :179
+                chat = alphabar / alphahat                              # :180
+                shat = lam / alphahat                                   # :181
+                rhoold = rho                                            # :184
+                rho = Tr(math.hypot(alphahat, beta))                    # :185
+                c = alphahat / rho                                      # :186
+                s = beta / rho                                          # :187
+                thetanew = s * alpha                                    # :188
+                alphabar = c * alpha                                    # :189
+                rhobarold = rhobar                                      # :192
+                zetaold = zeta                                          # :193
+                thetabar = sbar * rho                                   # :194
+                rhotemp = cbar * rho                                    # :195
+                rhobar = Tr(math.hypot(cbar * rho, thetanew))           # :196
+                cbar = cbar * rho / rhobar                              # :197
+                sbar = thetanew / rhobar                                # :198
+                zeta = cbar * zetabar                                   # :199
+                zetabar = -sbar * zetabar                               # :200
+                hbar[...] = hbar * T(-thetabar * rho / (rhoold * rhobarold)) + h   # :203
+                x += T(zeta / (rho * rhobar)) * hbar                    # :204
+                h[...] = h * T(-thetanew / rho) + v                     # :205
+                betaacute = chat * betadd                               # :214
+                betacheck = -shat * betadd                              # :215
+                betahat = c * betaacute                                 # :218
+                betadd = -s * betaacute                                 # :219
+                thetatildeold = thetatilde                              # :222
+                rhotildeold = Tr(math.hypot(rhodold, thetabar))         # :223
+                ctildeold = rhodold / rhotildeold                       # :224
+                stildeold = thetabar / rhotildeold                      # :225
+                thetatilde = stildeold * rhobar                         # :226
+                rhodold = ctildeold * rhobar                            # :227
+                betad = -stildeold * betad + ctildeold * betahat        # :228
+                tautildeold = (zetaold - thetatildeold * tautildeold) / rhotildeold   # :230
+                taud = (zeta - thetatilde * tautildeold) / rhodold      # :231
+                d = d + betacheck * betacheck                           # :232
+                normr = Tr(math.sqrt(d + (betad - taud) ** 2 + betadd * betadd))   # :233
+                normA2 = normA2 + beta * beta                           # :236
+                normA = Tr(math.sqrt(normA2))                           # :237
+                normA2 = normA2 + alpha * alpha                         # :238
+                maxrbar = max(maxrbar, rhobarold)                       # :241
+                if it > 1:
+                    minrbar = min(minrbar, rhobarold)                   # :242-244
+                condA = max(maxrbar, rhotemp) / min(minrbar, rhotemp)   # :245
+                normAr = abs(zetabar)                                   # :254
+                normx = Tr(np.linalg.norm(x))                           # :255
+                test1 = normr / normb                                   # :259
+                test2 = normAr / (normA * normr)                        # :260
+                test3 = 1 / condA                                       # :261
+                hist["cnorm"].append(float(test3))                      # :262
+                hist["anorm"].append(float(test2))                      # :263
+                hist["rnorm"].append(float(test1))                      # :264
+                t1 = test1 / (Tr(1) + normA * normx / normb)            # :267
+                rtol = btol + atol * normA * normx / normb              # :268
+            if it >= maxiter:
+                istop = 7                                               # :274
+                break
+            if Tr(1) + Tr(test3) <= 1:
+                istop = 6                                               # :275
+                break
+            if Tr(1) + Tr(test2) <= 1:
+                istop = 5                                               # :276
+                break
+            if Tr(1) + Tr(t1) <= 1:
+                istop = 4                                               # :277
+                break
+            if test3 <= ctol:
+                istop = 3                                               # :279
+                break
+            if test2 <= atol:
+                istop = 2                                               # :280
+                break
+            if test1 <= rtol:
+                istop = 1                                               # :281
+                break
+    history.isconverged = istop not in (3, 6, 7)                        # :285
+    history["istop"] = istop
+    for k, v_ in hist.items():
+        history[k] = np.array(v_, dtype=np.float64)
+    return (x, history) if log else x
+
+
+def lsmr(A, b, **kw):
+    """lsmr(A, b; kwargs...) = lsmr!(zerox(A, b), A, b; kwargs...) -- src/lsmr.jl:10."""
+    x = np.zeros(opsize(A, 1), dtype=b.dtype)
+    return lsmr_(x, A, b, **kw)
+
+
+# --------------------------------------------------------------------------------------------
+# IDR(s) (reference src/idrs.jl)
+# --------------------------------------------------------------------------------------------
+def _idrs_omega(t, s):
+    """omega(t, s) -- reference src/idrs.jl:70-81."""
+    angle = math.sqrt(2.0) / 2                                          # :71
+    ns = np.linalg.norm(s)                                              # :72
+    nt = np.linalg.norm(t)                                              # :73
+    ts = np.vdot(t, s)                                                  # :74
+    rho = abs(ts / (nt * ns))                                           # :75
+    om = ts / (nt * nt)                                                 # :76
+    if rho < angle:                                                     # :77-79
+        om = om * type(om)(angle) / rho
+    return om
+
+
+def idrs_(X, A, C, *, s=8, Pl=None, abstol=0.0, reltol=None, maxiter=None, log=False, smoothing=False, P=None,
+          rng=None):
+    """idrs!(x, A, b; s, Pl, abstol, reltol, maxiter, smoothing) -- reference src/idrs.jl:49-64,
+    idrs_iterable! :112-145, iterate :163-272.  `P` (list of s vectors) replaces the reference's
+    `rand!(copy(C))` draws (:132) so that runs are reproducible; otherwise they come from `rng`."""
+    T = C.dtype.type
+    Pl = Pl or Identity()
+    if reltol is None:
+        reltol = math.sqrt(_eps(_real_dtype(C.dtype)))                   # :53
+    if maxiter is None:
+        maxiter = opsize(A, 1)                                          # :54
+    history = ConvergenceHistory()
+    history["abstol"], history["reltol"] = abstol, reltol
+    resnorms = []
+    R = C - mul(A, X)                                                   # :115
+    normR = float(np.linalg.norm(R))                                    # :116
+    tol = max(reltol * normR, abstol)                                   # :117
+    if smoothing:                                                       # :119-122
+        X_s, R_s, T_s = X.copy(), R.copy(), np.zeros_like(R)
+    if P is None:
+        rng = rng or np.random.default_rng()
+        P = [rng.random(len(C)).astype(C.dtype) for _ in range(s)]      # :132
+    U = [np.zeros_like(C) for _ in range(s)]                            # :133
+    G = [np.zeros_like(C) for _ in range(s)]                            # :134
+    Q = np.zeros_like(C)                                                # :135
+    V = np.zeros_like(C)                                                # :136
+    M = np.eye(s, dtype=C.dtype)                                        # :138
+    f = np.zeros(s, dtype=C.dtype)                                      # :139
+    omega = T(1)                                                        # :142
+    it, step = 1, 1                                                     # :163
+    with np.errstate(divide="ignore", invalid="ignore"):
+        while True:
+            if normR < tol or it > maxiter:                             # :167
+                history.isconverged = 0 <= normR < tol                  # :168
+                if smoothing:
+                    X[...] = X_s                                        # :170-172
+                break
+            if 1 <= step <= s:                                          # :176
+                if step == 1:
+                    for i in range(s):
+                        f[i] = np.vdot(P[i], R)                         # :177-181
+                k = step - 1                                            # 0-based
+                L = np.tril(M[k:, k:])
+                c = np.zeros(s - k, dtype=C.dtype)                      # LowerTriangular(M[k:s,k:s]) \ f[k:s] :186
+                for j in range(s - k):
+                    c[j] = (f[k + j] - L[j, :j] @ c[:j]) / L[j, j]
+                V[...] = c[0] * G[k]                                    # :187
+                Q[...] = c[0] * U[k]                                    # :188
+                for i in range(k + 1, s):                               # :190-193
+                    V += c[i - k] * G[i]
+                    Q += c[i - k] * U[i]
+                V[...] = R - V                                          # :196
+                Pl.ldiv(V)                                              # :199
+                U[k][...] = Q + omega * V                               # :201
+                G[k][...] = mul(A, U[k])                                # :202
+                for i in range(k):                                      # :206-210
+                    alpha = np.vdot(P[i], G[k]) / M[i, i]
+                    G[k] -= alpha * G[i]
+                    U[k] -= alpha * U[i]
+                for i in range(k, s):                                   # :214-216
+                    M[i, k] = np.vdot(P[i], G[k])
+                beta = f[k] / M[k, k]                                   # :220
+                R -= beta * G[k]                                        # :221
+                X += beta * U[k]                                        # :222
+                normR = float(np.linalg.norm(R))                        # :224
+                if smoothing:                                           # :225-234
+                    T_s[...] = R_s - R
+                    gamma = np.vdot(R_s, T_s) / np.vdot(T_s, T_s)
+                    R_s -= gamma * T_s
+                    X_s -= gamma * (X_s - X)
+                    normR = float(np.linalg.norm(R_s))
+                if k + 1 < s:                                           # :235-237
+                    f[k + 1:] -= beta * M[k + 1:, k]
+                nextstep = step + 1
+            else:                                                       # step == s + 1 :239
+                V[...] = R                                              # :243
+                Pl.ldiv(V)                                              # :246
+                Q[...] = mul(A, V)                                      # :248
+                omega = T(_idrs_omega(Q, R))                            # :249
+                R -= omega * Q                                          # :250
+                X += omega * V                                          # :251
+                normR = float(np.linalg.norm(R))                        # :253
+                if smoothing:                                           # :254-263
+                    T_s[...] = R_s - R
+                    gamma = np.vdot(R_s, T_s) / np.vdot(T_s, T_s)
+                    R_s -= gamma * T_s
+                    X_s -= gamma * (X_s - X)
+                    normR = float(np.linalg.norm(R_s))
+                nextstep = 1
+            history.iters += 1                                          # nextiter!(it.log, mvps=1) :267
+            history.mvps += 1
+            resnorms.append(normR)                                      # :268
+            it, step = it + 1, nextstep                                 # :271
+    if log:
+        history["resnorm"] = np.array(resnorms)
+        history["tol"] = tol
+        return X, history
+    return X
+
+
+def idrs(A, b, **kw):
+    """idrs(A, b; kwargs...) = idrs!(zerox(A, b), A, b; kwargs...) -- src/idrs.jl:11."""
+    x = np.zeros(opsize(A, 1), dtype=b.dtype)
+    return idrs_(x, A, b, **kw)

@@ -1,0 +1,211 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE ONLY (never linked into libb200krylov.so, never imported by the
+// product package).
+//
+// A serial CPU backend for the fused-pass engines (csrc/pass_core.h): it runs the SAME pass functors, scalar
+// sections and driver loops that libb200krylov.so instantiates with the CUDA backend (csrc/pass.cuh), so that the
+// algorithmic content of those engines -- everything except the generic k_pass kernel and the SpMV kernels, which the
+// GPU tests cover -- is checked against the oracle on machines without a GPU.
+//
+//   order:  0 = rows ascending, 1 = rows descending.  A pass whose element update of row i touched any other
+//           row would give order-dependent vectors; the tests run both orders and compare.
+//   split:  0 = finish(tot) right after the reduction (single-GPU form), 1 = totals stored to sums() and
+//           finish(sums()) called separately (the multi-GPU form: allreduce between the two).
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../iterativesolvers.jl_b200/csrc/pass_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/qmr_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/lsqr_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/lsmr_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/idrs_core.h"
+
+#define EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+struct HostCsr {          // 0-based CSR, int64 row pointers, int32 columns
+  int64_t m, n;
+  const int64_t *rowptr;
+  const int32_t *colind;
+  const void *vals;
+  int is_f64;
+};
+
+struct HostBackend {
+  typedef HostCsr Op;
+  int order = 0, split = 0;
+  std::vector<char> ws;
+  long passes = 0, applies = 0;
+
+  bool single() const { return !split; }
+
+  int apply(const Op *A, const void *x, void *y) {
+    ++applies;
+    if (A->is_f64) {
+      const double *v = (const double *)A->vals, *xx = (const double *)x;
+      double *yy = (double *)y;
+      for (int64_t i = 0; i < A->m; ++i) {
+        double t = 0.0;
+        for (int64_t k = A->rowptr[i]; k < A->rowptr[i + 1]; ++k) t += v[k] * xx[A->colind[k]];
+        yy[i] = t;
+      }
+    } else {
+      const float *v = (const float *)A->vals, *xx = (const float *)x;
+      float *yy = (float *)y;
+      for (int64_t i = 0; i < A->m; ++i) {
+        float t = 0.0f;
+        for (int64_t k = A->rowptr[i]; k < A->rowptr[i + 1]; ++k) t += v[k] * xx[A->colind[k]];
+        yy[i] = t;
+      }
+    }
+    return 0;
+  }
+
+  template <typename P>
+  int pass(const P &p_in, int64_t n) {
+    ++passes;
+    if (p_in.skip()) return 0;
+    P p = p_in;
+    p.load();
+    double acc[P::NRED > 0 ? P::NRED : 1];
+    for (int j = 0; j < (P::NRED > 0 ? P::NRED : 1); ++j) acc[j] = 0.0;
+    if (order == 0) for (int64_t i = 0; i < n; ++i) p.elem(i, acc);
+    else for (int64_t i = n - 1; i >= 0; --i) p.elem(i, acc);
+    if (P::NRED > 0) {
+      if (!split) p.finish(acc);
+      else {
+        double *out = p.sums();
+        for (int j = 0; j < P::NRED; ++j) out[j] = acc[j];
+        if (!p.skip()) p.finish(p.sums());
+      }
+    }
+    return 0;
+  }
+  template <typename P>
+  int scalar(const P &p) {
+    if (p.skip()) return 0;
+    p.finish(p.sums());
+    return 0;
+  }
+  int zero(void *x, size_t bytes) { memset(x, 0, bytes); return 0; }
+  int copy(void *dst, const void *src, size_t bytes) { if (dst != src) memmove(dst, src, bytes); return 0; }
+  int to_device(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
+  int to_host(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); return 0; }
+  int read_flag(const int *flag, int *out) { *out = *flag; return 0; }
+  int workspace(size_t bytes, void **out) {
+    // poison the scratch so that reads of never-written storage show up as NaNs in the results
+    ws.assign(bytes + 256, (char)0xff);
+    *out = (void *)(((uintptr_t)ws.data() + 255) / 256 * 256);
+    return 0;
+  }
+};
+
+}  // namespace
+
+struct hostsim_csr {
+  int64_t m, n;
+  const int64_t *rowptr;
+  const int32_t *colind;
+  const void *vals;
+};
+struct hostsim_out {
+  int64_t iters, mvps, mtvps, n_hist;
+  double resnorm, tol;
+  int32_t converged, breakdown;
+  int64_t passes, applies;
+};
+
+static HostCsr mk(const hostsim_csr *a, int is_f64) { return HostCsr{a->m, a->n, a->rowptr, a->colind, a->vals, is_f64}; }
+
+EXPORT int hostsim_qmr(int is_f64, const hostsim_csr *A, const hostsim_csr *At, void *x, const void *b, double abstol,
+                       double reltol, int64_t maxiter, int initially_zero, int check_every, int64_t hist_cap,
+                       double *hist, int order, int split, hostsim_out *out) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64), at = mk(At, is_f64);
+  b200::QmrOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st = is_f64 ? b200::qmr_run<double>(be, &a, &at, A->m, A->n, (double *)x, (const double *)b, abstol, reltol,
+                                          maxiter, initially_zero, check_every, hist_cap, hist, &o)
+                  : b200::qmr_run<float>(be, &a, &at, A->m, A->n, (float *)x, (const float *)b, abstol, reltol,
+                                         maxiter, initially_zero, check_every, hist_cap, hist, &o);
+  out->iters = o.iters; out->mvps = o.mvps; out->mtvps = o.mtvps; out->n_hist = o.n_hist;
+  out->resnorm = o.resnorm; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
+  out->passes = be.passes; out->applies = be.applies;
+  return st;
+}
+
+struct hostsim_ls_out {
+  int64_t iters, mvps, mtvps, n_hist, hist_stride;
+  int32_t istop, converged, bad_x, early;
+  double atol, btol, ctol;
+  double est[5];   // lsqr: Anorm, Acond, rnorm, Arnorm, xnorm ; lsmr: normr, normAr, normA, condA, normx
+  int64_t passes, applies;
+};
+
+EXPORT int hostsim_lsqr(int is_f64, const hostsim_csr *A, const hostsim_csr *At, void *x, const void *b, double damp,
+                        double atol, double btol, double conlim, int64_t maxiter, int check_every, int64_t hist_cap,
+                        double *hist, int order, int split, hostsim_ls_out *out) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64), at = mk(At, is_f64);
+  b200::LsqrOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st = is_f64 ? b200::lsqr_run<double>(be, &a, &at, A->m, A->n, (double *)x, (const double *)b, damp, atol, btol,
+                                           conlim, maxiter, check_every, hist_cap, hist, &o)
+                  : b200::lsqr_run<float>(be, &a, &at, A->m, A->n, (float *)x, (const float *)b, damp, atol, btol,
+                                          conlim, maxiter, check_every, hist_cap, hist, &o);
+  out->iters = o.iters; out->mvps = o.mvps; out->mtvps = o.mtvps; out->n_hist = o.n_hist; out->hist_stride = o.hist_stride;
+  out->istop = o.istop; out->converged = o.converged; out->bad_x = o.bad_x; out->early = o.early;
+  out->atol = o.atol; out->btol = o.btol; out->ctol = o.ctol;
+  out->est[0] = o.anorm; out->est[1] = o.acond; out->est[2] = o.rnorm; out->est[3] = o.arnorm; out->est[4] = o.xnorm;
+  out->passes = be.passes; out->applies = be.applies;
+  return st;
+}
+
+EXPORT int hostsim_lsmr(int is_f64, const hostsim_csr *A, const hostsim_csr *At, void *x, const void *b, double lambda,
+                        double atol, double btol, double conlim, int64_t maxiter, int check_every, int64_t hist_cap,
+                        double *hist, int order, int split, hostsim_ls_out *out) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64), at = mk(At, is_f64);
+  b200::LsmrOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st = is_f64 ? b200::lsmr_run<double>(be, &a, &at, A->m, A->n, (double *)x, (const double *)b, lambda, atol, btol,
+                                           conlim, maxiter, check_every, hist_cap, hist, &o)
+                  : b200::lsmr_run<float>(be, &a, &at, A->m, A->n, (float *)x, (const float *)b, lambda, atol, btol,
+                                          conlim, maxiter, check_every, hist_cap, hist, &o);
+  out->iters = o.iters; out->mvps = o.mvps; out->mtvps = o.mtvps; out->n_hist = o.n_hist; out->hist_stride = o.hist_stride;
+  out->istop = o.istop; out->converged = o.converged; out->bad_x = 0; out->early = o.early;
+  out->atol = o.atol; out->btol = o.btol; out->ctol = o.ctol;
+  out->est[0] = o.normr; out->est[1] = o.normAr; out->est[2] = o.normA; out->est[3] = o.condA; out->est[4] = o.normx;
+  out->passes = be.passes; out->applies = be.applies;
+  return st;
+}
+
+EXPORT int hostsim_idrs(int is_f64, const hostsim_csr *A, void *x, const void *b, int s_dim, const void *P, int64_t ldp,
+                        const void *diag, double abstol, double reltol, int64_t maxiter, int smoothing, int check_every,
+                        int64_t hist_cap, double *hist, int order, int split, hostsim_out *out) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64);
+  b200::IdrsOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st = is_f64 ? b200::idrs_run<double>(be, &a, A->m, A->n, (double *)x, (const double *)b, s_dim, (const double *)P,
+                                           ldp, (const double *)diag, abstol, reltol, maxiter, smoothing, check_every,
+                                           hist_cap, hist, &o)
+                  : b200::idrs_run<float>(be, &a, A->m, A->n, (float *)x, (const float *)b, s_dim, (const float *)P, ldp,
+                                          (const float *)diag, abstol, reltol, maxiter, smoothing, check_every,
+                                          hist_cap, hist, &o);
+  out->iters = o.iters; out->mvps = o.iters; out->mtvps = 0; out->n_hist = o.n_hist;
+  out->resnorm = o.normR; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
+  out->passes = be.passes; out->applies = be.applies;
+  return st;
+}

@@ -1,0 +1,155 @@
+"""tests/hostsim/sim.py -- ctypes loader of the serial CPU backend for the fused-pass engines
+(TEST INFRASTRUCTURE ONLY: see hostsim.cpp).  Builds libhostsim.so with the committed Makefile (g++ only)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+import scipy.sparse as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class _Csr(C.Structure):
+    _fields_ = [("m", C.c_int64), ("n", C.c_int64), ("rowptr", C.c_void_p), ("colind", C.c_void_p),
+                ("vals", C.c_void_p)]
+
+
+class _Out(C.Structure):
+    _fields_ = [("iters", C.c_int64), ("mvps", C.c_int64), ("mtvps", C.c_int64), ("n_hist", C.c_int64),
+                ("resnorm", C.c_double), ("tol", C.c_double), ("converged", C.c_int32), ("breakdown", C.c_int32),
+                ("passes", C.c_int64), ("applies", C.c_int64)]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        subprocess.run(["make", "-s", "-C", _HERE], check=True)
+        _LIB = C.CDLL(os.path.join(_HERE, "libhostsim.so"))
+    return _LIB
+
+
+class Csr:
+    """0-based CSR copy (int64 row pointers, int32 columns) of a scipy matrix, kept alive for the C call."""
+
+    def __init__(self, A, dtype):
+        A = sp.csr_matrix(A)
+        A.sort_indices()
+        self.shape = A.shape
+        self.rowptr = np.ascontiguousarray(A.indptr, dtype=np.int64)
+        self.colind = np.ascontiguousarray(A.indices, dtype=np.int32)
+        self.vals = np.ascontiguousarray(A.data, dtype=dtype)
+        self.c = _Csr(A.shape[0], A.shape[1], self.rowptr.ctypes.data, self.colind.ctypes.data, self.vals.ctypes.data)
+
+
+@dataclass
+class Outcome:
+    iters: int
+    mvps: int
+    mtvps: int
+    resnorm: float
+    tol: float
+    converged: bool
+    breakdown: bool
+    hist: np.ndarray
+    passes: int
+    applies: int
+
+
+def _outcome(o: _Out, hist):
+    return Outcome(o.iters, o.mvps, o.mtvps, o.resnorm, o.tol, bool(o.converged), bool(o.breakdown),
+                   hist[: o.n_hist].copy(), o.passes, o.applies)
+
+
+def qmr_(x, A, b, *, abstol=0.0, reltol=-1.0, maxiter=-1, initially_zero=False, check_every=0, order=0, split=0):
+    """the qmr engine (csrc/qmr_core.h) on the serial backend; x updated in place."""
+    dt = x.dtype
+    Ac, Atc = Csr(A, dt), Csr(sp.csr_matrix(A).T, dt)
+    b = np.ascontiguousarray(b, dtype=dt)
+    cap = (maxiter if maxiter >= 0 else A.shape[1]) + 1
+    hist = np.zeros(cap)
+    out = _Out()
+    st = lib().hostsim_qmr(C.c_int(dt == np.float64), C.byref(Ac.c), C.byref(Atc.c), C.c_void_p(x.ctypes.data),
+                           C.c_void_p(b.ctypes.data), C.c_double(abstol), C.c_double(reltol), C.c_int64(maxiter),
+                           C.c_int(initially_zero), C.c_int(check_every), C.c_int64(cap),
+                           hist.ctypes.data_as(C.c_void_p), C.c_int(order), C.c_int(split), C.byref(out))
+    assert st == 0, st
+    return x, _outcome(out, hist)
+
+
+class _LsOut(C.Structure):
+    _fields_ = [("iters", C.c_int64), ("mvps", C.c_int64), ("mtvps", C.c_int64), ("n_hist", C.c_int64),
+                ("hist_stride", C.c_int64), ("istop", C.c_int32), ("converged", C.c_int32), ("bad_x", C.c_int32),
+                ("early", C.c_int32), ("atol", C.c_double), ("btol", C.c_double), ("ctol", C.c_double),
+                ("est", C.c_double * 5), ("passes", C.c_int64), ("applies", C.c_int64)]
+
+
+@dataclass
+class LsOutcome:
+    iters: int
+    mvps: int
+    mtvps: int
+    istop: int
+    converged: bool
+    bad_x: bool
+    early: bool
+    atol: float
+    btol: float
+    ctol: float
+    est: tuple
+    hist: dict          # resnorm (lsqr) / normr (lsmr), anorm, rnorm, cnorm
+    passes: int
+    applies: int
+
+
+def _ls(fn, first_row, x, A, b, p0, atol, btol, conlim, maxiter, check_every, order, split):
+    dt = x.dtype
+    Ac, Atc = Csr(A, dt), Csr(sp.csr_matrix(A).T, dt)
+    b = np.ascontiguousarray(b, dtype=dt)
+    cap = maxiter if maxiter >= 0 else max(A.shape)
+    hist = np.zeros(4 * max(cap, 1))
+    out = _LsOut()
+    st = fn(C.c_int(dt == np.float64), C.byref(Ac.c), C.byref(Atc.c), C.c_void_p(x.ctypes.data),
+            C.c_void_p(b.ctypes.data), C.c_double(p0), C.c_double(atol), C.c_double(btol), C.c_double(conlim),
+            C.c_int64(maxiter), C.c_int(check_every), C.c_int64(cap), hist.ctypes.data_as(C.c_void_p), C.c_int(order),
+            C.c_int(split), C.byref(out))
+    assert st == 0, st
+    sd, k = out.hist_stride, out.n_hist
+    rows = {name: hist[i * sd: i * sd + k].copy() for i, name in enumerate((first_row, "anorm", "rnorm", "cnorm"))}
+    return x, LsOutcome(out.iters, out.mvps, out.mtvps, out.istop, bool(out.converged), bool(out.bad_x),
+                        bool(out.early), out.atol, out.btol, out.ctol, tuple(out.est), rows, out.passes, out.applies)
+
+
+def lsqr_(x, A, b, *, damp=0.0, atol=-1.0, btol=-1.0, conlim=-1.0, maxiter=-1, check_every=0, order=0, split=0):
+    """the lsqr engine (csrc/lsqr_core.h) on the serial backend; x updated in place."""
+    return _ls(lib().hostsim_lsqr, "resnorm", x, A, b, damp, atol, btol, conlim, maxiter, check_every, order, split)
+
+
+def lsmr_(x, A, b, *, lam=0.0, atol=-1.0, btol=-1.0, conlim=-1.0, maxiter=-1, check_every=0, order=0, split=0):
+    """the lsmr engine (csrc/lsmr_core.h) on the serial backend; x updated in place."""
+    return _ls(lib().hostsim_lsmr, "normr", x, A, b, lam, atol, btol, conlim, maxiter, check_every, order, split)
+
+
+def idrs_(x, A, b, P, *, diag=None, abstol=0.0, reltol=-1.0, maxiter=-1, smoothing=False, check_every=0, order=0,
+          split=0):
+    """the idrs engine (csrc/idrs_core.h) on the serial backend; P: n x s (Fortran order), x updated in place."""
+    dt = x.dtype
+    Ac = Csr(A, dt)
+    b = np.ascontiguousarray(b, dtype=dt)
+    P = np.asfortranarray(P, dtype=dt)
+    d = None if diag is None else np.ascontiguousarray(diag, dtype=dt)
+    cap = (maxiter if maxiter >= 0 else A.shape[1]) + 1
+    hist = np.zeros(cap)
+    out = _Out()
+    st = lib().hostsim_idrs(C.c_int(dt == np.float64), C.byref(Ac.c), C.c_void_p(x.ctypes.data),
+                            C.c_void_p(b.ctypes.data), C.c_int(P.shape[1]), C.c_void_p(P.ctypes.data),
+                            C.c_int64(P.shape[0]), C.c_void_p(d.ctypes.data if d is not None else None),
+                            C.c_double(abstol), C.c_double(reltol), C.c_int64(maxiter), C.c_int(smoothing),
+                            C.c_int(check_every), C.c_int64(cap), hist.ctypes.data_as(C.c_void_p), C.c_int(order),
+                            C.c_int(split), C.byref(out))
+    assert st == 0, st
+    return x, _outcome(out, hist)
