@@ -279,6 +279,54 @@ typedef struct {
 B200_API int b200_qmr_solve(b200_ctx *ctx, const b200_csr *A, const b200_csr *At, void *x_dev, const void *b_dev,
                             const b200_qmr_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);
 
+/* lsqr! / lsmr! share one option block and one result block. */
+typedef struct {
+  double damp;              /* lsqr: damp = 0 (src/lsqr.jl:91); lsmr: λ = 0 (src/lsmr.jl:90)                       */
+  double atol, btol;        /* lsqr: sqrt(eps(real(T))) (src/lsqr.jl:91); lsmr: 1e-6 (src/lsmr.jl:89) -- <0: default */
+  double conlim;            /* lsqr: 1/sqrt(eps) (src/lsqr.jl:92); lsmr: 1e8 (src/lsmr.jl:89) -- <0: default         */
+  int64_t maxiter;          /* maximum(size(A)) (src/lsqr.jl:67, src/lsmr.jl:68) -- <0: default                      */
+  int32_t check_every;      /* iterations enqueued between host polls of the device-side done flag (<=0: 16)        */
+  int32_t reserved;
+} b200_lsq_opts;
+typedef struct {
+  int64_t iters;            /* history.iters                                                                        */
+  int64_t mvps, mtvps;      /* history.mvps / history.mtvps as the reference counts them (src/lsqr.jl:130,153,167;
+                               src/lsmr.jl:160-161,164,170)                                                         */
+  int32_t isconverged;      /* lsqr: istop > 0 (src/lsqr.jl:271); lsmr: istop not in (3, 6, 7) (src/lsmr.jl:285)      */
+  int32_t istop;            /* the stopping rule that fired, 0..7                                                   */
+  int32_t status;           /* 0, or B200_ERR_INVALID (lsqr: initial guess not finite, src/lsqr.jl:102-104)          */
+  int32_t reserved;
+  int64_t n_hist;           /* entries written to each history row                                                  */
+  int64_t hist_stride;      /* distance between the rows of hist_host = min(hist_cap, maxiter)                      */
+  double atol, btol, ctol;  /* history[:atol], [:btol], [:ctol]                                                     */
+} b200_lsq_result;
+/* lsqr!(x, A, b; damp, atol, btol, conlim, maxiter)  reference src/lsqr.jl:66-77, 90-275.
+ * lsmr!(x, A, b; λ, atol, btol, conlim, maxiter)     reference src/lsmr.jl:67-82, 88-287.
+ * A: m x n (rectangular allowed on single-GPU contexts), At = adjoint(A); x_dev: n values, updated in place;
+ * b_dev: m values, not modified.  hist_host (may be NULL): 4 rows of res->hist_stride doubles --
+ * row 0: history[:resnorm] (lsqr) / the ||r|| estimate (lsmr, not part of the reference's history),
+ * row 1: [:anorm], row 2: [:rnorm], row 3: [:cnorm]; hist_cap = capacity per row the caller provides. */
+B200_API int b200_lsqr_solve(b200_ctx *ctx, const b200_csr *A, const b200_csr *At, void *x_dev, const void *b_dev,
+                             const b200_lsq_opts *opts, b200_lsq_result *res, double *hist_host, int64_t hist_cap);
+B200_API int b200_lsmr_solve(b200_ctx *ctx, const b200_csr *A, const b200_csr *At, void *x_dev, const void *b_dev,
+                             const b200_lsq_opts *opts, b200_lsq_result *res, double *hist_host, int64_t hist_cap);
+
+typedef struct {
+  double abstol, reltol;    /* src/idrs.jl:52-53 (reltol < 0: sqrt(eps(real(T))))                                  */
+  int64_t maxiter;          /* size(A, 2)  src/idrs.jl:54 (<0: default)                                             */
+  int32_t s;                /* dimension of the shadow space, default 8 (src/idrs.jl:50); 1..16                     */
+  int32_t smoothing;        /* src/idrs.jl:112                                                                      */
+  b200_precond Pl;          /* src/idrs.jl:51                                                                       */
+  const void *P;            /* device, n_local x s column-major: the shadow vectors the reference draws with
+                               rand!(copy(C)) (src/idrs.jl:132) -- the host passes the draw                        */
+  int64_t ldp;
+  int32_t check_every;      /* steps enqueued between host polls of the device-side done flag (<=0: 16)             */
+  int32_t reserved;
+} b200_idrs_opts;
+/* idrs!(x, A, b; s, Pl, abstol, reltol, maxiter, smoothing)  reference src/idrs.jl:49-64, 112-145, 163-272. */
+B200_API int b200_idrs_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
+                             const b200_idrs_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);
+
 typedef struct {
   double abstol, reltol;    /* src/gmres.jl:187-188                                                */
   int64_t maxiter;          /* size(A,2)           src/gmres.jl:190                                */

@@ -4,7 +4,8 @@ B200-native C ABI (libb200krylov.so).
 Julia is not available in this image, so this Python layer plays the role of the Julia shim
 (INTEGRATION.md): same function names (`cg!` -> `cg_`), keyword arguments, defaults, return shapes
 (`x` or `(x, ConvergenceHistory)`) and error behaviour as reference src/cg.jl, src/gmres.jl,
-src/minres.jl, src/bicgstabl.jl, src/lobpcg.jl.  All arithmetic runs in the CUDA library; this
+src/minres.jl, src/bicgstabl.jl, src/lobpcg.jl (and, as the section 8(f) widening, src/chebyshev.jl, src/qmr.jl,
+src/lsqr.jl, src/lsmr.jl, src/idrs.jl).  All arithmetic runs in the CUDA library; this
 package contains no numerical fallback.
 
 The directory name contains a dot, so import it through the repo-root alias module:
@@ -17,4 +18,5 @@ from .history import ConvergenceHistory  # noqa: F401
 from .generators import laplace_matrix, laplace_csr_slab, advection_dominated  # noqa: F401
 from .solvers import (cg, cg_, chebyshev, chebyshev_, gmres, gmres_, minres, minres_, bicgstabl, bicgstabl_, lobpcg,  # noqa: F401
                       LOBPCGResults, orthogonalize_and_normalize_, hessenberg_ldiv_,
-                      cg_iterator_, CGIterable, CGStateVariables)
+                      cg_iterator_, CGIterable, CGStateVariables,
+                      qmr, qmr_, lsqr, lsqr_, lsmr, lsmr_, idrs, idrs_)

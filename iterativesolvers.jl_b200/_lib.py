@@ -13,6 +13,7 @@ _SO = os.path.join(_HERE, "libb200krylov.so")
 F64, F32 = 0, 1
 ORTH_MGS, ORTH_CGS, ORTH_DGKS = 0, 1, 2
 PREC_IDENTITY, PREC_JACOBI = 0, 1
+ERR_INVALID = -1
 ERR_BREAKDOWN = -5
 
 
@@ -49,6 +50,28 @@ class MinresOpts(C.Structure):
 class BicgstablOpts(C.Structure):
     _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("max_mv_products", C.c_int64), ("l", C.c_int32),
                 ("initial_zero", C.c_int32), ("Pl", Precond), ("r_shadow", C.c_void_p)]
+
+
+class QmrOpts(C.Structure):
+    _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("maxiter", C.c_int64),
+                ("initially_zero", C.c_int32), ("check_every", C.c_int32)]
+
+
+class LsqOpts(C.Structure):
+    _fields_ = [("damp", C.c_double), ("atol", C.c_double), ("btol", C.c_double), ("conlim", C.c_double),
+                ("maxiter", C.c_int64), ("check_every", C.c_int32), ("reserved", C.c_int32)]
+
+
+class LsqResult(C.Structure):
+    _fields_ = [("iters", C.c_int64), ("mvps", C.c_int64), ("mtvps", C.c_int64), ("isconverged", C.c_int32),
+                ("istop", C.c_int32), ("status", C.c_int32), ("reserved", C.c_int32), ("n_hist", C.c_int64),
+                ("hist_stride", C.c_int64), ("atol", C.c_double), ("btol", C.c_double), ("ctol", C.c_double)]
+
+
+class IdrsOpts(C.Structure):
+    _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("maxiter", C.c_int64), ("s", C.c_int32),
+                ("smoothing", C.c_int32), ("Pl", Precond), ("P", C.c_void_p), ("ldp", C.c_int64),
+                ("check_every", C.c_int32), ("reserved", C.c_int32)]
 
 
 class LobpcgOpts(C.Structure):
@@ -99,6 +122,7 @@ SIGNATURES = {
     "b200_csr_destroy": (_INT, [_P]),
     "b200_csr_info": (_INT, [_P, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_INT),
                              C.POINTER(_I64), C.POINTER(_I64)]),
+    "b200_csr_transpose": (_INT, [_P, _P, C.POINTER(_P)]),
     "b200_csr_diag": (_INT, [_P, _P, _P]),
     "b200_csr_download": (_INT, [_P, _P, _P, _P, _P]),
     "b200_halo_plan_create": (_INT, [_INT, _INT, C.POINTER(_I64), C.POINTER(_P)]),
@@ -135,6 +159,10 @@ SIGNATURES = {
     "b200_gmres_solve": (_INT, [_P, _P, _P, _P, C.POINTER(GmresOpts), C.POINTER(Result), _P, _I64]),
     "b200_minres_solve": (_INT, [_P, _P, _P, _P, C.POINTER(MinresOpts), C.POINTER(Result), _P, _I64]),
     "b200_bicgstabl_solve": (_INT, [_P, _P, _P, _P, C.POINTER(BicgstablOpts), C.POINTER(Result), _P, _I64]),
+    "b200_qmr_solve": (_INT, [_P, _P, _P, _P, _P, C.POINTER(QmrOpts), C.POINTER(Result), _P, _I64]),
+    "b200_lsqr_solve": (_INT, [_P, _P, _P, _P, _P, C.POINTER(LsqOpts), C.POINTER(LsqResult), _P, _I64]),
+    "b200_lsmr_solve": (_INT, [_P, _P, _P, _P, _P, C.POINTER(LsqOpts), C.POINTER(LsqResult), _P, _I64]),
+    "b200_idrs_solve": (_INT, [_P, _P, _P, _P, C.POINTER(IdrsOpts), C.POINTER(Result), _P, _I64]),
     "b200_lobpcg_solve": (_INT, [_P, _P, _P, _I64, C.POINTER(LobpcgOpts), C.POINTER(LobpcgResult), _P, _P]),
     "b200_dense_sygv_host": (_INT, [_INT, _P, _P, _P, _P]),
 }

@@ -123,6 +123,9 @@ class B200CSR:
         self.m_local, self.n_global, self.nnz, self.row_begin, self.n_halo = m.value, n.value, nnz.value, rb.value, nh.value
         self.dtype = np.dtype(np.float64 if dt.value == _lib.F64 else np.float32)
         self.code = dt.value
+        # size(A, 1): row-partitioned (multi-GPU) operators are square; single-GPU ones may be rectangular (lsqr!/lsmr!)
+        self.m_global = self.m_local if ctx.world == 1 else self.n_global
+        self._adjoint = None
 
     # --- constructors -----------------------------------------------------------------------
     @classmethod
@@ -172,7 +175,22 @@ class B200CSR:
     # --- reference operator contract ----------------------------------------------------------
     @property
     def shape(self):
-        return (self.n_global, self.n_global)
+        return (self.m_global, self.n_global)
+
+    def adjoint(self) -> "B200CSR":
+        """adjoint(A) as an operator of its own (what the reference stores as `adjoint(A)`, src/qmr.jl:54; used by
+        mul!(y, A', x) in qmr!/lsqr!/lsmr!).  Built once on the device from the CSR of A and cached.  On multi-GPU
+        contexts build it from the adjoint's own row slabs (from_csr_slab) and assign it with set_adjoint()."""
+        if self._adjoint is None:
+            h = C.c_void_p()
+            check(lib().b200_csr_transpose(self.ctx._h, self._h, C.byref(h)))
+            self._adjoint = B200CSR(self.ctx, h)
+            self._adjoint._adjoint_of = self          # keeps A alive as long as A' is (not the other way round)
+        return self._adjoint
+
+    def set_adjoint(self, At: "B200CSR"):
+        self._adjoint = At
+        return self
 
     def size(self, d=None):
         return self.shape if d is None else self.shape[d - 1]
@@ -189,7 +207,7 @@ class B200CSR:
     def __matmul__(self, x: np.ndarray) -> np.ndarray:
         """A * x with host arrays (convenience for tests)."""
         xd = DeviceArray.from_numpy(self.ctx, np.asarray(x, dtype=self.dtype))
-        yd = DeviceArray(self.ctx, xd.shape, self.dtype)
+        yd = DeviceArray(self.ctx, (self.m_local,) + tuple(xd.shape[1:]), self.dtype)
         self.mul_(yd, xd)
         return yd.numpy()
 
@@ -206,6 +224,9 @@ class B200CSR:
         return rowptr, colind, vals
 
     def close(self):
+        if getattr(self, "_adjoint", None) is not None and getattr(self._adjoint, "_adjoint_of", None) is self:
+            self._adjoint.close()
+        self._adjoint = None
         if self._h:
             lib().b200_csr_destroy(self._h)
             self._h = C.c_void_p()

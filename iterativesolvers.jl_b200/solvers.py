@@ -394,6 +394,181 @@ def bicgstabl(A, b, l=2, **kw):
 
 
 # ------------------------------------------------------------------------------------------------
+# the solvers that need A' (QMR, LSQR, LSMR) and IDR(s)
+# ------------------------------------------------------------------------------------------------
+class _StagedRect:
+    """host<->device staging for an m x n operator: x has n entries, b has m."""
+
+    def __init__(self, A: B200CSR, x, b):
+        m, n = A.m_local, (A.n_global if A.ctx.world == 1 else A.m_local)
+        self.host = not is_device(x)
+        self.x = x
+        if self.host:
+            if is_device(b):
+                raise TypeError("x and b must both be host arrays or both be device arrays")
+            if not (isinstance(x, np.ndarray) and x.dtype == A.dtype):
+                raise TypeError(f"x must be a numpy array of eltype {A.dtype} (got {getattr(x, 'dtype', type(x))})")
+            self.xd = DeviceArray.from_numpy(A.ctx, x)
+            self.bd = DeviceArray.from_numpy(A.ctx, np.asarray(b, dtype=A.dtype))
+        else:
+            self.xd, self.bd = x, b
+        if self.xd.shape[0] != n:
+            raise ValueError(f"x should be of length {n}")                   # src/lsqr.jl:99
+        if self.bd.shape[0] != m:
+            raise ValueError(f"b should be of length {m}")                   # src/lsqr.jl:100
+
+    def finish(self):
+        if self.host:
+            self.x[...] = self.xd.numpy().reshape(self.x.shape)
+        return self.x
+
+
+def qmr_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, lookahead=False, log=False, initially_zero=False,
+         verbose=False, check_every=0):
+    """qmr!(x, A, b; abstol, reltol, maxiter, lookahead, log, initially_zero, verbose) -- reference src/qmr.jl:262-297.
+    `lookahead` is accepted and ignored, as in the reference (it is never forwarded, src/qmr.jl:279-280)."""
+    _check_operator(A)
+    if reltol is None:
+        reltol = math.sqrt(_eps(A.dtype))                     # src/qmr.jl:267
+    if maxiter is None:
+        maxiter = A.size(2)                                   # src/qmr.jl:268
+    opts = _lib.QmrOpts(abstol, reltol, int(maxiter), int(bool(initially_zero)), int(check_every))
+    res = _lib.Result()
+    cap = int(maxiter) if log else 0                          # reserve!(history, :resnorm, maxiter)  :277
+    resnorm = np.zeros(max(cap, 1), dtype=np.float64)
+    st = _Staged(A, x, b)
+    check(lib().b200_qmr_solve(A.ctx._h, A._h, A.adjoint()._h, as_device_ptr(st.xd), as_device_ptr(st.bd),
+                               C.byref(opts), C.byref(res), resnorm.ctypes.data_as(C.c_void_p) if log else None, cap))
+    st.finish()
+    if verbose:
+        print("=== qmr ===\niter\tresnorm")
+        for i, r in enumerate(resnorm[: res.n_resnorm], start=1):
+            print(f"{i:3d}\t{r:1.2e}")
+        print()
+    qmr_.last_result = res
+    h = _history(res, resnorm, abstol, reltol, log)
+    h.isconverged = bool(res.isconverged) if log else False  # setconv only when log (src/qmr.jl:293)
+    h.mvps = 0                                                # nextiter!(history) without mvps (src/qmr.jl:285)
+    return (x, h) if log else x
+
+
+def qmr(A, b, **kw):
+    """qmr(A, b; kwargs...) = qmr!(zerox(A, b), A, b; initially_zero = true, kwargs...) -- src/qmr.jl:222."""
+    _check_operator(A)
+    x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
+    return qmr_(x, A, b, initially_zero=True, **kw)
+
+
+def _lsq(fn, first_key, x, A, b, damp, atol, btol, conlim, maxiter, log, verbose, check_every, name):
+    _check_operator(A)
+    if maxiter is None:
+        maxiter = max(A.shape)                                # maximum(size(A))  src/lsqr.jl:67, src/lsmr.jl:68
+    opts = _lib.LsqOpts(float(damp), float(atol), float(btol), float(conlim), int(maxiter), int(check_every), 0)
+    res = _lib.LsqResult()
+    cap = int(maxiter)                                        # reserve!(history, [...], maxiter)  src/lsqr.jl:73
+    hist = np.zeros(4 * max(cap, 1), dtype=np.float64)
+    st = _StagedRect(A, x, b)
+    status = fn(A.ctx._h, A._h, A.adjoint()._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
+                C.byref(res), hist.ctypes.data_as(C.c_void_p), cap)
+    if status == _lib.ERR_INVALID and res.status == _lib.ERR_INVALID:
+        raise ValueError("Initial guess for x must be finite")            # src/lsqr.jl:102-104
+    check(status)
+    st.finish()
+    h = ConvergenceHistory()
+    h["atol"], h["btol"], h["ctol"] = res.atol, res.btol, res.ctol       # src/lsqr.jl:118-120
+    h.isconverged = bool(res.isconverged)
+    h.iters, h.mvps, h.mtvps = int(res.iters), int(res.mvps), int(res.mtvps)
+    h["istop"] = int(res.istop)
+    sd, k = int(res.hist_stride), int(res.n_hist)
+    for i, key in enumerate((first_key, "anorm", "rnorm", "cnorm")):
+        if key is not None:
+            h[key] = hist[i * sd: i * sd + k].copy()
+    if verbose:
+        print(f"=== {name} ===")
+        for i in range(k):
+            print(f"{i + 1:3d}\t{h['anorm'][i]:1.2e}\t{h['cnorm'][i]:1.2e}\t{h['rnorm'][i]:1.2e}")
+        print()
+    return (x, h) if log else x
+
+
+def lsqr_(x, A, b, *, damp=0.0, atol=None, btol=None, conlim=None, maxiter=None, log=False, verbose=False,
+          check_every=0):
+    """lsqr!(x, A, b; damp, atol, btol, conlim, maxiter, verbose, log) -- reference src/lsqr.jl:66-77, 90-275.
+    A may be rectangular (m x n): x has n entries, b has m."""
+    s = math.sqrt(_eps(A.dtype)) if isinstance(A, B200CSR) else 0.0
+    atol = s if atol is None else atol                        # src/lsqr.jl:91
+    btol = s if btol is None else btol
+    conlim = (1.0 / s if s else 0.0) if conlim is None else conlim        # src/lsqr.jl:92
+    return _lsq(lib().b200_lsqr_solve, "resnorm", x, A, b, damp, atol, btol, conlim, maxiter, log, verbose,
+                check_every, "lsqr")
+
+
+def lsqr(A, b, **kw):
+    """lsqr(A, b; kwargs...) = lsqr!(zerox(A, b), A, b; kwargs...) -- src/lsqr.jl:8."""
+    _check_operator(A)
+    n = A.shape[1] if A.ctx.world == 1 else A.m_local
+    x = DeviceArray.zeros(A.ctx, n, A.dtype) if is_device(b) else np.zeros(n, dtype=A.dtype)
+    return lsqr_(x, A, b, **kw)
+
+
+def lsmr_(x, A, b, *, atol=1e-6, btol=1e-6, conlim=1e8, maxiter=None, lam=0.0, log=False, verbose=False,
+          check_every=0):
+    """lsmr!(x, A, b; atol, btol, conlim, maxiter, λ, verbose, log) -- reference src/lsmr.jl:67-82, 88-287
+    (`λ` is spelled `lam`).  The work vectors v, h, hbar of src/lsmr.jl:78 are device scratch of the engine."""
+    return _lsq(lib().b200_lsmr_solve, None, x, A, b, lam, atol, btol, conlim, maxiter, log, verbose, check_every,
+                "lsmr")
+
+
+def lsmr(A, b, **kw):
+    """lsmr(A, b; kwargs...) = lsmr!(zerox(A, b), A, b; kwargs...) -- src/lsmr.jl:10."""
+    _check_operator(A)
+    n = A.shape[1] if A.ctx.world == 1 else A.m_local
+    x = DeviceArray.zeros(A.ctx, n, A.dtype) if is_device(b) else np.zeros(n, dtype=A.dtype)
+    return lsmr_(x, A, b, **kw)
+
+
+def idrs_(x, A, b, *, s=8, Pl=None, abstol=0.0, reltol=None, maxiter=None, log=False, smoothing=False, verbose=False,
+          P=None, rng=None, check_every=0):
+    """idrs!(x, A, b; s, Pl, abstol, reltol, maxiter, log, smoothing, verbose) -- reference src/idrs.jl:49-64.
+    The reference draws the shadow space with rand!(copy(C)) (src/idrs.jl:132); here the draw happens on the host
+    (numpy Generator `rng`) unless `P` (n x s) is given."""
+    _check_operator(A)
+    if reltol is None:
+        reltol = math.sqrt(_eps(A.dtype))                     # src/idrs.jl:53
+    if maxiter is None:
+        maxiter = A.size(2)                                   # src/idrs.jl:54
+    if P is None:
+        rng = rng or np.random.default_rng()
+        P = np.asfortranarray(rng.random((A.m_local, int(s))).astype(A.dtype))
+    Pd = P if is_device(P) else DeviceArray.from_numpy(A.ctx, np.asfortranarray(P, dtype=A.dtype))
+    if Pd.shape[0] != A.m_local or Pd.shape[1] != int(s):
+        raise ValueError("P must be n x s")
+    opts = _lib.IdrsOpts(abstol, reltol, int(maxiter), int(s), int(bool(smoothing)), precond_to_c(Pl, A),
+                         as_device_ptr(Pd), int(Pd.shape[0]), int(check_every), 0)
+    res = _lib.Result()
+    cap = int(maxiter) if log else 0                          # reserve!(history, :resnorm, maxiter)  :60
+    resnorm = np.zeros(max(cap, 1), dtype=np.float64)
+    st = _Staged(A, x, b)
+    check(lib().b200_idrs_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
+                                C.byref(res), resnorm.ctypes.data_as(C.c_void_p) if log else None, cap))
+    st.finish()
+    if verbose:
+        print("=== idrs ===\niter\tstep\tresnorm")
+        for i, r in enumerate(resnorm[: res.n_resnorm], start=1):
+            print(f"{i:3d}\t{1 + (i - 1) % (int(s) + 1):3d}\t{r:1.2e}")
+        print()
+    idrs_.last_result = res
+    return (x, _history(res, resnorm, abstol, reltol, log)) if log else x
+
+
+def idrs(A, b, **kw):
+    """idrs(A, b; kwargs...) = idrs!(zerox(A, b), A, b; kwargs...) -- src/idrs.jl:11."""
+    _check_operator(A)
+    x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
+    return idrs_(x, A, b, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
 # LOBPCG  (reference src/lobpcg.jl:787-839, 865-893)
 # ------------------------------------------------------------------------------------------------
 @dataclass

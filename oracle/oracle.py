@@ -1295,7 +1295,7 @@ def lsmr_(x, A, b, *, atol=1e-6, btol=1e-6, conlim=1e8, maxiter=None, lam=0.0, l
     tautildeold = thetatilde = zeta = d = Tr(0)                         # :141-144
     normA2 = alpha * alpha                                              # :148
     maxrbar = Tr(0)                                                     # :149
-    minrbar = 1e100                                                     # :150
+    minrbar = np.float64(1e100)                                         # :150 (a Float64 literal: promotes, as in Julia)
     normb = beta                                                        # :153
     istop = 0
     normAr = alpha * beta                                               # :156
