@@ -7,13 +7,15 @@
 # whose signature table tests/test_abi_and_host.py checks against include/b200krylov.h).
 #
 # Keyword names, defaults and return shapes are the reference's: src/cg.jl:209-217, src/chebyshev.jl:131-139,
-# src/gmres.jl:184-194, src/minres.jl:200-207, src/bicgstabl.jl:181-188, src/lobpcg.jl:827-829.
+# src/gmres.jl:184-194, src/minres.jl:200-207, src/bicgstabl.jl:181-188, src/lobpcg.jl:827-829, and for the
+# SURVEY section 8(f) widening src/qmr.jl:262-272, src/lsqr.jl:66-69,90-94, src/lsmr.jl:67-70,88-92, src/idrs.jl:49-56.
 module B200Krylov
 
 using SparseArrays, LinearAlgebra
 import IterativeSolvers
-import IterativeSolvers: cg!, chebyshev!, gmres!, minres!, bicgstabl!, lobpcg, ConvergenceHistory, Identity,
-                         ClassicalGramSchmidt, ModifiedGramSchmidt, DGKS, OrthogonalizationMethod, LOBPCGResults
+import IterativeSolvers: cg!, chebyshev!, gmres!, minres!, bicgstabl!, lobpcg, qmr!, lsqr!, lsmr!, idrs!,
+                         ConvergenceHistory, Identity, ClassicalGramSchmidt, ModifiedGramSchmidt, DGKS,
+                         OrthogonalizationMethod, LOBPCGResults
 import LinearAlgebra: mul!, ldiv!
 
 const LIB = "libb200krylov.so"
@@ -85,20 +87,32 @@ Base.fill!(x::B200Vector{T}, a::Number) where {T} =
 mutable struct B200CSR{T<:BlasReal}
     h::Ptr{Cvoid}
     ctx::Ctx
-    n::Int
+    n::Int                                  # size(A, 1)
+    ncols::Int                              # size(A, 2)  (rectangular operators: lsqr!/lsmr!)
+    adj::Union{Nothing,B200CSR{T}}          # adjoint(A), built on first use
 end
 # stands where a SparseMatrixCSC is passed today (src/cg.jl:54, src/gmres.jl:287, ...): CSC -> device CSR int32
 function B200CSR(A::SparseMatrixCSC{T,Ti}; ctx::Ctx = default_ctx()) where {T<:BlasReal,Ti<:Union{Int32,Int64}}
-    size(A, 1) == size(A, 2) || throw(DimensionMismatch("square operators only"))
     r = Ref{Ptr{Cvoid}}()
     check(ccall((:b200_csr_from_csc, LIB), Cint,
                 (Ptr{Cvoid}, Int64, Int64, Ptr{Ti}, Ptr{Ti}, Ptr{T}, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
                 ctx.h, size(A, 1), size(A, 2), A.colptr, A.rowval, A.nzval, sizeof(Ti), dtype_code(T), 1, r))
-    finalizer(a -> ccall((:b200_csr_destroy, LIB), Cint, (Ptr{Cvoid},), a.h), B200CSR{T}(r[], ctx, size(A, 1)))
+    finalizer(a -> ccall((:b200_csr_destroy, LIB), Cint, (Ptr{Cvoid},), a.h),
+              B200CSR{T}(r[], ctx, size(A, 1), size(A, 2), nothing))
 end
-Base.size(A::B200CSR) = (A.n, A.n)
-Base.size(A::B200CSR, d::Integer) = d <= 2 ? A.n : 1
+Base.size(A::B200CSR) = (A.n, A.ncols)
+Base.size(A::B200CSR, d::Integer) = d == 1 ? A.n : (d == 2 ? A.ncols : 1)
 Base.eltype(::B200CSR{T}) where {T} = T
+# adjoint(A) as a device operator of its own (what LanczosDecomp stores, src/qmr.jl:54; lsqr src/lsqr.jl:128)
+function Base.adjoint(A::B200CSR{T}) where {T}
+    if A.adj === nothing
+        r = Ref{Ptr{Cvoid}}()
+        check(ccall((:b200_csr_transpose, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ref{Ptr{Cvoid}}), A.ctx.h, A.h, r))
+        A.adj = finalizer(a -> ccall((:b200_csr_destroy, LIB), Cint, (Ptr{Cvoid},), a.h),
+                          B200CSR{T}(r[], A.ctx, A.ncols, A.n, nothing))
+    end
+    A.adj
+end
 mul!(y::B200Vector{T}, A::B200CSR{T}, x::B200Vector{T}) where {T} =
     (check(ccall((:b200_spmv, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), A.ctx.h, A.h, x.p, y.p)); y)
 
@@ -158,6 +172,21 @@ end
 mutable struct LobpcgResult
     iterations::Int64; converged::Int32; status::Int32
     LobpcgResult() = new(0, 0, 0)
+end
+struct QmrOpts
+    abstol::Float64; reltol::Float64; maxiter::Int64; initially_zero::Int32; check_every::Int32
+end
+struct LsqOpts
+    damp::Float64; atol::Float64; btol::Float64; conlim::Float64; maxiter::Int64; check_every::Int32; reserved::Int32
+end
+mutable struct LsqResult
+    iters::Int64; mvps::Int64; mtvps::Int64; isconverged::Int32; istop::Int32; status::Int32; reserved::Int32
+    n_hist::Int64; hist_stride::Int64; atol::Float64; btol::Float64; ctol::Float64
+    LsqResult() = new(0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0.0, 0.0)
+end
+struct IdrsOpts
+    abstol::Float64; reltol::Float64; maxiter::Int64; s::Int32; smoothing::Int32; Pl::Precond
+    P::Ptr{Cvoid}; ldp::Int64; check_every::Int32; reserved::Int32
 end
 orth_code(::ModifiedGramSchmidt) = Int32(0); orth_code(::ClassicalGramSchmidt) = Int32(1); orth_code(::DGKS) = Int32(2)   # B200_ORTH_*
 
@@ -304,6 +333,81 @@ function lobpcg(A::B200CSR{T}, largest::Bool, X0::Matrix{T}; P = nothing, tol::R
     check(status)
     X = reshape(Array(Xd), n, bs)
     LOBPCGResults(T.(λ), X, T(tol), T.(rn), Int(res.iterations), Int(maxiter), res.converged != 0, nothing)
+end
+
+# ------------------------------------------------------------------------------------------- qmr!  (SURVEY 8f item 4)
+function qmr!(x::Vector{T}, A::B200CSR{T}, b::Vector{T};
+              abstol::Real = zero(T), reltol::Real = sqrt(eps(T)), maxiter::Int = size(A, 2), lookahead::Bool = false,
+              log::Bool = false, initially_zero::Bool = false, verbose::Bool = false) where {T}
+    res = Result(); hist = Vector{Float64}(undef, log ? maxiter : 0)
+    o = QmrOpts(abstol, reltol, maxiter, initially_zero, 0)
+    At = adjoint(A)
+    staged(A, x, b) do xd, bd
+        check(ccall((:b200_qmr_solve, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{QmrOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                    A.ctx.h, A.h, At.h, xd.p, bd.p, o, res, hist, length(hist)))
+    end
+    if log
+        h = history(res, hist, abstol, reltol)
+        h.mvps = 0                                            # nextiter!(history) without mvps, src/qmr.jl:285
+        return x, h
+    end
+    x
+end
+
+# ------------------------------------------------------------------------------------------- lsqr! / lsmr!
+function ls_history(res::LsqResult, hist::Vector{Float64}, first::Union{Nothing,Symbol})
+    h = ConvergenceHistory(partial = false)
+    h[:atol] = res.atol; h[:btol] = res.btol; h[:ctol] = res.ctol
+    h.mvps = res.mvps; h.mtvps = res.mtvps; h.iters = res.iters; h.isconverged = res.isconverged != 0
+    sd = res.hist_stride; k = res.n_hist
+    first === nothing || (h.data[first] = hist[1:k])
+    h.data[:anorm] = hist[sd+1:sd+k]; h.data[:rnorm] = hist[2sd+1:2sd+k]; h.data[:cnorm] = hist[3sd+1:3sd+k]
+    h
+end
+function ls_solve(sym::Symbol, first, x::Vector{T}, A::B200CSR{T}, b::Vector{T}, o::LsqOpts, maxiter::Int, log::Bool) where {T}
+    length(x) == size(A, 2) || error("x should be of length ", size(A, 2))     # src/lsqr.jl:99
+    length(b) == size(A, 1) || error("b should be of length ", size(A, 1))     # src/lsqr.jl:100
+    res = LsqResult(); hist = Vector{Float64}(undef, 4 * max(maxiter, 1))
+    At = adjoint(A)
+    xd, bd = B200Vector(A.ctx, x), B200Vector(A.ctx, b)
+    status = sym === :lsqr ?
+        ccall((:b200_lsqr_solve, LIB), Cint,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{LsqOpts}, Ref{LsqResult}, Ptr{Float64}, Int64),
+              A.ctx.h, A.h, At.h, xd.p, bd.p, o, res, hist, maxiter) :
+        ccall((:b200_lsmr_solve, LIB), Cint,
+              (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{LsqOpts}, Ref{LsqResult}, Ptr{Float64}, Int64),
+              A.ctx.h, A.h, At.h, xd.p, bd.p, o, res, hist, maxiter)
+    status == -1 && res.status == -1 && error("Initial guess for x must be finite")   # src/lsqr.jl:102-104
+    check(status)
+    copyto!(x, Array(xd))
+    log ? (x, ls_history(res, hist, first)) : x
+end
+function lsqr!(x::Vector{T}, A::B200CSR{T}, b::Vector{T};
+               maxiter::Int = maximum(size(A)), log::Bool = false, damp = 0, atol = sqrt(eps(T)), btol = sqrt(eps(T)),
+               conlim = one(T) / sqrt(eps(T)), verbose::Bool = false) where {T}
+    ls_solve(:lsqr, :resnorm, x, A, b, LsqOpts(damp, atol, btol, conlim, maxiter, 0, 0), maxiter, log)
+end
+function lsmr!(x::Vector{T}, A::B200CSR{T}, b::Vector{T};
+               maxiter::Int = maximum(size(A)), log::Bool = false, atol::Number = 1e-6, btol::Number = 1e-6,
+               conlim::Number = 1e8, λ::Number = 0, verbose::Bool = false) where {T}
+    ls_solve(:lsmr, nothing, x, A, b, LsqOpts(λ, atol, btol, conlim, maxiter, 0, 0), maxiter, log)
+end
+
+# ------------------------------------------------------------------------------------------- idrs!
+function idrs!(x::Vector{T}, A::B200CSR{T}, b::Vector{T};
+               s = 8, Pl = Identity(), abstol::Real = zero(T), reltol::Real = sqrt(eps(T)), maxiter = size(A, 2),
+               log::Bool = false, smoothing::Bool = false, verbose::Bool = false) where {T}
+    res = Result(); hist = Vector{Float64}(undef, log ? maxiter : 0)
+    n = length(b)
+    P = B200Vector(A.ctx, rand(T, n * s))                     # P = [rand!(copy(C)) for k in 1:s]  src/idrs.jl:132
+    o = IdrsOpts(abstol, reltol, maxiter, s, smoothing, prec(Pl), P.p, n, 0, 0)
+    GC.@preserve P staged(A, x, b) do xd, bd
+        check(ccall((:b200_idrs_solve, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{IdrsOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                    A.ctx.h, A.h, xd.p, bd.p, o, res, hist, length(hist)))
+    end
+    log ? (x, history(res, hist, abstol, reltol)) : x
 end
 
 end # module

@@ -22,7 +22,7 @@
 // Everything in the *_core.h headers is plain C++ (B200_HD = __host__ __device__ under nvcc, inline
 // otherwise), so that tests/hostsim -- TEST INFRASTRUCTURE, never linked into libb200krylov.so -- can run
 // the very same functors, scalar sections and driver loops on the CPU with a serial backend and compare
-// them with the oracle.  The product library instantiates the drivers with the CUDA backend only: there
+// them with the CPU checker.  The product library instantiates the drivers with the CUDA backend only: there
 // is no CPU fallback in it.
 #pragma once
 #include <math.h>
@@ -48,7 +48,7 @@ B200_HD double eps_of() {
 }
 
 // LinearAlgebra.givensAlgorithm(f, g) for real arguments -> (c, s, r) with [c s; -s c][f; g] = [r; 0]
-// (same convention as the GMRES / MINRES engines, pinned against reference test/hessenberg.jl in the oracle)
+// (same convention as the GMRES / MINRES engines, pinned against the fixtures of reference test/hessenberg.jl by the test-suite)
 B200_HD void givens_real(double f, double g, double &c, double &s, double &r) {
   if (g == 0.0) { c = 1.0; s = 0.0; r = f; return; }
   if (f == 0.0) { c = 0.0; s = 1.0; r = g; return; }

@@ -192,6 +192,11 @@ class B200CSR:
         self._adjoint = At
         return self
 
+    def set_adjoint_self(self):
+        """for Hermitian operators: adjoint(A) is A (no second copy of the matrix)."""
+        self._adjoint = self
+        return self
+
     def size(self, d=None):
         return self.shape if d is None else self.shape[d - 1]
 

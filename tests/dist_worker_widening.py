@@ -1,0 +1,76 @@
+"""Worker for the multi-GPU test of the section 8(f) item 4 solvers; launched by tests/test_zz_gpu_widening.py through
+torchrun (one process per GPU, NCCL).  Every rank owns a z-slab of laplace_matrix(Float64, N, 3) (symmetric, so the
+adjoint operator is the operator itself); the row-partitioned qmr!/idrs!/lsqr!/lsmr! -- every pass reduction
+allreduced, scalar sections run after the allreduce -- must reproduce the single-GPU runs (rank 0, global matrix)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 24
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import iterativesolvers_jl_b200 as isb
+    ctx = isb.Context.distributed(local)
+    n = N ** 3
+    cuts = [int(round(N * r / world)) for r in range(world + 1)]
+    offs = np.array([c * N * N for c in cuts], dtype=np.int64)
+    lo, m = int(offs[rank]), int(offs[rank + 1] - offs[rank])
+    rng = np.random.default_rng(1234321)
+    b_global = rng.standard_normal(n)
+    b_global /= np.linalg.norm(b_global)
+    P_global = np.asfortranarray(np.random.default_rng(7).random((n, 4)))
+    plan = isb.HaloPlan(rank, world, offs).scan_laplacian(N, 3).exchange()
+    A = isb.B200CSR.laplacian(N, 3, np.float64, lo, m, plan, ctx).set_adjoint_self()
+    b_loc = b_global[lo:lo + m].copy()
+
+    def run(Aop, b, P, size):
+        out = {}
+        out["qmr"] = isb.qmr_(np.zeros(size), Aop, b, initially_zero=True, log=True, reltol=1e-9)
+        out["idrs"] = isb.idrs_(np.zeros(size), Aop, b, s=4, P=P, log=True, reltol=1e-9)
+        out["idrs_s"] = isb.idrs_(np.zeros(size), Aop, b, s=4, P=P, log=True, reltol=1e-9, smoothing=True,
+                                  Pl=isb.JacobiPrec(Aop.diag(), Aop.ctx))
+        out["lsqr"] = isb.lsqr_(np.zeros(size), Aop, b, log=True, maxiter=25, atol=0.0, btol=0.0, conlim=0.0)
+        out["lsmr"] = isb.lsmr_(np.zeros(size), Aop, b, log=True, maxiter=25, atol=0.0, btol=0.0, conlim=0.0)
+        return out
+
+    mine = run(A, b_loc, np.asfortranarray(P_global[lo:lo + m]), m)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, {k: v[0] for k, v in mine.items()})
+    if rank == 0:
+        ctx1 = isb.Context(local)
+        cp, rv, nz, shape = isb.laplace_matrix(np.float64, N, 3, base=1)
+        Ag = isb.B200CSR.from_csc_arrays(cp, rv, nz, shape, base=1, ctx=ctx1)
+        ref = run(Ag, b_global, P_global, n)
+        for name in ("qmr", "idrs", "idrs_s"):
+            xd = np.concatenate([g[name] for g in gathered])
+            (xs, hs), h = ref[name], mine[name][1]
+            assert h.isconverged and hs.isconverged and h.iters == hs.iters, (name, h.iters, hs.iters)
+            assert np.max(np.abs(h["resnorm"] - hs["resnorm"]) / hs["resnorm"][0]) <= 1e-8, name
+            assert np.linalg.norm(xd - xs) <= 1e-8 * np.linalg.norm(xs), name
+        for name in ("lsqr", "lsmr"):
+            xd = np.concatenate([g[name] for g in gathered])
+            (xs, hs), h = ref[name], mine[name][1]
+            assert h.iters == hs.iters == 25 and h["istop"] == hs["istop"] == 7
+            assert (h.mvps, h.mtvps) == (hs.mvps, hs.mtvps)
+            for key in ("anorm", "rnorm", "cnorm"):
+                assert np.max(np.abs(h[key][:8] - hs[key][:8])) <= 1e-9 * np.max(np.abs(hs[key][:8])), (name, key)
+            assert np.linalg.norm(xd - xs) <= 1e-6 * np.linalg.norm(xs), name
+        print(f"qmr/idrs/lsqr/lsmr partitioned == single: world={world} N={N} "
+              f"iters {mine['qmr'][1].iters}/{mine['idrs'][1].iters}/{mine['idrs_s'][1].iters}")
+        print("DIST_WIDENING_OK")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -220,7 +220,8 @@ def test_julia_binding_source_uses_only_declared_symbols_and_matching_structs():
 
     for jl, ct in (("Precond", L.Precond), ("Result", L.Result), ("CgOpts", L.CgOpts), ("GmresOpts", L.GmresOpts),
                    ("MinresOpts", L.MinresOpts), ("BicgstablOpts", L.BicgstablOpts), ("LobpcgOpts", L.LobpcgOpts),
-                   ("LobpcgResult", L.LobpcgResult)):
+                   ("LobpcgResult", L.LobpcgResult), ("QmrOpts", L.QmrOpts), ("LsqOpts", L.LsqOpts),
+                   ("LsqResult", L.LsqResult), ("IdrsOpts", L.IdrsOpts)):
         assert julia_fields(jl) == [f[0] for f in ct._fields_], jl
 
 
@@ -235,3 +236,32 @@ def test_committed_ncu_traffic_matches_the_algorithmic_bytes():
     assert t["dram_bytes_per_launch"] == t["dram_bytes_read"] + t["dram_bytes_write"]
     assert abs(t["dram_bytes_per_launch"] - algorithmic) <= 0.02 * algorithmic
     assert os.path.exists(os.path.join(ROOT, t["source"].split(" ")[0]))
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """Every struct the host mirror passes by pointer has, field by field, the offset and the total size that gcc
+    gives the declaration in include/b200krylov.h (the header is compiled, not parsed)."""
+    from importlib import import_module
+    L = import_module("iterativesolvers_jl_b200")._lib
+    pairs = [("b200_precond", L.Precond), ("b200_result", L.Result), ("b200_cg_opts", L.CgOpts),
+             ("b200_gmres_opts", L.GmresOpts), ("b200_minres_opts", L.MinresOpts),
+             ("b200_bicgstabl_opts", L.BicgstablOpts), ("b200_lobpcg_opts", L.LobpcgOpts),
+             ("b200_lobpcg_result", L.LobpcgResult), ("b200_qmr_opts", L.QmrOpts), ("b200_lsq_opts", L.LsqOpts),
+             ("b200_lsq_result", L.LsqResult), ("b200_idrs_opts", L.IdrsOpts)]
+    lines = ['#include <stddef.h>', '#include <stdio.h>', f'#include "{os.path.join(ROOT, "include", "b200krylov.h")}"',
+             'int main(void) {']
+    for cname, ct in pairs:
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, stdout=subprocess.PIPE, text=True).stdout.split("\n")
+    got = {tuple(l.split()[:2]): int(l.split()[2]) for l in out if l.strip()}
+    for cname, ct in pairs:
+        assert got[(cname, "size")] == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert got[(cname, fname)] == getattr(ct, fname).offset, (cname, fname)

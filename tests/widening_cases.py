@@ -1,0 +1,204 @@
+"""Engine-vs-oracle cases for qmr!/lsqr!/lsmr!/idrs!, shared by
+  * tests/test_oracle_widening.py  -- the engines on the serial test backend (tests/hostsim), CPU, and
+  * tests/test_zz_gpu_widening.py  -- the same engines through the C ABI on the GPU (-m gpu).
+A `runner` hides which of the two executes the engine:
+    runner.qmr(x0, A, b, **kw)            -> x, R   (R.iters, R.converged, R.breakdown, R.hist, R.tol, R.nprods)
+    runner.lsqr / runner.lsmr(x0, A, b, **kw) -> x, R   (R.iters, R.istop, R.converged, R.mvps, R.mtvps, R.hist{...},
+                                                        R.ctol, R.early, R.bad_x)
+    runner.idrs(x0, A, b, P, diag=None, **kw) -> x, R
+A is a scipy sparse matrix; x0 is updated in place and returned.
+"""
+import math
+
+import numpy as np
+import scipy.sparse as sp
+
+
+def sol_matrix(m, n):
+    """reference test/lsqr.jl:25-29 / test/lsmr.jl:59-63."""
+    mn = min(m, n)
+    I = np.r_[np.arange(1, mn), np.arange(mn)]
+    J = np.r_[np.arange(mn - 1), np.arange(mn)]
+    V = np.r_[np.arange(1.0, mn), np.arange(1.0, mn + 1)]
+    return sp.coo_matrix((V, (I, J)), shape=(m, n)).tocsc()
+
+
+def tridiag(T):
+    return np.array([[2, -1, 0], [-1, 2, -1], [0, -1, 2]], dtype=T)
+
+
+def _systems():
+    yield 10, sp.random(10, 10, 0.5, random_state=3, format="csc") + 10 * sp.eye(10, format="csc")
+    yield 200, sp.random(200, 200, 0.05, random_state=4, format="csc") + 8 * sp.eye(200, format="csc")
+    yield 1000, sp.random(1000, 1000, 0.01, random_state=5, format="csc") + 6 * sp.eye(1000, format="csc")
+
+
+def case_qmr_matches_oracle(oracle, runners, dtype, tol):
+    rng = np.random.default_rng(7)
+    for n, M in _systems():
+        A = M.astype(dtype)
+        O = oracle.CSC.from_scipy(A.tocsc(), base=1)
+        b, x0 = rng.random(n).astype(dtype), rng.random(n).astype(dtype)
+        for init_zero in (False, True):
+            start = np.zeros(n, dtype) if init_zero else x0
+            xo, ho = oracle.qmr_(start.copy(), O, b, log=True, initially_zero=init_zero)
+            for run in runners:
+                xs, hs = run.qmr(start.copy(), A, b, initially_zero=init_zero, check_every=3)
+                assert hs.iters == ho.iters and hs.converged == ho.isconverged and not hs.breakdown
+                assert hs.nprods == 2 * ho.iters + (0 if init_zero else 1)
+                assert np.max(np.abs(hs.hist - ho["resnorm"])) <= tol * ho["resnorm"][0]
+                assert np.linalg.norm(xs - xo) <= tol * np.linalg.norm(xo)
+                assert abs(hs.tol - ho["tol"]) <= 1e-6 * ho["tol"]
+
+
+def case_qmr_advection_maxiter_breakdown(oracle, runners):
+    """a non-symmetric problem that needs ~100 Lanczos steps; maxiter; zero iterations; exact breakdown."""
+    M, b = oracle.advection_dominated(8, 50.0)
+    O = oracle.CSC.from_scipy(M.tocsc(), base=1)
+    xo, ho = oracle.qmr(O, b, log=True, reltol=1e-8)
+    assert ho.isconverged and ho.iters > 40
+    rng = np.random.default_rng(1)
+    A5, b5 = sp.csr_matrix(rng.random((5, 5))), rng.random(5)
+    # documented deviation: at delta == 0 the reference updates x with the wrong Lanczos vector (x stays 0 for A = I)
+    xi, hi = oracle.qmr(np.eye(4), np.ones(4), log=True)
+    assert np.all(xi == 0) and hi.iters == 1 and hi["resnorm"][0] == 0
+    for run in runners:
+        xs, hs = run.qmr(np.zeros_like(b), M, b, initially_zero=True, reltol=1e-8)
+        assert abs(hs.iters - ho.iters) <= 2 and hs.converged
+        k = min(20, ho.iters)
+        assert np.max(np.abs(hs.hist[:k] - ho["resnorm"][:k]) / ho["resnorm"][:k]) <= 1e-9
+        # resnorm is the quasi-residual; the true residuals of engine and oracle must agree with each other
+        assert np.linalg.norm(M @ xs - b) <= 3 * np.linalg.norm(M @ xo - b) <= 1e-5 * np.linalg.norm(b)
+        assert np.linalg.norm(xs - xo) <= 1e-6 * np.linalg.norm(xo)
+        xs, hs = run.qmr(np.zeros(5), A5, b5, initially_zero=True, maxiter=2)                    # test/qmr.jl:38-42
+        assert hs.iters == 2 and len(hs.hist) == 2
+        xs, hs = run.qmr(np.zeros(4), sp.eye(4, format="csr"), np.zeros(4), initially_zero=True)  # zero rhs
+        assert hs.iters == 0 and np.all(xs == 0)
+        xs, hs = run.qmr(np.zeros(4), sp.eye(4, format="csr"), np.ones(4), initially_zero=True)
+        assert hs.breakdown and hs.iters == 1 and hs.hist[0] == 0 and np.allclose(xs, 1.0)
+        for T in (np.float32, np.float64):                                                        # test/qmr.jl:44-66
+            A = sp.csr_matrix(tridiag(T))
+            bb = np.ones(3, dtype=T)
+            x0 = np.linalg.solve(A.toarray().astype(np.float64), bb.astype(np.float64)).astype(T)
+            pert = (10 * math.sqrt(np.finfo(T).eps) * np.array([-1, 1, -1])).astype(T)
+            xs, hs = run.qmr(x0 + pert, A, bb)
+            assert 2 <= hs.iters <= 3
+            r0 = np.linalg.norm(A @ (x0 + pert) - bb)
+            xs, hs = run.qmr(x0 + pert, A, bb, abstol=2 * r0, reltol=0.0)
+            assert hs.iters == 0
+
+
+LS_CASES = [
+    ("tall", lambda: sp.random(300, 120, 0.05, random_state=1, format="csc"), {}),
+    ("wide", lambda: sp.random(120, 300, 0.05, random_state=2, format="csc"), {}),
+    ("sol20x10", lambda: sol_matrix(20, 10), dict(atol=1e-7, btol=1e-7, conlim=1e10, maxiter=100)),
+    ("sol10x10", lambda: sol_matrix(10, 10), dict(atol=1e-7, btol=1e-7, conlim=1e10, maxiter=100)),
+]
+
+
+def case_lsqr_lsmr_match_oracle(oracle, runners, solver, dtype):
+    """The Golub-Kahan recurrences amplify rounding differences exponentially once the process has converged
+    (measured: 1e-16 -> 1e-2 between iterations 10 and 18 on `tall`, identically between two summation orders of
+    the SAME code), so histories are compared over the first 8 iterations (1e-9 of their scale in fp64) and the
+    solutions at the accuracy the stopping rule delivers; counters, stopping rule and flags must agree (+-2 iterations)."""
+    rng = np.random.default_rng(5)
+    orc = getattr(oracle, solver + "_")
+    damp_kw = "damp" if solver == "lsqr" else "lam"
+    first = "resnorm" if solver == "lsqr" else None
+    htol, xtol = (1e-9, 2e-6) if dtype == np.float64 else (2e-3, 2e-2)
+    for name, mk, kw in LS_CASES:
+        A = mk().astype(dtype)
+        m, n = A.shape
+        O = oracle.CSC.from_scipy(A.tocsc(), base=1)
+        b, x0 = rng.random(m).astype(dtype), rng.random(n).astype(dtype)
+        for extra in ({}, {damp_kw: 0.1}):
+            xo, ho = orc(x0.copy(), O, b, log=True, **kw, **extra)
+            for run in runners:
+                xs, hs = getattr(run, solver)(x0.copy(), A, b, check_every=5, **kw, **extra)
+                assert abs(hs.iters - ho.iters) <= 2, (name, extra)
+                assert hs.converged == ho.isconverged
+                if hs.iters == ho.iters:
+                    assert hs.istop == ho["istop"], (name, extra)
+                assert hs.mvps - hs.iters == ho.mvps - ho.iters and hs.mtvps - hs.iters == ho.mtvps - ho.iters
+                k = min(8 if dtype == np.float64 else 5, ho.iters, hs.iters)
+                for key in ([first] if first else []) + ["anorm", "rnorm", "cnorm"]:
+                    ref = ho[key][:k]
+                    assert np.max(np.abs(hs.hist[key][:k] - ref)) <= htol * np.max(np.abs(ref)), (name, key)
+                assert np.linalg.norm(xs - xo) <= xtol * np.linalg.norm(xo), (name, extra)
+                assert abs(hs.ctol - ho["ctol"]) <= 1e-6 * ho["ctol"]
+
+
+def case_lsqr_lsmr_edge_cases(oracle, runners):
+    A = sp.csr_matrix(np.eye(3))
+    x0 = np.array([1.0, 2.0, 3.0])
+    xo, ho = oracle.lsqr_(x0.copy(), np.eye(3), x0.copy(), log=True)
+    assert ho.iters == 0 and not ho.isconverged and ho.mtvps == 0
+    rng = np.random.default_rng(2)
+    M = sp.random(40, 30, 0.3, random_state=3, format="csr")
+    b = rng.random(40)
+    for run in runners:
+        # initial guess not finite (src/lsqr.jl:102-104)
+        xs, hs = run.lsqr(np.array([0.0, np.inf, 0.0]), A, np.ones(3))
+        assert hs.bad_x and hs.iters == 0
+        # b - A x == 0: lsqr returns at once (src/lsqr.jl:141-144), history empty, not converged
+        xs, hs = run.lsqr(x0.copy(), A, x0.copy())
+        assert hs.iters == 0 and not hs.converged and np.array_equal(xs, x0) and hs.mtvps == 0
+        # lsmr: the same input divides by zero in the reference (NaN iterates); the engine takes the announced exit
+        xs, hs = run.lsmr(x0.copy(), A, x0.copy())
+        assert hs.iters == 0 and hs.converged and np.array_equal(xs, x0) and (hs.mvps, hs.mtvps) == (1, 1)
+        # maxiter
+        for solver in ("lsqr", "lsmr"):
+            xs, hs = getattr(run, solver)(np.zeros(30), M, b, maxiter=3, atol=0.0, btol=0.0, conlim=0.0)
+            xo, ho = getattr(oracle, solver + "_")(np.zeros(30), oracle.CSC.from_scipy(M.tocsc()), b, maxiter=3,
+                                                    atol=0.0, btol=0.0, conlim=0.0, log=True)
+            assert hs.iters == ho.iters == 3 and hs.istop == ho["istop"] == 7 and hs.converged == ho.isconverged
+            assert np.linalg.norm(xs - xo) <= 1e-12 * np.linalg.norm(xo)
+
+
+def case_idrs_matches_oracle(oracle, runners, dtype, tol):
+    rng = np.random.default_rng(11)
+    for n, M in _systems():
+        A = M.astype(dtype)
+        O = oracle.CSC.from_scipy(A.tocsc(), base=1)
+        b, x0 = rng.random(n).astype(dtype), rng.random(n).astype(dtype)
+        for s in (1, 2, 4, 8):
+            P = np.asfortranarray(rng.random((n, s)).astype(dtype))
+            for smoothing in (False, True):
+                for jac in (False, True):
+                    d = A.diagonal().astype(dtype)
+                    xo, ho = oracle.idrs_(x0.copy(), O, b, s=s, P=[P[:, j].copy() for j in range(s)], log=True,
+                                          smoothing=smoothing, Pl=oracle.JacobiPrec(d) if jac else None)
+                    for run in runners:
+                        xs, hs = run.idrs(x0.copy(), A, b, P, smoothing=smoothing, diag=d if jac else None,
+                                          check_every=3)
+                        assert hs.iters == ho.iters and hs.converged == ho.isconverged and not hs.breakdown
+                        # fp32: IDR(s)'s intermediate residual peaks differ by up to ~1 % between fp32 and fp64 scalars
+                        htol = tol if dtype == np.float64 else 2e-2
+                        assert np.max(np.abs(hs.hist - ho["resnorm"])) <= htol * ho["resnorm"][0], (n, s, smoothing, jac)
+                        assert np.linalg.norm(xs - xo) <= tol * np.linalg.norm(xo), (n, s, smoothing, jac)
+
+
+def case_idrs_s16_maxiter_zero_iterations(oracle, runners):
+    rng = np.random.default_rng(3)
+    M, b = oracle.advection_dominated(8, 50.0)
+    n = M.shape[0]
+    O = oracle.CSC.from_scipy(M.tocsc(), base=1)
+    P = np.asfortranarray(rng.random((n, 16)))
+    xo, ho = oracle.idrs(O, b, s=16, P=[P[:, j].copy() for j in range(16)], log=True, reltol=1e-8)
+    assert ho.isconverged
+    A5, b5, P5 = sp.csr_matrix(rng.random((5, 5))), rng.random(5), rng.random((5, 8))
+    A = sp.csr_matrix(tridiag(np.float64))
+    bb = np.ones(3)
+    x0 = np.linalg.solve(A.toarray(), bb) + 10 * math.sqrt(np.finfo(np.float64).eps) * np.array([-1, 1, -1])
+    r0 = np.linalg.norm(A @ x0 - bb)
+    P3 = rng.random((3, 8))
+    for run in runners:
+        xs, hs = run.idrs(np.zeros(n), M, b, P, reltol=1e-8)
+        assert hs.converged and abs(hs.iters - ho.iters) <= 2
+        k = min(34, ho.iters, hs.iters)                      # two full cycles of 17 steps
+        assert np.max(np.abs(hs.hist[:k] - ho["resnorm"][:k]) / ho["resnorm"][:k]) <= 1e-7
+        assert np.linalg.norm(M @ xs - b) <= 1e-7 * np.linalg.norm(b)
+        xs, hs = run.idrs(np.zeros(5), A5, b5, P5, maxiter=2)                                     # test/idrs.jl:65-69
+        assert hs.iters == 2 and len(hs.hist) == 2
+        xs, hs = run.idrs(x0.copy(), A, bb, P3, abstol=2 * r0, reltol=0.0)                        # :100-104
+        assert hs.iters == 0 and hs.converged and np.array_equal(xs, x0)
