@@ -6,6 +6,8 @@
     minres    minres! on laplace_matrix(Float64, 256, 3), fixed maxiter
     bicgstabl bicgstabl!(l=2) on advection_dominated(N=256), fixed max_mv_products
     cg256     configs[1]: cg! on laplace_matrix(Float64, 256, 3)
+    widen     SURVEY 8(f) item 4: qmr!, lsqr!, lsmr!, idrs!(s=8) on laplace_matrix(Float64, N, 3), fixed iteration counts
+              (adjoint operator built by the device transpose)
 
 Each line is a JSON object with iterations/s, per-kernel-class CUDA-event times recorded inside the run
 (b200_ctx_profile_*), the algorithmic bytes and the achieved fraction of the measured
@@ -50,7 +52,7 @@ def prof_read(L, ctx):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["gmres", "lobpcg", "minres", "bicgstabl", "cg256"])
+    ap.add_argument("which", choices=["gmres", "lobpcg", "minres", "bicgstabl", "cg256", "widen"])
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--iters", type=int, default=None)
     ap.add_argument("--orth", default="cgs")
@@ -137,6 +139,59 @@ def main():
         out.update({"solver": args.which, "iters": h.niters, "seconds": dt, "iters_per_s": h.niters / dt,
                     "algorithmic_gb_per_iter": per_it / 1e9, "achieved_gbs": per_it * h.niters / dt / 1e9,
                     "profile": pr})
+    elif args.which == "widen":
+        A = isb.B200CSR.laplacian(N, 3, np.float64, ctx=ctx)
+        t0 = time.perf_counter()
+        At = A.adjoint()
+        ctx.sync()
+        out["transpose_seconds"] = time.perf_counter() - t0
+        b = rng.standard_normal(n)
+        b /= np.linalg.norm(b)
+        bd = isb.DeviceArray.from_numpy(ctx, b)
+        xd = isb.DeviceArray.zeros(ctx, n)
+        iters = args.iters or 100
+        V = 8
+        s_dim = 8
+        Pd = isb.DeviceArray.from_numpy(ctx, np.asfortranarray(rng.random((n, s_dim))))
+        spmv_b = nnz * 12 + (n + 1) * 4 + 2 * n * V
+        # IDR(s): vector passes of one cycle of s direction steps + the polynomial step (csrc/idrs_core.h)
+        cyc = (s_dim + 1) * n * V                                                         # D
+        for k in range(1, s_dim + 1):
+            cyc += (2 * (s_dim - k + 1) + 2) * n * V + spmv_b                             # V, S
+            if k == 1:
+                cyc += (1 + s_dim) * n * V                                                # new column of M
+            else:
+                cyc += 2 * n * V + (k - 2) * 7 * n * V + (6 + s_dim - k + 1) * n * V      # first dot, updates, last update
+            cyc += 6 * n * V                                                              # X
+        cyc += spmv_b + 2 * n * V + 5 * n * V                                             # S, O, X' (Identity)
+        per_it = {"qmr": 2 * spmv_b + 21 * n * V, "lsqr": 2 * spmv_b + 14 * n * V, "lsmr": 2 * spmv_b + 16 * n * V,
+                  "idrs": cyc / (s_dim + 1)}
+        res = {}
+        for name in ("qmr", "lsqr", "lsmr", "idrs"):
+            for rep in range(args.reps + 1):
+                L.b200_fill(ctx._h, n, 0.0, xd._p, 0)
+                if rep == 1:
+                    prof_reset(L, ctx)
+                ctx.sync()
+                t0 = time.perf_counter()
+                if name == "qmr":
+                    x, h = isb.qmr_(xd, A, bd, maxiter=iters, initially_zero=True, log=True, reltol=0.0)
+                elif name == "lsqr":
+                    x, h = isb.lsqr_(xd, A, bd, maxiter=iters, log=True, atol=0.0, btol=0.0, conlim=0.0)
+                elif name == "lsmr":
+                    x, h = isb.lsmr_(xd, A, bd, maxiter=iters, log=True, atol=0.0, btol=0.0, conlim=0.0)
+                else:
+                    x, h = isb.idrs_(xd, A, bd, s=s_dim, P=Pd, maxiter=iters, log=True, reltol=0.0)
+                ctx.sync()
+                dt = time.perf_counter() - t0
+            pr = prof_read(L, ctx)
+            key = "resnorm" if name in ("qmr", "idrs", "lsqr") else "rnorm"
+            res[name] = {"iters": h.iters, "seconds": dt, "iters_per_s": h.iters / dt,
+                         "algorithmic_gb_per_iter": per_it[name] / 1e9,
+                         "achieved_gbs": per_it[name] * h.iters / dt / 1e9,
+                         "frac_of_measured_peak": per_it[name] * h.iters / dt / 1e9 / pk,
+                         "first_last": [float(h[key][0]), float(h[key][-1])], "profile": pr}
+        out["solvers"] = res
     else:  # lobpcg
         bs = 16
         A = isb.B200CSR.laplacian(N, 3, np.float32, ctx=ctx)

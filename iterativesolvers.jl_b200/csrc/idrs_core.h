@@ -162,9 +162,9 @@ struct IdrsNewU {
 //   dot0, ndots: sums <P_{dot0+j}, G_k>, j < ndots, of the UPDATED G_k
 //   kind 0: the single sum is the numerator of the next alpha (next = dot0)   :207
 //   kind 1: the sums are the new column M[k:s, k]; then beta = f_k / M[k,k]    :214-220
-template <typename T>
+template <typename T, int NR>     // NR = 1 for the single-dot passes (fewer registers), kIdrsMaxS for the column of M
 struct IdrsOrth {
-  static constexpr int NRED = kIdrsMaxS;
+  static constexpr int NRED = NR;
   const T *P;
   T *G, *U;
   int64_t ld;
@@ -182,7 +182,7 @@ struct IdrsOrth {
     }
     const double gd = (double)g;
     B200_UNROLL
-    for (int j = 0; j < kIdrsMaxS; ++j)
+    for (int j = 0; j < NR; ++j)
       if (j < ndots) acc[j] += (double)P[i + (dot0 + j) * ld] * gd;
   }
   B200_HD double *sums() const { return s->sum; }
@@ -384,14 +384,16 @@ int idrs_run(B &be, const typename B::Op *A, int64_t n, int64_t n_global, T *x, 
         if ((st = be.apply(A, U + k * ld, G + k * ld))) return st;                                    // S :202
         // E: dots and updates interleaved; the last pass yields the new column of M
         if (k == 0) {
-          if ((st = be.pass(IdrsOrth<T>{Pw, G, U, ld, k, -1, k, s_dim - k, 1, sc}, n))) return st;
+          if ((st = be.pass(IdrsOrth<T, kIdrsMaxS>{Pw, G, U, ld, k, -1, k, s_dim - k, 1, sc}, n))) return st;
         } else {
-          if ((st = be.pass(IdrsOrth<T>{Pw, G, U, ld, k, -1, 0, 1, 0, sc}, n))) return st;           // <P_1, G_k>
+          if ((st = be.pass(IdrsOrth<T, 1>{Pw, G, U, ld, k, -1, 0, 1, 0, sc}, n))) return st;        // <P_1, G_k>
           for (int i = 0; i < k; ++i) {
             if (i + 1 < k) {
-              if ((st = be.pass(IdrsOrth<T>{Pw, G, U, ld, k, i, i + 1, 1, 0, sc}, n))) return st;
+              if ((st = be.pass(IdrsOrth<T, 1>{Pw, G, U, ld, k, i, i + 1, 1, 0, sc}, n))) return st;
+            } else if (s_dim - k == 1) {
+              if ((st = be.pass(IdrsOrth<T, 1>{Pw, G, U, ld, k, i, k, 1, 1, sc}, n))) return st;
             } else {
-              if ((st = be.pass(IdrsOrth<T>{Pw, G, U, ld, k, i, k, s_dim - k, 1, sc}, n))) return st;
+              if ((st = be.pass(IdrsOrth<T, kIdrsMaxS>{Pw, G, U, ld, k, i, k, s_dim - k, 1, sc}, n))) return st;
             }
           }
         }

@@ -2,8 +2,8 @@
 //
 //   k_pass<P>: grid = multiple of the SM count (stream_grid), 256 threads, grid-stride over the rows so that
 //   consecutive threads touch consecutive elements (coalesced 8-byte/4-byte accesses); the NRED sums are
-//   reduced warp -> block -> grid in a fixed order (per-block slots, the last block to arrive sums the slots
-//   by index: run-to-run reproducible, same scheme as k_bc_gram / k_block_dots), and the finishing thread
+//   reduced warp -> block -> grid in a fixed order (per-block slots; the last block to arrive sums the slots with all
+//   its threads in a fixed pattern: run-to-run reproducible), and the finishing thread
 //   runs the pass's scalar section.  Passes are HBM-bound streaming kernels: their algorithmic bytes are
 //   (vectors read + vectors written) * n * sizeof(T).
 #pragma once
@@ -58,9 +58,20 @@ __global__ void __launch_bounds__(kPassThreads) k_pass(const P p_in, int64_t n, 
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    // final sum by the whole block in a fixed order: thread t adds slots t, t+256, ... of a column, then the block
+    // tree (a single thread walking the ~1200 slots costs ~90 us of exposed L2 latency per pass: measured)
+#pragma unroll
+    for (int j = 0; j < NR; ++j) {
+      double a = 0.0;
+      for (unsigned int b = threadIdx.x; b < gridDim.x; b += kPassThreads)
+        a += __ldcg(&partials[(size_t)b * kMaxReduceWidth + j]);
+      a = warp_sum(a);
+      if (lane == 0) smem[warp][j] = a;
+    }
+    __syncthreads();
     if (threadIdx.x < NR) {
       double s = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * kMaxReduceWidth + threadIdx.x]);
+      for (int w = 0; w < kPassThreads / 32; ++w) s += smem[w][threadIdx.x];
       tot[threadIdx.x] = s;
     }
     __syncthreads();
