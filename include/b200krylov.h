@@ -146,7 +146,7 @@ B200_API int b200_csr_destroy(b200_csr *A);
 B200_API int b200_csr_info(const b200_csr *A, int64_t *m_local, int64_t *n_global, int64_t *nnz_local, int *dtype,
                            int64_t *row_begin, int64_t *n_halo);
 /* adjoint(A) as an operator (reference: `adjoint(A)` stored by LanczosDecomp src/qmr.jl:54 and used by
- * mul!(y, A', x) at src/qmr.jl:76, src/lsqr.jl:128,152, src/lsmr.jl:116,175).  Built on the device from the CSR of A
+ * mul!(y, A', x) at src/qmr.jl:76, src/lsqr.jl:132,172, src/lsmr.jl:118,172).  Built on the device from the CSR of A
  * (real element types: adjoint == transpose).  Single-GPU contexts; on multi-GPU contexts pass the row slabs of A'
  * to b200_csr_from_csr_slab. */
 B200_API int b200_csr_transpose(b200_ctx *ctx, const b200_csr *A, b200_csr **out);

@@ -550,8 +550,8 @@ int b200_csr_from_csc(b200_ctx *ctx, int64_t m, int64_t n, const void *colptr, c
   return B200_OK;
 }
 
-/* adjoint(A) as an operator of its own (reference: LanczosDecomp stores `adjoint(A)`, src/qmr.jl:54; lsqr src/lsqr.jl:120,
- * lsmr src/lsmr.jl:116): the device CSR arrays of A are the CSC arrays of A', so the CSC->CSR conversion above builds
+/* adjoint(A) as an operator of its own (reference: LanczosDecomp stores `adjoint(A)`, src/qmr.jl:54; lsqr src/lsqr.jl:128,
+ * lsmr src/lsmr.jl:117): the device CSR arrays of A are the CSC arrays of A', so the CSC->CSR conversion above builds
  * the CSR of A' without leaving the GPU.  Real element types: adjoint == transpose. */
 int b200_csr_transpose(b200_ctx *ctx, const b200_csr *A, b200_csr **out) {
   B200_REQUIRE(ctx && A && out, "NULL argument");

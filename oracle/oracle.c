@@ -51,7 +51,7 @@ EXPORT void oracle_csc_spmv_f32(int64_t n_rows, int64_t n_cols, const int64_t *c
 
 /* ---- SparseArrays mul!(y, adjoint(A)::Adjoint{SparseMatrixCSC}, x): one gather dot per column,
  *      y[col] = sum_k conj(nzval[k]) * x[rowval[k]]   (real eltypes: adjoint == transpose).
- *      Call sites in the reference: src/qmr.jl:76, src/lsqr.jl:128,152, src/lsmr.jl:116,175. ---- */
+ *      Call sites in the reference: src/qmr.jl:76, src/lsqr.jl:132,172, src/lsmr.jl:118,172. ---- */
 EXPORT void oracle_csc_spmv_adj_f64(int64_t n_rows, int64_t n_cols, const int64_t *colptr,
                                     const int64_t *rowval, const double *nzval, int64_t base,
                                     const double *x, double *y) {

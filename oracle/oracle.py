@@ -108,7 +108,7 @@ def csc_spmv(A: CSC, x: np.ndarray, y: np.ndarray | None = None) -> np.ndarray:
 
 def csc_spmv_adjoint(A: CSC, x: np.ndarray, y: np.ndarray | None = None) -> np.ndarray:
     """mul!(y, adjoint(A), x) for A::SparseMatrixCSC -- SparseArrays stdlib, one gather dot per column
-    (call sites: reference src/qmr.jl:76, src/lsqr.jl:128,152, src/lsmr.jl:116,175)."""
+    (call sites: reference src/qmr.jl:76, src/lsqr.jl:132,172, src/lsmr.jl:118,172)."""
     x = np.ascontiguousarray(x, dtype=A.dtype)
     if y is None:
         y = np.empty(A.n, dtype=A.dtype)
