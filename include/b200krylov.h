@@ -41,7 +41,8 @@ enum {
   B200_ERR_ALLOC = -4,
   B200_ERR_BREAKDOWN = -5, /* LAPACK-style failure: PosDefException (src/lobpcg.jl:380),
                               SingularException (src/bicgstabl.jl:123)                            */
-  B200_ERR_UNSUPPORTED = -6
+  B200_ERR_UNSUPPORTED = -6,
+  B200_ERR_CALLBACK = -7  /* a b200_linop callback returned non-zero                                   */
 };
 
 /* orth_meth of gmres! (reference src/orthogonalize.jl:5-8) */
@@ -279,6 +280,35 @@ typedef struct {
 B200_API int b200_qmr_solve(b200_ctx *ctx, const b200_csr *A, const b200_csr *At, void *x_dev, const void *b_dev,
                             const b200_qmr_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);
 
+/* ---------------------------------------------------------------- matrix-free operators and preconditioners
+ * The reference's operator contract is duck typing: anything with mul!(y, A, x), size and eltype
+ * (docs/src/getting_started.md:25-30; test/cg.jl:71-77 and test/lsqr.jl:36 run the solvers on LinearMaps), and any
+ * preconditioner with ldiv!(y, P, x) (docs/src/preconditioning.md:5-15).  A b200_linop is that contract at the C ABI:
+ * `apply(user, x_dev, y_dev, cuda_stream)` must ENQUEUE y = A x (or y = P \ x) on the given stream (the context's)
+ * without synchronising, for device vectors of n_local / m_local elements of `dtype`; y never aliases x; return 0.
+ * The *_op entry points below run the same engines as their b200_csr twins -- all recurrence scalars stay in device
+ * memory, the callback is simply the launch between two fused passes -- and on multi-GPU contexts the callback sees
+ * the local slabs (halo exchange is the callback's business) while the engines allreduce their sums. */
+typedef int (*b200_apply_fn)(void *user, const void *x_dev, void *y_dev, void *cuda_stream);
+typedef struct {
+  b200_apply_fn apply;
+  void *user;
+  int64_t m_local;          /* length of y (local rows)                                                  */
+  int64_t n_local;          /* length of x (local)                                                        */
+  int64_t n_global;         /* size(A, 2): default maxiter (src/cg.jl:212)                                */
+  int64_t m_global;         /* size(A, 1)                                                                 */
+  int32_t dtype;            /* B200_F64 / B200_F32                                                        */
+  int32_t reserved;
+} b200_linop;
+/* cg!(x, A, b; Pl, ...) for a general operator A and a general preconditioner (reference src/cg.jl:43-100,120-155,
+ * 209-242): Pl = NULL uses opts->Pl (Identity -> CGIterable, Jacobi -> PCGIterable with the division fused into the
+ * <c, r> pass); Pl != NULL is `ldiv!(c, Pl, r)` by callback.  opts->fixed_iterations / variant must be 0. */
+B200_API int b200_cg_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *Pl, void *x_dev, const void *b_dev,
+                              const b200_cg_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);
+/* qmr! / lsqr! / lsmr! / idrs! on callback operators (A and, where needed, At = adjoint(A)) */
+B200_API int b200_qmr_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *At, void *x_dev, const void *b_dev,
+                               const b200_qmr_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);
+
 /* lsqr! / lsmr! share one option block and one result block. */
 typedef struct {
   double damp;              /* lsqr: damp = 0 (src/lsqr.jl:91); lsmr: λ = 0 (src/lsmr.jl:90)                       */
@@ -311,6 +341,13 @@ B200_API int b200_lsqr_solve(b200_ctx *ctx, const b200_csr *A, const b200_csr *A
 B200_API int b200_lsmr_solve(b200_ctx *ctx, const b200_csr *A, const b200_csr *At, void *x_dev, const void *b_dev,
                              const b200_lsq_opts *opts, b200_lsq_result *res, double *hist_host, int64_t hist_cap);
 
+B200_API int b200_lsqr_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *At, void *x_dev,
+                                const void *b_dev, const b200_lsq_opts *opts, b200_lsq_result *res, double *hist_host,
+                                int64_t hist_cap);
+B200_API int b200_lsmr_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *At, void *x_dev,
+                                const void *b_dev, const b200_lsq_opts *opts, b200_lsq_result *res, double *hist_host,
+                                int64_t hist_cap);
+
 typedef struct {
   double abstol, reltol;    /* src/idrs.jl:52-53 (reltol < 0: sqrt(eps(real(T))))                                  */
   int64_t maxiter;          /* size(A, 2)  src/idrs.jl:54 (<0: default)                                             */
@@ -326,6 +363,9 @@ typedef struct {
 /* idrs!(x, A, b; s, Pl, abstol, reltol, maxiter, smoothing)  reference src/idrs.jl:49-64, 112-145, 163-272. */
 B200_API int b200_idrs_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
                              const b200_idrs_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);
+B200_API int b200_idrs_solve_op(b200_ctx *ctx, const b200_linop *A, void *x_dev, const void *b_dev,
+                                const b200_idrs_opts *opts, b200_result *res, double *resnorm_host,
+                                int64_t resnorm_cap);
 
 typedef struct {
   double abstol, reltol;    /* src/gmres.jl:187-188                                                */

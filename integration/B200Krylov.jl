@@ -50,6 +50,8 @@ mutable struct B200Vector{T<:BlasReal} <: AbstractVector{T}
         finalizer(v -> ccall((:b200_free, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), v.ctx.h, v.p),
                   new{T}(Ptr{T}(r[]), n, ctx))
     end
+    # non-owning view of device memory the library hands to an operator callback (no finalizer)
+    B200Vector{T}(ctx::Ctx, p::Ptr{T}, n::Integer, owner::Bool) where {T} = new{T}(p, n, ctx)
 end
 Base.size(v::B200Vector) = (v.n,)
 Base.similar(v::B200Vector{T}) where {T} = B200Vector{T}(v.ctx, v.n)
@@ -187,6 +189,10 @@ end
 struct IdrsOpts
     abstol::Float64; reltol::Float64; maxiter::Int64; s::Int32; smoothing::Int32; Pl::Precond
     P::Ptr{Cvoid}; ldp::Int64; check_every::Int32; reserved::Int32
+end
+struct LinOp                                   # b200_linop
+    apply::Ptr{Cvoid}; user::Ptr{Cvoid}; m_local::Int64; n_local::Int64; n_global::Int64; m_global::Int64
+    dtype::Int32; reserved::Int32
 end
 orth_code(::ModifiedGramSchmidt) = Int32(0); orth_code(::ClassicalGramSchmidt) = Int32(1); orth_code(::DGKS) = Int32(2)   # B200_ORTH_*
 
@@ -409,5 +415,43 @@ function idrs!(x::Vector{T}, A::B200CSR{T}, b::Vector{T};
     end
     log ? (x, history(res, hist, abstol, reltol)) : x
 end
+
+# ------------------------------------------------------------------------------------------- matrix-free operators
+# Anything with mul!(y::B200Vector, A, x::B200Vector) (a LinearMap over device vectors, a user type, a closure) can be
+# handed to the fused engines: the C library calls back between two of its kernels (b200_linop), on its own stream.
+struct B200LinearOperator{T,F}
+    f::F                                       # f(y::B200Vector{T}, x::B200Vector{T}) enqueues y = A x
+    ctx::Ctx
+    m::Int
+    n::Int
+end
+function linop_thunk(user::Ptr{Cvoid}, x::Ptr{Cvoid}, y::Ptr{Cvoid}, stream::Ptr{Cvoid})::Cint
+    op = unsafe_pointer_to_objref(user)::B200LinearOperator
+    T = typeof(op).parameters[1]
+    try
+        op.f(B200Vector{T}(op.ctx, Ptr{T}(y), op.m, false), B200Vector{T}(op.ctx, Ptr{T}(x), op.n, false))   # non-owning views
+        return Cint(0)
+    catch
+        return Cint(1)
+    end
+end
+linop(op::B200LinearOperator{T}) where {T} =
+    LinOp(@cfunction(linop_thunk, Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid})), pointer_from_objref(op),
+          op.m, op.n, op.n, op.m, dtype_code(T), 0)
+
+function cg!(x::B200Vector{T}, A::B200LinearOperator{T}, b::B200Vector{T};
+             abstol::Real = zero(T), reltol::Real = sqrt(eps(T)), maxiter::Int = A.n, log::Bool = false,
+             Pl = Identity(), initially_zero::Bool = false, verbose::Bool = false) where {T}
+    res = Result(); hist = Vector{Float64}(undef, log ? maxiter + 1 : 0)
+    cb = Pl isa B200LinearOperator                                         # ldiv!(c, Pl, r) by callback
+    o = CgOpts(abstol, reltol, maxiter, initially_zero, 0, cb ? prec(Identity()) : prec(Pl), 0, 0)
+    a = Ref(linop(A)); p = cb ? Ref(linop(Pl)) : C_NULL
+    GC.@preserve A Pl check(ccall((:b200_cg_solve_op, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{LinOp}, Ptr{LinOp}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{CgOpts}, Ref{Result}, Ptr{Float64}, Int64),
+        A.ctx.h, a, p, x.p, b.p, o, res, hist, length(hist)))
+    log ? (x, history(res, hist, abstol, reltol)) : x
+end
+# qmr!/lsqr!/lsmr!/idrs! on B200LinearOperator: the same pattern with b200_qmr_solve_op / b200_lsqr_solve_op /
+# b200_lsmr_solve_op / b200_idrs_solve_op (the adjoint is a second B200LinearOperator).
 
 end # module

@@ -15,6 +15,7 @@ ORTH_MGS, ORTH_CGS, ORTH_DGKS = 0, 1, 2
 PREC_IDENTITY, PREC_JACOBI = 0, 1
 ERR_INVALID = -1
 ERR_BREAKDOWN = -5
+ERR_CALLBACK = -7
 
 
 class B200Error(RuntimeError):
@@ -72,6 +73,14 @@ class IdrsOpts(C.Structure):
     _fields_ = [("abstol", C.c_double), ("reltol", C.c_double), ("maxiter", C.c_int64), ("s", C.c_int32),
                 ("smoothing", C.c_int32), ("Pl", Precond), ("P", C.c_void_p), ("ldp", C.c_int64),
                 ("check_every", C.c_int32), ("reserved", C.c_int32)]
+
+
+APPLY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p)   # b200_apply_fn
+
+
+class LinOp(C.Structure):
+    _fields_ = [("apply", APPLY_FN), ("user", C.c_void_p), ("m_local", C.c_int64), ("n_local", C.c_int64),
+                ("n_global", C.c_int64), ("m_global", C.c_int64), ("dtype", C.c_int32), ("reserved", C.c_int32)]
 
 
 class LobpcgOpts(C.Structure):
@@ -163,6 +172,15 @@ SIGNATURES = {
     "b200_lsqr_solve": (_INT, [_P, _P, _P, _P, _P, C.POINTER(LsqOpts), C.POINTER(LsqResult), _P, _I64]),
     "b200_lsmr_solve": (_INT, [_P, _P, _P, _P, _P, C.POINTER(LsqOpts), C.POINTER(LsqResult), _P, _I64]),
     "b200_idrs_solve": (_INT, [_P, _P, _P, _P, C.POINTER(IdrsOpts), C.POINTER(Result), _P, _I64]),
+    "b200_cg_solve_op": (_INT, [_P, C.POINTER(LinOp), C.POINTER(LinOp), _P, _P, C.POINTER(CgOpts), C.POINTER(Result), _P,
+                                _I64]),
+    "b200_qmr_solve_op": (_INT, [_P, C.POINTER(LinOp), C.POINTER(LinOp), _P, _P, C.POINTER(QmrOpts), C.POINTER(Result),
+                                 _P, _I64]),
+    "b200_lsqr_solve_op": (_INT, [_P, C.POINTER(LinOp), C.POINTER(LinOp), _P, _P, C.POINTER(LsqOpts),
+                                  C.POINTER(LsqResult), _P, _I64]),
+    "b200_lsmr_solve_op": (_INT, [_P, C.POINTER(LinOp), C.POINTER(LinOp), _P, _P, C.POINTER(LsqOpts),
+                                  C.POINTER(LsqResult), _P, _I64]),
+    "b200_idrs_solve_op": (_INT, [_P, C.POINTER(LinOp), _P, _P, C.POINTER(IdrsOpts), C.POINTER(Result), _P, _I64]),
     "b200_lobpcg_solve": (_INT, [_P, _P, _P, _I64, C.POINTER(LobpcgOpts), C.POINTER(LobpcgResult), _P, _P]),
     "b200_dense_sygv_host": (_INT, [_INT, _P, _P, _P, _P]),
 }

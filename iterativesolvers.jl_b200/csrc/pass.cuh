@@ -97,17 +97,29 @@ __global__ void k_pass_finish(P p) {
 
 #endif  // __CUDACC__
 
+// What the engines apply: the device CSR operator or a caller-supplied callback (b200_linop).
+struct CudaOp {
+  const b200_csr *csr = nullptr;
+  const b200_linop *fn = nullptr;
+};
+
 // The CUDA backend the engines are instantiated with in libb200krylov.so.
 struct CudaBackend {
-  typedef b200_csr Op;
+  typedef CudaOp Op;
   b200_ctx *ctx;
 
   bool single() const { return ctx->world == 1; }
 
-  // y = Op x (halo exchange included on multi-GPU contexts)
+  // y = Op x (b200_csr: halo exchange included on multi-GPU contexts; b200_linop: whatever the callback enqueues)
   int apply(const Op *A, const void *x, void *y) {
     ProfScope prof(ctx, 0);
-    return spmv(ctx, A, x, y);
+    if (A->csr) return spmv(ctx, A->csr, x, y);
+    const int st = A->fn->apply(A->fn->user, x, y, (void *)ctx->stream);
+    if (st != 0) {
+      set_error("operator / preconditioner callback returned %d", st);
+      return B200_ERR_CALLBACK;
+    }
+    return B200_OK;
   }
 
 #ifdef __CUDACC__

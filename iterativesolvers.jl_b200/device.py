@@ -142,6 +142,16 @@ class DeviceArray:
         check(lib().b200_download(self.ctx._h, out.ctypes.data_as(C.c_void_p), self._p, self.nbytes))
         return out
 
+    @classmethod
+    def view(cls, ctx: Context, ptr: int, n: int, dtype) -> "DeviceArray":
+        """non-owning vector view of `n` elements at the raw device address `ptr` (operator callbacks)."""
+        v = object.__new__(cls)
+        v.ctx, v.shape, v.dtype, v.code = ctx, (int(n),), np.dtype(dtype), dtype_code(dtype)
+        v.nbytes = int(n) * v.dtype.itemsize
+        v._p = C.c_void_p(ptr)
+        v._owner = False
+        return v
+
     def column(self, j: int) -> "DeviceArray":
         """view(V, :, j) -- non-owning."""
         v = object.__new__(DeviceArray)

@@ -241,3 +241,78 @@ class B200CSR:
             self.close()
         except Exception:
             pass
+
+
+class B200LinearOperator:
+    """A matrix-free operator (or preconditioner) on device vectors: the reference's duck-typed contract
+    `mul!(y, A, x)` / `size` / `eltype` (docs/src/getting_started.md:25-30; LinearMaps in test/cg.jl:71-77,
+    test/lsqr.jl:36) carried through the C ABI as a `b200_linop` callback.
+
+        mul(y, x)          enqueue y = A x on the context's stream; x, y are DeviceArray views (y never aliases x)
+        adjoint_mul(y, x)  optional: y = A' x  (needed by qmr!/lsqr!/lsmr!)
+
+    shape = (m, n) are the LOCAL lengths of y and x (on a single-GPU context also the global ones); on multi-GPU
+    contexts pass `global_shape` and do the halo exchange inside `mul`."""
+
+    def __init__(self, shape, dtype, mul, adjoint_mul=None, ctx: Context | None = None, global_shape=None):
+        self.ctx = ctx or default_context()
+        self.dtype = np.dtype(dtype)
+        self.code = dtype_code(dtype)
+        self.m_local, self.n_local = int(shape[0]), int(shape[1])
+        gm, gn = global_shape if global_shape is not None else shape
+        self.m_global, self.n_global = int(gm), int(gn)
+        self._mul, self._adjoint_mul = mul, adjoint_mul
+        self._exc = None
+        self._adjoint = None
+        self._cb = _lib.APPLY_FN(self._trampoline)            # keep the thunk alive as long as the operator
+        self._c = _lib.LinOp(self._cb, None, self.m_local, self.n_local, self.n_global, self.m_global, self.code, 0)
+
+    def _trampoline(self, user, x_ptr, y_ptr, stream):
+        try:
+            x = DeviceArray.view(self.ctx, x_ptr, self.n_local, self.dtype)
+            y = DeviceArray.view(self.ctx, y_ptr, self.m_local, self.dtype)
+            self._mul(y, x)
+            return 0
+        except BaseException as e:                            # never let an exception cross the C frames
+            self._exc = e
+            return 1
+
+    def raise_pending(self):
+        if self._exc is not None:
+            e, self._exc = self._exc, None
+            raise e
+
+    @property
+    def shape(self):
+        return (self.m_global, self.n_global)
+
+    def size(self, d=None):
+        return self.shape if d is None else self.shape[d - 1]
+
+    def mul_(self, y, x):
+        self._mul(y, x)
+        return y
+
+    def adjoint(self) -> "B200LinearOperator":
+        if self._adjoint is None:
+            if self._adjoint_mul is None:
+                raise TypeError("this operator has no adjoint_mul (needed by qmr!/lsqr!/lsmr!)")
+            self._adjoint = B200LinearOperator((self.n_local, self.m_local), self.dtype, self._adjoint_mul, self._mul,
+                                               self.ctx, (self.n_global, self.m_global))
+            self._adjoint._adjoint = self
+        return self._adjoint
+
+    @classmethod
+    def from_csr(cls, A: "B200CSR"):
+        """a B200CSR seen through the callback interface (lets a callback preconditioner be combined with it)."""
+        n_loc = A.n_global if A.ctx.world == 1 else A.m_local
+        return cls((A.m_local, n_loc), A.dtype, lambda y, x: A.mul_(y, x),
+                   (lambda y, x: A.adjoint().mul_(y, x)), A.ctx, A.shape)
+
+
+class FunctionPrec:
+    """A preconditioner given as a function: ldiv(y, x) enqueues y = P \\ x on device vectors
+    (`ldiv!(y, P, x)`, docs/src/preconditioning.md:5-15)."""
+
+    def __init__(self, n, dtype, ldiv, ctx: Context | None = None):
+        self.op = B200LinearOperator((n, n), dtype, ldiv, None, ctx)

@@ -19,16 +19,31 @@ from . import _lib
 from ._lib import B200Error, check, lib
 from .device import DeviceArray, as_device_ptr, is_device
 from .history import ConvergenceHistory
-from .operators import B200CSR, Identity, precond_to_c
+from .operators import B200CSR, B200LinearOperator, FunctionPrec, Identity, precond_to_c
 
 
 def _eps(dtype):
     return float(np.finfo(np.dtype(dtype)).eps)
 
 
-def _check_operator(A):
-    if not isinstance(A, B200CSR):
-        raise TypeError("the device path needs a B200CSR operator (B200CSR.from_scipy / from_csc_arrays)")
+def _check_operator(A, linop_ok=False):
+    if isinstance(A, B200CSR) or (linop_ok and isinstance(A, B200LinearOperator)):
+        return
+    raise TypeError("the device path needs a B200CSR operator (B200CSR.from_scipy / from_csc_arrays)"
+                    + (" or a B200LinearOperator" if linop_ok else ""))
+
+
+def _is_linop(A):
+    return isinstance(A, B200LinearOperator)
+
+
+def _call_op(fn, ops, *args):
+    """call a *_op entry point; re-raise an exception a Python callback stored while C frames were on the stack."""
+    status = fn(*args)
+    for o in ops:
+        if o is not None:
+            o.raise_pending()
+    return status
 
 
 class _Staged:
@@ -78,11 +93,29 @@ def cg_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, log=False, verbose=Fa
     """cg!(x, A, b; abstol, reltol, maxiter, log, statevars, verbose, Pl, initially_zero).
     With `statevars` (CGStateVariables of three device vectors) the solve runs through the iterator form of the
     engine on the caller's u, r, c -- exactly `cg_iterator!(...; statevars)` driven to done() (src/cg.jl:224-236)."""
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
     if reltol is None:
         reltol = math.sqrt(_eps(A.dtype))                     # src/cg.jl:211
     if maxiter is None:
         maxiter = A.size(2)                                   # src/cg.jl:212
+    if _is_linop(A) or isinstance(Pl, FunctionPrec):
+        # general operator / preconditioner: the pass-based engine (csrc/cg_core.h) with device callbacks
+        if statevars is not None or _fixed_iterations:
+            raise TypeError("statevars / _fixed_iterations are only available for B200CSR operators")
+        op = A if _is_linop(A) else B200LinearOperator.from_csr(A)
+        pl = Pl.op if isinstance(Pl, FunctionPrec) else None
+        opts = _lib.CgOpts(abstol, reltol, int(maxiter), int(bool(initially_zero)), int(check_every),
+                           precond_to_c(None if pl is not None else Pl, A), 0, 0)
+        res = _lib.Result()
+        cap = int(maxiter) + 1 if log else 0
+        resnorm = np.zeros(max(cap, 1), dtype=np.float64)
+        st = _Staged(A, x, b)
+        check(_call_op(lib().b200_cg_solve_op, (op, pl), A.ctx._h, C.byref(op._c), C.byref(pl._c) if pl else None,
+                       as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts), C.byref(res),
+                       resnorm.ctypes.data_as(C.c_void_p) if log else None, cap))
+        st.finish()
+        cg_.last_result = res
+        return (x, _history(res, resnorm, abstol, reltol, log)) if log else x
     if statevars is not None:
         it = cg_iterator_(x, A, b, abstol=abstol, reltol=reltol, maxiter=maxiter, statevars=statevars, Pl=Pl,
                           initially_zero=initially_zero)
@@ -237,7 +270,7 @@ def cg_iterator_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, statevars=No
 
 def cg(A, b, **kw):
     """cg(A, b; kw...) = cg!(zerox(A, b), A, b; initially_zero = true, kw...)  (src/cg.jl:162)."""
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
     if is_device(b):
         x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype)
     else:
@@ -400,7 +433,8 @@ class _StagedRect:
     """host<->device staging for an m x n operator: x has n entries, b has m."""
 
     def __init__(self, A: B200CSR, x, b):
-        m, n = A.m_local, (A.n_global if A.ctx.world == 1 else A.m_local)
+        m = A.m_local
+        n = A.n_local if isinstance(A, B200LinearOperator) else (A.n_global if A.ctx.world == 1 else A.m_local)
         self.host = not is_device(x)
         self.x = x
         if self.host:
@@ -427,7 +461,7 @@ def qmr_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, lookahead=False, log
          verbose=False, check_every=0):
     """qmr!(x, A, b; abstol, reltol, maxiter, lookahead, log, initially_zero, verbose) -- reference src/qmr.jl:262-297.
     `lookahead` is accepted and ignored, as in the reference (it is never forwarded, src/qmr.jl:279-280)."""
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
     if reltol is None:
         reltol = math.sqrt(_eps(A.dtype))                     # src/qmr.jl:267
     if maxiter is None:
@@ -437,8 +471,14 @@ def qmr_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, lookahead=False, log
     cap = int(maxiter) if log else 0                          # reserve!(history, :resnorm, maxiter)  :277
     resnorm = np.zeros(max(cap, 1), dtype=np.float64)
     st = _Staged(A, x, b)
-    check(lib().b200_qmr_solve(A.ctx._h, A._h, A.adjoint()._h, as_device_ptr(st.xd), as_device_ptr(st.bd),
-                               C.byref(opts), C.byref(res), resnorm.ctypes.data_as(C.c_void_p) if log else None, cap))
+    rp = resnorm.ctypes.data_as(C.c_void_p) if log else None
+    if _is_linop(A):
+        At = A.adjoint()
+        check(_call_op(lib().b200_qmr_solve_op, (A, At), A.ctx._h, C.byref(A._c), C.byref(At._c), as_device_ptr(st.xd),
+                       as_device_ptr(st.bd), C.byref(opts), C.byref(res), rp, cap))
+    else:
+        check(lib().b200_qmr_solve(A.ctx._h, A._h, A.adjoint()._h, as_device_ptr(st.xd), as_device_ptr(st.bd),
+                                   C.byref(opts), C.byref(res), rp, cap))
     st.finish()
     if verbose:
         print("=== qmr ===\niter\tresnorm")
@@ -454,13 +494,13 @@ def qmr_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, lookahead=False, log
 
 def qmr(A, b, **kw):
     """qmr(A, b; kwargs...) = qmr!(zerox(A, b), A, b; initially_zero = true, kwargs...) -- src/qmr.jl:222."""
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
     x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
     return qmr_(x, A, b, initially_zero=True, **kw)
 
 
 def _lsq(fn, first_key, x, A, b, damp, atol, btol, conlim, maxiter, log, verbose, check_every, name):
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
     if maxiter is None:
         maxiter = max(A.shape)                                # maximum(size(A))  src/lsqr.jl:67, src/lsmr.jl:68
     opts = _lib.LsqOpts(float(damp), float(atol), float(btol), float(conlim), int(maxiter), int(check_every), 0)
@@ -468,8 +508,14 @@ def _lsq(fn, first_key, x, A, b, damp, atol, btol, conlim, maxiter, log, verbose
     cap = int(maxiter)                                        # reserve!(history, [...], maxiter)  src/lsqr.jl:73
     hist = np.zeros(4 * max(cap, 1), dtype=np.float64)
     st = _StagedRect(A, x, b)
-    status = fn(A.ctx._h, A._h, A.adjoint()._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
-                C.byref(res), hist.ctypes.data_as(C.c_void_p), cap)
+    if _is_linop(A):
+        At = A.adjoint()
+        status = _call_op(getattr(lib(), f"b200_{name}_solve_op"), (A, At), A.ctx._h, C.byref(A._c), C.byref(At._c),
+                          as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts), C.byref(res),
+                          hist.ctypes.data_as(C.c_void_p), cap)
+    else:
+        status = fn(A.ctx._h, A._h, A.adjoint()._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
+                    C.byref(res), hist.ctypes.data_as(C.c_void_p), cap)
     if status == _lib.ERR_INVALID and res.status == _lib.ERR_INVALID:
         raise ValueError("Initial guess for x must be finite")            # src/lsqr.jl:102-104
     check(status)
@@ -495,7 +541,7 @@ def lsqr_(x, A, b, *, damp=0.0, atol=None, btol=None, conlim=None, maxiter=None,
           check_every=0):
     """lsqr!(x, A, b; damp, atol, btol, conlim, maxiter, verbose, log) -- reference src/lsqr.jl:66-77, 90-275.
     A may be rectangular (m x n): x has n entries, b has m."""
-    s = math.sqrt(_eps(A.dtype)) if isinstance(A, B200CSR) else 0.0
+    s = math.sqrt(_eps(A.dtype)) if isinstance(A, (B200CSR, B200LinearOperator)) else 0.0
     atol = s if atol is None else atol                        # src/lsqr.jl:91
     btol = s if btol is None else btol
     conlim = (1.0 / s if s else 0.0) if conlim is None else conlim        # src/lsqr.jl:92
@@ -505,8 +551,8 @@ def lsqr_(x, A, b, *, damp=0.0, atol=None, btol=None, conlim=None, maxiter=None,
 
 def lsqr(A, b, **kw):
     """lsqr(A, b; kwargs...) = lsqr!(zerox(A, b), A, b; kwargs...) -- src/lsqr.jl:8."""
-    _check_operator(A)
-    n = A.shape[1] if A.ctx.world == 1 else A.m_local
+    _check_operator(A, linop_ok=True)
+    n = A.n_local if _is_linop(A) else (A.shape[1] if A.ctx.world == 1 else A.m_local)
     x = DeviceArray.zeros(A.ctx, n, A.dtype) if is_device(b) else np.zeros(n, dtype=A.dtype)
     return lsqr_(x, A, b, **kw)
 
@@ -521,8 +567,8 @@ def lsmr_(x, A, b, *, atol=1e-6, btol=1e-6, conlim=1e8, maxiter=None, lam=0.0, l
 
 def lsmr(A, b, **kw):
     """lsmr(A, b; kwargs...) = lsmr!(zerox(A, b), A, b; kwargs...) -- src/lsmr.jl:10."""
-    _check_operator(A)
-    n = A.shape[1] if A.ctx.world == 1 else A.m_local
+    _check_operator(A, linop_ok=True)
+    n = A.n_local if _is_linop(A) else (A.shape[1] if A.ctx.world == 1 else A.m_local)
     x = DeviceArray.zeros(A.ctx, n, A.dtype) if is_device(b) else np.zeros(n, dtype=A.dtype)
     return lsmr_(x, A, b, **kw)
 
@@ -532,7 +578,7 @@ def idrs_(x, A, b, *, s=8, Pl=None, abstol=0.0, reltol=None, maxiter=None, log=F
     """idrs!(x, A, b; s, Pl, abstol, reltol, maxiter, log, smoothing, verbose) -- reference src/idrs.jl:49-64.
     The reference draws the shadow space with rand!(copy(C)) (src/idrs.jl:132); here the draw happens on the host
     (numpy Generator `rng`) unless `P` (n x s) is given."""
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
     if reltol is None:
         reltol = math.sqrt(_eps(A.dtype))                     # src/idrs.jl:53
     if maxiter is None:
@@ -549,8 +595,13 @@ def idrs_(x, A, b, *, s=8, Pl=None, abstol=0.0, reltol=None, maxiter=None, log=F
     cap = int(maxiter) if log else 0                          # reserve!(history, :resnorm, maxiter)  :60
     resnorm = np.zeros(max(cap, 1), dtype=np.float64)
     st = _Staged(A, x, b)
-    check(lib().b200_idrs_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
-                                C.byref(res), resnorm.ctypes.data_as(C.c_void_p) if log else None, cap))
+    rp = resnorm.ctypes.data_as(C.c_void_p) if log else None
+    if _is_linop(A):
+        check(_call_op(lib().b200_idrs_solve_op, (A,), A.ctx._h, C.byref(A._c), as_device_ptr(st.xd),
+                       as_device_ptr(st.bd), C.byref(opts), C.byref(res), rp, cap))
+    else:
+        check(lib().b200_idrs_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
+                                    C.byref(res), rp, cap))
     st.finish()
     if verbose:
         print("=== idrs ===\niter\tstep\tresnorm")
@@ -563,7 +614,7 @@ def idrs_(x, A, b, *, s=8, Pl=None, abstol=0.0, reltol=None, maxiter=None, log=F
 
 def idrs(A, b, **kw):
     """idrs(A, b; kwargs...) = idrs!(zerox(A, b), A, b; kwargs...) -- src/idrs.jl:11."""
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
     x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
     return idrs_(x, A, b, **kw)
 

@@ -21,6 +21,7 @@
 #include "../../iterativesolvers.jl_b200/csrc/lsqr_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/lsmr_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/idrs_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/cg_core.h"
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -206,6 +207,29 @@ EXPORT int hostsim_idrs(int is_f64, const hostsim_csr *A, void *x, const void *b
                                           hist_cap, hist, &o);
   out->iters = o.iters; out->mvps = o.iters; out->mtvps = 0; out->n_hist = o.n_hist;
   out->resnorm = o.normR; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
+  out->passes = be.passes; out->applies = be.applies;
+  return st;
+}
+
+// cg! / pcg on a general operator: Pl (may be NULL) is a second "operator" whose application is y = Pl \ x
+EXPORT int hostsim_cg(int is_f64, const hostsim_csr *A, const hostsim_csr *Pl, const void *diag, void *x, const void *b,
+                      double abstol, double reltol, int64_t maxiter, int initially_zero, int check_every,
+                      int64_t hist_cap, double *hist, int order, int split, hostsim_out *out) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64), p;
+  if (Pl) p = mk(Pl, is_f64);
+  b200::CgpOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st = is_f64 ? b200::cgp_run<double>(be, &a, Pl ? &p : nullptr, (const double *)diag, A->m, A->n, (double *)x,
+                                          (const double *)b, abstol, reltol, maxiter, initially_zero, check_every,
+                                          hist_cap, hist, &o)
+                  : b200::cgp_run<float>(be, &a, Pl ? &p : nullptr, (const float *)diag, A->m, A->n, (float *)x,
+                                         (const float *)b, abstol, reltol, maxiter, initially_zero, check_every,
+                                         hist_cap, hist, &o);
+  out->iters = o.iters; out->mvps = o.mvps; out->mtvps = 0; out->n_hist = o.n_hist;
+  out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
   out->passes = be.passes; out->applies = be.applies;
   return st;
 }

@@ -153,3 +153,24 @@ def idrs_(x, A, b, P, *, diag=None, abstol=0.0, reltol=-1.0, maxiter=-1, smoothi
                             C.c_int(split), C.byref(out))
     assert st == 0, st
     return x, _outcome(out, hist)
+
+
+def cg_(x, A, b, *, Pl=None, diag=None, abstol=0.0, reltol=-1.0, maxiter=-1, initially_zero=False, check_every=0,
+        order=0, split=0):
+    """the general-operator cg engine (csrc/cg_core.h) on the serial backend; Pl: a scipy matrix whose product is the
+    application of the preconditioner (y = Pl_inverse @ x), diag: Jacobi diagonal; x updated in place."""
+    dt = x.dtype
+    Ac = Csr(A, dt)
+    Pc = Csr(Pl, dt) if Pl is not None else None
+    b = np.ascontiguousarray(b, dtype=dt)
+    d = None if diag is None else np.ascontiguousarray(diag, dtype=dt)
+    cap = (maxiter if maxiter >= 0 else A.shape[1]) + 1
+    hist = np.zeros(cap)
+    out = _Out()
+    st = lib().hostsim_cg(C.c_int(dt == np.float64), C.byref(Ac.c), C.byref(Pc.c) if Pc else None,
+                          C.c_void_p(d.ctypes.data if d is not None else None), C.c_void_p(x.ctypes.data),
+                          C.c_void_p(b.ctypes.data), C.c_double(abstol), C.c_double(reltol), C.c_int64(maxiter),
+                          C.c_int(initially_zero), C.c_int(check_every), C.c_int64(cap),
+                          hist.ctypes.data_as(C.c_void_p), C.c_int(order), C.c_int(split), C.byref(out))
+    assert st == 0, st
+    return x, _outcome(out, hist)

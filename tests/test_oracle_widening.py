@@ -50,6 +50,14 @@ class SimRunner:
     def idrs(self, x, A, b, P, **kw):
         return self.sim.idrs_(x, A, b, P, order=self.order, split=self.split, **kw)
 
+    def cg(self, x, A, b, mode, d, **kw):
+        extra = {}
+        if mode == "jacobi":
+            extra["diag"] = d
+        elif mode == "callback":       # the preconditioner as a second operator: y = diag(1/d) x
+            extra["Pl"] = sp.diags(1.0 / np.asarray(d, dtype=np.float64)).tocsr()
+        return self.sim.cg_(x, A, b, order=self.order, split=self.split, **extra, **kw)
+
 
 @pytest.fixture(scope="module")
 def runners(sim):
@@ -242,3 +250,40 @@ def test_engine_idrs_matches_oracle(oracle, runners, dtype, tol):
 
 def test_engine_idrs_s16_maxiter_and_zero_iterations(oracle, runners):
     cases.case_idrs_s16_maxiter_zero_iterations(oracle, runners)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 2e-5)])
+def test_engine_cg_general_operator_matches_oracle(oracle, runners, dtype, tol):
+    cases.case_cg_general_operator(oracle, runners, dtype, tol)
+
+
+def test_python_callback_trampoline_without_a_gpu():
+    """B200LinearOperator's ctypes thunk: builds non-owning DeviceArray views of the right lengths, calls the user
+    function, returns 0; an exception is held back (it must not cross the C frames) and re-raised afterwards."""
+    import ctypes as C
+    from types import SimpleNamespace
+    import iterativesolvers_jl_b200 as isb
+    seen = []
+    ctx = SimpleNamespace(_h=None, world=1)
+    op = isb.B200LinearOperator((5, 3), np.float32, lambda y, x: seen.append((y.ptr, y.shape, x.ptr, x.shape, y.dtype)),
+                                adjoint_mul=lambda y, x: seen.append(("adj", y.shape, x.shape)), ctx=ctx)
+    assert op.shape == (5, 3) and op._c.m_local == 5 and op._c.n_local == 3 and op._c.dtype == 1
+    assert op._cb(None, 0x1000, 0x2000, None) == 0
+    assert seen[-1] == (0x2000, (5,), 0x1000, (3,), np.dtype(np.float32))
+    At = op.adjoint()
+    assert At.shape == (3, 5) and At.adjoint() is op and At._cb(None, 0x10, 0x20, None) == 0
+    assert seen[-1] == ("adj", (3,), (5,))
+
+    def boom(y, x):
+        raise KeyError("user code failed")
+
+    bad = isb.B200LinearOperator((2, 2), np.float64, boom, ctx=ctx)
+    assert bad._cb(None, 1, 2, None) == 1
+    with pytest.raises(KeyError):
+        bad.raise_pending()
+    bad.raise_pending()            # cleared
+    with pytest.raises(TypeError):
+        bad.adjoint()              # no adjoint_mul given
+    # the C struct really carries the thunk
+    fn = C.cast(op._c.apply, C.c_void_p).value
+    assert fn and fn == C.cast(op._cb, C.c_void_p).value

@@ -1,0 +1,123 @@
+"""GPU tests for matrix-free operators and callback preconditioners (b200_linop, csrc/cg_core.h, the *_op entry
+points): the reference's duck-typed `mul!` / `ldiv!` contract (docs/src/getting_started.md:25-30,
+docs/src/preconditioning.md:5-15; LinearMaps in test/cg.jl:71-77, test/lsqr.jl:36) through the C ABI.
+
+The engine-vs-oracle cases are shared with the CPU run on the serial backend (tests/widening_cases.py).
+(Written after the round's GPU budget was spent: first executed by the round-end GPU run.)
+"""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import widening_cases as cases
+
+pytestmark = pytest.mark.gpu
+SEED = 1234321
+
+
+@pytest.fixture(scope="module")
+def isb():
+    import iterativesolvers_jl_b200 as m
+    m.default_context()
+    return m
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+class GpuCgRunner:
+    """general-operator cg!: the operator always goes through the callback interface."""
+
+    def __init__(self, isb):
+        self.isb = isb
+
+    def cg(self, x, A, b, mode, d, **kw):
+        isb = self.isb
+        csr = isb.B200CSR.from_scipy(sp.csc_matrix(A).astype(x.dtype))
+        if mode == "callback":
+            jac = isb.JacobiPrec(np.asarray(d, dtype=x.dtype))
+            op, Pl = csr, isb.FunctionPrec(csr.m_local, x.dtype, lambda y, v: jac.ldiv_(y, v))   # CSR A + callback Pl
+        else:
+            op = isb.B200LinearOperator.from_csr(csr)                                              # callback A
+            Pl = isb.JacobiPrec(np.asarray(d, dtype=x.dtype)) if mode == "jacobi" else None
+        x, h = isb.cg_(x, op, np.asarray(b, dtype=x.dtype), Pl=Pl, log=True, **kw)
+        res = isb.cg_.last_result
+        return x, SimpleNamespace(iters=h.iters, converged=h.isconverged, mvps=h.mvps, hist=h["resnorm"],
+                                  breakdown=res.status != 0)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 2e-5)])
+def test_cg_general_operator_matches_oracle(isb, oracle, dtype, tol):
+    cases.case_cg_general_operator(oracle, [GpuCgRunner(isb)], dtype, tol)
+
+
+def test_general_cg_equals_the_specialised_engine(isb, oracle):
+    """same operator, same right-hand side: the pass-based engine behind a callback and the fused CSR engine of
+    cg.cu follow the same recurrence (history 1e-10, x 1e-10)."""
+    rng = np.random.default_rng(SEED)
+    O = oracle.laplace_matrix(np.float64, 24, 3, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    b = rng.standard_normal(O.n)
+    b /= np.linalg.norm(b)
+    x1, h1 = isb.cg(A, b, log=True)
+    x2, h2 = isb.cg(isb.B200LinearOperator.from_csr(A), b, log=True)
+    assert h1.iters == h2.iters and h1.mvps == h2.mvps and h1.isconverged and h2.isconverged
+    assert np.max(np.abs(h1["resnorm"] - h2["resnorm"]) / h1["resnorm"]) <= 1e-10 and relerr(x2, x1) <= 1e-10
+    Pj = isb.JacobiPrec(A.diag(), A.ctx)
+    x3, h3 = isb.cg(A, b, Pl=Pj, log=True)
+    x4, h4 = isb.cg(A, b, Pl=isb.FunctionPrec(A.m_local, np.float64, lambda y, v: Pj.ldiv_(y, v)), log=True)
+    assert h3.iters == h4.iters and relerr(x4, x3) <= 1e-10
+
+
+def test_shifted_operator_by_callback_all_solvers(isb, oracle):
+    """A matrix-free operator built from library calls inside the callback: B = A + sigma I (mul: y = A x, then
+    y += sigma x), solved by cg / qmr / idrs / lsqr / lsmr and compared with the assembled matrix."""
+    rng = np.random.default_rng(SEED)
+    n, sigma = 2000, 0.75
+    M = sp.random(n, n, 0.004, random_state=5, format="csc")
+    M = (M + M.T + 8 * sp.eye(n)).tocsc()                     # symmetric positive definite, so cg applies too
+    A = isb.B200CSR.from_scipy(M)
+    L = isb.lib()
+    calls = {"mul": 0}
+
+    def mul(y, x):
+        calls["mul"] += 1
+        A.mul_(y, x)
+        assert L.b200_axpby(A.ctx._h, n, sigma, x._p, 1.0, y._p, 0) == 0
+
+    B = isb.B200LinearOperator((n, n), np.float64, mul, adjoint_mul=mul)     # symmetric: A' = A
+    Bs = isb.B200CSR.from_scipy((M + sigma * sp.eye(n)).tocsc())
+    b = rng.standard_normal(n)
+    for name, kw in (("cg", {}), ("qmr", {}), ("idrs", dict(s=4, rng=np.random.default_rng(1))),
+                     ("lsqr", dict(atol=1e-12, btol=1e-12)), ("lsmr", dict(atol=1e-12, btol=1e-12))):
+        fn = getattr(isb, name)
+        before = calls["mul"]
+        kw2 = dict(kw)
+        if name == "idrs":
+            kw2["rng"] = np.random.default_rng(1)
+        x_cb, h_cb = fn(B, b, log=True, **kw)
+        x_as, h_as = fn(Bs, b, log=True, **kw2)
+        assert calls["mul"] > before
+        assert h_cb.isconverged and h_as.isconverged and abs(h_cb.iters - h_as.iters) <= 1, name
+        assert relerr(x_cb, x_as) <= 1e-8, name
+        assert relerr((M + sigma * sp.eye(n)) @ x_cb, b) <= 1e-6, name
+
+
+def test_callback_errors_surface_as_python_exceptions(isb):
+    n = 64
+    A = isb.B200CSR.from_scipy((sp.eye(n) * 2.0).tocsc())
+
+    def bad(y, x):
+        raise RuntimeError("operator failed")
+
+    op = isb.B200LinearOperator((n, n), np.float64, bad)
+    with pytest.raises(RuntimeError, match="operator failed"):
+        isb.cg(op, np.ones(n))
+    with pytest.raises(TypeError):
+        isb.qmr(isb.B200LinearOperator((n, n), np.float64, lambda y, x: A.mul_(y, x)), np.ones(n))   # no adjoint
+    # the library still works afterwards
+    x = isb.cg(A, np.ones(n))
+    assert relerr(x, 0.5 * np.ones(n)) <= 1e-12

@@ -6,6 +6,8 @@ A `runner` hides which of the two executes the engine:
     runner.lsqr / runner.lsmr(x0, A, b, **kw) -> x, R   (R.iters, R.istop, R.converged, R.mvps, R.mtvps, R.hist{...},
                                                         R.ctol, R.early, R.bad_x)
     runner.idrs(x0, A, b, P, diag=None, **kw) -> x, R
+    runner.cg(x0, A, b, mode, d, **kw)    -> x, R   general-operator cg!: mode "cg" (Identity), "jacobi" (diagonal d
+                                                    through the fused division), "callback" (ldiv! by callback)
 A is a scipy sparse matrix; x0 is updated in place and returned.
 """
 import math
@@ -202,3 +204,42 @@ def case_idrs_s16_maxiter_zero_iterations(oracle, runners):
         assert hs.iters == 2 and len(hs.hist) == 2
         xs, hs = run.idrs(x0.copy(), A, bb, P3, abstol=2 * r0, reltol=0.0)                        # :100-104
         assert hs.iters == 0 and hs.converged and np.array_equal(xs, x0)
+
+
+def case_cg_general_operator(oracle, runners, dtype, tol):
+    """cg! / pcg through the general-operator engine (csrc/cg_core.h): operator and preconditioner callbacks."""
+    rng = np.random.default_rng(3)
+    for N, dims in ((16, 2), (10, 3)):
+        L = oracle.laplace_matrix(dtype, N, dims, base=1).to_scipy().tocsr()
+        n = L.shape[0]
+        D = sp.diags(1.0 + rng.random(n)).astype(dtype)          # a non-constant diagonal, so that Jacobi matters
+        M = (D @ L @ D).tocsr().astype(dtype)
+        O = oracle.CSC.from_scipy(M.tocsc(), base=1)
+        b, x0 = rng.standard_normal(n).astype(dtype), rng.standard_normal(n).astype(dtype)
+        d = M.diagonal().astype(dtype)
+        for init_zero in (False, True):
+            start = np.zeros(n, dtype) if init_zero else x0
+            for mode in ("cg", "jacobi", "callback"):
+                Pl = oracle.JacobiPrec(d.copy()) if mode != "cg" else None
+                xo, ho = oracle.cg_(start.copy(), O, b, log=True, Pl=Pl, initially_zero=init_zero)
+                for run in runners:
+                    xs, hs = run.cg(start.copy(), M, b, mode, d, initially_zero=init_zero, check_every=5)
+                    assert hs.iters == ho.iters and hs.converged == ho.isconverged and hs.mvps == ho.mvps
+                    # unpreconditioned CG on this badly scaled matrix is the sensitive one (1e-10 between two orders)
+                    t = tol if mode != "cg" or dtype == np.float32 else max(tol, 2e-9)
+                    assert np.max(np.abs(hs.hist - ho["resnorm"])) <= t * ho["resnorm"][0], (N, mode)
+                    assert np.linalg.norm(xs - xo) <= t * np.linalg.norm(xo), (N, mode)
+    # reference termination tests (test/cg.jl:98-122) through the general engine
+    for T in (np.float32, np.float64):
+        A = sp.csr_matrix(tridiag(T))
+        bb = np.ones(3, dtype=T)
+        x0 = np.linalg.solve(A.toarray().astype(np.float64), bb.astype(np.float64)).astype(T)
+        pert = (10 * math.sqrt(np.finfo(T).eps) * np.array([-1, 1, -1])).astype(T)
+        r0 = np.linalg.norm(A @ (x0 + pert) - bb)
+        for run in runners:
+            xs, hs = run.cg(x0 + pert, A, bb, "cg", None)
+            assert 2 <= hs.iters <= 3
+            xs, hs = run.cg(x0 + pert, A, bb, "cg", None, abstol=2 * r0, reltol=0.0)
+            assert hs.iters == 0
+            xs, hs = run.cg(np.zeros(3, dtype=T), A, np.zeros(3, dtype=T), "cg", None, initially_zero=True)   # :50-51
+            assert hs.iters == 0 and np.all(xs == 0)
