@@ -427,6 +427,27 @@ B200_API int b200_lobpcg_solve(b200_ctx *ctx, const b200_csr *A, void *X_dev, in
                                const b200_lobpcg_opts *opts, b200_lobpcg_result *res, double *lambda_host,
                                double *resnorm_host);
 
+/* The constraint of lobpcg (`C` keyword, reference src/lobpcg.jl:829; struct Constraint :144-224): a basis Y the Ritz
+ * vectors are kept orthogonal to.  Standard problem (B = I).  Y_dev: n_local x nc column-major (copied); `capacity`
+ * >= nc columns are reserved for b200_lobpcg_constraint_append, which mirrors update! (:188-206: the Cholesky factor
+ * of Y'Y is extended by an identity block -- the appended columns must be orthonormal and orthogonal to Y, as the
+ * converged Ritz vectors of a constrained solve are); that is how the nev > blocksize driver (:925-962) deflates
+ * the batches it has already computed.  _apply: X <- X - Y (Y'Y \ Y'X) on a column-major block (:212-224). */
+typedef struct b200_lobpcg_constraint b200_lobpcg_constraint;
+B200_API int b200_lobpcg_constraint_create(b200_ctx *ctx, int64_t n_local, const void *Y_dev, int64_t ldy, int nc,
+                                           int capacity, int dtype, b200_lobpcg_constraint **out);
+B200_API int b200_lobpcg_constraint_append(b200_ctx *ctx, b200_lobpcg_constraint *c, const void *X_dev, int64_t ldx,
+                                           int k);
+B200_API int b200_lobpcg_constraint_apply(b200_ctx *ctx, const b200_lobpcg_constraint *c, void *X_dev, int64_t ldx,
+                                          int bs);
+B200_API int b200_lobpcg_constraint_info(const b200_lobpcg_constraint *c, int *nc, int *capacity);
+B200_API int b200_lobpcg_constraint_destroy(b200_lobpcg_constraint *c);
+/* lobpcg(A, largest, X0; C, ...): b200_lobpcg_solve with the constraint applied to the initial block (:868) and to the
+ * preconditioned active residuals of every step (precond_constr! :564-569).  C == NULL is b200_lobpcg_solve. */
+B200_API int b200_lobpcg_solve_constrained(b200_ctx *ctx, const b200_csr *A, void *X_dev, int64_t ldx,
+                                           const b200_lobpcg_opts *opts, const b200_lobpcg_constraint *C,
+                                           b200_lobpcg_result *res, double *lambda_host, double *resnorm_host);
+
 /* Host-side dense helpers used by the engines for their O(blocksize^3) pieces (fp64, column-major,
  * n <= 64): eigen!(Hermitian(A)[, Hermitian(B)]) -- eigenvalues ascending in w, eigenvectors in the
  * columns of Z with Z'BZ = I (reference src/lobpcg.jl:615,622 -> LAPACK syevd / sygvd).  B may be NULL.

@@ -416,6 +416,28 @@ function idrs!(x::Vector{T}, A::B200CSR{T}, b::Vector{T};
     log ? (x, history(res, hist, abstol, reltol)) : x
 end
 
+# ------------------------------------------------------------------------------------------- lobpcg: constraint, nev driver
+mutable struct B200Constraint{T}                     # Constraint(Y, nothing, X)  src/lobpcg.jl:144-224 (B = I)
+    h::Ptr{Cvoid}
+    ctx::Ctx
+end
+function B200Constraint(A::B200CSR{T}, Y::Matrix{T}; capacity::Integer = size(Y, 2)) where {T}
+    Yd = B200Vector(A.ctx, vec(Y)); r = Ref{Ptr{Cvoid}}()
+    check(ccall((:b200_lobpcg_constraint_create, LIB), Cint,
+                (Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
+                A.ctx.h, size(Y, 1), Yd.p, size(Y, 1), size(Y, 2), capacity, dtype_code(T), r))
+    finalizer(c -> ccall((:b200_lobpcg_constraint_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), B200Constraint{T}(r[], A.ctx))
+end
+# update!(constr!, X[:, 1:k], ...)  src/lobpcg.jl:188-206
+update!(c::B200Constraint, Xd::B200Vector, n::Integer, k::Integer) =
+    check(ccall((:b200_lobpcg_constraint_append, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Cint),
+                c.ctx.h, c.h, Xd.p, n, k))
+# lobpcg(A, largest, X0; C = Y, ...): as `lobpcg` above with
+#   ccall((:b200_lobpcg_solve_constrained, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{LobpcgOpts},
+#         Ptr{Cvoid}, Ref{LobpcgResult}, Ptr{Float64}, Ptr{Float64}), A.ctx.h, A.h, Xd.p, n, o, c.h, res, λ, rn)
+# lobpcg(A, largest, X0, nev; ...) (src/lobpcg.jl:925-962) is the same host loop as iterativesolvers.jl_b200/solvers.py:
+# solve a block, update!(constraint, converged columns), rand! the block, repeat.
+
 # ------------------------------------------------------------------------------------------- matrix-free operators
 # Anything with mul!(y::B200Vector, A, x::B200Vector) (a LinearMap over device vectors, a user type, a closure) can be
 # handed to the fused engines: the C library calls back between two of its kernels (b200_linop), on its own stream.

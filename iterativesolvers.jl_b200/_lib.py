@@ -182,6 +182,13 @@ SIGNATURES = {
                                   C.POINTER(LsqResult), _P, _I64]),
     "b200_idrs_solve_op": (_INT, [_P, C.POINTER(LinOp), _P, _P, C.POINTER(IdrsOpts), C.POINTER(Result), _P, _I64]),
     "b200_lobpcg_solve": (_INT, [_P, _P, _P, _I64, C.POINTER(LobpcgOpts), C.POINTER(LobpcgResult), _P, _P]),
+    "b200_lobpcg_constraint_create": (_INT, [_P, _I64, _P, _I64, _INT, _INT, _INT, C.POINTER(_P)]),
+    "b200_lobpcg_constraint_append": (_INT, [_P, _P, _P, _I64, _INT]),
+    "b200_lobpcg_constraint_apply": (_INT, [_P, _P, _P, _I64, _INT]),
+    "b200_lobpcg_constraint_info": (_INT, [_P, C.POINTER(_INT), C.POINTER(_INT)]),
+    "b200_lobpcg_constraint_destroy": (_INT, [_P]),
+    "b200_lobpcg_solve_constrained": (_INT, [_P, _P, _P, _I64, C.POINTER(LobpcgOpts), _P, C.POINTER(LobpcgResult), _P,
+                                             _P]),
     "b200_dense_sygv_host": (_INT, [_INT, _P, _P, _P, _P]),
 }
 

@@ -23,6 +23,7 @@
 // active blocks alias R/P/AP (no copies).
 // The contractions are fp32/fp64 FMA on CUDA cores: at bs = 16 they are HBM-bound (4 flop/byte) and TF32
 // tensor cores would cost the fp32 eigenvalue parity.
+#include "lobpcg_constraint.cuh"
 #include "blas1.cuh"
 #include "dense_small.h"
 #include "spmv_stream.cuh"
@@ -1058,7 +1059,7 @@ struct Lobpcg {
 
 template <typename T>
 int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b200_lobpcg_opts *o,
-                b200_lobpcg_result *res, double *lambda_host, double *resnorm_host) {
+                const b200_lobpcg_constraint *C, b200_lobpcg_result *res, double *lambda_host, double *resnorm_host) {
   cudaStream_t st = ctx->stream;
   const int64_t n = A->m_local;
   const int sizeX = o->blocksize;
@@ -1104,6 +1105,7 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
   }
   k_to_rowmajor<T><<<L.grid_vec, kThreads, 0, st>>>(Xcm, L.X, n, sizeX);
   B200_LAUNCH_CHECK(ctx);
+  if (C) B200_TRY(constraint_apply_block(ctx, C, L.X, BS, 1, sizeX));   // iterator.constr!(X, temp) :868 / :875
 
   std::vector<double> ritz(3 * sizeX, 0.0), residuals(sizeX, NAN);                                  // :473-477
   std::vector<char> mask(sizeX, 1);
@@ -1202,6 +1204,7 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
         k_block_jacobi<T><<<L.grid_vec, kThreads, 0, st>>>(aR, n, jac);
         B200_LAUNCH_CHECK(ctx);
       }
+      if (C) B200_TRY(constraint_apply_block(ctx, C, aR, BS, 1, bs));                               // constr!(R[:,1:bs]) :567
       status = L.cholqr(aR, nullptr, bs);                                                           // :524-532
       if (status) break;
       B200_TRY(L.spmm(aR, L.AR));
@@ -1310,8 +1313,26 @@ int b200_lobpcg_solve(b200_ctx *ctx, const b200_csr *A, void *X_dev, int64_t ldx
   B200_REQUIRE(is_square(A), "this solver needs a square operator (got %lld x %lld)", (long long)A->m_global,
                (long long)A->n_global);
   B200_CUDA(cudaSetDevice(ctx->device));
-  return A->dtype == B200_F64 ? lobpcg_impl<double>(ctx, A, (double *)X_dev, ldx, opts, res, lambda_host, resnorm_host)
-                              : lobpcg_impl<float>(ctx, A, (float *)X_dev, ldx, opts, res, lambda_host, resnorm_host);
+  return A->dtype == B200_F64
+             ? lobpcg_impl<double>(ctx, A, (double *)X_dev, ldx, opts, nullptr, res, lambda_host, resnorm_host)
+             : lobpcg_impl<float>(ctx, A, (float *)X_dev, ldx, opts, nullptr, res, lambda_host, resnorm_host);
+}
+
+int b200_lobpcg_solve_constrained(b200_ctx *ctx, const b200_csr *A, void *X_dev, int64_t ldx,
+                                  const b200_lobpcg_opts *opts, const b200_lobpcg_constraint *C,
+                                  b200_lobpcg_result *res, double *lambda_host, double *resnorm_host) {
+  B200_REQUIRE(ctx && A && X_dev && opts, "NULL argument");
+  B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
+  B200_REQUIRE(is_square(A), "this solver needs a square operator (got %lld x %lld)", (long long)A->m_global,
+               (long long)A->n_global);
+  if (C) {
+    B200_REQUIRE(C->ctx == ctx && C->dtype == A->dtype && C->n == A->m_local,
+                 "the constraint does not match the operator (context, eltype or local rows)");
+  }
+  B200_CUDA(cudaSetDevice(ctx->device));
+  return A->dtype == B200_F64
+             ? lobpcg_impl<double>(ctx, A, (double *)X_dev, ldx, opts, C, res, lambda_host, resnorm_host)
+             : lobpcg_impl<float>(ctx, A, (float *)X_dev, ldx, opts, C, res, lambda_host, resnorm_host);
 }
 
 int b200_dense_sygv_host(int n, const double *A, const double *B, double *w, double *Z) {

@@ -635,33 +635,164 @@ class LOBPCGResults:
     trace: list
 
 
-def lobpcg(A, largest: bool, X0, *, P=None, tol=None, maxiter=200, log=False, _fixed_iterations=False):
-    """lobpcg(A, largest, X0; P, tol, maxiter) -> LOBPCGResults (standard problem, B = I, no constraint).
-    X0: n x blocksize, host (numpy, any order) or DeviceArray (column-major)."""
+class LobpcgConstraint:
+    """Constraint(Y, nothing, X) -- reference src/lobpcg.jl:144-224 (standard problem): a basis Y (n x nc, host array
+    or DeviceArray; copied) the Ritz vectors are kept orthogonal to.  `capacity` columns are reserved for `append`
+    (update!, :188-206)."""
+
+    def __init__(self, ctx, n, dtype, Y=None, capacity=0):
+        self.ctx, self.n, self.dtype = ctx, int(n), np.dtype(dtype)
+        self._h = C.c_void_p()
+        nc = 0 if Y is None else int(Y.shape[1])
+        Yd = None
+        if nc:
+            Yd = Y if is_device(Y) else DeviceArray.from_numpy(ctx, np.asfortranarray(Y, dtype=self.dtype))
+            if Yd.shape[0] != self.n:
+                raise ValueError("the constraint must have as many rows as the operator")
+        check(lib().b200_lobpcg_constraint_create(ctx._h, self.n, as_device_ptr(Yd) if nc else None, self.n, nc,
+                                                  int(max(capacity, nc)), _lib.F64 if self.dtype == np.float64 else _lib.F32,
+                                                  C.byref(self._h)))
+
+    @property
+    def ncols(self):
+        k, cap = C.c_int(), C.c_int()
+        check(lib().b200_lobpcg_constraint_info(self._h, C.byref(k), C.byref(cap)))
+        return k.value
+
+    def append(self, Xd: DeviceArray, k=None):
+        """update!(constraint, X[:, 1:k], ...): the first k columns of the device block Xd join the basis."""
+        k = Xd.shape[1] if k is None else int(k)
+        check(lib().b200_lobpcg_constraint_append(self.ctx._h, self._h, as_device_ptr(Xd), Xd.shape[0], k))
+
+    def apply_(self, Xd: DeviceArray):
+        """constr!(X, temp): X <- X - Y (Y'Y \\ Y'X), in place on a device block."""
+        bs = Xd.shape[1] if len(Xd.shape) == 2 else 1
+        check(lib().b200_lobpcg_constraint_apply(self.ctx._h, self._h, as_device_ptr(Xd), Xd.shape[0], bs))
+        return Xd
+
+    def close(self):
+        if self._h:
+            lib().b200_lobpcg_constraint_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _lobpcg_block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, fixed):
+    """lobpcg!(iterator; ...) -- reference src/lobpcg.jl:865-893 on the device block Xd (overwritten)."""
+    n, bs = Xd.shape
+    if not not_zeros and not fixed:                            # :869-876 (the constraint itself is applied by the engine)
+        nrm = C.c_double()
+        for j in range(bs):                                    # all(x -> x == 0, X[:, j])  <=>  ||X[:, j]|| == 0
+            col = Xd.column(j)
+            check(lib().b200_nrm2(A.ctx._h, n, col._p, col.code, C.byref(nrm)))
+            if nrm.value == 0.0:
+                rng = rng or np.random.default_rng()
+                col.upload(rng.random(n).astype(A.dtype))      # X[:, j] .= rand.() :872
+    opts = _lib.LobpcgOpts(float(tol), int(maxiter), int(bool(largest)), int(bs), precond_to_c(P, A), int(bool(fixed)), 0)
+    res = _lib.LobpcgResult()
+    lam = np.zeros(bs, dtype=np.float64)
+    rn = np.zeros(bs, dtype=np.float64)
+    if constraint is None:
+        status = lib().b200_lobpcg_solve(A.ctx._h, A._h, as_device_ptr(Xd), n, C.byref(opts), C.byref(res),
+                                         lam.ctypes.data_as(C.c_void_p), rn.ctypes.data_as(C.c_void_p))
+    else:
+        status = lib().b200_lobpcg_solve_constrained(A.ctx._h, A._h, as_device_ptr(Xd), n, C.byref(opts), constraint._h,
+                                                     C.byref(res), lam.ctypes.data_as(C.c_void_p),
+                                                     rn.ctypes.data_as(C.c_void_p))
+    if status == _lib.ERR_BREAKDOWN:
+        raise np.linalg.LinAlgError("PosDefException in CholQR (reference src/lobpcg.jl:380)")
+    check(status)
+    return lam, rn, res
+
+
+def lobpcg(A, largest: bool, X0, nev=None, *, P=None, C_=None, tol=None, maxiter=200, log=False, not_zeros=False,
+           rng=None, _fixed_iterations=False, **kw):
+    """lobpcg(A, largest, X0; P, C, tol, maxiter, not_zeros) -> LOBPCGResults        reference src/lobpcg.jl:824-839
+    lobpcg(A, largest, nev::Int; ...)   (X0 = rand(n, nev), not_zeros = true)        :787-792
+    lobpcg(A, largest, X0, nev; ...)    (batches of size(X0, 2) with deflation)       :925-962
+    Standard problem (B = I).  The constraint is the keyword `C` (spelled `C=` here; `C_` is accepted as well):
+    an n x nc host array / DeviceArray, or a LobpcgConstraint.  X0: n x blocksize, host (numpy, any order) or
+    DeviceArray (column-major)."""
+    Cc = kw.pop("C", C_)
+    if kw:
+        raise TypeError(f"unexpected keyword arguments {sorted(kw)}")
     _check_operator(A)
     if tol is None:
         tol = _eps(A.dtype) ** 0.3                             # default_tolerance  src/lobpcg.jl:751
+    if isinstance(X0, (int, np.integer)):                      # lobpcg(A, largest, nev) :790-792
+        rng = rng or np.random.default_rng()
+        X0 = rng.random((A.m_local, int(X0))).astype(A.dtype)
+        not_zeros = True
     host = not is_device(X0)
     Xd = DeviceArray.from_numpy(A.ctx, np.asarray(X0, dtype=A.dtype)) if host else X0
     n, bs = Xd.shape
     if n != A.m_local:
         raise ValueError("X0 has the wrong number of rows")
+    if nev is not None and int(nev) > A.n_global:
+        raise B200Error("Number of eigenvectors desired exceeds the row dimension.")          # :933
     if n < 3 * bs:
-        # src/lobpcg.jl:833: throw("n must be at least 3 times the block size")
+        # src/lobpcg.jl:834: throw("... not stable to use when the matrix size is less than 3 times the block size ...")
         raise B200Error("The order of the matrix must be at least 3 times the block size")
-    opts = _lib.LobpcgOpts(float(tol), int(maxiter), int(bool(largest)), int(bs), precond_to_c(P, A),
-                           int(bool(_fixed_iterations)), 0)
-    res = _lib.LobpcgResult()
-    lam = np.zeros(bs, dtype=np.float64)
-    rn = np.zeros(bs, dtype=np.float64)
-    status = lib().b200_lobpcg_solve(A.ctx._h, A._h, as_device_ptr(Xd), n, C.byref(opts), C.byref(res),
-                                     lam.ctypes.data_as(C.c_void_p), rn.ctypes.data_as(C.c_void_p))
-    if status == _lib.ERR_BREAKDOWN:
-        raise np.linalg.LinAlgError("PosDefException in CholQR (reference src/lobpcg.jl:380)")
-    check(status)
-    X = Xd.numpy() if host else Xd
-    return LOBPCGResults(lam.astype(A.dtype), X, float(tol), rn.astype(A.dtype), int(res.iterations), int(maxiter),
-                         bool(res.converged), [])
+    if nev is None:
+        con = Cc if isinstance(Cc, LobpcgConstraint) or Cc is None else LobpcgConstraint(A.ctx, n, A.dtype, Cc)
+        lam, rn, res = _lobpcg_block(A, largest, Xd, P, con, tol, maxiter, not_zeros, rng, _fixed_iterations)
+        X = Xd.numpy() if host else Xd
+        return LOBPCGResults(lam.astype(A.dtype), X, float(tol), rn.astype(A.dtype), int(res.iterations), int(maxiter),
+                             bool(res.converged), [])
+    # ---- nev > blocksize driver :928-962
+    nev = int(nev)
+    rng = rng or np.random.default_rng()
+    sizeX = min(nev, bs)                                       # :936
+    if sizeX < bs:                                             # X = X0[:, 1:sizeX] :937
+        Xd = DeviceArray.from_numpy(A.ctx, np.asfortranarray(Xd.numpy()[:, :sizeX]))
+    elif not host:
+        Xd = DeviceArray.from_numpy(A.ctx, Xd.numpy())         # X0 is not overwritten by this form
+    sizeC = 0 if Cc is None else int(Cc.shape[1])
+    con = LobpcgConstraint(A.ctx, n, A.dtype, Cc, capacity=sizeC + (nev // sizeX) * sizeX)       # :501-508, :519
+    lam_all = np.zeros(nev, dtype=A.dtype)
+    rn_all = np.zeros(nev, dtype=A.dtype)
+    X_all = np.zeros((n, nev), dtype=A.dtype, order="F")
+    iterations, conv = [], np.zeros(nev, dtype=bool)
+
+    def run(nz):
+        lam, rn, res = _lobpcg_block(A, largest, Xd, P, con, tol, maxiter, nz, rng, False)
+        return lam, rn, res, Xd.numpy()
+
+    def append(r, n1, n2):                                     # append! :79-91
+        lam, rn, res, Xh = r
+        lam_all[n1:n1 + n2] = lam[-n2:]
+        rn_all[n1:n1 + n2] = rn[-n2:]
+        X_all[:, n1:n1 + n2] = Xh[:, -n2:]
+        iterations.append(int(res.iterations))
+        conv[n1:n1 + n2] = bool(res.converged)
+
+    r = run(not_zeros)                                         # :941
+    append(r, 0, sizeX)
+    converged_x = sizeX
+    while converged_x < nev:                                   # :944
+        Xh = r[3]
+        if nev - converged_x < sizeX:                          # :945-952
+            cutoff = sizeX - (nev - converged_x)
+            con.append(Xd, cutoff)                             # update!(constr!, X[:, 1:cutoff], ...)
+            Xh[:, :sizeX - cutoff] = Xh[:, cutoff:sizeX].copy()
+            Xh[:, cutoff:sizeX] = rng.random((n, sizeX - cutoff)).astype(A.dtype)
+            Xd.upload(Xh)
+            r = run(True)
+            append(r, converged_x, sizeX - cutoff)
+            converged_x += sizeX - cutoff
+        else:                                                  # :953-959
+            con.append(Xd)
+            Xd.upload(rng.random((n, sizeX)).astype(A.dtype))
+            r = run(True)
+            append(r, converged_x, sizeX)
+            converged_x += sizeX
+    con.close()
+    return LOBPCGResults(lam_all, X_all, float(tol), rn_all, iterations, int(maxiter), conv, [])
 
 
 # ------------------------------------------------------------------------------------------------

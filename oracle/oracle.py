@@ -864,16 +864,46 @@ def _cholqr(X, BX, AX=None, update_AX=False, update_BX=False, generalized=False)
         _rdiv_upper(BX, R)
 
 
-def lobpcg(A, largest, X0, *, B=None, P=None, tol=None, maxiter=200, log=False, not_zeros=False, rng=None,
-           fixed_iterations=False):
-    """lobpcg(A, [B,] largest, X0; P, tol, maxiter, log) -- reference src/lobpcg.jl:827-839 +
+class Constraint:
+    """Constraint(Y, B, X) -- reference src/lobpcg.jl:144-224: deflation of a block against span(Y) in the
+    B inner product.  `update` mirrors update! (:188-206): the Cholesky factor is EXTENDED BY AN IDENTITY BLOCK
+    for the appended columns (they are B-orthonormal Ritz vectors, B-orthogonal to the old Y), not recomputed."""
+
+    def __init__(self, Y, B=None):
+        self.B = B
+        self.Y = np.array(Y, order="F", copy=True)
+        self.BY = self.Y if B is None else np.asfortranarray(mul(B, self.Y))      # :163-168
+        g = self.Y.conj().T @ self.BY                                               # :178
+        g[np.diag_indices_from(g)] = g.diagonal().real                              # realdiag! :181
+        self.U = np.linalg.cholesky(g).conj().T if g.size else g                   # cholesky!(Hermitian(.)) :182 (upper)
+
+    def update(self, X, BX):                                                        # update! :188-206
+        k, m = self.Y.shape[1], X.shape[1]
+        self.Y = np.asfortranarray(np.hstack([self.Y, X]))
+        self.BY = self.Y if self.B is None else np.asfortranarray(np.hstack([self.BY, BX]))
+        U = np.eye(k + m, dtype=self.U.dtype if self.U.size else X.dtype)
+        U[:k, :k] = self.U
+        self.U = U
+
+    def apply(self, X):                                                             # (constr!::Constraint)(X, X_temp) :212-224
+        if self.Y.shape[1] > 0:
+            import scipy.linalg as sla
+            g = self.BY.conj().T @ X                                                # :217
+            t = sla.solve_triangular(self.U, sla.solve_triangular(self.U, g, trans="C"))   # ldiv!(tmp, gram_chol, g) :219
+            X -= (self.Y @ t).astype(X.dtype)                                       # :220-221
+
+
+def lobpcg(A, largest, X0, *, B=None, P=None, C=None, tol=None, maxiter=200, log=False, not_zeros=False, rng=None,
+           fixed_iterations=False, _constraint=None, _copy=True):
+    """lobpcg(A, [B,] largest, X0; P, C, tol, maxiter, log, not_zeros) -- reference src/lobpcg.jl:827-839 +
     lobpcg!(iterator) :865-893 + the step functor :692-749.  `fixed_iterations` (not in the
-    reference) disables soft-locking and the early exit so that throughput runs do constant work."""
+    reference) disables soft-locking and the early exit so that throughput runs do constant work.
+    `_constraint` / `_copy=False` are used by lobpcg_nev (the iterator keeps X and its Constraint between batches)."""
     import scipy.linalg as sla
     T = X0.dtype
     if tol is None:
         tol = float(np.finfo(T).eps) ** 0.3                             # default_tolerance :751
-    X = np.array(X0, dtype=T, order="F", copy=True)                     # X = copy(X0) :830
+    X = np.array(X0, dtype=T, order="F", copy=True) if _copy else X0    # X = copy(X0) :830
     n, sizeX = X.shape
     if sizeX > n:
         raise ValueError("X column dimension exceeds the row dimension")            # :833
@@ -881,11 +911,16 @@ def lobpcg(A, largest, X0, *, B=None, P=None, tol=None, maxiter=200, log=False, 
         raise ValueError("The LOBPCG algorithms is not stable to use when the matrix size is less than 3 times "
                          "the block size. Please use a dense solver instead.")       # :834
     generalized = B is not None
-    if not not_zeros:                                                   # :868-876
+    constr = _constraint if _constraint is not None else (Constraint(C, B) if C is not None else None)   # :452
+    if constr is not None:
+        constr.apply(X)                                                 # :868
+    if not not_zeros:                                                   # :869-876
         rng = rng or np.random.default_rng(0)
         for j in range(sizeX):
             if np.all(X[:, j] == 0):
                 X[:, j] = rng.random(n).astype(T)
+        if constr is not None:
+            constr.apply(X)                                             # :875
     AXb = np.zeros_like(X)
     BXb = np.zeros_like(X) if generalized else X
     R = np.zeros_like(X); AR = np.zeros_like(X); BR = np.zeros_like(X) if generalized else None
@@ -942,6 +977,8 @@ def lobpcg(A, largest, X0, *, B=None, P=None, tol=None, maxiter=200, log=False, 
                 aAP = np.array(AP[:, mask], order="F")
                 aBP = np.array(BP[:, mask], order="F") if generalized else aP
             precond(aR)                                                 # precond_constr! :564-569
+            if constr is not None:
+                constr.apply(aR)                                        # :567
             aBR = np.asfortranarray(mul(B, aR)) if generalized else aR  # ortho_AB_mul_X! :524-532
             _cholqr(aR, aBR, update_BX=True, generalized=generalized)
             aAR = np.asfortranarray(mul(A, aR))
@@ -1000,7 +1037,64 @@ def lobpcg(A, largest, X0, *, B=None, P=None, tol=None, maxiter=200, log=False, 
             break
         iteration += 1                                                  # :886
     lam = ritz[:sizeX].copy()
-    return LOBPCGResults(lam, X, tol, residuals.copy(), iteration, maxiter, bool(np.all(residuals <= tol)), trace)
+    res = LOBPCGResults(lam, X, tol, residuals.copy(), iteration, maxiter, bool(np.all(residuals <= tol)), trace)
+    res.BX = BXb
+    return res
+
+
+def lobpcg_nev(A, largest, X0, nev, *, B=None, P=None, C=None, tol=None, maxiter=200, log=False, not_zeros=False,
+               rng=None):
+    """lobpcg(A, [B,] largest, X0, nev; ...) -- reference src/lobpcg.jl:925-962: batches of size(X0, 2) Ritz pairs,
+    every converged batch appended to the constraint (update!, :947/:954) and the block refilled with rand!."""
+    T = X0.dtype
+    rng = rng or np.random.default_rng(0)
+    n, sizeX = X0.shape
+    if nev > n:
+        raise ValueError("Number of eigenvectors desired exceeds the row dimension.")          # :933
+    if 3 * sizeX > n:
+        raise ValueError("The LOBPCG algorithms is not stable to use when the matrix size is less than 3 times "
+                         "the block size. Please use a dense solver instead.")                # :934
+    if tol is None:
+        tol = float(np.finfo(T).eps) ** 0.3
+    sizeX = min(nev, sizeX)                                             # :936
+    X = np.array(X0[:, :sizeX], dtype=T, order="F", copy=True)         # :937
+    constr = Constraint(np.zeros((n, 0), dtype=T) if C is None else C, B)   # LOBPCGIterator(..., nev, P, C) :497-522
+    lam = np.zeros(nev, dtype=T)
+    resn = np.zeros(nev, dtype=_real_dtype(T))
+    Xall = np.zeros((n, nev), dtype=T, order="F")
+    iterations, conv = [], np.zeros(nev, dtype=bool)
+
+    def run(nz):
+        return lobpcg(A, largest, X, B=B, P=P, tol=tol, maxiter=maxiter, log=log, not_zeros=nz, rng=rng,
+                      _constraint=constr, _copy=False)
+
+    def append(r, n1, n2):                                              # append! :79-91
+        lam[n1:n1 + n2] = r.lam[-n2:]
+        resn[n1:n1 + n2] = r.residual_norms[-n2:]
+        Xall[:, n1:n1 + n2] = r.X[:, -n2:]
+        iterations.append(r.iterations)
+        conv[n1:n1 + n2] = r.converged
+
+    r = run(not_zeros)                                                  # :941
+    append(r, 0, sizeX)
+    converged_x = sizeX
+    while converged_x < nev:                                            # :944
+        BX = r.BX if B is not None else X
+        if nev - converged_x < sizeX:                                   # :945-952
+            cutoff = sizeX - (nev - converged_x)
+            constr.update(X[:, :cutoff].copy(), BX[:, :cutoff].copy())
+            X[:, :sizeX - cutoff] = X[:, cutoff:sizeX].copy()
+            X[:, cutoff:sizeX] = rng.random((n, sizeX - cutoff)).astype(T)
+            r = run(True)
+            append(r, converged_x, sizeX - cutoff)
+            converged_x += sizeX - cutoff
+        else:                                                           # :953-959
+            constr.update(X.copy(), BX.copy())
+            X[...] = rng.random((n, sizeX)).astype(T)
+            r = run(True)
+            append(r, converged_x, sizeX)
+            converged_x += sizeX
+    return LOBPCGResults(lam, Xall, tol, resn, iterations, maxiter, conv, [])
 
 
 # ============================================================================================

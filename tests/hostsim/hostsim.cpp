@@ -22,6 +22,7 @@
 #include "../../iterativesolvers.jl_b200/csrc/lsmr_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/idrs_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/cg_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/lobpcg_constraint_core.h"
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -232,4 +233,26 @@ EXPORT int hostsim_cg(int is_f64, const hostsim_csr *A, const hostsim_csr *Pl, c
   out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
   out->passes = be.passes; out->applies = be.applies;
   return st;
+}
+
+// Constraint (reference src/lobpcg.jl:144-224): factor Y'Y, optionally extend the factor by an identity block for the
+// last `appended` columns (update! :188-206), and deflate the block X (strides rs, cs; bs <= 16 columns).
+EXPORT int hostsim_constraint_apply(int is_f64, int64_t n, const void *Y, int64_t ldy, int nc, int appended, void *X,
+                                    int64_t rs, int64_t cs, int bs, int order, int split) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  const int nc0 = nc - appended;
+  std::vector<double> g_dev((size_t)(nc > 0 ? nc : 1) * b200::kConBlock), g_host(g_dev.size()), U0((size_t)nc0 * nc0);
+  int st = is_f64 ? b200::constraint_factor<double>(be, (const double *)Y, ldy, nc0, n, g_dev.data(), g_host.data(), U0.data())
+                  : b200::constraint_factor<float>(be, (const float *)Y, ldy, nc0, n, g_dev.data(), g_host.data(), U0.data());
+  if (st) return st;
+  std::vector<double> U((size_t)nc * nc, 0.0);
+  for (int j = 0; j < nc0; ++j)
+    for (int i = 0; i <= j; ++i) U[i + (size_t)j * nc] = U0[i + (size_t)j * nc0];
+  for (int j = nc0; j < nc; ++j) U[j + (size_t)j * nc] = 1.0;
+  return is_f64 ? b200::constraint_apply<double>(be, (const double *)Y, ldy, nc, U.data(), (double *)X, rs, cs, bs, n,
+                                                 g_dev.data(), g_host.data())
+                : b200::constraint_apply<float>(be, (const float *)Y, ldy, nc, U.data(), (float *)X, rs, cs, bs, n,
+                                                g_dev.data(), g_host.data());
 }

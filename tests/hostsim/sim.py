@@ -174,3 +174,24 @@ def cg_(x, A, b, *, Pl=None, diag=None, abstol=0.0, reltol=-1.0, maxiter=-1, ini
                           hist.ctypes.data_as(C.c_void_p), C.c_int(order), C.c_int(split), C.byref(out))
     assert st == 0, st
     return x, _outcome(out, hist)
+
+
+def constraint_apply_(X, Y, *, appended=0, row_major=False, order=0, split=0):
+    """the Constraint passes (csrc/lobpcg_constraint_core.h) on the serial backend: X <- X - Y (chol(Y'Y) \\ Y'X).
+    X: n x bs (bs <= 16); row_major: X is laid out like the LOBPCG engine's internal n x 16 blocks."""
+    dt = X.dtype
+    Y = np.asfortranarray(Y, dtype=dt)
+    n, bs = X.shape
+    if row_major:
+        buf = np.zeros((n, 16), dtype=dt, order="C")
+        buf[:, :bs] = X
+        rs, cs = 16, 1
+    else:
+        buf = np.asfortranarray(X)
+        rs, cs = 1, n
+    st = lib().hostsim_constraint_apply(C.c_int(dt == np.float64), C.c_int64(n), C.c_void_p(Y.ctypes.data), C.c_int64(n),
+                                        C.c_int(Y.shape[1]), C.c_int(appended), C.c_void_p(buf.ctypes.data),
+                                        C.c_int64(rs), C.c_int64(cs), C.c_int(bs), C.c_int(order), C.c_int(split))
+    assert st == 0, st
+    X[...] = buf[:, :bs]
+    return X

@@ -287,3 +287,37 @@ def test_python_callback_trampoline_without_a_gpu():
     # the C struct really carries the thunk
     fn = C.cast(op._c.apply, C.c_void_p).value
     assert fn and fn == C.cast(op._cb, C.c_void_p).value
+
+
+# ------------------------------------------------------------------------------------------ LOBPCG constraint, nev driver
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("largest", [True, False])
+def test_oracle_lobpcg_constraint_and_nev_reference_properties(oracle, dtype, largest):
+    """test/lobpcg.jl:213-228 (Constraint), :291-306 (nev = 3, block size 1 and 2), :324-342 (nev + Constraint)."""
+    rng = np.random.default_rng(123)
+    n = 10
+    tol = float(np.finfo(dtype).eps) ** 0.3
+    A = rng.random((n, n)).astype(dtype)
+    A = A.T + A + 20 * np.eye(n, dtype=dtype)
+    r = oracle.lobpcg(A, largest, rng.random((n, 1)).astype(dtype), tol=tol, maxiter=10 ** 6, not_zeros=True)
+    X1 = r.X.copy()
+    r2 = oracle.lobpcg(A, largest, rng.random((n, 1)).astype(dtype), C=X1.copy(), tol=tol, maxiter=10 ** 6,
+                       not_zeros=True)
+    assert np.linalg.norm(A @ r2.X - r2.X * r2.lam) <= tol and abs((X1.T @ r2.X)[0, 0]) <= 2 * n * tol
+    w = np.sort(np.linalg.eigvalsh(A.astype(np.float64)))
+    for block_size in (1, 2):
+        X0 = rng.random((n, block_size)).astype(dtype)
+        r3 = oracle.lobpcg_nev(A, largest, X0, 3, tol=tol, maxiter=10 ** 6, rng=rng)
+        assert np.max(np.linalg.norm(A @ r3.X - r3.X * r3.lam[None, :], axis=0)) <= tol
+        assert np.allclose(r3.X.T @ r3.X, np.eye(3), atol=2 * n * tol)
+        assert np.allclose(np.sort(r3.lam), w[-3:] if largest else w[:3], atol=10 * tol)
+        r4 = oracle.lobpcg_nev(A, largest, X0, 3, C=X1.copy(), tol=tol, maxiter=10 ** 6, rng=rng)
+        assert np.max(np.linalg.norm(A @ r4.X - r4.X * r4.lam[None, :], axis=0)) <= tol
+        assert np.allclose(r4.X.T @ r4.X, np.eye(3), atol=2 * n * tol) and np.all(np.abs(X1.T @ r4.X) <= 2 * n * tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-13), (np.float32, 2e-5)])
+def test_engine_constraint_passes_match_oracle(oracle, sim, dtype, tol):
+    fns = [lambda X, Y, app, rm=rm, o=o, s=s: sim.constraint_apply_(X, Y, appended=app, row_major=rm, order=o, split=s)
+           for rm in (False, True) for o, s in ((0, 0), (1, 1))]
+    cases.case_constraint_apply(oracle, fns, dtype, tol)

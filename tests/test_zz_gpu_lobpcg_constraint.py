@@ -1,0 +1,105 @@
+"""GPU tests for the LOBPCG constraint (`C` keyword, reference src/lobpcg.jl:144-224, :829) and the nev > blocksize
+driver (:925-962): the constraint passes through the C ABI against the oracle, constrained `lobpcg` against the
+oracle's, and the reference's own property tests (test/lobpcg.jl:213-228, :291-306, :324-342) on the device path.
+(Written after the round's GPU budget was spent: first executed by the round-end GPU run.)"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import widening_cases as cases
+
+pytestmark = pytest.mark.gpu
+SEED = 1234321
+
+
+@pytest.fixture(scope="module")
+def isb():
+    import iterativesolvers_jl_b200 as m
+    m.default_context()
+    return m
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-5)])
+def test_constraint_apply_matches_oracle(isb, oracle, dtype, tol):
+    ctx = isb.default_context()
+
+    def fn(X, Y, appended):
+        n, k = Y.shape[0], Y.shape[1] - appended
+        con = isb.LobpcgConstraint(ctx, n, dtype, Y[:, :k], capacity=Y.shape[1])
+        if appended:
+            con.append(isb.DeviceArray.from_numpy(ctx, np.asfortranarray(Y[:, k:])))
+        assert con.ncols == Y.shape[1]
+        Xd = isb.DeviceArray.from_numpy(ctx, X)
+        con.apply_(Xd)
+        X[...] = Xd.numpy()
+        con.close()
+        return X
+
+    cases.case_constraint_apply(oracle, [fn], dtype, tol)
+
+
+def test_constraint_rejects_dependent_basis(isb):
+    ctx = isb.default_context()
+    Y = np.ones((40, 2))
+    with pytest.raises(isb.B200Error) as e:
+        isb.LobpcgConstraint(ctx, 40, np.float64, Y)
+    assert "PosDef" in str(e.value)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-7), (np.float32, 5e-3)])
+@pytest.mark.parametrize("largest", [False, True])
+def test_constrained_lobpcg_matches_oracle_and_reference_properties(isb, oracle, dtype, tol, largest):
+    """three extreme pairs, then a constrained solve for the next two -- against the oracle's constrained lobpcg
+    (same X0, same C: iteration count +-3, Ritz values), the prescribed spectrum, and the reference's property test:
+    residual <= tol and orthogonality to the constraint (test/lobpcg.jl:213-228)."""
+    rng = np.random.default_rng(SEED)
+    n = 60
+    M, d = cases.separated_spectrum_matrix(n)
+    Md = M.astype(dtype)
+    A = isb.B200CSR.from_scipy(sp.csc_matrix(Md))
+    ex = d[::-1] if largest else d
+    r1 = isb.lobpcg(A, largest, rng.random((n, 3)).astype(dtype), tol=tol, maxiter=500)
+    assert r1.converged and np.allclose(np.sort(r1.lam), np.sort(ex[:3]), atol=20 * tol)
+    X0 = rng.random((n, 2)).astype(dtype)
+    r2 = isb.lobpcg(A, largest, X0, C=r1.X.copy(), tol=tol, maxiter=500)
+    ro = oracle.lobpcg(Md, largest, X0, C=np.asarray(r1.X, dtype=dtype).copy(), tol=tol, maxiter=500)
+    assert r2.converged and ro.converged
+    if dtype == np.float64:        # same recurrence up to rounding; the fp32 engine multiplies in 3xTF32
+        assert abs(r2.iterations - ro.iterations) <= 3
+    assert np.allclose(np.sort(r2.lam), np.sort(ex[3:5]), atol=20 * tol)
+    assert np.allclose(np.sort(r2.lam), np.sort(ro.lam), atol=20 * tol)
+    X2 = np.asarray(r2.X, dtype=np.float64)
+    assert np.max(np.linalg.norm(M @ X2 - X2 * r2.lam[None, :].astype(np.float64), axis=0)) <= 4 * tol
+    assert np.max(np.abs(np.asarray(r1.X, dtype=np.float64).T @ X2)) <= 2 * n * tol           # test/lobpcg.jl:226
+    # C as a LobpcgConstraint object is the same thing
+    con = isb.LobpcgConstraint(A.ctx, n, dtype, r1.X.copy())
+    r3 = isb.lobpcg(A, largest, X0, C=con, tol=tol, maxiter=500)
+    assert np.allclose(r3.lam, r2.lam, atol=20 * tol) and r3.iterations == r2.iterations
+
+
+@pytest.mark.parametrize("block_size,nev", [(1, 3), (2, 5), (3, 6), (4, 8)])
+def test_nev_driver_reference_properties(isb, oracle, block_size, nev):
+    """lobpcg(A, largest, X0, nev) (test/lobpcg.jl:291-306, :324-342): batches with deflation, with and without the
+    tail batch (`cutoff` branch, src/lobpcg.jl:945-952); residuals, orthonormality, the prescribed eigenvalues; an
+    initial constraint on top."""
+    rng = np.random.default_rng(SEED)
+    n = 60
+    M, d = cases.separated_spectrum_matrix(n)
+    A = isb.B200CSR.from_scipy(sp.csc_matrix(M))
+    tol = 1e-6
+    for largest in (False, True):
+        ex = d[::-1] if largest else d
+        r = isb.lobpcg(A, largest, rng.random((n, block_size)), nev, tol=tol, maxiter=2000, rng=rng)
+        assert r.X.shape == (n, nev) and len(r.iterations) == -(-nev // block_size) and np.all(r.converged)
+        assert np.max(np.linalg.norm(M @ r.X - r.X * r.lam[None, :], axis=0)) <= tol
+        assert np.allclose(r.X.T @ r.X, np.eye(nev), atol=2 * n * tol)
+        assert np.allclose(np.sort(r.lam), np.sort(ex[:nev]), atol=1e-5)
+    # with an initial constraint: the eigenpairs after the first two
+    r1 = isb.lobpcg(A, False, rng.random((n, 2)), tol=tol, maxiter=2000)
+    k = max(3, 2 * block_size) if block_size > 1 else 3
+    r2 = isb.lobpcg(A, False, rng.random((n, block_size)), k, C=r1.X.copy(), tol=tol, maxiter=2000, rng=rng)
+    assert np.allclose(np.sort(r2.lam), d[2:2 + k], atol=1e-5)
+    assert np.max(np.abs(r1.X.T @ r2.X)) <= 2 * n * tol
+    if block_size == 1:
+        r3 = isb.lobpcg(A, False, 3, tol=tol, maxiter=2000, rng=rng)                           # lobpcg(A, largest, nev::Int)
+        assert np.allclose(np.sort(r3.lam), d[:3], atol=1e-5)

@@ -243,3 +243,40 @@ def case_cg_general_operator(oracle, runners, dtype, tol):
             assert hs.iters == 0
             xs, hs = run.cg(np.zeros(3, dtype=T), A, np.zeros(3, dtype=T), "cg", None, initially_zero=True)   # :50-51
             assert hs.iters == 0 and np.all(xs == 0)
+
+
+def case_constraint_apply(oracle, apply_fns, dtype, tol):
+    """Constraint (reference src/lobpcg.jl:144-224): X <- X - Y (chol(Y'Y) \\ Y'X) against the oracle's Constraint,
+    for narrow / full / wider-than-16 bases, and with update!'s identity-extended factor (:188-206).
+    apply_fns: callables (X, Y, appended) -> X (in place)."""
+    rng = np.random.default_rng(2)
+    for n, nc, bs in ((50, 1, 1), (200, 5, 3), (300, 16, 16), (400, 37, 16), (64, 20, 7)):
+        Y = rng.standard_normal((n, nc)).astype(dtype)
+        X = rng.standard_normal((n, bs)).astype(dtype)
+        c = oracle.Constraint(Y.copy())
+        Xo = np.asfortranarray(X.copy())
+        c.apply(Xo)
+        assert np.abs(Y.T.astype(np.float64) @ Xo).max() <= 100 * tol * np.linalg.norm(Y) * np.linalg.norm(Xo)
+        # appended columns: orthonormal, orthogonal to Y (what a constrained lobpcg batch delivers)
+        Q = rng.standard_normal((n, 3))
+        oracle.Constraint(Y.astype(np.float64)).apply(Q)
+        Q = np.linalg.qr(Q)[0].astype(dtype)
+        c3 = oracle.Constraint(Y.copy())
+        c3.update(Q.copy(), Q.copy())
+        Xo3 = np.asfortranarray(X.copy())
+        c3.apply(Xo3)
+        for fn in apply_fns:
+            Xs = fn(np.asfortranarray(X.copy()), Y, 0)
+            assert np.linalg.norm(Xs - Xo) <= tol * np.linalg.norm(Xo), (n, nc, bs)
+            Xs = fn(np.asfortranarray(X.copy()), np.hstack([Y, Q]), 3)
+            assert np.linalg.norm(Xs - Xo3) <= tol * np.linalg.norm(Xo3), (n, nc, bs, "appended")
+
+
+def separated_spectrum_matrix(n, seed=7):
+    """dense symmetric test matrix with a prescribed, well separated spectrum at both ends (LOBPCG converges in tens
+    of iterations, no multiple eigenvalues: the 2-D Laplacian's double eigenvalues make a block miss a copy)."""
+    rng = np.random.default_rng(seed)
+    Q = np.linalg.qr(rng.standard_normal((n, n)))[0]
+    d = np.r_[np.array([1, 2, 4, 7, 11, 16, 22, 29, 37, 46.0]), np.linspace(60, 100, n - 20),
+              np.array([120, 135, 150, 170, 190, 215, 240, 270, 300, 340.0])]
+    return (Q * d) @ Q.T, np.sort(d)
