@@ -1,4 +1,4 @@
-"""Worker for the multi-GPU test of the section 8(f) item 4 solvers; launched by tests/test_zz_gpu_widening.py through
+"""Worker for the multi-GPU test of the section 8(f) item 4 solvers; launched by tests/test_zy_gpu_widening.py through
 torchrun (one process per GPU, NCCL).  Every rank owns a z-slab of laplace_matrix(Float64, N, 3) (symmetric, so the
 adjoint operator is the operator itself); the row-partitioned qmr!/idrs!/lsqr!/lsmr! -- every pass reduction
 allreduced, scalar sections run after the allreduce -- must reproduce the single-GPU runs (rank 0, global matrix)."""

@@ -7,9 +7,10 @@
     on the serial test backend (tests/hostsim) and compared with the oracle: same iteration counts, histories
     and solutions to a stated tolerance, in both row orders (a pass must not couple rows) and in both
     finishing modes (single-GPU: finish in the reduction; multi-GPU: totals stored, then finish).
-The CUDA instantiation of the same engines is covered by tests/test_zz_gpu_widening.py (-m gpu).
+The CUDA instantiation of the same engines is covered by tests/test_zy_gpu_widening.py (-m gpu).
 """
 import math
+from types import SimpleNamespace
 
 import numpy as np
 import pytest
@@ -321,3 +322,93 @@ def test_engine_constraint_passes_match_oracle(oracle, sim, dtype, tol):
     fns = [lambda X, Y, app, rm=rm, o=o, s=s: sim.constraint_apply_(X, Y, appended=app, row_major=rm, order=o, split=s)
            for rm in (False, True) for o, s in ((0, 0), (1, 1))]
     cases.case_constraint_apply(oracle, fns, dtype, tol)
+
+
+def test_python_lobpcg_wrapper_control_flow_with_a_fake_library(monkeypatch):
+    """The host-side lobpcg wrapper (plain, `C=`, nev driver incl. the cutoff tail batch, zero-column refill) driven
+    against a recording fake of the C library: every call it makes, in order, with the right shapes -- no GPU needed.
+    (The numerics of those calls are covered by the oracle / serial-backend tests and by the GPU suite.)"""
+    import ctypes as C
+    from importlib import import_module
+    import iterativesolvers_jl_b200 as isb
+    S = import_module("iterativesolvers_jl_b200.solvers")
+    calls = []
+
+    class FakeArr:                                  # numpy-backed stand-in for DeviceArray
+        def __init__(self, a):
+            self.a = np.array(a, order="F")
+            self.shape, self.dtype = self.a.shape, self.a.dtype
+            self.code = 0 if self.dtype == np.float64 else 1
+            self._p = C.c_void_p(id(self) & 0xFFFFFFF0)
+
+        @classmethod
+        def from_numpy(cls, ctx, a):
+            return cls(a)
+
+        def numpy(self):
+            return self.a.copy(order="F")
+
+        def upload(self, a):
+            self.a[...] = np.asarray(a).reshape(self.a.shape)
+
+        def column(self, j):
+            outer = self
+
+            class Col:
+                _p, code, shape = C.c_void_p(1), outer.code, (outer.shape[0],)
+
+                def upload(self_, v):
+                    outer.a[:, j] = v
+                    calls.append(("refill", j))
+            c = Col()
+            c.j = j
+            return c
+
+    class FakeLib:
+        def __getattr__(self, name):
+            def f(*args):
+                calls.append((name,) + tuple(a for a in args if isinstance(a, int)))
+                if name == "b200_nrm2":             # report column 1 as all-zero once
+                    args[-1]._obj.value = 0.0 if (len([c for c in calls if c[0] == "b200_nrm2"]) == 2) else 1.0
+                if name == "b200_lobpcg_constraint_create":
+                    args[-1]._obj.value = 0x1234    # the handle
+                if name == "b200_lobpcg_constraint_info":
+                    args[1]._obj.value, args[2]._obj.value = 3, 8
+                return 0
+            return f
+
+    monkeypatch.setattr(S, "lib", lambda: FakeLib())
+    monkeypatch.setattr(S, "DeviceArray", FakeArr)
+    monkeypatch.setattr(S, "is_device", lambda v: isinstance(v, FakeArr))
+    monkeypatch.setattr(S, "as_device_ptr", lambda v: v._p)
+    monkeypatch.setattr(S, "precond_to_c", lambda P, A: S._lib.Precond(0, 0, None))
+    A = S.B200CSR.__new__(S.B200CSR)
+    A.ctx, A._h, A.m_local, A.n_global, A.dtype = SimpleNamespace(_h=None, world=1), C.c_void_p(7), 30, 30, np.dtype(np.float64)
+    A.close = lambda: None
+    rng = np.random.default_rng(0)
+    r = isb.lobpcg(A, False, rng.random((30, 2)), maxiter=5)
+    # not_zeros = false: one nrm2 per column; the fake reports column 1 as all-zero -> it is refilled with rand (:869-876)
+    assert [c[0] for c in calls] == ["b200_nrm2", "b200_nrm2", "refill", "b200_lobpcg_solve"] and calls[2] == ("refill", 1)
+    assert r.X.shape == (30, 2) and r.iterations == 0
+    calls.clear()
+    r = isb.lobpcg(A, False, rng.random((30, 2)), C=rng.random((30, 3)), not_zeros=True)
+    # (the temporary constraint made from the array is destroyed when the call returns)
+    assert [c[0] for c in calls][:2] == ["b200_lobpcg_constraint_create", "b200_lobpcg_solve_constrained"]
+    assert [c[0] for c in calls][2:] in ([], ["b200_lobpcg_constraint_destroy"])
+    calls.clear()
+    r = isb.lobpcg(A, True, rng.random((30, 2)), 5, C=rng.random((30, 1)), not_zeros=True, rng=rng)   # batches 2, 2, 1
+    names = [c[0] for c in calls]
+    assert names == ["b200_lobpcg_constraint_create", "b200_lobpcg_solve_constrained", "b200_lobpcg_constraint_append",
+                     "b200_lobpcg_solve_constrained", "b200_lobpcg_constraint_append", "b200_lobpcg_solve_constrained",
+                     "b200_lobpcg_constraint_destroy"], names
+    create, app1, app2 = calls[0], calls[2], calls[4]
+    assert create[-3:] == (1, 5, 0)                 # nc = 1, capacity = 1 + (5 // 2) * 2, dtype f64
+    assert app1[-1] == 2 and app2[-1] == 1          # whole block, then cutoff = 1 column (src/lobpcg.jl:945-947)
+    assert r.X.shape == (30, 5) and len(r.iterations) == 3 and r.lam.shape == (5,)
+    calls.clear()
+    isb.lobpcg(A, False, 4, maxiter=3, rng=rng)     # lobpcg(A, largest, nev::Int): random X0, not_zeros = true
+    assert [c[0] for c in calls] == ["b200_lobpcg_solve"]
+    with pytest.raises(TypeError):
+        isb.lobpcg(A, False, rng.random((30, 2)), bogus=1)
+    with pytest.raises(isb.B200Error):
+        isb.lobpcg(A, False, rng.random((30, 11)))  # n < 3 * blocksize (src/lobpcg.jl:834)

@@ -1,6 +1,6 @@
 """Engine-vs-oracle cases for qmr!/lsqr!/lsmr!/idrs!, shared by
   * tests/test_oracle_widening.py  -- the engines on the serial test backend (tests/hostsim), CPU, and
-  * tests/test_zz_gpu_widening.py  -- the same engines through the C ABI on the GPU (-m gpu).
+  * tests/test_zy_gpu_widening.py  -- the same engines through the C ABI on the GPU (-m gpu).
 A `runner` hides which of the two executes the engine:
     runner.qmr(x0, A, b, **kw)            -> x, R   (R.iters, R.converged, R.breakdown, R.hist, R.tol, R.nprods)
     runner.lsqr / runner.lsmr(x0, A, b, **kw) -> x, R   (R.iters, R.istop, R.converged, R.mvps, R.mtvps, R.hist{...},
