@@ -412,3 +412,88 @@ def test_python_lobpcg_wrapper_control_flow_with_a_fake_library(monkeypatch):
         isb.lobpcg(A, False, rng.random((30, 2)), bogus=1)
     with pytest.raises(isb.B200Error):
         isb.lobpcg(A, False, rng.random((30, 11)))  # n < 3 * blocksize (src/lobpcg.jl:834)
+
+
+def test_python_linop_paths_with_a_fake_library(monkeypatch):
+    """cg!/qmr!/lsqr!/lsmr!/idrs! with B200LinearOperator / FunctionPrec against a fake C library that calls the
+    b200_linop thunks back the way the real engines do: right entry point, the callbacks really fire with views of the
+    right length, a Python exception raised inside a callback comes out of the solver call."""
+    import ctypes as C
+    from importlib import import_module
+    import iterativesolvers_jl_b200 as isb
+    S = import_module("iterativesolvers_jl_b200.solvers")
+    L = S._lib
+    calls, seen = [], []
+
+    class FakeArr:
+        def __init__(self, a):
+            self.a = np.array(a, order="F")
+            self.shape, self.dtype = self.a.shape, self.a.dtype
+            self._p = C.c_void_p(0x5000)
+
+        @classmethod
+        def from_numpy(cls, ctx, a):
+            return cls(a)
+
+        @classmethod
+        def zeros(cls, ctx, n, dtype):
+            return cls(np.zeros(n, dtype))
+
+        def numpy(self):
+            return self.a.copy()
+
+    class FakeLib:
+        def __getattr__(self, name):
+            def f(*args):
+                calls.append(name)
+                rc = 0
+                for a in args:                       # call every b200_linop passed by reference, as the engines would
+                    obj = getattr(a, "_obj", None)
+                    if isinstance(obj, L.LinOp):
+                        rc = rc or obj.apply(None, 0x1000, 0x2000, None)
+                return -7 if rc else 0               # B200_ERR_CALLBACK
+            return f
+
+        def b200_last_error(self):
+            return b"operator / preconditioner callback returned 1"
+
+    monkeypatch.setattr(S, "lib", lambda: FakeLib())
+    monkeypatch.setattr(S, "check", lambda st: (_ for _ in ()).throw(isb.B200Error(f"status {st}")) if st else 0)
+    monkeypatch.setattr(S, "DeviceArray", FakeArr)
+    monkeypatch.setattr(S, "is_device", lambda v: isinstance(v, FakeArr))
+    monkeypatch.setattr(S, "as_device_ptr", lambda v: v._p)
+    ctx = SimpleNamespace(_h=None, world=1)
+    n = 12
+
+    def mul(y, x):
+        seen.append(("mul", y.shape, x.shape, y.ptr, x.ptr))
+
+    op = isb.B200LinearOperator((n, n), np.float64, mul, adjoint_mul=lambda y, x: seen.append(("adj", y.shape, x.shape)),
+                                ctx=ctx)
+    b = np.ones(n)
+    for name, entry, kw in (("cg", "b200_cg_solve_op", {}), ("qmr", "b200_qmr_solve_op", {}),
+                            ("lsqr", "b200_lsqr_solve_op", {}), ("lsmr", "b200_lsmr_solve_op", {}),
+                            ("idrs", "b200_idrs_solve_op", dict(s=2, rng=np.random.default_rng(0)))):
+        calls.clear()
+        seen.clear()
+        x, h = getattr(isb, name)(op, b, log=True, **kw)
+        assert calls == [entry], (name, calls)
+        assert seen and seen[0] == ("mul", (n,), (n,), 0x2000, 0x1000)
+        if name in ("qmr", "lsqr", "lsmr"):
+            assert ("adj", (n,), (n,)) in seen      # the adjoint operator was handed over too
+        assert x.shape == (n,)
+    # callback preconditioner on top of a callback operator
+    calls.clear()
+    seen.clear()
+    Pl = isb.FunctionPrec(n, np.float64, lambda y, x: seen.append(("ldiv", y.shape)), ctx=ctx)
+    isb.cg(op, b, Pl=Pl)
+    assert calls == ["b200_cg_solve_op"] and ("ldiv", (n,)) in seen and seen[0][0] == "mul"
+
+    def boom(y, x):
+        raise ZeroDivisionError("inside the operator")
+
+    bad = isb.B200LinearOperator((n, n), np.float64, boom, ctx=ctx)
+    with pytest.raises(ZeroDivisionError, match="inside the operator"):
+        isb.cg(bad, b)
+    with pytest.raises(TypeError):
+        isb.gmres(op, b)                             # the GMRES engine is CSR-only
