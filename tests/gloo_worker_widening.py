@@ -1,0 +1,108 @@
+"""World-size-2 gloo worker (CPU) for the multi-GPU form of the fused-pass engines (qmr!, lsqr!, lsmr!, idrs!, general
+cg!): every rank owns a row slab of A (and of A'), the operator application is "gather the operand, multiply the
+slab" (what the halo exchange + SpMV do on the GPUs) and every pass total goes through an allreduce before its scalar
+section runs -- the control flow of the CUDA backend on a multi-GPU context (csrc/pass.cuh), with torch.distributed
+in the place of NCCL.  Each rank compares its slab of the solution and the whole history with the single-process run."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    rank, port = int(sys.argv[1]), sys.argv[2]
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=2)
+    from hostsim import sim
+    rng = np.random.default_rng(99)
+    n = 150
+    M = (sp.random(n, n, 0.05, random_state=8, format="csr") + 6 * sp.eye(n, format="csr")).tocsr()
+    Mt = M.T.tocsr()
+    S = (M + Mt).tocsr()                                       # symmetric positive definite, for cg
+    b = rng.random(n)
+    P = np.asfortranarray(rng.random((n, 4)))
+    cuts = [0, 83, n]
+    lo, hi = cuts[rank], cuts[rank + 1]
+    m = hi - lo
+
+    # ---- single-process references (every rank computes them; cheap)
+    ref = {
+        "qmr": sim.qmr_(np.zeros(n), M, b, initially_zero=True),
+        "idrs": sim.idrs_(np.zeros(n), M, b, P),
+        "lsqr": sim.lsqr_(np.zeros(n), M, b, maxiter=12, atol=0.0, btol=0.0, conlim=0.0),
+        "lsmr": sim.lsmr_(np.zeros(n), M, b, maxiter=12, atol=0.0, btol=0.0, conlim=0.0),
+        "cg": sim.cg_(np.zeros(n), S, b, initially_zero=True, diag=S.diagonal()),
+    }
+
+    # ---- row-partitioned runs
+    slabs = {}                                                  # op_id -> the slab whose product the engine asks for
+
+    def register(mat):
+        c = sim.Csr(mat, np.float64)
+        return c
+
+    def apply(op_id, x_ptr, y_ptr):
+        slab = slabs[op_id]
+        x_loc = np.ctypeslib.as_array(C.cast(x_ptr, C.POINTER(C.c_double)), shape=(m,))
+        mx = max(cuts[r + 1] - cuts[r] for r in range(2))               # gloo's all_gather wants equal sizes: pad
+        mine = torch.zeros(mx, dtype=torch.float64)
+        mine[:m] = torch.from_numpy(x_loc.copy())
+        parts = [torch.zeros(mx, dtype=torch.float64) for _ in range(2)]
+        dist.all_gather(parts, mine)                                    # the "halo exchange": here the whole operand
+        x_full = np.concatenate([parts[r].numpy()[: cuts[r + 1] - cuts[r]] for r in range(2)])
+        y = slab @ x_full
+        np.ctypeslib.as_array(C.cast(y_ptr, C.POINTER(C.c_double)), shape=(m,))[:] = y
+        return 0
+
+    def allreduce(buf, count):
+        a = np.ctypeslib.as_array(buf, shape=(count,))
+        t = torch.from_numpy(a.copy())
+        dist.all_reduce(t)
+        a[:] = t.numpy()
+
+    # sim builds its Csr objects inside each call, so the slabs are looked up by CONTENT: patch Csr to register itself
+    orig_csr = sim.Csr
+
+    class RegCsr(orig_csr):
+        def __init__(self, A, dtype):
+            super().__init__(A, dtype)
+            slabs[self.rowptr.ctypes.data] = sp.csr_matrix((self.vals, self.colind, self.rowptr), shape=self.shape)
+
+    sim.Csr = RegCsr
+    sim.set_dist(apply, allreduce)
+    A_loc, At_loc, S_loc = M[lo:hi], Mt[lo:hi], S[lo:hi]
+    out = {
+        "qmr": sim.qmr_(np.zeros(m), A_loc, b[lo:hi], initially_zero=True, At=At_loc),
+        "idrs": sim.idrs_(np.zeros(m), A_loc, b[lo:hi], P[lo:hi]),
+        "lsqr": sim.lsqr_(np.zeros(m), A_loc, b[lo:hi], maxiter=12, atol=0.0, btol=0.0, conlim=0.0, At=At_loc),
+        "lsmr": sim.lsmr_(np.zeros(m), A_loc, b[lo:hi], maxiter=12, atol=0.0, btol=0.0, conlim=0.0, At=At_loc),
+        "cg": sim.cg_(np.zeros(m), S_loc, b[lo:hi], initially_zero=True, diag=S.diagonal()[lo:hi]),
+    }
+    sim.set_dist()
+    sim.Csr = orig_csr
+
+    for name in ("qmr", "idrs", "cg"):
+        (xr, hr), (xd, hd) = ref[name], out[name]
+        assert hd.iters == hr.iters and hd.converged == hr.converged, (name, hd.iters, hr.iters)
+        assert np.max(np.abs(hd.hist - hr.hist)) <= 1e-10 * hr.hist[0], name
+        assert np.linalg.norm(xd - xr[lo:hi]) <= 1e-10 * np.linalg.norm(xr), name
+    for name in ("lsqr", "lsmr"):
+        (xr, hr), (xd, hd) = ref[name], out[name]
+        assert hd.iters == hr.iters == 12 and hd.istop == hr.istop == 7 and (hd.mvps, hd.mtvps) == (hr.mvps, hr.mtvps)
+        for key in ("anorm", "rnorm", "cnorm"):
+            assert np.max(np.abs(hd.hist[key][:8] - hr.hist[key][:8])) <= 1e-10 * np.max(np.abs(hr.hist[key][:8])), (name, key)
+        assert np.linalg.norm(xd - xr[lo:hi]) <= 1e-8 * np.linalg.norm(xr), name
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank", rank, "ok")
+
+
+if __name__ == "__main__":
+    main()

@@ -36,6 +36,14 @@ struct HostCsr {          // 0-based CSR, int64 row pointers, int32 columns
   int is_f64;
 };
 
+// Row-partitioned runs (one process per "GPU", torch.distributed/gloo in the test): the operator application and the
+// reduction of the pass sums are delegated to the host program, exactly where the CUDA backend calls the halo
+// exchange + SpMV and ncclAllReduce.
+typedef int (*hs_apply_cb)(const void *op_id, const void *x, void *y);
+typedef void (*hs_allreduce_cb)(double *buf, int count);
+static hs_apply_cb g_apply = nullptr;
+static hs_allreduce_cb g_allreduce = nullptr;
+
 struct HostBackend {
   typedef HostCsr Op;
   int order = 0, split = 0;
@@ -46,6 +54,7 @@ struct HostBackend {
 
   int apply(const Op *A, const void *x, void *y) {
     ++applies;
+    if (g_apply) return g_apply((const void *)A->rowptr, x, y);
     if (A->is_f64) {
       const double *v = (const double *)A->vals, *xx = (const double *)x;
       double *yy = (double *)y;
@@ -77,10 +86,11 @@ struct HostBackend {
     if (order == 0) for (int64_t i = 0; i < n; ++i) p.elem(i, acc);
     else for (int64_t i = n - 1; i >= 0; --i) p.elem(i, acc);
     if (P::NRED > 0) {
-      if (!split) p.finish(acc);
+      if (!split && !g_allreduce) p.finish(acc);
       else {
         double *out = p.sums();
         for (int j = 0; j < P::NRED; ++j) out[j] = acc[j];
+        if (g_allreduce) g_allreduce(out, P::NRED);
         if (!p.skip()) p.finish(p.sums());
       }
     }
@@ -120,6 +130,11 @@ struct hostsim_out {
   int64_t passes, applies;
 };
 
+EXPORT void hostsim_set_dist(hs_apply_cb a, hs_allreduce_cb r) {
+  g_apply = a;
+  g_allreduce = r;
+}
+
 static HostCsr mk(const hostsim_csr *a, int is_f64) { return HostCsr{a->m, a->n, a->rowptr, a->colind, a->vals, is_f64}; }
 
 EXPORT int hostsim_qmr(int is_f64, const hostsim_csr *A, const hostsim_csr *At, void *x, const void *b, double abstol,
@@ -158,9 +173,9 @@ EXPORT int hostsim_lsqr(int is_f64, const hostsim_csr *A, const hostsim_csr *At,
   HostCsr a = mk(A, is_f64), at = mk(At, is_f64);
   b200::LsqrOutcome o;
   memset(&o, 0, sizeof(o));
-  int st = is_f64 ? b200::lsqr_run<double>(be, &a, &at, A->m, A->n, (double *)x, (const double *)b, damp, atol, btol,
+  int st = is_f64 ? b200::lsqr_run<double>(be, &a, &at, A->m, At->m, (double *)x, (const double *)b, damp, atol, btol,
                                            conlim, maxiter, check_every, hist_cap, hist, &o)
-                  : b200::lsqr_run<float>(be, &a, &at, A->m, A->n, (float *)x, (const float *)b, damp, atol, btol,
+                  : b200::lsqr_run<float>(be, &a, &at, A->m, At->m, (float *)x, (const float *)b, damp, atol, btol,
                                           conlim, maxiter, check_every, hist_cap, hist, &o);
   out->iters = o.iters; out->mvps = o.mvps; out->mtvps = o.mtvps; out->n_hist = o.n_hist; out->hist_stride = o.hist_stride;
   out->istop = o.istop; out->converged = o.converged; out->bad_x = o.bad_x; out->early = o.early;
@@ -179,9 +194,9 @@ EXPORT int hostsim_lsmr(int is_f64, const hostsim_csr *A, const hostsim_csr *At,
   HostCsr a = mk(A, is_f64), at = mk(At, is_f64);
   b200::LsmrOutcome o;
   memset(&o, 0, sizeof(o));
-  int st = is_f64 ? b200::lsmr_run<double>(be, &a, &at, A->m, A->n, (double *)x, (const double *)b, lambda, atol, btol,
+  int st = is_f64 ? b200::lsmr_run<double>(be, &a, &at, A->m, At->m, (double *)x, (const double *)b, lambda, atol, btol,
                                            conlim, maxiter, check_every, hist_cap, hist, &o)
-                  : b200::lsmr_run<float>(be, &a, &at, A->m, A->n, (float *)x, (const float *)b, lambda, atol, btol,
+                  : b200::lsmr_run<float>(be, &a, &at, A->m, At->m, (float *)x, (const float *)b, lambda, atol, btol,
                                           conlim, maxiter, check_every, hist_cap, hist, &o);
   out->iters = o.iters; out->mvps = o.mvps; out->mtvps = o.mtvps; out->n_hist = o.n_hist; out->hist_stride = o.hist_stride;
   out->istop = o.istop; out->converged = o.converged; out->bad_x = 0; out->early = o.early;

@@ -65,10 +65,12 @@ def _outcome(o: _Out, hist):
                    hist[: o.n_hist].copy(), o.passes, o.applies)
 
 
-def qmr_(x, A, b, *, abstol=0.0, reltol=-1.0, maxiter=-1, initially_zero=False, check_every=0, order=0, split=0):
-    """the qmr engine (csrc/qmr_core.h) on the serial backend; x updated in place."""
+def qmr_(x, A, b, *, abstol=0.0, reltol=-1.0, maxiter=-1, initially_zero=False, check_every=0, order=0, split=0,
+         At=None):
+    """the qmr engine (csrc/qmr_core.h) on the serial backend; x updated in place.  At: the adjoint operator's own
+    rows (row-partitioned runs); default: the transpose of A."""
     dt = x.dtype
-    Ac, Atc = Csr(A, dt), Csr(sp.csr_matrix(A).T, dt)
+    Ac, Atc = Csr(A, dt), Csr(sp.csr_matrix(A).T if At is None else At, dt)
     b = np.ascontiguousarray(b, dtype=dt)
     cap = (maxiter if maxiter >= 0 else A.shape[1]) + 1
     hist = np.zeros(cap)
@@ -106,9 +108,9 @@ class LsOutcome:
     applies: int
 
 
-def _ls(fn, first_row, x, A, b, p0, atol, btol, conlim, maxiter, check_every, order, split):
+def _ls(fn, first_row, x, A, b, p0, atol, btol, conlim, maxiter, check_every, order, split, At=None):
     dt = x.dtype
-    Ac, Atc = Csr(A, dt), Csr(sp.csr_matrix(A).T, dt)
+    Ac, Atc = Csr(A, dt), Csr(sp.csr_matrix(A).T if At is None else At, dt)
     b = np.ascontiguousarray(b, dtype=dt)
     cap = maxiter if maxiter >= 0 else max(A.shape)
     hist = np.zeros(4 * max(cap, 1))
@@ -124,14 +126,16 @@ def _ls(fn, first_row, x, A, b, p0, atol, btol, conlim, maxiter, check_every, or
                         bool(out.early), out.atol, out.btol, out.ctol, tuple(out.est), rows, out.passes, out.applies)
 
 
-def lsqr_(x, A, b, *, damp=0.0, atol=-1.0, btol=-1.0, conlim=-1.0, maxiter=-1, check_every=0, order=0, split=0):
+def lsqr_(x, A, b, *, damp=0.0, atol=-1.0, btol=-1.0, conlim=-1.0, maxiter=-1, check_every=0, order=0, split=0,
+          At=None):
     """the lsqr engine (csrc/lsqr_core.h) on the serial backend; x updated in place."""
-    return _ls(lib().hostsim_lsqr, "resnorm", x, A, b, damp, atol, btol, conlim, maxiter, check_every, order, split)
+    return _ls(lib().hostsim_lsqr, "resnorm", x, A, b, damp, atol, btol, conlim, maxiter, check_every, order, split, At)
 
 
-def lsmr_(x, A, b, *, lam=0.0, atol=-1.0, btol=-1.0, conlim=-1.0, maxiter=-1, check_every=0, order=0, split=0):
+def lsmr_(x, A, b, *, lam=0.0, atol=-1.0, btol=-1.0, conlim=-1.0, maxiter=-1, check_every=0, order=0, split=0,
+          At=None):
     """the lsmr engine (csrc/lsmr_core.h) on the serial backend; x updated in place."""
-    return _ls(lib().hostsim_lsmr, "normr", x, A, b, lam, atol, btol, conlim, maxiter, check_every, order, split)
+    return _ls(lib().hostsim_lsmr, "normr", x, A, b, lam, atol, btol, conlim, maxiter, check_every, order, split, At)
 
 
 def idrs_(x, A, b, P, *, diag=None, abstol=0.0, reltol=-1.0, maxiter=-1, smoothing=False, check_every=0, order=0,
@@ -195,3 +199,21 @@ def constraint_apply_(X, Y, *, appended=0, row_major=False, order=0, split=0):
     assert st == 0, st
     X[...] = buf[:, :bs]
     return X
+
+
+_APPLY_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+_ALLREDUCE_CB = C.CFUNCTYPE(None, C.POINTER(C.c_double), C.c_int)
+_dist_keep = []
+
+
+def set_dist(apply=None, allreduce=None):
+    """row-partitioned runs: `apply(op_id, x_ptr, y_ptr) -> 0` replaces every operator application (op_id = address of
+    the operator's row-pointer array: Csr(...).rowptr.ctypes.data), `allreduce(buf, count)` sums the pass totals over
+    the ranks in place.  set_dist() without arguments restores the serial behaviour."""
+    _dist_keep.clear()
+    if apply is None:
+        lib().hostsim_set_dist(None, None)
+        return
+    a, r = _APPLY_CB(apply), _ALLREDUCE_CB(allreduce)
+    _dist_keep.extend([a, r])
+    lib().hostsim_set_dist(a, r)

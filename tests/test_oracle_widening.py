@@ -497,3 +497,24 @@ def test_python_linop_paths_with_a_fake_library(monkeypatch):
         isb.cg(bad, b)
     with pytest.raises(TypeError):
         isb.gmres(op, b)                             # the GMRES engine is CSR-only
+
+
+def test_partitioned_engines_world2_gloo():
+    """world_size-2 gloo group on CPU: the multi-GPU control flow of the fused-pass engines (per-rank row slabs, operator
+    application through an exchange, every pass total allreduced before its scalar section) reproduces the
+    single-process runs of qmr!, idrs!, lsqr!, lsmr! and the general cg! (tests/gloo_worker_widening.py)."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "gloo_worker_widening.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), str(port)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{o[-3000:]}"
+        assert f"rank {r} ok" in o
