@@ -188,6 +188,16 @@ B200_API int64_t b200_gen_advection_csc_i64(int64_t N, double beta, int base, in
 B200_API int64_t b200_gen_laplace_csr_slab_i32(int64_t N, int dims, int64_t row_begin, int64_t m_local,
                                                int32_t *rowptr, int32_t *colind_global, double *vals);
 
+/* Matrix Market ingestion (host code): the reference's benchmark scripts load their
+ * real-world operators with MatrixMarket.jl (benchmark/matrixmarket.jl:2,9-10).  `coordinate` format, field real /
+ * integer / pattern, symmetry general / symmetric / skew-symmetric.  _info: dimensions, the number of nonzeros AFTER
+ * expanding symmetric storage and summing duplicates, field (0 real, 1 integer, 2 pattern), symmetry (0, 1, 2).
+ * _read_csc_i64: the three arrays of the SparseMatrixCSC{Float64,Int64} that mmread builds (rows ascending inside a
+ * column; base = 1 for Julia) into caller-owned buffers: colptr n+1, rowval / nzval nnz_capacity >= nnz. */
+B200_API int b200_mm_info(const char *path, int64_t *m, int64_t *n, int64_t *nnz, int *field, int *symmetry);
+B200_API int b200_mm_read_csc_i64(const char *path, int base, int64_t nnz_capacity, int64_t *colptr, int64_t *rowval,
+                                  double *nzval);
+
 /* ---------------------------------------------------------------- L0: operator / vector algebra
  * (each Julia op of SURVEY.md section 8b is one call; x,y are LOCAL slabs on multi-GPU contexts,
  * reductions return the GLOBAL value on every rank)

@@ -148,6 +148,9 @@ SIGNATURES = {
     "b200_gen_laplace_csc_i64": (_I64, [_I64, _INT, _INT, _P, _P, _P]),
     "b200_gen_advection_csc_i64": (_I64, [_I64, _DBL, _INT, _P, _P, _P, _P]),
     "b200_gen_laplace_csr_slab_i32": (_I64, [_I64, _INT, _I64, _I64, _P, _P, _P]),
+    "b200_mm_info": (_INT, [C.c_char_p, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_INT),
+                            C.POINTER(_INT)]),
+    "b200_mm_read_csc_i64": (_INT, [C.c_char_p, _INT, _I64, _P, _P, _P]),
     "b200_spmv": (_INT, [_P, _P, _P, _P]),
     "b200_spmm": (_INT, [_P, _P, _P, _I64, _P, _I64, _INT]),
     "b200_dot": (_INT, [_P, _I64, _P, _P, _INT, C.POINTER(_DBL)]),

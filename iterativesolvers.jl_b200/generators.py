@@ -3,10 +3,11 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
-from ._lib import B200Error, lib
+from ._lib import B200Error, check, lib
 
 
 def _vp(a):
@@ -54,3 +55,19 @@ def advection_dominated(N: int = 50, beta: float = 1000.0, base: int = 0):
     got = lib().b200_gen_advection_csc_i64(N, float(beta), base, _vp(colptr), _vp(rowval), _vp(nzval), _vp(b))
     assert got == nnz
     return colptr, rowval, nzval, (n, n), b
+
+
+def mmread(path, base: int = 0):
+    """MatrixMarket.mmread for the sparse (coordinate) format -- what the reference's benchmark scripts use to load
+    their operators (benchmark/matrixmarket.jl:2,9-10): returns (colptr, rowval, nzval, shape) of the
+    SparseMatrixCSC{Float64,Int64} (symmetric storage expanded, duplicates summed, rows sorted; base = 1 for Julia's
+    indexing).  Feed it to B200CSR.from_csc_arrays."""
+    p = os.fsencode(path)
+    m, n, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+    field, sym = C.c_int(), C.c_int()
+    check(lib().b200_mm_info(p, C.byref(m), C.byref(n), C.byref(nnz), C.byref(field), C.byref(sym)))
+    colptr = np.empty(n.value + 1, dtype=np.int64)
+    rowval = np.empty(max(nnz.value, 1), dtype=np.int64)
+    nzval = np.empty(max(nnz.value, 1), dtype=np.float64)
+    check(lib().b200_mm_read_csc_i64(p, base, nnz.value, _vp(colptr), _vp(rowval), _vp(nzval)))
+    return colptr, rowval[: nnz.value], nzval[: nnz.value], (m.value, n.value)
