@@ -437,6 +437,41 @@ B200_API int b200_lobpcg_solve(b200_ctx *ctx, const b200_csr *A, void *X_dev, in
                                const b200_lobpcg_opts *opts, b200_lobpcg_result *res, double *lambda_host,
                                double *resnorm_host);
 
+/* svdl(A; nsv, k, j, tol, reltol, maxiter, method, vecs, dolock, v0)  reference src/svdl.jl:157-247 (SURVEY.md section
+ * 8f item 4): singular values (and vectors) by Golub-Kahan-Lanczos bidiagonalisation with thick restart. */
+typedef struct {
+  int32_t nsv;              /* 6                          src/svdl.jl:158   (<=0: default)                          */
+  int32_t k;                /* 2nsv Lanczos vectors       src/svdl.jl:158   (<=0: default; at most 64)              */
+  int32_t j;                /* nsv vectors kept at restart src/svdl.jl:178  (<=0: default)                          */
+  int32_t method;           /* 0 = :ritz (src/svdl.jl:376-404); :harmonic (:424-520) is not implemented             */
+  int64_t maxiter;          /* minimum(size(A))           src/svdl.jl:159   (<0: default)                           */
+  double tol, reltol;       /* sqrt(eps()) each           src/svdl.jl:158,179 (<0: default)                         */
+  int32_t dolock;           /* src/svdl.jl:181, :214-221                                                            */
+  int32_t reserved;
+} b200_svdl_opts;
+typedef struct {
+  int64_t iters;            /* history.iters (one per restart, src/svdl.jl:189)                                     */
+  int64_t mvps, mtvps;      /* products with A / A' as extend! counts them (src/svdl.jl:564, :582)                  */
+  int32_t isconverged;      /* all(conv) reached (src/svdl.jl:222)                                                  */
+  int32_t k;                /* size of the projected matrix B                                                       */
+  double beta;              /* L.beta at exit                                                                       */
+  double tol;               /* history[:tol]                                                                        */
+} b200_svdl_result;
+/* A: m x n operator, At = adjoint(A); v0_dev: n values (starting vector, a copy is normalised); sigma_host: nsv values
+ * (F.S[1:nsv], :227).  U_dev (m x nsv, ld ldu) / V_dev (n x nsv, ld ldv): device, left / right singular vectors as the
+ * reference forms them (L.P*F.U[:,1:l], L.Q[:,1:k]*F.V[:,1:l], :230-241) or NULL (vecs = :none).  Histories (host, may
+ * be NULL): hist_ritz maxiter x k (:ritz), hist_resnorm maxiter x nsv (:resnorm = the error bounds of isconverged),
+ * hist_conv maxiter x nsv (:conv), hist_betas maxiter (:betas); row `it` is written by iteration it+1.  B_host:
+ * k x k column-major, the projected matrix L.B at exit (may be NULL). */
+B200_API int b200_svdl(b200_ctx *ctx, const b200_csr *A, const b200_csr *At, const void *v0_dev,
+                       const b200_svdl_opts *opts, b200_svdl_result *res, double *sigma_host, void *U_dev, int64_t ldu,
+                       void *V_dev, int64_t ldv, double *hist_ritz, double *hist_resnorm, int32_t *hist_conv,
+                       double *hist_betas, double *B_host);
+B200_API int b200_svdl_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *At, const void *v0_dev,
+                          const b200_svdl_opts *opts, b200_svdl_result *res, double *sigma_host, void *U_dev,
+                          int64_t ldu, void *V_dev, int64_t ldv, double *hist_ritz, double *hist_resnorm,
+                          int32_t *hist_conv, double *hist_betas, double *B_host);
+
 /* The constraint of lobpcg (`C` keyword, reference src/lobpcg.jl:829; struct Constraint :144-224): a basis Y the Ritz
  * vectors are kept orthogonal to.  Standard problem (B = I).  Y_dev: n_local x nc column-major (copied); `capacity`
  * >= nc columns are reserved for b200_lobpcg_constraint_append, which mirrors update! (:188-206: the Cholesky factor

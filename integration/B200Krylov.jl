@@ -13,7 +13,7 @@ module B200Krylov
 
 using SparseArrays, LinearAlgebra
 import IterativeSolvers
-import IterativeSolvers: cg!, chebyshev!, gmres!, minres!, bicgstabl!, lobpcg, qmr!, lsqr!, lsmr!, idrs!,
+import IterativeSolvers: cg!, chebyshev!, gmres!, minres!, bicgstabl!, lobpcg, qmr!, lsqr!, lsmr!, idrs!, svdl,
                          ConvergenceHistory, Identity, ClassicalGramSchmidt, ModifiedGramSchmidt, DGKS,
                          OrthogonalizationMethod, LOBPCGResults
 import LinearAlgebra: mul!, ldiv!
@@ -437,6 +437,45 @@ update!(c::B200Constraint, Xd::B200Vector, n::Integer, k::Integer) =
 #         Ptr{Cvoid}, Ref{LobpcgResult}, Ptr{Float64}, Ptr{Float64}), A.ctx.h, A.h, Xd.p, n, o, c.h, res, λ, rn)
 # lobpcg(A, largest, X0, nev; ...) (src/lobpcg.jl:925-962) is the same host loop as iterativesolvers.jl_b200/solvers.py:
 # solve a block, update!(constraint, converged columns), rand! the block, repeat.
+
+# ------------------------------------------------------------------------------------------- svdl
+struct SvdlOpts
+    nsv::Int32; k::Int32; j::Int32; method::Int32; maxiter::Int64; tol::Float64; reltol::Float64
+    dolock::Int32; reserved::Int32
+end
+mutable struct SvdlResult
+    iters::Int64; mvps::Int64; mtvps::Int64; isconverged::Int32; k::Int32; beta::Float64; tol::Float64
+    SvdlResult() = new(0, 0, 0, 0, 0, 0.0, 0.0)
+end
+# svdl(A; nsv, k, tol, maxiter, method = :ritz, v0, j, reltol, vecs, dolock)  src/svdl.jl:157-247
+function svdl(A::B200CSR{T}; nsv::Int = 6, k::Int = 2nsv, tol::Real = √eps(), maxiter::Int = minimum(size(A)),
+                               method::Symbol = :ritz, log::Bool = false, j::Int = nsv, reltol::Real = √eps(),
+                               v0::Vector{T} = (x = randn(T, size(A, 2)); x ./ norm(x)), vecs::Symbol = :none,
+                               dolock::Bool = false) where {T}
+    method == :ritz || throw(ArgumentError("Unknown restart method $method"))
+    m, n = size(A); At = adjoint(A)
+    v0d = B200Vector(A.ctx, v0); res = SvdlResult(); σ = Vector{Float64}(undef, nsv)
+    Ud = vecs in (:left, :both) ? B200Vector{T}(A.ctx, m * nsv) : nothing
+    Vd = vecs in (:right, :both) ? B200Vector{T}(A.ctx, n * nsv) : nothing
+    ritz = zeros(k, maxiter); resn = zeros(nsv, maxiter); conv = zeros(Int32, nsv, maxiter); betas = zeros(maxiter); B = zeros(k, k)
+    o = SvdlOpts(nsv, k, j, 0, maxiter, tol, reltol, dolock, 0)
+    check(ccall((:b200_svdl, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{SvdlOpts}, Ref{SvdlResult}, Ptr{Float64}, Ptr{Cvoid}, Int64,
+                 Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+                A.ctx.h, A.h, At.h, v0d.p, o, res, σ, Ud === nothing ? C_NULL : Ud.p, m, Vd === nothing ? C_NULL : Vd.p, n,
+                ritz, resn, conv, betas, B))
+    values = T.(σ)
+    X = vecs == :none ? values :
+        LinearAlgebra.SVD(Ud === nothing ? zeros(T, m, 0) : reshape(Array(Ud), m, nsv), values,
+                          Vd === nothing ? zeros(T, 0, n) : Matrix(reshape(Array(Vd), n, nsv)'))
+    L = (B = B, β = res.beta)                              # the projected factorisation (P, Q stay on the device)
+    log || return X, L
+    h = ConvergenceHistory(partial = false); h[:tol] = res.tol
+    h.iters = res.iters; h.mvps = res.mvps; h.mtvps = res.mtvps; h.isconverged = res.isconverged != 0
+    it = res.iters
+    h.data[:ritz] = ritz[:, 1:it]; h.data[:resnorm] = resn[:, 1:it]; h.data[:conv] = conv[:, 1:it] .!= 0; h.data[:betas] = betas[1:it]
+    X, L, h
+end
 
 # ------------------------------------------------------------------------------------------- matrix-free operators
 # Anything with mul!(y::B200Vector, A, x::B200Vector) (a LinearMap over device vectors, a user type, a closure) can be

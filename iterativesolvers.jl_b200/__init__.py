@@ -19,4 +19,5 @@ from .generators import laplace_matrix, laplace_csr_slab, advection_dominated, m
 from .solvers import (cg, cg_, chebyshev, chebyshev_, gmres, gmres_, minres, minres_, bicgstabl, bicgstabl_, lobpcg,  # noqa: F401
                       LOBPCGResults, orthogonalize_and_normalize_, hessenberg_ldiv_,
                       cg_iterator_, CGIterable, CGStateVariables,
-                      qmr, qmr_, lsqr, lsqr_, lsmr, lsmr_, idrs, idrs_, LobpcgConstraint)
+                      qmr, qmr_, lsqr, lsqr_, lsmr, lsmr_, idrs, idrs_, LobpcgConstraint, svdl, SVD,
+                      PartialFactorization)

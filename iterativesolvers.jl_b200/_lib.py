@@ -83,6 +83,16 @@ class LinOp(C.Structure):
                 ("n_global", C.c_int64), ("m_global", C.c_int64), ("dtype", C.c_int32), ("reserved", C.c_int32)]
 
 
+class SvdlOpts(C.Structure):
+    _fields_ = [("nsv", C.c_int32), ("k", C.c_int32), ("j", C.c_int32), ("method", C.c_int32), ("maxiter", C.c_int64),
+                ("tol", C.c_double), ("reltol", C.c_double), ("dolock", C.c_int32), ("reserved", C.c_int32)]
+
+
+class SvdlResult(C.Structure):
+    _fields_ = [("iters", C.c_int64), ("mvps", C.c_int64), ("mtvps", C.c_int64), ("isconverged", C.c_int32),
+                ("k", C.c_int32), ("beta", C.c_double), ("tol", C.c_double)]
+
+
 class LobpcgOpts(C.Structure):
     _fields_ = [("tol", C.c_double), ("maxiter", C.c_int64), ("largest", C.c_int32), ("blocksize", C.c_int32),
                 ("P", Precond), ("fixed_iterations", C.c_int32), ("reserved", C.c_int32)]
@@ -185,6 +195,10 @@ SIGNATURES = {
                                   C.POINTER(LsqResult), _P, _I64]),
     "b200_idrs_solve_op": (_INT, [_P, C.POINTER(LinOp), _P, _P, C.POINTER(IdrsOpts), C.POINTER(Result), _P, _I64]),
     "b200_lobpcg_solve": (_INT, [_P, _P, _P, _I64, C.POINTER(LobpcgOpts), C.POINTER(LobpcgResult), _P, _P]),
+    "b200_svdl": (_INT, [_P, _P, _P, _P, C.POINTER(SvdlOpts), C.POINTER(SvdlResult), _P, _P, _I64, _P, _I64, _P, _P, _P, _P,
+                         _P]),
+    "b200_svdl_op": (_INT, [_P, C.POINTER(LinOp), C.POINTER(LinOp), _P, C.POINTER(SvdlOpts), C.POINTER(SvdlResult), _P, _P,
+                            _I64, _P, _I64, _P, _P, _P, _P, _P]),
     "b200_lobpcg_constraint_create": (_INT, [_P, _I64, _P, _I64, _INT, _INT, _INT, C.POINTER(_P)]),
     "b200_lobpcg_constraint_append": (_INT, [_P, _P, _P, _I64, _INT]),
     "b200_lobpcg_constraint_apply": (_INT, [_P, _P, _P, _I64, _INT]),

@@ -796,6 +796,92 @@ def lobpcg(A, largest: bool, X0, nev=None, *, P=None, C_=None, tol=None, maxiter
 
 
 # ------------------------------------------------------------------------------------------------
+# svdl  (reference src/svdl.jl:157-247)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class PartialFactorization:
+    """what svdl returns as `L` (reference src/svdl.jl:76-84): here the projected matrix B (k x k, dense) and beta;
+    the Lanczos bases P, Q stay on the device inside the engine."""
+    B: np.ndarray
+    beta: float
+
+
+@dataclass
+class SVD:
+    """LinearAlgebra.SVD(leftvecs, values, rightvecs) as svdl builds it (src/svdl.jl:243-246): U m x nsv, S, Vt nsv x n
+    (empty blocks for the sides `vecs` did not ask for)."""
+    U: np.ndarray
+    S: np.ndarray
+    Vt: np.ndarray
+
+
+def svdl(A, *, nsv=6, k=None, tol=None, maxiter=None, method="ritz", log=False, v0=None, j=None, reltol=None,
+         vecs="none", dolock=False, verbose=False, rng=None):
+    """svdl(A; nsv, k, tol, maxiter, method, log, v0, j, reltol, vecs, dolock) -> Σ, L[, history]
+    (reference src/svdl.jl:157-247).  A: B200CSR (m x n, single GPU) or a B200LinearOperator with adjoint_mul.
+    v0: starting vector in the domain of A (host or device); default randn normalised (src/svdl.jl:178)."""
+    _check_operator(A, linop_ok=True)
+    if method == "harmonic":
+        raise B200Error("method = :harmonic is not implemented (reference src/svdl.jl:424-520); use :ritz")
+    if method != "ritz":
+        raise ValueError(f"Unknown restart method {method}")              # ArgumentError  src/svdl.jl:199
+    if vecs not in ("none", "left", "right", "both"):
+        raise ValueError(f"vecs = {vecs!r}")
+    m, n = A.m_local, (A.n_local if _is_linop(A) else (A.n_global if A.ctx.world == 1 else A.m_local))
+    sq = math.sqrt(np.finfo(np.float64).eps)                              # sqrt(eps()): Float64 literal  :158, :179
+    tol = sq if tol is None else tol
+    reltol = sq if reltol is None else reltol
+    k = 2 * nsv if k is None else int(k)                                  # :158
+    j = nsv if j is None else int(j)                                      # :178
+    maxiter = min(A.shape) if maxiter is None else int(maxiter)           # :159
+    if v0 is None:
+        rng = rng or np.random.default_rng()
+        v0 = rng.standard_normal(n).astype(A.dtype)
+        v0 /= np.linalg.norm(v0)
+    v0d = v0 if is_device(v0) else DeviceArray.from_numpy(A.ctx, np.asarray(v0, dtype=A.dtype))
+    if v0d.shape[0] != n:
+        raise ValueError("v0 must have as many entries as A has columns")
+    want_u, want_v = vecs in ("left", "both"), vecs in ("right", "both")
+    Ud = DeviceArray(A.ctx, (m, nsv), A.dtype) if want_u else None
+    Vd = DeviceArray(A.ctx, (n, nsv), A.dtype) if want_v else None
+    opts = _lib.SvdlOpts(int(nsv), k, j, 0, maxiter, float(tol), float(reltol), int(bool(dolock)), 0)
+    res = _lib.SvdlResult()
+    sigma = np.zeros(nsv)
+    mi = max(maxiter, 1)
+    ritz, resn = np.zeros((mi, k)), np.zeros((mi, nsv))
+    conv, betas, Bk = np.zeros((mi, nsv), dtype=np.int32), np.zeros(mi), np.zeros((k, k), order="F")
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    common = (as_device_ptr(v0d), C.byref(opts), C.byref(res), vp(sigma), as_device_ptr(Ud) if want_u else None, m,
+              as_device_ptr(Vd) if want_v else None, n, vp(ritz), vp(resn), vp(conv), vp(betas), vp(Bk))
+    if _is_linop(A):
+        At = A.adjoint()
+        check(_call_op(lib().b200_svdl_op, (A, At), A.ctx._h, C.byref(A._c), C.byref(At._c), *common))
+    else:
+        check(lib().b200_svdl(A.ctx._h, A._h, A.adjoint()._h, *common))
+    it = int(res.iters)
+    values = sigma.astype(A.dtype)
+    L = PartialFactorization(Bk, float(res.beta))
+    if vecs == "none":
+        X = values                                                        # :243-244
+    else:
+        U = Ud.numpy() if want_u else np.zeros((m, 0), dtype=A.dtype)     # :230-235
+        Vt = Vd.numpy().T.copy() if want_v else np.zeros((0, n), dtype=A.dtype)   # :236-241
+        X = SVD(U, values, Vt)
+    if verbose:
+        for i in range(it):
+            print(f"Iteration {i + 1}: beta = {betas[i]:1.3e}, converged {int(conv[i].sum())}/{nsv}")
+    if not log:
+        return X, L
+    h = ConvergenceHistory()
+    h["tol"] = float(res.tol)                                             # :164
+    h.isconverged = bool(res.isconverged)
+    h.iters, h.mvps, h.mtvps = it, int(res.mvps), int(res.mtvps)
+    h["ritz"], h["resnorm"] = ritz[:it].copy(), resn[:it].copy()          # :209, :348
+    h["conv"], h["betas"] = conv[:it].astype(bool), betas[:it].copy()     # :208, :211
+    return X, L, h
+
+
+# ------------------------------------------------------------------------------------------------
 # L1 helpers exposed for tests / drop-in use
 # ------------------------------------------------------------------------------------------------
 def orthogonalize_and_normalize_(V: DeviceArray, w: DeviceArray, h: np.ndarray, method="mgs", k=None):

@@ -1619,3 +1619,156 @@ def idrs(A, b, **kw):
     """idrs(A, b; kwargs...) = idrs!(zerox(A, b), A, b; kwargs...) -- src/idrs.jl:11."""
     x = np.zeros(opsize(A, 1), dtype=b.dtype)
     return idrs_(x, A, b, **kw)
+
+
+# --------------------------------------------------------------------------------------------
+# svdl (reference src/svdl.jl) -- Golub-Kahan-Lanczos bidiagonalisation with thick restart (method = :ritz)
+# --------------------------------------------------------------------------------------------
+@dataclass
+class PartialFactorization:
+    """A ~ P * [B 0; 0 beta] * Q  -- reference src/svdl.jl:76-84.  B is kept dense here (the reference stores a
+    Bidiagonal / BrokenArrowBidiagonal, :19-66: same entries)."""
+    P: np.ndarray
+    Q: np.ndarray
+    B: np.ndarray
+    beta: float
+
+
+def _svdl_extend(history, A, L, k, orthleft=False, orthright=True, alpha_thr=1 / math.sqrt(2)):
+    """extend!(log, A, L, k) -- reference src/svdl.jl:542-609."""
+    l = L.B.shape[1] - 1                                                # :547
+    p = L.P[:, l].copy()                                                # :548
+    Tr = L.B.dtype.type
+    B = np.zeros((k, k), dtype=L.B.dtype)
+    B[: L.B.shape[0], : L.B.shape[1]] = L.B
+    beta = L.beta                                                       # :561
+    for j in range(l + 1, k + 1):                                       # :563 (1-based j)
+        history.mtvps += 1                                              # :564
+        q = mul_adjoint(A, p)                                           # :565
+        if orthright:                                                   # :567-574
+            oldqnorm = np.linalg.norm(q)
+            q = q - L.Q @ (L.Q.conj().T @ q)
+            if np.linalg.norm(q) <= alpha_thr * oldqnorm:
+                q = q - L.Q @ (L.Q.conj().T @ q)
+        beta = Tr(np.linalg.norm(q))                                    # :576
+        q = q * (Tr(1) / beta)                                          # :577
+        L.Q = np.column_stack([L.Q, q])                                 # :579
+        if j == k:                                                      # :580
+            break
+        history.mvps += 1                                               # :582
+        p = mul(A, q)                                                   # :584
+        p = p - beta * L.P[:, j - 1]                                    # :585
+        if orthleft:                                                    # :587-594
+            oldpnorm = np.linalg.norm(p)
+            p = p - L.P @ (L.P.conj().T @ p)
+            if np.linalg.norm(p) <= alpha_thr * oldpnorm:
+                p = p - L.P @ (L.P.conj().T @ p)
+        alpha = Tr(np.linalg.norm(p))                                   # :596
+        p = p * (Tr(1) / alpha)                                         # :597
+        B[j, j] = alpha                                                 # push!(L.B.dv, alpha) :599 / :602
+        B[j - 1, j] = beta                                              # push!(L.B.ev, beta)  :600 / :603
+        L.P = np.column_stack([L.P, p])                                 # :605
+    L.B = B
+    L.beta = beta                                                       # :607
+    return L
+
+
+def _svdl_thickrestart(A, L, U, S, V, l):
+    """thickrestart!(A, L, F, l) -- reference src/svdl.jl:376-404."""
+    k = V.shape[0]                                                      # :379
+    Tr = L.B.dtype.type
+    Q = L.Q[:, :k] @ V[:, :l]                                           # :384
+    L.Q = np.column_stack([Q, L.Q[:, k]])                               # :385
+    f = mul(A, L.Q[:, l])                                               # :390
+    rho = L.beta * U[-1, :l]                                            # :391
+    L.P = L.P[:, :k] @ U[:, :l]                                         # :392
+    f = f - L.P @ rho                                                   # :395
+    alpha = Tr(np.linalg.norm(f))                                       # :396
+    f = f * (Tr(1) / alpha)                                             # :397
+    L.P = np.column_stack([L.P, f])                                     # :398
+    g = mul_adjoint(A, f) - alpha * L.Q[:, -1]                          # :400
+    L.beta = Tr(np.linalg.norm(g))                                      # :401
+    B = np.zeros((l + 1, l + 1), dtype=L.B.dtype)                       # BrokenArrowBidiagonal([S[1:l]; alpha], rho, []) :402
+    B[np.arange(l), np.arange(l)] = S[:l]
+    B[l, l] = alpha
+    B[:l, l] = rho
+    L.B = B
+    return L
+
+
+def _svdl_isconverged(L, U, S, k, tol, reltol):
+    """isconverged(L, F, k, tol, reltol, log) -- reference src/svdl.jl:290-350; returns (conv, delta_sigma)."""
+    sigma = S[:k]                                                       # :296
+    dsig = L.beta * np.abs(U[-1, :k])                                   # :297
+    delta = dsig.copy()                                                 # :300
+    if k > 1:                                                           # :307
+        d = np.inf
+        for i in range(k):
+            for j in range(i):
+                d = min(d, abs(sigma[i] - sigma[j]))                    # :308-311
+        for i in range(k):                                              # :316-340
+            a = dsig[i]
+            if 2 * a <= d:
+                y = a * a / d                                           # :326
+                delta[i] = min(delta[i], y)                             # :328
+    return delta[:k] < max(tol, reltol * sigma[0]), delta[:k]           # :349
+
+
+def svdl(A, *, nsv=6, k=None, tol=None, maxiter=None, method="ritz", log=False, v0=None, j=None, reltol=None,
+         vecs="none", dolock=False, rng=None):
+    """svdl(A; nsv, k, tol, maxiter, method, log, v0, j, reltol, vecs, dolock) -- reference src/svdl.jl:157-175 and
+    svdl_method! :177-247 (method = :ritz; :harmonic raises like an unknown method would not: NotImplementedError)."""
+    m, n = opsize(A, 0), opsize(A, 1)
+    sq = math.sqrt(np.finfo(np.float64).eps)                            # tol::Real = sqrt(eps()) :158, :179 (Float64 literal)
+    tol = sq if tol is None else tol
+    reltol = sq if reltol is None else reltol
+    k = 2 * nsv if k is None else k                                     # :158
+    j = nsv if j is None else j                                         # :178
+    maxiter = min(m, n) if maxiter is None else maxiter                 # :159
+    if method == "harmonic":
+        raise NotImplementedError("method = :harmonic is not restated")
+    if method != "ritz":
+        raise ValueError(f"Unknown restart method {method}")            # :199 ArgumentError
+    if v0 is None:
+        rng = rng or np.random.default_rng()
+        v0 = rng.standard_normal(n)
+        v0 = v0 / np.linalg.norm(v0)                                    # :178
+    history = ConvergenceHistory()
+    history["tol"] = tol
+    conv_h, ritz_h, res_h, beta_h = [], [], [], []
+    assert k > 1                                                        # :183
+    T = v0.dtype.type
+    # build(log, A, v0, k) :353-363
+    q = v0.astype(v0.dtype, copy=True)
+    beta = np.linalg.norm(q)                                            # :356
+    q = q * (T(1) / T(beta))                                            # :357
+    p = mul(A, q)                                                       # :358
+    alpha = T(np.linalg.norm(p))                                        # :359
+    p = p * (T(1) / alpha)                                              # :360
+    L = PartialFactorization(p.reshape(m, 1), q.reshape(n, 1), np.array([[alpha]], dtype=v0.dtype), T(beta))
+    L = _svdl_extend(history, A, L, k)                                  # :362
+    U = S = Vt = None
+    l = nsv
+    for it in range(1, maxiter + 1):                                    # :188
+        history.iters += 1                                              # nextiter!(log) :189
+        U, S, Vt = np.linalg.svd(np.asarray(L.B, dtype=v0.dtype))       # F = svd(L.B) :192
+        L = _svdl_thickrestart(A, L, U, S, Vt.conj().T, j)              # :195
+        L = _svdl_extend(history, A, L, k)                              # :201
+        conv, dsig = _svdl_isconverged(L, U, S, l, tol, reltol)         # :207
+        conv_h.append(conv.copy()); ritz_h.append(S[:k].copy()); res_h.append(dsig.copy()); beta_h.append(float(L.beta))
+        if dolock:                                                      # :214-221
+            for i in range(len(conv)):
+                if conv[i]:
+                    L.B[i, j] = 0                                       # L.B.av[i] = 0
+        if np.all(conv):                                                # :222
+            history.isconverged = True
+            break
+    values = S[:l].copy()                                               # :227
+    V = Vt.conj().T
+    res = values
+    if vecs != "none":
+        leftvecs = L.P @ U[:, :l] if vecs in ("left", "both") else np.zeros((m, 0), dtype=v0.dtype)       # :230-241
+        rightvecs = (L.Q[:, :-1] @ V[:, :l]).conj().T if vecs in ("right", "both") else np.zeros((0, n), dtype=v0.dtype)
+        res = (leftvecs, values, rightvecs)                             # LinearAlgebra.SVD(leftvecs, values, rightvecs)
+    history["conv"], history["ritz"], history["resnorm"], history["betas"] = conv_h, ritz_h, res_h, beta_h
+    return (res, L, history) if log else (res, L)

@@ -23,6 +23,7 @@
 #include "../../iterativesolvers.jl_b200/csrc/idrs_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/cg_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/lobpcg_constraint_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/svdl_core.h"
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -270,4 +271,38 @@ EXPORT int hostsim_constraint_apply(int is_f64, int64_t n, const void *Y, int64_
                                                  g_dev.data(), g_host.data())
                 : b200::constraint_apply<float>(be, (const float *)Y, ldy, nc, U.data(), (float *)X, rs, cs, bs, n,
                                                 g_dev.data(), g_host.data());
+}
+
+struct hostsim_svdl_out {
+  int64_t iters, mvps, mtvps;
+  int32_t converged, kdim;
+  double beta;
+};
+EXPORT int hostsim_svdl(int is_f64, const hostsim_csr *A, const hostsim_csr *At, const void *v0, int nsv, int k, int jkeep,
+                        double tol, double reltol, int64_t maxiter, int dolock, double *sigma, void *U, void *V,
+                        double *hist_ritz, double *hist_resnorm, int *hist_conv, double *hist_betas, double *Bk,
+                        int order, int split, hostsim_svdl_out *out) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64), at = mk(At, is_f64);
+  b200::SvdlOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st = is_f64 ? b200::svdl_run<double>(be, &a, &at, A->m, At->m, (const double *)v0, nsv, k, jkeep, tol, reltol, maxiter,
+                                           dolock, sigma, (double *)U, A->m, (double *)V, At->m, hist_ritz, hist_resnorm,
+                                           hist_conv, hist_betas, Bk, &o)
+                  : b200::svdl_run<float>(be, &a, &at, A->m, At->m, (const float *)v0, nsv, k, jkeep, tol, reltol, maxiter,
+                                          dolock, sigma, (float *)U, A->m, (float *)V, At->m, hist_ritz, hist_resnorm,
+                                          hist_conv, hist_betas, Bk, &o);
+  out->iters = o.iters; out->mvps = o.mvps; out->mtvps = o.mtvps; out->converged = o.converged; out->kdim = o.kdim;
+  out->beta = o.beta;
+  return st;
+}
+
+EXPORT void hostsim_dense_svd(int n, const double *A, double *U, double *S, double *V) {
+  std::vector<double> a(A, A + (size_t)n * n), u, s, v;
+  b200::dense_svd(a, n, u, s, v);
+  memcpy(U, u.data(), sizeof(double) * (size_t)n * n);
+  memcpy(S, s.data(), sizeof(double) * n);
+  memcpy(V, v.data(), sizeof(double) * (size_t)n * n);
 }

@@ -217,3 +217,49 @@ def set_dist(apply=None, allreduce=None):
     a, r = _APPLY_CB(apply), _ALLREDUCE_CB(allreduce)
     _dist_keep.extend([a, r])
     lib().hostsim_set_dist(a, r)
+
+
+class _SvdlOut(C.Structure):
+    _fields_ = [("iters", C.c_int64), ("mvps", C.c_int64), ("mtvps", C.c_int64), ("converged", C.c_int32),
+                ("kdim", C.c_int32), ("beta", C.c_double)]
+
+
+def svdl(A, v0, *, nsv=6, k=None, j=None, tol=None, reltol=None, maxiter=None, dolock=False, vecs=True, order=0, split=0,
+         At=None):
+    """the svdl engine (csrc/svdl_core.h) on the serial backend -> dict(sigma, U, V, iters, mvps, mtvps, converged,
+    ritz, resnorm, conv, betas, B)."""
+    dt = np.dtype(v0.dtype)
+    Ac, Atc = Csr(A, dt), Csr(sp.csr_matrix(A).T if At is None else At, dt)
+    m, n = Ac.shape[0], Atc.shape[0]
+    k = 2 * nsv if k is None else k
+    j = nsv if j is None else j
+    sq = float(np.sqrt(np.finfo(np.float64).eps))
+    tol = sq if tol is None else tol
+    reltol = sq if reltol is None else reltol
+    maxiter = min(A.shape) if maxiter is None else maxiter
+    v0 = np.ascontiguousarray(v0, dtype=dt)
+    sigma = np.zeros(nsv)
+    U = np.zeros((m, nsv), dtype=dt, order="F") if vecs else None
+    V = np.zeros((n, nsv), dtype=dt, order="F") if vecs else None
+    ritz, resn = np.zeros((maxiter, k)), np.zeros((maxiter, nsv))
+    conv, betas, Bk = np.zeros((maxiter, nsv), dtype=np.int32), np.zeros(maxiter), np.zeros((k, k), order="F")
+    out = _SvdlOut()
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+    st = lib().hostsim_svdl(C.c_int(dt == np.float64), C.byref(Ac.c), C.byref(Atc.c), vp(v0), C.c_int(nsv), C.c_int(k),
+                            C.c_int(j), C.c_double(tol), C.c_double(reltol), C.c_int64(maxiter), C.c_int(dolock),
+                            vp(sigma), vp(U), vp(V), vp(ritz), vp(resn), vp(conv), vp(betas), vp(Bk), C.c_int(order),
+                            C.c_int(split), C.byref(out))
+    assert st == 0, st
+    it = out.iters
+    return dict(sigma=sigma, U=U, V=V, iters=it, mvps=out.mvps, mtvps=out.mtvps, converged=bool(out.converged),
+                ritz=ritz[:it], resnorm=resn[:it], conv=conv[:it].astype(bool), betas=betas[:it], B=Bk, beta=out.beta)
+
+
+def dense_svd(A):
+    """the host SVD the svdl engine applies to its projected matrix (one-sided Jacobi, csrc/svdl_core.h)."""
+    A = np.asfortranarray(A, dtype=np.float64)
+    n = A.shape[0]
+    U, S, V = np.zeros((n, n), order="F"), np.zeros(n), np.zeros((n, n), order="F")
+    lib().hostsim_dense_svd(C.c_int(n), C.c_void_p(A.ctypes.data), C.c_void_p(U.ctypes.data), C.c_void_p(S.ctypes.data),
+                            C.c_void_p(V.ctypes.data))
+    return U, S, V

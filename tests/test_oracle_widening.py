@@ -518,3 +518,123 @@ def test_partitioned_engines_world2_gloo():
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, f"rank {r} failed:\n{o[-3000:]}"
         assert f"rank {r} ok" in o
+
+
+# ------------------------------------------------------------------------------------------ svdl
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_oracle_svdl_reference_tests(oracle, dtype):
+    """test/svdl.jl:16-69 on the oracle (method = :ritz): diagonal matrix, singular vectors, issue #55, rectangular."""
+    n, ns, tol = 30, 5, 1e-5
+    A = np.diag(np.arange(1.0, n + 1)).astype(dtype)
+    q = (np.ones(n) / np.sqrt(n)).astype(dtype)
+    sig, L, h = oracle.svdl(A, nsv=ns, v0=q, tol=tol, reltol=tol, maxiter=n, vecs="none", log=True)
+    assert np.linalg.norm(sig - np.arange(n, n - 5, -1.0)) < 5 ** 2 * 1e-5
+    with pytest.raises(ValueError):
+        oracle.svdl(A, nsv=ns, v0=q, tol=tol, reltol=tol, maxiter=n, method="fakemethod")
+    (U, S, Vt), L = oracle.svdl(A, nsv=ns, v0=q, tol=tol, reltol=tol, maxiter=n, vecs="both")
+    U, Vt = U.copy(), Vt.copy()
+    for i in range(5):
+        U[n - 1 - i, i] -= np.sign(U[n - 1 - i, i])
+        Vt[i, n - 1 - i] -= np.sign(Vt[i, n - 1 - i])
+    assert np.linalg.norm(U) < sig[0] * math.sqrt(tol) and np.linalg.norm(Vt) < sig[0] * math.sqrt(tol)
+    assert np.linalg.norm(sig - S) < 2 * max(tol * ns * sig[0], tol)
+    s1, _ = oracle.svdl(A, nsv=1, tol=tol, reltol=tol, rng=np.random.default_rng(3))                    # issue #55
+    assert abs(sig[0] - s1[0]) < 10 * max(tol * sig[0], tol)
+    rng = np.random.default_rng(1)
+    B = rng.standard_normal((300, 200)).astype(dtype)
+    q = rng.standard_normal(200).astype(dtype)
+    q /= np.linalg.norm(q)
+    s, L = oracle.svdl(B, nsv=5, k=10, v0=q, tol=1e-5, maxiter=30)
+    assert np.linalg.norm(s - np.linalg.svd(B.astype(np.float64), compute_uv=False)[:5]) < 25 * 1e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 2e-5)])
+def test_engine_svdl_matches_oracle(oracle, sim, dtype, tol):
+    for order, split in ((0, 0), (1, 1)):
+        cases.case_svdl_matches_oracle(oracle, lambda A, v0, **kw: sim.svdl(A, v0, order=order, split=split, **kw),
+                                       dtype, tol)
+
+
+def test_dense_svd_host_helper(sim):
+    """the one-sided Jacobi SVD the svdl engine applies to its projected matrix (stands where the reference calls
+    LAPACK through svd(L.B), src/svdl.jl:192): against numpy on random, graded, upper-bidiagonal and broken-arrow
+    matrices (the two shapes L.B takes, src/svdl.jl:19-66)."""
+    rng = np.random.default_rng(5)
+    mats = [rng.standard_normal((n, n)) for n in (1, 2, 7, 20)]
+    mats.append(rng.standard_normal((9, 9)) @ np.diag(10.0 ** -np.arange(9.0)) @ rng.standard_normal((9, 9)))
+    bid = np.diag(rng.random(12) + 0.5) + np.diag(rng.random(11), 1)
+    mats.append(bid)
+    arrow = np.diag(np.sort(rng.random(8) + 1)[::-1])
+    arrow[:5, 5] = 1e-3 * rng.random(5)
+    arrow[5, 6], arrow[6, 7] = 0.3, 0.2
+    mats.append(arrow)
+    for A in mats:
+        n = A.shape[0]
+        U, S, V = sim.dense_svd(A)
+        assert np.all(np.diff(S) <= 0) and np.abs(S - np.linalg.svd(A, compute_uv=False)).max() <= 1e-13 * max(S[0], 1)
+        assert np.abs(U @ np.diag(S) @ V.T - A).max() <= 1e-13 * max(S[0], 1)
+        assert np.abs(U.T @ U - np.eye(n)).max() <= 1e-12 and np.abs(V.T @ V - np.eye(n)).max() <= 1e-12
+
+
+def test_python_svdl_wrapper_with_a_fake_library(monkeypatch):
+    """argument marshalling of isb.svdl (CSR and callback operators, vecs, log, defaults, argument errors) against a
+    recording fake of the C library."""
+    import ctypes as C
+    from importlib import import_module
+    import iterativesolvers_jl_b200 as isb
+    S = import_module("iterativesolvers_jl_b200.solvers")
+    calls = []
+
+    class FakeArr:
+        def __init__(self, a=None, shape=None, dtype=np.float64):
+            self.a = np.array(a, order="F") if a is not None else np.zeros(shape, dtype=dtype, order="F")
+            self.shape, self.dtype = self.a.shape, self.a.dtype
+            self._p = C.c_void_p(0x7000)
+
+        @classmethod
+        def from_numpy(cls, ctx, a):
+            return cls(a)
+
+        def numpy(self):
+            return self.a.copy(order="F")
+
+    class FakeLib:
+        def __getattr__(self, name):
+            def f(*args):
+                calls.append((name, args))
+                if name.startswith("b200_svdl"):
+                    opts = [a._obj for a in args if isinstance(getattr(a, "_obj", None), S._lib.SvdlOpts)][0]
+                    res = [a._obj for a in args if isinstance(getattr(a, "_obj", None), S._lib.SvdlResult)][0]
+                    res.iters, res.mvps, res.mtvps, res.isconverged, res.k, res.beta, res.tol = 2, 7, 9, 1, opts.k, 0.5, opts.tol
+                    calls.append(("opts", (opts.nsv, opts.k, opts.j, opts.method, opts.maxiter, opts.dolock)))
+                return 0
+            return f
+
+    monkeypatch.setattr(S, "lib", lambda: FakeLib())
+    monkeypatch.setattr(S, "DeviceArray", lambda ctx, shape, dtype: FakeArr(shape=shape, dtype=dtype))
+    S.DeviceArray.from_numpy = FakeArr.from_numpy
+    monkeypatch.setattr(S, "is_device", lambda v: isinstance(v, FakeArr))
+    monkeypatch.setattr(S, "as_device_ptr", lambda v: v._p)
+    A = S.B200CSR.__new__(S.B200CSR)
+    A.ctx, A._h, A.m_local, A.n_global, A.m_global, A.dtype = SimpleNamespace(_h=None, world=1), C.c_void_p(7), 40, 25, 40, np.dtype(np.float64)
+    A._adjoint = SimpleNamespace(_h=C.c_void_p(8))
+    A.close = lambda: None
+    sig, L = isb.svdl(A, nsv=3, rng=np.random.default_rng(0))
+    assert calls[0][0] == "b200_svdl" and calls[1] == ("opts", (3, 6, 3, 0, 25, 0)) and sig.shape == (3,) and L.B.shape == (6, 6)
+    calls.clear()
+    X, L, h = isb.svdl(A, nsv=2, k=8, j=2, maxiter=5, vecs="both", log=True, dolock=True, v0=np.ones(25) / 5)
+    assert calls[1] == ("opts", (2, 8, 2, 0, 5, 1))
+    assert X.U.shape == (40, 2) and X.Vt.shape == (2, 25) and X.S.shape == (2,)
+    assert (h.iters, h.mvps, h.mtvps, h.isconverged) == (2, 7, 9, True) and h["ritz"].shape == (2, 8) and h["conv"].shape == (2, 2)
+    X, L = isb.svdl(A, nsv=2, vecs="left", v0=np.ones(25) / 5)
+    assert X.U.shape == (40, 2) and X.Vt.shape == (0, 25)
+    with pytest.raises(ValueError):
+        isb.svdl(A, method="fakemethod")                     # test/svdl.jl:28
+    with pytest.raises(isb.B200Error):
+        isb.svdl(A, method="harmonic")
+    with pytest.raises(ValueError):
+        isb.svdl(A, v0=np.ones(40))                          # v0 lives in the domain of A
+    calls.clear()
+    op = isb.B200LinearOperator((40, 25), np.float64, lambda y, x: None, adjoint_mul=lambda y, x: None, ctx=A.ctx)
+    isb.svdl(op, nsv=2, v0=np.ones(25) / 5)
+    assert calls[0][0] == "b200_svdl_op"
