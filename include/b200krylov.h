@@ -50,7 +50,10 @@ enum { B200_ORTH_MGS = 0, B200_ORTH_CGS = 1, B200_ORTH_DGKS = 2 };
 
 /* Pl / Pr kinds.  Identity() = reference src/common.jl:28-32; JACOBI = the diagonal
  * preconditioner idiom of reference test/cg.jl:14-18 (ldiv!(y,P,x) = y .= x ./ P.diagonal). */
-enum { B200_PREC_IDENTITY = 0, B200_PREC_JACOBI = 1 };
+enum { B200_PREC_IDENTITY = 0, B200_PREC_JACOBI = 1,
+       B200_PREC_CALLBACK = 2 /* `diag` points to a b200_linop whose apply is ldiv!(y, Pl, x); accepted by
+                                 b200_idrs_solve / b200_idrs_solve_op (b200_cg_solve_op takes its callback as an
+                                 argument); the other engines reject it */ };
 
 typedef struct b200_ctx b200_ctx;   /* device + stream (+ NCCL communicator)                     */
 typedef struct b200_csr b200_csr;   /* the operator A: CSR int32 on device, row-partitioned       */

@@ -12,7 +12,7 @@ _SO = os.path.join(_HERE, "libb200krylov.so")
 
 F64, F32 = 0, 1
 ORTH_MGS, ORTH_CGS, ORTH_DGKS = 0, 1, 2
-PREC_IDENTITY, PREC_JACOBI = 0, 1
+PREC_IDENTITY, PREC_JACOBI, PREC_CALLBACK = 0, 1, 2
 ERR_INVALID = -1
 ERR_BREAKDOWN = -5
 ERR_CALLBACK = -7

@@ -14,21 +14,30 @@ int idrs_dispatch(b200_ctx *ctx, const CudaOp &A, int dtype, int64_t n, int64_t 
   B200_REQUIRE(opts->s >= 1 && opts->s <= kIdrsMaxS, "shadow space dimension s must be in [1, %d]", kIdrsMaxS);
   B200_REQUIRE(opts->P && opts->ldp >= n, "P (n x s shadow vectors, device) is required: the reference draws "
                                           "rand!(copy(C)) (src/idrs.jl:132), the host passes the draw");
-  B200_REQUIRE(opts->Pl.kind == B200_PREC_IDENTITY || (opts->Pl.kind == B200_PREC_JACOBI && opts->Pl.diag),
+  B200_REQUIRE(opts->Pl.kind == B200_PREC_IDENTITY ||
+                   ((opts->Pl.kind == B200_PREC_JACOBI || opts->Pl.kind == B200_PREC_CALLBACK) && opts->Pl.diag),
                "unsupported preconditioner");
+  const b200_linop *plfn = opts->Pl.kind == B200_PREC_CALLBACK ? (const b200_linop *)opts->Pl.diag : nullptr;
+  if (plfn) {
+    B200_TRY(check_linop(plfn, "Pl"));
+    B200_REQUIRE(plfn->dtype == dtype && plfn->m_local == n && plfn->n_local == n,
+                 "Pl must act on vectors of the operator's local length");
+  }
   B200_CUDA(cudaSetDevice(ctx->device));
   CudaBackend be{ctx};
   IdrsOutcome o;
   memset(&o, 0, sizeof(o));
   const void *diag = opts->Pl.kind == B200_PREC_JACOBI ? opts->Pl.diag : nullptr;
+  CudaOp plop{nullptr, plfn};
+  const CudaOp *plp = plfn ? &plop : nullptr;
   const int st =
       dtype == B200_F64
           ? idrs_run<double>(be, &A, n, n_global, (double *)x_dev, (const double *)b_dev, opts->s,
                              (const double *)opts->P, opts->ldp, (const double *)diag, opts->abstol, opts->reltol,
-                             opts->maxiter, opts->smoothing, opts->check_every, resnorm_cap, resnorm_host, &o)
+                             opts->maxiter, opts->smoothing, opts->check_every, resnorm_cap, resnorm_host, &o, plp)
           : idrs_run<float>(be, &A, n, n_global, (float *)x_dev, (const float *)b_dev, opts->s, (const float *)opts->P,
                             opts->ldp, (const float *)diag, opts->abstol, opts->reltol, opts->maxiter, opts->smoothing,
-                            opts->check_every, resnorm_cap, resnorm_host, &o);
+                            opts->check_every, resnorm_cap, resnorm_host, &o, plp);
   if (st != B200_OK) return st;
   if (res) {
     res->iters = o.iters;

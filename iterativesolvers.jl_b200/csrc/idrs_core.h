@@ -157,6 +157,51 @@ struct IdrsNewU {
   B200_HD void finish(const double *) const {}
 };
 
+// ---- V with a callback preconditioner: the fused form above is split around ldiv!(Pl, V) (:199)
+template <typename T>
+struct IdrsVQ {               // V = R - sum c_i G_i ; Q = sum c_i U_i   :187-196
+  static constexpr int NRED = 0;
+  const T *G, *U, *R;
+  T *V, *Q;
+  int64_t ld;
+  int k;
+  const IdrsScal *s;
+  int ns;
+  T c[kIdrsMaxS];
+  B200_HD bool skip() const { return s->done != 0; }
+  B200_HD void load() {
+    ns = s->s;
+    for (int j = 0; j < kIdrsMaxS; ++j) c[j] = (T)s->c[j];
+  }
+  B200_HD void elem(int64_t i, double *) const {
+    T v = c[0] * G[i + k * ld];
+    T q = c[0] * U[i + k * ld];
+    B200_UNROLL
+    for (int j = 1; j < kIdrsMaxS; ++j)
+      if (k + j < ns) {
+        v = v + c[j] * G[i + (k + j) * ld];
+        q = q + c[j] * U[i + (k + j) * ld];
+      }
+    V[i] = R[i] - v;
+    Q[i] = q;
+  }
+  B200_HD double *sums() const { return nullptr; }
+  B200_HD void finish(const double *) const {}
+};
+template <typename T>
+struct IdrsUfromVQ {          // U_k = Q + omega * (Pl \ V)   :201
+  static constexpr int NRED = 0;
+  const T *Q, *PV;
+  T *Uk;
+  const IdrsScal *s;
+  T omega;
+  B200_HD bool skip() const { return s->done != 0; }
+  B200_HD void load() { omega = (T)s->omega; }
+  B200_HD void elem(int64_t i, double *) const { Uk[i] = Q[i] + omega * PV[i]; }
+  B200_HD double *sums() const { return nullptr; }
+  B200_HD void finish(const double *) const {}
+};
+
 // ---- E: bi-orthogonalisation sweep :206-216.  One pass = [apply alpha_i] + [the dots the next scalar section needs].
 //   upd >= 0: G_k -= alpha G_upd ; U_k -= alpha U_upd with alpha = s->alpha (set by the previous pass)
 //   dot0, ndots: sums <P_{dot0+j}, G_k>, j < ndots, of the UPDATED G_k
@@ -308,11 +353,12 @@ struct IdrsOutcome {
   int converged, breakdown;
 };
 
-// x, b: n values; P: n x s (leading dimension ldp) drawn by the caller; diag: Jacobi Pl or NULL (Identity).
+// x, b: n values; P: n x s (leading dimension ldp) drawn by the caller; diag: Jacobi Pl or NULL; Plop: callback
+// preconditioner (y = Pl \ x) or NULL (Identity when both are NULL).
 template <typename T, typename B>
 int idrs_run(B &be, const typename B::Op *A, int64_t n, int64_t n_global, T *x, const T *b, int s_dim, const T *P,
              int64_t ldp, const T *diag, double abstol, double reltol, int64_t maxiter, int smoothing, int check_every,
-             int64_t hist_cap, double *hist_host, IdrsOutcome *out) {
+             int64_t hist_cap, double *hist_host, IdrsOutcome *out, const typename B::Op *Plop = nullptr) {
   if (reltol < 0) reltol = sqrt(eps_of<T>());                               // :53
   if (maxiter < 0) maxiter = n_global;                                      // :54
   if (!hist_host) hist_cap = 0;
@@ -323,7 +369,7 @@ int idrs_run(B &be, const typename B::Op *A, int64_t n, int64_t n_global, T *x, 
   const size_t sb = (sizeof(IdrsScal) + 255) / 256 * 256;
   const bool copy_p = ldp != ld;     // the passes index P, U and G with one leading dimension
   void *ws = nullptr;
-  int st = be.workspace(vb * (size_t)(2 * s_dim + 3 + (smoothing ? 2 : 0) + (copy_p ? s_dim : 0)) + sb + hb, &ws);
+  int st = be.workspace(vb * (size_t)(2 * s_dim + 4 + (smoothing ? 2 : 0) + (copy_p ? s_dim : 0)) + sb + hb, &ws);
   if (st) return st;
   char *p = (char *)ws;
   T *U = (T *)p; p += vb * s_dim;
@@ -331,6 +377,7 @@ int idrs_run(B &be, const typename B::Op *A, int64_t n, int64_t n_global, T *x, 
   T *R = (T *)p; p += vb;
   T *Q = (T *)p; p += vb;
   T *V = (T *)p; p += vb;
+  T *V2 = (T *)p; p += vb;                 // Pl \ V with a callback preconditioner
   T *Xs = nullptr, *Rs = nullptr;
   if (smoothing) {
     Xs = (T *)p; p += vb;
@@ -380,7 +427,11 @@ int idrs_run(B &be, const typename B::Op *A, int64_t n, int64_t n_global, T *x, 
       if (step < s_dim) {
         const int k = step;
         if (k == 0 && (st = be.pass(IdrsF<T>{Pw, ld, R, sc}, n))) return st;                         // D
-        if ((st = be.pass(IdrsNewU<T>{G, R, diag, U, ld, k, sc}, n))) return st;                      // V
+        if (Plop) {                                                                                   // V, split at ldiv! :199
+          if ((st = be.pass(IdrsVQ<T>{G, U, R, V, Q, ld, k, sc}, n))) return st;
+          if ((st = be.apply(Plop, V, V2))) return st;
+          if ((st = be.pass(IdrsUfromVQ<T>{Q, V2, U + k * ld, sc}, n))) return st;
+        } else if ((st = be.pass(IdrsNewU<T>{G, R, diag, U, ld, k, sc}, n))) return st;               // V
         if ((st = be.apply(A, U + k * ld, G + k * ld))) return st;                                    // S :202
         // E: dots and updates interleaved; the last pass yields the new column of M
         if (k == 0) {
@@ -402,13 +453,16 @@ int idrs_run(B &be, const typename B::Op *A, int64_t n, int64_t n_global, T *x, 
         step += 1;
       } else {
         const T *Vin = R;
-        if (diag) {
+        if (Plop) {
+          if ((st = be.apply(Plop, R, V))) return st;                                                 // W by callback :243-246
+          Vin = V;
+        } else if (diag) {
           if ((st = be.pass(IdrsPrecR<T>{R, diag, V, sc}, n))) return st;                             // W
           Vin = V;
         }
         if ((st = be.apply(A, Vin, Q))) return st;                                                   // :248
         if ((st = be.pass(IdrsOmega<T>{Q, R, sc}, n))) return st;                                     // O
-        if ((st = be.pass(IdrsUpdate<T>{R, x, Q, diag ? V : nullptr, Rs, -1, sc}, n))) return st;     // X'
+        if ((st = be.pass(IdrsUpdate<T>{R, x, Q, Vin == R ? nullptr : V, Rs, -1, sc}, n))) return st; // X'
         if ((st = finish_step())) return st;
         step = 0;
       }

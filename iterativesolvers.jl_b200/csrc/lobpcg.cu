@@ -1312,6 +1312,8 @@ int b200_lobpcg_solve(b200_ctx *ctx, const b200_csr *A, void *X_dev, int64_t ldx
   B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
   B200_REQUIRE(is_square(A), "this solver needs a square operator (got %lld x %lld)", (long long)A->m_global,
                (long long)A->n_global);
+  B200_REQUIRE(opts->P.kind == B200_PREC_IDENTITY || (opts->P.kind == B200_PREC_JACOBI && opts->P.diag),
+               "unsupported preconditioner P (this engine takes Identity or Jacobi)");
   B200_CUDA(cudaSetDevice(ctx->device));
   return A->dtype == B200_F64
              ? lobpcg_impl<double>(ctx, A, (double *)X_dev, ldx, opts, nullptr, res, lambda_host, resnorm_host)
@@ -1325,6 +1327,8 @@ int b200_lobpcg_solve_constrained(b200_ctx *ctx, const b200_csr *A, void *X_dev,
   B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
   B200_REQUIRE(is_square(A), "this solver needs a square operator (got %lld x %lld)", (long long)A->m_global,
                (long long)A->n_global);
+  B200_REQUIRE(opts->P.kind == B200_PREC_IDENTITY || (opts->P.kind == B200_PREC_JACOBI && opts->P.diag),
+               "unsupported preconditioner P (this engine takes Identity or Jacobi)");
   if (C) {
     B200_REQUIRE(C->ctx == ctx && C->dtype == A->dtype && C->n == A->m_local,
                  "the constraint does not match the operator (context, eltype or local rows)");

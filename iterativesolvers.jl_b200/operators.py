@@ -45,6 +45,8 @@ class JacobiPrec:
 def precond_to_c(P, A):
     if P is None:
         return Identity()._as_c(A)
+    if isinstance(P, FunctionPrec):        # B200_PREC_CALLBACK: `diag` carries the address of the b200_linop
+        return _lib.Precond(_lib.PREC_CALLBACK, 0, C.cast(C.pointer(P.op._c), C.c_void_p))
     if hasattr(P, "_as_c"):
         return P._as_c(A)
     raise TypeError(f"unsupported preconditioner {type(P)}: the device path takes Identity() or JacobiPrec "

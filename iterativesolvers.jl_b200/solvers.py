@@ -596,12 +596,13 @@ def idrs_(x, A, b, *, s=8, Pl=None, abstol=0.0, reltol=None, maxiter=None, log=F
     resnorm = np.zeros(max(cap, 1), dtype=np.float64)
     st = _Staged(A, x, b)
     rp = resnorm.ctypes.data_as(C.c_void_p) if log else None
+    plop = Pl.op if isinstance(Pl, FunctionPrec) else None      # ldiv!(Pl, V) by callback (B200_PREC_CALLBACK)
     if _is_linop(A):
-        check(_call_op(lib().b200_idrs_solve_op, (A,), A.ctx._h, C.byref(A._c), as_device_ptr(st.xd),
+        check(_call_op(lib().b200_idrs_solve_op, (A, plop), A.ctx._h, C.byref(A._c), as_device_ptr(st.xd),
                        as_device_ptr(st.bd), C.byref(opts), C.byref(res), rp, cap))
     else:
-        check(lib().b200_idrs_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
-                                    C.byref(res), rp, cap))
+        check(_call_op(lib().b200_idrs_solve, (plop,), A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd),
+                       C.byref(opts), C.byref(res), rp, cap))
     st.finish()
     if verbose:
         print("=== idrs ===\niter\tstep\tresnorm")

@@ -209,19 +209,21 @@ EXPORT int hostsim_lsmr(int is_f64, const hostsim_csr *A, const hostsim_csr *At,
 
 EXPORT int hostsim_idrs(int is_f64, const hostsim_csr *A, void *x, const void *b, int s_dim, const void *P, int64_t ldp,
                         const void *diag, double abstol, double reltol, int64_t maxiter, int smoothing, int check_every,
-                        int64_t hist_cap, double *hist, int order, int split, hostsim_out *out) {
+                        int64_t hist_cap, double *hist, int order, int split, hostsim_out *out, const hostsim_csr *Pl) {
   HostBackend be;
   be.order = order;
   be.split = split;
-  HostCsr a = mk(A, is_f64);
+  HostCsr a = mk(A, is_f64), pl;
+  if (Pl) pl = mk(Pl, is_f64);
+  const HostCsr *plp = Pl ? &pl : nullptr;
   b200::IdrsOutcome o;
   memset(&o, 0, sizeof(o));
   int st = is_f64 ? b200::idrs_run<double>(be, &a, A->m, A->n, (double *)x, (const double *)b, s_dim, (const double *)P,
                                            ldp, (const double *)diag, abstol, reltol, maxiter, smoothing, check_every,
-                                           hist_cap, hist, &o)
+                                           hist_cap, hist, &o, plp)
                   : b200::idrs_run<float>(be, &a, A->m, A->n, (float *)x, (const float *)b, s_dim, (const float *)P, ldp,
                                           (const float *)diag, abstol, reltol, maxiter, smoothing, check_every,
-                                          hist_cap, hist, &o);
+                                          hist_cap, hist, &o, plp);
   out->iters = o.iters; out->mvps = o.iters; out->mtvps = 0; out->n_hist = o.n_hist;
   out->resnorm = o.normR; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
   out->passes = be.passes; out->applies = be.applies;

@@ -139,13 +139,14 @@ def lsmr_(x, A, b, *, lam=0.0, atol=-1.0, btol=-1.0, conlim=-1.0, maxiter=-1, ch
 
 
 def idrs_(x, A, b, P, *, diag=None, abstol=0.0, reltol=-1.0, maxiter=-1, smoothing=False, check_every=0, order=0,
-          split=0):
+          split=0, Pl=None):
     """the idrs engine (csrc/idrs_core.h) on the serial backend; P: n x s (Fortran order), x updated in place."""
     dt = x.dtype
     Ac = Csr(A, dt)
     b = np.ascontiguousarray(b, dtype=dt)
     P = np.asfortranarray(P, dtype=dt)
     d = None if diag is None else np.ascontiguousarray(diag, dtype=dt)
+    Pc = Csr(Pl, dt) if Pl is not None else None        # callback preconditioner: a matrix whose product is Pl \\ x
     cap = (maxiter if maxiter >= 0 else A.shape[1]) + 1
     hist = np.zeros(cap)
     out = _Out()
@@ -154,7 +155,7 @@ def idrs_(x, A, b, P, *, diag=None, abstol=0.0, reltol=-1.0, maxiter=-1, smoothi
                             C.c_int64(P.shape[0]), C.c_void_p(d.ctypes.data if d is not None else None),
                             C.c_double(abstol), C.c_double(reltol), C.c_int64(maxiter), C.c_int(smoothing),
                             C.c_int(check_every), C.c_int64(cap), hist.ctypes.data_as(C.c_void_p), C.c_int(order),
-                            C.c_int(split), C.byref(out))
+                            C.c_int(split), C.byref(out), C.byref(Pc.c) if Pc else None)
     assert st == 0, st
     return x, _outcome(out, hist)
 

@@ -48,7 +48,9 @@ class SimRunner:
     def lsmr(self, x, A, b, **kw):
         return self.sim.lsmr_(x, A, b, order=self.order, split=self.split, **kw)
 
-    def idrs(self, x, A, b, P, **kw):
+    def idrs(self, x, A, b, P, cb_diag=None, **kw):
+        if cb_diag is not None:        # callback preconditioner: a second operator whose product is Pl \\ x
+            kw["Pl"] = sp.diags(1.0 / np.asarray(cb_diag, dtype=np.float64)).tocsr()
         return self.sim.idrs_(x, A, b, P, order=self.order, split=self.split, **kw)
 
     def cg(self, x, A, b, mode, d, **kw):
@@ -489,6 +491,27 @@ def test_python_linop_paths_with_a_fake_library(monkeypatch):
     isb.cg(op, b, Pl=Pl)
     assert calls == ["b200_cg_solve_op"] and ("ldiv", (n,)) in seen and seen[0][0] == "mul"
 
+    # idrs! with a callback preconditioner: B200_PREC_CALLBACK carries the address of the preconditioner's b200_linop
+    calls.clear()
+    seen.clear()
+
+    class FakeLibPl(FakeLib):
+        def __getattr__(self, name):
+            inner = FakeLib.__getattr__(self, name)
+
+            def f(*args):
+                for a in args:
+                    obj = getattr(a, "_obj", None)
+                    if isinstance(obj, L.IdrsOpts) and obj.Pl.kind == 2:
+                        C.cast(obj.Pl.diag, C.POINTER(L.LinOp)).contents.apply(None, 0x3000, 0x4000, None)
+                return inner(*args)
+            return f
+
+    monkeypatch.setattr(S, "lib", lambda: FakeLibPl())
+    isb.idrs(op, b, Pl=Pl, s=2, rng=np.random.default_rng(0))
+    assert calls == ["b200_idrs_solve_op"] and ("ldiv", (n,)) in seen
+    monkeypatch.setattr(S, "lib", lambda: FakeLib())
+
     def boom(y, x):
         raise ZeroDivisionError("inside the operator")
 
@@ -638,3 +661,7 @@ def test_python_svdl_wrapper_with_a_fake_library(monkeypatch):
     op = isb.B200LinearOperator((40, 25), np.float64, lambda y, x: None, adjoint_mul=lambda y, x: None, ctx=A.ctx)
     isb.svdl(op, nsv=2, v0=np.ones(25) / 5)
     assert calls[0][0] == "b200_svdl_op"
+
+
+def test_engine_idrs_callback_preconditioner(oracle, runners):
+    cases.case_idrs_callback_preconditioner(oracle, runners)

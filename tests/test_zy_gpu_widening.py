@@ -61,9 +61,12 @@ class GpuRunner:
     def lsmr(self, x, A, b, **kw):
         return self._ls(self.isb.lsmr_, None, x, A, b, kw)
 
-    def idrs(self, x, A, b, P, diag=None, **kw):
+    def idrs(self, x, A, b, P, diag=None, cb_diag=None, **kw):
         op = self._op(A, x.dtype)
         Pl = self.isb.JacobiPrec(np.asarray(diag, dtype=x.dtype)) if diag is not None else None
+        if cb_diag is not None:        # ldiv!(Pl, V) by callback
+            jac = self.isb.JacobiPrec(np.asarray(cb_diag, dtype=x.dtype))
+            Pl = self.isb.FunctionPrec(op.m_local, x.dtype, lambda y, v: jac.ldiv_(y, v))
         x, h = self.isb.idrs_(x, op, np.asarray(b, dtype=x.dtype), s=P.shape[1], P=np.asarray(P, dtype=x.dtype), Pl=Pl,
                               log=True, **kw)
         res = self.isb.idrs_.last_result

@@ -121,3 +121,14 @@ def test_callback_errors_surface_as_python_exceptions(isb):
     # the library still works afterwards
     x = isb.cg(A, np.ones(n))
     assert relerr(x, 0.5 * np.ones(n)) <= 1e-12
+
+
+def test_idrs_callback_preconditioner(isb, oracle):
+    from test_zy_gpu_widening import GpuRunner
+    cases.case_idrs_callback_preconditioner(oracle, [GpuRunner(isb)])
+    # the CSR-only engines say so instead of silently ignoring a callback preconditioner
+    A = isb.B200CSR.from_scipy((sp.eye(32) * 2.0).tocsc())
+    Pl = isb.FunctionPrec(32, np.float64, lambda y, x: None)
+    for fn in (isb.gmres, isb.bicgstabl):
+        with pytest.raises(isb.B200Error, match="unsupported preconditioner"):
+            fn(A, np.ones(32), Pl=Pl)

@@ -328,3 +328,23 @@ def case_svdl_matches_oracle(oracle, run_svdl, dtype, tol):
     r2 = run_svdl(sp.csr_matrix(A), q, nsv=k, k=l, tol=1e-5, maxiter=30, dolock=True)
     s2, L2, h2 = oracle.svdl(A, nsv=k, k=l, v0=q, tol=1e-5, maxiter=30, dolock=True, log=True)
     assert abs(r2["iters"] - h2.iters) <= 1 and np.linalg.norm(r2["sigma"] - exact) < k ** 2 * 1e-5
+
+
+def case_idrs_callback_preconditioner(oracle, runners):
+    """idrs! with ldiv!(Pl, V) by callback (src/idrs.jl:199, :246): the fused direction pass is split around the
+    callback; against the oracle with the same diagonal preconditioner.  runner.idrs(..., cb_diag=d)."""
+    rng = np.random.default_rng(11)
+    n = 200
+    A = (sp.random(n, n, 0.05, random_state=4, format="csc") + sp.diags(4 + 8 * rng.random(n))).tocsc()
+    O = oracle.CSC.from_scipy(A, base=1)
+    b, x0, d = rng.random(n), rng.random(n), A.diagonal()
+    for s in (1, 4, 8):
+        P = np.asfortranarray(rng.random((n, s)))
+        for smoothing in (False, True):
+            xo, ho = oracle.idrs_(x0.copy(), O, b, s=s, P=[P[:, j].copy() for j in range(s)], log=True,
+                                  smoothing=smoothing, Pl=oracle.JacobiPrec(d.copy()))
+            for run in runners:
+                xs, hs = run.idrs(x0.copy(), A, b, P, smoothing=smoothing, cb_diag=d)
+                assert hs.iters == ho.iters and hs.converged
+                assert np.max(np.abs(hs.hist - ho["resnorm"])) <= 1e-9 * ho["resnorm"][0]
+                assert np.linalg.norm(xs - xo) <= 1e-9 * np.linalg.norm(xo)
