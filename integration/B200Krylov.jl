@@ -438,6 +438,38 @@ update!(c::B200Constraint, Xd::B200Vector, n::Integer, k::Integer) =
 # lobpcg(A, largest, X0, nev; ...) (src/lobpcg.jl:925-962) is the same host loop as iterativesolvers.jl_b200/solvers.py:
 # solve a block, update!(constraint, converged columns), rand! the block, repeat.
 
+# ------------------------------------------------------------------------------------------- lobpcg(A, B, largest, X0)
+# The generalized problem A x = λ B x (src/lobpcg.jl:824-839 with B given; LOBPCGIterator{true} :292-316), callback
+# operators (B200LinearOperator: `mul!(y, A, x)`), a callback preconditioner, and a constraint in the B inner product
+# (Constraint(Y, B, X) :162-186) go through the general engine.  b200_csr_as_linop wraps a CSR handle as a b200_linop
+# whose `apply` is the library's own SpMV, so nothing crosses into Julia inside the iteration for CSR operands.
+function as_linop(A::B200CSR{T}) where {T}
+    r = Ref{LinOp}()
+    check(ccall((:b200_csr_as_linop, LIB), Cint, (Ptr{Cvoid}, Ref{LinOp}), A.h, r)); r[]
+end
+function B200Constraint(A::B200CSR{T}, B::B200CSR{T}, Y::Matrix{T}) where {T}           # Constraint(Y, B, X) :162-186
+    Yd = B200Vector(A.ctx, vec(Y)); r = Ref{Ptr{Cvoid}}(); b = as_linop(B)
+    check(ccall((:b200_lobpcg_constraint_create_b, LIB), Cint,
+                (Ptr{Cvoid}, Ref{LinOp}, Int64, Ptr{Cvoid}, Int64, Cint, Cint, Ref{Ptr{Cvoid}}),
+                A.ctx.h, b, size(Y, 1), Yd.p, size(Y, 1), size(Y, 2), dtype_code(T), r))
+    finalizer(c -> ccall((:b200_lobpcg_constraint_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), B200Constraint{T}(r[], A.ctx))
+end
+function lobpcg(A::B200CSR{T}, B::B200CSR{T}, largest::Bool, X0::Matrix{T}; P = nothing, C = nothing,
+                tol::Real = eps(T)^(3 / 10), maxiter::Integer = 200, log::Bool = false) where {T}
+    n, bs = size(X0)
+    Xd = B200Vector(A.ctx, vec(copy(X0)))
+    λ = Vector{Float64}(undef, bs); rn = Vector{Float64}(undef, bs); res = LobpcgResult()
+    o = LobpcgOpts(tol, maxiter, largest, bs, P === nothing ? prec(Identity()) : prec(P), 0, 0)
+    con = C === nothing ? C_NULL : B200Constraint(A, B, C).h
+    a = as_linop(A); b = as_linop(B)
+    status = ccall((:b200_lobpcg_solve_op, LIB), Cint,
+                   (Ptr{Cvoid}, Ref{LinOp}, Ref{LinOp}, Ptr{Cvoid}, Int64, Ref{LobpcgOpts}, Ptr{Cvoid}, Ref{LobpcgResult},
+                    Ptr{Float64}, Ptr{Float64}), A.ctx.h, a, b, Xd.p, n, o, con, res, λ, rn)
+    status == -5 && throw(PosDefException(0))                 # cholesky! in CholQR :380 / in the Rayleigh-Ritz step :455
+    check(status)
+    LOBPCGResults(T.(λ), reshape(Array(Xd), n, bs), T(tol), T.(rn), Int(res.iterations), Int(maxiter), res.converged != 0, nothing)
+end
+
 # ------------------------------------------------------------------------------------------- svdl
 struct SvdlOpts
     nsv::Int32; k::Int32; j::Int32; method::Int32; maxiter::Int64; tol::Float64; reltol::Float64

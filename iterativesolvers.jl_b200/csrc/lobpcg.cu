@@ -1332,6 +1332,7 @@ int b200_lobpcg_solve_constrained(b200_ctx *ctx, const b200_csr *A, void *X_dev,
   if (C) {
     B200_REQUIRE(C->ctx == ctx && C->dtype == A->dtype && C->n == A->m_local,
                  "the constraint does not match the operator (context, eltype or local rows)");
+    B200_REQUIRE(!C->BY, "a generalized-problem constraint needs b200_lobpcg_solve_op");
   }
   B200_CUDA(cudaSetDevice(ctx->device));
   return A->dtype == B200_F64

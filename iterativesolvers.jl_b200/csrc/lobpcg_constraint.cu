@@ -80,6 +80,7 @@ int b200_lobpcg_constraint_create(b200_ctx *ctx, int64_t n_local, const void *Y_
 int b200_lobpcg_constraint_append(b200_ctx *ctx, b200_lobpcg_constraint *c, const void *X_dev, int64_t ldx, int k) {
   B200_REQUIRE(ctx && c && c->ctx == ctx && k >= 0 && (k == 0 || (X_dev && ldx >= c->n)), "bad arguments");
   B200_REQUIRE(c->nc + k <= c->cap, "constraint capacity %d exceeded (%d + %d columns)", c->cap, c->nc, k);
+  B200_REQUIRE(!c->BY, "append is available for the standard problem only (the generalized update! needs B*X)");
   if (k == 0) return B200_OK;
   B200_CUDA(cudaSetDevice(ctx->device));
   const size_t vs = dtype_size(c->dtype);
@@ -100,6 +101,7 @@ int b200_lobpcg_constraint_append(b200_ctx *ctx, b200_lobpcg_constraint *c, cons
 
 int b200_lobpcg_constraint_apply(b200_ctx *ctx, const b200_lobpcg_constraint *c, void *X_dev, int64_t ldx, int bs) {
   B200_REQUIRE(ctx && c && X_dev && ldx >= c->n && bs >= 0, "bad arguments");
+  B200_REQUIRE(!c->BY, "b200_lobpcg_constraint_apply: standard-problem constraints only");
   B200_CUDA(cudaSetDevice(ctx->device));
   const size_t vs = dtype_size(c->dtype);
   for (int j0 = 0; j0 < bs; j0 += kConBlock) {         // blocks wider than 16 columns: 16 at a time
@@ -123,6 +125,7 @@ int b200_lobpcg_constraint_destroy(b200_lobpcg_constraint *c) {
     cudaStreamSynchronize(c->ctx->stream);
   }
   cudaFree(c->Y);
+  cudaFree(c->BY);
   cudaFree(c->g_dev);
   delete c;
   return B200_OK;

@@ -12,6 +12,7 @@ struct b200_lobpcg_constraint {
   int64_t ld = 0;           // leading dimension of Y (elements)
   int nc = 0, cap = 0;      // columns in use / allocated
   void *Y = nullptr;        // device, column-major n x cap (own copy: the reference keeps C alive the same way)
+  void *BY = nullptr;       // generalized problem: B*Y (b200_lobpcg_constraint_create_b); nullptr: BY aliases Y (:163-164)
   double *g_dev = nullptr;  // device scratch: cap x 16 doubles
   std::vector<double> U;    // host: upper Cholesky factor of Y'Y, nc x nc column-major
   std::vector<double> g_host;

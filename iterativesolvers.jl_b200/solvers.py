@@ -636,23 +636,42 @@ class LOBPCGResults:
     trace: list
 
 
+def _linop_struct(op):
+    """(b200_linop struct, python callback operator or None) of a B200CSR (applied by the library itself, no Python in
+    the loop: b200_csr_as_linop) or of a B200LinearOperator."""
+    if isinstance(op, B200LinearOperator):
+        return op._c, op
+    s = _lib.LinOp()
+    check(lib().b200_csr_as_linop(op._h, C.byref(s)))
+    return s, None
+
+
 class LobpcgConstraint:
     """Constraint(Y, nothing, X) -- reference src/lobpcg.jl:144-224 (standard problem): a basis Y (n x nc, host array
     or DeviceArray; copied) the Ritz vectors are kept orthogonal to.  `capacity` columns are reserved for `append`
     (update!, :188-206)."""
 
-    def __init__(self, ctx, n, dtype, Y=None, capacity=0):
+    def __init__(self, ctx, n, dtype, Y=None, capacity=0, B=None):
         self.ctx, self.n, self.dtype = ctx, int(n), np.dtype(dtype)
         self._h = C.c_void_p()
+        self.generalized = B is not None
         nc = 0 if Y is None else int(Y.shape[1])
         Yd = None
         if nc:
             Yd = Y if is_device(Y) else DeviceArray.from_numpy(ctx, np.asfortranarray(Y, dtype=self.dtype))
             if Yd.shape[0] != self.n:
                 raise ValueError("the constraint must have as many rows as the operator")
-        check(lib().b200_lobpcg_constraint_create(ctx._h, self.n, as_device_ptr(Yd) if nc else None, self.n, nc,
-                                                  int(max(capacity, nc)), _lib.F64 if self.dtype == np.float64 else _lib.F32,
-                                                  C.byref(self._h)))
+        code = _lib.F64 if self.dtype == np.float64 else _lib.F32
+        if B is not None:                                      # Constraint(Y, B, X) with BY = B*Y  src/lobpcg.jl:161-186
+            if not nc:
+                raise ValueError("a generalized-problem constraint needs at least one column")
+            bs, bop = _linop_struct(B)
+            self._keep = (bs, B)
+            check(_call_op(lib().b200_lobpcg_constraint_create_b, (bop,), ctx._h, C.byref(bs), self.n, as_device_ptr(Yd),
+                           self.n, nc, code, C.byref(self._h)))
+        else:
+            check(lib().b200_lobpcg_constraint_create(ctx._h, self.n, as_device_ptr(Yd) if nc else None, self.n, nc,
+                                                      int(max(capacity, nc)), code, C.byref(self._h)))
 
     @property
     def ncols(self):
@@ -683,7 +702,7 @@ class LobpcgConstraint:
             pass
 
 
-def _lobpcg_block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, fixed):
+def _lobpcg_block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, fixed, B=None):
     """lobpcg!(iterator; ...) -- reference src/lobpcg.jl:865-893 on the device block Xd (overwritten)."""
     n, bs = Xd.shape
     if not not_zeros and not fixed:                            # :869-876 (the constraint itself is applied by the engine)
@@ -698,7 +717,16 @@ def _lobpcg_block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, f
     res = _lib.LobpcgResult()
     lam = np.zeros(bs, dtype=np.float64)
     rn = np.zeros(bs, dtype=np.float64)
-    if constraint is None:
+    if B is not None or _is_linop(A) or isinstance(P, FunctionPrec):
+        # the general engine (csrc/lobpcg_general_core.h): generalized problem, callback operators / preconditioner
+        a_s, a_op = _linop_struct(A)
+        b_s, b_op = _linop_struct(B) if B is not None else (None, None)
+        p_op = P.op if isinstance(P, FunctionPrec) else None
+        status = _call_op(lib().b200_lobpcg_solve_op, (a_op, b_op, p_op), A.ctx._h, C.byref(a_s),
+                          C.byref(b_s) if b_s is not None else None, as_device_ptr(Xd), n, C.byref(opts),
+                          constraint._h if constraint is not None else None, C.byref(res),
+                          lam.ctypes.data_as(C.c_void_p), rn.ctypes.data_as(C.c_void_p))
+    elif constraint is None:
         status = lib().b200_lobpcg_solve(A.ctx._h, A._h, as_device_ptr(Xd), n, C.byref(opts), C.byref(res),
                                          lam.ctypes.data_as(C.c_void_p), rn.ctypes.data_as(C.c_void_p))
     else:
@@ -711,18 +739,25 @@ def _lobpcg_block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, f
     return lam, rn, res
 
 
-def lobpcg(A, largest: bool, X0, nev=None, *, P=None, C_=None, tol=None, maxiter=200, log=False, not_zeros=False,
-           rng=None, _fixed_iterations=False, **kw):
-    """lobpcg(A, largest, X0; P, C, tol, maxiter, not_zeros) -> LOBPCGResults        reference src/lobpcg.jl:824-839
-    lobpcg(A, largest, nev::Int; ...)   (X0 = rand(n, nev), not_zeros = true)        :787-792
+def lobpcg(A, largest: bool, X0, nev=None, *, B=None, P=None, C_=None, tol=None, maxiter=200, log=False,
+           not_zeros=False, rng=None, _fixed_iterations=False, **kw):
+    """lobpcg(A, [B,] largest, X0; P, C, tol, maxiter, not_zeros) -> LOBPCGResults   reference src/lobpcg.jl:824-839
+    lobpcg(A, [B,] largest, nev::Int; ...)   (X0 = rand(n, nev), not_zeros = true)   :787-792
     lobpcg(A, largest, X0, nev; ...)    (batches of size(X0, 2) with deflation)       :925-962
-    Standard problem (B = I).  The constraint is the keyword `C` (spelled `C=` here; `C_` is accepted as well):
-    an n x nc host array / DeviceArray, or a LobpcgConstraint.  X0: n x blocksize, host (numpy, any order) or
-    DeviceArray (column-major)."""
+    `B=` (a B200CSR or B200LinearOperator) selects the generalized problem A x = λ B x; A may be a
+    B200LinearOperator and P a FunctionPrec (callbacks): those three go through the general engine, the standard problem
+    on a B200CSR with Identity / JacobiPrec through the tuned one.  The constraint is the keyword `C` (spelled `C=`
+    here; `C_` is accepted as well): an n x nc host array / DeviceArray, or a LobpcgConstraint.  X0: n x blocksize,
+    host (numpy, any order) or DeviceArray (column-major)."""
     Cc = kw.pop("C", C_)
     if kw:
         raise TypeError(f"unexpected keyword arguments {sorted(kw)}")
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
+    if B is not None:
+        _check_operator(B, linop_ok=True)
+        if nev is not None:
+            raise B200Error("the nev > blocksize driver is implemented for the standard problem only "
+                            "(the generalized update! needs B*X of every converged batch)")
     if tol is None:
         tol = _eps(A.dtype) ** 0.3                             # default_tolerance  src/lobpcg.jl:751
     if isinstance(X0, (int, np.integer)):                      # lobpcg(A, largest, nev) :790-792
@@ -740,8 +775,8 @@ def lobpcg(A, largest: bool, X0, nev=None, *, P=None, C_=None, tol=None, maxiter
         # src/lobpcg.jl:834: throw("... not stable to use when the matrix size is less than 3 times the block size ...")
         raise B200Error("The order of the matrix must be at least 3 times the block size")
     if nev is None:
-        con = Cc if isinstance(Cc, LobpcgConstraint) or Cc is None else LobpcgConstraint(A.ctx, n, A.dtype, Cc)
-        lam, rn, res = _lobpcg_block(A, largest, Xd, P, con, tol, maxiter, not_zeros, rng, _fixed_iterations)
+        con = Cc if isinstance(Cc, LobpcgConstraint) or Cc is None else LobpcgConstraint(A.ctx, n, A.dtype, Cc, B=B)
+        lam, rn, res = _lobpcg_block(A, largest, Xd, P, con, tol, maxiter, not_zeros, rng, _fixed_iterations, B=B)
         X = Xd.numpy() if host else Xd
         return LOBPCGResults(lam.astype(A.dtype), X, float(tol), rn.astype(A.dtype), int(res.iterations), int(maxiter),
                              bool(res.converged), [])

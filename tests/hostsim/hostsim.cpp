@@ -24,6 +24,7 @@
 #include "../../iterativesolvers.jl_b200/csrc/cg_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/lobpcg_constraint_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/svdl_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/lobpcg_general_core.h"
 
 #define EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -307,4 +308,49 @@ EXPORT void hostsim_dense_svd(int n, const double *A, double *U, double *S, doub
   memcpy(U, u.data(), sizeof(double) * (size_t)n * n);
   memcpy(S, s.data(), sizeof(double) * n);
   memcpy(V, v.data(), sizeof(double) * (size_t)n * n);
+}
+
+// general LOBPCG: A, optional B, optional callback preconditioner (as a matrix whose product is M \ x) or Jacobi diagonal,
+// optional constraint Y (BY and the factor of Y'BY are formed here, as Constraint(Y, B, X) does, src/lobpcg.jl:161-186)
+EXPORT int hostsim_lobpcg_general(int is_f64, const hostsim_csr *A, const hostsim_csr *Bm, const hostsim_csr *Pm,
+                                  const void *jac, const void *Y, int nc, void *X, int sizeX, int largest, double tol,
+                                  int64_t maxiter, int fixed, double *lambda, double *resnorm, int order, int split,
+                                  int64_t *iterations, int *converged, int *status) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64), b, pm;
+  if (Bm) b = mk(Bm, is_f64);
+  if (Pm) pm = mk(Pm, is_f64);
+  const int64_t n = A->m;
+  b200::LobpcgGenOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st;
+  auto body = [&](auto tag) -> int {
+    typedef decltype(tag) T;
+    std::vector<T> BY;
+    std::vector<double> U((size_t)nc * nc), g_dev((size_t)(nc > 0 ? nc : 1) * b200::kConBlock), g_host(g_dev.size());
+    const T *Yp = (const T *)Y, *BYp = Yp;
+    if (nc > 0) {
+      if (Bm) {                                   // BY = B * Y :166-167
+        BY.resize((size_t)n * nc);
+        for (int j = 0; j < nc; ++j) be.apply(&b, Yp + (size_t)j * n, BY.data() + (size_t)j * n);
+        BYp = BY.data();
+      }
+      // gram = Y' BY ; cholesky :178-182
+      for (int c0 = 0; c0 < nc; c0 += b200::kConBlock) {
+        const int bs = nc - c0 < b200::kConBlock ? nc - c0 : b200::kConBlock;
+        int s2 = b200::constraint_gram<T>(be, Yp, n, nc, BYp + (size_t)c0 * n, 1, n, bs, n, g_dev.data(), g_host.data());
+        if (s2) return s2;
+        for (int k = 0; k < nc; ++k)
+          for (int j = 0; j < bs; ++j) U[k + (size_t)(c0 + j) * nc] = g_host[(size_t)k * b200::kConBlock + j];
+      }
+      if (b200::con_cholesky_upper(U.data(), nc)) return -5;
+    }
+    return b200::lobpcg_general_run<T>(be, &a, Bm ? &b : nullptr, Pm ? &pm : nullptr, (const T *)jac, Yp, BYp, n, nc,
+                                       U.data(), (T *)X, n, sizeX, n, largest, tol, maxiter, fixed, lambda, resnorm, &o);
+  };
+  st = is_f64 ? body(double()) : body(float());
+  *iterations = o.iterations; *converged = o.converged; *status = o.status;
+  return st;
 }

@@ -264,3 +264,28 @@ def dense_svd(A):
     lib().hostsim_dense_svd(C.c_int(n), C.c_void_p(A.ctypes.data), C.c_void_p(U.ctypes.data), C.c_void_p(S.ctypes.data),
                             C.c_void_p(V.ctypes.data))
     return U, S, V
+
+
+def lobpcg_general(A, largest, X0, *, B=None, Pm=None, jac=None, C_=None, tol=-1.0, maxiter=200, fixed=False, order=0,
+                   split=0):
+    """the general LOBPCG engine (csrc/lobpcg_general_core.h) on the serial backend.  B: second operator (generalized
+    problem), Pm: a matrix whose product applies the preconditioner (M \\ x), jac: Jacobi diagonal, C_: constraint basis.
+    Returns dict(lam, X, resnorm, iterations, converged, status)."""
+    dt = np.dtype(X0.dtype)
+    Ac = Csr(A, dt)
+    Bc = Csr(B, dt) if B is not None else None
+    Pc = Csr(Pm, dt) if Pm is not None else None
+    X = np.array(X0, dtype=dt, order="F", copy=True)
+    n, sizeX = X.shape
+    d = None if jac is None else np.ascontiguousarray(jac, dtype=dt)
+    Y = None if C_ is None else np.asfortranarray(C_, dtype=dt)
+    lam, rn = np.zeros(sizeX), np.zeros(sizeX)
+    it, conv, status = C.c_int64(), C.c_int(), C.c_int()
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+    st = lib().hostsim_lobpcg_general(C.c_int(dt == np.float64), C.byref(Ac.c), C.byref(Bc.c) if Bc else None,
+                                      C.byref(Pc.c) if Pc else None, vp(d), vp(Y), C.c_int(0 if Y is None else Y.shape[1]),
+                                      vp(X), C.c_int(sizeX), C.c_int(bool(largest)), C.c_double(tol), C.c_int64(maxiter),
+                                      C.c_int(fixed), vp(lam), vp(rn), C.c_int(order), C.c_int(split), C.byref(it),
+                                      C.byref(conv), C.byref(status))
+    assert st == 0, st
+    return dict(lam=lam, X=X, resnorm=rn, iterations=it.value, converged=bool(conv.value), status=status.value)

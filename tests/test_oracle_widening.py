@@ -665,3 +665,100 @@ def test_python_svdl_wrapper_with_a_fake_library(monkeypatch):
 
 def test_engine_idrs_callback_preconditioner(oracle, runners):
     cases.case_idrs_callback_preconditioner(oracle, runners)
+
+
+# ------------------------------------------------------------------------------------------ general LOBPCG engine
+@pytest.mark.parametrize("dtype,tol,ltol", [(np.float64, 1e-7, 1e-9), (np.float32, 5e-3, 2e-4)])
+def test_engine_lobpcg_general_matches_oracle(oracle, sim, dtype, tol, ltol):
+    for order, split in ((0, 0), (1, 1)):
+        def run(A, largest, X0, B=None, jac=None, cb_diag=None, C=None, tol=None, maxiter=200):
+            return sim.lobpcg_general(sp.csr_matrix(A), largest, X0, B=None if B is None else sp.csr_matrix(B), jac=jac,
+                                      Pm=None if cb_diag is None else sp.diags(1.0 / np.asarray(cb_diag)).tocsr(),
+                                      C_=C, tol=tol, maxiter=maxiter, order=order, split=split)
+        cases.case_lobpcg_general(oracle, run, dtype, tol, ltol)
+
+
+def test_oracle_lobpcg_generalized_reference_properties(oracle):
+    """test/lobpcg.jl:52-70 (generalized, single eigenvalue) and :229-246 (generalized + constraint) on the oracle."""
+    rng = np.random.default_rng(321)
+    n = 10
+    for dtype in (np.float32, np.float64):
+        tol = float(np.finfo(dtype).eps) ** 0.3
+        for largest in (True, False):
+            A = rng.random((n, n)).astype(dtype)
+            A = A.T + A + 20 * np.eye(n, dtype=dtype)
+            B = rng.random((n, n)).astype(dtype)
+            B = B.T + B + 20 * np.eye(n, dtype=dtype)
+            r = oracle.lobpcg(A, largest, rng.random((n, 1)).astype(dtype), B=B, tol=tol, maxiter=10 ** 6, not_zeros=True)
+            assert np.linalg.norm(A @ r.X - B @ r.X * r.lam) <= tol
+            assert abs((r.X.T @ B @ r.X)[0, 0] - 1) <= 5e-3 if dtype == np.float32 else 1e-6
+            r2 = oracle.lobpcg(A, largest, rng.random((n, 1)).astype(dtype), B=B, C=r.X.copy(), tol=tol, maxiter=10 ** 6,
+                               not_zeros=True)
+            assert np.linalg.norm(A @ r2.X - B @ r2.X * r2.lam) <= tol
+            assert abs((r.X.T @ B @ r2.X)[0, 0]) <= 2 * n * tol
+
+
+def test_python_general_lobpcg_path_with_a_fake_library(monkeypatch):
+    """isb.lobpcg(A, largest, X0, B=...) / callback operator / FunctionPrec go to b200_lobpcg_solve_op with b200_linop
+    structs made by b200_csr_as_linop (CSR operands: no Python in the loop) or carrying the Python thunk; a generalized
+    constraint is built with b200_lobpcg_constraint_create_b; the generalized nev driver is refused."""
+    import ctypes as C
+    from importlib import import_module
+    import iterativesolvers_jl_b200 as isb
+    S = import_module("iterativesolvers_jl_b200.solvers")
+    calls = []
+
+    class FakeArr:
+        def __init__(self, a):
+            self.a = np.array(a, order="F")
+            self.shape, self.dtype = self.a.shape, self.a.dtype
+            self._p = C.c_void_p(0x9000)
+
+        @classmethod
+        def from_numpy(cls, ctx, a):
+            return cls(a)
+
+        def numpy(self):
+            return self.a.copy(order="F")
+
+    class FakeLib:
+        def __getattr__(self, name):
+            def f(*args):
+                calls.append((name, args))
+                if name in ("b200_lobpcg_constraint_create", "b200_lobpcg_constraint_create_b"):
+                    args[-1]._obj.value = 0x77
+                return 0
+            return f
+
+    monkeypatch.setattr(S, "lib", lambda: FakeLib())
+    monkeypatch.setattr(S, "DeviceArray", FakeArr)
+    monkeypatch.setattr(S, "is_device", lambda v: isinstance(v, FakeArr))
+    monkeypatch.setattr(S, "as_device_ptr", lambda v: v._p)
+
+    def mk():
+        A = S.B200CSR.__new__(S.B200CSR)
+        A.ctx, A._h, A.m_local, A.n_global, A.m_global, A.dtype = SimpleNamespace(_h=None, world=1), C.c_void_p(7), 30, 30, 30, np.dtype(np.float64)
+        A.close = lambda: None
+        return A
+
+    A, B = mk(), mk()
+    rng = np.random.default_rng(0)
+    isb.lobpcg(A, False, rng.random((30, 2)), B=B, not_zeros=True)
+    names = [c[0] for c in calls]
+    assert names == ["b200_csr_as_linop", "b200_csr_as_linop", "b200_lobpcg_solve_op"], names
+    solve_args = calls[-1][1]
+    assert isinstance(solve_args[1]._obj, S._lib.LinOp) and isinstance(solve_args[2]._obj, S._lib.LinOp)
+    calls.clear()
+    isb.lobpcg(A, True, rng.random((30, 2)), B=B, C=rng.random((30, 1)), not_zeros=True)
+    names = [c[0] for c in calls if c[0] != "b200_lobpcg_constraint_destroy"]
+    assert names == ["b200_csr_as_linop", "b200_lobpcg_constraint_create_b", "b200_csr_as_linop", "b200_csr_as_linop",
+                     "b200_lobpcg_solve_op"], names
+    calls.clear()
+    Pl = isb.FunctionPrec(30, np.float64, lambda y, x: None, ctx=A.ctx)
+    isb.lobpcg(A, False, rng.random((30, 2)), P=Pl, not_zeros=True)                # standard problem, callback P
+    assert [c[0] for c in calls] == ["b200_csr_as_linop", "b200_lobpcg_solve_op"]
+    opts = [a._obj for a in calls[-1][1] if isinstance(getattr(a, "_obj", None), S._lib.LobpcgOpts)][0]
+    assert opts.P.kind == 2 and opts.P.diag == C.addressof(Pl.op._c)
+    assert calls[-1][1][2] is None                                                  # B = NULL
+    with pytest.raises(isb.B200Error):
+        isb.lobpcg(A, False, rng.random((30, 2)), 4, B=B)                           # generalized nev driver

@@ -103,3 +103,38 @@ def test_nev_driver_reference_properties(isb, oracle, block_size, nev):
     if block_size == 1:
         r3 = isb.lobpcg(A, False, 3, tol=tol, maxiter=2000, rng=rng)                           # lobpcg(A, largest, nev::Int)
         assert np.allclose(np.sort(r3.lam), d[:3], atol=1e-5)
+
+
+# ------------------------------------------------------------------ the general engine: B != I, callbacks
+@pytest.mark.parametrize("dtype,tol,ltol", [(np.float64, 1e-7, 1e-9), (np.float32, 5e-3, 2e-4)])
+def test_general_lobpcg_matches_oracle(isb, oracle, dtype, tol, ltol):
+    """generalized problem, callback operator / preconditioner, constraint in the B inner product through
+    b200_lobpcg_solve_op -- the case the serial backend runs (tests/widening_cases.py)."""
+    def run(A, largest, X0, B=None, jac=None, cb_diag=None, C=None, tol=None, maxiter=200):
+        Ad = isb.B200CSR.from_scipy(sp.csc_matrix(A).astype(X0.dtype))
+        op = Ad if B is not None else isb.B200LinearOperator.from_csr(Ad)       # standard problem: force the general engine
+        Bd = None if B is None else isb.B200CSR.from_scipy(sp.csc_matrix(B).astype(X0.dtype))
+        P = None
+        if jac is not None:
+            P = isb.JacobiPrec(np.asarray(jac, dtype=X0.dtype))
+        if cb_diag is not None:
+            j = isb.JacobiPrec(np.asarray(cb_diag, dtype=X0.dtype))
+            P = isb.FunctionPrec(Ad.m_local, X0.dtype, lambda y, v: j.ldiv_(y, v))
+        try:
+            r = isb.lobpcg(op, largest, X0, B=Bd, P=P, C=C, tol=tol, maxiter=maxiter, not_zeros=True)
+        except np.linalg.LinAlgError:
+            return dict(status=1, converged=False)
+        return dict(lam=np.asarray(r.lam, dtype=np.float64), X=r.X, resnorm=r.residual_norms, iterations=r.iterations,
+                    converged=r.converged, status=0)
+    cases.case_lobpcg_general(oracle, run, dtype, tol, ltol)
+
+
+def test_general_engine_equals_tuned_engine_on_the_standard_problem(isb, oracle):
+    rng = np.random.default_rng(SEED)
+    O = oracle.laplace_matrix(np.float64, 8, 3, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    X0 = rng.random((O.n, 4))
+    r1 = isb.lobpcg(A, False, X0, tol=1e-6, maxiter=300)
+    r2 = isb.lobpcg(isb.B200LinearOperator.from_csr(A), False, X0, tol=1e-6, maxiter=300)
+    assert r1.converged and r2.converged and abs(r1.iterations - r2.iterations) <= 2
+    assert np.abs(np.sort(r1.lam) - np.sort(r2.lam)).max() <= 1e-8

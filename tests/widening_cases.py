@@ -348,3 +348,54 @@ def case_idrs_callback_preconditioner(oracle, runners):
                 assert hs.iters == ho.iters and hs.converged
                 assert np.max(np.abs(hs.hist - ho["resnorm"])) <= 1e-9 * ho["resnorm"][0]
                 assert np.linalg.norm(xs - xo) <= 1e-9 * np.linalg.norm(xo)
+
+
+def case_lobpcg_general(oracle, run, dtype, tol, ltol):
+    """the general LOBPCG engine (csrc/lobpcg_general_core.h) against the oracle's lobpcg: standard and generalized
+    problem, block sizes 1 and 3, Jacobi and callback preconditioner, constraint in the (B-)inner product -- identical
+    iteration counts in fp64 (the two follow the same recurrence to rounding), Ritz values and residual norms.
+    run(A, largest, X0, B=None, jac=None, cb_diag=None, C=None, tol, maxiter) -> dict(lam, X, resnorm, iterations,
+    converged, status) with status != 0 for a PosDefException."""
+    rng = np.random.default_rng(5)
+    n = 60
+    M, d = separated_spectrum_matrix(n)
+    Bm = rng.standard_normal((n, n))
+    Bm = Bm @ Bm.T / n + 2 * np.eye(n)                       # symmetric positive definite
+    dg = np.abs(M.diagonal()) + 1.0
+    Md = M.astype(dtype)
+    exact64 = dtype == np.float64
+    for gen in (False, True):
+        Bd = Bm.astype(dtype) if gen else None
+        Bq = Bm if gen else np.eye(n)
+        for largest in (False, True):
+            for bs in (1, 3):
+                X0 = rng.random((n, bs)).astype(dtype)
+                r = run(Md, largest, X0, B=Bd, tol=tol, maxiter=300)
+                try:
+                    ro = oracle.lobpcg(Md, largest, X0, B=Bd, tol=tol, maxiter=300, not_zeros=True)
+                except np.linalg.LinAlgError:
+                    # PosDefException in the reference's algorithm (fp32, clustered Ritz values): the engine must break
+                    # down the same way (status != 0), not return something
+                    assert not exact64 and r["status"] != 0, (gen, largest, bs)
+                    continue
+                assert r["status"] == 0 and ro.converged and r["converged"]
+                assert (r["iterations"] == ro.iterations) if exact64 else abs(r["iterations"] - ro.iterations) <= 5
+                assert np.abs(np.sort(ro.lam) - np.sort(r["lam"])).max() <= ltol * np.abs(ro.lam).max()
+                X = np.asarray(r["X"], dtype=np.float64)
+                assert np.max(np.linalg.norm(M @ X - Bq @ X * r["lam"][None, :], axis=0)) <= 4 * tol
+                assert np.abs(X.T @ Bq @ X - np.eye(bs)).max() <= 2 * n * tol          # test/lobpcg.jl:62-69
+        if not exact64:
+            continue           # fp32 + preconditioner / constraint: the reference itself runs into PosDefException here
+        X0 = rng.random((n, 3)).astype(dtype)
+        ro = oracle.lobpcg(Md, False, X0, B=Bd, P=oracle.JacobiPrec(dg.astype(dtype)), tol=tol, maxiter=300, not_zeros=True)
+        for kw in (dict(jac=dg), dict(cb_diag=dg)):
+            r = run(Md, False, X0, B=Bd, tol=tol, maxiter=300, **kw)
+            assert r["converged"] and r["iterations"] == ro.iterations
+            assert np.abs(np.sort(ro.lam) - np.sort(r["lam"])).max() <= ltol * np.abs(ro.lam).max()
+        rc = oracle.lobpcg(Md, False, rng.random((n, 2)).astype(dtype), B=Bd, tol=tol, maxiter=300, not_zeros=True)
+        X1 = rng.random((n, 3)).astype(dtype)
+        ro = oracle.lobpcg(Md, False, X1, B=Bd, C=rc.X.copy(), tol=tol, maxiter=300, not_zeros=True)
+        r = run(Md, False, X1, B=Bd, C=rc.X.copy(), tol=tol, maxiter=300)
+        assert r["converged"] and r["iterations"] == ro.iterations
+        assert np.abs(np.sort(ro.lam) - np.sort(r["lam"])).max() <= ltol * np.abs(ro.lam).max()
+        assert np.abs(rc.X.astype(np.float64).T @ Bq @ np.asarray(r["X"], dtype=np.float64)).max() <= 2 * n * tol
