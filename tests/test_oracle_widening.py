@@ -762,3 +762,66 @@ def test_python_general_lobpcg_path_with_a_fake_library(monkeypatch):
     assert calls[-1][1][2] is None                                                  # B = NULL
     with pytest.raises(isb.B200Error):
         isb.lobpcg(A, False, rng.random((30, 2)), 4, B=B)                           # generalized nev driver
+
+
+@pytest.mark.parametrize("block_size,nev", [(1, 3), (2, 5), (3, 6), (4, 8)])
+def test_python_nev_driver_over_the_serial_backend(monkeypatch, sim, block_size, nev):
+    """the package's own lobpcg(A, largest, X0, nev) host loop (src/lobpcg.jl:925-962: batches, update!(constraint),
+    cutoff branch, rand! refills) with its device pieces replaced by numpy stand-ins that run the LOBPCG engine on the
+    serial backend: the case tests/test_zz_gpu_lobpcg_constraint.py runs on the GPU, rehearsed on the CPU."""
+    from importlib import import_module
+    import iterativesolvers_jl_b200 as isb
+    S = import_module("iterativesolvers_jl_b200.solvers")
+
+    class Arr:                                           # DeviceArray stand-in
+        def __init__(self, a):
+            self.a = np.array(a, order="F")
+
+        shape = property(lambda self: self.a.shape)
+        dtype = property(lambda self: self.a.dtype)
+
+        @classmethod
+        def from_numpy(cls, ctx, a):
+            return cls(a)
+
+        def numpy(self):
+            return self.a.copy(order="F")
+
+        def upload(self, a):
+            assert a.shape == self.a.shape
+            self.a[...] = a
+
+    class Con:                                           # LobpcgConstraint stand-in: the basis, grown by append
+        def __init__(self, ctx, n, dtype, Y=None, capacity=0, B=None):
+            assert B is None
+            self.Y = np.zeros((n, 0), dtype=dtype) if Y is None else np.array(Y.a if isinstance(Y, Arr) else Y, dtype=dtype)
+            self.capacity = max(capacity, self.Y.shape[1])
+
+        def append(self, Xd, k=None):
+            k = Xd.shape[1] if k is None else k
+            self.Y = np.hstack([self.Y, Xd.a[:, :k]])
+            assert self.Y.shape[1] <= self.capacity
+
+        def close(self):
+            pass
+
+    def block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, fixed, B=None):
+        assert P is None and B is None and not fixed
+        Y = None if constraint is None or constraint.Y.shape[1] == 0 else constraint.Y
+        r = sim.lobpcg_general(A.M, largest, Xd.a, C_=Y, tol=tol, maxiter=maxiter)
+        if r["status"]:
+            raise np.linalg.LinAlgError("PosDefException")
+        Xd.a[...] = r["X"]
+        return r["lam"], r["resnorm"], SimpleNamespace(iterations=r["iterations"], converged=r["converged"])
+
+    monkeypatch.setattr(S, "DeviceArray", Arr)
+    monkeypatch.setattr(S, "LobpcgConstraint", Con)
+    monkeypatch.setattr(S, "_lobpcg_block", block)
+    monkeypatch.setattr(S, "is_device", lambda v: isinstance(v, Arr))
+    monkeypatch.setattr(S, "_check_operator", lambda *a, **k: None)
+
+    def make_A(M):
+        n = M.shape[0]
+        return SimpleNamespace(M=sp.csr_matrix(M), ctx=None, dtype=np.dtype(np.float64), m_local=n, n_global=n, m_global=n)
+
+    cases.case_nev_driver(isb.lobpcg, make_A, block_size, nev)

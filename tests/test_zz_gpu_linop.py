@@ -102,7 +102,7 @@ def test_shifted_operator_by_callback_all_solvers(isb, oracle):
         x_as, h_as = fn(Bs, b, log=True, **kw2)
         assert calls["mul"] > before
         assert h_cb.isconverged and h_as.isconverged and abs(h_cb.iters - h_as.iters) <= 1, name
-        assert relerr(x_cb, x_as) <= 1e-8, name
+        assert relerr(x_cb, x_as) <= (1e-8 if h_cb.iters == h_as.iters else 1e-5), name
         assert relerr((M + sigma * sp.eye(n)) @ x_cb, b) <= 1e-6, name
 
 

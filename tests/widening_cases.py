@@ -15,6 +15,8 @@ import math
 import numpy as np
 import scipy.sparse as sp
 
+SEED = 1234321
+
 
 def sol_matrix(m, n):
     """reference test/lsqr.jl:25-29 / test/lsmr.jl:59-63."""
@@ -350,13 +352,21 @@ def case_idrs_callback_preconditioner(oracle, runners):
                 assert np.linalg.norm(xs - xo) <= 1e-9 * np.linalg.norm(xo)
 
 
-def case_lobpcg_general(oracle, run, dtype, tol, ltol):
+def case_lobpcg_general(oracle, run, dtype, tol, ltol, same_arithmetic=True):
     """the general LOBPCG engine (csrc/lobpcg_general_core.h) against the oracle's lobpcg: standard and generalized
     problem, block sizes 1 and 3, Jacobi and callback preconditioner, constraint in the (B-)inner product -- identical
     iteration counts in fp64 (the two follow the same recurrence to rounding), Ritz values and residual norms.
     run(A, largest, X0, B=None, jac=None, cb_diag=None, C=None, tol, maxiter) -> dict(lam, X, resnorm, iterations,
-    converged, status) with status != 0 for a PosDefException."""
+    converged, status) with status != 0 for a PosDefException.
+    same_arithmetic=False (the GPU: other summation order in every reduction) allows the iteration counts to differ by
+    max(3, 10 %) and does not require an fp32 PosDefException -- which hangs on the last bits of a Gram matrix -- to
+    strike in the same configuration, only that most configurations run to the end on both sides."""
     rng = np.random.default_rng(5)
+    compared = 0
+
+    def same_count(a, b):
+        return a == b if (exact64 and same_arithmetic) else abs(a - b) <= max(3 if exact64 else 5, b // 10)
+
     n = 60
     M, d = separated_spectrum_matrix(n)
     Bm = rng.standard_normal((n, n))
@@ -376,26 +386,57 @@ def case_lobpcg_general(oracle, run, dtype, tol, ltol):
                 except np.linalg.LinAlgError:
                     # PosDefException in the reference's algorithm (fp32, clustered Ritz values): the engine must break
                     # down the same way (status != 0), not return something
-                    assert not exact64 and r["status"] != 0, (gen, largest, bs)
+                    assert not exact64 and (r["status"] != 0 or not same_arithmetic), (gen, largest, bs)
                     continue
+                if r["status"] != 0 and not exact64 and not same_arithmetic:
+                    continue
+                compared += 1
                 assert r["status"] == 0 and ro.converged and r["converged"]
-                assert (r["iterations"] == ro.iterations) if exact64 else abs(r["iterations"] - ro.iterations) <= 5
+                assert same_count(r["iterations"], ro.iterations), (r["iterations"], ro.iterations)
                 assert np.abs(np.sort(ro.lam) - np.sort(r["lam"])).max() <= ltol * np.abs(ro.lam).max()
                 X = np.asarray(r["X"], dtype=np.float64)
                 assert np.max(np.linalg.norm(M @ X - Bq @ X * r["lam"][None, :], axis=0)) <= 4 * tol
                 assert np.abs(X.T @ Bq @ X - np.eye(bs)).max() <= 2 * n * tol          # test/lobpcg.jl:62-69
         if not exact64:
+            assert compared >= (gen + 1) * 2, compared
             continue           # fp32 + preconditioner / constraint: the reference itself runs into PosDefException here
         X0 = rng.random((n, 3)).astype(dtype)
         ro = oracle.lobpcg(Md, False, X0, B=Bd, P=oracle.JacobiPrec(dg.astype(dtype)), tol=tol, maxiter=300, not_zeros=True)
         for kw in (dict(jac=dg), dict(cb_diag=dg)):
             r = run(Md, False, X0, B=Bd, tol=tol, maxiter=300, **kw)
-            assert r["converged"] and r["iterations"] == ro.iterations
+            assert r["converged"] and same_count(r["iterations"], ro.iterations)
             assert np.abs(np.sort(ro.lam) - np.sort(r["lam"])).max() <= ltol * np.abs(ro.lam).max()
         rc = oracle.lobpcg(Md, False, rng.random((n, 2)).astype(dtype), B=Bd, tol=tol, maxiter=300, not_zeros=True)
         X1 = rng.random((n, 3)).astype(dtype)
         ro = oracle.lobpcg(Md, False, X1, B=Bd, C=rc.X.copy(), tol=tol, maxiter=300, not_zeros=True)
         r = run(Md, False, X1, B=Bd, C=rc.X.copy(), tol=tol, maxiter=300)
-        assert r["converged"] and r["iterations"] == ro.iterations
+        assert r["converged"] and same_count(r["iterations"], ro.iterations)
         assert np.abs(np.sort(ro.lam) - np.sort(r["lam"])).max() <= ltol * np.abs(ro.lam).max()
         assert np.abs(rc.X.astype(np.float64).T @ Bq @ np.asarray(r["X"], dtype=np.float64)).max() <= 2 * n * tol
+
+
+def case_nev_driver(lobpcg, make_A, block_size, nev):
+    """lobpcg(A, largest, X0, nev) (reference test/lobpcg.jl:291-306, :324-342): batches with deflation, with and without
+    the tail batch (`cutoff` branch, src/lobpcg.jl:945-952); residuals, orthonormality, the prescribed eigenvalues; an
+    initial constraint on top; lobpcg(A, largest, nev::Int).  lobpcg: the package's function; make_A(M) its operator."""
+    rng = np.random.default_rng(SEED)
+    n = 60
+    M, d = separated_spectrum_matrix(n)
+    A = make_A(M)
+    tol = 1e-6
+    for largest in (False, True):
+        ex = d[::-1] if largest else d
+        r = lobpcg(A, largest, rng.random((n, block_size)), nev, tol=tol, maxiter=2000, rng=rng)
+        assert r.X.shape == (n, nev) and len(r.iterations) == -(-nev // block_size) and np.all(r.converged)
+        assert np.max(np.linalg.norm(M @ r.X - r.X * r.lam[None, :], axis=0)) <= tol
+        assert np.allclose(r.X.T @ r.X, np.eye(nev), atol=2 * n * tol)
+        assert np.allclose(np.sort(r.lam), np.sort(ex[:nev]), atol=1e-5)
+    # with an initial constraint: the eigenpairs after the first two
+    r1 = lobpcg(A, False, rng.random((n, 2)), tol=tol, maxiter=2000)
+    k = max(3, 2 * block_size) if block_size > 1 else 3
+    r2 = lobpcg(A, False, rng.random((n, block_size)), k, C=r1.X.copy(), tol=tol, maxiter=2000, rng=rng)
+    assert np.allclose(np.sort(r2.lam), d[2:2 + k], atol=1e-5)
+    assert np.max(np.abs(r1.X.T @ r2.X)) <= 2 * n * tol
+    if block_size == 1:
+        r3 = lobpcg(A, False, 3, tol=tol, maxiter=2000, rng=rng)                           # lobpcg(A, largest, nev::Int)
+        assert np.allclose(np.sort(r3.lam), d[:3], atol=1e-5)
