@@ -52,7 +52,7 @@ enum { B200_ORTH_MGS = 0, B200_ORTH_CGS = 1, B200_ORTH_DGKS = 2 };
  * preconditioner idiom of reference test/cg.jl:14-18 (ldiv!(y,P,x) = y .= x ./ P.diagonal). */
 enum { B200_PREC_IDENTITY = 0, B200_PREC_JACOBI = 1,
        B200_PREC_CALLBACK = 2 /* `diag` points to a b200_linop whose apply is ldiv!(y, Pl, x); accepted by
-                                 b200_idrs_solve / b200_idrs_solve_op (b200_cg_solve_op takes its callback as an
+                                 the gmres / idrs / lobpcg entry points (b200_cg_solve_op takes its callback as an
                                  argument); the other engines reject it */ };
 
 typedef struct b200_ctx b200_ctx;   /* device + stream (+ NCCL communicator)                     */
@@ -393,6 +393,12 @@ typedef struct {
 B200_API int b200_gmres_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
                               const b200_gmres_opts *opts, b200_result *res, double *resnorm_host,
                               int64_t resnorm_cap);
+/* gmres! for a callback operator `mul!(y, A, x)`; opts->Pl / opts->Pr may be Identity, Jacobi or B200_PREC_CALLBACK
+ * (`ldiv!(y, P, x)` by callback; src/gmres.jl:249,281,294,300,303).  b200_gmres_solve with a callback preconditioner runs
+ * the same engine (csrc/gmres_core.h: Hessenberg matrix, residual recurrence and least-squares solve device-resident). */
+B200_API int b200_gmres_solve_op(b200_ctx *ctx, const b200_linop *A, void *x_dev, const void *b_dev,
+                                 const b200_gmres_opts *opts, b200_result *res, double *resnorm_host,
+                                 int64_t resnorm_cap);
 
 typedef struct {
   double abstol, reltol;    /* src/minres.jl:204-205                                               */

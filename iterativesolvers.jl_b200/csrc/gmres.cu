@@ -14,6 +14,7 @@
 // Algorithmic bytes per CGS step k: (2k+5) * n * V.
 #include "blas1.cuh"
 #include "spmv.cuh"
+#include "linop.cuh"
 
 using namespace b200;
 
@@ -545,10 +546,13 @@ int b200_gmres_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *
   B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
   B200_REQUIRE(is_square(A), "this solver needs a square operator (got %lld x %lld)", (long long)A->m_global,
                (long long)A->n_global);
+  if (opts->Pl.kind == B200_PREC_CALLBACK || opts->Pr.kind == B200_PREC_CALLBACK)     // ldiv! callbacks: the general engine
+    return gmres_general(ctx, CudaOp{A, nullptr}, A->dtype, A->m_local, A->n_global, x_dev, b_dev, opts, res, resnorm_host,
+                         resnorm_cap);
   B200_REQUIRE(opts->Pl.kind == B200_PREC_IDENTITY || (opts->Pl.kind == B200_PREC_JACOBI && opts->Pl.diag),
-               "unsupported preconditioner Pl (this engine takes Identity or Jacobi)");
+               "unsupported preconditioner Pl");
   B200_REQUIRE(opts->Pr.kind == B200_PREC_IDENTITY || (opts->Pr.kind == B200_PREC_JACOBI && opts->Pr.diag),
-               "unsupported preconditioner Pr (this engine takes Identity or Jacobi)");
+               "unsupported preconditioner Pr");
   B200_CUDA(cudaSetDevice(ctx->device));
   return A->dtype == B200_F64
              ? gmres_impl<double>(ctx, A, (double *)x_dev, (const double *)b_dev, opts, res, resnorm_host, resnorm_cap)

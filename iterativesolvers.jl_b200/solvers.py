@@ -322,8 +322,10 @@ _ORTH = {"mgs": _lib.ORTH_MGS, "cgs": _lib.ORTH_CGS, "dgks": _lib.ORTH_DGKS,
 
 def gmres_(x, A, b, *, Pl=None, Pr=None, abstol=0.0, reltol=None, restart=None, maxiter=None, log=False,
            initially_zero=False, verbose=False, orth_meth="mgs"):
-    """gmres!(x, A, b; Pl, Pr, abstol, reltol, restart, maxiter, log, initially_zero, verbose, orth_meth)."""
-    _check_operator(A)
+    """gmres!(x, A, b; Pl, Pr, abstol, reltol, restart, maxiter, log, initially_zero, verbose, orth_meth).
+    A: B200CSR or B200LinearOperator (`mul!` by callback); Pl / Pr: Identity, JacobiPrec or FunctionPrec (`ldiv!` by
+    callback).  A B200CSR with Identity / Jacobi runs the tuned engine, everything else the general one."""
+    _check_operator(A, linop_ok=True)
     if reltol is None:
         reltol = math.sqrt(_eps(A.dtype))
     if restart is None:
@@ -336,8 +338,14 @@ def gmres_(x, A, b, *, Pl=None, Pr=None, abstol=0.0, reltol=None, restart=None, 
     cap = int(maxiter) if log else 0                          # reserve!(history, :resnorm, maxiter)  :198
     resnorm = np.zeros(max(cap, 1), dtype=np.float64)
     st = _Staged(A, x, b)
-    check(lib().b200_gmres_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
-                                 C.byref(res), resnorm.ctypes.data_as(C.c_void_p) if log else None, cap))
+    rp = resnorm.ctypes.data_as(C.c_void_p) if log else None
+    cbs = tuple(P.op for P in (Pl, Pr) if isinstance(P, FunctionPrec))
+    if _is_linop(A):
+        check(_call_op(lib().b200_gmres_solve_op, (A,) + cbs, A.ctx._h, C.byref(A._c), as_device_ptr(st.xd),
+                       as_device_ptr(st.bd), C.byref(opts), C.byref(res), rp, cap))
+    else:
+        check(_call_op(lib().b200_gmres_solve, cbs, A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd),
+                       C.byref(opts), C.byref(res), rp, cap))
     st.finish()
     if verbose:
         print("=== gmres ===\nrest\titer\tresnorm")
@@ -349,7 +357,7 @@ def gmres_(x, A, b, *, Pl=None, Pr=None, abstol=0.0, reltol=None, restart=None, 
 
 
 def gmres(A, b, **kw):
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
     x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
     return gmres_(x, A, b, initially_zero=True, **kw)
 

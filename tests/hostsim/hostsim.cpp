@@ -22,6 +22,7 @@
 #include "../../iterativesolvers.jl_b200/csrc/lsmr_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/idrs_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/cg_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/gmres_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/lobpcg_constraint_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/svdl_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/lobpcg_general_core.h"
@@ -248,6 +249,32 @@ EXPORT int hostsim_cg(int is_f64, const hostsim_csr *A, const hostsim_csr *Pl, c
                   : b200::cgp_run<float>(be, &a, Pl ? &p : nullptr, (const float *)diag, A->m, A->n, (float *)x,
                                          (const float *)b, abstol, reltol, maxiter, initially_zero, check_every,
                                          hist_cap, hist, &o);
+  out->iters = o.iters; out->mvps = o.mvps; out->mtvps = 0; out->n_hist = o.n_hist;
+  out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
+  out->passes = be.passes; out->applies = be.applies;
+  return st;
+}
+
+// gmres! on general operators: Pl / Pr (may be NULL) are "operators" whose application is y = P \ x; pl_diag / pr_diag
+// Jacobi diagonals
+EXPORT int hostsim_gmres(int is_f64, const hostsim_csr *A, const hostsim_csr *Pl, const hostsim_csr *Pr, const void *pl_diag,
+                         const void *pr_diag, void *x, const void *b, double abstol, double reltol, int restart,
+                         int64_t maxiter, int initially_zero, int orth_meth, int64_t hist_cap, double *hist, int order,
+                         int split, hostsim_out *out) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64), pl, pr;
+  if (Pl) pl = mk(Pl, is_f64);
+  if (Pr) pr = mk(Pr, is_f64);
+  b200::GmresOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st = is_f64 ? b200::gmres_run<double>(be, &a, Pl ? &pl : nullptr, Pr ? &pr : nullptr, (const double *)pl_diag,
+                                            (const double *)pr_diag, A->m, A->n, (double *)x, (const double *)b, abstol,
+                                            reltol, restart, maxiter, initially_zero, orth_meth, hist_cap, hist, &o)
+                  : b200::gmres_run<float>(be, &a, Pl ? &pl : nullptr, Pr ? &pr : nullptr, (const float *)pl_diag,
+                                           (const float *)pr_diag, A->m, A->n, (float *)x, (const float *)b, abstol,
+                                           reltol, restart, maxiter, initially_zero, orth_meth, hist_cap, hist, &o);
   out->iters = o.iters; out->mvps = o.mvps; out->mtvps = 0; out->n_hist = o.n_hist;
   out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
   out->passes = be.passes; out->applies = be.applies;

@@ -181,6 +181,30 @@ def cg_(x, A, b, *, Pl=None, diag=None, abstol=0.0, reltol=-1.0, maxiter=-1, ini
     return x, _outcome(out, hist)
 
 
+def gmres_(x, A, b, *, Pl=None, Pr=None, pl_diag=None, pr_diag=None, abstol=0.0, reltol=-1.0, restart=-1, maxiter=-1,
+           initially_zero=False, orth_meth="mgs", order=0, split=0):
+    """the general-operator gmres engine (csrc/gmres_core.h) on the serial backend; Pl / Pr: scipy matrices whose
+    product applies the preconditioner (y = P_inverse @ x), pl_diag / pr_diag: Jacobi diagonals; x updated in place."""
+    dt = x.dtype
+    Ac = Csr(A, dt)
+    Plc = Csr(Pl, dt) if Pl is not None else None
+    Prc = Csr(Pr, dt) if Pr is not None else None
+    b = np.ascontiguousarray(b, dtype=dt)
+    dl = None if pl_diag is None else np.ascontiguousarray(pl_diag, dtype=dt)
+    dr = None if pr_diag is None else np.ascontiguousarray(pr_diag, dtype=dt)
+    cap = maxiter if maxiter >= 0 else A.shape[1]
+    hist = np.zeros(max(cap, 1))
+    out = _Out()
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+    st = lib().hostsim_gmres(C.c_int(dt == np.float64), C.byref(Ac.c), C.byref(Plc.c) if Plc else None,
+                             C.byref(Prc.c) if Prc else None, vp(dl), vp(dr), vp(x), vp(b), C.c_double(abstol),
+                             C.c_double(reltol), C.c_int(restart), C.c_int64(maxiter), C.c_int(initially_zero),
+                             C.c_int({"mgs": 0, "cgs": 1, "dgks": 2}[orth_meth]), C.c_int64(cap), vp(hist), C.c_int(order),
+                             C.c_int(split), C.byref(out))
+    assert st == 0, st
+    return x, _outcome(out, hist)
+
+
 def constraint_apply_(X, Y, *, appended=0, row_major=False, order=0, split=0):
     """the Constraint passes (csrc/lobpcg_constraint_core.h) on the serial backend: X <- X - Y (chol(Y'Y) \\ Y'X).
     X: n x bs (bs <= 16); row_major: X is laid out like the LOBPCG engine's internal n x 16 blocks."""

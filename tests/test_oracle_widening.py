@@ -518,8 +518,48 @@ def test_python_linop_paths_with_a_fake_library(monkeypatch):
     bad = isb.B200LinearOperator((n, n), np.float64, boom, ctx=ctx)
     with pytest.raises(ZeroDivisionError, match="inside the operator"):
         isb.cg(bad, b)
+    # gmres!: callback operator -> b200_gmres_solve_op; CSR operator + callback Pl / Pr -> b200_gmres_solve (which
+    # forwards to the same engine), opts.Pl / opts.Pr carrying the addresses of the preconditioners' b200_linop
+    calls.clear()
+    seen.clear()
+    isb.gmres(op, b, restart=5)
+    assert calls == ["b200_gmres_solve_op"] and seen[0][0] == "mul"
+    csr = S.B200CSR.__new__(S.B200CSR)
+    csr.ctx, csr._h, csr.m_local, csr.n_global, csr.m_global, csr.dtype = ctx, C.c_void_p(7), n, n, n, np.dtype(np.float64)
+    csr.close = lambda: None
+    got = []
+
+    class FakeLibG(FakeLib):
+        def __getattr__(self, name):
+            inner = FakeLib.__getattr__(self, name)
+
+            def f(*args):
+                for a in args:
+                    obj = getattr(a, "_obj", None)
+                    if isinstance(obj, L.GmresOpts):
+                        got.append((obj.Pl.kind, obj.Pr.kind, obj.restart, obj.orth_meth))
+                        for P in (obj.Pl, obj.Pr):
+                            if P.kind == 2:
+                                C.cast(P.diag, C.POINTER(L.LinOp)).contents.apply(None, 0x3000, 0x4000, None)
+                return inner(*args)
+            return f
+
+    monkeypatch.setattr(S, "lib", lambda: FakeLibG())
+    calls.clear()
+    seen.clear()
+    Pr = isb.FunctionPrec(n, np.float64, lambda y, x: seen.append(("rdiv", y.shape)), ctx=ctx)
+    isb.gmres(csr, b, Pl=Pl, Pr=Pr, restart=7, orth_meth="dgks")
+    assert calls == ["b200_gmres_solve"] and got == [(2, 2, 7, 2)]
+    assert ("ldiv", (n,)) in seen and ("rdiv", (n,)) in seen
+
+    def boom_p(y, x):
+        raise KeyError("inside the preconditioner")
+
+    with pytest.raises(KeyError, match="inside the preconditioner"):
+        isb.gmres(csr, b, Pr=isb.FunctionPrec(n, np.float64, boom_p, ctx=ctx))
+    monkeypatch.setattr(S, "lib", lambda: FakeLib())
     with pytest.raises(TypeError):
-        isb.gmres(op, b)                             # the GMRES engine is CSR-only
+        isb.minres(op, b)                            # the MINRES engine is CSR-only
 
 
 def test_partitioned_engines_world2_gloo():
@@ -825,3 +865,19 @@ def test_python_nev_driver_over_the_serial_backend(monkeypatch, sim, block_size,
         return SimpleNamespace(M=sp.csr_matrix(M), ctx=None, dtype=np.dtype(np.float64), m_local=n, n_global=n, m_global=n)
 
     cases.case_nev_driver(isb.lobpcg, make_A, block_size, nev)
+
+
+# ------------------------------------------------------------------------------------------ general gmres! engine
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 2e-5)])
+def test_engine_gmres_general_matches_oracle(oracle, sim, dtype, tol):
+    for order, split in ((0, 0), (1, 1)):
+        def run(x, A, b, d, pl, pr, restart, maxiter, meth, **kw):
+            Dinv = sp.diags(1.0 / d.astype(np.float64)).tocsr()
+            args = {}
+            if pl is not None:
+                args["pl_diag" if pl == "jac" else "Pl"] = d if pl == "jac" else Dinv
+            if pr is not None:
+                args["pr_diag" if pr == "jac" else "Pr"] = d if pr == "jac" else Dinv
+            return sim.gmres_(x, sp.csr_matrix(A), b, restart=restart, maxiter=maxiter, orth_meth=meth, order=order,
+                              split=split, **args, **kw)
+        cases.case_gmres_general(oracle, run, dtype, tol)

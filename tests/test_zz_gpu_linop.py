@@ -129,6 +129,32 @@ def test_idrs_callback_preconditioner(isb, oracle):
     # the CSR-only engines say so instead of silently ignoring a callback preconditioner
     A = isb.B200CSR.from_scipy((sp.eye(32) * 2.0).tocsc())
     Pl = isb.FunctionPrec(32, np.float64, lambda y, x: None)
-    for fn in (isb.gmres, isb.bicgstabl):
-        with pytest.raises(isb.B200Error, match="unsupported preconditioner"):
-            fn(A, np.ones(32), Pl=Pl)
+    with pytest.raises(isb.B200Error, match="unsupported preconditioner"):
+        isb.bicgstabl(A, np.ones(32), Pl=Pl)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 5e-5)])
+def test_gmres_general_operator_and_callback_preconditioners(isb, oracle, dtype, tol):
+    """gmres! with `mul!` / `ldiv!` callbacks (b200_gmres_solve_op; b200_gmres_solve forwarding a callback Pl / Pr to the
+    same engine) against the oracle -- the case the serial backend runs (tests/widening_cases.py)."""
+    def run(x, A, b, d, pl, pr, restart, maxiter, meth, **kw):
+        csr = isb.B200CSR.from_scipy(sp.csc_matrix(A).astype(x.dtype))
+        jac = isb.JacobiPrec(np.asarray(d, dtype=x.dtype))
+        mk = lambda kind: None if kind is None else (jac if kind == "jac" else
+                                                     isb.FunctionPrec(csr.m_local, x.dtype, lambda y, v: jac.ldiv_(y, v)))
+        op = csr if "cb" in (pl, pr) else isb.B200LinearOperator.from_csr(csr)
+        x, h = isb.gmres_(x, op, b, Pl=mk(pl), Pr=mk(pr), restart=restart, maxiter=maxiter, orth_meth=meth, log=True, **kw)
+        return x, SimpleNamespace(iters=h.iters, mvps=h.mvps, converged=h.isconverged, hist=h["resnorm"])
+    cases.case_gmres_general(oracle, run, dtype, tol)
+
+
+def test_general_gmres_equals_the_specialised_engine(isb, oracle):
+    rng = np.random.default_rng(SEED)
+    O = oracle.laplace_matrix(np.float64, 16, 3, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    b = rng.standard_normal(O.n)
+    for meth in ("mgs", "cgs", "dgks"):
+        x1, h1 = isb.gmres(A, b, restart=30, maxiter=90, orth_meth=meth, log=True)
+        x2, h2 = isb.gmres(isb.B200LinearOperator.from_csr(A), b, restart=30, maxiter=90, orth_meth=meth, log=True)
+        assert h1.iters == h2.iters and h1.mvps == h2.mvps and h1.isconverged == h2.isconverged
+        assert np.max(np.abs(h1["resnorm"] - h2["resnorm"])) <= 1e-9 * h1["resnorm"][0] and relerr(x2, x1) <= 1e-8

@@ -440,3 +440,41 @@ def case_nev_driver(lobpcg, make_A, block_size, nev):
     if block_size == 1:
         r3 = lobpcg(A, False, 3, tol=tol, maxiter=2000, rng=rng)                           # lobpcg(A, largest, nev::Int)
         assert np.allclose(np.sort(r3.lam), d[:3], atol=1e-5)
+
+
+def case_gmres_general(oracle, run, dtype, tol):
+    """the general gmres! engine (csrc/gmres_core.h: callback operator, Pl / Pr as Jacobi diagonals or callbacks, the three
+    orthogonalisation methods) against the oracle's gmres_: iteration and product counts, the residual history, x.
+    run(x0, A, b, d, pl, pr, restart, maxiter, orth_meth) -> (x, outcome with iters, mvps, converged, hist); pl / pr in
+    {None, "jac", "cb"} select Identity, the Jacobi diagonal d, or d applied through a callback."""
+    rng = np.random.default_rng(3)
+    n = 300
+    A = (sp.random(n, n, 0.03, random_state=1, format="csc") + 4 * sp.eye(n)).tocsc()
+    b = rng.standard_normal(n)
+    d = A.diagonal()
+    Ad, bd = A.astype(dtype), b.astype(dtype)
+    mk = lambda kind: None if kind is None else oracle.JacobiPrec(d.astype(dtype))
+    for meth in ("mgs", "cgs", "dgks"):
+        for pl, pr in ((None, None), ("jac", None), (None, "jac"), ("cb", "cb"), ("jac", "cb"), ("cb", None)):
+            for restart in (5, 20):
+                x0 = rng.standard_normal(n).astype(dtype)
+                xo, ho = oracle.gmres_(x0.copy(), Ad, bd, Pl=mk(pl), Pr=mk(pr), restart=restart, maxiter=60, log=True,
+                                       orth_meth=meth)
+                xs, hs = run(x0.copy(), Ad, bd, d.astype(dtype), pl, pr, restart, 60, meth)
+                ro = np.asarray(ho["resnorm"])
+                assert hs.converged == ho.isconverged and abs(hs.iters - ho.iters) <= (0 if dtype == np.float64 else 1)
+                if hs.iters == ho.iters:
+                    assert hs.mvps == ho.mvps
+                k = min(hs.iters, ho.iters)
+                assert np.max(np.abs(ro[:k] - np.asarray(hs.hist)[:k])) <= tol * ro[0], (meth, pl, pr, restart)
+                assert np.linalg.norm(xs - xo) <= 20 * tol * np.linalg.norm(xo), (meth, pl, pr, restart)
+    # restart > 16 columns in one cycle (two dot / update passes), maxiter reached inside a cycle, zero iterations
+    x0 = np.zeros(n, dtype=dtype)
+    xo, ho = oracle.gmres_(x0.copy(), Ad, bd, restart=40, maxiter=23, reltol=1e-30, log=True, orth_meth="dgks", initially_zero=True)
+    xs, hs = run(x0.copy(), Ad, bd, d.astype(dtype), None, None, 40, 23, "dgks", reltol=1e-30, initially_zero=True)
+    assert hs.iters == ho.iters == 23 and hs.mvps == ho.mvps and not hs.converged
+    assert np.linalg.norm(xs - xo) <= 20 * tol * np.linalg.norm(xo)
+    xe = rng.standard_normal(n).astype(dtype)
+    be = (Ad @ xe).astype(dtype)
+    xs, hs = run(xe.copy(), Ad, be, d.astype(dtype), None, None, 20, 60, "mgs", abstol=1e-3)
+    assert hs.iters == 0 and hs.converged and np.array_equal(xs, xe)
