@@ -52,8 +52,8 @@ enum { B200_ORTH_MGS = 0, B200_ORTH_CGS = 1, B200_ORTH_DGKS = 2 };
  * preconditioner idiom of reference test/cg.jl:14-18 (ldiv!(y,P,x) = y .= x ./ P.diagonal). */
 enum { B200_PREC_IDENTITY = 0, B200_PREC_JACOBI = 1,
        B200_PREC_CALLBACK = 2 /* `diag` points to a b200_linop whose apply is ldiv!(y, Pl, x); accepted by
-                                 the gmres / idrs / lobpcg entry points (b200_cg_solve_op takes its callback as an
-                                 argument); the other engines reject it */ };
+                                 the gmres / bicgstabl / idrs / lobpcg entry points (b200_cg_solve_op takes its callback as an
+                                 argument); cg / chebyshev on a b200_csr reject it */ };
 
 typedef struct b200_ctx b200_ctx;   /* device + stream (+ NCCL communicator)                     */
 typedef struct b200_csr b200_csr;   /* the operator A: CSR int32 on device, row-partitioned       */
@@ -410,6 +410,10 @@ typedef struct {
 B200_API int b200_minres_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
                                const b200_minres_opts *opts, b200_result *res, double *resnorm_host,
                                int64_t resnorm_cap);
+/* minres! for a callback operator `mul!(y, A, x)` (csrc/minres_core.h; src/minres.jl:61,104) */
+B200_API int b200_minres_solve_op(b200_ctx *ctx, const b200_linop *A, void *x_dev, const void *b_dev,
+                                  const b200_minres_opts *opts, b200_result *res, double *resnorm_host,
+                                  int64_t resnorm_cap);
 
 typedef struct {
   double abstol, reltol;    /* src/bicgstabl.jl:182-183                                            */
@@ -424,6 +428,12 @@ typedef struct {
 B200_API int b200_bicgstabl_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev,
                                   const b200_bicgstabl_opts *opts, b200_result *res, double *resnorm_host,
                                   int64_t resnorm_cap);
+/* bicgstabl! for a callback operator; opts->Pl may be Identity, Jacobi or B200_PREC_CALLBACK (`ldiv!(y, Pl, x)` by
+ * callback; src/bicgstabl.jl:55,98,108).  b200_bicgstabl_solve with a callback preconditioner runs the same engine
+ * (csrc/bicgstabl_core.h); l <= 8. */
+B200_API int b200_bicgstabl_solve_op(b200_ctx *ctx, const b200_linop *A, void *x_dev, const void *b_dev,
+                                     const b200_bicgstabl_opts *opts, b200_result *res, double *resnorm_host,
+                                     int64_t resnorm_cap);
 
 typedef struct {
   double tol;               /* default_tolerance(T) = eps(real(T))^(3/10)  src/lobpcg.jl:751       */

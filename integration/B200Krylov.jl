@@ -547,4 +547,73 @@ end
 # qmr!/lsqr!/lsmr!/idrs! on B200LinearOperator: the same pattern with b200_qmr_solve_op / b200_lsqr_solve_op /
 # b200_lsmr_solve_op / b200_idrs_solve_op (the adjoint is a second B200LinearOperator).
 
+# A preconditioner given as a B200LinearOperator (f(y, x) enqueues y = P \ x, i.e. ldiv!(y, P, x)) travels in the
+# b200_precond slot as B200_PREC_CALLBACK = 2 with the address of its b200_linop; the Ref must outlive the call.
+prec_cb(P, keep::Vector{Any}) = prec(P)
+function prec_cb(P::B200LinearOperator, keep::Vector{Any})
+    r = Ref(linop(P)); push!(keep, r)
+    Precond(2, 0, Base.unsafe_convert(Ptr{Cvoid}, r))
+end
+
+# gmres!(x, A, b; Pl, Pr, ...) with `mul!` / `ldiv!` callbacks  src/gmres.jl:184-194 (expand! :285-304)
+function gmres!(x::B200Vector{T}, A::Union{B200CSR{T},B200LinearOperator{T}}, b::B200Vector{T};
+                Pl = Identity(), Pr = Identity(), abstol::Real = zero(T), reltol::Real = sqrt(eps(T)),
+                restart::Int = min(20, size(A, 2)), maxiter::Int = size(A, 2), log::Bool = false,
+                initially_zero::Bool = false, verbose::Bool = false,
+                orth_meth::OrthogonalizationMethod = ModifiedGramSchmidt()) where {T}
+    res = Result(); hist = Vector{Float64}(undef, log ? maxiter : 0); keep = Any[]
+    o = GmresOpts(abstol, reltol, maxiter, restart, initially_zero, orth_code(orth_meth), 0, prec_cb(Pl, keep), prec_cb(Pr, keep))
+    GC.@preserve A Pl Pr keep begin
+        if A isa B200LinearOperator
+            a = Ref(linop(A))
+            check(ccall((:b200_gmres_solve_op, LIB), Cint,
+                        (Ptr{Cvoid}, Ptr{LinOp}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{GmresOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                        A.ctx.h, a, x.p, b.p, o, res, hist, length(hist)))
+        else                                    # CSR operator: b200_gmres_solve forwards callback preconditioners
+            check(ccall((:b200_gmres_solve, LIB), Cint,
+                        (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{GmresOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                        A.ctx.h, A.h, x.p, b.p, o, res, hist, length(hist)))
+        end
+    end
+    log ? (x, history(res, hist, abstol, reltol; restart = restart)) : x
+end
+
+# minres!(x, A, b; ...) with a `mul!` callback  src/minres.jl:200-207
+function minres!(x::B200Vector{T}, A::B200LinearOperator{T}, b::B200Vector{T};
+                 skew_hermitian::Bool = false, verbose::Bool = false, log::Bool = false, abstol::Real = zero(T),
+                 reltol::Real = sqrt(eps(T)), maxiter::Int = A.n, initially_zero::Bool = false) where {T}
+    res = Result(); hist = Vector{Float64}(undef, log ? maxiter : 0)
+    o = MinresOpts(abstol, reltol, maxiter, initially_zero, skew_hermitian); a = Ref(linop(A))
+    GC.@preserve A check(ccall((:b200_minres_solve_op, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{LinOp}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{MinresOpts}, Ref{Result}, Ptr{Float64}, Int64),
+        A.ctx.h, a, x.p, b.p, o, res, hist, length(hist)))
+    log ? (x, history(res, hist, abstol, reltol)) : x
+end
+
+# bicgstabl!(x, A, b, l; Pl, ...) with `mul!` / `ldiv!` callbacks  src/bicgstabl.jl:181-188
+function bicgstabl!(x::B200Vector{T}, A::Union{B200CSR{T},B200LinearOperator{T}}, b::B200Vector{T}, l::Int = 2;
+                    abstol::Real = zero(T), reltol::Real = sqrt(eps(T)), max_mv_products::Int = size(A, 2),
+                    log::Bool = false, verbose::Bool = false, Pl = Identity(), initial_zero::Bool = false,
+                    r_shadow::B200Vector{T} = B200Vector(A.ctx, rand(T, size(A, 1)))) where {T}      # rand(T, n) :38
+    res = Result(); hist = Vector{Float64}(undef, log ? max_mv_products : 0); keep = Any[]
+    o = BicgstablOpts(abstol, reltol, max_mv_products, l, initial_zero, prec_cb(Pl, keep), r_shadow.p)
+    status = GC.@preserve A Pl keep r_shadow begin
+        if A isa B200LinearOperator
+            a = Ref(linop(A))
+            ccall((:b200_bicgstabl_solve_op, LIB), Cint,
+                  (Ptr{Cvoid}, Ptr{LinOp}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{BicgstablOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                  A.ctx.h, a, x.p, b.p, o, res, hist, length(hist))
+        else
+            ccall((:b200_bicgstabl_solve, LIB), Cint,
+                  (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{BicgstablOpts}, Ref{Result}, Ptr{Float64}, Int64),
+                  A.ctx.h, A.h, x.p, b.p, o, res, hist, length(hist))
+        end
+    end
+    status == -5 && throw(SingularException(0))                            # lu! in the MR step  src/bicgstabl.jl:123
+    check(status)
+    log ? (x, history(res, hist, abstol, reltol)) : x
+end
+Base.size(A::B200LinearOperator) = (A.m, A.n)
+Base.size(A::B200LinearOperator, d::Integer) = d == 1 ? A.m : (d == 2 ? A.n : 1)
+
 end # module

@@ -12,6 +12,7 @@
 // The (l x l) LU solve (:123-124, partial pivoting as lu!) runs in a one-thread kernel.
 #include "blas1.cuh"
 #include "spmv.cuh"
+#include "linop.cuh"
 
 using namespace b200;
 
@@ -379,8 +380,11 @@ int b200_bicgstabl_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const vo
   B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
   B200_REQUIRE(is_square(A), "this solver needs a square operator (got %lld x %lld)", (long long)A->m_global,
                (long long)A->n_global);
+  if (opts->Pl.kind == B200_PREC_CALLBACK)                                       // ldiv! by callback: the general engine
+    return bicgstabl_general(ctx, CudaOp{A, nullptr}, A->dtype, A->m_local, A->n_global, x_dev, b_dev, opts, res,
+                             resnorm_host, resnorm_cap);
   B200_REQUIRE(opts->Pl.kind == B200_PREC_IDENTITY || (opts->Pl.kind == B200_PREC_JACOBI && opts->Pl.diag),
-               "unsupported preconditioner Pl (this engine takes Identity or Jacobi)");
+               "unsupported preconditioner Pl");
   B200_CUDA(cudaSetDevice(ctx->device));
   return A->dtype == B200_F64 ? bicgstabl_impl<double>(ctx, A, (double *)x_dev, (const double *)b_dev, opts, res,
                                                        resnorm_host, resnorm_cap)

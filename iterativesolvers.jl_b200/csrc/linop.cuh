@@ -8,4 +8,7 @@ int check_linop(const b200_linop *A, const char *what);   // qmr.cu
 // their preconditioners is a callback
 int gmres_general(b200_ctx *ctx, const CudaOp &A, int dtype, int64_t n, int64_t n_global, void *x_dev, const void *b_dev,
                   const b200_gmres_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);   // gmres_op.cu
+int bicgstabl_general(b200_ctx *ctx, const CudaOp &A, int dtype, int64_t n, int64_t n_global, void *x_dev,
+                      const void *b_dev, const b200_bicgstabl_opts *opts, b200_result *res, double *resnorm_host,
+                      int64_t resnorm_cap);                                                                     // minres_bicgstabl_op.cu
 }

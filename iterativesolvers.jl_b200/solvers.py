@@ -367,7 +367,9 @@ def gmres(A, b, **kw):
 # ------------------------------------------------------------------------------------------------
 def minres_(x, A, b, *, skew_hermitian=False, verbose=False, log=False, abstol=0.0, reltol=None, maxiter=None,
             initially_zero=False):
-    _check_operator(A)
+    """minres!(x, A, b; skew_hermitian, verbose, log, abstol, reltol, maxiter, initially_zero) -- reference
+    src/minres.jl:200-207.  A: B200CSR (tuned engine) or B200LinearOperator (`mul!` by callback: general engine)."""
+    _check_operator(A, linop_ok=True)
     if reltol is None:
         reltol = math.sqrt(_eps(A.dtype))
     if maxiter is None:
@@ -377,8 +379,13 @@ def minres_(x, A, b, *, skew_hermitian=False, verbose=False, log=False, abstol=0
     cap = int(maxiter) if log else 0
     resnorm = np.zeros(max(cap, 1), dtype=np.float64)
     st = _Staged(A, x, b)
-    check(lib().b200_minres_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
-                                  C.byref(res), resnorm.ctypes.data_as(C.c_void_p) if log else None, cap))
+    rp = resnorm.ctypes.data_as(C.c_void_p) if log else None
+    if _is_linop(A):
+        check(_call_op(lib().b200_minres_solve_op, (A,), A.ctx._h, C.byref(A._c), as_device_ptr(st.xd),
+                       as_device_ptr(st.bd), C.byref(opts), C.byref(res), rp, cap))
+    else:
+        check(lib().b200_minres_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
+                                      C.byref(res), rp, cap))
     st.finish()
     if verbose:
         for i, r in enumerate(resnorm[: res.n_resnorm], start=1):
@@ -388,7 +395,7 @@ def minres_(x, A, b, *, skew_hermitian=False, verbose=False, log=False, abstol=0
 
 
 def minres(A, b, **kw):
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
     x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
     return minres_(x, A, b, initially_zero=True, **kw)
 
@@ -399,8 +406,10 @@ def minres(A, b, **kw):
 def bicgstabl_(x, A, b, l=2, *, abstol=0.0, reltol=None, max_mv_products=None, log=False, verbose=False, Pl=None,
                initial_zero=False, r_shadow=None, rng=None):
     """bicgstabl!(x, A, b, l; ...).  The reference draws r_shadow = rand(T, n) (src/bicgstabl.jl:38);
-    here the draw happens on the host (numpy Generator `rng`) unless `r_shadow` is given."""
-    _check_operator(A)
+    here the draw happens on the host (numpy Generator `rng`) unless `r_shadow` is given.
+    A: B200CSR or B200LinearOperator; Pl: Identity, JacobiPrec or FunctionPrec (`ldiv!` by callback).  A B200CSR with
+    Identity / Jacobi runs the tuned engine, everything else the general one (l <= 8)."""
+    _check_operator(A, linop_ok=True)
     if reltol is None:
         reltol = math.sqrt(_eps(A.dtype))
     if max_mv_products is None:
@@ -415,8 +424,14 @@ def bicgstabl_(x, A, b, l=2, *, abstol=0.0, reltol=None, max_mv_products=None, l
     cap = int(max_mv_products) if log else 0                  # src/bicgstabl.jl:194
     resnorm = np.zeros(max(cap, 1), dtype=np.float64)
     st = _Staged(A, x, b)
-    status = lib().b200_bicgstabl_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), C.byref(opts),
-                                        C.byref(res), resnorm.ctypes.data_as(C.c_void_p) if log else None, cap)
+    rp = resnorm.ctypes.data_as(C.c_void_p) if log else None
+    cbs = (Pl.op,) if isinstance(Pl, FunctionPrec) else ()
+    if _is_linop(A):
+        status = _call_op(lib().b200_bicgstabl_solve_op, (A,) + cbs, A.ctx._h, C.byref(A._c), as_device_ptr(st.xd),
+                          as_device_ptr(st.bd), C.byref(opts), C.byref(res), rp, cap)
+    else:
+        status = _call_op(lib().b200_bicgstabl_solve, cbs, A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd),
+                          C.byref(opts), C.byref(res), rp, cap)
     if status == _lib.ERR_BREAKDOWN:
         raise np.linalg.LinAlgError("SingularException in BiCGStab(l) MR step (reference src/bicgstabl.jl:123)")
     check(status)
@@ -429,7 +444,7 @@ def bicgstabl_(x, A, b, l=2, *, abstol=0.0, reltol=None, max_mv_products=None, l
 
 
 def bicgstabl(A, b, l=2, **kw):
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
     x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
     return bicgstabl_(x, A, b, l, initial_zero=True, **kw)
 

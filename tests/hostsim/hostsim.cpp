@@ -23,6 +23,8 @@
 #include "../../iterativesolvers.jl_b200/csrc/idrs_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/cg_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/gmres_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/minres_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/bicgstabl_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/lobpcg_constraint_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/svdl_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/lobpcg_general_core.h"
@@ -277,6 +279,50 @@ EXPORT int hostsim_gmres(int is_f64, const hostsim_csr *A, const hostsim_csr *Pl
                                            reltol, restart, maxiter, initially_zero, orth_meth, hist_cap, hist, &o);
   out->iters = o.iters; out->mvps = o.mvps; out->mtvps = 0; out->n_hist = o.n_hist;
   out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
+  out->passes = be.passes; out->applies = be.applies;
+  return st;
+}
+
+// minres! on a general operator
+EXPORT int hostsim_minres(int is_f64, const hostsim_csr *A, void *x, const void *b, double abstol, double reltol,
+                          int64_t maxiter, int initially_zero, int skew, int check_every, int64_t hist_cap, double *hist,
+                          int order, int split, hostsim_out *out) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64);
+  b200::MinresOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st = is_f64 ? b200::minres_run<double>(be, &a, A->m, A->n, (double *)x, (const double *)b, abstol, reltol, maxiter,
+                                             initially_zero, skew, check_every, hist_cap, hist, &o)
+                  : b200::minres_run<float>(be, &a, A->m, A->n, (float *)x, (const float *)b, abstol, reltol, maxiter,
+                                            initially_zero, skew, check_every, hist_cap, hist, &o);
+  out->iters = o.iters; out->mvps = o.mvps; out->mtvps = 0; out->n_hist = o.n_hist;
+  out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
+  out->passes = be.passes; out->applies = be.applies;
+  return st;
+}
+
+// bicgstabl! on general operators: Pl (may be NULL) is an "operator" whose application is y = Pl \ x; diag: Jacobi
+EXPORT int hostsim_bicgstabl(int is_f64, const hostsim_csr *A, const hostsim_csr *Pl, const void *diag, void *x,
+                             const void *b, const void *shadow, int l, double abstol, double reltol, int64_t max_mv,
+                             int initial_zero, int check_every, int64_t hist_cap, double *hist, int order, int split,
+                             hostsim_out *out) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64), p;
+  if (Pl) p = mk(Pl, is_f64);
+  b200::BcgOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st = is_f64 ? b200::bicgstabl_run<double>(be, &a, Pl ? &p : nullptr, (const double *)diag, A->m, A->n, (double *)x,
+                                                (const double *)b, (const double *)shadow, l, abstol, reltol, max_mv,
+                                                initial_zero, check_every, hist_cap, hist, &o)
+                  : b200::bicgstabl_run<float>(be, &a, Pl ? &p : nullptr, (const float *)diag, A->m, A->n, (float *)x,
+                                               (const float *)b, (const float *)shadow, l, abstol, reltol, max_mv,
+                                               initial_zero, check_every, hist_cap, hist, &o);
+  out->iters = o.iters; out->mvps = o.mvps; out->mtvps = 0; out->n_hist = o.n_hist;
+  out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown | (o.singular << 1);
   out->passes = be.passes; out->applies = be.applies;
   return st;
 }

@@ -205,6 +205,47 @@ def gmres_(x, A, b, *, Pl=None, Pr=None, pl_diag=None, pr_diag=None, abstol=0.0,
     return x, _outcome(out, hist)
 
 
+def minres_(x, A, b, *, abstol=0.0, reltol=-1.0, maxiter=-1, initially_zero=False, skew_hermitian=False, check_every=0,
+            order=0, split=0):
+    """the general-operator minres engine (csrc/minres_core.h) on the serial backend; x updated in place."""
+    dt = x.dtype
+    Ac = Csr(A, dt)
+    b = np.ascontiguousarray(b, dtype=dt)
+    cap = maxiter if maxiter >= 0 else A.shape[1]
+    hist = np.zeros(max(cap, 1))
+    out = _Out()
+    st = lib().hostsim_minres(C.c_int(dt == np.float64), C.byref(Ac.c), C.c_void_p(x.ctypes.data), C.c_void_p(b.ctypes.data),
+                              C.c_double(abstol), C.c_double(reltol), C.c_int64(maxiter), C.c_int(initially_zero),
+                              C.c_int(skew_hermitian), C.c_int(check_every), C.c_int64(cap), hist.ctypes.data_as(C.c_void_p),
+                              C.c_int(order), C.c_int(split), C.byref(out))
+    assert st == 0, st
+    return x, _outcome(out, hist)
+
+
+def bicgstabl_(x, A, b, l, shadow, *, Pl=None, diag=None, abstol=0.0, reltol=-1.0, max_mv_products=-1, initial_zero=False,
+               check_every=0, order=0, split=0):
+    """the general-operator bicgstabl engine (csrc/bicgstabl_core.h) on the serial backend; Pl: a scipy matrix whose
+    product applies the preconditioner, diag: Jacobi diagonal; breakdown bit 1 = SingularException in the MR step."""
+    dt = x.dtype
+    Ac = Csr(A, dt)
+    Pc = Csr(Pl, dt) if Pl is not None else None
+    b = np.ascontiguousarray(b, dtype=dt)
+    sh = np.ascontiguousarray(shadow, dtype=dt)
+    d = None if diag is None else np.ascontiguousarray(diag, dtype=dt)
+    cap = max_mv_products if max_mv_products >= 0 else A.shape[1]
+    hist = np.zeros(max(cap, 1))
+    out = _Out()
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+    st = lib().hostsim_bicgstabl(C.c_int(dt == np.float64), C.byref(Ac.c), C.byref(Pc.c) if Pc else None, vp(d), vp(x), vp(b),
+                                 vp(sh), C.c_int(l), C.c_double(abstol), C.c_double(reltol), C.c_int64(max_mv_products),
+                                 C.c_int(initial_zero), C.c_int(check_every), C.c_int64(cap), vp(hist), C.c_int(order),
+                                 C.c_int(split), C.byref(out))
+    assert st == 0, st
+    o = _outcome(out, hist)
+    o.singular = bool(out.breakdown & 2)
+    return x, o
+
+
 def constraint_apply_(X, Y, *, appended=0, row_major=False, order=0, split=0):
     """the Constraint passes (csrc/lobpcg_constraint_core.h) on the serial backend: X <- X - Y (chol(Y'Y) \\ Y'X).
     X: n x bs (bs <= 16); row_major: X is laid out like the LOBPCG engine's internal n x 16 blocks."""

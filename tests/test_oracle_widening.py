@@ -558,8 +558,42 @@ def test_python_linop_paths_with_a_fake_library(monkeypatch):
     with pytest.raises(KeyError, match="inside the preconditioner"):
         isb.gmres(csr, b, Pr=isb.FunctionPrec(n, np.float64, boom_p, ctx=ctx))
     monkeypatch.setattr(S, "lib", lambda: FakeLib())
+    # minres! / bicgstabl!: callback operator -> *_solve_op; bicgstabl! on a CSR operator with a callback Pl ->
+    # b200_bicgstabl_solve with B200_PREC_CALLBACK
+    calls.clear()
+    seen.clear()
+    isb.minres(op, b)
+    assert calls == ["b200_minres_solve_op"] and seen[0][0] == "mul"
+    calls.clear()
+    seen.clear()
+    isb.bicgstabl(op, b, 2, rng=np.random.default_rng(0))
+    assert calls == ["b200_bicgstabl_solve_op"] and seen[0][0] == "mul"
+    kinds = []
+
+    class FakeLibB(FakeLib):
+        def __getattr__(self, name):
+            inner = FakeLib.__getattr__(self, name)
+
+            def f(*args):
+                for a in args:
+                    obj = getattr(a, "_obj", None)
+                    if isinstance(obj, L.BicgstablOpts):
+                        kinds.append((obj.Pl.kind, obj.l))
+                        if obj.Pl.kind == 2:
+                            C.cast(obj.Pl.diag, C.POINTER(L.LinOp)).contents.apply(None, 0x3000, 0x4000, None)
+                return inner(*args)
+            return f
+
+    monkeypatch.setattr(S, "lib", lambda: FakeLibB())
+    calls.clear()
+    seen.clear()
+    isb.bicgstabl(csr, b, 4, Pl=Pl, rng=np.random.default_rng(0))
+    assert calls == ["b200_bicgstabl_solve"] and kinds == [(2, 4)] and ("ldiv", (n,)) in seen
+    with pytest.raises(KeyError, match="inside the preconditioner"):
+        isb.bicgstabl(csr, b, Pl=isb.FunctionPrec(n, np.float64, boom_p, ctx=ctx), rng=np.random.default_rng(0))
+    monkeypatch.setattr(S, "lib", lambda: FakeLib())
     with pytest.raises(TypeError):
-        isb.minres(op, b)                            # the MINRES engine is CSR-only
+        isb.chebyshev(op, b, 1.0, 2.0)               # chebyshev! is CSR-only
 
 
 def test_partitioned_engines_world2_gloo():
@@ -881,3 +915,27 @@ def test_engine_gmres_general_matches_oracle(oracle, sim, dtype, tol):
             return sim.gmres_(x, sp.csr_matrix(A), b, restart=restart, maxiter=maxiter, orth_meth=meth, order=order,
                               split=split, **args, **kw)
         cases.case_gmres_general(oracle, run, dtype, tol)
+
+
+# ------------------------------------------------------------------------------------------ general minres! / bicgstabl!
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 2e-5)])
+def test_engine_minres_general_matches_oracle(oracle, sim, dtype, tol):
+    for order, split in ((0, 0), (1, 1)):
+        def run(x, A, b, **kw):
+            return sim.minres_(x, sp.csr_matrix(A), b, order=order, split=split, **kw)
+        cases.case_minres_general(oracle, run, dtype, tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 5e-5)])
+def test_engine_bicgstabl_general_matches_oracle(oracle, sim, dtype, tol):
+    for order, split in ((0, 0), (1, 1)):
+        def run(x, A, b, l, shadow, d, pk, **kw):
+            args = {}
+            if pk == "jac":
+                args["diag"] = d
+            if pk == "cb":
+                args["Pl"] = sp.diags(1.0 / d.astype(np.float64)).tocsr()
+            x, h = sim.bicgstabl_(x, sp.csr_matrix(A), b, l, shadow, order=order, split=split, **args, **kw)
+            return x, SimpleNamespace(iters=h.iters, mvps=h.mvps, converged=h.converged, hist=h.hist,
+                                      singular=h.singular)
+        cases.case_bicgstabl_general(oracle, run, dtype, tol)

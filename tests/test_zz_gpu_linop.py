@@ -130,7 +130,7 @@ def test_idrs_callback_preconditioner(isb, oracle):
     A = isb.B200CSR.from_scipy((sp.eye(32) * 2.0).tocsc())
     Pl = isb.FunctionPrec(32, np.float64, lambda y, x: None)
     with pytest.raises(isb.B200Error, match="unsupported preconditioner"):
-        isb.bicgstabl(A, np.ones(32), Pl=Pl)
+        isb.chebyshev(A, np.ones(32), 1.0, 3.0, Pl=Pl)
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 5e-5)])
@@ -158,3 +158,50 @@ def test_general_gmres_equals_the_specialised_engine(isb, oracle):
         x2, h2 = isb.gmres(isb.B200LinearOperator.from_csr(A), b, restart=30, maxiter=90, orth_meth=meth, log=True)
         assert h1.iters == h2.iters and h1.mvps == h2.mvps and h1.isconverged == h2.isconverged
         assert np.max(np.abs(h1["resnorm"] - h2["resnorm"])) <= 1e-9 * h1["resnorm"][0] and relerr(x2, x1) <= 1e-8
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 5e-5)])
+def test_minres_general_operator(isb, oracle, dtype, tol):
+    """minres! with a `mul!` callback (b200_minres_solve_op) against the oracle -- the case of the serial backend."""
+    def run(x, A, b, **kw):
+        csr = isb.B200CSR.from_scipy(sp.csc_matrix(A).astype(x.dtype))
+        x, h = isb.minres_(x, isb.B200LinearOperator.from_csr(csr), b, log=True, **kw)
+        return x, SimpleNamespace(iters=h.iters, mvps=h.mvps, converged=h.isconverged, hist=h["resnorm"])
+    cases.case_minres_general(oracle, run, dtype, tol)
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 2e-4)])
+def test_bicgstabl_general_operator_and_callback_preconditioner(isb, oracle, dtype, tol):
+    """bicgstabl! with `mul!` / `ldiv!` callbacks (b200_bicgstabl_solve_op; b200_bicgstabl_solve forwarding a callback Pl)
+    against the oracle with the same shadow residual -- the case of the serial backend."""
+    def run(x, A, b, l, shadow, d, pk, **kw):
+        csr = isb.B200CSR.from_scipy(sp.csc_matrix(A).astype(x.dtype))
+        jac = isb.JacobiPrec(np.asarray(d, dtype=x.dtype))
+        Pl = None if pk is None else (jac if pk == "jac" else
+                                      isb.FunctionPrec(csr.m_local, x.dtype, lambda y, v: jac.ldiv_(y, v)))
+        op = csr if pk == "cb" else isb.B200LinearOperator.from_csr(csr)
+        try:
+            x, h = isb.bicgstabl_(x, op, b, l, Pl=Pl, r_shadow=shadow, log=True, **kw)
+        except np.linalg.LinAlgError:
+            return x, SimpleNamespace(singular=True)
+        return x, SimpleNamespace(iters=h.iters, mvps=h.mvps, converged=h.isconverged, hist=h["resnorm"], singular=False)
+    cases.case_bicgstabl_general(oracle, run, dtype, tol)
+
+
+def test_general_minres_and_bicgstabl_equal_the_specialised_engines(isb, oracle):
+    rng = np.random.default_rng(SEED)
+    O = oracle.laplace_matrix(np.float64, 16, 3, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    op = isb.B200LinearOperator.from_csr(A)
+    b = rng.standard_normal(O.n)
+    x1, h1 = isb.minres(A, b, log=True)
+    x2, h2 = isb.minres(op, b, log=True)
+    assert h1.iters == h2.iters and h1.isconverged and h2.isconverged and relerr(x2, x1) <= 1e-8
+    k = min(30, h1.iters)
+    assert np.max(np.abs(h1["resnorm"][:k] - h2["resnorm"][:k])) <= 1e-9 * h1["resnorm"][0]
+    sh = rng.random(O.n)
+    x1, h1 = isb.bicgstabl(A, b, 2, r_shadow=sh, log=True)
+    x2, h2 = isb.bicgstabl(op, b, 2, r_shadow=sh, log=True)
+    assert abs(h1.iters - h2.iters) <= 1 and h1.isconverged and h2.isconverged and relerr(x2, x1) <= 1e-6
+    k = min(10, h1.iters, h2.iters)
+    assert np.max(np.abs(h1["resnorm"][:k] - h2["resnorm"][:k])) <= 1e-6 * h1["resnorm"][0]

@@ -478,3 +478,79 @@ def case_gmres_general(oracle, run, dtype, tol):
     be = (Ad @ xe).astype(dtype)
     xs, hs = run(xe.copy(), Ad, be, d.astype(dtype), None, None, 20, 60, "mgs", abstol=1e-3)
     assert hs.iters == 0 and hs.converged and np.array_equal(xs, xe)
+
+
+def case_minres_general(oracle, run, dtype, tol):
+    """the general minres! engine (csrc/minres_core.h) against the oracle's minres_ on a symmetric indefinite and on a
+    skew-symmetric operator: counts, residual history, x; maxiter; zero iterations.
+    run(x0, A, b, **kw) -> (x, outcome with iters, mvps, converged, hist)."""
+    rng = np.random.default_rng(3)
+    n = 400
+    R = sp.random(n, n, 0.02, random_state=2, format="csc")
+    S = (0.1 * (R + R.T) + sp.diags(np.where(np.arange(n) % 2 == 0, 1.0, -1.0) * np.linspace(1, 3, n))).tocsc()
+    K = sp.random(n, n, 0.02, random_state=4, format="csc")
+    K = (K - K.T).tocsc()
+    b = rng.standard_normal(n).astype(dtype)
+    for M, skew in ((S, False), (K, True)):
+        Md = M.astype(dtype)
+        for iz in (True, False):
+            x0 = np.zeros(n, dtype) if iz else rng.standard_normal(n).astype(dtype)
+            kw = dict(maxiter=80, initially_zero=iz, skew_hermitian=skew)
+            xo, ho = oracle.minres_(x0.copy(), Md, b, log=True, **kw)
+            xs, hs = run(x0.copy(), Md, b, **kw)
+            ro = np.asarray(ho["resnorm"])
+            assert abs(hs.iters - ho.iters) <= (0 if dtype == np.float64 else 1) and hs.converged == ho.isconverged
+            if hs.iters == ho.iters:
+                assert hs.mvps == ho.mvps
+            k = min(hs.iters, ho.iters, 40)
+            assert np.max(np.abs(ro[:k] - np.asarray(hs.hist)[:k])) <= tol * ro[0], (skew, iz)
+            if ho.isconverged:                                  # (a run cut by maxiter is compared through its history)
+                assert np.linalg.norm(xs - xo) <= 50 * tol * np.linalg.norm(xo), (skew, iz)
+    xo, ho = oracle.minres_(np.zeros(n, dtype), S.astype(dtype), b, log=True, maxiter=7, reltol=1e-30, initially_zero=True)
+    xs, hs = run(np.zeros(n, dtype), S.astype(dtype), b, maxiter=7, reltol=1e-30, initially_zero=True)
+    assert hs.iters == ho.iters == 7 and not hs.converged and np.linalg.norm(xs - xo) <= 50 * tol * np.linalg.norm(xo)
+    xe = rng.standard_normal(n).astype(dtype)
+    xs, hs = run(xe.copy(), S.astype(dtype), (S.astype(dtype) @ xe).astype(dtype), abstol=1e-3)
+    assert hs.iters == 0 and hs.converged and np.array_equal(xs, xe)
+
+
+def case_bicgstabl_general(oracle, run, dtype, tol):
+    """the general bicgstabl! engine (csrc/bicgstabl_core.h: callback operator, Pl as Jacobi diagonal or callback) against
+    the oracle's bicgstabl_ with the same shadow residual: l = 1, 2, 4; counts, residual history, x; the product budget;
+    the SingularException of the MR step (reference test/bicgstabl.jl:34-38).
+    run(x0, A, b, l, shadow, d, pk, **kw) -> (x, outcome with iters, mvps, converged, hist, singular)."""
+    rng = np.random.default_rng(3)
+    n = 400
+    A = (sp.random(n, n, 0.02, random_state=1, format="csc") + 4 * sp.eye(n)).tocsc()
+    d = A.diagonal().astype(dtype)
+    b = rng.standard_normal(n).astype(dtype)
+    Ad = A.astype(dtype)
+    for l in (1, 2, 4):
+        for pk in (None, "jac", "cb"):
+            for iz in (True, False):
+                sh = rng.random(n).astype(dtype)
+                x0 = np.zeros(n, dtype) if iz else rng.standard_normal(n).astype(dtype)
+                Pl = None if pk is None else oracle.JacobiPrec(d)
+                xo, ho = oracle.bicgstabl_(x0.copy(), Ad, b, l, Pl=Pl, max_mv_products=200, log=True, initial_zero=iz,
+                                           r_shadow=sh)
+                xs, hs = run(x0.copy(), Ad, b, l, sh, d, pk, max_mv_products=200, initial_zero=iz)
+                ro = np.asarray(ho["resnorm"])
+                assert not hs.singular and hs.converged == ho.isconverged
+                assert abs(hs.iters - ho.iters) <= (0 if dtype == np.float64 else 1)
+                if hs.iters == ho.iters:
+                    assert hs.mvps == ho.mvps
+                k = min(hs.iters, ho.iters)
+                scale = 10.0 ** (l - 1)                          # the MR step's normal equations lose digits with l
+                assert np.max(np.abs(ro[:k] - np.asarray(hs.hist)[:k])) <= scale * tol * ro[0], (l, pk, iz)
+                assert np.linalg.norm(xs - xo) <= 50 * tol * np.linalg.norm(xo), (l, pk, iz)
+    sh = rng.random(n).astype(dtype)
+    xo, ho = oracle.bicgstabl_(np.zeros(n, dtype), Ad, b, 2, max_mv_products=9, reltol=1e-30, log=True, initial_zero=True,
+                               r_shadow=sh)
+    xs, hs = run(np.zeros(n, dtype), Ad, b, 2, sh, d, None, max_mv_products=9, reltol=1e-30, initial_zero=True)
+    assert hs.iters == ho.iters == 3 and hs.mvps == ho.mvps == 12 and not hs.converged
+    assert np.linalg.norm(xs - xo) <= 50 * tol * np.linalg.norm(xo)
+    # exact solution after the BiCG part: rs[:, 2:end] = 0, the MR Gram matrix is singular -> SingularException
+    I = sp.identity(16, format="csc").astype(dtype)
+    xs, hs = run(np.zeros(16, dtype), I, np.ones(16, dtype), 2, np.ones(16, dtype), np.ones(16, dtype), None,
+                 initial_zero=True)
+    assert hs.singular
