@@ -277,7 +277,7 @@ template <typename T, typename B>
 int bicgstabl_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const T *diag, int64_t n, int64_t n_global,
                   T *x, const T *b, const T *shadow, int l, double abstol, double reltol, int64_t max_mv, int initial_zero,
                   int check_every, int64_t hist_cap, double *hist_host, BcgOutcome *out) {
-  if (l < 1 || l > kBcMaxL) return -2;                                      // B200_ERR_ARG
+  if (l < 1 || l > kBcMaxL) return -1;                                      // B200_ERR_INVALID (checked by the callers)
   if (reltol < 0) reltol = sqrt(eps_of<T>());                               // :183
   if (max_mv < 0) max_mv = n_global;                                        // :184
   if (!hist_host) hist_cap = 0;

@@ -102,6 +102,7 @@ struct b200_ctx {
   int64_t prof_n[4] = {0, 0, 0, 0};
   void *ws = nullptr;            // grow-only solver workspace (reused across solves: no malloc in the timed path)
   size_t ws_bytes = 0;
+  int in_callback = 0;           // > 0 while an operator / preconditioner callback runs: the workspace belongs to the caller
 };
 
 namespace b200 {
@@ -241,6 +242,11 @@ struct ProfScope {
 
 // grow-only workspace; contents are scratch (valid until the next ws_get on this context)
 inline int ws_get(b200_ctx *ctx, size_t bytes, void **out) {
+  if (ctx->in_callback) {
+    set_error("a solver was started on this context from inside an operator / preconditioner callback: the context's "
+              "workspace is in use by the outer solve (use a second context for nested solves)");
+    return B200_ERR_INVALID;
+  }
   if (bytes > ctx->ws_bytes) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->ws) cudaFree(ctx->ws);

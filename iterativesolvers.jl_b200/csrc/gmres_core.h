@@ -315,7 +315,7 @@ int gmres_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const ty
   if (reltol < 0) reltol = sqrt(eps_of<T>());                               // :187
   if (restart <= 0) restart = (int)(n_global < 20 ? n_global : 20);         // :188
   if (maxiter < 0) maxiter = n_global;                                      // :189
-  if (restart > kGmMaxRestart) return -2;                                   // B200_ERR_ARG
+  if (restart > kGmMaxRestart) return -1;                                   // B200_ERR_INVALID (checked by the callers)
   if (!hist_host) hist_cap = 0;
   if (hist_cap > maxiter) hist_cap = maxiter;                               // reserve!(history, :resnorm, maxiter) :198
   const size_t vb = ((sizeof(T) * (size_t)(n > 0 ? n : 1)) + 255) / 256 * 256;

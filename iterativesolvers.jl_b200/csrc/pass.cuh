@@ -114,7 +114,9 @@ struct CudaBackend {
   int apply(const Op *A, const void *x, void *y) {
     ProfScope prof(ctx, 0);
     if (A->csr) return spmv(ctx, A->csr, x, y);
+    ctx->in_callback += 1;
     const int st = A->fn->apply(A->fn->user, x, y, (void *)ctx->stream);
+    ctx->in_callback -= 1;
     if (st != 0) {
       set_error("operator / preconditioner callback returned %d", st);
       return B200_ERR_CALLBACK;

@@ -205,3 +205,17 @@ def test_general_minres_and_bicgstabl_equal_the_specialised_engines(isb, oracle)
     assert abs(h1.iters - h2.iters) <= 1 and h1.isconverged and h2.isconverged and relerr(x2, x1) <= 1e-6
     k = min(10, h1.iters, h2.iters)
     assert np.max(np.abs(h1["resnorm"][:k] - h2["resnorm"][:k])) <= 1e-6 * h1["resnorm"][0]
+
+
+def test_nested_solve_inside_a_callback_is_refused(isb):
+    """the context's scratch belongs to the running solve: starting another solve on the same context from inside an
+    operator callback fails loudly instead of overwriting it."""
+    n = 64
+    A = isb.B200CSR.from_scipy((sp.eye(n) * 2.0).tocsc())
+
+    def inner(y, x):
+        isb.cg_(y, A, x)
+
+    with pytest.raises(isb.B200Error, match="inside an operator"):
+        isb.cg(isb.B200LinearOperator((n, n), np.float64, inner), np.ones(n))
+    assert relerr(isb.cg(A, np.ones(n)), 0.5 * np.ones(n)) <= 1e-12
