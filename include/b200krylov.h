@@ -435,6 +435,25 @@ B200_API int b200_bicgstabl_solve_op(b200_ctx *ctx, const b200_linop *A, void *x
                                      const b200_bicgstabl_opts *opts, b200_result *res, double *resnorm_host,
                                      int64_t resnorm_cap);
 
+/* gmres_iterable! (src/gmres.jl:108-136), minres_iterable! (src/minres.jl:39-89), bicgstabl_iterator!
+ * (src/bicgstabl.jl:27-73): the resumable forms ("the iterator is the solver", docs/src/iterators.md).  Exactly one of
+ * A (device CSR) and Aop (callback operator) is non-NULL; the preconditioners travel in the option block (Identity,
+ * Jacobi or B200_PREC_CALLBACK).  Creation performs the solver's setup (initial residual, tolerance); the iterable owns
+ * its scratch, x_dev / b_dev (and r_shadow) stay the caller's.  b200_iter_next performs up to k calls of iterate()
+ * (inner iterations for gmres, outer ones -- 2 l products -- for bicgstabl), stopping at done(); k = 0 reports the state.
+ * res->iters / mvps / residual / tol / isconverged describe the iterable, res->status is 1 once done() holds, and
+ * resnorm_host (may be NULL; at most 4096 entries per call) receives the residual norms of the iterations performed by
+ * this call.  Results are identical to the one-shot *_solve_op engines for every chunking. */
+typedef struct b200_iter b200_iter;
+B200_API int b200_gmres_iter_create(b200_ctx *ctx, const b200_csr *A, const b200_linop *Aop, void *x_dev,
+                                    const void *b_dev, const b200_gmres_opts *opts, b200_iter **out);
+B200_API int b200_minres_iter_create(b200_ctx *ctx, const b200_csr *A, const b200_linop *Aop, void *x_dev,
+                                     const void *b_dev, const b200_minres_opts *opts, b200_iter **out);
+B200_API int b200_bicgstabl_iter_create(b200_ctx *ctx, const b200_csr *A, const b200_linop *Aop, void *x_dev,
+                                        const void *b_dev, const b200_bicgstabl_opts *opts, b200_iter **out);
+B200_API int b200_iter_next(b200_iter *it, int64_t k, b200_result *res, double *resnorm_host, int64_t resnorm_cap);
+B200_API int b200_iter_destroy(b200_iter *it);
+
 typedef struct {
   double tol;               /* default_tolerance(T) = eps(real(T))^(3/10)  src/lobpcg.jl:751       */
   int64_t maxiter;          /* 200   src/lobpcg.jl:865                                             */

@@ -613,6 +613,40 @@ function bicgstabl!(x::B200Vector{T}, A::Union{B200CSR{T},B200LinearOperator{T}}
     check(status)
     log ? (x, history(res, hist, abstol, reltol)) : x
 end
+# gmres_iterable! / minres_iterable! / bicgstabl_iterator! (docs/src/iterators.md): b200_*_iter_create + b200_iter_next.
+# `for (iteration, residual) in enumerate(it)` works as with the reference's iterables; x is updated in place.
+mutable struct B200Iterable{T}
+    h::Ptr{Cvoid}; ctx::Ctx; res::Result; x::B200Vector{T}; keep::Vector{Any}
+end
+function iter_finalize(it::B200Iterable)
+    it.h == C_NULL || ccall((:b200_iter_destroy, LIB), Cint, (Ptr{Cvoid},), it.h); it.h = C_NULL
+end
+function gmres_iterable!(x::B200Vector{T}, A::Union{B200CSR{T},B200LinearOperator{T}}, b::B200Vector{T};
+                         Pl = Identity(), Pr = Identity(), abstol::Real = zero(T), reltol::Real = sqrt(eps(T)),
+                         restart::Int = min(20, size(A, 2)), maxiter::Int = size(A, 2), initially_zero::Bool = false,
+                         orth_meth::OrthogonalizationMethod = ModifiedGramSchmidt()) where {T}
+    keep = Any[A, Pl, Pr, b]; r = Ref{Ptr{Cvoid}}()
+    o = GmresOpts(abstol, reltol, maxiter, restart, initially_zero, orth_code(orth_meth), 0, prec_cb(Pl, keep), prec_cb(Pr, keep))
+    csr = A isa B200CSR ? A.h : C_NULL
+    a = A isa B200LinearOperator ? (ar = Ref(linop(A)); push!(keep, ar); Base.unsafe_convert(Ptr{LinOp}, ar)) : Ptr{LinOp}(C_NULL)
+    check(ccall((:b200_gmres_iter_create, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{LinOp}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{GmresOpts}, Ref{Ptr{Cvoid}}),
+                A.ctx.h, csr, a, x.p, b.p, o, r))
+    finalizer(iter_finalize, B200Iterable{T}(r[], A.ctx, Result(), x, keep))
+end
+# minres_iterable!(x, A, b; ...) and bicgstabl_iterator!(x, A, b, l; ...): same pattern with b200_minres_iter_create
+# (Ref{MinresOpts}) / b200_bicgstabl_iter_create (Ref{BicgstablOpts}).
+function step!(it::B200Iterable, k::Integer = 1)
+    buf = Vector{Float64}(undef, min(k, 4096))
+    status = GC.@preserve it ccall((:b200_iter_next, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{Result}, Ptr{Float64}, Int64),
+                                   it.h, k, it.res, buf, length(buf))
+    status == -5 && throw(SingularException(0)); check(status)
+    resize!(buf, it.res.n_resnorm)
+end
+Base.iterate(it::B200Iterable, state = nothing) =
+    it.res.status == 1 ? nothing : (r = step!(it, 1); isempty(r) ? nothing : (r[1], nothing))   # yields the residual norm
+converged(it::B200Iterable) = it.res.isconverged != 0
+
 Base.size(A::B200LinearOperator) = (A.m, A.n)
 Base.size(A::B200LinearOperator, d::Integer) = d == 1 ? A.m : (d == 2 ? A.n : 1)
 

@@ -18,6 +18,7 @@ from .history import ConvergenceHistory  # noqa: F401
 from .generators import laplace_matrix, laplace_csr_slab, advection_dominated, mmread  # noqa: F401
 from .solvers import (cg, cg_, chebyshev, chebyshev_, gmres, gmres_, minres, minres_, bicgstabl, bicgstabl_, lobpcg,  # noqa: F401
                       LOBPCGResults, orthogonalize_and_normalize_, hessenberg_ldiv_,
-                      cg_iterator_, CGIterable, CGStateVariables,
+                      cg_iterator_, CGIterable, CGStateVariables, KrylovIterable, gmres_iterable_, minres_iterable_,
+                      bicgstabl_iterator_,
                       qmr, qmr_, lsqr, lsqr_, lsmr, lsmr_, idrs, idrs_, LobpcgConstraint, svdl, SVD,
                       PartialFactorization)

@@ -268,46 +268,84 @@ struct BcgMr {
 struct BcgOutcome {
   int64_t iters, mvps, n_hist;
   double residual, tol;
-  int converged, breakdown, singular;
+  int converged, breakdown, singular, done;
 };
 
-// A: the operator; Pl: preconditioner callback or nullptr; diag: Jacobi diagonal or nullptr.  shadow: r_shadow (:38,
-// drawn by the caller).
+// ---- the driver in resumable pieces: scratch layout, setup (bicgstabl_iterator! :27-73), advance (up to k outer
+// iterations :79-134), collect.  bicgstabl_run is the one-shot form; the iterator of the C ABI keeps the scratch.
+template <typename T>
+struct BcgLayout {
+  T *rs, *us, *tmp;
+  int64_t ld;
+  BcgScal *s;
+  double *hist;
+  int64_t hist_cap;
+};
+inline size_t bcg_vec_bytes(size_t elem, int64_t n) { return ((elem * (size_t)(n > 0 ? n : 1)) + 255) / 256 * 256; }
+template <typename T>
+size_t bicgstabl_ws_bytes(int64_t n, int l, int64_t hist_cap) {
+  return bcg_vec_bytes(sizeof(T), n) * (size_t)(2 * (l + 1) + 1) + (sizeof(BcgScal) + 255) / 256 * 256 +
+         ((sizeof(double) * (size_t)(hist_cap > 0 ? hist_cap : 1)) + 255) / 256 * 256;
+}
+template <typename T>
+BcgLayout<T> bicgstabl_layout(void *ws, int64_t n, int l, int64_t hist_cap) {
+  const size_t vb = bcg_vec_bytes(sizeof(T), n);
+  BcgLayout<T> L;
+  char *p = (char *)ws;
+  L.rs = (T *)p; p += vb * (size_t)(l + 1);
+  L.us = (T *)p; p += vb * (size_t)(l + 1);
+  L.tmp = (T *)p; p += vb;
+  L.ld = (int64_t)(vb / sizeof(T));
+  L.s = (BcgScal *)p; p += (sizeof(BcgScal) + 255) / 256 * 256;
+  L.hist = hist_cap > 0 ? (double *)p : nullptr;
+  L.hist_cap = hist_cap > 0 ? hist_cap : 0;
+  return L;
+}
+
+// A: the operator; Pl: preconditioner callback or nullptr; diag: Jacobi diagonal or nullptr.
 template <typename T, typename B>
-int bicgstabl_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const T *diag, int64_t n, int64_t n_global,
-                  T *x, const T *b, const T *shadow, int l, double abstol, double reltol, int64_t max_mv, int initial_zero,
-                  int check_every, int64_t hist_cap, double *hist_host, BcgOutcome *out) {
+int bicgstabl_setup(B &be, const typename B::Op *A, const typename B::Op *Pl, const T *diag, const BcgLayout<T> &L,
+                    int64_t n, int64_t n_global, T *x, const T *b, int l, double abstol, double reltol, int64_t max_mv,
+                    int initial_zero) {
   if (l < 1 || l > kBcMaxL) return -1;                                      // B200_ERR_INVALID (checked by the callers)
   if (reltol < 0) reltol = sqrt(eps_of<T>());                               // :183
   if (max_mv < 0) max_mv = n_global;                                        // :184
-  if (!hist_host) hist_cap = 0;
-  if (hist_cap > max_mv) hist_cap = max_mv;                                 // reserve!(history, :resnorm, max_mv_products) :194
-  const size_t vb = ((sizeof(T) * (size_t)(n > 0 ? n : 1)) + 255) / 256 * 256;
-  const int64_t ld = (int64_t)(vb / sizeof(T));
-  const size_t sb = (sizeof(BcgScal) + 255) / 256 * 256;
-  const size_t hb = ((sizeof(double) * (size_t)(hist_cap > 0 ? hist_cap : 1)) + 255) / 256 * 256;
-  void *ws = nullptr;
-  int st = be.workspace(vb * (size_t)(2 * (l + 1) + 1) + sb + hb, &ws);
-  if (st) return st;
-  char *p = (char *)ws;
-  T *rs = (T *)p; p += vb * (size_t)(l + 1);
-  T *us = (T *)p; p += vb * (size_t)(l + 1);
-  T *tmp = (T *)p; p += vb;
-  BcgScal *s = (BcgScal *)p; p += sb;
-  double *hist = hist_cap ? (double *)p : nullptr;
-
   BcgScal h;
   memset(&h, 0, sizeof(h));
   h.abstol = abstol;
   h.reltol = reltol;
   h.max_mv = max_mv;
   h.l = l;
-  h.hist = hist;
-  h.hist_cap = hist_cap;
+  h.hist = L.hist;
+  h.hist_cap = L.hist_cap;
   h.mv_products = initial_zero ? 0 : 1;                                     // :45-53
+  int st;
+  T *rs = L.rs, *us = L.us, *tmp = L.tmp;
+  BcgScal *s = L.s;
+  const size_t vb = bcg_vec_bytes(sizeof(T), n);
   if ((st = be.to_device(s, &h, sizeof(h)))) return st;
   if ((st = be.zero(us, vb * (size_t)(l + 1)))) return st;                  // zeros(T, n, l + 1) :40
+  if (!initial_zero && (st = be.apply(A, x, tmp))) return st;               // mul!(residual, A, x) :49
+  if (Pl) {
+    if ((st = be.pass(BcgInit<T>{b, initial_zero ? nullptr : tmp, nullptr, us, s, 0}, n))) return st;   // us[:, 1] as scratch
+    if ((st = be.apply(Pl, us, rs))) return st;                             // ldiv!(Pl, residual) :55
+    if ((st = be.zero(us, sizeof(T) * (size_t)n))) return st;
+    return be.pass(BcgNorm0<T>{rs, s}, n);
+  }
+  return be.pass(BcgInit<T>{b, initial_zero ? nullptr : tmp, diag, rs, s, 1}, n);
+}
 
+// up to k more outer iterations (k < 0: until done)
+template <typename T, typename B>
+int bicgstabl_advance(B &be, const typename B::Op *A, const typename B::Op *Pl, const T *diag, const BcgLayout<T> &L,
+                      int64_t n, T *x, const T *shadow, int l, int64_t k, int check_every) {
+  int st;
+  T *rs = L.rs, *us = L.us, *tmp = L.tmp;
+  const int64_t ld = L.ld;
+  BcgScal *s = L.s;
+  BcgScal h;
+  if ((st = be.to_host(&h, s, sizeof(h)))) return st;
+  if (h.done) return 0;
   // y = Pl \ (A v): callback through tmp, Jacobi in place, Identity nothing :97-98 / :107-108
   auto apply_prec_A = [&](const T *v, T *y) -> int {
     int s2;
@@ -319,25 +357,16 @@ int bicgstabl_run(B &be, const typename B::Op *A, const typename B::Op *Pl, cons
     if (diag) return be.pass(BcgJacobi<T>{y, diag, s}, n);
     return 0;
   };
-
-  if (!initial_zero && (st = be.apply(A, x, tmp))) return st;               // mul!(residual, A, x) :49
-  if (Pl) {
-    if ((st = be.pass(BcgInit<T>{b, initial_zero ? nullptr : tmp, nullptr, us, s, 0}, n))) return st;   // us[:, 1] as scratch
-    if ((st = be.apply(Pl, us, rs))) return st;                             // ldiv!(Pl, residual) :55
-    if ((st = be.zero(us, sizeof(T) * (size_t)n))) return st;
-    if ((st = be.pass(BcgNorm0<T>{rs, s}, n))) return st;
-  } else {
-    if ((st = be.pass(BcgInit<T>{b, initial_zero ? nullptr : tmp, diag, rs, s, 1}, n))) return st;
-  }
-
+  const int64_t left_mv = h.max_mv - h.mv_products;
+  const int64_t left = left_mv > 0 ? (left_mv + 2 * l - 1) / (2 * l) : 0;   // outer iterations until the product budget ends
+  const int64_t todo = (k < 0 || k > left) ? left : k;
   if (check_every <= 0) check_every = 4;
-  const int64_t max_outer = max_mv > 0 ? (max_mv + 2 * l - 1) / (2 * l) + 1 : 1;
   int64_t enqueued = 0;
   for (;;) {
     int done = 0;
     if ((st = be.read_flag(&s->done, &done))) return st;
-    if (done || enqueued >= max_outer) break;
-    const int64_t batch = check_every < max_outer - enqueued ? check_every : max_outer - enqueued;
+    if (done || enqueued >= todo) break;
+    const int64_t batch = check_every < todo - enqueued ? check_every : todo - enqueued;
     for (int64_t q = 0; q < batch; ++q) {
       for (int j = 1; j <= l; ++j) {                                                                       // :88
         T *rj = rs + (int64_t)j * ld, *rjm = rs + (int64_t)(j - 1) * ld;
@@ -356,7 +385,14 @@ int bicgstabl_run(B &be, const typename B::Op *A, const typename B::Op *Pl, cons
     }
     enqueued += batch;
   }
-  if ((st = be.to_host(&h, s, sizeof(h)))) return st;
+  return 0;
+}
+
+template <typename T, typename B>
+int bicgstabl_collect(B &be, const BcgLayout<T> &L, double *hist_host, BcgOutcome *out) {
+  int st;
+  BcgScal h;
+  if ((st = be.to_host(&h, L.s, sizeof(h)))) return st;
   out->iters = h.iters;
   out->mvps = h.mv_products;                                                // history.mvps = iterable.mv_products :207
   out->residual = h.residual;
@@ -364,9 +400,33 @@ int bicgstabl_run(B &be, const typename B::Op *A, const typename B::Op *Pl, cons
   out->converged = h.residual <= h.tol;                                     // converged :75
   out->breakdown = h.breakdown;
   out->singular = h.singular;
-  out->n_hist = h.n_hist < hist_cap ? h.n_hist : hist_cap;
-  if (out->n_hist > 0 && (st = be.to_host(hist_host, hist, sizeof(double) * (size_t)out->n_hist))) return st;
+  out->done = h.done;
+  out->n_hist = h.n_hist < L.hist_cap ? h.n_hist : L.hist_cap;
+  if (hist_host && out->n_hist > 0 && (st = be.to_host(hist_host, L.hist, sizeof(double) * (size_t)out->n_hist))) return st;
   return 0;
+}
+template <typename B>
+int bicgstabl_reset_window(B &be, BcgScal *s) {
+  const long long zero = 0;
+  return be.to_device(&s->n_hist, &zero, sizeof(zero));
+}
+
+// shadow: r_shadow (:38, drawn by the caller).
+template <typename T, typename B>
+int bicgstabl_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const T *diag, int64_t n, int64_t n_global,
+                  T *x, const T *b, const T *shadow, int l, double abstol, double reltol, int64_t max_mv, int initial_zero,
+                  int check_every, int64_t hist_cap, double *hist_host, BcgOutcome *out) {
+  if (l < 1 || l > kBcMaxL) return -1;                                      // B200_ERR_INVALID (checked by the callers)
+  if (max_mv < 0) max_mv = n_global;
+  if (!hist_host) hist_cap = 0;
+  if (hist_cap > max_mv) hist_cap = max_mv;                                 // reserve!(history, :resnorm, max_mv_products) :194
+  void *ws = nullptr;
+  int st = be.workspace(bicgstabl_ws_bytes<T>(n, l, hist_cap), &ws);
+  if (st) return st;
+  const BcgLayout<T> L = bicgstabl_layout<T>(ws, n, l, hist_cap);
+  if ((st = bicgstabl_setup<T>(be, A, Pl, diag, L, n, n_global, x, b, l, abstol, reltol, max_mv, initial_zero))) return st;
+  if ((st = bicgstabl_advance<T>(be, A, Pl, diag, L, n, x, shadow, l, -1, check_every))) return st;
+  return bicgstabl_collect<T>(be, L, hist_host, out);
 }
 
 }  // namespace b200

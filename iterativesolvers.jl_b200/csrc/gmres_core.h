@@ -303,37 +303,73 @@ B200_HD void gm_step(GmScal *q) {
 struct GmresOutcome {
   int64_t iters, mvps, n_hist;
   double residual, tol;
-  int converged, breakdown;
+  int converged, breakdown, done, pad;
 };
 
-// A: the operator.  Pl / Pr: preconditioner callbacks (y = P \ x) or nullptr; pl_diag / pr_diag: Jacobi diagonals or
-// nullptr (Identity when both are null on a side).
-template <typename T, typename B>
-int gmres_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const typename B::Op *Pr, const T *pl_diag,
-              const T *pr_diag, int64_t n, int64_t n_global, T *x, const T *b, double abstol, double reltol, int restart,
-              int64_t maxiter, int initially_zero, int orth_meth, int64_t hist_cap, double *hist_host, GmresOutcome *out) {
-  if (reltol < 0) reltol = sqrt(eps_of<T>());                               // :187
-  if (restart <= 0) restart = (int)(n_global < 20 ? n_global : 20);         // :188
-  if (maxiter < 0) maxiter = n_global;                                      // :189
-  if (restart > kGmMaxRestart) return -1;                                   // B200_ERR_INVALID (checked by the callers)
-  if (!hist_host) hist_cap = 0;
-  if (hist_cap > maxiter) hist_cap = maxiter;                               // reserve!(history, :resnorm, maxiter) :198
-  const size_t vb = ((sizeof(T) * (size_t)(n > 0 ? n : 1)) + 255) / 256 * 256;
-  const int64_t ld = (int64_t)(vb / sizeof(T));
-  const size_t sb = (sizeof(GmScal) + 255) / 256 * 256;
-  const size_t hb = ((sizeof(double) * (size_t)(hist_cap > 0 ? hist_cap : 1)) + 255) / 256 * 256;
-  void *ws = nullptr;
-  int st = be.workspace(vb * (size_t)(restart + 3) + sb + hb, &ws);
-  if (st) return st;
+// ---- the driver in resumable pieces: scratch layout, setup (gmres_iterable! :108-136), advance (up to k calls of
+// iterate :57-106), collect.  gmres_run is the one-shot form; the iterator of the C ABI keeps the scratch between calls.
+template <typename T>
+struct GmresLayout {
+  T *V, *t1, *t2;
+  int64_t ld;
+  GmScal *s;
+  double *hist;
+  int64_t hist_cap;
+};
+inline size_t gm_vec_bytes(size_t elem, int64_t n) { return ((elem * (size_t)(n > 0 ? n : 1)) + 255) / 256 * 256; }
+template <typename T>
+size_t gmres_ws_bytes(int64_t n, int restart, int64_t hist_cap) {
+  return gm_vec_bytes(sizeof(T), n) * (size_t)(restart + 3) + (sizeof(GmScal) + 255) / 256 * 256 +
+         ((sizeof(double) * (size_t)(hist_cap > 0 ? hist_cap : 1)) + 255) / 256 * 256;
+}
+template <typename T>
+GmresLayout<T> gmres_layout(void *ws, int64_t n, int restart, int64_t hist_cap) {
+  const size_t vb = gm_vec_bytes(sizeof(T), n);
+  GmresLayout<T> L;
   char *p = (char *)ws;
-  T *V = (T *)p; p += vb * (size_t)(restart + 1);
-  T *t1 = (T *)p; p += vb;
-  T *t2 = (T *)p; p += vb;
-  GmScal *s = (GmScal *)p; p += sb;
-  double *hist = hist_cap ? (double *)p : nullptr;
-  auto col = [&](int j) { return V + (int64_t)j * ld; };
-  const bool has_pr = Pr != nullptr || pr_diag != nullptr;
+  L.V = (T *)p; p += vb * (size_t)(restart + 1);
+  L.t1 = (T *)p; p += vb;
+  L.t2 = (T *)p; p += vb;
+  L.ld = (int64_t)(vb / sizeof(T));
+  L.s = (GmScal *)p; p += (sizeof(GmScal) + 255) / 256 * 256;
+  L.hist = hist_cap > 0 ? (double *)p : nullptr;
+  L.hist_cap = hist_cap > 0 ? hist_cap : 0;
+  return L;
+}
 
+// The operators of one solve: A; Pl / Pr: preconditioner callbacks (y = P \ x) or nullptr; pl_diag / pr_diag: Jacobi
+// diagonals or nullptr (Identity when both are null on a side).
+template <typename T, typename B>
+struct GmresOps {
+  const typename B::Op *A, *Pl, *Pr;
+  const T *pl_diag, *pr_diag;
+};
+
+// init! :235-255
+template <typename T, typename B>
+int gmres_init_residual(B &be, const GmresOps<T, B> &op, const GmresLayout<T> &L, int64_t n, const T *x, const T *b,
+                        bool zero) {
+  int s2;
+  T *v0 = L.V, *t1 = L.t1, *t2 = L.t2;
+  GmScal *s = L.s;
+  if (!zero && (s2 = be.apply(op.A, x, t1))) return s2;                     // mul!(Ax, A, x) :245
+  if (op.Pl) {
+    if ((s2 = be.pass(GmResidual<T>{b, zero ? nullptr : t1, nullptr, t2, s, 0}, n))) return s2;
+    if ((s2 = be.apply(op.Pl, t2, v0))) return s2;                          // ldiv!(Pl, first_col) :249
+    if ((s2 = be.pass(GmNorm<T>{v0, s}, n))) return s2;
+  } else {
+    if ((s2 = be.pass(GmResidual<T>{b, zero ? nullptr : t1, op.pl_diag, v0, s, 1}, n))) return s2;
+  }
+  return be.pass(GmScale<T>{v0, &s->beta, (T)0}, n);                        // first_col .*= inv(beta) :253
+}
+
+template <typename T, typename B>
+int gmres_setup(B &be, const GmresOps<T, B> &op, const GmresLayout<T> &L, int64_t n, int64_t n_global, T *x, const T *b,
+                double abstol, double reltol, int restart, int64_t maxiter, int initially_zero, int64_t *mv_products) {
+  if (reltol < 0) reltol = sqrt(eps_of<T>());                               // :187
+  if (maxiter < 0) maxiter = n_global;                                      // :189
+  if (restart < 1 || restart > kGmMaxRestart) return -1;                    // B200_ERR_INVALID (checked by the callers)
+  int st;
   {
     std::unique_ptr<GmScal> h(new GmScal);
     memset(h.get(), 0, sizeof(GmScal));
@@ -342,30 +378,31 @@ int gmres_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const ty
     h->abstol = abstol;
     h->reltol = reltol;
     h->maxiter = maxiter;
-    h->hist = hist;
-    h->hist_cap = hist_cap;
+    h->hist = L.hist;
+    h->hist_cap = L.hist_cap;
     h->k = 1;
     h->restart = restart;
     h->first = 1;
-    if ((st = be.to_device(s, h.get(), sizeof(GmScal)))) return st;
+    if ((st = be.to_device(L.s, h.get(), sizeof(GmScal)))) return st;
   }
-  if ((st = be.zero(V, vb * (size_t)(restart + 1)))) return st;            // zeros(T, n, order + 1) :13
+  if ((st = be.zero(L.V, gm_vec_bytes(sizeof(T), n) * (size_t)(restart + 1)))) return st;   // zeros(T, n, order + 1) :13
+  *mv_products = initially_zero ? 1 : 0;                                    // :122 (sic)
+  return gmres_init_residual<T, B>(be, op, L, n, x, b, initially_zero != 0);   // :126
+}
 
-  int64_t mv_products = initially_zero ? 1 : 0;                             // :122 (sic)
+// up to kmax more inner iterations (kmax < 0: until done); *mv_products is advanced by the products performed
+template <typename T, typename B>
+int gmres_advance(B &be, const GmresOps<T, B> &op, const GmresLayout<T> &L, int64_t n, T *x, const T *b, int orth_meth,
+                  int64_t kmax, int64_t *mv_products) {
+  T *V = L.V, *t1 = L.t1, *t2 = L.t2;
+  const int64_t ld = L.ld;
+  GmScal *s = L.s;
+  const typename B::Op *A = op.A, *Pl = op.Pl, *Pr = op.Pr;
+  const T *pl_diag = op.pl_diag, *pr_diag = op.pr_diag;
+  auto col = [&](int j) { return V + (int64_t)j * ld; };
+  const bool has_pr = Pr != nullptr || pr_diag != nullptr;
+  int st;
 
-  auto init = [&](bool zero) -> int {                                       // init! :235-255
-    int s2;
-    T *v0 = col(0);
-    if (!zero && (s2 = be.apply(A, x, t1))) return s2;                      // mul!(Ax, A, x) :245
-    if (Pl) {
-      if ((s2 = be.pass(GmResidual<T>{b, zero ? nullptr : t1, nullptr, t2, s, 0}, n))) return s2;
-      if ((s2 = be.apply(Pl, t2, v0))) return s2;                           // ldiv!(Pl, first_col) :249
-      if ((s2 = be.pass(GmNorm<T>{v0, s}, n))) return s2;
-    } else {
-      if ((s2 = be.pass(GmResidual<T>{b, zero ? nullptr : t1, pl_diag, v0, s, 1}, n))) return s2;
-    }
-    return be.pass(GmScale<T>{v0, &s->beta, (T)0}, n);                      // first_col .*= inv(beta) :253
-  };
   auto apply_prec = [&](const typename B::Op *P, const T *diag, const T *in, T *out) -> int {   // out = P \ in (out != in for callbacks)
     if (P) return be.apply(P, in, out);
     return be.pass(GmJacobi<T>{in, diag, out}, n);
@@ -452,13 +489,13 @@ int gmres_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const ty
     return 0;
   };
 
-  if ((st = init(initially_zero != 0))) return st;                          // :126
-  int flags = 0;
+  int flags = 0, k = 1;
   if ((st = be.read_flag(&s->flags, &flags))) return st;
-  int k = 1;
-  while (!(flags & GM_DONE)) {                                              // :59
+  if ((st = be.read_flag(&s->k, &k))) return st;                            // position inside the restart cycle
+  int64_t performed = 0;
+  while (!(flags & GM_DONE) && (kmax < 0 || performed < kmax)) {            // :59
     if ((st = expand(k))) return st;                                        // :63
-    mv_products += 1;                                                       // :65
+    *mv_products += 1;                                                      // :65
     if ((st = orth(k))) return st;                                          // :68-73
     if ((st = be.scalar(ScalarStep<GmScal, gm_step>{s}))) return st;
     if ((st = be.read_flag(&s->flags, &flags))) return st;
@@ -466,25 +503,59 @@ int gmres_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const ty
       if ((st = update_solution(k))) return st;                             // :85-88 (m = k columns)
       k = 1;
       if (flags & GM_REINIT) {
-        if ((st = init(false))) return st;                                  // :96-99
-        mv_products += 1;                                                   // :101
+        if ((st = gmres_init_residual<T, B>(be, op, L, n, x, b, false))) return st;   // :96-99
+        *mv_products += 1;                                                  // :101
       }
     } else {
       k += 1;
     }
+    performed += 1;
     if (flags & GM_BREAKDOWN) break;
   }
+  return 0;
+}
+
+template <typename T, typename B>
+int gmres_collect(B &be, const GmresLayout<T> &L, int64_t mv_products, double *hist_host, GmresOutcome *out) {
+  int st;
   std::unique_ptr<GmScal> h(new GmScal);
-  if ((st = be.to_host(h.get(), s, sizeof(GmScal)))) return st;
+  if ((st = be.to_host(h.get(), L.s, sizeof(GmScal)))) return st;
   out->iters = h->iteration;
   out->mvps = mv_products;                                                  // history.mvps = iterable.mv_products :210
   out->residual = h->current;
   out->tol = h->tol;
   out->converged = h->current <= h->tol;                                    // :218
   out->breakdown = (h->flags & GM_BREAKDOWN) != 0;
-  out->n_hist = h->n_hist < hist_cap ? h->n_hist : hist_cap;
-  if (out->n_hist > 0 && (st = be.to_host(hist_host, hist, sizeof(double) * (size_t)out->n_hist))) return st;
+  out->done = (h->flags & GM_DONE) != 0;
+  out->n_hist = h->n_hist < L.hist_cap ? h->n_hist : L.hist_cap;
+  if (hist_host && out->n_hist > 0 && (st = be.to_host(hist_host, L.hist, sizeof(double) * (size_t)out->n_hist))) return st;
   return 0;
+}
+template <typename B>
+int gmres_reset_window(B &be, GmScal *s) {
+  const long long zero = 0;
+  return be.to_device(&s->n_hist, &zero, sizeof(zero));
+}
+
+template <typename T, typename B>
+int gmres_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const typename B::Op *Pr, const T *pl_diag,
+              const T *pr_diag, int64_t n, int64_t n_global, T *x, const T *b, double abstol, double reltol, int restart,
+              int64_t maxiter, int initially_zero, int orth_meth, int64_t hist_cap, double *hist_host, GmresOutcome *out) {
+  if (restart <= 0) restart = (int)(n_global < 20 ? n_global : 20);         // :188
+  if (maxiter < 0) maxiter = n_global;                                      // :189
+  if (restart > kGmMaxRestart) return -1;                                   // B200_ERR_INVALID (checked by the callers)
+  if (!hist_host) hist_cap = 0;
+  if (hist_cap > maxiter) hist_cap = maxiter;                               // reserve!(history, :resnorm, maxiter) :198
+  void *ws = nullptr;
+  int st = be.workspace(gmres_ws_bytes<T>(n, restart, hist_cap), &ws);
+  if (st) return st;
+  const GmresLayout<T> L = gmres_layout<T>(ws, n, restart, hist_cap);
+  const GmresOps<T, B> op{A, Pl, Pr, pl_diag, pr_diag};
+  int64_t mv_products = 0;
+  if ((st = gmres_setup<T, B>(be, op, L, n, n_global, x, b, abstol, reltol, restart, maxiter, initially_zero, &mv_products)))
+    return st;
+  if ((st = gmres_advance<T, B>(be, op, L, n, x, b, orth_meth, -1, &mv_products))) return st;
+  return gmres_collect<T, B>(be, L, mv_products, hist_host, out);
 }
 
 }  // namespace b200

@@ -200,30 +200,43 @@ struct MinresP3 {
 struct MinresOutcome {
   int64_t iters, mvps, n_hist;
   double residual, tol;
-  int converged, breakdown;
+  int converged, breakdown, done, pad;
 };
 
+// ---- the driver, in resumable pieces: layout of the scratch, setup (minres_iterable! :39-89), advance (up to k calls of
+// iterate :97-159), collect.  minres_run is the one-shot form; the iterator of the C ABI keeps the scratch between calls.
+template <typename T>
+struct MinresLayout {
+  T *v[3], *w[3];              // roles at iteration 1: v[0] = v_prev, v[1] = v_curr, v[2] = v_next (same for w)
+  MinresScal *s;
+  double *hist;
+  int64_t hist_cap;
+};
+
+inline size_t minres_vec_bytes(size_t elem, int64_t n) { return ((elem * (size_t)(n > 0 ? n : 1)) + 255) / 256 * 256; }
+template <typename T>
+size_t minres_ws_bytes(int64_t n, int64_t hist_cap) {
+  return 6 * minres_vec_bytes(sizeof(T), n) + 512 + ((sizeof(double) * (size_t)(hist_cap > 0 ? hist_cap : 1)) + 255) / 256 * 256;
+}
+template <typename T>
+MinresLayout<T> minres_layout(void *ws, int64_t n, int64_t hist_cap) {
+  static_assert(sizeof(MinresScal) <= 512, "MinresScal outgrew its slot");
+  const size_t vb = minres_vec_bytes(sizeof(T), n);
+  MinresLayout<T> L;
+  char *p = (char *)ws;
+  for (int i = 0; i < 3; ++i) { L.v[i] = (T *)p; p += vb; }
+  for (int i = 0; i < 3; ++i) { L.w[i] = (T *)p; p += vb; }
+  L.s = (MinresScal *)p; p += 512;
+  L.hist = hist_cap > 0 ? (double *)p : nullptr;
+  L.hist_cap = hist_cap > 0 ? hist_cap : 0;
+  return L;
+}
+
 template <typename T, typename B>
-int minres_run(B &be, const typename B::Op *A, int64_t n, int64_t n_global, T *x, const T *b, double abstol,
-               double reltol, int64_t maxiter, int initially_zero, int skew_hermitian, int check_every, int64_t hist_cap,
-               double *hist_host, MinresOutcome *out) {
+int minres_setup(B &be, const typename B::Op *A, const MinresLayout<T> &L, int64_t n, int64_t n_global, T *x, const T *b,
+                 double abstol, double reltol, int64_t maxiter, int initially_zero, int skew_hermitian, int64_t *mvps0) {
   if (reltol < 0) reltol = sqrt(eps_of<T>());                               // :205
   if (maxiter < 0) maxiter = n_global;                                      // :206
-  if (!hist_host) hist_cap = 0;
-  if (hist_cap > maxiter) hist_cap = maxiter;                               // reserve!(history, :resnorm, maxiter) :212
-  const size_t vb = ((sizeof(T) * (size_t)(n > 0 ? n : 1)) + 255) / 256 * 256;
-  const size_t hb = ((sizeof(double) * (size_t)(hist_cap > 0 ? hist_cap : 1)) + 255) / 256 * 256;
-  void *ws = nullptr;
-  int st = be.workspace(6 * vb + 512 + hb, &ws);
-  if (st) return st;
-  char *p = (char *)ws;
-  T *v[3], *w[3];
-  for (int i = 0; i < 3; ++i) { v[i] = (T *)p; p += vb; }
-  for (int i = 0; i < 3; ++i) { w[i] = (T *)p; p += vb; }
-  MinresScal *s = (MinresScal *)p; p += 512;
-  static_assert(sizeof(MinresScal) <= 512, "MinresScal outgrew its slot");
-  double *hist = hist_cap ? (double *)p : nullptr;
-
   MinresScal h;
   memset(&h, 0, sizeof(h));
   h.abstol = abstol;
@@ -232,49 +245,98 @@ int minres_run(B &be, const typename B::Op *A, int64_t n, int64_t n_global, T *x
   h.iteration = 1;
   h.stamp = -1;
   h.c_prev = h.c_curr = 1.0;                                                // :77-78
-  h.hist = hist;
-  h.hist_cap = hist_cap;
+  h.hist = L.hist;
+  h.hist_cap = L.hist_cap;
   h.skew = skew_hermitian != 0;
-  if ((st = be.to_device(s, &h, sizeof(h)))) return st;
-
-  // roles: v[0] = v_prev, v[1] = v_curr, v[2] = v_next (same for w)
-  int64_t mvps0 = 0;
+  int st;
+  if ((st = be.to_device(L.s, &h, sizeof(h)))) return st;
+  *mvps0 = 0;
   if (!initially_zero) {                                                    // :58-63
-    if ((st = be.apply(A, x, v[2]))) return st;
-    mvps0 = 1;
+    if ((st = be.apply(A, x, L.v[2]))) return st;
+    *mvps0 = 1;
   }
-  if ((st = be.pass(MinresInit<T>{b, initially_zero ? nullptr : v[2], v[1], s}, n))) return st;
-  if ((st = be.pass(MinresScaleV<T>{v[1], s, (T)0}, n))) return st;
+  if ((st = be.pass(MinresInit<T>{b, initially_zero ? nullptr : L.v[2], L.v[1], L.s}, n))) return st;
+  return be.pass(MinresScaleV<T>{L.v[1], L.s, (T)0}, n);
+}
 
+// up to k more iterations (k < 0: until done).  Everything the loop needs besides the scratch is read back from the device.
+template <typename T, typename B>
+int minres_advance(B &be, const typename B::Op *A, const MinresLayout<T> &L, int64_t n, T *x, int64_t k, int check_every) {
+  int st;
+  MinresScal h;
+  if ((st = be.to_host(&h, L.s, sizeof(h)))) return st;
+  if (h.done) return 0;
+  const int64_t it0 = h.iteration - 1;                                      // iterations performed so far
+  const int64_t left = h.maxiter - it0;
+  const int64_t todo = (k < 0 || k > left) ? left : k;
+  T *v[3], *w[3];
+  for (int i = 0; i < 3; ++i) {                                             // the pointer rotation :147-148, it0 times
+    v[i] = L.v[(i + it0) % 3];
+    w[i] = L.w[(i + it0) % 3];
+  }
   if (check_every <= 0) check_every = 16;
   int64_t enqueued = 0;
   for (;;) {
     int done = 0;
-    if ((st = be.read_flag(&s->done, &done))) return st;
-    if (done || enqueued >= maxiter) break;
-    const int64_t batch = check_every < maxiter - enqueued ? check_every : maxiter - enqueued;
+    if ((st = be.read_flag(&L.s->done, &done))) return st;
+    if (done || enqueued >= todo) break;
+    const int64_t batch = check_every < todo - enqueued ? check_every : todo - enqueued;
     for (int64_t q = 0; q < batch; ++q) {
-      const long long me = (long long)(enqueued + q);
+      const long long me = (long long)(it0 + enqueued + q);
       if ((st = be.apply(A, v[1], v[2]))) return st;                                             // S  :104
-      if ((st = be.pass(MinresP1<T>{v[2], v[0], v[1], s, (T)0, 0}, n))) return st;                // P1
-      if ((st = be.pass(MinresP2<T>{v[2], v[1], s, me, (T)0}, n))) return st;                     // P2
-      MinresP3<T> p3{v[2], w[2], x, v[1], w[1], w[0], s, me, (T)0, (T)0, (T)0, (T)0, (T)0, 0, 0};
+      if ((st = be.pass(MinresP1<T>{v[2], v[0], v[1], L.s, (T)0, 0}, n))) return st;              // P1
+      if ((st = be.pass(MinresP2<T>{v[2], v[1], L.s, me, (T)0}, n))) return st;                   // P2
+      MinresP3<T> p3{v[2], w[2], x, v[1], w[1], w[0], L.s, me, (T)0, (T)0, (T)0, (T)0, (T)0, 0, 0};
       if ((st = be.pass(p3, n))) return st;                                                      // P3
       T *t = v[0]; v[0] = v[1]; v[1] = v[2]; v[2] = t;                                           // :147
       t = w[0]; w[0] = w[1]; w[1] = w[2]; w[2] = t;                                              // :148
     }
     enqueued += batch;
   }
-  if ((st = be.to_host(&h, s, sizeof(h)))) return st;
+  return 0;
+}
+
+// state of the iteration; the history entries recorded since hist_from (an iteration count) go to hist_host
+template <typename T, typename B>
+int minres_collect(B &be, const MinresLayout<T> &L, int64_t mvps0, double *hist_host, MinresOutcome *out) {
+  int st;
+  MinresScal h;
+  if ((st = be.to_host(&h, L.s, sizeof(h)))) return st;
   out->iters = h.iteration - 1;
   out->mvps = mvps0 + (h.iteration - 1);                                    // nextiter!(history, mvps = 1) :227
   out->residual = h.resnorm;
   out->tol = h.tol;
   out->converged = h.resnorm <= h.tol;                                      // converged :91
   out->breakdown = h.breakdown;
-  out->n_hist = (h.iteration - 1) < hist_cap ? (h.iteration - 1) : hist_cap;
-  if (out->n_hist > 0 && (st = be.to_host(hist_host, hist, sizeof(double) * (size_t)out->n_hist))) return st;
+  out->done = h.done;
+  out->n_hist = h.n_hist < L.hist_cap ? h.n_hist : L.hist_cap;
+  if (hist_host && out->n_hist > 0 && (st = be.to_host(hist_host, L.hist, sizeof(double) * (size_t)out->n_hist))) return st;
   return 0;
+}
+
+// start a new history window (the iterator returns the residuals of each call separately)
+template <typename B>
+int minres_reset_window(B &be, MinresScal *s) {
+  const long long zero = 0;
+  return be.to_device(&s->n_hist, &zero, sizeof(zero));
+}
+
+template <typename T, typename B>
+int minres_run(B &be, const typename B::Op *A, int64_t n, int64_t n_global, T *x, const T *b, double abstol,
+               double reltol, int64_t maxiter, int initially_zero, int skew_hermitian, int check_every, int64_t hist_cap,
+               double *hist_host, MinresOutcome *out) {
+  if (maxiter < 0) maxiter = n_global;
+  if (!hist_host) hist_cap = 0;
+  if (hist_cap > maxiter) hist_cap = maxiter;                               // reserve!(history, :resnorm, maxiter) :212
+  void *ws = nullptr;
+  int st = be.workspace(minres_ws_bytes<T>(n, hist_cap), &ws);
+  if (st) return st;
+  const MinresLayout<T> L = minres_layout<T>(ws, n, hist_cap);
+  int64_t mvps0 = 0;
+  if ((st = minres_setup<T>(be, A, L, n, n_global, x, b, abstol, reltol, maxiter, initially_zero, skew_hermitian, &mvps0)))
+    return st;
+  if ((st = minres_advance<T>(be, A, L, n, x, -1, check_every))) return st;
+  return minres_collect<T>(be, L, mvps0, hist_host, out);
 }
 
 }  // namespace b200

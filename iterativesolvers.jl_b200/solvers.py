@@ -450,6 +450,128 @@ def bicgstabl(A, b, l=2, **kw):
 
 
 # ------------------------------------------------------------------------------------------------
+# The resumable forms: gmres_iterable!, minres_iterable!, bicgstabl_iterator!  (docs/src/iterators.md)
+# ------------------------------------------------------------------------------------------------
+class KrylovIterable:
+    """What gmres_iterable! (reference src/gmres.jl:108-136), minres_iterable! (src/minres.jl:39-89) and
+    bicgstabl_iterator! (src/bicgstabl.jl:27-73) return: iterating yields the residual norm after each iterate() and
+    leaves x updated in place; `step(k)` performs up to k iterations in one call.  The object owns its device scratch
+    (other solves may run on the context in between); x, b (and the preconditioners / callbacks) are kept alive here."""
+
+    def __init__(self, create, x, A, b, opts, keep):
+        self._A, self._x, self._keep = A, x, keep
+        self._st = _Staged(A, x, b)
+        self._cbs = tuple(o for o in keep if isinstance(o, B200LinearOperator))
+        self._h = C.c_void_p()
+        a_csr = None if _is_linop(A) else A._h
+        a_op = C.byref(A._c) if _is_linop(A) else None
+        check(_call_op(create, self._cbs, A.ctx._h, a_csr, a_op, as_device_ptr(self._st.xd), as_device_ptr(self._st.bd),
+                       C.byref(opts), C.byref(self._h)))
+        self._opts = opts
+        self.result = _lib.Result()
+        self._buf = np.zeros(4096, dtype=np.float64)
+        self.step(0)                                           # residual / tol of the initial state
+
+    residual = property(lambda self: float(self.result.residual))
+    tol = property(lambda self: float(self.result.tol))
+    iteration = property(lambda self: int(self.result.iters))
+    mv_products = property(lambda self: int(self.result.mvps))
+    converged = property(lambda self: bool(self.result.isconverged))       # converged(it)
+    done = property(lambda self: self.result.status == 1)                 # done(it, iteration)
+    x = property(lambda self: self._x)
+
+    def step(self, k=1):
+        """up to k calls of iterate(it); returns the residual norms of the iterations performed."""
+        if self._h is None:
+            raise RuntimeError("iterator is closed")
+        k = int(k)
+        out = []
+        while True:
+            kk = min(k, 4096)
+            status = _call_op(lib().b200_iter_next, self._cbs, self._h, kk, C.byref(self.result),
+                              self._buf.ctypes.data_as(C.c_void_p), 4096)
+            if status == _lib.ERR_BREAKDOWN:
+                raise np.linalg.LinAlgError("breakdown in the iteration (SingularException of the BiCGStab(l) MR step, "
+                                            "reference src/bicgstabl.jl:123, or a NaN residual)")
+            check(status)
+            out.extend(self._buf[: self.result.n_resnorm].tolist())
+            k -= kk
+            if k <= 0 or self.done:
+                break
+        self._st.finish()                                      # host x: copy the completed iterate back
+        return out
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        if self.done:
+            raise StopIteration
+        r = self.step(1)
+        if not r:
+            raise StopIteration
+        return r[0]
+
+    def close(self):
+        if self._h is not None:
+            lib().b200_iter_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def gmres_iterable_(x, A, b, *, Pl=None, Pr=None, abstol=0.0, reltol=None, restart=None, maxiter=None,
+                    initially_zero=False, orth_meth="mgs"):
+    """gmres_iterable!(x, A, b; Pl, Pr, abstol, reltol, restart, maxiter, initially_zero, orth_meth) -- reference
+    src/gmres.jl:108-136; one step = one inner iteration (iterate :57-106)."""
+    _check_operator(A, linop_ok=True)
+    if reltol is None:
+        reltol = math.sqrt(_eps(A.dtype))
+    if restart is None:
+        restart = min(20, A.size(2))
+    if maxiter is None:
+        maxiter = A.size(2)
+    opts = _lib.GmresOpts(abstol, reltol, int(maxiter), int(restart), int(bool(initially_zero)), _ORTH[orth_meth], 0,
+                          precond_to_c(Pl, A), precond_to_c(Pr, A))
+    keep = [P for P in (Pl, Pr) if P is not None] + [P.op for P in (Pl, Pr) if isinstance(P, FunctionPrec)] + [A]
+    return KrylovIterable(lib().b200_gmres_iter_create, x, A, b, opts, keep)
+
+
+def minres_iterable_(x, A, b, *, skew_hermitian=False, abstol=0.0, reltol=None, maxiter=None, initially_zero=False):
+    """minres_iterable!(x, A, b; initially_zero, skew_hermitian, abstol, reltol, maxiter) -- reference src/minres.jl:39-89."""
+    _check_operator(A, linop_ok=True)
+    if reltol is None:
+        reltol = math.sqrt(_eps(A.dtype))
+    if maxiter is None:
+        maxiter = A.size(2)
+    opts = _lib.MinresOpts(abstol, reltol, int(maxiter), int(bool(initially_zero)), int(bool(skew_hermitian)))
+    return KrylovIterable(lib().b200_minres_iter_create, x, A, b, opts, [A])
+
+
+def bicgstabl_iterator_(x, A, b, l=2, *, Pl=None, max_mv_products=None, abstol=0.0, reltol=None, initial_zero=False,
+                        r_shadow=None, rng=None):
+    """bicgstabl_iterator!(x, A, b, l; Pl, max_mv_products, abstol, reltol, initial_zero) -- reference
+    src/bicgstabl.jl:27-73; one step = one outer iteration (2 l products, iterate :79-134)."""
+    _check_operator(A, linop_ok=True)
+    if reltol is None:
+        reltol = math.sqrt(_eps(A.dtype))
+    if max_mv_products is None:
+        max_mv_products = A.size(2)
+    if r_shadow is None:
+        rng = rng or np.random.default_rng()
+        r_shadow = rng.random(A.m_local).astype(A.dtype)       # rand(T, n) :38
+    rs = r_shadow if is_device(r_shadow) else DeviceArray.from_numpy(A.ctx, np.asarray(r_shadow, dtype=A.dtype))
+    opts = _lib.BicgstablOpts(abstol, reltol, int(max_mv_products), int(l), int(bool(initial_zero)), precond_to_c(Pl, A),
+                              as_device_ptr(rs))
+    keep = [rs, A] + ([Pl] if Pl is not None else []) + ([Pl.op] if isinstance(Pl, FunctionPrec) else [])
+    return KrylovIterable(lib().b200_bicgstabl_iter_create, x, A, b, opts, keep)
+
+
+# ------------------------------------------------------------------------------------------------
 # SURVEY.md section 8(f) item 4: the solvers that need A' (QMR, LSQR, LSMR) and IDR(s)
 # ------------------------------------------------------------------------------------------------
 class _StagedRect:

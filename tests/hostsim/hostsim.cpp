@@ -327,6 +327,98 @@ EXPORT int hostsim_bicgstabl(int is_f64, const hostsim_csr *A, const hostsim_csr
   return st;
 }
 
+// The resumable forms (what csrc/iterables.cu does with the CUDA backend): setup once, then advance `chunk` iterations
+// per call with a fresh history window each time, until done.  kind: 1 gmres, 2 minres, 3 bicgstabl.  The histories of
+// the calls are concatenated into hist; calls = number of advance calls made.
+template <typename T>
+static int chunked_impl(int kind, HostBackend &be, const HostCsr *a, const HostCsr *pl, const HostCsr *pr, const T *pl_diag,
+                        const T *pr_diag, int64_t n, int64_t n_global, T *x, const T *b, const T *shadow, int l, int restart,
+                        int orth, int skew, double abstol, double reltol, int64_t maxiter, int zero, int64_t chunk,
+                        int64_t hist_cap, double *hist, hostsim_out *out, int *calls) {
+  const int64_t W = 7;                                    // a small window, so that the reset is exercised
+  int st;
+  void *ws = nullptr;
+  int64_t nh = 0;
+  std::vector<double> win((size_t)W);
+  *calls = 0;
+  if (kind == 1) {
+    if (restart <= 0) restart = (int)(n_global < 20 ? n_global : 20);
+    if ((st = be.workspace(b200::gmres_ws_bytes<T>(n, restart, W), &ws))) return st;
+    const b200::GmresLayout<T> L = b200::gmres_layout<T>(ws, n, restart, W);
+    const b200::GmresOps<T, HostBackend> op{a, pl, pr, pl_diag, pr_diag};
+    int64_t mv = 0;
+    if ((st = b200::gmres_setup<T, HostBackend>(be, op, L, n, n_global, x, b, abstol, reltol, restart, maxiter, zero, &mv))) return st;
+    for (;;) {
+      b200::GmresOutcome o;
+      memset(&o, 0, sizeof(o));
+      if ((st = b200::gmres_reset_window(be, L.s))) return st;
+      if ((st = b200::gmres_advance<T, HostBackend>(be, op, L, n, x, b, orth, chunk, &mv))) return st;
+      if ((st = b200::gmres_collect<T, HostBackend>(be, L, mv, win.data(), &o))) return st;
+      *calls += 1;
+      for (int64_t i = 0; i < o.n_hist && nh < hist_cap; ++i) hist[nh++] = win[(size_t)i];
+      out->iters = o.iters; out->mvps = o.mvps; out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged;
+      out->breakdown = o.breakdown;
+      if (o.done || o.breakdown) break;
+    }
+  } else if (kind == 2) {
+    if ((st = be.workspace(b200::minres_ws_bytes<T>(n, W), &ws))) return st;
+    const b200::MinresLayout<T> L = b200::minres_layout<T>(ws, n, W);
+    int64_t mv0 = 0;
+    if ((st = b200::minres_setup<T, HostBackend>(be, a, L, n, n_global, x, b, abstol, reltol, maxiter, zero, skew, &mv0))) return st;
+    for (;;) {
+      b200::MinresOutcome o;
+      memset(&o, 0, sizeof(o));
+      if ((st = b200::minres_reset_window(be, L.s))) return st;
+      if ((st = b200::minres_advance<T, HostBackend>(be, a, L, n, x, chunk, 3))) return st;
+      if ((st = b200::minres_collect<T, HostBackend>(be, L, mv0, win.data(), &o))) return st;
+      *calls += 1;
+      for (int64_t i = 0; i < o.n_hist && nh < hist_cap; ++i) hist[nh++] = win[(size_t)i];
+      out->iters = o.iters; out->mvps = o.mvps; out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged;
+      out->breakdown = o.breakdown;
+      if (o.done || o.breakdown) break;
+    }
+  } else {
+    if ((st = be.workspace(b200::bicgstabl_ws_bytes<T>(n, l, W), &ws))) return st;
+    const b200::BcgLayout<T> L = b200::bicgstabl_layout<T>(ws, n, l, W);
+    if ((st = b200::bicgstabl_setup<T, HostBackend>(be, a, pl, pl_diag, L, n, n_global, x, b, l, abstol, reltol, maxiter, zero))) return st;
+    for (;;) {
+      b200::BcgOutcome o;
+      memset(&o, 0, sizeof(o));
+      if ((st = b200::bicgstabl_reset_window(be, L.s))) return st;
+      if ((st = b200::bicgstabl_advance<T, HostBackend>(be, a, pl, pl_diag, L, n, x, shadow, l, chunk, 2))) return st;
+      if ((st = b200::bicgstabl_collect<T, HostBackend>(be, L, win.data(), &o))) return st;
+      *calls += 1;
+      for (int64_t i = 0; i < o.n_hist && nh < hist_cap; ++i) hist[nh++] = win[(size_t)i];
+      out->iters = o.iters; out->mvps = o.mvps; out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged;
+      out->breakdown = o.breakdown | (o.singular << 1);
+      if (o.done || o.breakdown || o.singular) break;
+    }
+  }
+  out->mtvps = 0;
+  out->n_hist = nh;
+  out->passes = be.passes; out->applies = be.applies;
+  return 0;
+}
+
+EXPORT int hostsim_chunked(int kind, int is_f64, const hostsim_csr *A, const hostsim_csr *Pl, const hostsim_csr *Pr,
+                           const void *pl_diag, const void *pr_diag, void *x, const void *b, const void *shadow, int l,
+                           int restart, int orth, int skew, double abstol, double reltol, int64_t maxiter, int zero,
+                           int64_t chunk, int64_t hist_cap, double *hist, int order, int split, hostsim_out *out, int *calls) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64), pl, pr;
+  if (Pl) pl = mk(Pl, is_f64);
+  if (Pr) pr = mk(Pr, is_f64);
+  return is_f64 ? chunked_impl<double>(kind, be, &a, Pl ? &pl : nullptr, Pr ? &pr : nullptr, (const double *)pl_diag,
+                                       (const double *)pr_diag, A->m, A->n, (double *)x, (const double *)b,
+                                       (const double *)shadow, l, restart, orth, skew, abstol, reltol, maxiter, zero, chunk,
+                                       hist_cap, hist, out, calls)
+                : chunked_impl<float>(kind, be, &a, Pl ? &pl : nullptr, Pr ? &pr : nullptr, (const float *)pl_diag,
+                                      (const float *)pr_diag, A->m, A->n, (float *)x, (const float *)b, (const float *)shadow,
+                                      l, restart, orth, skew, abstol, reltol, maxiter, zero, chunk, hist_cap, hist, out, calls);
+}
+
 // Constraint (reference src/lobpcg.jl:144-224): factor Y'Y, optionally extend the factor by an identity block for the
 // last `appended` columns (update! :188-206), and deflate the block X (strides rs, cs; bs <= 16 columns).
 EXPORT int hostsim_constraint_apply(int is_f64, int64_t n, const void *Y, int64_t ldy, int nc, int appended, void *X,

@@ -246,6 +246,35 @@ def bicgstabl_(x, A, b, l, shadow, *, Pl=None, diag=None, abstol=0.0, reltol=-1.
     return x, o
 
 
+def chunked(kind, x, A, b, chunk, *, Pl=None, Pr=None, pl_diag=None, pr_diag=None, shadow=None, l=2, restart=-1,
+            orth_meth="mgs", skew_hermitian=False, abstol=0.0, reltol=-1.0, maxiter=-1, initially_zero=False, order=0, split=0):
+    """the resumable form of gmres / minres / bicgstabl on the serial backend: setup, then `chunk` iterations per call
+    (fresh history window per call) until done -> (x, outcome, number of calls).  maxiter is max_mv_products for
+    bicgstabl."""
+    dt = x.dtype
+    Ac = Csr(A, dt)
+    Plc = Csr(Pl, dt) if Pl is not None else None
+    Prc = Csr(Pr, dt) if Pr is not None else None
+    b = np.ascontiguousarray(b, dtype=dt)
+    arr = lambda a: None if a is None else np.ascontiguousarray(a, dtype=dt)
+    dl, dr, sh = arr(pl_diag), arr(pr_diag), arr(shadow)
+    cap = (maxiter if maxiter >= 0 else A.shape[1]) + 1
+    hist = np.zeros(cap)
+    out, calls = _Out(), C.c_int()
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+    st = lib().hostsim_chunked(C.c_int({"gmres": 1, "minres": 2, "bicgstabl": 3}[kind]), C.c_int(dt == np.float64),
+                               C.byref(Ac.c), C.byref(Plc.c) if Plc else None, C.byref(Prc.c) if Prc else None, vp(dl),
+                               vp(dr), vp(x), vp(b), vp(sh), C.c_int(l), C.c_int(restart),
+                               C.c_int({"mgs": 0, "cgs": 1, "dgks": 2}[orth_meth]), C.c_int(skew_hermitian),
+                               C.c_double(abstol), C.c_double(reltol), C.c_int64(maxiter), C.c_int(initially_zero),
+                               C.c_int64(chunk), C.c_int64(cap), vp(hist), C.c_int(order), C.c_int(split), C.byref(out),
+                               C.byref(calls))
+    assert st == 0, st
+    o = _outcome(out, hist)
+    o.singular = bool(out.breakdown & 2)
+    return x, o, calls.value
+
+
 def constraint_apply_(X, Y, *, appended=0, row_major=False, order=0, split=0):
     """the Constraint passes (csrc/lobpcg_constraint_core.h) on the serial backend: X <- X - Y (chol(Y'Y) \\ Y'X).
     X: n x bs (bs <= 16); row_major: X is laid out like the LOBPCG engine's internal n x 16 blocks."""

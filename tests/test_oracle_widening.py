@@ -939,3 +939,126 @@ def test_engine_bicgstabl_general_matches_oracle(oracle, sim, dtype, tol):
             return x, SimpleNamespace(iters=h.iters, mvps=h.mvps, converged=h.converged, hist=h.hist,
                                       singular=h.singular)
         cases.case_bicgstabl_general(oracle, run, dtype, tol)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_resumable_forms_reproduce_the_one_shot_solves(sim, dtype):
+    """gmres_iterable! / minres_iterable! / bicgstabl_iterator! (setup once, k iterations per call, history window reset at
+    every call -- the pieces csrc/iterables.cu drives with the CUDA backend) give bit-for-bit the x, the history and the
+    counters of the one-shot engines, whatever the chunk size (cycle boundaries, DGKS rounds, the done iteration)."""
+    rng = np.random.default_rng(11)
+    n = 300
+    A = (sp.random(n, n, 0.03, random_state=1, format="csr") + 4 * sp.eye(n)).tocsr().astype(dtype)
+    R = sp.random(n, n, 0.02, random_state=2, format="csr")
+    S = (0.1 * (R + R.T) + sp.diags(np.where(np.arange(n) % 2 == 0, 1.0, -1.0) * np.linspace(1, 3, n))).tocsr().astype(dtype)
+    d = A.diagonal()
+    Dinv = sp.diags(1.0 / d.astype(np.float64)).tocsr()
+    b = rng.standard_normal(n).astype(dtype)
+    x0 = rng.standard_normal(n).astype(dtype)
+    sh = rng.random(n).astype(dtype)
+    one = {
+        "gmres": sim.gmres_(x0.copy(), A, b, pl_diag=d, Pr=Dinv, restart=6, maxiter=50, orth_meth="dgks"),
+        "minres": sim.minres_(x0.copy(), S, b, maxiter=50),
+        "bicgstabl": sim.bicgstabl_(x0.copy(), A, b, 2, sh, Pl=Dinv, max_mv_products=60, reltol=1e-13),
+    }
+    for chunk in (1, 4, 1000):
+        many = {
+            "gmres": sim.chunked("gmres", x0.copy(), A, b, chunk, pl_diag=d, Pr=Dinv, restart=6, maxiter=50, orth_meth="dgks"),
+            "minres": sim.chunked("minres", x0.copy(), S, b, chunk, maxiter=50),
+            "bicgstabl": sim.chunked("bicgstabl", x0.copy(), A, b, chunk, Pl=Dinv, shadow=sh, l=2, maxiter=60, reltol=1e-13),
+        }
+        for name in one:
+            (x1, h1), (x2, h2, calls) = one[name], many[name]
+            assert h1.iters > 3 and h2.iters == h1.iters and h2.mvps == h1.mvps and h2.converged == h1.converged, name
+            m = len(h1.hist) if chunk <= 7 else min(7, len(h1.hist))       # a call records at most one window (7 here)
+            assert np.array_equal(x1, x2) and len(h2.hist) == m and np.array_equal(h1.hist[:m], h2.hist), (name, chunk)
+            assert calls == 1 if chunk == 1000 else calls >= -(-h1.iters // chunk), (name, chunk, calls)
+
+
+def test_python_iterables_with_a_fake_library(monkeypatch):
+    """gmres_iterable_ / minres_iterable_ / bicgstabl_iterator_: the right create entry point with the CSR handle or the
+    callback descriptor, step(0) at creation, windows of 4096 residuals, done -> StopIteration, close -> destroy."""
+    import ctypes as C
+    from importlib import import_module
+    import iterativesolvers_jl_b200 as isb
+    S = import_module("iterativesolvers_jl_b200.solvers")
+    L = S._lib
+    calls = []
+    state = {"iters": 0, "maxiter": 9000}
+
+    class FakeArr:
+        def __init__(self, a):
+            self.a = np.array(a, order="F")
+            self.shape, self.dtype = self.a.shape, self.a.dtype
+            self._p = C.c_void_p(0x5000)
+
+        @classmethod
+        def from_numpy(cls, ctx, a):
+            return cls(a)
+
+        def numpy(self):
+            return self.a.copy()
+
+    class FakeLib:
+        def __getattr__(self, name):
+            def f(*args):
+                calls.append((name, args))
+                if name.endswith("_iter_create"):
+                    args[-1]._obj.value = 0x99
+                    state["iters"] = 0
+                if name == "b200_iter_next":
+                    h, k, res, buf, cap = args
+                    done_before = state["iters"] >= state["maxiter"]
+                    k = 0 if done_before else min(k, state["maxiter"] - state["iters"])
+                    state["iters"] += k
+                    r = res._obj
+                    r.iters, r.mvps, r.residual, r.tol = state["iters"], state["iters"] + 1, 1.0 / (1 + state["iters"]), 1e-3
+                    r.status = 1 if state["iters"] >= state["maxiter"] else 0
+                    r.isconverged = 0
+                    r.n_resnorm = min(k, cap)
+                    out = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_double)), shape=(4096,))
+                    out[: r.n_resnorm] = np.arange(state["iters"] - k, state["iters"] - k + r.n_resnorm)
+                return 0
+            return f
+
+    monkeypatch.setattr(S, "lib", lambda: FakeLib())
+    monkeypatch.setattr(S, "DeviceArray", FakeArr)
+    monkeypatch.setattr(S, "is_device", lambda v: isinstance(v, FakeArr))
+    monkeypatch.setattr(S, "as_device_ptr", lambda v: v._p)
+    ctx = SimpleNamespace(_h=None, world=1)
+    n = 12
+    csr = S.B200CSR.__new__(S.B200CSR)
+    csr.ctx, csr._h, csr.m_local, csr.n_global, csr.m_global, csr.dtype = ctx, C.c_void_p(7), n, n, n, np.dtype(np.float64)
+    csr.close = lambda: None
+    op = isb.B200LinearOperator((n, n), np.float64, lambda y, x: None, ctx=ctx)
+    b = np.ones(n)
+
+    it = isb.gmres_iterable_(np.zeros(n), csr, b, restart=5, maxiter=9000)
+    assert [c[0] for c in calls] == ["b200_gmres_iter_create", "b200_iter_next"]
+    cargs = calls[0][1]
+    assert cargs[1].value == 7 and cargs[2] is None and calls[1][1][1] == 0          # CSR handle, no callback; step(0)
+    res = it.step(5000)                                          # two windows: 4096 + 904
+    assert [c[1][1] for c in calls[2:]] == [4096, 904] and res == list(range(5000)) and it.iteration == 5000
+    assert not it.done and it.mv_products == 5001 and it.tol == 1e-3
+    res = it.step(10 ** 6)                                       # stops at done
+    assert it.done and it.iteration == 9000 and len(res) == 4000
+    with pytest.raises(StopIteration):
+        next(it)
+    it.close()
+    assert calls[-1][0] == "b200_iter_destroy"
+    with pytest.raises(RuntimeError):
+        it.step(1)
+
+    calls.clear()
+    state["maxiter"] = 3
+    it = isb.minres_iterable_(np.zeros(n), op, b)
+    cargs = calls[0][1]
+    assert calls[0][0] == "b200_minres_iter_create" and cargs[1] is None and isinstance(cargs[2]._obj, L.LinOp)
+    assert [r for r in it] == [0.0, 1.0, 2.0] and it.done
+
+    calls.clear()
+    Pl = isb.FunctionPrec(n, np.float64, lambda y, x: None, ctx=ctx)
+    it = isb.bicgstabl_iterator_(np.zeros(n), csr, b, 4, Pl=Pl, rng=np.random.default_rng(0))
+    o = calls[0][1][5]._obj
+    assert calls[0][0] == "b200_bicgstabl_iter_create" and o.l == 4 and o.Pl.kind == 2 and o.r_shadow
+    assert it.step(2) == [0.0, 1.0]
