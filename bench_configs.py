@@ -8,6 +8,9 @@
     cg256     configs[1]: cg! on laplace_matrix(Float64, 256, 3)
     widen     SURVEY 8(f) item 4: qmr!, lsqr!, lsmr!, idrs!(s=8) on laplace_matrix(Float64, N, 3), fixed iteration counts
               (adjoint operator built by the device transpose)
+    general   the general (callback-operator) engines of DESIGN sections 11 / 16 next to the tuned ones: cg!, minres! on
+              laplace_matrix(Float64, N, 3), gmres!(30, CGS), bicgstabl!(2) on advection_dominated(N); the operator goes
+              through the b200_linop interface with the library's own SpMV thunk (no host code inside the iteration)
 
 Each line is a JSON object with iterations/s, per-kernel-class CUDA-event times recorded inside the run
 (b200_ctx_profile_*), the algorithmic bytes and the achieved fraction of the measured
@@ -52,7 +55,7 @@ def prof_read(L, ctx):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["gmres", "lobpcg", "minres", "bicgstabl", "cg256", "widen"])
+    ap.add_argument("which", choices=["gmres", "lobpcg", "minres", "bicgstabl", "cg256", "widen", "general"])
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--iters", type=int, default=None)
     ap.add_argument("--orth", default="cgs")
@@ -191,6 +194,56 @@ def main():
                          "achieved_gbs": per_it[name] * h.iters / dt / 1e9,
                          "frac_of_measured_peak": per_it[name] * h.iters / dt / 1e9 / pk,
                          "first_last": [float(h[key][0]), float(h[key][-1])], "profile": pr}
+        out["solvers"] = res
+    elif args.which == "general":
+        V = 8
+        spmv_b = nnz * 12 + (n + 1) * 4 + 2 * n * V
+        iters = args.iters or 90
+        res = {}
+        Alap = isb.B200CSR.laplacian(N, 3, np.float64, ctx=ctx)
+        b = rng.standard_normal(n)
+        b /= np.linalg.norm(b)
+        bd = isb.DeviceArray.from_numpy(ctx, b)
+        xd = isb.DeviceArray.zeros(ctx, n)
+        sh = isb.DeviceArray.from_numpy(ctx, rng.random(n))
+        restart = 30
+        gm_cyc = sum(spmv_b + (2 * k + 5) * n * V for k in range(1, restart + 1)) + (restart + 2) * n * V + spmv_b + 6 * n * V
+        runs = {   # name -> (callable(operator) -> history, algorithmic bytes per iteration of the TUNED engine, matrix)
+            "cg": (lambda op: isb.cg_(xd, op, bd, maxiter=iters, initially_zero=True, log=True, reltol=0.0)[1],
+                   spmv_b + 10 * n * V, "lap"),
+            "minres": (lambda op: isb.minres_(xd, op, bd, maxiter=iters, initially_zero=True, log=True, reltol=0.0)[1],
+                       spmv_b + 13 * n * V, "lap"),
+            "gmres": (lambda op: isb.gmres_(xd, op, bd, restart=restart, maxiter=iters, orth_meth="cgs", initially_zero=True,
+                                            log=True, reltol=0.0)[1], gm_cyc / restart, "adv"),
+            "bicgstabl": (lambda op: isb.bicgstabl_(xd, op, bd, 2, max_mv_products=4 * (iters // 4), initial_zero=True,
+                                                    r_shadow=sh, log=True, reltol=0.0)[1], None, "adv"),
+        }
+        Aadv = None
+        for name, (fn, per_it, mat) in runs.items():
+            if mat == "adv" and Aadv is None:
+                cp, rv, nz, shape, badv = isb.advection_dominated(N, 1000.0, base=1)
+                Aadv = isb.B200CSR.from_csc_arrays(cp, rv, nz, shape, base=1, ctx=ctx)
+                del cp, rv, nz
+                bd.upload(badv)
+            A = Alap if mat == "lap" else Aadv
+            entry = {}
+            for kind, op in (("tuned", A), ("general", isb.B200LinearOperator.from_csr(A))):
+                for rep in range(args.reps + 1):
+                    L.b200_fill(ctx._h, n, 0.0, xd._p, 0)
+                    ctx.sync()
+                    t0 = time.perf_counter()
+                    h = fn(op)
+                    ctx.sync()
+                    dt = time.perf_counter() - t0
+                units = h.mvps if name == "bicgstabl" else h.iters
+                entry[kind] = {"units": int(units), "seconds": dt, "units_per_s": units / dt,
+                               "last_resnorm": float(h["resnorm"][-1]) if len(h["resnorm"]) else None}
+                if per_it:
+                    entry[kind]["achieved_gbs_on_tuned_bytes"] = per_it * units / dt / 1e9
+                    entry[kind]["frac_of_measured_peak"] = per_it * units / dt / 1e9 / pk
+            entry["unit"] = "mv-products" if name == "bicgstabl" else "iterations"
+            entry["general_over_tuned"] = entry["general"]["units_per_s"] / entry["tuned"]["units_per_s"]
+            res[name] = entry
         out["solvers"] = res
     else:  # lobpcg
         bs = 16

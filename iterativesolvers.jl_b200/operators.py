@@ -306,10 +306,14 @@ class B200LinearOperator:
 
     @classmethod
     def from_csr(cls, A: "B200CSR"):
-        """a B200CSR seen through the callback interface (lets a callback preconditioner be combined with it)."""
+        """a B200CSR seen through the callback interface: the descriptor's `apply` is the library's own SpMV thunk
+        (b200_csr_as_linop), so no Python runs inside the iteration; `mul_` from Python still works."""
         n_loc = A.n_global if A.ctx.world == 1 else A.m_local
-        return cls((A.m_local, n_loc), A.dtype, lambda y, x: A.mul_(y, x),
-                   (lambda y, x: A.adjoint().mul_(y, x)), A.ctx, A.shape)
+        op = cls((A.m_local, n_loc), A.dtype, lambda y, x: A.mul_(y, x),
+                 (lambda y, x: A.adjoint().mul_(y, x)), A.ctx, A.shape)
+        op._csr = A                                            # the descriptor points at the CSR handle
+        check(lib().b200_csr_as_linop(A._h, C.byref(op._c)))
+        return op
 
 
 class FunctionPrec:
