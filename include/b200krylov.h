@@ -52,8 +52,8 @@ enum { B200_ORTH_MGS = 0, B200_ORTH_CGS = 1, B200_ORTH_DGKS = 2 };
  * preconditioner idiom of reference test/cg.jl:14-18 (ldiv!(y,P,x) = y .= x ./ P.diagonal). */
 enum { B200_PREC_IDENTITY = 0, B200_PREC_JACOBI = 1,
        B200_PREC_CALLBACK = 2 /* `diag` points to a b200_linop whose apply is ldiv!(y, Pl, x); accepted by
-                                 the gmres / bicgstabl / idrs / lobpcg entry points (b200_cg_solve_op takes its callback as an
-                                 argument); cg / chebyshev on a b200_csr reject it */ };
+                                 the chebyshev / gmres / bicgstabl / idrs / lobpcg entry points (b200_cg_solve_op takes its callback as an
+                                 argument); b200_cg_solve on a b200_csr rejects it */ };
 
 typedef struct b200_ctx b200_ctx;   /* device + stream (+ NCCL communicator)                     */
 typedef struct b200_csr b200_csr;   /* the operator A: CSR int32 on device, row-partitioned       */
@@ -279,6 +279,7 @@ B200_API int b200_chebyshev_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev,
                                   double lambda_min, double lambda_max, const b200_cg_opts *opts, b200_result *res,
                                   double *resnorm_host, int64_t resnorm_cap);
 
+
 typedef struct {
   double abstol;            /* zero(real(eltype(b)))       src/qmr.jl:266                           */
   double reltol;            /* sqrt(eps(real(eltype(b))))  src/qmr.jl:267 -- pass <0 for that default */
@@ -318,6 +319,11 @@ typedef struct {
  * <c, r> pass); Pl != NULL is `ldiv!(c, Pl, r)` by callback.  opts->fixed_iterations / variant must be 0. */
 B200_API int b200_cg_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *Pl, void *x_dev, const void *b_dev,
                               const b200_cg_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);
+/* chebyshev! for a callback operator; opts->Pl: Identity, Jacobi or B200_PREC_CALLBACK (src/chebyshev.jl:37).
+ * b200_chebyshev_solve with a callback preconditioner runs the same engine (csrc/chebyshev_core.h). */
+B200_API int b200_chebyshev_solve_op(b200_ctx *ctx, const b200_linop *A, void *x_dev, const void *b_dev,
+                                     double lambda_min, double lambda_max, const b200_cg_opts *opts, b200_result *res,
+                                     double *resnorm_host, int64_t resnorm_cap);
 /* qmr! / lsqr! / lsmr! / idrs! on callback operators (A and, where needed, At = adjoint(A)) */
 B200_API int b200_qmr_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *At, void *x_dev, const void *b_dev,
                                const b200_qmr_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);

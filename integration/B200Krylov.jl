@@ -547,6 +547,11 @@ end
 # qmr!/lsqr!/lsmr!/idrs! on B200LinearOperator: the same pattern with b200_qmr_solve_op / b200_lsqr_solve_op /
 # b200_lsmr_solve_op / b200_idrs_solve_op (the adjoint is a second B200LinearOperator).
 
+# chebyshev!(x, A, b, λmin, λmax; Pl, ...) on a B200LinearOperator: as cg! above with
+#   ccall((:b200_chebyshev_solve_op, LIB), Cint, (Ptr{Cvoid}, Ptr{LinOp}, Ptr{Cvoid}, Ptr{Cvoid}, Float64, Float64,
+#         Ref{CgOpts}, Ref{Result}, Ptr{Float64}, Int64), A.ctx.h, a, x.p, b.p, λmin, λmax, o, res, hist, length(hist))
+# and the preconditioner in o.Pl (prec_cb below).
+
 # A preconditioner given as a B200LinearOperator (f(y, x) enqueues y = P \ x, i.e. ldiv!(y, P, x)) travels in the
 # b200_precond slot as B200_PREC_CALLBACK = 2 with the address of its b200_linop; the Ref must outlive the call.
 prec_cb(P, keep::Vector{Any}) = prec(P)

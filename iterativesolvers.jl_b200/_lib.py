@@ -178,6 +178,7 @@ SIGNATURES = {
     "b200_cg_iter_next": (_INT, [_P, _I64, C.POINTER(Result), _P, _I64]),
     "b200_cg_iter_destroy": (_INT, [_P]),
     "b200_chebyshev_solve": (_INT, [_P, _P, _P, _P, _DBL, _DBL, C.POINTER(CgOpts), C.POINTER(Result), _P, _I64]),
+    "b200_chebyshev_solve_op": (_INT, [_P, C.POINTER(LinOp), _P, _P, _DBL, _DBL, C.POINTER(CgOpts), C.POINTER(Result), _P, _I64]),
     "b200_gmres_solve": (_INT, [_P, _P, _P, _P, C.POINTER(GmresOpts), C.POINTER(Result), _P, _I64]),
     "b200_gmres_solve_op": (_INT, [_P, C.POINTER(LinOp), _P, _P, C.POINTER(GmresOpts), C.POINTER(Result), _P, _I64]),
     "b200_gmres_iter_create": (_INT, [_P, _P, C.POINTER(LinOp), _P, _P, C.POINTER(GmresOpts), C.POINTER(_P)]),

@@ -1,11 +1,70 @@
-// cg_op.cu -- cg!(x, A, b; Pl, ...) for general (callback) operators and preconditioners: the fused-pass engine of
-// cg_core.h on the CUDA backend.  b200_csr operators with Identity / Jacobi take the specialised engine of cg.cu.
+// cg_op.cu -- cg!(x, A, b; Pl, ...) and chebyshev!(x, A, b, lmin, lmax; Pl, ...) for general (callback) operators and
+// preconditioners: the fused-pass engines of cg_core.h / chebyshev_core.h on the CUDA backend.  b200_csr operators with Identity / Jacobi take the specialised engine of cg.cu.
 #include "linop.cuh"
 #include "cg_core.h"
+#include "chebyshev_core.h"
 
 using namespace b200;
 
+namespace b200 {
+
+// chebyshev! on a CSR or callback operator with Identity / Jacobi / callback preconditioner (chebyshev_core.h)
+int chebyshev_general(b200_ctx *ctx, const CudaOp &A, int dtype, int64_t n, int64_t n_global, void *x_dev,
+                      const void *b_dev, double lmin, double lmax, const b200_cg_opts *opts, b200_result *res,
+                      double *resnorm_host, int64_t resnorm_cap) {
+  const b200_linop *plf = nullptr;
+  const void *diag = nullptr;
+  if (opts->Pl.kind == B200_PREC_JACOBI) {
+    B200_REQUIRE(opts->Pl.diag, "Jacobi preconditioner without a diagonal");
+    diag = opts->Pl.diag;
+  } else if (opts->Pl.kind == B200_PREC_CALLBACK) {
+    plf = (const b200_linop *)opts->Pl.diag;
+    B200_TRY(check_linop(plf, "Pl"));
+    B200_REQUIRE(plf->dtype == dtype && plf->m_local == n && plf->n_local == n,
+                 "Pl must act on vectors of the operator's local length");
+  } else {
+    B200_REQUIRE(opts->Pl.kind == B200_PREC_IDENTITY, "unsupported preconditioner");
+  }
+  B200_REQUIRE(!opts->fixed_iterations && !opts->variant, "fixed_iterations / variant are not available on this path");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  CudaBackend be{ctx};
+  CudaOp pl{nullptr, plf};
+  ChebOutcome o;
+  memset(&o, 0, sizeof(o));
+  const int st =
+      dtype == B200_F64
+          ? chebyshev_run<double>(be, &A, plf ? &pl : nullptr, (const double *)diag, n, n_global, (double *)x_dev,
+                                  (const double *)b_dev, lmin, lmax, opts->abstol, opts->reltol, opts->maxiter,
+                                  opts->initially_zero, opts->check_every, resnorm_cap, resnorm_host, &o)
+          : chebyshev_run<float>(be, &A, plf ? &pl : nullptr, (const float *)diag, n, n_global, (float *)x_dev,
+                                 (const float *)b_dev, lmin, lmax, opts->abstol, opts->reltol, opts->maxiter,
+                                 opts->initially_zero, opts->check_every, resnorm_cap, resnorm_host, &o);
+  if (st != B200_OK) return st;
+  if (res) {
+    res->iters = o.iters;
+    res->mvps = o.mvps;
+    res->isconverged = o.converged;
+    res->status = o.breakdown ? B200_ERR_BREAKDOWN : 0;
+    res->tol = o.tol;
+    res->residual = o.residual;
+    res->n_resnorm = o.n_hist;
+  }
+  return B200_OK;
+}
+
+}  // namespace b200
+
 extern "C" {
+
+int b200_chebyshev_solve_op(b200_ctx *ctx, const b200_linop *A, void *x_dev, const void *b_dev, double lambda_min,
+                            double lambda_max, const b200_cg_opts *opts, b200_result *res, double *resnorm_host,
+                            int64_t resnorm_cap) {
+  B200_REQUIRE(ctx && x_dev && b_dev && opts, "NULL argument");
+  B200_TRY(check_linop(A, "A"));
+  B200_REQUIRE(A->m_global == A->n_global && A->m_local == A->n_local, "chebyshev! needs a square operator");
+  return chebyshev_general(ctx, CudaOp{nullptr, A}, A->dtype, A->m_local, A->n_global, x_dev, b_dev, lambda_min,
+                           lambda_max, opts, res, resnorm_host, resnorm_cap);
+}
 
 int b200_cg_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *Pl, void *x_dev, const void *b_dev,
                      const b200_cg_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap) {

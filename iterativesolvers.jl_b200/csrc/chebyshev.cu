@@ -11,6 +11,7 @@
 //   K3  x += alpha*u ; r -= alpha*c ; ||r||^2 -> residual, history, done
 #include "blas1.cuh"
 #include "csr.cuh"
+#include "linop.cuh"
 
 using namespace b200;
 
@@ -225,6 +226,9 @@ int b200_chebyshev_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const vo
   B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
   B200_REQUIRE(is_square(A), "this solver needs a square operator (got %lld x %lld)", (long long)A->m_global,
                (long long)A->n_global);
+  if (opts->Pl.kind == B200_PREC_CALLBACK)                                       // ldiv! by callback: the general engine
+    return chebyshev_general(ctx, CudaOp{A, nullptr}, A->dtype, A->m_local, A->n_global, x_dev, b_dev, lambda_min,
+                             lambda_max, opts, res, resnorm_host, resnorm_cap);
   B200_REQUIRE(opts->Pl.kind == B200_PREC_IDENTITY || (opts->Pl.kind == B200_PREC_JACOBI && opts->Pl.diag),
                "unsupported preconditioner");
   B200_CUDA(cudaSetDevice(ctx->device));

@@ -283,8 +283,9 @@ def cg(A, b, **kw):
 # ------------------------------------------------------------------------------------------------
 def chebyshev_(x, A, b, lmin, lmax, *, abstol=0.0, reltol=None, Pl=None, maxiter=None, log=False, verbose=False,
                initially_zero=False):
-    """chebyshev!(x, A, b, λmin, λmax; abstol, reltol, Pl, maxiter, log, verbose, initially_zero)."""
-    _check_operator(A)
+    """chebyshev!(x, A, b, λmin, λmax; abstol, reltol, Pl, maxiter, log, verbose, initially_zero).
+    A: B200CSR or B200LinearOperator; Pl: Identity, JacobiPrec or FunctionPrec (callbacks: the general engine)."""
+    _check_operator(A, linop_ok=True)
     if reltol is None:
         reltol = math.sqrt(_eps(A.dtype))
     if maxiter is None:
@@ -294,9 +295,14 @@ def chebyshev_(x, A, b, lmin, lmax, *, abstol=0.0, reltol=None, Pl=None, maxiter
     cap = int(maxiter)                                          # reserve!(history, :resnorm, maxiter)  :144
     resnorm = np.zeros(max(cap, 1), dtype=np.float64)
     st = _Staged(A, x, b)
-    check(lib().b200_chebyshev_solve(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), float(lmin),
-                                     float(lmax), C.byref(opts), C.byref(res),
-                                     resnorm.ctypes.data_as(C.c_void_p), cap))
+    cbs = (Pl.op,) if isinstance(Pl, FunctionPrec) else ()
+    if _is_linop(A):
+        check(_call_op(lib().b200_chebyshev_solve_op, (A,) + cbs, A.ctx._h, C.byref(A._c), as_device_ptr(st.xd),
+                       as_device_ptr(st.bd), float(lmin), float(lmax), C.byref(opts), C.byref(res),
+                       resnorm.ctypes.data_as(C.c_void_p), cap))
+    else:
+        check(_call_op(lib().b200_chebyshev_solve, cbs, A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd),
+                       float(lmin), float(lmax), C.byref(opts), C.byref(res), resnorm.ctypes.data_as(C.c_void_p), cap))
     st.finish()
     if verbose:
         print("=== chebyshev ===\niter\tresnorm")
@@ -308,7 +314,7 @@ def chebyshev_(x, A, b, lmin, lmax, *, abstol=0.0, reltol=None, Pl=None, maxiter
 
 
 def chebyshev(A, b, lmin, lmax, **kw):
-    _check_operator(A)
+    _check_operator(A, linop_ok=True)
     x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
     return chebyshev_(x, A, b, lmin, lmax, initially_zero=True, **kw)
 

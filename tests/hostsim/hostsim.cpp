@@ -23,6 +23,7 @@
 #include "../../iterativesolvers.jl_b200/csrc/idrs_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/cg_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/gmres_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/chebyshev_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/minres_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/bicgstabl_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/lobpcg_constraint_core.h"
@@ -277,6 +278,30 @@ EXPORT int hostsim_gmres(int is_f64, const hostsim_csr *A, const hostsim_csr *Pl
                   : b200::gmres_run<float>(be, &a, Pl ? &pl : nullptr, Pr ? &pr : nullptr, (const float *)pl_diag,
                                            (const float *)pr_diag, A->m, A->n, (float *)x, (const float *)b, abstol,
                                            reltol, restart, maxiter, initially_zero, orth_meth, hist_cap, hist, &o);
+  out->iters = o.iters; out->mvps = o.mvps; out->mtvps = 0; out->n_hist = o.n_hist;
+  out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
+  out->passes = be.passes; out->applies = be.applies;
+  return st;
+}
+
+// chebyshev! on general operators
+EXPORT int hostsim_chebyshev(int is_f64, const hostsim_csr *A, const hostsim_csr *Pl, const void *diag, void *x,
+                             const void *b, double lmin, double lmax, double abstol, double reltol, int64_t maxiter,
+                             int initially_zero, int check_every, int64_t hist_cap, double *hist, int order, int split,
+                             hostsim_out *out) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64), p;
+  if (Pl) p = mk(Pl, is_f64);
+  b200::ChebOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st = is_f64 ? b200::chebyshev_run<double>(be, &a, Pl ? &p : nullptr, (const double *)diag, A->m, A->n, (double *)x,
+                                                (const double *)b, lmin, lmax, abstol, reltol, maxiter, initially_zero,
+                                                check_every, hist_cap, hist, &o)
+                  : b200::chebyshev_run<float>(be, &a, Pl ? &p : nullptr, (const float *)diag, A->m, A->n, (float *)x,
+                                               (const float *)b, lmin, lmax, abstol, reltol, maxiter, initially_zero,
+                                               check_every, hist_cap, hist, &o);
   out->iters = o.iters; out->mvps = o.mvps; out->mtvps = 0; out->n_hist = o.n_hist;
   out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
   out->passes = be.passes; out->applies = be.applies;

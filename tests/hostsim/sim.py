@@ -205,6 +205,26 @@ def gmres_(x, A, b, *, Pl=None, Pr=None, pl_diag=None, pr_diag=None, abstol=0.0,
     return x, _outcome(out, hist)
 
 
+def chebyshev_(x, A, b, lmin, lmax, *, Pl=None, diag=None, abstol=0.0, reltol=-1.0, maxiter=-1, initially_zero=False,
+               check_every=0, order=0, split=0):
+    """the general-operator chebyshev engine (csrc/chebyshev_core.h) on the serial backend."""
+    dt = x.dtype
+    Ac = Csr(A, dt)
+    Pc = Csr(Pl, dt) if Pl is not None else None
+    b = np.ascontiguousarray(b, dtype=dt)
+    d = None if diag is None else np.ascontiguousarray(diag, dtype=dt)
+    cap = maxiter if maxiter >= 0 else A.shape[1]
+    hist = np.zeros(max(cap, 1))
+    out = _Out()
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
+    st = lib().hostsim_chebyshev(C.c_int(dt == np.float64), C.byref(Ac.c), C.byref(Pc.c) if Pc else None, vp(d), vp(x), vp(b),
+                                 C.c_double(lmin), C.c_double(lmax), C.c_double(abstol), C.c_double(reltol),
+                                 C.c_int64(maxiter), C.c_int(initially_zero), C.c_int(check_every), C.c_int64(cap), vp(hist),
+                                 C.c_int(order), C.c_int(split), C.byref(out))
+    assert st == 0, st
+    return x, _outcome(out, hist)
+
+
 def minres_(x, A, b, *, abstol=0.0, reltol=-1.0, maxiter=-1, initially_zero=False, skew_hermitian=False, check_every=0,
             order=0, split=0):
     """the general-operator minres engine (csrc/minres_core.h) on the serial backend; x updated in place."""

@@ -592,8 +592,12 @@ def test_python_linop_paths_with_a_fake_library(monkeypatch):
     with pytest.raises(KeyError, match="inside the preconditioner"):
         isb.bicgstabl(csr, b, Pl=isb.FunctionPrec(n, np.float64, boom_p, ctx=ctx), rng=np.random.default_rng(0))
     monkeypatch.setattr(S, "lib", lambda: FakeLib())
+    calls.clear()
+    seen.clear()
+    isb.chebyshev(op, b, 1.0, 2.0)                   # callback operator -> b200_chebyshev_solve_op
+    assert calls == ["b200_chebyshev_solve_op"] and seen[0][0] == "mul"
     with pytest.raises(TypeError):
-        isb.chebyshev(op, b, 1.0, 2.0)               # chebyshev! is CSR-only
+        isb.cg(object(), b)                          # not an operator at all
 
 
 def test_partitioned_engines_world2_gloo():
@@ -1062,3 +1066,16 @@ def test_python_iterables_with_a_fake_library(monkeypatch):
     o = calls[0][1][5]._obj
     assert calls[0][0] == "b200_bicgstabl_iter_create" and o.l == 4 and o.Pl.kind == 2 and o.r_shadow
     assert it.step(2) == [0.0, 1.0]
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-12), (np.float32, 2e-6)])
+def test_engine_chebyshev_general_matches_oracle(oracle, sim, dtype, tol):
+    for order, split in ((0, 0), (1, 1)):
+        def run(x, A, b, lmin, lmax, d, pk, **kw):
+            args = {}
+            if pk == "jac":
+                args["diag"] = d
+            if pk == "cb":
+                args["Pl"] = sp.diags(1.0 / d.astype(np.float64)).tocsr()
+            return sim.chebyshev_(x, sp.csr_matrix(A), b, lmin, lmax, order=order, split=split, **args, **kw)
+        cases.case_chebyshev_general(oracle, run, dtype, tol)

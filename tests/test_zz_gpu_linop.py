@@ -126,11 +126,15 @@ def test_callback_errors_surface_as_python_exceptions(isb):
 def test_idrs_callback_preconditioner(isb, oracle):
     from test_zy_gpu_widening import GpuRunner
     cases.case_idrs_callback_preconditioner(oracle, [GpuRunner(isb)])
-    # the CSR-only engines say so instead of silently ignoring a callback preconditioner
+    # an unknown preconditioner kind is refused, not ignored
     A = isb.B200CSR.from_scipy((sp.eye(32) * 2.0).tocsc())
-    Pl = isb.FunctionPrec(32, np.float64, lambda y, x: None)
-    with pytest.raises(isb.B200Error, match="unsupported preconditioner"):
-        isb.chebyshev(A, np.ones(32), 1.0, 3.0, Pl=Pl)
+    L = isb.lib()
+    import ctypes as C
+    from iterativesolvers_jl_b200 import _lib
+    opts = _lib.CgOpts(0.0, 1e-8, 10, 1, 0, _lib.Precond(9, 0, None), 0, 0)
+    x, b = isb.DeviceArray.zeros(A.ctx, 32), isb.DeviceArray.from_numpy(A.ctx, np.ones(32))
+    assert L.b200_cg_solve(A.ctx._h, A._h, x._p, b._p, C.byref(opts), None, None, 0) != 0
+    assert b"preconditioner" in L.b200_last_error()
 
 
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 5e-5)])
@@ -219,3 +223,18 @@ def test_nested_solve_inside_a_callback_is_refused(isb):
     with pytest.raises(isb.B200Error, match="inside an operator"):
         isb.cg(isb.B200LinearOperator((n, n), np.float64, inner), np.ones(n))
     assert relerr(isb.cg(A, np.ones(n)), 0.5 * np.ones(n)) <= 1e-12
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 5e-6)])
+def test_chebyshev_general_operator_and_callback_preconditioner(isb, oracle, dtype, tol):
+    """chebyshev! with `mul!` / `ldiv!` callbacks (b200_chebyshev_solve_op; b200_chebyshev_solve forwarding a callback Pl)
+    against the oracle -- the case of the serial backend."""
+    def run(x, A, b, lmin, lmax, d, pk, **kw):
+        csr = isb.B200CSR.from_scipy(sp.csc_matrix(A).astype(x.dtype))
+        jac = isb.JacobiPrec(np.asarray(d, dtype=x.dtype))
+        Pl = None if pk is None else (jac if pk == "jac" else
+                                      isb.FunctionPrec(csr.m_local, x.dtype, lambda y, v: jac.ldiv_(y, v)))
+        op = csr if pk == "cb" else isb.B200LinearOperator.from_csr(csr)
+        x, h = isb.chebyshev_(x, op, b, lmin, lmax, Pl=Pl, log=True, **kw)
+        return x, SimpleNamespace(iters=h.iters, mvps=h.mvps, converged=h.isconverged, hist=h["resnorm"])
+    cases.case_chebyshev_general(oracle, run, dtype, tol)

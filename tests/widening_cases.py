@@ -554,3 +554,36 @@ def case_bicgstabl_general(oracle, run, dtype, tol):
     xs, hs = run(np.zeros(16, dtype), I, np.ones(16, dtype), 2, np.ones(16, dtype), np.ones(16, dtype), None,
                  initial_zero=True)
     assert hs.singular
+
+
+def case_chebyshev_general(oracle, run, dtype, tol):
+    """the general chebyshev! engine (csrc/chebyshev_core.h: callback operator, Pl as Jacobi diagonal or callback) against
+    the oracle's chebyshev_ (bounds from the exact spectrum, widened by 10 %): counts, history, x.
+    run(x0, A, b, lmin, lmax, d, pk, **kw) -> (x, outcome with iters, mvps, converged, hist)."""
+    rng = np.random.default_rng(5)
+    n = 300
+    R = sp.random(n, n, 0.03, random_state=3, format="csc")
+    S = (R + R.T).tocsc()
+    S = (S + sp.diags(np.asarray(np.abs(S).sum(axis=1)).ravel() + 1.0)).tocsc()
+    d = S.diagonal()
+    Ds = sp.diags(1 / np.sqrt(d))
+    ev, evp = np.linalg.eigvalsh(S.toarray()), np.linalg.eigvalsh((Ds @ S @ Ds).toarray())
+    b = rng.standard_normal(n).astype(dtype)
+    Sd = S.astype(dtype)
+    for pk in (None, "jac", "cb"):
+        lo, hi = (ev[0] * 0.9, ev[-1] * 1.1) if pk is None else (evp[0] * 0.9, evp[-1] * 1.1)
+        for iz in (True, False):
+            x0 = np.zeros(n, dtype) if iz else rng.standard_normal(n).astype(dtype)
+            Pl = None if pk is None else oracle.JacobiPrec(d.astype(dtype))
+            xo, ho = oracle.chebyshev_(x0.copy(), Sd, b, lo, hi, Pl=Pl, maxiter=200, log=True, initially_zero=iz)
+            xs, hs = run(x0.copy(), Sd, b, lo, hi, d.astype(dtype), pk, maxiter=200, initially_zero=iz)
+            ro = np.asarray(ho["resnorm"])
+            assert ho.isconverged and hs.converged and abs(hs.iters - ho.iters) <= (0 if dtype == np.float64 else 1)
+            if hs.iters == ho.iters:
+                assert hs.mvps == ho.mvps
+            k = min(hs.iters, ho.iters)
+            assert np.max(np.abs(ro[:k] - np.asarray(hs.hist)[:k])) <= tol * ro[0], (pk, iz)
+            assert np.linalg.norm(xs - xo) <= 20 * tol * np.linalg.norm(xo), (pk, iz)
+    xo, ho = oracle.chebyshev_(np.zeros(n, dtype), Sd, b, ev[0], ev[-1], maxiter=5, reltol=1e-30, log=True, initially_zero=True)
+    xs, hs = run(np.zeros(n, dtype), Sd, b, ev[0], ev[-1], d.astype(dtype), None, maxiter=5, reltol=1e-30, initially_zero=True)
+    assert hs.iters == ho.iters == 5 and not hs.converged and np.linalg.norm(xs - xo) <= 20 * tol * np.linalg.norm(xo)
