@@ -468,6 +468,12 @@ typedef struct {
   b200_precond P;           /* src/lobpcg.jl:226-242 (RPreconditioner)                             */
   int32_t fixed_iterations; /* bench only: never soft-lock, run exactly maxiter steps              */
   int32_t reserved;
+  /* log = true (src/lobpcg.jl:744-745, :881-884): the LOBPCGState of every iteration.  Host arrays (or NULL) with
+   * `blocksize` doubles per iteration, row it-1 = residual norms / Ritz values after iteration it; at most trace_cap
+   * rows are written (results.iterations says how many iterations ran). */
+  double *trace_resnorm;
+  double *trace_ritz;
+  int64_t trace_cap;
 } b200_lobpcg_opts;
 typedef struct {
   int64_t iterations;       /* results.iterations  src/lobpcg.jl:890                               */

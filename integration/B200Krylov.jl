@@ -170,6 +170,7 @@ end
 struct LobpcgOpts
     tol::Float64; maxiter::Int64; largest::Int32; blocksize::Int32; P::Precond
     fixed_iterations::Int32; reserved::Int32
+    trace_resnorm::Ptr{Float64}; trace_ritz::Ptr{Float64}; trace_cap::Int64      # log = true: one row per iteration
 end
 mutable struct LobpcgResult
     iterations::Int64; converged::Int32; status::Int32
@@ -331,14 +332,18 @@ function lobpcg(A::B200CSR{T}, largest::Bool, X0::Matrix{T}; P = nothing, tol::R
     Xd = B200Vector(A.ctx, vec(copy(X0)))                     # X0 is copied  src/lobpcg.jl:830
     λ = Vector{Float64}(undef, bs); rn = Vector{Float64}(undef, bs)
     res = LobpcgResult()
-    o = LobpcgOpts(tol, maxiter, largest, bs, P === nothing ? prec(Identity()) : prec(P), 0, 0)
-    status = ccall((:b200_lobpcg_solve, LIB), Cint,
+    tr_r = log ? Matrix{Float64}(undef, bs, maxiter) : Matrix{Float64}(undef, 0, 0)     # LOBPCGState per iteration :744-745
+    tr_l = log ? Matrix{Float64}(undef, bs, maxiter) : Matrix{Float64}(undef, 0, 0)
+    o = LobpcgOpts(tol, maxiter, largest, bs, P === nothing ? prec(Identity()) : prec(P), 0, 0,
+                   log ? pointer(tr_r) : C_NULL, log ? pointer(tr_l) : C_NULL, log ? maxiter : 0)
+    status = GC.@preserve tr_r tr_l ccall((:b200_lobpcg_solve, LIB), Cint,
                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ref{LobpcgOpts}, Ref{LobpcgResult}, Ptr{Float64}, Ptr{Float64}),
                    A.ctx.h, A.h, Xd.p, n, o, res, λ, rn)
     status == -5 && throw(PosDefException(0))                 # cholesky! in CholQR  src/lobpcg.jl:380
     check(status)
     X = reshape(Array(Xd), n, bs)
-    LOBPCGResults(T.(λ), X, T(tol), T.(rn), Int(res.iterations), Int(maxiter), res.converged != 0, nothing)
+    trace = log ? [LOBPCGState(i, T.(tr_r[:, i]), T.(tr_l[:, i])) for i in 1:min(Int(res.iterations), maxiter)] : nothing
+    LOBPCGResults(T.(λ), X, T(tol), T.(rn), Int(res.iterations), Int(maxiter), res.converged != 0, trace)
 end
 
 # ------------------------------------------------------------------------------------------- qmr!  (SURVEY 8f item 4)
@@ -459,7 +464,7 @@ function lobpcg(A::B200CSR{T}, B::B200CSR{T}, largest::Bool, X0::Matrix{T}; P = 
     n, bs = size(X0)
     Xd = B200Vector(A.ctx, vec(copy(X0)))
     λ = Vector{Float64}(undef, bs); rn = Vector{Float64}(undef, bs); res = LobpcgResult()
-    o = LobpcgOpts(tol, maxiter, largest, bs, P === nothing ? prec(Identity()) : prec(P), 0, 0)
+    o = LobpcgOpts(tol, maxiter, largest, bs, P === nothing ? prec(Identity()) : prec(P), 0, 0, C_NULL, C_NULL, 0)
     con = C === nothing ? C_NULL : B200Constraint(A, B, C).h
     a = as_linop(A); b = as_linop(B)
     status = ccall((:b200_lobpcg_solve_op, LIB), Cint,

@@ -95,7 +95,8 @@ class SvdlResult(C.Structure):
 
 class LobpcgOpts(C.Structure):
     _fields_ = [("tol", C.c_double), ("maxiter", C.c_int64), ("largest", C.c_int32), ("blocksize", C.c_int32),
-                ("P", Precond), ("fixed_iterations", C.c_int32), ("reserved", C.c_int32)]
+                ("P", Precond), ("fixed_iterations", C.c_int32), ("reserved", C.c_int32),
+                ("trace_resnorm", C.c_void_p), ("trace_ritz", C.c_void_p), ("trace_cap", C.c_int64)]
 
 
 class LobpcgResult(C.Structure):

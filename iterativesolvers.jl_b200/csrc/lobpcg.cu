@@ -1277,6 +1277,12 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
       select(w, sub, perm);
       B200_TRY(upload_v_and_update(Z, sub, perm, n2, n3, aR, L.AR, aP, aAP));
     }
+    if (iteration - 1 < o->trace_cap) {                            // log = true: LOBPCGState(iteration, residuals, ritz_values) :744-745
+      for (int j = 0; j < sizeX; ++j) {
+        if (o->trace_resnorm) o->trace_resnorm[(iteration - 1) * sizeX + j] = residuals[j];
+        if (o->trace_ritz) o->trace_ritz[(iteration - 1) * sizeX + j] = ritz[j];
+      }
+    }
     bs = 0;                                                                                         // update_mask! :549-555
     for (int j = 0; j < sizeX; ++j) {
       mask[j] = o->fixed_iterations ? 1 : (residuals[j] > tol);

@@ -80,10 +80,12 @@ int b200_lobpcg_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *B
       A->dtype == B200_F64
           ? lobpcg_general_run<double>(be, &a, B ? &b : nullptr, pfn ? &p : nullptr, (const double *)jac, (const double *)Y,
                                        (const double *)BY, ldy, nc, U, (double *)X_dev, ldx, sizeX, n, opts->largest,
-                                       opts->tol, opts->maxiter, opts->fixed_iterations, lambda_host, resnorm_host, &o)
+                                       opts->tol, opts->maxiter, opts->fixed_iterations, lambda_host, resnorm_host, &o,
+                                       opts->trace_resnorm, opts->trace_ritz, opts->trace_cap)
           : lobpcg_general_run<float>(be, &a, B ? &b : nullptr, pfn ? &p : nullptr, (const float *)jac, (const float *)Y,
                                       (const float *)BY, ldy, nc, U, (float *)X_dev, ldx, sizeX, n, opts->largest,
-                                      opts->tol, opts->maxiter, opts->fixed_iterations, lambda_host, resnorm_host, &o);
+                                      opts->tol, opts->maxiter, opts->fixed_iterations, lambda_host, resnorm_host, &o,
+                                      opts->trace_resnorm, opts->trace_ritz, opts->trace_cap);
   if (st != B200_OK) return st;
   if (res) {
     res->iterations = o.iterations;

@@ -186,7 +186,8 @@ template <typename T, typename B>
 int lobpcg_general_run(B &be, const typename B::Op *A, const typename B::Op *Bop, const typename B::Op *Pop, const T *jac,
                        const T *Y, const T *BY, int64_t ldy, int nc, const double *Ucon, T *Xuser, int64_t ldx,
                        int sizeX, int64_t n, int largest, double tol, int64_t maxiter, int fixed_iterations,
-                       double *lambda_host, double *resnorm_host, LobpcgGenOutcome *out) {
+                       double *lambda_host, double *resnorm_host, LobpcgGenOutcome *out, double *trace_resnorm = nullptr,
+                       double *trace_ritz = nullptr, int64_t trace_cap = 0) {
   const bool generalized = Bop != nullptr;
   if (tol < 0) tol = pow(eps_of<T>(), 0.3);                                          // default_tolerance :751
   if (maxiter < 0) maxiter = 200;                                                    // :865
@@ -363,6 +364,12 @@ int lobpcg_general_run(B &be, const typename B::Op *A, const typename B::Op *Bop
       if ((st = L.copy_block(X, T1, sizeX))) return st;
       if ((st = L.copy_block(AX, T2, sizeX))) return st;
       if ((st = residuals_())) return st;
+    }
+    if (iteration - 1 < trace_cap) {                               // log = true: LOBPCGState(iteration, residuals, ritz_values) :744-745
+      for (int j = 0; j < sizeX; ++j) {
+        if (trace_resnorm) trace_resnorm[(iteration - 1) * sizeX + j] = residuals[j];
+        if (trace_ritz) trace_ritz[(iteration - 1) * sizeX + j] = ritz[j];
+      }
     }
     bs = 0;                                                                           // update_mask! :549-555
     for (int j = 0; j < sizeX; ++j) {

@@ -853,8 +853,9 @@ class LobpcgConstraint:
             pass
 
 
-def _lobpcg_block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, fixed, B=None):
-    """lobpcg!(iterator; ...) -- reference src/lobpcg.jl:865-893 on the device block Xd (overwritten)."""
+def _lobpcg_block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, fixed, B=None, trace=None):
+    """lobpcg!(iterator; ...) -- reference src/lobpcg.jl:865-893 on the device block Xd (overwritten).  `trace`: a list
+    that receives (iteration, residual_norms, ritz_values) per iteration (log = true, :881-884)."""
     n, bs = Xd.shape
     if not not_zeros and not fixed:                            # :869-876 (the constraint itself is applied by the engine)
         nrm = C.c_double()
@@ -865,6 +866,9 @@ def _lobpcg_block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, f
                 rng = rng or np.random.default_rng()
                 col.upload(rng.random(n).astype(A.dtype))      # X[:, j] .= rand.() :872
     opts = _lib.LobpcgOpts(float(tol), int(maxiter), int(bool(largest)), int(bs), precond_to_c(P, A), int(bool(fixed)), 0)
+    if trace is not None:
+        tr_r, tr_l = np.zeros((max(int(maxiter), 1), bs)), np.zeros((max(int(maxiter), 1), bs))
+        opts.trace_resnorm, opts.trace_ritz, opts.trace_cap = tr_r.ctypes.data, tr_l.ctypes.data, int(maxiter)
     res = _lib.LobpcgResult()
     lam = np.zeros(bs, dtype=np.float64)
     rn = np.zeros(bs, dtype=np.float64)
@@ -887,6 +891,9 @@ def _lobpcg_block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, f
     if status == _lib.ERR_BREAKDOWN:
         raise np.linalg.LinAlgError("PosDefException in CholQR (reference src/lobpcg.jl:380)")
     check(status)
+    if trace is not None:                                      # LOBPCGState(iteration, residual_norms, ritz_values) :744-745
+        for i in range(min(int(res.iterations), int(maxiter))):
+            trace.append((i + 1, tr_r[i].astype(A.dtype), tr_l[i].astype(A.dtype)))
     return lam, rn, res
 
 
@@ -927,10 +934,12 @@ def lobpcg(A, largest: bool, X0, nev=None, *, B=None, P=None, C_=None, tol=None,
         raise B200Error("The order of the matrix must be at least 3 times the block size")
     if nev is None:
         con = Cc if isinstance(Cc, LobpcgConstraint) or Cc is None else LobpcgConstraint(A.ctx, n, A.dtype, Cc, B=B)
-        lam, rn, res = _lobpcg_block(A, largest, Xd, P, con, tol, maxiter, not_zeros, rng, _fixed_iterations, B=B)
+        trace = [] if log else None
+        lam, rn, res = _lobpcg_block(A, largest, Xd, P, con, tol, maxiter, not_zeros, rng, _fixed_iterations, B=B,
+                                     trace=trace)
         X = Xd.numpy() if host else Xd
         return LOBPCGResults(lam.astype(A.dtype), X, float(tol), rn.astype(A.dtype), int(res.iterations), int(maxiter),
-                             bool(res.converged), [])
+                             bool(res.converged), trace or [])
     # ---- nev > blocksize driver :928-962
     nev = int(nev)
     rng = rng or np.random.default_rng()
@@ -946,8 +955,13 @@ def lobpcg(A, largest: bool, X0, nev=None, *, B=None, P=None, C_=None, tol=None,
     X_all = np.zeros((n, nev), dtype=A.dtype, order="F")
     iterations, conv = [], np.zeros(nev, dtype=bool)
 
+    traces = []                                                # results.trace: one LOBPCGTrace per batch :74, :88
+
     def run(nz):
-        lam, rn, res = _lobpcg_block(A, largest, Xd, P, con, tol, maxiter, nz, rng, False)
+        tr = [] if log else None
+        lam, rn, res = _lobpcg_block(A, largest, Xd, P, con, tol, maxiter, nz, rng, False, trace=tr)
+        if log:
+            traces.append(tr)
         return lam, rn, res, Xd.numpy()
 
     def append(r, n1, n2):                                     # append! :79-91
@@ -979,7 +993,7 @@ def lobpcg(A, largest: bool, X0, nev=None, *, B=None, P=None, C_=None, tol=None,
             append(r, converged_x, sizeX)
             converged_x += sizeX
     con.close()
-    return LOBPCGResults(lam_all, X_all, float(tol), rn_all, iterations, int(maxiter), conv, [])
+    return LOBPCGResults(lam_all, X_all, float(tol), rn_all, iterations, int(maxiter), conv, traces)
 
 
 # ------------------------------------------------------------------------------------------------

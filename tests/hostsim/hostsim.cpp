@@ -505,7 +505,8 @@ EXPORT void hostsim_dense_svd(int n, const double *A, double *U, double *S, doub
 EXPORT int hostsim_lobpcg_general(int is_f64, const hostsim_csr *A, const hostsim_csr *Bm, const hostsim_csr *Pm,
                                   const void *jac, const void *Y, int nc, void *X, int sizeX, int largest, double tol,
                                   int64_t maxiter, int fixed, double *lambda, double *resnorm, int order, int split,
-                                  int64_t *iterations, int *converged, int *status) {
+                                  int64_t *iterations, int *converged, int *status, double *trace_resnorm,
+                                  double *trace_ritz, int64_t trace_cap) {
   HostBackend be;
   be.order = order;
   be.split = split;
@@ -538,7 +539,8 @@ EXPORT int hostsim_lobpcg_general(int is_f64, const hostsim_csr *A, const hostsi
       if (b200::con_cholesky_upper(U.data(), nc)) return -5;
     }
     return b200::lobpcg_general_run<T>(be, &a, Bm ? &b : nullptr, Pm ? &pm : nullptr, (const T *)jac, Yp, BYp, n, nc,
-                                       U.data(), (T *)X, n, sizeX, n, largest, tol, maxiter, fixed, lambda, resnorm, &o);
+                                       U.data(), (T *)X, n, sizeX, n, largest, tol, maxiter, fixed, lambda, resnorm, &o,
+                                       trace_resnorm, trace_ritz, trace_cap);
   };
   st = is_f64 ? body(double()) : body(float());
   *iterations = o.iterations; *converged = o.converged; *status = o.status;

@@ -394,12 +394,15 @@ def lobpcg_general(A, largest, X0, *, B=None, Pm=None, jac=None, C_=None, tol=-1
     d = None if jac is None else np.ascontiguousarray(jac, dtype=dt)
     Y = None if C_ is None else np.asfortranarray(C_, dtype=dt)
     lam, rn = np.zeros(sizeX), np.zeros(sizeX)
+    tr_r, tr_l = np.zeros((max(maxiter, 1), sizeX)), np.zeros((max(maxiter, 1), sizeX))   # LOBPCGState per iteration (log = true)
     it, conv, status = C.c_int64(), C.c_int(), C.c_int()
     vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
     st = lib().hostsim_lobpcg_general(C.c_int(dt == np.float64), C.byref(Ac.c), C.byref(Bc.c) if Bc else None,
                                       C.byref(Pc.c) if Pc else None, vp(d), vp(Y), C.c_int(0 if Y is None else Y.shape[1]),
                                       vp(X), C.c_int(sizeX), C.c_int(bool(largest)), C.c_double(tol), C.c_int64(maxiter),
                                       C.c_int(fixed), vp(lam), vp(rn), C.c_int(order), C.c_int(split), C.byref(it),
-                                      C.byref(conv), C.byref(status))
+                                      C.byref(conv), C.byref(status), vp(tr_r), vp(tr_l), C.c_int64(maxiter))
     assert st == 0, st
-    return dict(lam=lam, X=X, resnorm=rn, iterations=it.value, converged=bool(conv.value), status=status.value)
+    k = min(it.value, maxiter)
+    return dict(lam=lam, X=X, resnorm=rn, iterations=it.value, converged=bool(conv.value), status=status.value,
+                trace=[(i + 1, tr_r[i].copy(), tr_l[i].copy()) for i in range(k)])

@@ -840,6 +840,15 @@ def test_python_general_lobpcg_path_with_a_fake_library(monkeypatch):
     assert calls[-1][1][2] is None                                                  # B = NULL
     with pytest.raises(isb.B200Error):
         isb.lobpcg(A, False, rng.random((30, 2)), 4, B=B)                           # generalized nev driver
+    # log = true: the option block carries two host arrays of maxiter x blocksize doubles for the per-iteration states
+    calls.clear()
+    r = isb.lobpcg(A, False, rng.random((30, 2)), B=B, not_zeros=True, log=True, maxiter=17)
+    opts = [a._obj for a in calls[-1][1] if isinstance(getattr(a, "_obj", None), S._lib.LobpcgOpts)][0]
+    assert opts.trace_cap == 17 and opts.trace_resnorm and opts.trace_ritz and r.trace == []   # (the fake ran 0 iterations)
+    calls.clear()
+    isb.lobpcg(A, False, rng.random((30, 2)), B=B, not_zeros=True)
+    opts = [a._obj for a in calls[-1][1] if isinstance(getattr(a, "_obj", None), S._lib.LobpcgOpts)][0]
+    assert opts.trace_cap == 0 and not opts.trace_resnorm and not opts.trace_ritz
 
 
 @pytest.mark.parametrize("block_size,nev", [(1, 3), (2, 5), (3, 6), (4, 8)])
@@ -883,13 +892,15 @@ def test_python_nev_driver_over_the_serial_backend(monkeypatch, sim, block_size,
         def close(self):
             pass
 
-    def block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, fixed, B=None):
+    def block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, fixed, B=None, trace=None):
         assert P is None and B is None and not fixed
         Y = None if constraint is None or constraint.Y.shape[1] == 0 else constraint.Y
         r = sim.lobpcg_general(A.M, largest, Xd.a, C_=Y, tol=tol, maxiter=maxiter)
         if r["status"]:
             raise np.linalg.LinAlgError("PosDefException")
         Xd.a[...] = r["X"]
+        if trace is not None:
+            trace.extend(r["trace"])
         return r["lam"], r["resnorm"], SimpleNamespace(iterations=r["iterations"], converged=r["converged"])
 
     monkeypatch.setattr(S, "DeviceArray", Arr)

@@ -117,3 +117,22 @@ def test_general_engine_equals_tuned_engine_on_the_standard_problem(isb, oracle)
     r2 = isb.lobpcg(isb.B200LinearOperator.from_csr(A), False, X0, tol=1e-6, maxiter=300)
     assert r1.converged and r2.converged and abs(r1.iterations - r2.iterations) <= max(3, r1.iterations // 10)
     assert np.abs(np.sort(r1.lam) - np.sort(r2.lam)).max() <= 1e-8
+
+
+@pytest.mark.parametrize("general", [False, True])
+def test_lobpcg_log_trace_matches_oracle(isb, oracle, general):
+    """log = true (reference src/lobpcg.jl:744-745, :881-884): one (iteration, residual_norms, ritz_values) state per
+    iteration, from the tuned and from the general engine, against the oracle's trace."""
+    rng = np.random.default_rng(SEED)
+    O = oracle.laplace_matrix(np.float64, 8, 3, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    X0 = rng.random((O.n, 4))
+    op = isb.B200LinearOperator.from_csr(A) if general else A
+    r = isb.lobpcg(op, False, X0, tol=1e-6, maxiter=300, log=True)
+    ro = oracle.lobpcg(O, False, X0, tol=1e-6, maxiter=300, log=True)
+    assert r.converged and len(r.trace) == r.iterations and [t[0] for t in r.trace] == list(range(1, r.iterations + 1))
+    assert np.array_equal(r.trace[-1][1], r.residual_norms) and np.array_equal(r.trace[-1][2], r.lam)
+    for (i1, rn1, l1), (i2, rn2, l2) in list(zip(r.trace, ro.trace))[:12]:
+        assert i1 == i2 and np.abs(l1 - l2).max() <= 1e-8 * np.abs(l2).max()
+        assert np.abs(rn1 - rn2).max() <= 1e-5 * np.abs(rn2).max() + 1e-8
+    assert isb.lobpcg(op, False, X0, tol=1e-6, maxiter=300).trace == []

@@ -394,6 +394,12 @@ def case_lobpcg_general(oracle, run, dtype, tol, ltol, same_arithmetic=True):
                 assert r["status"] == 0 and ro.converged and r["converged"]
                 assert same_count(r["iterations"], ro.iterations), (r["iterations"], ro.iterations)
                 assert np.abs(np.sort(ro.lam) - np.sort(r["lam"])).max() <= ltol * np.abs(ro.lam).max()
+                if "trace" in r and exact64 and same_arithmetic:            # log = true: the LOBPCGState of every iteration
+                    rt = oracle.lobpcg(Md, largest, X0, B=Bd, tol=tol, maxiter=300, not_zeros=True, log=True).trace
+                    assert len(r["trace"]) == len(rt) == ro.iterations
+                    for (i1, rn1, l1), (i2, rn2, l2) in zip(r["trace"], rt):
+                        assert i1 == i2 and np.abs(l1 - l2).max() <= 1e-8 * np.abs(ro.lam).max()
+                        assert np.abs(rn1 - rn2).max() <= 1e-4 * np.abs(rn2).max() + 1e-2 * tol   # (residuals near tol carry rounding noise)
                 X = np.asarray(r["X"], dtype=np.float64)
                 assert np.max(np.linalg.norm(M @ X - Bq @ X * r["lam"][None, :], axis=0)) <= 4 * tol
                 assert np.abs(X.T @ Bq @ X - np.eye(bs)).max() <= 2 * n * tol          # test/lobpcg.jl:62-69
@@ -426,8 +432,12 @@ def case_nev_driver(lobpcg, make_A, block_size, nev):
     tol = 1e-6
     for largest in (False, True):
         ex = d[::-1] if largest else d
-        r = lobpcg(A, largest, rng.random((n, block_size)), nev, tol=tol, maxiter=2000, rng=rng)
+        r = lobpcg(A, largest, rng.random((n, block_size)), nev, tol=tol, maxiter=2000, rng=rng, log=True)
         assert r.X.shape == (n, nev) and len(r.iterations) == -(-nev // block_size) and np.all(r.converged)
+        assert len(r.trace) == len(r.iterations)                    # one LOBPCGTrace per batch (src/lobpcg.jl:74, :88)
+        for tr, its in zip(r.trace, r.iterations):
+            assert len(tr) == its and [t[0] for t in tr] == list(range(1, its + 1))
+            assert np.all(tr[-1][1] <= tol) and tr[-1][1].shape == tr[-1][2].shape
         assert np.max(np.linalg.norm(M @ r.X - r.X * r.lam[None, :], axis=0)) <= tol
         assert np.allclose(r.X.T @ r.X, np.eye(nev), atol=2 * n * tol)
         assert np.allclose(np.sort(r.lam), np.sort(ex[:nev]), atol=1e-5)
