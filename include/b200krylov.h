@@ -548,13 +548,14 @@ B200_API int b200_lobpcg_solve_constrained(b200_ctx *ctx, const b200_csr *A, voi
  * `diag` points to the preconditioner's b200_linop), constraint in the B inner product.  Block sizes 1..16.  The standard
  * problem on a b200_csr with Identity / Jacobi is faster through b200_lobpcg_solve[_constrained] (tuned engine).
  * b200_csr_as_linop fills a b200_linop that applies a b200_csr (so that CSR and callback operators can be mixed);
- * b200_lobpcg_constraint_create_b is Constraint(Y, B, X) for B != nothing (:161-186). */
+ * b200_lobpcg_constraint_create_b is Constraint(Y, B, X) for B != nothing (:161-186); nc may be 0 with `capacity` columns
+ * reserved for b200_lobpcg_constraint_append, which then also forms B * X for the new columns (update!, :188-206). */
 B200_API int b200_csr_as_linop(const b200_csr *A, b200_linop *out);
 B200_API int b200_lobpcg_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *B, void *X_dev, int64_t ldx,
                                   const b200_lobpcg_opts *opts, const b200_lobpcg_constraint *C, b200_lobpcg_result *res,
                                   double *lambda_host, double *resnorm_host);
 B200_API int b200_lobpcg_constraint_create_b(b200_ctx *ctx, const b200_linop *B, int64_t n_local, const void *Y_dev,
-                                             int64_t ldy, int nc, int dtype, b200_lobpcg_constraint **out);
+                                             int64_t ldy, int nc, int capacity, int dtype, b200_lobpcg_constraint **out);
 
 /* Host-side dense helpers used by the engines for their O(blocksize^3) pieces (fp64, column-major,
  * n <= 64): eigen!(Hermitian(A)[, Hermitian(B)]) -- eigenvalues ascending in w, eigenvectors in the

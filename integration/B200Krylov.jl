@@ -452,11 +452,11 @@ function as_linop(A::B200CSR{T}) where {T}
     r = Ref{LinOp}()
     check(ccall((:b200_csr_as_linop, LIB), Cint, (Ptr{Cvoid}, Ref{LinOp}), A.h, r)); r[]
 end
-function B200Constraint(A::B200CSR{T}, B::B200CSR{T}, Y::Matrix{T}) where {T}           # Constraint(Y, B, X) :162-186
+function B200Constraint(A::B200CSR{T}, B::B200CSR{T}, Y::Matrix{T}; capacity::Integer = size(Y, 2)) where {T}   # Constraint(Y, B, X) :162-186
     Yd = B200Vector(A.ctx, vec(Y)); r = Ref{Ptr{Cvoid}}(); b = as_linop(B)
     check(ccall((:b200_lobpcg_constraint_create_b, LIB), Cint,
-                (Ptr{Cvoid}, Ref{LinOp}, Int64, Ptr{Cvoid}, Int64, Cint, Cint, Ref{Ptr{Cvoid}}),
-                A.ctx.h, b, size(Y, 1), Yd.p, size(Y, 1), size(Y, 2), dtype_code(T), r))
+                (Ptr{Cvoid}, Ref{LinOp}, Int64, Ptr{Cvoid}, Int64, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
+                A.ctx.h, b, size(Y, 1), Yd.p, size(Y, 1), size(Y, 2), capacity, dtype_code(T), r))
     finalizer(c -> ccall((:b200_lobpcg_constraint_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), B200Constraint{T}(r[], A.ctx))
 end
 function lobpcg(A::B200CSR{T}, B::B200CSR{T}, largest::Bool, X0::Matrix{T}; P = nothing, C = nothing,

@@ -219,7 +219,7 @@ SIGNATURES = {
     "b200_csr_as_linop": (_INT, [_P, C.POINTER(LinOp)]),
     "b200_lobpcg_solve_op": (_INT, [_P, C.POINTER(LinOp), C.POINTER(LinOp), _P, _I64, C.POINTER(LobpcgOpts), _P,
                                     C.POINTER(LobpcgResult), _P, _P]),
-    "b200_lobpcg_constraint_create_b": (_INT, [_P, C.POINTER(LinOp), _I64, _P, _I64, _INT, _INT, C.POINTER(_P)]),
+    "b200_lobpcg_constraint_create_b": (_INT, [_P, C.POINTER(LinOp), _I64, _P, _I64, _INT, _INT, _INT, C.POINTER(_P)]),
     "b200_dense_sygv_host": (_INT, [_INT, _P, _P, _P, _P]),
 }
 

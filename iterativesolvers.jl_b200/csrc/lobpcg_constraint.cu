@@ -80,13 +80,18 @@ int b200_lobpcg_constraint_create(b200_ctx *ctx, int64_t n_local, const void *Y_
 int b200_lobpcg_constraint_append(b200_ctx *ctx, b200_lobpcg_constraint *c, const void *X_dev, int64_t ldx, int k) {
   B200_REQUIRE(ctx && c && c->ctx == ctx && k >= 0 && (k == 0 || (X_dev && ldx >= c->n)), "bad arguments");
   B200_REQUIRE(c->nc + k <= c->cap, "constraint capacity %d exceeded (%d + %d columns)", c->cap, c->nc, k);
-  B200_REQUIRE(!c->BY, "append is available for the standard problem only (the generalized update! needs B*X)");
   if (k == 0) return B200_OK;
   B200_CUDA(cudaSetDevice(ctx->device));
   const size_t vs = dtype_size(c->dtype);
   if (c->n > 0)
     B200_CUDA(cudaMemcpy2DAsync((char *)c->Y + vs * (size_t)c->ld * c->nc, vs * c->ld, X_dev, vs * ldx, vs * c->n, k,
                                 cudaMemcpyDeviceToDevice, ctx->stream));
+  if (c->BY) {                                          // generalized problem: BY[:, new] = B * X  (update!(c, X, BX) :188-206)
+    CudaBackend be{ctx};
+    CudaOp bop{nullptr, &c->Bfn};
+    for (int j = 0; j < k; ++j)
+      B200_TRY(be.apply(&bop, (char *)c->Y + vs * (size_t)c->ld * (c->nc + j), (char *)c->BY + vs * (size_t)c->ld * (c->nc + j)));
+  }
   // update! (reference src/lobpcg.jl:188-206): the factor is extended by an identity block -- the appended columns
   // are orthonormal Ritz vectors, orthogonal to the old Y by construction
   const int nc0 = c->nc, nc1 = c->nc + k;

@@ -13,6 +13,7 @@ struct b200_lobpcg_constraint {
   int nc = 0, cap = 0;      // columns in use / allocated
   void *Y = nullptr;        // device, column-major n x cap (own copy: the reference keeps C alive the same way)
   void *BY = nullptr;       // generalized problem: B*Y (b200_lobpcg_constraint_create_b); nullptr: BY aliases Y (:163-164)
+  b200_linop Bfn{};         // generalized problem: copy of the caller's B descriptor (update! needs B*X, :188-206)
   double *g_dev = nullptr;  // device scratch: cap x 16 doubles
   std::vector<double> U;    // host: upper Cholesky factor of Y'Y, nc x nc column-major
   std::vector<double> g_host;

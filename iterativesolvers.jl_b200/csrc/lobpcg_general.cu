@@ -63,7 +63,7 @@ int b200_lobpcg_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *B
   }
   if (C) {
     B200_REQUIRE(C->ctx == ctx && C->dtype == A->dtype && C->n == n, "the constraint does not match the operator");
-    B200_REQUIRE((C->BY != nullptr) == (B != nullptr) || C->nc == 0,
+    B200_REQUIRE((C->BY != nullptr) == (B != nullptr) || (C->nc == 0 && !C->BY),
                  "generalized problems need a constraint built with b200_lobpcg_constraint_create_b (and vice versa)");
   }
   B200_CUDA(cudaSetDevice(ctx->device));
@@ -103,12 +103,14 @@ int b200_lobpcg_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *B
 // Constraint(Y, B, X) for the generalized problem (reference src/lobpcg.jl:161-186): BY = B*Y is kept next to Y and
 // the factor is that of Y' BY.
 int b200_lobpcg_constraint_create_b(b200_ctx *ctx, const b200_linop *B, int64_t n_local, const void *Y_dev, int64_t ldy,
-                                    int nc, int dtype, b200_lobpcg_constraint **out) {
-  B200_REQUIRE(ctx && out && B && nc >= 1 && Y_dev && ldy >= n_local, "bad arguments");
+                                    int nc, int capacity, int dtype, b200_lobpcg_constraint **out) {
+  B200_REQUIRE(ctx && out && B && nc >= 0 && (nc == 0 || (Y_dev && ldy >= n_local)), "bad arguments");
   B200_TRY(check_linop(B, "B"));
   B200_REQUIRE(B->dtype == dtype && B->m_local == n_local && B->n_local == n_local, "B does not match the constraint");
   b200_lobpcg_constraint *c = nullptr;
-  B200_TRY(b200_lobpcg_constraint_create(ctx, n_local, nullptr, n_local, 0, nc, dtype, &c));   // storage only
+  B200_TRY(b200_lobpcg_constraint_create(ctx, n_local, nullptr, n_local, 0, std::max(std::max(nc, capacity), 1), dtype,
+                                         &c));                                                  // storage only
+  c->Bfn = *B;
   const size_t vs = dtype_size(dtype);
   auto fail = [&](int s) {
     b200_lobpcg_constraint_destroy(c);
@@ -118,7 +120,7 @@ int b200_lobpcg_constraint_create_b(b200_ctx *ctx, const b200_linop *B, int64_t 
     set_error("constraint: cudaMalloc failed");
     return fail(B200_ERR_ALLOC);
   }
-  if (n_local > 0 &&
+  if (n_local > 0 && nc > 0 &&
       cudaMemcpy2DAsync(c->Y, vs * c->ld, Y_dev, vs * ldy, vs * n_local, nc, cudaMemcpyDeviceToDevice, ctx->stream) !=
           cudaSuccess) {
     set_error("constraint: copy of Y failed");

@@ -814,12 +814,10 @@ class LobpcgConstraint:
                 raise ValueError("the constraint must have as many rows as the operator")
         code = _lib.F64 if self.dtype == np.float64 else _lib.F32
         if B is not None:                                      # Constraint(Y, B, X) with BY = B*Y  src/lobpcg.jl:161-186
-            if not nc:
-                raise ValueError("a generalized-problem constraint needs at least one column")
             bs, bop = _linop_struct(B)
-            self._keep = (bs, B)
-            check(_call_op(lib().b200_lobpcg_constraint_create_b, (bop,), ctx._h, C.byref(bs), self.n, as_device_ptr(Yd),
-                           self.n, nc, code, C.byref(self._h)))
+            self._keep, self._bop = (bs, B), bop               # append applies B again (update!, :188-206)
+            check(_call_op(lib().b200_lobpcg_constraint_create_b, (bop,), ctx._h, C.byref(bs), self.n,
+                           as_device_ptr(Yd) if nc else None, self.n, nc, int(max(capacity, nc)), code, C.byref(self._h)))
         else:
             check(lib().b200_lobpcg_constraint_create(ctx._h, self.n, as_device_ptr(Yd) if nc else None, self.n, nc,
                                                       int(max(capacity, nc)), code, C.byref(self._h)))
@@ -833,7 +831,8 @@ class LobpcgConstraint:
     def append(self, Xd: DeviceArray, k=None):
         """update!(constraint, X[:, 1:k], ...): the first k columns of the device block Xd join the basis."""
         k = Xd.shape[1] if k is None else int(k)
-        check(lib().b200_lobpcg_constraint_append(self.ctx._h, self._h, as_device_ptr(Xd), Xd.shape[0], k))
+        check(_call_op(lib().b200_lobpcg_constraint_append, (getattr(self, "_bop", None),), self.ctx._h, self._h,
+                       as_device_ptr(Xd), Xd.shape[0], k))
 
     def apply_(self, Xd: DeviceArray):
         """constr!(X, temp): X <- X - Y (Y'Y \\ Y'X), in place on a device block."""
@@ -901,7 +900,7 @@ def lobpcg(A, largest: bool, X0, nev=None, *, B=None, P=None, C_=None, tol=None,
            not_zeros=False, rng=None, _fixed_iterations=False, **kw):
     """lobpcg(A, [B,] largest, X0; P, C, tol, maxiter, not_zeros) -> LOBPCGResults   reference src/lobpcg.jl:824-839
     lobpcg(A, [B,] largest, nev::Int; ...)   (X0 = rand(n, nev), not_zeros = true)   :787-792
-    lobpcg(A, largest, X0, nev; ...)    (batches of size(X0, 2) with deflation)       :925-962
+    lobpcg(A, [B,] largest, X0, nev; ...)  (batches of size(X0, 2) with deflation)    :925-962
     `B=` (a B200CSR or B200LinearOperator) selects the generalized problem A x = λ B x; A may be a
     B200LinearOperator and P a FunctionPrec (callbacks): those three go through the general engine, the standard problem
     on a B200CSR with Identity / JacobiPrec through the tuned one.  The constraint is the keyword `C` (spelled `C=`
@@ -913,9 +912,6 @@ def lobpcg(A, largest: bool, X0, nev=None, *, B=None, P=None, C_=None, tol=None,
     _check_operator(A, linop_ok=True)
     if B is not None:
         _check_operator(B, linop_ok=True)
-        if nev is not None:
-            raise B200Error("the nev > blocksize driver is implemented for the standard problem only "
-                            "(the generalized update! needs B*X of every converged batch)")
     if tol is None:
         tol = _eps(A.dtype) ** 0.3                             # default_tolerance  src/lobpcg.jl:751
     if isinstance(X0, (int, np.integer)):                      # lobpcg(A, largest, nev) :790-792
@@ -949,7 +945,7 @@ def lobpcg(A, largest: bool, X0, nev=None, *, B=None, P=None, C_=None, tol=None,
     elif not host:
         Xd = DeviceArray.from_numpy(A.ctx, Xd.numpy())         # X0 is not overwritten by this form
     sizeC = 0 if Cc is None else int(Cc.shape[1])
-    con = LobpcgConstraint(A.ctx, n, A.dtype, Cc, capacity=sizeC + (nev // sizeX) * sizeX)       # :501-508, :519
+    con = LobpcgConstraint(A.ctx, n, A.dtype, Cc, capacity=sizeC + (nev // sizeX) * sizeX, B=B)  # :501-508, :519
     lam_all = np.zeros(nev, dtype=A.dtype)
     rn_all = np.zeros(nev, dtype=A.dtype)
     X_all = np.zeros((n, nev), dtype=A.dtype, order="F")
@@ -959,7 +955,7 @@ def lobpcg(A, largest: bool, X0, nev=None, *, B=None, P=None, C_=None, tol=None,
 
     def run(nz):
         tr = [] if log else None
-        lam, rn, res = _lobpcg_block(A, largest, Xd, P, con, tol, maxiter, nz, rng, False, trace=tr)
+        lam, rn, res = _lobpcg_block(A, largest, Xd, P, con, tol, maxiter, nz, rng, False, B=B, trace=tr)
         if log:
             traces.append(tr)
         return lam, rn, res, Xd.numpy()

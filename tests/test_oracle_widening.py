@@ -779,7 +779,7 @@ def test_oracle_lobpcg_generalized_reference_properties(oracle):
 def test_python_general_lobpcg_path_with_a_fake_library(monkeypatch):
     """isb.lobpcg(A, largest, X0, B=...) / callback operator / FunctionPrec go to b200_lobpcg_solve_op with b200_linop
     structs made by b200_csr_as_linop (CSR operands: no Python in the loop) or carrying the Python thunk; a generalized
-    constraint is built with b200_lobpcg_constraint_create_b; the generalized nev driver is refused."""
+    constraint is built with b200_lobpcg_constraint_create_b."""
     import ctypes as C
     from importlib import import_module
     import iterativesolvers_jl_b200 as isb
@@ -838,8 +838,6 @@ def test_python_general_lobpcg_path_with_a_fake_library(monkeypatch):
     opts = [a._obj for a in calls[-1][1] if isinstance(getattr(a, "_obj", None), S._lib.LobpcgOpts)][0]
     assert opts.P.kind == 2 and opts.P.diag == C.addressof(Pl.op._c)
     assert calls[-1][1][2] is None                                                  # B = NULL
-    with pytest.raises(isb.B200Error):
-        isb.lobpcg(A, False, rng.random((30, 2)), 4, B=B)                           # generalized nev driver
     # log = true: the option block carries two host arrays of maxiter x blocksize doubles for the per-iteration states
     calls.clear()
     r = isb.lobpcg(A, False, rng.random((30, 2)), B=B, not_zeros=True, log=True, maxiter=17)
@@ -880,7 +878,6 @@ def test_python_nev_driver_over_the_serial_backend(monkeypatch, sim, block_size,
 
     class Con:                                           # LobpcgConstraint stand-in: the basis, grown by append
         def __init__(self, ctx, n, dtype, Y=None, capacity=0, B=None):
-            assert B is None
             self.Y = np.zeros((n, 0), dtype=dtype) if Y is None else np.array(Y.a if isinstance(Y, Arr) else Y, dtype=dtype)
             self.capacity = max(capacity, self.Y.shape[1])
 
@@ -893,9 +890,9 @@ def test_python_nev_driver_over_the_serial_backend(monkeypatch, sim, block_size,
             pass
 
     def block(A, largest, Xd, P, constraint, tol, maxiter, not_zeros, rng, fixed, B=None, trace=None):
-        assert P is None and B is None and not fixed
+        assert P is None and not fixed
         Y = None if constraint is None or constraint.Y.shape[1] == 0 else constraint.Y
-        r = sim.lobpcg_general(A.M, largest, Xd.a, C_=Y, tol=tol, maxiter=maxiter)
+        r = sim.lobpcg_general(A.M, largest, Xd.a, B=None if B is None else B.M, C_=Y, tol=tol, maxiter=maxiter)
         if r["status"]:
             raise np.linalg.LinAlgError("PosDefException")
         Xd.a[...] = r["X"]
@@ -914,6 +911,8 @@ def test_python_nev_driver_over_the_serial_backend(monkeypatch, sim, block_size,
         return SimpleNamespace(M=sp.csr_matrix(M), ctx=None, dtype=np.dtype(np.float64), m_local=n, n_global=n, m_global=n)
 
     cases.case_nev_driver(isb.lobpcg, make_A, block_size, nev)
+    if block_size == 2:
+        cases.case_nev_driver_generalized(isb.lobpcg, make_A)
 
 
 # ------------------------------------------------------------------------------------------ general gmres! engine

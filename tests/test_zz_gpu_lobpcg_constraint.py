@@ -136,3 +136,9 @@ def test_lobpcg_log_trace_matches_oracle(isb, oracle, general):
         assert i1 == i2 and np.abs(l1 - l2).max() <= 1e-8 * np.abs(l2).max()
         assert np.abs(rn1 - rn2).max() <= 1e-5 * np.abs(rn2).max() + 1e-8
     assert isb.lobpcg(op, False, X0, tol=1e-6, maxiter=300).trace == []
+
+
+def test_generalized_nev_driver(isb):
+    """lobpcg(A, B, largest, X0, nev): the deflation basis of the generalized problem grows through
+    b200_lobpcg_constraint_append, which forms B * X for the new columns."""
+    cases.case_nev_driver_generalized(isb.lobpcg, lambda M: isb.B200CSR.from_scipy(sp.csc_matrix(M)))

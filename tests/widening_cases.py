@@ -597,3 +597,25 @@ def case_chebyshev_general(oracle, run, dtype, tol):
     xo, ho = oracle.chebyshev_(np.zeros(n, dtype), Sd, b, ev[0], ev[-1], maxiter=5, reltol=1e-30, log=True, initially_zero=True)
     xs, hs = run(np.zeros(n, dtype), Sd, b, ev[0], ev[-1], d.astype(dtype), None, maxiter=5, reltol=1e-30, initially_zero=True)
     assert hs.iters == ho.iters == 5 and not hs.converged and np.linalg.norm(xs - xo) <= 20 * tol * np.linalg.norm(xo)
+
+
+def case_nev_driver_generalized(lobpcg, make_A):
+    """lobpcg(A, B, largest, X0, nev) (reference src/lobpcg.jl:925-962 with B given): batches of 2, five pairs, against the
+    dense generalized eigenproblem; residuals A x - lambda B x, B-orthonormality across the batches (the deflation basis is
+    kept B-orthogonal through update!(constraint, X, BX), :188-206)."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(SEED)
+    n = 60
+    M, d = separated_spectrum_matrix(n)
+    Bm = rng.standard_normal((n, n))
+    Bm = Bm @ Bm.T / n + 2 * np.eye(n)
+    ex = sla.eigh(M, Bm, eigvals_only=True)
+    A, B = make_A(M), make_A(Bm)
+    tol = 1e-6
+    for largest in (False, True):
+        want = ex[::-1][:5] if largest else ex[:5]
+        r = lobpcg(A, largest, rng.random((n, 2)), 5, B=B, tol=tol, maxiter=2000, rng=rng)
+        assert r.X.shape == (n, 5) and len(r.iterations) == 3 and np.all(r.converged)
+        assert np.max(np.linalg.norm(M @ r.X - Bm @ r.X * r.lam[None, :], axis=0)) <= 4 * tol
+        assert np.allclose(r.X.T @ Bm @ r.X, np.eye(5), atol=2 * n * tol)
+        assert np.allclose(np.sort(r.lam), np.sort(want), atol=1e-5 * np.abs(ex).max())
