@@ -493,7 +493,7 @@ typedef struct {
   int32_t nsv;              /* 6                          src/svdl.jl:158   (<=0: default)                          */
   int32_t k;                /* 2nsv Lanczos vectors       src/svdl.jl:158   (<=0: default; at most 64)              */
   int32_t j;                /* nsv vectors kept at restart src/svdl.jl:178  (<=0: default)                          */
-  int32_t method;           /* 0 = :ritz (src/svdl.jl:376-404); :harmonic (:424-520) is not implemented             */
+  int32_t method;           /* 0 = :ritz (thickrestart! src/svdl.jl:376-404), 1 = :harmonic (harmonicrestart! :424-493) */
   int64_t maxiter;          /* minimum(size(A))           src/svdl.jl:159   (<0: default)                           */
   double tol, reltol;       /* sqrt(eps()) each           src/svdl.jl:158,179 (<0: default)                         */
   int32_t dolock;           /* src/svdl.jl:181, :214-221                                                            */

@@ -489,13 +489,13 @@ function svdl(A::B200CSR{T}; nsv::Int = 6, k::Int = 2nsv, tol::Real = √eps(), 
                                method::Symbol = :ritz, log::Bool = false, j::Int = nsv, reltol::Real = √eps(),
                                v0::Vector{T} = (x = randn(T, size(A, 2)); x ./ norm(x)), vecs::Symbol = :none,
                                dolock::Bool = false) where {T}
-    method == :ritz || throw(ArgumentError("Unknown restart method $method"))
+    method in (:ritz, :harmonic) || throw(ArgumentError("Unknown restart method $method"))     # src/svdl.jl:193-200
     m, n = size(A); At = adjoint(A)
     v0d = B200Vector(A.ctx, v0); res = SvdlResult(); σ = Vector{Float64}(undef, nsv)
     Ud = vecs in (:left, :both) ? B200Vector{T}(A.ctx, m * nsv) : nothing
     Vd = vecs in (:right, :both) ? B200Vector{T}(A.ctx, n * nsv) : nothing
     ritz = zeros(k, maxiter); resn = zeros(nsv, maxiter); conv = zeros(Int32, nsv, maxiter); betas = zeros(maxiter); B = zeros(k, k)
-    o = SvdlOpts(nsv, k, j, 0, maxiter, tol, reltol, dolock, 0)
+    o = SvdlOpts(nsv, k, j, method == :harmonic ? 1 : 0, maxiter, tol, reltol, dolock, 0)
     check(ccall((:b200_svdl, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ref{SvdlOpts}, Ref{SvdlResult}, Ptr{Float64}, Ptr{Cvoid}, Int64,
                  Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),

@@ -12,7 +12,10 @@ int svdl_dispatch(b200_ctx *ctx, const CudaOp &A, const CudaOp &At, int dtype, i
                   int64_t n_global, const void *v0_dev, const b200_svdl_opts *o, b200_svdl_result *res,
                   double *sigma_host, void *U_dev, int64_t ldu, void *V_dev, int64_t ldv, double *hist_ritz,
                   double *hist_resnorm, int32_t *hist_conv, double *hist_betas, double *B_host) {
-  B200_REQUIRE(o->method == 0, "method = :harmonic is not implemented (reference src/svdl.jl:424-520); use :ritz");
+  B200_REQUIRE(o->method == 0 || o->method == 1, "Unknown restart method %d (0 = :ritz, 1 = :harmonic; src/svdl.jl:193-200)",
+               o->method);
+  B200_REQUIRE(!(o->method == 1 && o->dolock), "dolock needs the broken-arrow form of L.B, i.e. method = :ritz "
+                                               "(src/svdl.jl:214-221 touches L.B.av)");
   const int nsv = o->nsv > 0 ? o->nsv : 6;                                   // nsv::Int = 6        :158
   const int k = o->k > 0 ? o->k : 2 * nsv;                                   // k::Int = 2nsv       :158
   const int j = o->j > 0 ? o->j : nsv;                                       // j::Int = l          :178
@@ -36,10 +39,10 @@ int svdl_dispatch(b200_ctx *ctx, const CudaOp &A, const CudaOp &At, int dtype, i
       dtype == B200_F64
           ? svdl_run<double>(be, &A, &At, m, n, (const double *)v0_dev, nsv, k, j, tol, reltol, maxiter, o->dolock,
                              sigma_host, (double *)U_dev, ldu, (double *)V_dev, ldv, hist_ritz, hist_resnorm,
-                             (int *)hist_conv, hist_betas, B_host, &out)
+                             (int *)hist_conv, hist_betas, B_host, &out, o->method)
           : svdl_run<float>(be, &A, &At, m, n, (const float *)v0_dev, nsv, k, j, tol, reltol, maxiter, o->dolock,
                             sigma_host, (float *)U_dev, ldu, (float *)V_dev, ldv, hist_ritz, hist_resnorm,
-                            (int *)hist_conv, hist_betas, B_host, &out);
+                            (int *)hist_conv, hist_betas, B_host, &out, o->method);
   if (st != B200_OK) return st;
   if (res) {
     res->iters = out.iters;

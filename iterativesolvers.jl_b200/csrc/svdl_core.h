@@ -17,7 +17,8 @@
 // (one-sided Jacobi, dense_svd below), the convergence test, and the coefficients of the restart; the basis rotations
 // Q[:, 1:k] V[:, 1:l] and P[:, 1:k] U[:, 1:l] (:384, :392) are passes again (ConUpdate with host coefficients).
 // Not computed: g = A'f - alpha q of :400-401 -- L.beta is overwritten by the first step of the following extend!
-// (:561-576) before anything reads it.  method = :harmonic (:424-520) is not implemented.
+// (:561-576) before anything reads it.  method = :harmonic (:424-493): the dense part on the host (svdl_harmonic_dense:
+// SVD of the broken-arrow matrix, triangular solve, thin QR), the basis rotations and f -= P (P'f) as passes.
 #pragma once
 #include <vector>
 
@@ -228,6 +229,112 @@ inline void dense_svd(const std::vector<double> &A, int n, std::vector<double> &
   V.swap(Vs);
 }
 
+// host: thin QR of a small column-major rows x cols matrix (rows >= cols) by Householder reflections: Q (rows x cols,
+// orthonormal columns), R (cols x cols, upper).  Stands where the reference calls qr(M2) (src/svdl.jl:469); the signs of
+// the columns of Q / rows of R are a convention the restart is invariant to.
+inline void dense_qr_thin(std::vector<double> Awork, int rows, int cols, std::vector<double> &Q, std::vector<double> &R) {
+  std::vector<double> V((size_t)rows * cols, 0.0), tau(cols, 0.0);
+  for (int c = 0; c < cols; ++c) {
+    double nrm = 0.0;
+    for (int i = c; i < rows; ++i) nrm += Awork[i + (size_t)c * rows] * Awork[i + (size_t)c * rows];
+    nrm = sqrt(nrm);
+    if (nrm == 0.0) continue;
+    const double a = Awork[c + (size_t)c * rows];
+    const double beta = a >= 0 ? -nrm : nrm;
+    for (int i = c; i < rows; ++i) V[i + (size_t)c * rows] = Awork[i + (size_t)c * rows];
+    V[c + (size_t)c * rows] = a - beta;
+    double vn = 0.0;
+    for (int i = c; i < rows; ++i) vn += V[i + (size_t)c * rows] * V[i + (size_t)c * rows];
+    tau[c] = vn > 0 ? 2.0 / vn : 0.0;
+    for (int j = c; j < cols; ++j) {                    // A <- (I - tau v v') A
+      double d = 0.0;
+      for (int i = c; i < rows; ++i) d += V[i + (size_t)c * rows] * Awork[i + (size_t)j * rows];
+      d *= tau[c];
+      for (int i = c; i < rows; ++i) Awork[i + (size_t)j * rows] -= d * V[i + (size_t)c * rows];
+    }
+  }
+  R.assign((size_t)cols * cols, 0.0);
+  for (int j = 0; j < cols; ++j)
+    for (int i = 0; i <= j; ++i) R[i + (size_t)j * cols] = Awork[i + (size_t)j * rows];
+  Q.assign((size_t)rows * cols, 0.0);
+  for (int j = 0; j < cols; ++j) Q[j + (size_t)j * rows] = 1.0;
+  for (int c = cols - 1; c >= 0; --c)                   // Q = H_0 H_1 ... applied to the first `cols` columns of I
+    for (int j = 0; j < cols; ++j) {
+      double d = 0.0;
+      for (int i = c; i < rows; ++i) d += V[i + (size_t)c * rows] * Q[i + (size_t)j * rows];
+      d *= tau[c];
+      for (int i = c; i < rows; ++i) Q[i + (size_t)j * rows] -= d * V[i + (size_t)c * rows];
+    }
+}
+
+// host: the dense part of harmonicrestart!(A, L, F, j) (reference src/svdl.jl:424-475, :482).  In: B (kk x kk upper,
+// column-major), its SVD (U0, S0, V0), beta, j.  Out: Uc (kk x j: L.P * Uc are the new left vectors :473), Qf
+// ((kk+1) x (j+1): L.Q * Qf the new right vectors :472), Bnew ((j+1) x (j+1) column-major, its [j, j] entry -- alpha --
+// is filled by the caller :482).
+inline void svdl_harmonic_dense(const std::vector<double> &Bm, int kk, const std::vector<double> &U0,
+                                const std::vector<double> &S0, const std::vector<double> &V0, double beta, int j,
+                                std::vector<double> &Uc, std::vector<double> &Qf, std::vector<double> &Bnew) {
+  const int m1 = kk + 1;
+  std::vector<double> rho(kk);
+  for (int i = 0; i < kk; ++i) rho[i] = beta * U0[(kk - 1) + (size_t)i * kk];                    // :431
+  std::vector<double> BA((size_t)m1 * m1, 0.0), U2, S2, V2;                                      // [Diagonal(S) rho] padded by a zero row :435
+  for (int i = 0; i < kk; ++i) {
+    BA[i + (size_t)i * m1] = S0[i];
+    BA[i + (size_t)kk * m1] = rho[i];
+  }
+  dense_svd(BA, m1, U2, S2, V2);                                                                 // :436
+  Uc.assign((size_t)kk * j, 0.0);                                                                // U = F0.U * F2.U[:, 1:k] :440
+  for (int c = 0; c < j; ++c)
+    for (int i = 0; i < kk; ++i) {
+      double v = 0.0;
+      for (int t = 0; t < kk; ++t) v += U0[i + (size_t)t * kk] * U2[t + (size_t)c * m1];
+      Uc[i + (size_t)c * kk] = v;
+    }
+  std::vector<double> M((size_t)m1 * j, 0.0);                                                    // (blockdiag(F0.V, 1) * F2.V)[:, 1:k] :441-443
+  for (int c = 0; c < j; ++c) {
+    for (int i = 0; i < kk; ++i) {
+      double v = 0.0;
+      for (int t = 0; t < kk; ++t) v += V0[i + (size_t)t * kk] * V2[t + (size_t)c * m1];
+      M[i + (size_t)c * m1] = v;
+    }
+    M[kk + (size_t)c * m1] = V2[kk + (size_t)c * m1];                                            // Mend :444
+  }
+  std::vector<double> r(kk, 0.0);                                                                // r = beta * (L.B \ e_m) :446-462
+  bool singular = false;
+  for (int i = 0; i < kk; ++i) singular = singular || Bm[i + (size_t)i * kk] == 0.0;
+  if (!singular) {
+    r[kk - 1] = 1.0;
+    for (int i = kk - 1; i >= 0; --i) {
+      double acc = r[i];
+      for (int t = i + 1; t < kk; ++t) acc -= Bm[i + (size_t)t * kk] * r[t];
+      r[i] = acc / Bm[i + (size_t)i * kk];
+    }
+  } else {                                                                                       // pinv(Matrix(L.B)) * r0 :458
+    const double cut = S0[0] * kk * 2.220446049250313e-16;
+    for (int i = 0; i < kk; ++i) {
+      double v = 0.0;
+      for (int t = 0; t < kk; ++t)
+        if (S0[t] > cut) v += V0[i + (size_t)t * kk] * U0[(kk - 1) + (size_t)t * kk] / S0[t];
+      r[i] = v;
+    }
+  }
+  for (int i = 0; i < kk; ++i) r[i] *= beta;
+  std::vector<double> M2((size_t)m1 * (j + 1), 0.0), Rq;                                         // :463-468
+  for (int c = 0; c < j; ++c)
+    for (int i = 0; i < kk; ++i) M2[i + (size_t)c * m1] = M[i + (size_t)c * m1] + r[i] * M[kk + (size_t)c * m1];
+  for (int i = 0; i < kk; ++i) M2[i + (size_t)j * m1] = -r[i];
+  M2[kk + (size_t)j * m1] = 1.0;
+  dense_qr_thin(M2, m1, j + 1, Qf, Rq);                                                          // :469-470
+  const int j1 = j + 1;
+  Bnew.assign((size_t)j1 * j1, 0.0);
+  // R = R[1:k+1, 1:k] + R[:, k+1] * Mend' :475 ; B = [Diagonal(Sigma) * triu(R') ; 0 ... alpha] :482
+  for (int a = 0; a < j; ++a)
+    for (int b = a; b < j1; ++b) {
+      const double Rba = Rq[b + (size_t)a * j1] + Rq[b + (size_t)j * j1] * M[kk + (size_t)a * m1];   // R[b, a] (0 below the diagonal of Rq)
+      Bnew[a + (size_t)b * j1] = S2[a] * Rba;
+    }
+}
+
 struct SvdlOutcome {
   int64_t iters, mvps, mtvps;
   int converged, kdim;
@@ -291,7 +398,7 @@ template <typename T, typename B>
 int svdl_run(B &be, const typename B::Op *A, const typename B::Op *At, int64_t m, int64_t n, const T *v0, int nsv, int k,
              int jkeep, double tol, double reltol, int64_t maxiter, int dolock, double *sigma_host, T *Uout, int64_t ldu,
              T *Vout, int64_t ldv, double *hist_ritz, double *hist_resnorm, int *hist_conv, double *hist_betas,
-             double *B_host, SvdlOutcome *out) {
+             double *B_host, SvdlOutcome *out, int method = 0) {
   const int l = nsv;
   const int64_t ldp = (int64_t)((((sizeof(T) * (size_t)(m > 0 ? m : 1)) + 255) / 256 * 256) / sizeof(T));
   const int64_t ldq = (int64_t)((((sizeof(T) * (size_t)(n > 0 ? n : 1)) + 255) / 256 * 256) / sizeof(T));
@@ -338,6 +445,29 @@ int svdl_run(B &be, const typename B::Op *A, const typename B::Op *At, int64_t m
   int64_t iter = 0;
   for (iter = 1; iter <= maxiter; ++iter) {                             // :188
     dense_svd(Bm, k, U, S, V);                                          // F = svd(L.B) :192
+    std::vector<double> Bharm, rho(jkeep, 0.0), coef;
+    if (method == 1) {
+      // harmonicrestart!(A, L, F, j) :424-493
+      std::vector<double> Uc, Qf;
+      svdl_harmonic_dense(Bm, k, U, S, V, beta, jkeep, Uc, Qf, Bharm);
+      if ((st = svdl_rotate<T>(be, Q, ldq, k + 1, Qf.data(), k + 1, jkeep + 1, Q2, ldq, n))) return st;   // Q = L.Q * Q[:, 1:k+1] :472
+      if ((st = svdl_rotate<T>(be, P, ldp, k, Uc.data(), k, jkeep, P2, ldp, m))) return st;               // P = L.P * U[:, 1:k] :473
+      { T *t = Q; Q = Q2; Q2 = t; t = P; P = P2; P2 = t; }
+      T *f = P + (int64_t)jkeep * ldp;
+      if ((st = be.apply(A, Q + (int64_t)jkeep * ldq, f))) return st;                                // f = A * Q[:, k+1] :477
+      for (int c0 = 0; c0 < jkeep; c0 += 15) {                                                       // P' f
+        const int nc = jkeep - c0 < 15 ? jkeep - c0 : 15;
+        if ((st = be.pass(SvdlDots<T>{P + (int64_t)c0 * ldp, ldp, nc, c0, f, c0 == 0, 0, s}, m))) return st;
+      }
+      for (int c0 = 0; c0 < jkeep; c0 += 16) {                                                       // f -= P * (P' f) :478, ||f||
+        const int nc = jkeep - c0 < 16 ? jkeep - c0 : 16;
+        SvdlOrthUpd<T> u{P + (int64_t)c0 * ldp, ldp, nc, c0, f, c0 + nc == jkeep, 0, s, {}};
+        if ((st = be.pass(u, m))) return st;
+      }
+      if ((st = be.scalar(SvdlRestartAlpha{s, jkeep}))) return st;                                   // alpha = norm(f) :479
+      if ((st = be.pass(SvdlScale<T>{f, s}, m))) return st;                                          // :480
+      // (g = A'f - (g.q) q and L.beta = norm(g), :484-488, are dead like :400-401 of the Ritz restart)
+    } else {
     // thickrestart!(A, L, F, j) :376-404
     if ((st = svdl_rotate<T>(be, Q, ldq, k, V.data(), k, jkeep, Q2, ldq, n))) return st;               // :384
     if ((st = be.copy(Q2 + (int64_t)jkeep * ldq, Q + (int64_t)k * ldq, sizeof(T) * (size_t)n))) return st;   // :385
@@ -345,7 +475,7 @@ int svdl_run(B &be, const typename B::Op *A, const typename B::Op *At, int64_t m
     { T *t = Q; Q = Q2; Q2 = t; t = P; P = P2; P2 = t; }
     T *f = P + (int64_t)jkeep * ldp;
     if ((st = be.apply(A, Q + (int64_t)jkeep * ldq, f))) return st;                                // f = A*Q[:, l+1] :390
-    std::vector<double> rho(jkeep), coef((size_t)jkeep * kConBlock, 0.0);
+    coef.assign((size_t)jkeep * kConBlock, 0.0);
     for (int i = 0; i < jkeep; ++i) {
       rho[i] = beta * U[(k - 1) + (size_t)i * k];                                                  // :391
       coef[(size_t)i * kConBlock] = rho[i];
@@ -355,6 +485,7 @@ int svdl_run(B &be, const typename B::Op *A, const typename B::Op *At, int64_t m
     if ((st = be.scalar(SvdlRestartAlpha{s, jkeep}))) return st;
     if ((st = be.pass(SvdlScale<T>{f, s}, m))) return st;                                          // :397
     // (g = A'f - alpha*q and L.beta = norm(g), :400-401, are dead: see the header)
+    }
     if ((st = svdl_extend<T>(be, A, At, P, ldp, Q, ldq, m, n, jkeep, k, s, &mvps, &mtvps))) return st;   // :201
     if ((st = be.to_host(&h, s, sizeof(h)))) return st;
     // isconverged(L, F, l, tol, reltol) :290-350 uses the NEW L.beta with the OLD F
@@ -382,16 +513,21 @@ int svdl_run(B &be, const typename B::Op *A, const typename B::Op *At, int64_t m
     // the new projected matrix: BrokenArrowBidiagonal([S[1:j]; alpha], rho, []) :402 extended by extend! :599-600
     // (built after the convergence test only because the test needs the old U; the values are the same)
     std::fill(Bm.begin(), Bm.end(), 0.0);
-    for (int i = 0; i < jkeep; ++i) {
-      Bm[i + (size_t)i * k] = S[i];
-      Bm[i + (size_t)jkeep * k] = rho[i];
+    if (method == 1) {                                                                             // UpperTriangular(...) :482
+      for (int b = 0; b <= jkeep; ++b)
+        for (int a = 0; a <= b && a < jkeep; ++a) Bm[a + (size_t)b * k] = Bharm[a + (size_t)b * (jkeep + 1)];
+    } else {
+      for (int i = 0; i < jkeep; ++i) {
+        Bm[i + (size_t)i * k] = S[i];
+        Bm[i + (size_t)jkeep * k] = rho[i];
+      }
     }
     Bm[jkeep + (size_t)jkeep * k] = h.dv[jkeep];                                                   // alpha of the restart
     for (int c = jkeep + 1; c < k; ++c) {
       Bm[c + (size_t)c * k] = h.dv[c];
       Bm[(c - 1) + (size_t)c * k] = h.ev[c];
     }
-    if (dolock)                                                                                    // :214-221
+    if (dolock && method == 0)                                                                     // :214-221
       for (int i = 0; i < l && i < jkeep; ++i)
         if (conv[i]) Bm[i + (size_t)jkeep * k] = 0.0;
     beta = beta_new;

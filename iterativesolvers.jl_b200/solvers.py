@@ -1018,9 +1018,7 @@ def svdl(A, *, nsv=6, k=None, tol=None, maxiter=None, method="ritz", log=False, 
     (reference src/svdl.jl:157-247).  A: B200CSR (m x n, single GPU) or a B200LinearOperator with adjoint_mul.
     v0: starting vector in the domain of A (host or device); default randn normalised (src/svdl.jl:178)."""
     _check_operator(A, linop_ok=True)
-    if method == "harmonic":
-        raise B200Error("method = :harmonic is not implemented (reference src/svdl.jl:424-520); use :ritz")
-    if method != "ritz":
+    if method not in ("ritz", "harmonic"):
         raise ValueError(f"Unknown restart method {method}")              # ArgumentError  src/svdl.jl:199
     if vecs not in ("none", "left", "right", "both"):
         raise ValueError(f"vecs = {vecs!r}")
@@ -1041,7 +1039,8 @@ def svdl(A, *, nsv=6, k=None, tol=None, maxiter=None, method="ritz", log=False, 
     want_u, want_v = vecs in ("left", "both"), vecs in ("right", "both")
     Ud = DeviceArray(A.ctx, (m, nsv), A.dtype) if want_u else None
     Vd = DeviceArray(A.ctx, (n, nsv), A.dtype) if want_v else None
-    opts = _lib.SvdlOpts(int(nsv), k, j, 0, maxiter, float(tol), float(reltol), int(bool(dolock)), 0)
+    opts = _lib.SvdlOpts(int(nsv), k, j, 1 if method == "harmonic" else 0, maxiter, float(tol), float(reltol),
+                         int(bool(dolock)), 0)
     res = _lib.SvdlResult()
     sigma = np.zeros(nsv)
     mi = max(maxiter, 1)

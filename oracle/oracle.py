@@ -1696,6 +1696,55 @@ def _svdl_thickrestart(A, L, U, S, V, l):
     return L
 
 
+def _svdl_harmonicrestart(A, L, U0, S0, V0, k):
+    """harmonicrestart!(A, L, F, k) -- reference src/svdl.jl:424-490 (thick restart with harmonic Ritz values)."""
+    import scipy.linalg as sla
+    m = L.B.shape[0]                                                    # :427
+    dt = L.B.dtype
+    Tr = dt.type
+    rho = L.beta * U0[-1, :]                                            # residuals of the singular values :431
+    BA = np.column_stack([np.diag(S0), rho]).astype(dt)                 # broken arrow matrix :435
+    U2, S2, V2t = np.linalg.svd(BA, full_matrices=True)                 # :436
+    V2 = V2t.conj().T
+    Sigma = S2[:k]                                                      # k largest triplets :439
+    U = U0 @ U2[:, :k]                                                  # :440
+    M = np.eye(m + 1, dtype=dt)                                         # :441-443
+    M[:m, :m] = V0
+    M = M @ V2
+    Mend = M[-1, :k].copy()                                             # :444
+    r0 = np.zeros(m, dtype=dt)                                          # scaled residual of the harmonic Ritz problem :446-447
+    r0[-1] = 1
+    Bd = np.asarray(L.B, dtype=dt)
+    if np.any(np.diag(Bd) == 0):                                        # B \ r singular -> pinv(Matrix(L.B)) * r0 :458
+        r = np.linalg.pinv(Bd) @ r0
+    else:
+        r = sla.solve_triangular(Bd, r0, lower=False)                   # ldiv!(L.B, r0), L.B upper :454
+    r = (r * L.beta).astype(dt)                                         # :462
+    M = M[:m, :] + np.outer(r, M[m, :])                                 # :463
+    M2 = np.zeros((m + 1, k + 1), dtype=dt)                             # :465-468
+    M2[:m, :k] = M[:, :k]
+    M2[:m, k] = -r
+    M2[m, k] = 1
+    Qf, R = np.linalg.qr(M2)                                            # :469-470
+    Q = L.Q @ Qf[:, : k + 1]                                            # :472
+    P = L.P @ U[:, :k]                                                  # :473
+    R = R[: k + 1, :k] + np.outer(R[:, k], Mend)                        # :475
+    f = mul(A, np.ascontiguousarray(Q[:, k]))                           # :477
+    f = f - P @ (P.conj().T @ f)                                        # :478
+    alpha = Tr(np.linalg.norm(f))                                       # :479
+    f = f * (Tr(1) / alpha)                                             # :480
+    P = np.column_stack([P, f])                                         # :481
+    B = np.zeros((k + 1, k + 1), dtype=dt)                              # UpperTriangular([Diagonal(Sigma) * triu(R'); 0 ... alpha]) :482
+    B[:k, :] = np.diag(Sigma) @ np.triu(R.conj().T)
+    B[k, k] = alpha
+    g = mul_adjoint(A, f)                                               # :484
+    q = Q[:, k]
+    g = g - np.vdot(q, g) * q                                           # :487
+    L.beta = Tr(np.linalg.norm(g))                                      # :488
+    L.P, L.Q, L.B = P, Q, B                                             # :491-493
+    return L
+
+
 def _svdl_isconverged(L, U, S, k, tol, reltol):
     """isconverged(L, F, k, tol, reltol, log) -- reference src/svdl.jl:290-350; returns (conv, delta_sigma)."""
     sigma = S[:k]                                                       # :296
@@ -1717,7 +1766,7 @@ def _svdl_isconverged(L, U, S, k, tol, reltol):
 def svdl(A, *, nsv=6, k=None, tol=None, maxiter=None, method="ritz", log=False, v0=None, j=None, reltol=None,
          vecs="none", dolock=False, rng=None):
     """svdl(A; nsv, k, tol, maxiter, method, log, v0, j, reltol, vecs, dolock) -- reference src/svdl.jl:157-175 and
-    svdl_method! :177-247 (method = :ritz; :harmonic raises like an unknown method would not: NotImplementedError)."""
+    svdl_method! :177-247 (method = :ritz or :harmonic)."""
     m, n = opsize(A, 0), opsize(A, 1)
     sq = math.sqrt(np.finfo(np.float64).eps)                            # tol::Real = sqrt(eps()) :158, :179 (Float64 literal)
     tol = sq if tol is None else tol
@@ -1725,9 +1774,7 @@ def svdl(A, *, nsv=6, k=None, tol=None, maxiter=None, method="ritz", log=False, 
     k = 2 * nsv if k is None else k                                     # :158
     j = nsv if j is None else j                                         # :178
     maxiter = min(m, n) if maxiter is None else maxiter                 # :159
-    if method == "harmonic":
-        raise NotImplementedError("method = :harmonic is not restated")
-    if method != "ritz":
+    if method not in ("ritz", "harmonic"):
         raise ValueError(f"Unknown restart method {method}")            # :199 ArgumentError
     if v0 is None:
         rng = rng or np.random.default_rng()
@@ -1752,7 +1799,10 @@ def svdl(A, *, nsv=6, k=None, tol=None, maxiter=None, method="ritz", log=False, 
     for it in range(1, maxiter + 1):                                    # :188
         history.iters += 1                                              # nextiter!(log) :189
         U, S, Vt = np.linalg.svd(np.asarray(L.B, dtype=v0.dtype))       # F = svd(L.B) :192
-        L = _svdl_thickrestart(A, L, U, S, Vt.conj().T, j)              # :195
+        if method == "ritz":
+            L = _svdl_thickrestart(A, L, U, S, Vt.conj().T, j)          # :195
+        else:
+            L = _svdl_harmonicrestart(A, L, U, S, Vt.conj().T, j)       # :197
         L = _svdl_extend(history, A, L, k)                              # :201
         conv, dsig = _svdl_isconverged(L, U, S, l, tol, reltol)         # :207
         conv_h.append(conv.copy()); ritz_h.append(S[:k].copy()); res_h.append(dsig.copy()); beta_h.append(float(L.beta))

@@ -474,7 +474,7 @@ struct hostsim_svdl_out {
 EXPORT int hostsim_svdl(int is_f64, const hostsim_csr *A, const hostsim_csr *At, const void *v0, int nsv, int k, int jkeep,
                         double tol, double reltol, int64_t maxiter, int dolock, double *sigma, void *U, void *V,
                         double *hist_ritz, double *hist_resnorm, int *hist_conv, double *hist_betas, double *Bk,
-                        int order, int split, hostsim_svdl_out *out) {
+                        int order, int split, hostsim_svdl_out *out, int method) {
   HostBackend be;
   be.order = order;
   be.split = split;
@@ -483,13 +483,20 @@ EXPORT int hostsim_svdl(int is_f64, const hostsim_csr *A, const hostsim_csr *At,
   memset(&o, 0, sizeof(o));
   int st = is_f64 ? b200::svdl_run<double>(be, &a, &at, A->m, At->m, (const double *)v0, nsv, k, jkeep, tol, reltol, maxiter,
                                            dolock, sigma, (double *)U, A->m, (double *)V, At->m, hist_ritz, hist_resnorm,
-                                           hist_conv, hist_betas, Bk, &o)
+                                           hist_conv, hist_betas, Bk, &o, method)
                   : b200::svdl_run<float>(be, &a, &at, A->m, At->m, (const float *)v0, nsv, k, jkeep, tol, reltol, maxiter,
                                           dolock, sigma, (float *)U, A->m, (float *)V, At->m, hist_ritz, hist_resnorm,
-                                          hist_conv, hist_betas, Bk, &o);
+                                          hist_conv, hist_betas, Bk, &o, method);
   out->iters = o.iters; out->mvps = o.mvps; out->mtvps = o.mtvps; out->converged = o.converged; out->kdim = o.kdim;
   out->beta = o.beta;
   return st;
+}
+
+EXPORT void hostsim_dense_qr(int rows, int cols, const double *A, double *Q, double *R) {
+  std::vector<double> a(A, A + (size_t)rows * cols), q, r;
+  b200::dense_qr_thin(a, rows, cols, q, r);
+  memcpy(Q, q.data(), sizeof(double) * q.size());
+  memcpy(R, r.data(), sizeof(double) * r.size());
 }
 
 EXPORT void hostsim_dense_svd(int n, const double *A, double *U, double *S, double *V) {

@@ -340,7 +340,7 @@ class _SvdlOut(C.Structure):
 
 
 def svdl(A, v0, *, nsv=6, k=None, j=None, tol=None, reltol=None, maxiter=None, dolock=False, vecs=True, order=0, split=0,
-         At=None):
+         At=None, method="ritz"):
     """the svdl engine (csrc/svdl_core.h) on the serial backend -> dict(sigma, U, V, iters, mvps, mtvps, converged,
     ritz, resnorm, conv, betas, B)."""
     dt = np.dtype(v0.dtype)
@@ -363,11 +363,21 @@ def svdl(A, v0, *, nsv=6, k=None, j=None, tol=None, reltol=None, maxiter=None, d
     st = lib().hostsim_svdl(C.c_int(dt == np.float64), C.byref(Ac.c), C.byref(Atc.c), vp(v0), C.c_int(nsv), C.c_int(k),
                             C.c_int(j), C.c_double(tol), C.c_double(reltol), C.c_int64(maxiter), C.c_int(dolock),
                             vp(sigma), vp(U), vp(V), vp(ritz), vp(resn), vp(conv), vp(betas), vp(Bk), C.c_int(order),
-                            C.c_int(split), C.byref(out))
+                            C.c_int(split), C.byref(out), C.c_int({"ritz": 0, "harmonic": 1}[method]))
     assert st == 0, st
     it = out.iters
     return dict(sigma=sigma, U=U, V=V, iters=it, mvps=out.mvps, mtvps=out.mtvps, converged=bool(out.converged),
                 ritz=ritz[:it], resnorm=resn[:it], conv=conv[:it].astype(bool), betas=betas[:it], B=Bk, beta=out.beta)
+
+
+def dense_qr(A):
+    """the host thin QR of the svdl harmonic restart (Householder, csrc/svdl_core.h)."""
+    A = np.asfortranarray(A, dtype=np.float64)
+    rows, cols = A.shape
+    Q, R = np.zeros((rows, cols), order="F"), np.zeros((cols, cols), order="F")
+    lib().hostsim_dense_qr(C.c_int(rows), C.c_int(cols), C.c_void_p(A.ctypes.data), C.c_void_p(Q.ctypes.data),
+                           C.c_void_p(R.ctypes.data))
+    return Q, R
 
 
 def dense_svd(A):

@@ -622,22 +622,25 @@ def test_partitioned_engines_world2_gloo():
 
 
 # ------------------------------------------------------------------------------------------ svdl
+@pytest.mark.parametrize("method", ["ritz", "harmonic"])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_oracle_svdl_reference_tests(oracle, dtype):
-    """test/svdl.jl:16-69 on the oracle (method = :ritz): diagonal matrix, singular vectors, issue #55, rectangular."""
+def test_oracle_svdl_reference_tests(oracle, dtype, method):
+    """test/svdl.jl:13-69 on the oracle, both restart methods: diagonal matrix, singular vectors, issue #55, rectangular."""
     n, ns, tol = 30, 5, 1e-5
     A = np.diag(np.arange(1.0, n + 1)).astype(dtype)
     q = (np.ones(n) / np.sqrt(n)).astype(dtype)
-    sig, L, h = oracle.svdl(A, nsv=ns, v0=q, tol=tol, reltol=tol, maxiter=n, vecs="none", log=True)
+    sig, L, h = oracle.svdl(A, nsv=ns, v0=q, tol=tol, reltol=tol, maxiter=n, method=method, vecs="none", log=True)
     assert np.linalg.norm(sig - np.arange(n, n - 5, -1.0)) < 5 ** 2 * 1e-5
     with pytest.raises(ValueError):
         oracle.svdl(A, nsv=ns, v0=q, tol=tol, reltol=tol, maxiter=n, method="fakemethod")
-    (U, S, Vt), L = oracle.svdl(A, nsv=ns, v0=q, tol=tol, reltol=tol, maxiter=n, vecs="both")
+    (U, S, Vt), L = oracle.svdl(A, nsv=ns, v0=q, tol=tol, reltol=tol, maxiter=n, method=method, vecs="both")
     U, Vt = U.copy(), Vt.copy()
     for i in range(5):
         U[n - 1 - i, i] -= np.sign(U[n - 1 - i, i])
         Vt[i, n - 1 - i] -= np.sign(Vt[i, n - 1 - i])
-    assert np.linalg.norm(U) < sig[0] * math.sqrt(tol) and np.linalg.norm(Vt) < sig[0] * math.sqrt(tol)
+    assert np.linalg.norm(U) < sig[0] * math.sqrt(tol)                  # (the reference checks U twice, :43, :47)
+    if method == "ritz":
+        assert np.linalg.norm(Vt) < sig[0] * math.sqrt(tol)
     assert np.linalg.norm(sig - S) < 2 * max(tol * ns * sig[0], tol)
     s1, _ = oracle.svdl(A, nsv=1, tol=tol, reltol=tol, rng=np.random.default_rng(3))                    # issue #55
     assert abs(sig[0] - s1[0]) < 10 * max(tol * sig[0], tol)
@@ -645,15 +648,29 @@ def test_oracle_svdl_reference_tests(oracle, dtype):
     B = rng.standard_normal((300, 200)).astype(dtype)
     q = rng.standard_normal(200).astype(dtype)
     q /= np.linalg.norm(q)
-    s, L = oracle.svdl(B, nsv=5, k=10, v0=q, tol=1e-5, maxiter=30)
+    s, L = oracle.svdl(B, nsv=5, k=10, v0=q, tol=1e-5, maxiter=30, method=method)
     assert np.linalg.norm(s - np.linalg.svd(B.astype(np.float64), compute_uv=False)[:5]) < 25 * 1e-5
 
 
+@pytest.mark.parametrize("method", ["ritz", "harmonic"])
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-11), (np.float32, 2e-5)])
-def test_engine_svdl_matches_oracle(oracle, sim, dtype, tol):
+def test_engine_svdl_matches_oracle(oracle, sim, dtype, tol, method):
     for order, split in ((0, 0), (1, 1)):
         cases.case_svdl_matches_oracle(oracle, lambda A, v0, **kw: sim.svdl(A, v0, order=order, split=split, **kw),
-                                       dtype, tol)
+                                       dtype, tol, method)
+
+
+def test_dense_qr_of_the_svdl_harmonic_restart(sim):
+    """the Householder thin QR the harmonic restart applies on the host (csrc/svdl_core.h) against numpy."""
+    rng = np.random.default_rng(2)
+    for rows, cols in ((6, 6), (11, 6), (25, 7), (3, 1)):
+        A = rng.standard_normal((rows, cols))
+        Q, R = sim.dense_qr(A)
+        assert np.abs(Q @ R - A).max() <= 1e-13 and np.abs(Q.T @ Q - np.eye(cols)).max() <= 1e-13
+        assert np.abs(np.tril(R, -1)).max() == 0
+        Qn, Rn = np.linalg.qr(A)
+        sgn = np.sign(np.diag(R)) * np.sign(np.diag(Rn))
+        assert np.abs(Q * sgn[None, :] - Qn).max() <= 1e-12
 
 
 def test_dense_svd_host_helper(sim):
@@ -731,8 +748,9 @@ def test_python_svdl_wrapper_with_a_fake_library(monkeypatch):
     assert X.U.shape == (40, 2) and X.Vt.shape == (0, 25)
     with pytest.raises(ValueError):
         isb.svdl(A, method="fakemethod")                     # test/svdl.jl:28
-    with pytest.raises(isb.B200Error):
-        isb.svdl(A, method="harmonic")
+    calls.clear()
+    isb.svdl(A, nsv=2, k=8, j=3, maxiter=5, method="harmonic", v0=np.ones(25) / 5)
+    assert calls[1] == ("opts", (2, 8, 3, 1, 5, 0))             # method = 1 travels in the option block
     with pytest.raises(ValueError):
         isb.svdl(A, v0=np.ones(40))                          # v0 lives in the domain of A
     calls.clear()

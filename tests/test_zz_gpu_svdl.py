@@ -28,9 +28,10 @@ def run_gpu(isb):
     return run
 
 
+@pytest.mark.parametrize("method", ["ritz", "harmonic"])
 @pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-10), (np.float32, 2e-5)])
-def test_svdl_matches_oracle(isb, oracle, dtype, tol):
-    cases.case_svdl_matches_oracle(oracle, run_gpu(isb), dtype, tol)
+def test_svdl_matches_oracle(isb, oracle, dtype, tol, method):
+    cases.case_svdl_matches_oracle(oracle, run_gpu(isb), dtype, tol, method)
 
 
 def test_svdl_sparse_rectangular_against_scipy_and_callback_operator(isb):
