@@ -324,6 +324,20 @@ B200_API int b200_cg_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_lin
 B200_API int b200_chebyshev_solve_op(b200_ctx *ctx, const b200_linop *A, void *x_dev, const void *b_dev,
                                      double lambda_min, double lambda_max, const b200_cg_opts *opts, b200_result *res,
                                      double *resnorm_host, int64_t resnorm_cap);
+/* powm!(B, x; shift, inverse, tol, maxiter) and invpowm!(B, x; shift, ...) = powm!(...; inverse = true) -- reference
+ * src/simple.jl:118-151, :186 (beyond SURVEY section 8: the simple eigensolvers of the reference).  Exactly one of A and Aop
+ * is non-NULL; for inverse iteration the operator applies inv(A - shift I) (:83-88).  x_dev: the normalised start vector,
+ * overwritten by the eigenvector approximation.  *lambda_out = shift + (inverse ? 1/theta : theta), theta the Rayleigh
+ * quotient (:51).  Up to maxiter + 1 iterations (done() tests `iteration > maxiter`, :27). */
+typedef struct {
+  double tol;               /* eps(real(T)) * size(B, 2)^3  src/simple.jl:119  (<0: default)                          */
+  int64_t maxiter;          /* size(B, 1)                   src/simple.jl:120  (<0: default)                          */
+  double shift;             /* src/simple.jl:121                                                                       */
+  int32_t inverse;          /* src/simple.jl:122                                                                       */
+  int32_t check_every;      /* iterations enqueued between host polls of the device-side done flag (<=0: 16)          */
+} b200_powm_opts;
+B200_API int b200_powm(b200_ctx *ctx, const b200_csr *A, const b200_linop *Aop, void *x_dev, const b200_powm_opts *opts,
+                       b200_result *res, double *lambda_out, double *resnorm_host, int64_t resnorm_cap);
 /* qmr! / lsqr! / lsmr! / idrs! on callback operators (A and, where needed, At = adjoint(A)) */
 B200_API int b200_qmr_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *At, void *x_dev, const void *b_dev,
                                const b200_qmr_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);

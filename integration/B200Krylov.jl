@@ -13,7 +13,7 @@ module B200Krylov
 
 using SparseArrays, LinearAlgebra
 import IterativeSolvers
-import IterativeSolvers: cg!, chebyshev!, gmres!, minres!, bicgstabl!, lobpcg, qmr!, lsqr!, lsmr!, idrs!, svdl,
+import IterativeSolvers: cg!, chebyshev!, gmres!, minres!, bicgstabl!, lobpcg, qmr!, lsqr!, lsmr!, idrs!, svdl, powm!, invpowm!,
                          ConvergenceHistory, Identity, ClassicalGramSchmidt, ModifiedGramSchmidt, DGKS,
                          OrthogonalizationMethod, LOBPCGResults
 import LinearAlgebra: mul!, ldiv!
@@ -656,6 +656,27 @@ end
 Base.iterate(it::B200Iterable, state = nothing) =
     it.res.status == 1 ? nothing : (r = step!(it, 1); isempty(r) ? nothing : (r[1], nothing))   # yields the residual norm
 converged(it::B200Iterable) = it.res.isconverged != 0
+
+# ------------------------------------------------------------------------------------------- powm! / invpowm!
+struct PowmOpts
+    tol::Float64; maxiter::Int64; shift::Float64; inverse::Int32; check_every::Int32
+end
+# powm!(B, x; shift, inverse, tol, maxiter, log)  src/simple.jl:118-151 ; invpowm!(B, x; ...) = powm!(...; inverse = true) :186
+function powm!(B::Union{B200CSR{T},B200LinearOperator{T}}, x::B200Vector{T}; tol::Real = eps(T) * size(B, 2)^3,
+               maxiter::Int = size(B, 1), shift::Real = zero(T), inverse::Bool = false, log::Bool = false,
+               verbose::Bool = false) where {T}
+    res = Result(); λ = Ref{Float64}(); hist = Vector{Float64}(undef, log ? maxiter + 1 : 0)
+    o = PowmOpts(tol, maxiter, shift, inverse, 0)
+    csr = B isa B200CSR ? B.h : C_NULL
+    GC.@preserve B begin
+        a = B isa B200LinearOperator ? Ref(linop(B)) : Ptr{LinOp}(C_NULL)
+        check(ccall((:b200_powm, LIB), Cint,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{LinOp}, Ptr{Cvoid}, Ref{PowmOpts}, Ref{Result}, Ref{Float64}, Ptr{Float64}, Int64),
+                    B.ctx.h, csr, a, x.p, o, res, λ, hist, length(hist)))
+    end
+    log ? (T(λ[]), x, history(res, hist, 0.0, 0.0)) : (T(λ[]), x)
+end
+invpowm!(B, x0; kwargs...) = powm!(B, x0; inverse = true, kwargs...)
 
 Base.size(A::B200LinearOperator) = (A.m, A.n)
 Base.size(A::B200LinearOperator, d::Integer) = d == 1 ? A.m : (d == 2 ? A.n : 1)

@@ -93,6 +93,11 @@ class SvdlResult(C.Structure):
                 ("k", C.c_int32), ("beta", C.c_double), ("tol", C.c_double)]
 
 
+class PowmOpts(C.Structure):
+    _fields_ = [("tol", C.c_double), ("maxiter", C.c_int64), ("shift", C.c_double), ("inverse", C.c_int32),
+                ("check_every", C.c_int32)]
+
+
 class LobpcgOpts(C.Structure):
     _fields_ = [("tol", C.c_double), ("maxiter", C.c_int64), ("largest", C.c_int32), ("blocksize", C.c_int32),
                 ("P", Precond), ("fixed_iterations", C.c_int32), ("reserved", C.c_int32),
@@ -217,6 +222,7 @@ SIGNATURES = {
     "b200_lobpcg_solve_constrained": (_INT, [_P, _P, _P, _I64, C.POINTER(LobpcgOpts), _P, C.POINTER(LobpcgResult), _P,
                                              _P]),
     "b200_csr_as_linop": (_INT, [_P, C.POINTER(LinOp)]),
+    "b200_powm": (_INT, [_P, _P, C.POINTER(LinOp), _P, C.POINTER(PowmOpts), C.POINTER(Result), C.POINTER(C.c_double), _P, _I64]),
     "b200_lobpcg_solve_op": (_INT, [_P, C.POINTER(LinOp), C.POINTER(LinOp), _P, _I64, C.POINTER(LobpcgOpts), _P,
                                     C.POINTER(LobpcgResult), _P, _P]),
     "b200_lobpcg_constraint_create_b": (_INT, [_P, C.POINTER(LinOp), _I64, _P, _I64, _INT, _INT, _INT, C.POINTER(_P)]),

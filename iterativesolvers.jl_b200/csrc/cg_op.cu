@@ -1,8 +1,10 @@
 // cg_op.cu -- cg!(x, A, b; Pl, ...) and chebyshev!(x, A, b, lmin, lmax; Pl, ...) for general (callback) operators and
-// preconditioners: the fused-pass engines of cg_core.h / chebyshev_core.h on the CUDA backend.  b200_csr operators with Identity / Jacobi take the specialised engine of cg.cu.
+// preconditioners, and the power method powm! / invpowm!: the fused-pass engines of cg_core.h / chebyshev_core.h /
+// powm_core.h on the CUDA backend.  b200_csr operators with Identity / Jacobi take the specialised engine of cg.cu.
 #include "linop.cuh"
 #include "cg_core.h"
 #include "chebyshev_core.h"
+#include "powm_core.h"
 
 using namespace b200;
 
@@ -97,6 +99,52 @@ int b200_cg_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *Pl, v
   if (res) {
     res->iters = o.iters;
     res->mvps = o.mvps;
+    res->isconverged = o.converged;
+    res->status = o.breakdown ? B200_ERR_BREAKDOWN : 0;
+    res->tol = o.tol;
+    res->residual = o.residual;
+    res->n_resnorm = o.n_hist;
+  }
+  return B200_OK;
+}
+
+// powm!(B, x; shift, inverse, tol, maxiter) / invpowm! (reference src/simple.jl:118-151, :186): exactly one of A (device CSR)
+// and Aop (callback: e.g. the action of inv(A - shift I) for inverse iteration) is non-NULL.
+int b200_powm(b200_ctx *ctx, const b200_csr *A, const b200_linop *Aop, void *x_dev, const b200_powm_opts *opts,
+              b200_result *res, double *lambda_out, double *resnorm_host, int64_t resnorm_cap) {
+  B200_REQUIRE(ctx && x_dev && opts, "NULL argument");
+  B200_REQUIRE((A != nullptr) != (Aop != nullptr), "exactly one of the CSR operator and the callback operator must be given");
+  CudaOp op;
+  int dtype;
+  int64_t n, n_global;
+  if (A) {
+    B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
+    B200_REQUIRE(is_square(A), "powm! needs a square operator");
+    op = CudaOp{A, nullptr};
+    dtype = A->dtype;
+    n = A->m_local;
+    n_global = A->n_global;
+  } else {
+    B200_TRY(check_linop(Aop, "B"));
+    B200_REQUIRE(Aop->m_global == Aop->n_global && Aop->m_local == Aop->n_local, "powm! needs a square operator");
+    op = CudaOp{nullptr, Aop};
+    dtype = Aop->dtype;
+    n = Aop->m_local;
+    n_global = Aop->n_global;
+  }
+  B200_CUDA(cudaSetDevice(ctx->device));
+  CudaBackend be{ctx};
+  PowmOutcome o;
+  memset(&o, 0, sizeof(o));
+  const int st = dtype == B200_F64 ? powm_run<double>(be, &op, n, n_global, (double *)x_dev, opts->tol, opts->maxiter,
+                                                      opts->check_every, resnorm_cap, resnorm_host, &o)
+                                   : powm_run<float>(be, &op, n, n_global, (float *)x_dev, opts->tol, opts->maxiter,
+                                                     opts->check_every, resnorm_cap, resnorm_host, &o);
+  if (st != B200_OK) return st;
+  if (lambda_out) *lambda_out = opts->shift + (opts->inverse ? 1.0 / o.theta : o.theta);   // transform_eigenvalue :51
+  if (res) {
+    res->iters = o.iters;
+    res->mvps = o.iters;                 // nextiter!(history, mvps = 1) :133
     res->isconverged = o.converged;
     res->status = o.breakdown ? B200_ERR_BREAKDOWN : 0;
     res->tol = o.tol;

@@ -456,6 +456,69 @@ def bicgstabl(A, b, l=2, **kw):
 
 
 # ------------------------------------------------------------------------------------------------
+# Power method and inverse iteration  (reference src/simple.jl)
+# ------------------------------------------------------------------------------------------------
+def powm_(B, x, *, tol=None, maxiter=None, shift=0.0, inverse=False, log=False, verbose=False, check_every=0):
+    """powm!(B, x; shift, inverse, tol, maxiter, log, verbose) -> λ, x[, history] -- reference src/simple.jl:118-151.
+    B: B200CSR or B200LinearOperator (for shift-and-invert: the action of inv(A - shift I), :83-88); x: normalised start
+    vector (host or device), overwritten by the eigenvector approximation."""
+    _check_operator(B, linop_ok=True)
+    if tol is None:
+        tol = float(_eps(B.dtype)) * B.size(2) ** 3            # :119
+    if maxiter is None:
+        maxiter = B.size(1)                                    # :120
+    host = not is_device(x)
+    if host and not (isinstance(x, np.ndarray) and x.dtype == B.dtype):
+        raise TypeError(f"x must be a numpy array of eltype {B.dtype}")
+    xd = DeviceArray.from_numpy(B.ctx, x) if host else x
+    if xd.shape[0] != B.m_local:
+        raise ValueError("dimension mismatch between B and x")
+    opts = _lib.PowmOpts(float(tol), int(maxiter), float(shift), int(bool(inverse)), int(check_every))
+    res, lam = _lib.Result(), C.c_double()
+    cap = int(maxiter) + 1                                     # done() lets iteration == maxiter through, :27
+    resnorm = np.zeros(cap, dtype=np.float64)
+    a_csr = None if _is_linop(B) else B._h
+    a_op = C.byref(B._c) if _is_linop(B) else None
+    check(_call_op(lib().b200_powm, (B,) if _is_linop(B) else (), B.ctx._h, a_csr, a_op, as_device_ptr(xd), C.byref(opts),
+                   C.byref(res), C.byref(lam), resnorm.ctypes.data_as(C.c_void_p), cap))
+    if host:
+        x[...] = xd.numpy()
+    if verbose:
+        print("=== powm ===\niter\tresnorm")
+        for i, r in enumerate(resnorm[: res.n_resnorm], start=1):
+            print(f"{i:3d}\t{r:1.2e}")
+        print()
+    lam_T = B.dtype.type(lam.value)
+    if not log:
+        return lam_T, x
+    h = ConvergenceHistory()
+    h["tol"] = float(res.tol)
+    h.isconverged, h.mvps, h.iters = bool(res.isconverged), int(res.mvps), int(res.iters)
+    h["resnorm"] = resnorm[: res.n_resnorm].copy()
+    return lam_T, x, h
+
+
+def powm(B, *, rng=None, **kw):
+    """powm(B; kwargs...) = powm!(B, x0; kwargs...) with a random unit start vector -- src/simple.jl:63-67 (the reference
+    draws a complex vector; element types are real here)."""
+    _check_operator(B, linop_ok=True)
+    rng = rng or np.random.default_rng()
+    x0 = rng.random(B.m_local).astype(B.dtype)
+    x0 /= np.linalg.norm(x0)
+    return powm_(B, x0, **kw)
+
+
+def invpowm_(B, x, **kw):
+    """invpowm!(B, x0; shift, kwargs...) = powm!(B, x0; inverse = true, kwargs...) -- src/simple.jl:186."""
+    return powm_(B, x, inverse=True, **kw)
+
+
+def invpowm(B, *, rng=None, **kw):
+    """invpowm(B; shift, kwargs...) -- src/simple.jl:172-176."""
+    return powm(B, rng=rng, inverse=True, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
 # The resumable forms: gmres_iterable!, minres_iterable!, bicgstabl_iterator!  (docs/src/iterators.md)
 # ------------------------------------------------------------------------------------------------
 class KrylovIterable:

@@ -548,6 +548,50 @@ def orthogonalize_and_normalize_(V, w, h, method="mgs"):
 
 
 # --------------------------------------------------------------------------------------------
+# Power method / inverse iteration (reference src/simple.jl)
+# --------------------------------------------------------------------------------------------
+def powm_(B, x, *, tol=None, maxiter=None, shift=0.0, inverse=False, log=False):
+    """powm!(B, x; shift, inverse, tol, maxiter, log) -- reference src/simple.jl:118-151 with PowerMethodIterable :6-15,
+    iterate :29-48 (done uses `iteration > maxiter`, :27: up to maxiter + 1 steps).  B: anything mul() accepts, or a
+    callable y = B(x) (the LinearMap of shift-and-invert, :83-88).  Returns (lambda, x[, history]); x is updated in place."""
+    T = x.dtype
+    n1, n2 = (x.shape[0], x.shape[0]) if callable(B) else (opsize(B, 0), opsize(B, 1))
+    if tol is None:
+        tol = float(_eps(_real_dtype(T))) * n2 ** 3                      # :119
+    if maxiter is None:
+        maxiter = n1                                                    # :120
+    apply = B if callable(B) else (lambda v: mul(B, v))
+    history = ConvergenceHistory()
+    history["tol"] = tol
+    resnorms = []
+    theta = T.type(0)
+    residual = float(np.finfo(_real_dtype(T)).max)                      # floatmax :55
+    iteration = 0
+    while not (iteration > maxiter or residual <= tol):                 # done :27
+        Ax = np.asarray(apply(np.ascontiguousarray(x)), dtype=T)        # :32
+        theta = np.vdot(x, Ax)                                          # :35
+        r = Ax - theta * x                                              # :38-39
+        residual = float(np.linalg.norm(r))                             # :42
+        x[...] = Ax                                                     # :45
+        x *= T.type(1) / T.type(np.linalg.norm(x))                      # :46
+        iteration += 1
+        history.iters += 1                                              # nextiter!(history, mvps = 1) :133
+        history.mvps += 1
+        resnorms.append(residual)
+    history.isconverged = residual <= tol                               # :137
+    lam = shift + (1 / theta if inverse else theta)                     # transform_eigenvalue :51
+    if log:
+        history["resnorm"] = np.array(resnorms)
+        return lam, x, history
+    return lam, x
+
+
+def invpowm_(B, x, **kw):
+    """invpowm!(B, x0; shift, kwargs...) = powm!(B, x0; inverse = true, kwargs...) -- src/simple.jl:186."""
+    return powm_(B, x, inverse=True, **kw)
+
+
+# --------------------------------------------------------------------------------------------
 # GMRES (reference src/gmres.jl)
 # --------------------------------------------------------------------------------------------
 def gmres_(x, A, b, *, Pl=None, Pr=None, abstol=0.0, reltol=None, restart=None, maxiter=None, log=False,

@@ -24,6 +24,7 @@
 #include "../../iterativesolvers.jl_b200/csrc/cg_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/gmres_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/chebyshev_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/powm_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/minres_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/bicgstabl_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/lobpcg_constraint_core.h"
@@ -305,6 +306,24 @@ EXPORT int hostsim_chebyshev(int is_f64, const hostsim_csr *A, const hostsim_csr
   out->iters = o.iters; out->mvps = o.mvps; out->mtvps = 0; out->n_hist = o.n_hist;
   out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
   out->passes = be.passes; out->applies = be.applies;
+  return st;
+}
+
+// powm! on a general operator (for inverse iteration the "operator" applies inv(A - shift I))
+EXPORT int hostsim_powm(int is_f64, const hostsim_csr *A, void *x, double tol, int64_t maxiter, int check_every,
+                        int64_t hist_cap, double *hist, int order, int split, hostsim_out *out, double *theta) {
+  HostBackend be;
+  be.order = order;
+  be.split = split;
+  HostCsr a = mk(A, is_f64);
+  b200::PowmOutcome o;
+  memset(&o, 0, sizeof(o));
+  int st = is_f64 ? b200::powm_run<double>(be, &a, A->m, A->n, (double *)x, tol, maxiter, check_every, hist_cap, hist, &o)
+                  : b200::powm_run<float>(be, &a, A->m, A->n, (float *)x, tol, maxiter, check_every, hist_cap, hist, &o);
+  out->iters = o.iters; out->mvps = o.iters; out->mtvps = 0; out->n_hist = o.n_hist;
+  out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged; out->breakdown = o.breakdown;
+  out->passes = be.passes; out->applies = be.applies;
+  *theta = o.theta;
   return st;
 }
 

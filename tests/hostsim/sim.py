@@ -225,6 +225,20 @@ def chebyshev_(x, A, b, lmin, lmax, *, Pl=None, diag=None, abstol=0.0, reltol=-1
     return x, _outcome(out, hist)
 
 
+def powm_(A, x, *, tol=-1.0, maxiter=-1, check_every=0, order=0, split=0):
+    """the power-method engine (csrc/powm_core.h) on the serial backend -> (theta, x, outcome); x updated in place."""
+    dt = x.dtype
+    Ac = Csr(A, dt)
+    cap = (maxiter if maxiter >= 0 else A.shape[0]) + 1
+    hist = np.zeros(max(cap, 1))
+    out, theta = _Out(), C.c_double()
+    st = lib().hostsim_powm(C.c_int(dt == np.float64), C.byref(Ac.c), C.c_void_p(x.ctypes.data), C.c_double(tol),
+                            C.c_int64(maxiter), C.c_int(check_every), C.c_int64(cap), hist.ctypes.data_as(C.c_void_p),
+                            C.c_int(order), C.c_int(split), C.byref(out), C.byref(theta))
+    assert st == 0, st
+    return theta.value, x, _outcome(out, hist)
+
+
 def minres_(x, A, b, *, abstol=0.0, reltol=-1.0, maxiter=-1, initially_zero=False, skew_hermitian=False, check_every=0,
             order=0, split=0):
     """the general-operator minres engine (csrc/minres_core.h) on the serial backend; x updated in place."""

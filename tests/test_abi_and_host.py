@@ -222,7 +222,7 @@ def test_julia_binding_source_uses_only_declared_symbols_and_matching_structs():
                    ("MinresOpts", L.MinresOpts), ("BicgstablOpts", L.BicgstablOpts), ("LobpcgOpts", L.LobpcgOpts),
                    ("LobpcgResult", L.LobpcgResult), ("QmrOpts", L.QmrOpts), ("LsqOpts", L.LsqOpts),
                    ("LsqResult", L.LsqResult), ("IdrsOpts", L.IdrsOpts), ("LinOp", L.LinOp),
-                   ("SvdlOpts", L.SvdlOpts), ("SvdlResult", L.SvdlResult)):
+                   ("SvdlOpts", L.SvdlOpts), ("SvdlResult", L.SvdlResult), ("PowmOpts", L.PowmOpts)):
         assert julia_fields(jl) == [f[0] for f in ct._fields_], jl
 
 
@@ -249,7 +249,7 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
              ("b200_bicgstabl_opts", L.BicgstablOpts), ("b200_lobpcg_opts", L.LobpcgOpts),
              ("b200_lobpcg_result", L.LobpcgResult), ("b200_qmr_opts", L.QmrOpts), ("b200_lsq_opts", L.LsqOpts),
              ("b200_lsq_result", L.LsqResult), ("b200_idrs_opts", L.IdrsOpts), ("b200_linop", L.LinOp),
-             ("b200_svdl_opts", L.SvdlOpts), ("b200_svdl_result", L.SvdlResult)]
+             ("b200_svdl_opts", L.SvdlOpts), ("b200_svdl_result", L.SvdlResult), ("b200_powm_opts", L.PowmOpts)]
     lines = ['#include <stddef.h>', '#include <stdio.h>', f'#include "{os.path.join(ROOT, "include", "b200krylov.h")}"',
              'int main(void) {']
     for cname, ct in pairs:

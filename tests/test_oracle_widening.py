@@ -1107,3 +1107,71 @@ def test_engine_chebyshev_general_matches_oracle(oracle, sim, dtype, tol):
                 args["Pl"] = sp.diags(1.0 / d.astype(np.float64)).tocsr()
             return sim.chebyshev_(x, sp.csr_matrix(A), b, lmin, lmax, order=order, split=split, **args, **kw)
         cases.case_chebyshev_general(oracle, run, dtype, tol)
+
+
+# ------------------------------------------------------------------------------------------ powm! / invpowm!
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_engine_powm_matches_oracle_and_reference_tests(oracle, sim, dtype):
+    for order, split in ((0, 0), (1, 1)):
+        def run(A, x0, tol, maxiter):
+            return sim.powm_(A, x0, tol=tol, maxiter=maxiter, order=order, split=split)
+        cases.case_powm(oracle, run, dtype)
+
+
+def test_python_powm_wrappers_with_a_fake_library(monkeypatch):
+    """powm_ / powm / invpowm_ / invpowm: option block (tol default eps * n^3, maxiter default n, shift, inverse), CSR handle
+    or callback descriptor, the transformed eigenvalue and the history come back."""
+    import ctypes as C
+    from importlib import import_module
+    import iterativesolvers_jl_b200 as isb
+    S = import_module("iterativesolvers_jl_b200.solvers")
+    L = S._lib
+    calls = []
+
+    class FakeArr:
+        def __init__(self, a):
+            self.a = np.array(a, order="F")
+            self.shape, self.dtype = self.a.shape, self.a.dtype
+            self._p = C.c_void_p(0x5000)
+
+        @classmethod
+        def from_numpy(cls, ctx, a):
+            return cls(a)
+
+        def numpy(self):
+            return self.a.copy() * 2
+
+    class FakeLib:
+        def b200_powm(self, ctx, a_csr, a_op, x, opts, res, lam, hist, cap):
+            o = opts._obj
+            calls.append((a_csr, a_op, o.tol, o.maxiter, o.shift, o.inverse, cap))
+            lam._obj.value = o.shift + (0.5 if o.inverse else 3.0)
+            r = res._obj
+            r.iters, r.mvps, r.isconverged, r.tol, r.residual, r.n_resnorm = 2, 2, 1, o.tol, 1e-9, 2
+            np.ctypeslib.as_array(C.cast(hist, C.POINTER(C.c_double)), shape=(cap,))[:2] = [0.5, 1e-9]
+            return 0
+
+    monkeypatch.setattr(S, "lib", lambda: FakeLib())
+    monkeypatch.setattr(S, "DeviceArray", FakeArr)
+    monkeypatch.setattr(S, "is_device", lambda v: isinstance(v, FakeArr))
+    monkeypatch.setattr(S, "as_device_ptr", lambda v: v._p)
+    ctx = SimpleNamespace(_h=None, world=1)
+    n = 12
+    csr = S.B200CSR.__new__(S.B200CSR)
+    csr.ctx, csr._h, csr.m_local, csr.n_global, csr.m_global, csr.dtype = ctx, C.c_void_p(7), n, n, n, np.dtype(np.float64)
+    csr.close = lambda: None
+    x = np.ones(n) / np.sqrt(n)
+    lam, xo, h = isb.powm_(csr, x, log=True)
+    a_csr, a_op, tol, maxiter, shift, inverse, cap = calls[-1]
+    assert a_csr.value == 7 and a_op is None and tol == np.finfo(np.float64).eps * n ** 3 and (maxiter, shift, inverse) == (n, 0.0, 0)
+    assert cap == n + 1 and lam == 3.0 and xo is x and np.allclose(x, 2 / np.sqrt(n))        # x copied back
+    assert h.isconverged and h.iters == 2 and list(h["resnorm"]) == [0.5, 1e-9]
+    op = isb.B200LinearOperator((n, n), np.float64, lambda y, v: None, ctx=ctx)
+    lam, xo = isb.invpowm_(op, np.ones(n) / np.sqrt(n), shift=1.25, tol=1e-4, maxiter=200)
+    a_csr, a_op, tol, maxiter, shift, inverse, cap = calls[-1]
+    assert a_csr is None and isinstance(a_op._obj, L.LinOp) and (tol, maxiter, shift, inverse) == (1e-4, 200, 1.25, 1)
+    assert lam == 1.75
+    lam, xo = isb.powm(csr, rng=np.random.default_rng(0))
+    assert abs(np.linalg.norm(xo) - 2) < 1e-12 and calls[-1][5] == 0
+    isb.invpowm(csr, shift=2.0, rng=np.random.default_rng(0))
+    assert calls[-1][4:6] == (2.0, 1)

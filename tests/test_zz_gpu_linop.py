@@ -238,3 +238,21 @@ def test_chebyshev_general_operator_and_callback_preconditioner(isb, oracle, dty
         x, h = isb.chebyshev_(x, op, b, lmin, lmax, Pl=Pl, log=True, **kw)
         return x, SimpleNamespace(iters=h.iters, mvps=h.mvps, converged=h.isconverged, hist=h["resnorm"])
     cases.case_chebyshev_general(oracle, run, dtype, tol)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_powm_and_invpowm(isb, oracle, dtype):
+    """powm! / invpowm! (reference src/simple.jl, test/simple_eigensolvers.jl:14-50) through b200_powm on a CSR operator --
+    the case of the serial backend (inverse iteration with the explicit inverse standing for the reference's LU LinearMap) --
+    and the dominant eigenvalue of a 2-D Laplacian."""
+    def run(A, x0, tol, maxiter):
+        lam, x, h = isb.powm_(isb.B200CSR.from_scipy(sp.csc_matrix(A).astype(x0.dtype)), x0, tol=tol, maxiter=maxiter, log=True)
+        return float(lam), x, SimpleNamespace(iters=h.iters, converged=h.isconverged, hist=h["resnorm"])
+    cases.case_powm(oracle, run, dtype)
+    # a larger sparse operator: dominant eigenvalue of the 2-D Laplacian = 8 - (smallest eigenvalue)
+    N = 24
+    O = oracle.laplace_matrix(np.float64, N, 2, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    lam, x, h = isb.powm(A, tol=1e-3, maxiter=20000, log=True, rng=np.random.default_rng(SEED))
+    exact = 4 + 4 * np.cos(np.pi / (N + 1))
+    assert h.isconverged and abs(lam - exact) <= 1e-3 and abs(np.linalg.norm(x) - 1) <= 1e-12

@@ -627,3 +627,38 @@ def case_nev_driver_generalized(lobpcg, make_A):
         assert np.max(np.linalg.norm(M @ r.X - Bm @ r.X * r.lam[None, :], axis=0)) <= 4 * tol
         assert np.allclose(r.X.T @ Bm @ r.X, np.eye(5), atol=2 * n * tol)
         assert np.allclose(np.sort(r.lam), np.sort(want), atol=1e-5 * np.abs(ex).max())
+
+
+def case_powm(oracle, run, dtype):
+    """powm! / invpowm! (reference src/simple.jl; test/simple_eigensolvers.jl:14-50, real element types): the engine against
+    the oracle's restatement (iterations, Rayleigh quotient, residual history, x) and the reference's own assertions.
+    run(A, x0, tol, maxiter) -> (theta, x, outcome with iters, converged, hist); A: scipy matrix the engine applies
+    (for inverse iteration the explicit inverse of A - sigma I, standing for the reference's LU LinearMap)."""
+    rng = np.random.default_rng(SEED)
+    n = 10
+    A = rng.random((n, n)).astype(dtype) + np.eye(n, dtype=dtype)
+    A = (A.T @ A).astype(dtype)
+    ls = np.linalg.eigvalsh(A.astype(np.float64))
+    tol = n ** 2 * np.linalg.cond(A.astype(np.float64)) * float(np.finfo(dtype).eps)
+    x0 = rng.random(n).astype(dtype)
+    x0 /= np.linalg.norm(x0)
+    lam, x, h = oracle.powm_(A, x0.copy(), tol=tol, maxiter=10 * n, log=True)
+    assert h.isconverged and abs(lam - ls[-1]) <= 1e-5 * ls[-1] and np.linalg.norm(A @ x - lam * x) <= tol   # :27-28
+    th, xs, hs = run(sp.csr_matrix(A), x0.copy(), tol, 10 * n)
+    eps = float(np.finfo(dtype).eps)
+    assert hs.iters == h.iters and hs.converged and abs(th - lam) <= 50 * eps * abs(lam)
+    assert np.abs(xs - x).max() <= 50 * eps and np.max(np.abs(hs.hist[: h.iters] - h["resnorm"])) <= 200 * eps * ls[-1]
+    idx = n // 2                                                         # inverse iteration near a middle eigenvalue :32-48
+    sigma = dtype(0.75 * ls[idx - 1] + 0.25 * ls[idx])
+    Finv = np.linalg.inv(A.astype(np.float64) - float(sigma) * np.eye(n))
+    lam2, x2, h2 = oracle.invpowm_(lambda v: (Finv @ v.astype(np.float64)).astype(dtype), x0.copy(), shift=float(sigma),
+                                   tol=tol, maxiter=10 * n, log=True)
+    assert h2.isconverged and abs(lam2 - ls[idx - 1]) <= 1e-4 * ls[idx - 1]
+    th2, xs2, hs2 = run(sp.csr_matrix(Finv.astype(dtype)), x0.copy(), tol, 10 * n)
+    lam_e = float(sigma) + 1.0 / th2
+    assert abs(hs2.iters - h2.iters) <= 1 and hs2.converged and abs(lam_e - ls[idx - 1]) <= 1e-4 * ls[idx - 1]
+    assert np.linalg.norm(A.astype(np.float64) @ xs2 - lam_e * xs2) <= 10 * tol * max(1.0, abs(lam_e))
+    # maxiter: done() tests `iteration > maxiter` -> maxiter + 1 steps
+    lam3, x3, h3 = oracle.powm_(A, x0.copy(), tol=0.0, maxiter=3, log=True)
+    th3, xs3, hs3 = run(sp.csr_matrix(A), x0.copy(), 0.0, 3)
+    assert h3.iters == hs3.iters == 4 and not hs3.converged and np.abs(xs3 - x3).max() <= 50 * eps
