@@ -338,6 +338,14 @@ typedef struct {
 } b200_powm_opts;
 B200_API int b200_powm(b200_ctx *ctx, const b200_csr *A, const b200_linop *Aop, void *x_dev, const b200_powm_opts *opts,
                        b200_result *res, double *lambda_out, double *resnorm_host, int64_t resnorm_cap);
+/* jacobi!(x, A, b; maxiter), gauss_seidel!, sor!(x, A, b, omega; maxiter), ssor! for sparse matrices -- reference
+ * src/stationary_sparse.jl:203-424 (beyond SURVEY section 8: the stationary methods of the reference).  Exactly `maxiter`
+ * iterations (<0: 10, the reference's default), no stopping test.  The sweeps are level-scheduled: every row performs the
+ * reference's arithmetic in the reference's order (csrc/stationary_core.h).  A zero or missing diagonal entry is the
+ * SingularException of DiagonalIndices (:19) -> B200_ERR_BREAKDOWN.  Single-GPU contexts; x_dev is updated in place. */
+enum { B200_STATIONARY_JACOBI = 0, B200_STATIONARY_GAUSS_SEIDEL = 1, B200_STATIONARY_SOR = 2, B200_STATIONARY_SSOR = 3 };
+B200_API int b200_stationary(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev, int method, double omega,
+                             int64_t maxiter);
 /* qmr! / lsqr! / lsmr! / idrs! on callback operators (A and, where needed, At = adjoint(A)) */
 B200_API int b200_qmr_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *At, void *x_dev, const void *b_dev,
                                const b200_qmr_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);

@@ -678,6 +678,19 @@ function powm!(B::Union{B200CSR{T},B200LinearOperator{T}}, x::B200Vector{T}; tol
 end
 invpowm!(B, x0; kwargs...) = powm!(B, x0; inverse = true, kwargs...)
 
+# ------------------------------------------------------------------------------------------- stationary methods
+# jacobi!(x, A, b; maxiter), gauss_seidel!, sor!(x, A, b, ω; maxiter), ssor!  src/stationary_sparse.jl:233-424
+for (f, code, hasω) in ((:jacobi!, 0, false), (:gauss_seidel!, 1, false), (:sor!, 2, true), (:ssor!, 3, true))
+    args = hasω ? (:(ω::Real),) : ()
+    ωv = hasω ? :ω : 1.0
+    @eval function IterativeSolvers.$f(x::B200Vector{T}, A::B200CSR{T}, b::B200Vector{T}, $(args...); maxiter::Int = 10) where {T}
+        status = ccall((:b200_stationary, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Float64, Int64),
+                       A.ctx.h, A.h, x.p, b.p, $code, $ωv, maxiter)
+        status == -5 && throw(SingularException(0))            # DiagonalIndices  src/stationary_sparse.jl:19
+        check(status); x
+    end
+end
+
 Base.size(A::B200LinearOperator) = (A.m, A.n)
 Base.size(A::B200LinearOperator, d::Integer) = d == 1 ? A.m : (d == 2 ? A.n : 1)
 

@@ -19,6 +19,7 @@ from .generators import laplace_matrix, laplace_csr_slab, advection_dominated, m
 from .solvers import (cg, cg_, chebyshev, chebyshev_, gmres, gmres_, minres, minres_, bicgstabl, bicgstabl_, lobpcg,  # noqa: F401
                       LOBPCGResults, orthogonalize_and_normalize_, hessenberg_ldiv_,
                       cg_iterator_, CGIterable, CGStateVariables, KrylovIterable, gmres_iterable_, minres_iterable_,
-                      bicgstabl_iterator_, powm_, powm, invpowm_, invpowm,
+                      bicgstabl_iterator_, powm_, powm, invpowm_, invpowm, jacobi_, jacobi, gauss_seidel_, gauss_seidel,
+                      sor_, sor, ssor_, ssor,
                       qmr, qmr_, lsqr, lsqr_, lsmr, lsmr_, idrs, idrs_, LobpcgConstraint, svdl, SVD,
                       PartialFactorization)

@@ -222,6 +222,7 @@ SIGNATURES = {
     "b200_lobpcg_solve_constrained": (_INT, [_P, _P, _P, _I64, C.POINTER(LobpcgOpts), _P, C.POINTER(LobpcgResult), _P,
                                              _P]),
     "b200_csr_as_linop": (_INT, [_P, C.POINTER(LinOp)]),
+    "b200_stationary": (_INT, [_P, _P, _P, _P, _INT, _DBL, _I64]),
     "b200_powm": (_INT, [_P, _P, C.POINTER(LinOp), _P, C.POINTER(PowmOpts), C.POINTER(Result), C.POINTER(C.c_double), _P, _I64]),
     "b200_lobpcg_solve_op": (_INT, [_P, C.POINTER(LinOp), C.POINTER(LinOp), _P, _I64, C.POINTER(LobpcgOpts), _P,
                                     C.POINTER(LobpcgResult), _P, _P]),

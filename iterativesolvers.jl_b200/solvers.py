@@ -456,6 +456,65 @@ def bicgstabl(A, b, l=2, **kw):
 
 
 # ------------------------------------------------------------------------------------------------
+# Stationary methods  (reference src/stationary_sparse.jl)
+# ------------------------------------------------------------------------------------------------
+def _stationary(method, x, A, b, omega, maxiter):
+    _check_operator(A)
+    st = _Staged(A, x, b)
+    status = lib().b200_stationary(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), method, float(omega),
+                                   int(maxiter))
+    if status == _lib.ERR_BREAKDOWN:
+        raise np.linalg.LinAlgError("SingularException: zero or missing diagonal entry "
+                                    "(reference src/stationary_sparse.jl:19)")
+    check(status)
+    return st.finish()
+
+
+def _zerox(A, b):
+    return DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
+
+
+def jacobi_(x, A, b, *, maxiter=10):
+    """jacobi!(x, A::SparseMatrixCSC, b; maxiter = 10) -> x -- reference src/stationary_sparse.jl:233-237."""
+    return _stationary(0, x, A, b, 1.0, maxiter)
+
+
+def gauss_seidel_(x, A, b, *, maxiter=10):
+    """gauss_seidel!(x, A::SparseMatrixCSC, b; maxiter = 10) -> x -- reference src/stationary_sparse.jl:280-284."""
+    return _stationary(1, x, A, b, 1.0, maxiter)
+
+
+def sor_(x, A, b, omega, *, maxiter=10):
+    """sor!(x, A::SparseMatrixCSC, b, ω; maxiter = 10) -> x -- reference src/stationary_sparse.jl:344-348."""
+    return _stationary(2, x, A, b, omega, maxiter)
+
+
+def ssor_(x, A, b, omega, *, maxiter=10):
+    """ssor!(x, A::SparseMatrixCSC, b, ω; maxiter = 10) -> x -- reference src/stationary_sparse.jl:420-424."""
+    return _stationary(3, x, A, b, omega, maxiter)
+
+
+def jacobi(A, b, **kw):
+    _check_operator(A)
+    return jacobi_(_zerox(A, b), A, b, **kw)                   # jacobi!(zerox(A, b), A, b; kwargs...)  src/stationary.jl:19
+
+
+def gauss_seidel(A, b, **kw):
+    _check_operator(A)
+    return gauss_seidel_(_zerox(A, b), A, b, **kw)             # src/stationary.jl:79
+
+
+def sor(A, b, omega, **kw):
+    _check_operator(A)
+    return sor_(_zerox(A, b), A, b, omega, **kw)               # src/stationary.jl:136-137
+
+
+def ssor(A, b, omega, **kw):
+    _check_operator(A)
+    return ssor_(_zerox(A, b), A, b, omega, **kw)              # src/stationary.jl:195-196
+
+
+# ------------------------------------------------------------------------------------------------
 # Power method and inverse iteration  (reference src/simple.jl)
 # ------------------------------------------------------------------------------------------------
 def powm_(B, x, *, tol=None, maxiter=None, shift=0.0, inverse=False, log=False, verbose=False, check_every=0):

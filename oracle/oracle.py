@@ -548,6 +548,111 @@ def orthogonalize_and_normalize_(V, w, h, method="mgs"):
 
 
 # --------------------------------------------------------------------------------------------
+# Stationary methods for sparse matrices (reference src/stationary_sparse.jl), restated column by column as the reference
+# sweeps its SparseMatrixCSC.  A: CSC (this module's class) or anything CSC.from_scipy accepts.
+# --------------------------------------------------------------------------------------------
+def _st_prepare(A):
+    if not isinstance(A, CSC):
+        import scipy.sparse as sp
+        A = CSC.from_scipy(sp.csc_matrix(A))
+    cp = A.colptr - A.base
+    rv = A.rowval - A.base
+    n = A.n
+    diag = np.zeros(n, dtype=np.int64)                                  # DiagonalIndices :6-27
+    for col in range(n):
+        r1, r2 = cp[col], cp[col + 1]
+        k = r1 + np.searchsorted(rv[r1:r2], col)
+        if k >= r2 or rv[k] != col or A.nzval[k] == 0:
+            raise np.linalg.LinAlgError(f"SingularException({col + 1})")   # :19
+        diag[col] = k
+    return A, cp, rv, A.nzval, diag, n
+
+
+def _gs_multiply_upper(cp, rv, nz, diag, n, alpha, x, beta, y, z):     # gauss_seidel_multiply!(alpha, U, x, beta, y, z) :179-191
+    for col in range(n):
+        ax = alpha * x[col]
+        for j in range(cp[col], diag[col]):
+            z[rv[j]] += nz[j] * ax
+        z[col] = beta * y[col]
+
+
+def _gs_multiply_lower(cp, rv, nz, diag, n, alpha, x, beta, y, z):     # gauss_seidel_multiply!(alpha, L, x, beta, y, z) :197-209
+    for col in range(n - 1, -1, -1):
+        ax = alpha * x[col]
+        z[col] = beta * y[col]
+        for j in range(diag[col] + 1, cp[col + 1]):
+            z[rv[j]] += nz[j] * ax
+
+
+def _forward_sub(cp, rv, nz, diag, n, x, alpha=None, beta=None, y=None):   # forward_sub! :64-79 / :84-102
+    for col in range(n):
+        idx = diag[col]
+        x[col] = x[col] / nz[idx] if alpha is None else alpha * x[col] / nz[idx] + beta * y[col]
+        for i in range(idx + 1, cp[col + 1]):
+            x[rv[i]] -= nz[i] * x[col]
+
+
+def _backward_sub(cp, rv, nz, diag, n, x, alpha, beta, y):              # backward_sub!(alpha, U, x, beta, y) :126-143
+    for col in range(n - 1, -1, -1):
+        idx = diag[col]
+        x[col] = alpha * x[col] / nz[idx] + beta * y[col]
+        for i in range(cp[col], idx):
+            x[rv[i]] -= nz[i] * x[col]
+
+
+def jacobi_(x, A, b, *, maxiter=10):
+    """jacobi!(x, A::SparseMatrixCSC, b; maxiter = 10) -- reference src/stationary_sparse.jl:203-237."""
+    A, cp, rv, nz, diag, n = _st_prepare(A)
+    T = x.dtype.type
+    for _ in range(maxiter):
+        nxt = b.astype(x.dtype, copy=True)                              # copyto!(j.next, j.b) :214
+        for col in range(n):                                            # mul!(-one(T), O, x, one(T), next) :148-173
+            ax = T(-1) * x[col]
+            for j in range(cp[col], diag[col]):
+                nxt[rv[j]] += nz[j] * ax
+            for j in range(diag[col] + 1, cp[col + 1]):
+                nxt[rv[j]] += nz[j] * ax
+        x[...] = nxt / nz[diag]                                         # ldiv!(j.x, j.O.diag, j.next) :217
+    return x
+
+
+def gauss_seidel_(x, A, b, *, maxiter=10):
+    """gauss_seidel!(x, A::SparseMatrixCSC, b; maxiter = 10) -- reference src/stationary_sparse.jl:247-284."""
+    A, cp, rv, nz, diag, n = _st_prepare(A)
+    T = x.dtype.type
+    for _ in range(maxiter):
+        _gs_multiply_upper(cp, rv, nz, diag, n, T(-1), x, T(1), b, x)   # :264
+        _forward_sub(cp, rv, nz, diag, n, x)                            # :265
+    return x
+
+
+def sor_(x, A, b, omega, *, maxiter=10):
+    """sor!(x, A::SparseMatrixCSC, b, omega; maxiter = 10) -- reference src/stationary_sparse.jl:293-348.  Returns the
+    iterate (the reference returns iterable.x, which after an odd number of pointer swaps is not the caller's array)."""
+    A, cp, rv, nz, diag, n = _st_prepare(A)
+    T = x.dtype.type
+    nxt = np.zeros_like(x)
+    for _ in range(maxiter):
+        _gs_multiply_upper(cp, rv, nz, diag, n, T(-1), x, T(1), b, nxt)                     # next = b - U x :312
+        _forward_sub(cp, rv, nz, diag, n, nxt, T(omega), T(1) - T(omega), x)                # :315
+        x, nxt = nxt, x                                                                     # :318
+    return x
+
+
+def ssor_(x, A, b, omega, *, maxiter=10):
+    """ssor!(x, A::SparseMatrixCSC, b, omega; maxiter = 10) -- reference src/stationary_sparse.jl:358-424."""
+    A, cp, rv, nz, diag, n = _st_prepare(A)
+    T = x.dtype.type
+    tmp = np.zeros_like(x)
+    for _ in range(maxiter):
+        _gs_multiply_upper(cp, rv, nz, diag, n, T(-1), x, T(1), b, tmp)                     # :394
+        _forward_sub(cp, rv, nz, diag, n, tmp, T(omega), T(1) - T(omega), x)                # :397-400
+        _gs_multiply_lower(cp, rv, nz, diag, n, T(-1), tmp, T(1), b, x)                     # :403
+        _backward_sub(cp, rv, nz, diag, n, x, T(omega), T(1) - T(omega), tmp)               # :406
+    return x
+
+
+# --------------------------------------------------------------------------------------------
 # Power method / inverse iteration (reference src/simple.jl)
 # --------------------------------------------------------------------------------------------
 def powm_(B, x, *, tol=None, maxiter=None, shift=0.0, inverse=False, log=False):

@@ -25,6 +25,7 @@
 #include "../../iterativesolvers.jl_b200/csrc/gmres_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/chebyshev_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/powm_core.h"
+#include "../../iterativesolvers.jl_b200/csrc/stationary_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/minres_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/bicgstabl_core.h"
 #include "../../iterativesolvers.jl_b200/csrc/lobpcg_constraint_core.h"
@@ -325,6 +326,30 @@ EXPORT int hostsim_powm(int is_f64, const hostsim_csr *A, void *x, double tol, i
   out->passes = be.passes; out->applies = be.applies;
   *theta = o.theta;
   return st;
+}
+
+// jacobi! / gauss_seidel! / sor! / ssor! on a CSR matrix with sorted rows (method 0..3); returns 0, or i+1 for the
+// SingularException of DiagonalIndices; *levels_f / *levels_b: number of dependency levels of the sweeps
+EXPORT int64_t hostsim_stationary(int is_f64, const hostsim_csr *A, void *x, const void *b, int method, double omega,
+                                  int64_t maxiter, int order, int *levels_f, int *levels_b, long *passes) {
+  HostBackend be;
+  be.order = order;
+  HostCsr a = mk(A, is_f64);
+  auto body = [&](auto tag) -> int64_t {
+    typedef decltype(tag) T;
+    b200::StLevels lv;
+    const bool fwd = method != b200::ST_JACOBI, bwd = method == b200::ST_SSOR;
+    const int64_t sing = b200::stationary_analyse<T, int64_t>(a.m, a.rowptr, a.colind, (const T *)a.vals, fwd, bwd, &lv);
+    if (sing) return sing;
+    *levels_f = fwd ? (int)lv.lptr_f.size() - 1 : 0;
+    *levels_b = bwd ? (int)lv.lptr_b.size() - 1 : 0;
+    b200::CsrView<T, int64_t> view{a.m, a.rowptr, a.colind, (const T *)a.vals};
+    const int st = b200::stationary_run<T, int64_t>(be, view, lv, lv.dpos.data(), lv.rows_f.data(), lv.rows_b.data(), (T *)x,
+                                                    (const T *)b, method, omega, maxiter);
+    *passes = be.passes;
+    return st ? -1 : 0;
+  };
+  return is_f64 ? body(double()) : body(float());
 }
 
 // minres! on a general operator

@@ -1175,3 +1175,63 @@ def test_python_powm_wrappers_with_a_fake_library(monkeypatch):
     assert abs(np.linalg.norm(xo) - 2) < 1e-12 and calls[-1][5] == 0
     isb.invpowm(csr, shift=2.0, rng=np.random.default_rng(0))
     assert calls[-1][4:6] == (2.0, 1)
+
+
+# ------------------------------------------------------------------------------------------ stationary methods
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_engine_stationary_methods_match_oracle_bit_for_bit(oracle, sim, dtype):
+    """the level-scheduled sweeps (csrc/stationary_core.h) reproduce the sequential column sweeps of the reference exactly."""
+    for order in (0, 1):
+        cases.case_stationary(oracle, lambda name, x, A, b, w, mi: sim.stationary_(name, x, A, b, w, maxiter=mi, order=order)[0],
+                              dtype, exact=True)
+    O = oracle.laplace_matrix(np.float64, 5, 3)
+    x, info = sim.stationary_("ssor", np.zeros(O.n), O.to_scipy(), np.ones(O.n), 1.0, maxiter=1)
+    assert info.levels_f == info.levels_b == 3 * 5 - 2 and info.passes == 2 * (3 * 5 - 2)      # wavefronts i + j + k = const
+
+
+def test_python_stationary_wrappers_with_a_fake_library(monkeypatch):
+    import ctypes as C
+    from importlib import import_module
+    import iterativesolvers_jl_b200 as isb
+    S = import_module("iterativesolvers_jl_b200.solvers")
+    calls = []
+
+    class FakeArr:
+        def __init__(self, a):
+            self.a = np.array(a, order="F")
+            self.shape, self.dtype = self.a.shape, self.a.dtype
+            self._p = C.c_void_p(0x5000)
+
+        @classmethod
+        def from_numpy(cls, ctx, a):
+            return cls(a)
+
+        def numpy(self):
+            return self.a + 1
+
+    class FakeLib:
+        def b200_stationary(self, ctx, A, x, b, method, omega, maxiter):
+            calls.append((method, omega, maxiter))
+            return -5 if maxiter == 99 else 0
+
+    monkeypatch.setattr(S, "lib", lambda: FakeLib())
+    monkeypatch.setattr(S, "DeviceArray", FakeArr)
+    monkeypatch.setattr(S, "is_device", lambda v: isinstance(v, FakeArr))
+    monkeypatch.setattr(S, "as_device_ptr", lambda v: v._p)
+    n = 6
+    csr = S.B200CSR.__new__(S.B200CSR)
+    csr.ctx, csr._h, csr.m_local, csr.n_global, csr.m_global, csr.dtype = SimpleNamespace(_h=None, world=1), C.c_void_p(7), n, n, n, np.dtype(np.float64)
+    csr.close = lambda: None
+    b = np.ones(n)
+    x = np.zeros(n)
+    assert isb.jacobi_(x, csr, b) is x and np.all(x == 1) and calls[-1] == (0, 1.0, 10)
+    isb.gauss_seidel_(x, csr, b, maxiter=3)
+    isb.sor_(x, csr, b, 1.3, maxiter=4)
+    isb.ssor_(x, csr, b, 0.7)
+    assert calls[-3:] == [(1, 1.0, 3), (2, 1.3, 4), (3, 0.7, 10)]
+    assert np.all(isb.jacobi(csr, b, maxiter=2) == 1) and np.all(isb.ssor(csr, b, 1.1) == 1) and calls[-1] == (3, 1.1, 10)
+    assert isb.sor(csr, b, 1.2, maxiter=5).shape == (n,) and isb.gauss_seidel(csr, b).shape == (n,)
+    with pytest.raises(np.linalg.LinAlgError):
+        isb.jacobi_(x, csr, b, maxiter=99)
+    with pytest.raises(TypeError):
+        isb.jacobi(isb.B200LinearOperator((n, n), np.float64, lambda y, v: None, ctx=csr.ctx), b)   # needs the matrix itself

@@ -256,3 +256,19 @@ def test_powm_and_invpowm(isb, oracle, dtype):
     lam, x, h = isb.powm(A, tol=1e-3, maxiter=20000, log=True, rng=np.random.default_rng(SEED))
     exact = 4 + 4 * np.cos(np.pi / (N + 1))
     assert h.isconverged and abs(lam - exact) <= 1e-3 and abs(np.linalg.norm(x) - 1) <= 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_stationary_methods(isb, oracle, dtype):
+    """jacobi! / gauss_seidel! / sor! / ssor! (reference src/stationary_sparse.jl) through b200_stationary: the level-scheduled
+    sweeps against the oracle's sequential column sweeps and the reference's own tests -- the case of the serial backend."""
+    def run(name, x, A, b, w, mi):
+        op = isb.B200CSR.from_scipy(sp.csc_matrix(A).astype(x.dtype))
+        fn = getattr(isb, name + "_")
+        return fn(x, op, b, w, maxiter=mi) if name in ("sor", "ssor") else fn(x, op, b, maxiter=mi)
+    cases.case_stationary(oracle, run, dtype, exact=False)
+    O = oracle.laplace_matrix(np.float64, 16, 3, base=1)                 # 46 wavefront levels, 4096 rows
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    b = np.ones(O.n)
+    x = isb.ssor(A, b, 1.2, maxiter=8)
+    assert relerr(x, oracle.ssor_(np.zeros(O.n), O, b, 1.2, maxiter=8)) <= 1e-13

@@ -12,6 +12,8 @@ A is a scipy sparse matrix; x0 is updated in place and returned.
 """
 import math
 
+import pytest
+
 import numpy as np
 import scipy.sparse as sp
 
@@ -662,3 +664,50 @@ def case_powm(oracle, run, dtype):
     lam3, x3, h3 = oracle.powm_(A, x0.copy(), tol=0.0, maxiter=3, log=True)
     th3, xs3, hs3 = run(sp.csr_matrix(A), x0.copy(), 0.0, 3)
     assert h3.iters == hs3.iters == 4 and not hs3.converged and np.abs(xs3 - x3).max() <= 50 * eps
+
+
+def case_stationary(oracle, run, dtype, exact):
+    """jacobi! / gauss_seidel! / sor! / ssor! for sparse matrices (reference src/stationary_sparse.jl, test/stationary.jl:17-95)
+    against the oracle's column-by-column restatement: the reference's assertions (residual after 2n sweeps of a diagonally
+    dominant system, SOR(1) == Gauss-Seidel, SingularException for a zero diagonal) and the iterates themselves -- bit for
+    bit when `exact` (serial backend: same arithmetic in the same order), to a few ulps otherwise (the GPU contracts a*b+c).
+    run(method, x0, A_scipy, b, omega, maxiter) -> x (raises np.linalg.LinAlgError for a singular diagonal)."""
+    rng = np.random.default_rng(1234322)
+    n, omega = 10, 1.2
+    eps = float(np.finfo(dtype).eps)
+    A = (sp.random(n, n, 4 / n, random_state=7, format="csc") + 2 * n * sp.eye(n)).tocsc().astype(dtype)
+    b, x0 = rng.random(n).astype(dtype), rng.random(n).astype(dtype)
+    tol = math.sqrt(eps)
+    fo = dict(jacobi=oracle.jacobi_, gauss_seidel=oracle.gauss_seidel_, sor=oracle.sor_, ssor=oracle.ssor_)
+
+    def same(a, c, sweeps):
+        return np.array_equal(a, c) if exact else np.abs(a - c).max() <= 8 * sweeps * eps * np.abs(c).max()
+
+    for name in fo:
+        args = (omega,) if name in ("sor", "ssor") else ()
+        for start in (np.zeros(n, dtype), x0):                           # jacobi(A, b) and jacobi!(copy(x0), A, b)
+            for mi in (1, 2, 7, 2 * n):
+                xo = fo[name](start.copy(), A, b, *args, maxiter=mi)
+                xs = run(name, start.copy(), A, b, omega, mi)
+                assert same(xs, xo, mi), (name, mi)
+            assert np.linalg.norm(b - A @ xs) / np.linalg.norm(b) <= tol, name                 # test/stationary.jl:33-54
+    A2 = (sp.random(10, 10, 0.4, random_state=11, format="csc") + 4 * sp.eye(10)).tocsc().astype(dtype)   # :60-73
+    b2 = (A2 @ np.ones(10)).astype(dtype)
+    for mi in range(1, 6):
+        g = run("gauss_seidel", np.zeros(10, dtype), A2, b2, 1.0, mi)
+        r = run("sor", np.zeros(10, dtype), A2, b2, 1.0, mi)
+        assert np.allclose(g, r, rtol=50 * eps, atol=0)
+    Z = sp.csc_matrix(np.array([[0.0, 1.0], [1.0, 0.0]], dtype=dtype))                          # :75-90
+    for name in fo:
+        with pytest.raises(np.linalg.LinAlgError):
+            run(name, np.zeros(2, dtype), Z, np.ones(2, dtype), omega, 3)
+    # larger patterns: a 3-D Laplacian (wavefront levels) and a random non-symmetric pattern
+    O = oracle.laplace_matrix(dtype, 6, 3)
+    L3 = O.to_scipy()
+    R = (sp.random(200, 200, 0.03, random_state=3, format="csc") + 10 * sp.eye(200)).tocsc().astype(dtype)
+    for M, w in ((L3, 1.5), (R, 0.8)):
+        m = M.shape[0]
+        bb, xx = rng.random(m).astype(dtype), rng.random(m).astype(dtype)
+        for name in fo:
+            args = (w,) if name in ("sor", "ssor") else ()
+            assert same(run(name, xx.copy(), M, bb, w, 5), fo[name](xx.copy(), M, bb, *args, maxiter=5), 5), name
