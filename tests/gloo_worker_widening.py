@@ -1,5 +1,5 @@
 """World-size-2 gloo worker (CPU) for the multi-GPU form of the fused-pass engines (qmr!, lsqr!, lsmr!, idrs!, and the
-general cg!, gmres!, minres!, bicgstabl!): every rank owns a row slab of A (and of A'), the operator application is "gather the operand, multiply the
+general cg!, gmres!, minres!, bicgstabl!, chebyshev!, powm!): every rank owns a row slab of A (and of A'), the operator application is "gather the operand, multiply the
 slab" (what the halo exchange + SpMV do on the GPUs) and every pass total goes through an allreduce before its scalar
 section runs -- the control flow of the CUDA backend on a multi-GPU context (csrc/pass.cuh), with torch.distributed
 in the place of NCCL.  Each rank compares its slab of the solution and the whole history with the single-process run."""
@@ -32,9 +32,13 @@ def main():
     Dinv = sp.diags(1.0 / dM).tocsr()                          # a preconditioner applied through the operator interface
     Sm = (S - 9.0 * sp.eye(n, format="csr")).tocsr()           # symmetric indefinite, for minres
     shadow = rng.random(n)
+    DinvS = sp.diags(1.0 / S.diagonal()).tocsr()
+    ds = 1.0 / np.sqrt(S.diagonal())
+    evp = np.linalg.eigvalsh((sp.diags(ds) @ S @ sp.diags(ds)).toarray())
+    lo, hi = 0.9 * evp[0], 1.1 * evp[-1]                       # bounds of the Jacobi-preconditioned spectrum, for chebyshev
     cuts = [0, 83, n]
-    lo, hi = cuts[rank], cuts[rank + 1]
-    m = hi - lo
+    lo_, hi_ = cuts[rank], cuts[rank + 1]
+    m = hi_ - lo_
 
     # ---- single-process references (every rank computes them; cheap)
     ref = {
@@ -47,7 +51,11 @@ def main():
                             initially_zero=True),
         "minres": sim.minres_(np.zeros(n), Sm, b, maxiter=60, initially_zero=True),
         "bicgstabl": sim.bicgstabl_(np.zeros(n), M, b, 2, shadow, Pl=Dinv, max_mv_products=80, initial_zero=True),
+        "chebyshev": sim.chebyshev_(np.zeros(n), S, b, lo, hi, Pl=DinvS, maxiter=60, initially_zero=True),
     }
+    x0p = rng.random(n)
+    x0p /= np.linalg.norm(x0p)
+    th_ref, xp_ref, hp_ref = sim.powm_(S, x0p.copy(), tol=1e-9, maxiter=400)
 
     # ---- row-partitioned runs
     slabs = {}                                                  # op_id -> the slab whose product the engine asks for
@@ -85,36 +93,40 @@ def main():
 
     sim.Csr = RegCsr
     sim.set_dist(apply, allreduce)
-    A_loc, At_loc, S_loc = M[lo:hi], Mt[lo:hi], S[lo:hi]
+    A_loc, At_loc, S_loc = M[lo_:hi_], Mt[lo_:hi_], S[lo_:hi_]
     out = {
-        "qmr": sim.qmr_(np.zeros(m), A_loc, b[lo:hi], initially_zero=True, At=At_loc),
-        "idrs": sim.idrs_(np.zeros(m), A_loc, b[lo:hi], P[lo:hi]),
-        "lsqr": sim.lsqr_(np.zeros(m), A_loc, b[lo:hi], maxiter=12, atol=0.0, btol=0.0, conlim=0.0, At=At_loc),
-        "lsmr": sim.lsmr_(np.zeros(m), A_loc, b[lo:hi], maxiter=12, atol=0.0, btol=0.0, conlim=0.0, At=At_loc),
-        "cg": sim.cg_(np.zeros(m), S_loc, b[lo:hi], initially_zero=True, diag=S.diagonal()[lo:hi]),
-        "gmres": sim.gmres_(np.zeros(m), A_loc, b[lo:hi], pl_diag=dM[lo:hi], Pr=Dinv[lo:hi], restart=7, maxiter=40,
+        "qmr": sim.qmr_(np.zeros(m), A_loc, b[lo_:hi_], initially_zero=True, At=At_loc),
+        "idrs": sim.idrs_(np.zeros(m), A_loc, b[lo_:hi_], P[lo_:hi_]),
+        "lsqr": sim.lsqr_(np.zeros(m), A_loc, b[lo_:hi_], maxiter=12, atol=0.0, btol=0.0, conlim=0.0, At=At_loc),
+        "lsmr": sim.lsmr_(np.zeros(m), A_loc, b[lo_:hi_], maxiter=12, atol=0.0, btol=0.0, conlim=0.0, At=At_loc),
+        "cg": sim.cg_(np.zeros(m), S_loc, b[lo_:hi_], initially_zero=True, diag=S.diagonal()[lo_:hi_]),
+        "gmres": sim.gmres_(np.zeros(m), A_loc, b[lo_:hi_], pl_diag=dM[lo_:hi_], Pr=Dinv[lo_:hi_], restart=7, maxiter=40,
                             orth_meth="dgks", initially_zero=True),
-        "minres": sim.minres_(np.zeros(m), Sm[lo:hi], b[lo:hi], maxiter=60, initially_zero=True),
-        "bicgstabl": sim.bicgstabl_(np.zeros(m), A_loc, b[lo:hi], 2, shadow[lo:hi], Pl=Dinv[lo:hi], max_mv_products=80,
+        "minres": sim.minres_(np.zeros(m), Sm[lo_:hi_], b[lo_:hi_], maxiter=60, initially_zero=True),
+        "bicgstabl": sim.bicgstabl_(np.zeros(m), A_loc, b[lo_:hi_], 2, shadow[lo_:hi_], Pl=Dinv[lo_:hi_], max_mv_products=80,
                                     initial_zero=True),
+        "chebyshev": sim.chebyshev_(np.zeros(m), S_loc, b[lo_:hi_], lo, hi, Pl=DinvS[lo_:hi_], maxiter=60, initially_zero=True),
     }
+    th_d, xp_d, hp_d = sim.powm_(S_loc, x0p[lo_:hi_].copy(), tol=1e-9, maxiter=400)
     sim.set_dist()
     sim.Csr = orig_csr
 
-    for name in ("qmr", "idrs", "cg", "gmres", "minres", "bicgstabl"):
+    assert hp_d.iters == hp_ref.iters and hp_d.converged and abs(th_d - th_ref) <= 1e-12 * abs(th_ref)
+    assert np.linalg.norm(xp_d - xp_ref[lo_:hi_]) <= 1e-10
+    for name in ("qmr", "idrs", "cg", "gmres", "minres", "bicgstabl", "chebyshev"):
         (xr, hr), (xd, hd) = ref[name], out[name]
         assert hd.iters == hr.iters and hd.converged == hr.converged and hd.mvps == hr.mvps, (name, hd.iters, hr.iters)
         # (minres on an indefinite operator amplifies the last-bit differences of another summation order by ~10x per
         # few iterations -- the same between two orders of the single-process run: compare the first 15 iterations)
         k = min(len(hr.hist), 15 if name == "minres" else 30)
         assert k > 3 and np.max(np.abs(hd.hist[:k] - hr.hist[:k])) <= 1e-10 * hr.hist[0], name
-        assert np.linalg.norm(xd - xr[lo:hi]) <= (1e-2 if name == "minres" else 1e-10) * np.linalg.norm(xr), name
+        assert np.linalg.norm(xd - xr[lo_:hi_]) <= (1e-2 if name == "minres" else 1e-10) * np.linalg.norm(xr), name
     for name in ("lsqr", "lsmr"):
         (xr, hr), (xd, hd) = ref[name], out[name]
         assert hd.iters == hr.iters == 12 and hd.istop == hr.istop == 7 and (hd.mvps, hd.mtvps) == (hr.mvps, hr.mtvps)
         for key in ("anorm", "rnorm", "cnorm"):
             assert np.max(np.abs(hd.hist[key][:8] - hr.hist[key][:8])) <= 1e-10 * np.max(np.abs(hr.hist[key][:8])), (name, key)
-        assert np.linalg.norm(xd - xr[lo:hi]) <= 1e-8 * np.linalg.norm(xr), name
+        assert np.linalg.norm(xd - xr[lo_:hi_]) <= 1e-8 * np.linalg.norm(xr), name
     dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")
