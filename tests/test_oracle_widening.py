@@ -1235,3 +1235,65 @@ def test_python_stationary_wrappers_with_a_fake_library(monkeypatch):
         isb.jacobi_(x, csr, b, maxiter=99)
     with pytest.raises(TypeError):
         isb.jacobi(isb.B200LinearOperator((n, n), np.float64, lambda y, v: None, ctx=csr.ctx), b)   # needs the matrix itself
+
+
+def test_dense_stationary_iterations_equal_the_sparse_ones(oracle):
+    """the AbstractMatrix methods of reference src/stationary.jl (:48-70 Jacobi, :108-127 Gauss-Seidel, :167-186 SOR,
+    :227-258 SSOR), restated literally, against the sparse restatement the engine is verified with: Jacobi and
+    Gauss-Seidel bit for bit, SOR to rounding (the dense code writes the relaxation as x += w (t / a - x)); dense SSOR is a
+    different iteration."""
+    rng = np.random.default_rng(7)
+    n, w = 12, 1.2
+    A = rng.random((n, n)) + 2 * n * np.eye(n)
+    b, x0 = rng.random(n), rng.random(n)
+
+    def dense(kind, x, maxiter):
+        x = x.copy()
+        tmp = np.zeros(n)
+        for _ in range(maxiter):
+            if kind == "jacobi":
+                nxt = b.copy()
+                for col in range(n):
+                    for row in range(n):
+                        if row != col:
+                            nxt[row] -= A[row, col] * x[col]
+                x = nxt / np.diag(A)
+                continue
+            if kind == "gauss_seidel":
+                for col in range(n):
+                    for row in range(col):
+                        x[row] -= A[row, col] * x[col]
+                    x[col] = b[col]
+                for col in range(n):
+                    x[col] /= A[col, col]
+                    for row in range(col + 1, n):
+                        x[row] -= A[row, col] * x[col]
+                continue
+            for col in range(n):                                       # SOR, and the forward half of SSOR
+                for row in range(col):
+                    tmp[row] -= A[row, col] * x[col]
+                tmp[col] = b[col]
+            for col in range(n):
+                x[col] += w * (tmp[col] / A[col, col] - x[col])
+                for row in range(col + 1, n):
+                    tmp[row] -= A[row, col] * x[col]
+            if kind == "ssor":
+                for col in range(n - 1, -1, -1):
+                    tmp[col] = b[col]
+                    for row in range(col + 1, n):
+                        tmp[row] -= A[row, col] * x[col]
+                for col in range(n - 1, -1, -1):
+                    for row in range(col):
+                        tmp[row] -= A[row, col] * x[col]
+                    x[col] += w * (tmp[col] / A[col, col] - x[col])
+        return x
+
+    assert np.array_equal(dense("jacobi", x0, 5), oracle.jacobi_(x0.copy(), A, b, maxiter=5))
+    assert np.array_equal(dense("gauss_seidel", x0, 5), oracle.gauss_seidel_(x0.copy(), A, b, maxiter=5))
+    assert np.abs(dense("sor", x0, 5) - oracle.sor_(x0.copy(), A, b, w, maxiter=5)).max() <= 1e-15
+    # the dense SSOR is NOT the sparse one: its backward half reads the upper triangle with the forward half's values
+    # (src/stationary.jl:253-257 subtracts A[row, col] * x[col] before x[col] is updated) -- the package refuses dense ssor
+    assert np.abs(dense("ssor", x0, 5) - oracle.ssor_(x0.copy(), A, b, w, maxiter=5)).max() > 1e-8
+    import iterativesolvers_jl_b200 as isb
+    with pytest.raises(isb.B200Error, match="different iteration"):
+        isb.ssor(A, b, w)
