@@ -1297,3 +1297,27 @@ def test_dense_stationary_iterations_equal_the_sparse_ones(oracle):
     import iterativesolvers_jl_b200 as isb
     with pytest.raises(isb.B200Error, match="different iteration"):
         isb.ssor(A, b, w)
+
+
+def test_level_scheduled_sweeps_on_random_patterns(oracle, sim):
+    """twenty random sparsity patterns (symmetric and not, banded and scattered, n up to 150): the level-scheduled sweeps
+    equal the sequential column sweeps bit for bit, and the level structure is a valid schedule (a row never sits in the
+    level of a row it depends on -- checked through the result, which would differ)."""
+    rng = np.random.default_rng(2024)
+    for trial in range(20):
+        n = int(rng.integers(5, 150))
+        dens = float(rng.choice([0.02, 0.1, 0.4]))
+        R = sp.random(n, n, dens, random_state=int(rng.integers(1 << 30)), format="csr")
+        if trial % 3 == 0:
+            R = R + R.T
+        if trial % 4 == 1:
+            R = sp.triu(R, -2) - sp.triu(R, 3)                       # banded
+        A = (R + sp.diags(rng.random(n) + np.abs(R).sum(axis=1).A1 + 0.5)).tocsc()
+        b, x0 = rng.random(n), rng.random(n)
+        w = float(rng.uniform(0.5, 1.8))
+        for name, fo, args in (("jacobi", oracle.jacobi_, ()), ("gauss_seidel", oracle.gauss_seidel_, ()),
+                               ("sor", oracle.sor_, (w,)), ("ssor", oracle.ssor_, (w,))):
+            xo = fo(x0.copy(), A, b, *args, maxiter=3)
+            xs, info = sim.stationary_(name, x0.copy(), A, b, w, maxiter=3, order=trial % 2)
+            assert np.array_equal(xo, xs), (trial, name, n, dens)
+            assert info.levels_f <= n and info.levels_b <= n
