@@ -14,12 +14,12 @@ The directory name contains a dot, so import it through the repo-root alias modu
 from ._lib import B200Error, lib  # noqa: F401
 from .device import Context, DeviceArray, default_context, pinned_empty  # noqa: F401
 from .operators import B200CSR, B200LinearOperator, FunctionPrec, HaloPlan, Identity, JacobiPrec  # noqa: F401
-from .history import ConvergenceHistory  # noqa: F401
+from .history import ConvergenceHistory, niters, nprods, nrests  # noqa: F401
 from .generators import laplace_matrix, laplace_csr_slab, advection_dominated, mmread  # noqa: F401
 from .solvers import (cg, cg_, chebyshev, chebyshev_, gmres, gmres_, minres, minres_, bicgstabl, bicgstabl_, lobpcg,  # noqa: F401
                       LOBPCGResults, orthogonalize_and_normalize_, hessenberg_ldiv_,
                       cg_iterator_, CGIterable, CGStateVariables, KrylovIterable, gmres_iterable_, minres_iterable_,
-                      bicgstabl_iterator_, powm_, powm, invpowm_, invpowm, jacobi_, jacobi, gauss_seidel_, gauss_seidel,
+                      bicgstabl_iterator_, minres_iterable, bicgstabl_iterator, LOBPCGIterator, lobpcg_, powm_, powm, invpowm_, invpowm, jacobi_, jacobi, gauss_seidel_, gauss_seidel,
                       sor_, sor, ssor_, ssor,
                       qmr, qmr_, lsqr, lsqr_, lsmr, lsmr_, idrs, idrs_, LobpcgConstraint, svdl, SVD,
                       PartialFactorization)

@@ -33,3 +33,18 @@ class ConvergenceHistory:
         if self.restart is None:
             raise ValueError("not a restarted method")
         return int(math.ceil(self.iters / self.restart))
+
+
+def niters(history: ConvergenceHistory) -> int:
+    """niters(history) -- reference src/history.jl:245."""
+    return history.niters
+
+
+def nprods(history: ConvergenceHistory) -> int:
+    """nprods(history) -- reference src/history.jl:238."""
+    return history.nprods
+
+
+def nrests(history: ConvergenceHistory) -> int:
+    """nrests(history) -- reference src/history.jl:252."""
+    return history.nrests

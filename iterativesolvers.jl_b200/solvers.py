@@ -703,6 +703,22 @@ def minres_iterable_(x, A, b, *, skew_hermitian=False, abstol=0.0, reltol=None, 
     return KrylovIterable(lib().b200_minres_iter_create, x, A, b, opts, [A])
 
 
+def minres_iterable(A, b, **kw):
+    """minres_iterable(A, b; kwargs...) = minres_iterable!(zerox(A, b), A, b; initially_zero = true, kwargs...)
+    -- reference src/minres.jl:27-37."""
+    _check_operator(A, linop_ok=True)
+    x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
+    return minres_iterable_(x, A, b, initially_zero=True, **kw)
+
+
+def bicgstabl_iterator(A, b, l=2, **kw):
+    """bicgstabl_iterator(A, b, l; kwargs...) = bicgstabl_iterator!(zerox(A, b), A, b, l; initial_zero = true, kwargs...)
+    -- reference src/bicgstabl.jl:24-25."""
+    _check_operator(A, linop_ok=True)
+    x = DeviceArray.zeros(A.ctx, A.m_local, A.dtype) if is_device(b) else np.zeros(A.m_local, dtype=A.dtype)
+    return bicgstabl_iterator_(x, A, b, l, initial_zero=True, **kw)
+
+
 def bicgstabl_iterator_(x, A, b, l=2, *, Pl=None, max_mv_products=None, abstol=0.0, reltol=None, initial_zero=False,
                         r_shadow=None, rng=None):
     """bicgstabl_iterator!(x, A, b, l; Pl, max_mv_products, abstol, reltol, initial_zero) -- reference
@@ -1135,6 +1151,52 @@ def lobpcg(A, largest: bool, X0, nev=None, *, B=None, P=None, C_=None, tol=None,
             converged_x += sizeX
     con.close()
     return LOBPCGResults(lam_all, X_all, float(tol), rn_all, iterations, int(maxiter), conv, traces)
+
+
+class LOBPCGIterator:
+    """LOBPCGIterator(A, B, largest, X, P = nothing, C = nothing) -- reference src/lobpcg.jl:450-493: the operators, the
+    block X the iteration overwrites, the preconditioner and the constraint (built once: Constraint(C, B, X), :452).  The
+    reference preallocates every block here; on the device the context scratch plays that role, so this object only ties the
+    pieces together for `lobpcg_(iterator; ...)`.  X: n x blocksize host array (updated in place) or DeviceArray."""
+
+    def __init__(self, A, B, largest: bool, X, P=None, C_=None, **kw):
+        Cc = kw.pop("C", C_)
+        if kw:
+            raise TypeError(f"unexpected keyword arguments {sorted(kw)}")
+        _check_operator(A, linop_ok=True)
+        if B is not None:
+            _check_operator(B, linop_ok=True)
+        self.A, self.B, self.largest, self.P = A, B, bool(largest), P
+        self.X = X
+        n, bs = X.shape
+        if n != A.m_local:
+            raise ValueError("X has the wrong number of rows")
+        if n < 3 * bs:
+            raise B200Error("The order of the matrix must be at least 3 times the block size")       # src/lobpcg.jl:834
+        self.constraint = (Cc if isinstance(Cc, LobpcgConstraint) or Cc is None
+                           else LobpcgConstraint(A.ctx, n, A.dtype, Cc, B=B))
+        self.iteration = 0
+        self.trace = []
+
+
+def lobpcg_(iterator: LOBPCGIterator, *, log=False, maxiter=200, not_zeros=False, tol=None, rng=None):
+    """lobpcg!(iterator::LOBPCGIterator; log, maxiter, not_zeros, tol) -> LOBPCGResults -- reference src/lobpcg.jl:865-893.
+    Overwrites iterator.X with the Ritz vectors (as the reference overwrites iterator.XBlocks.block)."""
+    it = iterator
+    A = it.A
+    if tol is None:
+        tol = _eps(A.dtype) ** 0.3                             # default_tolerance :751
+    host = not is_device(it.X)
+    Xd = DeviceArray.from_numpy(A.ctx, np.asarray(it.X, dtype=A.dtype)) if host else it.X
+    trace = [] if log else None
+    lam, rn, res = _lobpcg_block(A, it.largest, Xd, it.P, it.constraint, tol, maxiter, not_zeros, rng, False, B=it.B,
+                                 trace=trace)
+    if host:
+        it.X[...] = Xd.numpy()
+    it.iteration = int(res.iterations)
+    it.trace = trace or []
+    return LOBPCGResults(lam.astype(A.dtype), it.X, float(tol), rn.astype(A.dtype), int(res.iterations), int(maxiter),
+                         bool(res.converged), it.trace)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1321,3 +1321,76 @@ def test_level_scheduled_sweeps_on_random_patterns(oracle, sim):
             xs, info = sim.stationary_(name, x0.copy(), A, b, w, maxiter=3, order=trial % 2)
             assert np.array_equal(xo, xs), (trial, name, n, dens)
             assert info.levels_f <= n and info.levels_b <= n
+
+
+def test_lobpcg_iterator_and_allocating_iterable_forms_with_a_fake_library(monkeypatch):
+    """LOBPCGIterator + lobpcg_(iterator) (reference src/lobpcg.jl:450-493, :865-893: X is overwritten, the constraint is
+    built once), minres_iterable / bicgstabl_iterator (zerox + initially_zero), niters / nprods / nrests."""
+    import ctypes as C
+    from importlib import import_module
+    import iterativesolvers_jl_b200 as isb
+    S = import_module("iterativesolvers_jl_b200.solvers")
+    calls = []
+
+    class FakeArr:
+        def __init__(self, a):
+            self.a = np.array(a, order="F")
+            self.shape, self.dtype = self.a.shape, self.a.dtype
+            self._p = C.c_void_p(0x5000)
+
+        @classmethod
+        def from_numpy(cls, ctx, a):
+            return cls(a)
+
+        def numpy(self):
+            return self.a + 1
+
+        code = 0
+
+        def column(self, j):
+            return FakeArr(self.a[:, j])
+
+    class FakeLib:
+        def __getattr__(self, name):
+            def f(*args):
+                calls.append((name, args))
+                if name == "b200_lobpcg_constraint_create":
+                    args[-1]._obj.value = 0x77
+                if name.endswith("_iter_create"):
+                    args[-1]._obj.value = 0x99
+                if name == "b200_nrm2":
+                    args[-1]._obj.value = 1.0
+                if name in ("b200_lobpcg_solve", "b200_lobpcg_solve_constrained"):
+                    res = [a._obj for a in args if isinstance(getattr(a, "_obj", None), S._lib.LobpcgResult)][0]
+                    res.iterations, res.converged = 7, 1
+                return 0
+            return f
+
+    monkeypatch.setattr(S, "lib", lambda: FakeLib())
+    monkeypatch.setattr(S, "DeviceArray", FakeArr)
+    monkeypatch.setattr(S, "is_device", lambda v: isinstance(v, FakeArr))
+    monkeypatch.setattr(S, "as_device_ptr", lambda v: v._p)
+    n = 30
+    A = S.B200CSR.__new__(S.B200CSR)
+    A.ctx, A._h, A.m_local, A.n_global, A.m_global, A.dtype = SimpleNamespace(_h=None, world=1), C.c_void_p(7), n, n, n, np.dtype(np.float64)
+    A.close = lambda: None
+    X = np.zeros((n, 2)) + 0.5
+    it = isb.LOBPCGIterator(A, None, False, X, None, C=np.ones((n, 1)))
+    assert [c[0] for c in calls] == ["b200_lobpcg_constraint_create"]
+    r = isb.lobpcg_(it, maxiter=50, tol=1e-3, not_zeros=True)
+    assert calls[-1][0] == "b200_lobpcg_solve_constrained" and r.X is X and np.all(X == 1.5) and r.iterations == it.iteration == 7
+    r = isb.lobpcg_(it, log=True)                                # the same iterator again: no new constraint
+    assert [c[0] for c in calls].count("b200_lobpcg_constraint_create") == 1 and r.trace == it.trace
+    with pytest.raises(isb.B200Error):
+        isb.LOBPCGIterator(A, None, True, np.zeros((n, 11)))     # n < 3 * blocksize
+    calls.clear()
+    b = np.ones(n)
+    it2 = isb.minres_iterable(A, b, maxiter=5)
+    o = calls[0][1][5]._obj
+    assert calls[0][0] == "b200_minres_iter_create" and o.initially_zero == 1 and o.maxiter == 5 and it2.x.shape == (n,)
+    calls.clear()
+    it3 = isb.bicgstabl_iterator(A, b, 3, rng=np.random.default_rng(0))
+    o = calls[0][1][5]._obj
+    assert calls[0][0] == "b200_bicgstabl_iter_create" and o.initial_zero == 1 and o.l == 3
+    h = isb.ConvergenceHistory(mvps=5, mtvps=2, iters=9, restart=4)
+    assert (isb.niters(h), isb.nprods(h), isb.nrests(h)) == (9, 7, 3)
