@@ -23,3 +23,8 @@ from .solvers import (cg, cg_, chebyshev, chebyshev_, gmres, gmres_, minres, min
                       sor_, sor, ssor_, ssor,
                       qmr, qmr_, lsqr, lsqr_, lsmr, lsmr_, idrs, idrs_, LobpcgConstraint, svdl, SVD,
                       PartialFactorization)
+
+# type names the reference exports for its iterables (src/cg.jl:3, src/bicgstabl.jl:3): one device class serves both CG
+# variants (the preconditioner decides), and the fused-pass iterables share a class
+PCGIterable = CGIterable
+BiCGStabIterable = KrylovIterable
