@@ -53,7 +53,7 @@ enum { B200_ORTH_MGS = 0, B200_ORTH_CGS = 1, B200_ORTH_DGKS = 2 };
 enum { B200_PREC_IDENTITY = 0, B200_PREC_JACOBI = 1,
        B200_PREC_CALLBACK = 2 /* `diag` points to a b200_linop whose apply is ldiv!(y, Pl, x); accepted by
                                  the chebyshev / gmres / bicgstabl / idrs / lobpcg entry points (b200_cg_solve_op takes its callback as an
-                                 argument); b200_cg_solve on a b200_csr rejects it */ };
+                                 argument as well) */ };
 
 typedef struct b200_ctx b200_ctx;   /* device + stream (+ NCCL communicator)                     */
 typedef struct b200_csr b200_csr;   /* the operator A: CSR int32 on device, row-partitioned       */

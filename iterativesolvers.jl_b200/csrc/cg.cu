@@ -24,6 +24,7 @@
 //     by a 1-thread bookkeeping kernel.
 #include "blas1.cuh"
 #include "spmv_stream.cuh"
+#include "linop.cuh"
 
 using namespace b200;
 
@@ -655,6 +656,12 @@ extern "C" {
 
 int b200_cg_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev, const b200_cg_opts *opts,
                   b200_result *res, double *resnorm_host, int64_t resnorm_cap) {
+  if (ctx && A && x_dev && b_dev && opts && opts->Pl.kind == B200_PREC_CALLBACK) {   // ldiv! by callback: the general engine
+    B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
+    B200_REQUIRE(is_square(A), "this solver needs a square operator");
+    return cg_general(ctx, CudaOp{A, nullptr}, A->dtype, A->m_local, A->n_global, nullptr, x_dev, b_dev, opts, res,
+                      resnorm_host, resnorm_cap);
+  }
   B200_TRY(check_cg_args(ctx, A, x_dev, b_dev, opts));
   B200_CUDA(cudaSetDevice(ctx->device));
   return A->dtype == B200_F64

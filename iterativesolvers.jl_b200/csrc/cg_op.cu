@@ -10,6 +10,46 @@ using namespace b200;
 
 namespace b200 {
 
+// cg! on a CSR or callback operator (cg_core.h).  Pl: the preconditioner callback given as an argument, or NULL: then
+// opts->Pl decides (Identity, Jacobi, or B200_PREC_CALLBACK with the descriptor in opts->Pl.diag).
+int cg_general(b200_ctx *ctx, const CudaOp &A, int dtype, int64_t n, int64_t n_global, const b200_linop *Pl, void *x_dev,
+               const void *b_dev, const b200_cg_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap) {
+  if (!Pl && opts->Pl.kind == B200_PREC_CALLBACK) Pl = (const b200_linop *)opts->Pl.diag;
+  if (Pl) {
+    B200_TRY(check_linop(Pl, "Pl"));
+    B200_REQUIRE(Pl->dtype == dtype && Pl->m_local == n && Pl->n_local == n,
+                 "Pl must act on vectors of the operator's local length");
+  } else {
+    B200_REQUIRE(opts->Pl.kind == B200_PREC_IDENTITY || (opts->Pl.kind == B200_PREC_JACOBI && opts->Pl.diag),
+                 "unsupported preconditioner");
+  }
+  B200_REQUIRE(!opts->fixed_iterations && !opts->variant, "fixed_iterations / variant are not available on this path");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  CudaBackend be{ctx};
+  CudaOp p{nullptr, Pl};
+  const void *diag = (!Pl && opts->Pl.kind == B200_PREC_JACOBI) ? opts->Pl.diag : nullptr;
+  CgpOutcome o;
+  memset(&o, 0, sizeof(o));
+  const int st = dtype == B200_F64
+                     ? cgp_run<double>(be, &A, Pl ? &p : nullptr, (const double *)diag, n, n_global, (double *)x_dev,
+                                       (const double *)b_dev, opts->abstol, opts->reltol, opts->maxiter,
+                                       opts->initially_zero, opts->check_every, resnorm_cap, resnorm_host, &o)
+                     : cgp_run<float>(be, &A, Pl ? &p : nullptr, (const float *)diag, n, n_global, (float *)x_dev,
+                                      (const float *)b_dev, opts->abstol, opts->reltol, opts->maxiter,
+                                      opts->initially_zero, opts->check_every, resnorm_cap, resnorm_host, &o);
+  if (st != B200_OK) return st;
+  if (res) {
+    res->iters = o.iters;
+    res->mvps = o.mvps;
+    res->isconverged = o.converged;
+    res->status = o.breakdown ? B200_ERR_BREAKDOWN : 0;
+    res->tol = o.tol;
+    res->residual = o.residual;
+    res->n_resnorm = o.n_hist;
+  }
+  return B200_OK;
+}
+
 // chebyshev! on a CSR or callback operator with Identity / Jacobi / callback preconditioner (chebyshev_core.h)
 int chebyshev_general(b200_ctx *ctx, const CudaOp &A, int dtype, int64_t n, int64_t n_global, void *x_dev,
                       const void *b_dev, double lmin, double lmax, const b200_cg_opts *opts, b200_result *res,
@@ -73,39 +113,8 @@ int b200_cg_solve_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *Pl, v
   B200_REQUIRE(ctx && x_dev && b_dev && opts, "NULL argument");
   B200_TRY(check_linop(A, "A"));
   B200_REQUIRE(A->m_global == A->n_global && A->m_local == A->n_local, "cg! needs a square operator");
-  if (Pl) {
-    B200_TRY(check_linop(Pl, "Pl"));
-    B200_REQUIRE(Pl->dtype == A->dtype && Pl->m_local == A->m_local && Pl->n_local == A->m_local,
-                 "Pl must act on vectors of the operator's local length");
-  }
-  B200_REQUIRE(opts->Pl.kind == B200_PREC_IDENTITY || (opts->Pl.kind == B200_PREC_JACOBI && opts->Pl.diag),
-               "unsupported preconditioner");
-  B200_REQUIRE(!opts->fixed_iterations && !opts->variant, "fixed_iterations / variant are not available on this path");
-  B200_CUDA(cudaSetDevice(ctx->device));
-  CudaBackend be{ctx};
-  CudaOp a{nullptr, A}, p{nullptr, Pl};
-  const void *diag = (!Pl && opts->Pl.kind == B200_PREC_JACOBI) ? opts->Pl.diag : nullptr;
-  CgpOutcome o;
-  memset(&o, 0, sizeof(o));
-  const int64_t n = A->m_local;
-  const int st = A->dtype == B200_F64
-                     ? cgp_run<double>(be, &a, Pl ? &p : nullptr, (const double *)diag, n, A->n_global, (double *)x_dev,
-                                       (const double *)b_dev, opts->abstol, opts->reltol, opts->maxiter,
-                                       opts->initially_zero, opts->check_every, resnorm_cap, resnorm_host, &o)
-                     : cgp_run<float>(be, &a, Pl ? &p : nullptr, (const float *)diag, n, A->n_global, (float *)x_dev,
-                                      (const float *)b_dev, opts->abstol, opts->reltol, opts->maxiter,
-                                      opts->initially_zero, opts->check_every, resnorm_cap, resnorm_host, &o);
-  if (st != B200_OK) return st;
-  if (res) {
-    res->iters = o.iters;
-    res->mvps = o.mvps;
-    res->isconverged = o.converged;
-    res->status = o.breakdown ? B200_ERR_BREAKDOWN : 0;
-    res->tol = o.tol;
-    res->residual = o.residual;
-    res->n_resnorm = o.n_hist;
-  }
-  return B200_OK;
+  return cg_general(ctx, CudaOp{nullptr, A}, A->dtype, A->m_local, A->n_global, Pl, x_dev, b_dev, opts, res, resnorm_host,
+                    resnorm_cap);
 }
 
 // powm!(B, x; shift, inverse, tol, maxiter) / invpowm! (reference src/simple.jl:118-151, :186): exactly one of A (device CSR)

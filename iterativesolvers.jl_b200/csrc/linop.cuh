@@ -14,4 +14,6 @@ int bicgstabl_general(b200_ctx *ctx, const CudaOp &A, int dtype, int64_t n, int6
 int chebyshev_general(b200_ctx *ctx, const CudaOp &A, int dtype, int64_t n, int64_t n_global, void *x_dev,
                       const void *b_dev, double lmin, double lmax, const b200_cg_opts *opts, b200_result *res,
                       double *resnorm_host, int64_t resnorm_cap);                                               // cg_op.cu
+int cg_general(b200_ctx *ctx, const CudaOp &A, int dtype, int64_t n, int64_t n_global, const b200_linop *Pl, void *x_dev,
+               const void *b_dev, const b200_cg_opts *opts, b200_result *res, double *resnorm_host, int64_t resnorm_cap);   // cg_op.cu
 }

@@ -272,3 +272,27 @@ def test_stationary_methods(isb, oracle, dtype):
     b = np.ones(O.n)
     x = isb.ssor(A, b, 1.2, maxiter=8)
     assert relerr(x, oracle.ssor_(np.zeros(O.n), O, b, 1.2, maxiter=8)) <= 1e-13
+
+
+def test_cg_solve_forwards_a_callback_preconditioner(isb):
+    """b200_cg_solve on a CSR operator with B200_PREC_CALLBACK in the option block runs the general CG engine (what a C / Julia
+    caller gets; the Python cg_ reaches the same engine through b200_cg_solve_op)."""
+    import ctypes as C
+    from iterativesolvers_jl_b200 import _lib
+    rng = np.random.default_rng(SEED)
+    n = 500
+    M = sp.random(n, n, 0.01, random_state=5, format="csc")
+    M = (M + M.T + 10 * sp.eye(n)).tocsc()
+    A = isb.B200CSR.from_scipy(M)
+    jac = isb.JacobiPrec(M.diagonal())
+    Pl = isb.FunctionPrec(n, np.float64, lambda y, v: jac.ldiv_(y, v))
+    b = rng.standard_normal(n)
+    x_ref, h_ref = isb.cg(A, b, Pl=jac, log=True)                                 # tuned engine, Jacobi
+    xd, bd = isb.DeviceArray.zeros(A.ctx, n), isb.DeviceArray.from_numpy(A.ctx, b)
+    opts = _lib.CgOpts(0.0, float(np.sqrt(np.finfo(np.float64).eps)), n, 1, 0, isb.operators.precond_to_c(Pl, A), 0, 0)
+    res = _lib.Result()
+    hist = np.zeros(n + 1)
+    assert isb.lib().b200_cg_solve(A.ctx._h, A._h, xd._p, bd._p, C.byref(opts), C.byref(res),
+                                   hist.ctypes.data_as(C.c_void_p), n + 1) == 0
+    Pl.op.raise_pending()
+    assert res.isconverged and abs(res.iters - h_ref.iters) <= 1 and relerr(xd.numpy(), x_ref) <= 1e-7
