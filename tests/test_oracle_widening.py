@@ -1394,3 +1394,56 @@ def test_lobpcg_iterator_and_allocating_iterable_forms_with_a_fake_library(monke
     assert calls[0][0] == "b200_bicgstabl_iter_create" and o.initial_zero == 1 and o.l == 3
     h = isb.ConvergenceHistory(mvps=5, mtvps=2, iters=9, restart=4)
     assert (isb.niters(h), isb.nprods(h), isb.nrests(h)) == (9, 7, 3)
+
+
+def test_general_engines_edge_cases(oracle, sim):
+    """the corner cases the reference's tests pin (test/cg.jl:50-51 zero rhs => zero x in 0 iterations, test/gmres.jl:68-73
+    identity => lucky breakdown after one step) and a few more -- n = 1, 2, 3 with restart > n, maxiter = 0 -- on the
+    general cg / gmres / minres / bicgstabl / chebyshev engines against the oracle."""
+    import warnings
+    rng = np.random.default_rng(0)
+
+    def same(xs, hs, xo, ho):
+        assert hs.iters == ho.iters and hs.converged == ho.isconverged
+        assert np.allclose(xs, xo, rtol=1e-9, atol=1e-12, equal_nan=True)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        n = 6
+        Ir, Ic = sp.identity(n, format="csr"), sp.identity(n, format="csc")
+        b = rng.standard_normal(n)
+        for meth in ("mgs", "cgs", "dgks"):
+            xo, ho = oracle.gmres_(np.zeros(n), Ic, b, log=True, orth_meth=meth, initially_zero=True)
+            xs, hs = sim.gmres_(np.zeros(n), Ir, b, orth_meth=meth, initially_zero=True)
+            same(xs, hs, xo, ho)
+            assert hs.iters == 1 and np.allclose(xs, b)                  # x .== b  test/gmres.jl:72
+        z = np.zeros(n)
+        for fo, fs in (
+            (lambda: oracle.cg_(z.copy(), 2 * Ic, z, log=True, initially_zero=True), lambda: sim.cg_(z.copy(), 2 * Ir, z, initially_zero=True)),
+            (lambda: oracle.gmres_(z.copy(), 2 * Ic, z, log=True, initially_zero=True), lambda: sim.gmres_(z.copy(), 2 * Ir, z, initially_zero=True)),
+            (lambda: oracle.minres_(z.copy(), 2 * Ic, z, log=True, initially_zero=True), lambda: sim.minres_(z.copy(), 2 * Ir, z, initially_zero=True)),
+            (lambda: oracle.bicgstabl_(z.copy(), 2 * Ic, z, 2, log=True, initial_zero=True, r_shadow=np.ones(n)),
+             lambda: sim.bicgstabl_(z.copy(), 2 * Ir, z, 2, np.ones(n), initial_zero=True)),
+            (lambda: oracle.chebyshev_(z.copy(), 2 * Ic, z, 1.0, 3.0, log=True, initially_zero=True),
+             lambda: sim.chebyshev_(z.copy(), 2 * Ir, z, 1.0, 3.0, initially_zero=True)),
+        ):
+            (xo, ho), (xs, hs) = fo(), fs()
+            same(xs, hs, xo, ho)
+            assert hs.iters == 0 and hs.converged and not xs.any()       # test/cg.jl:50-51
+        for m in (1, 2, 3):
+            A = (sp.random(m, m, 1.0, random_state=m, format="csr") + 3 * sp.identity(m)).tocsr()
+            S = (A + A.T).tocsr()
+            bb = rng.standard_normal(m)
+            same(*sim.gmres_(np.zeros(m), A, bb, initially_zero=True, restart=20, maxiter=10),
+                 *oracle.gmres_(np.zeros(m), A.tocsc(), bb, log=True, initially_zero=True, restart=20, maxiter=10))
+            same(*sim.minres_(np.zeros(m), S, bb, initially_zero=True, maxiter=10),
+                 *oracle.minres_(np.zeros(m), S.tocsc(), bb, log=True, initially_zero=True, maxiter=10))
+            same(*sim.cg_(np.zeros(m), S, bb, initially_zero=True, maxiter=10),
+                 *oracle.cg_(np.zeros(m), S.tocsc(), bb, log=True, initially_zero=True, maxiter=10))
+        n = 8
+        A = (sp.random(n, n, 0.5, random_state=1, format="csr") + 4 * sp.identity(n)).tocsr()
+        b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+        same(*sim.gmres_(x0.copy(), A, b, maxiter=0), *oracle.gmres_(x0.copy(), A.tocsc(), b, log=True, maxiter=0))
+        same(*sim.minres_(x0.copy(), (A + A.T).tocsr(), b, maxiter=0), *oracle.minres_(x0.copy(), (A + A.T).tocsc(), b, log=True, maxiter=0))
+        same(*sim.bicgstabl_(x0.copy(), A, b, 2, np.ones(n), max_mv_products=0),
+             *oracle.bicgstabl_(x0.copy(), A.tocsc(), b, 2, log=True, max_mv_products=0, r_shadow=np.ones(n)))
