@@ -1447,3 +1447,19 @@ def test_general_engines_edge_cases(oracle, sim):
         same(*sim.minres_(x0.copy(), (A + A.T).tocsr(), b, maxiter=0), *oracle.minres_(x0.copy(), (A + A.T).tocsc(), b, log=True, maxiter=0))
         same(*sim.bicgstabl_(x0.copy(), A, b, 2, np.ones(n), max_mv_products=0),
              *oracle.bicgstabl_(x0.copy(), A.tocsc(), b, 2, log=True, max_mv_products=0, r_shadow=np.ones(n)))
+
+
+@pytest.mark.parametrize("method", ["ritz", "harmonic"])
+def test_engine_svdl_parameter_corners(oracle, sim, method):
+    """nsv / k / j at the edges (one singular value with two Lanczos vectors, j < nsv < k, k = n - 1): same iteration
+    counts as the oracle, singular values to 1e-12 of it and to the tolerance of the exact ones."""
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((40, 25))
+    q = rng.standard_normal(25)
+    q /= np.linalg.norm(q)
+    ex = np.linalg.svd(A, compute_uv=False)
+    for nsv, k, j in ((1, 2, 1), (1, 4, 2), (3, 6, 3), (3, 12, 5), (6, 24, 6)):
+        so, L, h = oracle.svdl(A, nsv=nsv, k=k, j=j, v0=q, tol=1e-8, reltol=1e-10, maxiter=200, log=True, method=method)
+        r = sim.svdl(sp.csr_matrix(A), q, nsv=nsv, k=k, j=j, tol=1e-8, reltol=1e-10, maxiter=200, method=method)
+        assert r["iters"] == h.iters and r["converged"] and h.isconverged, (nsv, k, j)
+        assert np.abs(r["sigma"] - so).max() <= 1e-12 * ex[0] and np.abs(r["sigma"] - ex[:nsv]).max() <= 1e-7 * ex[0]
