@@ -748,6 +748,7 @@ int b200_csr_destroy(b200_csr *A) {
   cudaFree(A->send_idx);
   cudaFree(A->send_buf);
   cudaFree(A->halo);
+  if (A->st_plan && A->st_plan_free) A->st_plan_free(A->st_plan);
   delete A;
   return B200_OK;
 }

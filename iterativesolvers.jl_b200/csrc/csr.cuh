@@ -43,6 +43,10 @@ struct b200_csr {
   void *halo_peer = nullptr;               // = ctx->peer_local + kPeerHeaderBytes
   std::vector<int64_t> peer_dst_offset;    // [peer] element offset of MY values inside the peer's halo segment
   unsigned int recv_mask = 0, send_mask = 0;
+  // lazily built analysis of the stationary sweeps (stationary.cu): diagonal positions and dependency levels; the
+  // operator is immutable, so the plan stays valid for its lifetime
+  mutable void *st_plan = nullptr;
+  mutable void (*st_plan_free)(void *) = nullptr;
 };
 
 namespace b200 {

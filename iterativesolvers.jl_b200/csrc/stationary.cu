@@ -1,7 +1,9 @@
 // stationary.cu -- jacobi!, gauss_seidel!, sor!, ssor! on a device CSR operator (reference src/stationary_sparse.jl): the
-// level-scheduled sweeps of stationary_core.h on the CUDA backend.  One call = host analysis of the sparsity pattern
-// (diagonal positions, dependency levels: the reference's DiagonalIndices and the order its column sweeps impose) followed
-// by exactly `maxiter` iterations, one kernel per dependency level.
+// level-scheduled sweeps of stationary_core.h on the CUDA backend.  The host analysis of the sparsity pattern (diagonal
+// positions, dependency levels: the reference's DiagonalIndices and the order its column sweeps impose) is done on the
+// first call and kept with the operator; a call then runs exactly `maxiter` iterations, one kernel per dependency level.
+#include <memory>
+
 #include "pass.cuh"
 #include "stationary_core.h"
 
@@ -23,8 +25,21 @@ struct DevInts {
   }
 };
 
+// the analysis of one operator (what the reference's DiagonalIndices and the order of its column sweeps encode), built on
+// first use and kept with the operator: level sets of both sweep directions, on the host and on the device
+struct StPlan {
+  StLevels lv;
+  DevInts dpos, rows_f, rows_b;
+  int64_t singular = 0;            // row + 1 of a zero / missing diagonal entry
+};
+void st_plan_free(void *p) { delete (StPlan *)p; }
+
 template <typename T>
-int stationary_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, int method, double omega, int64_t maxiter) {
+int stationary_plan(b200_ctx *ctx, const b200_csr *A, const StPlan **out) {
+  if (A->st_plan) {
+    *out = (const StPlan *)A->st_plan;
+    return B200_OK;
+  }
   const int64_t n = A->m_local;
   std::vector<int> rowptr((size_t)n + 1), colind((size_t)A->nnz);
   std::vector<T> vals((size_t)A->nnz);
@@ -36,22 +51,33 @@ int stationary_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, int meth
     for (int p = rowptr[(size_t)i] + 1; p < rowptr[(size_t)i + 1]; ++p)
       B200_REQUIRE(colind[(size_t)p - 1] < colind[(size_t)p], "stationary methods need rows with ascending column indices "
                    "(row %lld)", (long long)i);
-  StLevels lv;
-  const bool fwd = method != ST_JACOBI, bwd = method == ST_SSOR;
-  const int64_t sing = stationary_analyse<T, int>(n, rowptr.data(), colind.data(), vals.data(), fwd, bwd, &lv);
-  if (sing) {
-    set_error("SingularException(%lld): zero or missing diagonal entry (reference src/stationary_sparse.jl:19)", (long long)sing);
+  std::unique_ptr<StPlan> plan(new StPlan());
+  plan->singular = stationary_analyse<T, int>(n, rowptr.data(), colind.data(), vals.data(), true, true, &plan->lv);
+  if (!plan->singular) {
+    B200_TRY(plan->dpos.upload(plan->lv.dpos, ctx->stream));
+    B200_TRY(plan->rows_f.upload(plan->lv.rows_f, ctx->stream));
+    B200_TRY(plan->rows_b.upload(plan->lv.rows_b, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  A->st_plan = plan.release();
+  A->st_plan_free = st_plan_free;
+  *out = (const StPlan *)A->st_plan;
+  return B200_OK;
+}
+
+template <typename T>
+int stationary_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, int method, double omega, int64_t maxiter) {
+  const StPlan *plan = nullptr;
+  B200_TRY(stationary_plan<T>(ctx, A, &plan));
+  if (plan->singular) {
+    set_error("SingularException(%lld): zero or missing diagonal entry (reference src/stationary_sparse.jl:19)",
+              (long long)plan->singular);
     return B200_ERR_BREAKDOWN;
   }
-  DevInts dpos, rows_f, rows_b;
-  B200_TRY(dpos.upload(lv.dpos, ctx->stream));
-  B200_TRY(rows_f.upload(lv.rows_f, ctx->stream));
-  B200_TRY(rows_b.upload(lv.rows_b, ctx->stream));
   CudaBackend be{ctx};
-  const CsrView<T, int> view{n, A->rowptr, A->colind, (const T *)A->vals};
-  const int st = stationary_run<T, int>(be, view, lv, dpos.p, rows_f.p, rows_b.p, x, b, method, omega, maxiter);
-  B200_CUDA(cudaStreamSynchronize(ctx->stream));     // the index arrays are freed on return
-  return st;
+  const CsrView<T, int> view{A->m_local, A->rowptr, A->colind, (const T *)A->vals};
+  return stationary_run<T, int>(be, view, plan->lv, plan->dpos.p, plan->rows_f.p, plan->rows_b.p, x, b, method, omega,
+                                maxiter);
 }
 
 }  // namespace
