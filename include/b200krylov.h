@@ -302,7 +302,11 @@ B200_API int b200_qmr_solve(b200_ctx *ctx, const b200_csr *A, const b200_csr *At
  * without synchronising, for device vectors of n_local / m_local elements of `dtype`; y never aliases x; return 0.
  * The *_op entry points below run the same engines as their b200_csr twins -- all recurrence scalars stay in device
  * memory, the callback is simply the launch between two fused passes -- and on multi-GPU contexts the callback sees
- * the local slabs (halo exchange is the callback's business) while the engines allreduce their sums. */
+ * the local slabs (halo exchange is the callback's business) while the engines allreduce their sums.  A callback may call
+ * the operator-level functions (b200_spmv, b200_axpby, b200_jacobi_ldiv, ...) on the same context; starting another SOLVE
+ * on that context from inside a callback is refused (B200_ERR_INVALID: the context's scratch belongs to the running solve) --
+ * use a second context for nested solves.  The solver keeps a pointer to the descriptor for the duration of the call (the
+ * iterables and the generalized LOBPCG constraint copy it). */
 typedef int (*b200_apply_fn)(void *user, const void *x_dev, void *y_dev, void *cuda_stream);
 typedef struct {
   b200_apply_fn apply;
@@ -343,7 +347,11 @@ B200_API int b200_powm(b200_ctx *ctx, const b200_csr *A, const b200_linop *Aop, 
  * iterations (<0: 10, the reference's default), no stopping test.  The sweeps are level-scheduled: every row performs the
  * reference's arithmetic in the reference's order (csrc/stationary_core.h).  A zero or missing diagonal entry is the
  * SingularException of DiagonalIndices (:19) -> B200_ERR_BREAKDOWN.  Single-GPU contexts; x_dev is updated in place. */
-enum { B200_STATIONARY_JACOBI = 0, B200_STATIONARY_GAUSS_SEIDEL = 1, B200_STATIONARY_SOR = 2, B200_STATIONARY_SSOR = 3 };
+enum { B200_STATIONARY_JACOBI = 0, B200_STATIONARY_GAUSS_SEIDEL = 1, B200_STATIONARY_SOR = 2, B200_STATIONARY_SSOR = 3,
+       /* OR-ed in: the arithmetic of the dense-matrix methods of src/stationary.jl (SOR relaxation written as
+          x + w (t / a - x), :179; SSOR's backward half reading both triangles with the forward half's values, :247-258) for
+          a dense matrix stored as CSR */
+       B200_STATIONARY_DENSE_ARITHMETIC = 16 };
 B200_API int b200_stationary(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b_dev, int method, double omega,
                              int64_t maxiter);
 /* qmr! / lsqr! / lsmr! / idrs! on callback operators (A and, where needed, At = adjoint(A)) */

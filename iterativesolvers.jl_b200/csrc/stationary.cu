@@ -90,9 +90,11 @@ int b200_stationary(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *b
   B200_REQUIRE(A->ctx == ctx, "operator belongs to another context");
   B200_REQUIRE(ctx->world == 1, "the stationary methods sweep the whole matrix in order: single-GPU contexts only");
   B200_REQUIRE(is_square(A), "this solver needs a square operator");
-  B200_REQUIRE(method >= B200_STATIONARY_JACOBI && method <= B200_STATIONARY_SSOR, "unknown stationary method %d", method);
+  const int base = method & ~B200_STATIONARY_DENSE_ARITHMETIC;
+  B200_REQUIRE(base >= B200_STATIONARY_JACOBI && base <= B200_STATIONARY_SSOR, "unknown stationary method %d", method);
   static_assert(B200_STATIONARY_JACOBI == ST_JACOBI && B200_STATIONARY_GAUSS_SEIDEL == ST_GAUSS_SEIDEL &&
-                B200_STATIONARY_SOR == ST_SOR && B200_STATIONARY_SSOR == ST_SSOR, "method codes");
+                B200_STATIONARY_SOR == ST_SOR && B200_STATIONARY_SSOR == ST_SSOR &&
+                B200_STATIONARY_DENSE_ARITHMETIC == ST_DENSE_ARITHMETIC, "method codes");
   B200_CUDA(cudaSetDevice(ctx->device));
   return A->dtype == B200_F64 ? stationary_impl<double>(ctx, A, (double *)x_dev, (const double *)b_dev, method, omega, maxiter)
                               : stationary_impl<float>(ctx, A, (float *)x_dev, (const float *)b_dev, method, omega, maxiter);

@@ -26,6 +26,11 @@
 namespace b200 {
 
 enum { ST_JACOBI = 0, ST_GAUSS_SEIDEL = 1, ST_SOR = 2, ST_SSOR = 3 };
+// OR-ed into the method: the arithmetic of the reference's dense-matrix methods (src/stationary.jl) instead of the sparse
+// ones.  Jacobi :48-70 and Gauss-Seidel :108-127 are the same operations; SOR :167-186 writes the relaxation as
+// x_i + w (acc / a_ii - x_i); the backward half of SSOR :248-258 reads BOTH triangles with the values of the forward half
+// (it subtracts A[row, col] x[col] before x[col] is updated): a Jacobi-like relaxation, rows independent.
+enum { ST_DENSE_ARITHMETIC = 16 };
 
 template <typename T, typename RP>
 struct CsrView {                       // rows with ascending column indices
@@ -45,7 +50,7 @@ struct StRow {
   const T *mix;                        // SOR / SSOR: the (1 - w) term; nullptr: out_i = acc / a_ii
   T *out;
   T omega, one_minus;
-  int backward, jacobi;
+  int backward, jacobi, dense;
   B200_HD bool skip() const { return false; }
   B200_HD void load() {}
   B200_HD void elem(int64_t k, double *) const {
@@ -63,8 +68,11 @@ struct StRow {
       for (int64_t p = r1 - 1; p > d; --p) acc = acc - A.vals[p] * xnew[A.colind[p]];      // backward_sub! :137-139
     }
     const T dv = A.vals[d];
-    out[i] = mix ? omega * acc / dv + one_minus * mix[i]                 // alpha x[col] / nzval[idx] + beta y[col] :93 / :134
-                 : acc / dv;                                             // :72 ; ldiv!(x, D, next) :31
+    if (mix && dense)
+      out[i] = mix[i] + omega * (acc / dv - mix[i]);                     // x[col] += w (tmp[col] / A[col, col] - x[col])  stationary.jl:179
+    else
+      out[i] = mix ? omega * acc / dv + one_minus * mix[i]               // alpha x[col] / nzval[idx] + beta y[col] :93 / :134
+                   : acc / dv;                                           // :72 ; ldiv!(x, D, next) :31
   }
   B200_HD double *sums() const { return nullptr; }
   B200_HD void finish(const double *) const {}
@@ -128,6 +136,8 @@ template <typename T, typename RP, typename B>
 int stationary_run(B &be, const CsrView<T, RP> &A, const StLevels &lv, const int *dpos_dev, const int *rows_f_dev,
                    const int *rows_b_dev, T *x, const T *b, int method, double omega, int64_t maxiter) {
   const int64_t n = A.n;
+  const int dense = (method & ST_DENSE_ARITHMETIC) != 0;
+  method &= ~ST_DENSE_ARITHMETIC;
   if (maxiter < 0) maxiter = 10;                                         // maxiter::Int = 10
   void *ws = nullptr;
   int st = be.workspace(sizeof(T) * (size_t)(n > 0 ? n : 1), &ws);
@@ -138,7 +148,7 @@ int stationary_run(B &be, const CsrView<T, RP> &A, const StLevels &lv, const int
                    int backward) -> int {
     for (size_t l = 0; l + 1 < lptr.size(); ++l) {
       const int64_t cnt = lptr[l + 1] - lptr[l];
-      StRow<T, RP> r{A, rows + lptr[l], dpos_dev, b, xold, xnew, mix, out, w, omw, backward, 0};
+      StRow<T, RP> r{A, rows + lptr[l], dpos_dev, b, xold, xnew, mix, out, w, omw, backward, 0, dense};
       const int s2 = be.pass(r, cnt);
       if (s2) return s2;
     }
@@ -146,7 +156,7 @@ int stationary_run(B &be, const CsrView<T, RP> &A, const StLevels &lv, const int
   };
   for (int64_t it = 0; it < maxiter; ++it) {
     if (method == ST_JACOBI) {
-      StRow<T, RP> r{A, nullptr, dpos_dev, b, x, x, nullptr, next, w, omw, 0, 1};
+      StRow<T, RP> r{A, nullptr, dpos_dev, b, x, x, nullptr, next, w, omw, 0, 1, dense};
       if ((st = be.pass(r, n))) return st;                               // next = D \ (b - (A - D) x) :213-217
       if ((st = be.copy(x, next, sizeof(T) * (size_t)n))) return st;
     } else if (method == ST_GAUSS_SEIDEL) {
@@ -155,9 +165,15 @@ int stationary_run(B &be, const CsrView<T, RP> &A, const StLevels &lv, const int
     } else if (method == ST_SOR) {
       if ((st = sweep(lv.lptr_f, rows_f_dev, x, next, x, next, 0))) return st;         // :310-315
       if ((st = be.copy(x, next, sizeof(T) * (size_t)n))) return st;                   // s.x, s.next = s.next, s.x :318
-    } else {
+    } else if (!dense) {
       if ((st = sweep(lv.lptr_f, rows_f_dev, x, next, x, next, 0))) return st;         // tmp :394-400
       if ((st = sweep(lv.lptr_b, rows_b_dev, next, x, next, x, 1))) return st;         // x :402-406
+    } else {
+      // dense SSOR, stationary.jl:227-258: the forward half is the dense SOR sweep; the backward half relaxes every row
+      // against the forward half's values (both triangles, descending accumulation order) -- no dependencies
+      if ((st = sweep(lv.lptr_f, rows_f_dev, x, next, x, next, 0))) return st;
+      StRow<T, RP> r{A, nullptr, dpos_dev, b, next, next, next, x, w, omw, 1, 0, 1};
+      if ((st = be.pass(r, n))) return st;
     }
   }
   return 0;

@@ -460,32 +460,38 @@ def bicgstabl(A, b, l=2, **kw):
 # ------------------------------------------------------------------------------------------------
 def _stationary_operator(A, method=None):
     """B200CSR as is; a dense matrix (numpy 2-D: the AbstractMatrix methods of reference src/stationary.jl) or a scipy sparse
-    matrix is uploaded as CSR.  The dense Jacobi and Gauss-Seidel iterations of the reference (:48-70, :108-127) perform, row
-    by row, the same arithmetic in the same order as the sparse ones on the stored entries (a zero entry contributes
-    0 * x_j = 0); dense SOR / SSOR (:167-186, :227-258) write the relaxation as x += w (t / a_ii - x) where the sparse code
-    has w t / a_ii + (1 - w) x -- the same number up to rounding; the backward half of the dense SSOR (:248-258) reads the
-    upper triangle with the values of the forward half (it subtracts A[row, col] * x[col] before x[col] is updated), which is
-    a different iteration from the sparse one: a dense matrix is therefore refused for ssor (convert it with
-    scipy.sparse.csc_matrix to get the sparse method).  A full matrix has n dependency levels of one row each, so this is
-    a convenience, not a fast path."""
+    matrix is uploaded as CSR.  For a dense matrix the engine is asked for the arithmetic of the reference's dense methods
+    (B200_STATIONARY_DENSE_ARITHMETIC): Jacobi and Gauss-Seidel (:48-70, :108-127) are the sparse operations on the stored
+    entries (a zero entry contributes 0 * x_j = 0); dense SOR / SSOR (:167-186, :227-258) write the relaxation as
+    x += w (t / a_ii - x); the backward half of the dense SSOR reads both triangles with the forward half's values
+    (:247-258 subtract A[row, col] * x[col] before x[col] is updated) -- a different iteration from the sparse SSOR, and
+    reproduced as such.  A full matrix has n dependency levels of one row each: a convenience, not a fast path."""
     if isinstance(A, B200CSR):
         return A
     if isinstance(A, B200LinearOperator):
         raise TypeError("the stationary methods need the matrix itself (its diagonal and triangles), not a callback operator")
     import scipy.sparse as sp
-    if isinstance(A, np.ndarray) and A.ndim == 2 and method == 3:
-        raise B200Error("ssor! on a dense matrix is a different iteration in the reference (src/stationary.jl:248-258 vs "
-                        "src/stationary_sparse.jl:402-406); pass scipy.sparse.csc_matrix(A) for the sparse method")
     if sp.issparse(A) or (isinstance(A, np.ndarray) and A.ndim == 2):
         return B200CSR.from_scipy(sp.csc_matrix(A))
     raise TypeError("the stationary methods take a B200CSR, a scipy sparse matrix or a dense numpy matrix")
 
 
+def _stationary_prepare(A):
+    """the operator for a stationary method; remembers that it came from a dense matrix (the AbstractMatrix methods of
+    src/stationary.jl use slightly different arithmetic than the SparseMatrixCSC ones)."""
+    dense = isinstance(A, np.ndarray) or getattr(A, "_dense_arithmetic", False)
+    A = _stationary_operator(A)
+    if dense:
+        A._dense_arithmetic = True
+    return A
+
+
 def _stationary(method, x, A, b, omega, maxiter):
-    A = _stationary_operator(A, method)
+    A = _stationary_prepare(A)
+    dense = getattr(A, "_dense_arithmetic", False)
     st = _Staged(A, x, b)
-    status = lib().b200_stationary(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd), method, float(omega),
-                                   int(maxiter))
+    status = lib().b200_stationary(A.ctx._h, A._h, as_device_ptr(st.xd), as_device_ptr(st.bd),
+                                   method | (16 if dense else 0), float(omega), int(maxiter))
     if status == _lib.ERR_BREAKDOWN:
         raise np.linalg.LinAlgError("SingularException: zero or missing diagonal entry "
                                     "(reference src/stationary_sparse.jl:19)")
@@ -518,22 +524,22 @@ def ssor_(x, A, b, omega, *, maxiter=10):
 
 
 def jacobi(A, b, **kw):
-    A = _stationary_operator(A)
+    A = _stationary_prepare(A)
     return jacobi_(_zerox(A, b), A, b, **kw)                   # jacobi!(zerox(A, b), A, b; kwargs...)  src/stationary.jl:19
 
 
 def gauss_seidel(A, b, **kw):
-    A = _stationary_operator(A)
+    A = _stationary_prepare(A)
     return gauss_seidel_(_zerox(A, b), A, b, **kw)             # src/stationary.jl:79
 
 
 def sor(A, b, omega, **kw):
-    A = _stationary_operator(A)
+    A = _stationary_prepare(A)
     return sor_(_zerox(A, b), A, b, omega, **kw)               # src/stationary.jl:136-137
 
 
 def ssor(A, b, omega, **kw):
-    A = _stationary_operator(A, 3)
+    A = _stationary_prepare(A)
     return ssor_(_zerox(A, b), A, b, omega, **kw)              # src/stationary.jl:195-196
 
 

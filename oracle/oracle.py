@@ -652,6 +652,59 @@ def ssor_(x, A, b, omega, *, maxiter=10):
     return x
 
 
+def stationary_dense_(kind, x, A, b, omega=1.0, *, maxiter=10):
+    """jacobi! / gauss_seidel! / sor! / ssor! for an AbstractMatrix -- reference src/stationary.jl: DenseJacobiIterable :48-70,
+    DenseGaussSeidelIterable :108-127, DenseSORIterable :167-186, DenseSSORIterable :227-258, restated loop by loop.
+    kind in {"jacobi", "gauss_seidel", "sor", "ssor"}; A dense (n x n array); returns the iterate."""
+    A = np.asarray(A)
+    n = A.shape[0]
+    T = x.dtype.type
+    w = T(omega)
+    if np.any(np.diag(A) == 0):
+        raise np.linalg.LinAlgError("SingularException")                 # check_diag :6-16
+    x = x.copy()
+    tmp = np.zeros_like(x)
+    for _ in range(maxiter):
+        if kind == "jacobi":
+            nxt = b.astype(x.dtype, copy=True)                           # :52
+            for col in range(n):                                         # :55-63
+                for row in range(col):
+                    nxt[row] -= A[row, col] * x[col]
+                for row in range(col + 1, n):
+                    nxt[row] -= A[row, col] * x[col]
+            for col in range(n):                                         # :66-68
+                x[col] = nxt[col] / A[col, col]
+            continue
+        if kind == "gauss_seidel":
+            for col in range(n):                                         # :113-119
+                for row in range(col):
+                    x[row] -= A[row, col] * x[col]
+                x[col] = b[col]
+            for col in range(n):                                         # :121-126
+                x[col] /= A[col, col]
+                for row in range(col + 1, n):
+                    x[row] -= A[row, col] * x[col]
+            continue
+        for col in range(n):                                             # SOR :172-178 / SSOR :232-238
+            for row in range(col):
+                tmp[row] -= A[row, col] * x[col]
+            tmp[col] = b[col]
+        for col in range(n):                                             # :180-185 / :240-245
+            x[col] += w * (tmp[col] / A[col, col] - x[col])
+            for row in range(col + 1, n):
+                tmp[row] -= A[row, col] * x[col]
+        if kind == "ssor":
+            for col in range(n - 1, -1, -1):                             # :247-252
+                tmp[col] = b[col]
+                for row in range(col + 1, n):
+                    tmp[row] -= A[row, col] * x[col]
+            for col in range(n - 1, -1, -1):                             # :254-259
+                for row in range(col):
+                    tmp[row] -= A[row, col] * x[col]
+                x[col] += w * (tmp[col] / A[col, col] - x[col])
+    return x
+
+
 # --------------------------------------------------------------------------------------------
 # Power method / inverse iteration (reference src/simple.jl)
 # --------------------------------------------------------------------------------------------

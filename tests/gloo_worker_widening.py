@@ -1,5 +1,5 @@
 """World-size-2 gloo worker (CPU) for the multi-GPU form of the fused-pass engines (qmr!, lsqr!, lsmr!, idrs!, and the
-general cg!, gmres!, minres!, bicgstabl!, chebyshev!, powm!): every rank owns a row slab of A (and of A'), the operator application is "gather the operand, multiply the
+general cg!, gmres!, minres!, bicgstabl!, chebyshev!, powm!, lobpcg): every rank owns a row slab of A (and of A'), the operator application is "gather the operand, multiply the
 slab" (what the halo exchange + SpMV do on the GPUs) and every pass total goes through an allreduce before its scalar
 section runs -- the control flow of the CUDA backend on a multi-GPU context (csrc/pass.cuh), with torch.distributed
 in the place of NCCL.  Each rank compares its slab of the solution and the whole history with the single-process run."""
@@ -56,6 +56,9 @@ def main():
     x0p = rng.random(n)
     x0p /= np.linalg.norm(x0p)
     th_ref, xp_ref, hp_ref = sim.powm_(S, x0p.copy(), tol=1e-9, maxiter=400)
+    X0 = rng.random((n, 3))
+    Yc = rng.random((n, 2))
+    lob_ref = sim.lobpcg_general(S, False, X0, jac=S.diagonal(), C_=Yc, tol=1e-12, maxiter=25)
 
     # ---- row-partitioned runs
     slabs = {}                                                  # op_id -> the slab whose product the engine asks for
@@ -108,9 +111,17 @@ def main():
         "chebyshev": sim.chebyshev_(np.zeros(m), S_loc, b[lo_:hi_], lo, hi, Pl=DinvS[lo_:hi_], maxiter=60, initially_zero=True),
     }
     th_d, xp_d, hp_d = sim.powm_(S_loc, x0p[lo_:hi_].copy(), tol=1e-9, maxiter=400)
+    lob_d = sim.lobpcg_general(S_loc, False, X0[lo_:hi_], jac=S.diagonal()[lo_:hi_], C_=Yc[lo_:hi_], tol=1e-12, maxiter=25)
     sim.set_dist()
     sim.Csr = orig_csr
 
+    # general LOBPCG (Jacobi preconditioner, constraint): every Gram entry is a pass total that goes through the allreduce
+    assert lob_d["status"] == 0 and lob_ref["status"] == 0 and lob_d["iterations"] == lob_ref["iterations"] == 26
+    assert np.abs(lob_d["lam"] - lob_ref["lam"]).max() <= 1e-9 * np.abs(lob_ref["lam"]).max()
+    assert np.abs(lob_d["resnorm"] - lob_ref["resnorm"]).max() <= 1e-6 * np.abs(lob_ref["resnorm"]).max()
+    ov = torch.from_numpy(np.sum(lob_d["X"] * lob_ref["X"][lo_:hi_], axis=0))
+    dist.all_reduce(ov)                                        # <x_dist, x_ref> over the whole vectors: +-1 for the same Ritz vectors
+    assert np.abs(np.abs(ov.numpy()) - 1).max() <= 1e-6
     assert hp_d.iters == hp_ref.iters and hp_d.converged and abs(th_d - th_ref) <= 1e-12 * abs(th_ref)
     assert np.linalg.norm(xp_d - xp_ref[lo_:hi_]) <= 1e-10
     for name in ("qmr", "idrs", "cg", "gmres", "minres", "bicgstabl", "chebyshev"):

@@ -338,7 +338,8 @@ EXPORT int64_t hostsim_stationary(int is_f64, const hostsim_csr *A, void *x, con
   auto body = [&](auto tag) -> int64_t {
     typedef decltype(tag) T;
     b200::StLevels lv;
-    const bool fwd = method != b200::ST_JACOBI, bwd = method == b200::ST_SSOR;
+    const int base = method & ~b200::ST_DENSE_ARITHMETIC;
+    const bool fwd = base != b200::ST_JACOBI, bwd = base == b200::ST_SSOR && !(method & b200::ST_DENSE_ARITHMETIC);
     const int64_t sing = b200::stationary_analyse<T, int64_t>(a.m, a.rowptr, a.colind, (const T *)a.vals, fwd, bwd, &lv);
     if (sing) return sing;
     *levels_f = fwd ? (int)lv.lptr_f.size() - 1 : 0;

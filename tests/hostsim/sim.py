@@ -239,7 +239,7 @@ def powm_(A, x, *, tol=-1.0, maxiter=-1, check_every=0, order=0, split=0):
     return theta.value, x, _outcome(out, hist)
 
 
-def stationary_(method, x, A, b, omega=1.0, *, maxiter=10, order=0):
+def stationary_(method, x, A, b, omega=1.0, *, maxiter=10, order=0, dense=False):
     """jacobi! / gauss_seidel! / sor! / ssor! (csrc/stationary_core.h: one pass per dependency level) on the serial backend.
     Returns (x, info) with info.levels_f / levels_b / passes; raises LinAlgError for a zero or missing diagonal entry."""
     dt = x.dtype
@@ -249,7 +249,8 @@ def stationary_(method, x, A, b, omega=1.0, *, maxiter=10, order=0):
     fn = lib().hostsim_stationary
     fn.restype = C.c_int64
     r = fn(C.c_int(dt == np.float64), C.byref(Ac.c), C.c_void_p(x.ctypes.data), C.c_void_p(b.ctypes.data),
-           C.c_int({"jacobi": 0, "gauss_seidel": 1, "sor": 2, "ssor": 3}[method]), C.c_double(omega), C.c_int64(maxiter),
+           C.c_int({"jacobi": 0, "gauss_seidel": 1, "sor": 2, "ssor": 3}[method] | (16 if dense else 0)), C.c_double(omega),
+           C.c_int64(maxiter),
            C.c_int(order), C.byref(lf), C.byref(lb), C.byref(passes))
     if r > 0:
         raise np.linalg.LinAlgError(f"SingularException({r})")

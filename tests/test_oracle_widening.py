@@ -1233,70 +1233,43 @@ def test_python_stationary_wrappers_with_a_fake_library(monkeypatch):
     assert isb.sor(csr, b, 1.2, maxiter=5).shape == (n,) and isb.gauss_seidel(csr, b).shape == (n,)
     with pytest.raises(np.linalg.LinAlgError):
         isb.jacobi_(x, csr, b, maxiter=99)
+    # a dense numpy matrix is uploaded as CSR and the dense arithmetic of src/stationary.jl is asked for (method | 16)
+    monkeypatch.setattr(S.B200CSR, "from_scipy", classmethod(lambda cls, M, **kw: csr))
+    csr._dense_arithmetic = False
+    isb.ssor(np.eye(n) * 3.0, b, 1.1, maxiter=2)
+    assert calls[-1] == (3 | 16, 1.1, 2)
+    import scipy.sparse as sps
+    csr._dense_arithmetic = False
+    isb.sor_(x, sps.identity(n, format="csc") * 3.0, b, 1.3)
+    assert calls[-1] == (2, 1.3, 10)                               # a scipy sparse matrix: the sparse methods
     with pytest.raises(TypeError):
         isb.jacobi(isb.B200LinearOperator((n, n), np.float64, lambda y, v: None, ctx=csr.ctx), b)   # needs the matrix itself
 
 
-def test_dense_stationary_iterations_equal_the_sparse_ones(oracle):
-    """the AbstractMatrix methods of reference src/stationary.jl (:48-70 Jacobi, :108-127 Gauss-Seidel, :167-186 SOR,
-    :227-258 SSOR), restated literally, against the sparse restatement the engine is verified with: Jacobi and
-    Gauss-Seidel bit for bit, SOR to rounding (the dense code writes the relaxation as x += w (t / a - x)); dense SSOR is a
-    different iteration."""
+def test_dense_stationary_methods(oracle, sim):
+    """the AbstractMatrix methods of reference src/stationary.jl (DenseJacobiIterable :48-70, DenseGaussSeidelIterable
+    :108-127, DenseSORIterable :167-186, DenseSSORIterable :227-258), restated loop by loop in the oracle: the engine's
+    dense-arithmetic mode reproduces all four bit for bit; dense Jacobi / Gauss-Seidel ARE the sparse iterations, dense SOR
+    equals the sparse one to rounding, dense SSOR is a different iteration (its backward half reads both triangles with
+    the forward half's values); the reference's residual test (test/stationary.jl:33-54, sparse = false) holds."""
     rng = np.random.default_rng(7)
     n, w = 12, 1.2
-    A = rng.random((n, n)) + 2 * n * np.eye(n)
-    b, x0 = rng.random(n), rng.random(n)
-
-    def dense(kind, x, maxiter):
-        x = x.copy()
-        tmp = np.zeros(n)
-        for _ in range(maxiter):
-            if kind == "jacobi":
-                nxt = b.copy()
-                for col in range(n):
-                    for row in range(n):
-                        if row != col:
-                            nxt[row] -= A[row, col] * x[col]
-                x = nxt / np.diag(A)
-                continue
-            if kind == "gauss_seidel":
-                for col in range(n):
-                    for row in range(col):
-                        x[row] -= A[row, col] * x[col]
-                    x[col] = b[col]
-                for col in range(n):
-                    x[col] /= A[col, col]
-                    for row in range(col + 1, n):
-                        x[row] -= A[row, col] * x[col]
-                continue
-            for col in range(n):                                       # SOR, and the forward half of SSOR
-                for row in range(col):
-                    tmp[row] -= A[row, col] * x[col]
-                tmp[col] = b[col]
-            for col in range(n):
-                x[col] += w * (tmp[col] / A[col, col] - x[col])
-                for row in range(col + 1, n):
-                    tmp[row] -= A[row, col] * x[col]
-            if kind == "ssor":
-                for col in range(n - 1, -1, -1):
-                    tmp[col] = b[col]
-                    for row in range(col + 1, n):
-                        tmp[row] -= A[row, col] * x[col]
-                for col in range(n - 1, -1, -1):
-                    for row in range(col):
-                        tmp[row] -= A[row, col] * x[col]
-                    x[col] += w * (tmp[col] / A[col, col] - x[col])
-        return x
-
-    assert np.array_equal(dense("jacobi", x0, 5), oracle.jacobi_(x0.copy(), A, b, maxiter=5))
-    assert np.array_equal(dense("gauss_seidel", x0, 5), oracle.gauss_seidel_(x0.copy(), A, b, maxiter=5))
-    assert np.abs(dense("sor", x0, 5) - oracle.sor_(x0.copy(), A, b, w, maxiter=5)).max() <= 1e-15
-    # the dense SSOR is NOT the sparse one: its backward half reads the upper triangle with the forward half's values
-    # (src/stationary.jl:253-257 subtracts A[row, col] * x[col] before x[col] is updated) -- the package refuses dense ssor
-    assert np.abs(dense("ssor", x0, 5) - oracle.ssor_(x0.copy(), A, b, w, maxiter=5)).max() > 1e-8
-    import iterativesolvers_jl_b200 as isb
-    with pytest.raises(isb.B200Error, match="different iteration"):
-        isb.ssor(A, b, w)
+    for dtype in (np.float64, np.float32):
+        A = (rng.random((n, n)) + 2 * n * np.eye(n)).astype(dtype)
+        b, x0 = rng.random(n).astype(dtype), rng.random(n).astype(dtype)
+        for kind in ("jacobi", "gauss_seidel", "sor", "ssor"):
+            for mi in (1, 2, 5, 2 * n):
+                xo = oracle.stationary_dense_(kind, x0, A, b, w, maxiter=mi)
+                xs, _ = sim.stationary_(kind, x0.copy(), sp.csr_matrix(A), b, w, maxiter=mi, dense=True)
+                assert np.array_equal(xo, xs), (kind, mi)
+            assert np.linalg.norm(b - A @ xs) / np.linalg.norm(b) <= np.sqrt(np.finfo(dtype).eps)
+    A, b, x0 = A.astype(np.float64), b.astype(np.float64), x0.astype(np.float64)
+    assert np.array_equal(oracle.stationary_dense_("jacobi", x0, A, b, maxiter=5), oracle.jacobi_(x0.copy(), A, b, maxiter=5))
+    assert np.array_equal(oracle.stationary_dense_("gauss_seidel", x0, A, b, maxiter=5), oracle.gauss_seidel_(x0.copy(), A, b, maxiter=5))
+    assert np.abs(oracle.stationary_dense_("sor", x0, A, b, w, maxiter=5) - oracle.sor_(x0.copy(), A, b, w, maxiter=5)).max() <= 1e-15
+    assert np.abs(oracle.stationary_dense_("ssor", x0, A, b, w, maxiter=5) - oracle.ssor_(x0.copy(), A, b, w, maxiter=5)).max() > 1e-8
+    with pytest.raises(np.linalg.LinAlgError):
+        oracle.stationary_dense_("jacobi", np.zeros(2), np.array([[0.0, 1.0], [1.0, 0.0]]), np.ones(2))   # test/stationary.jl:75-90
 
 
 def test_level_scheduled_sweeps_on_random_patterns(oracle, sim):

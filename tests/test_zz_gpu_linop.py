@@ -272,6 +272,17 @@ def test_stationary_methods(isb, oracle, dtype):
     b = np.ones(O.n)
     x = isb.ssor(A, b, 1.2, maxiter=8)
     assert relerr(x, oracle.ssor_(np.zeros(O.n), O, b, 1.2, maxiter=8)) <= 1e-13
+    # a dense matrix selects the arithmetic of the reference's dense methods (src/stationary.jl), dense SSOR included
+    rng = np.random.default_rng(7)
+    n = 12
+    D = (rng.random((n, n)) + 2 * n * np.eye(n)).astype(dtype)
+    bd, x0 = rng.random(n).astype(dtype), rng.random(n).astype(dtype)
+    eps = float(np.finfo(dtype).eps)
+    for kind in ("jacobi", "gauss_seidel", "sor", "ssor"):
+        fn = getattr(isb, kind + "_")
+        xs = fn(x0.copy(), D, bd, 1.2, maxiter=5) if kind in ("sor", "ssor") else fn(x0.copy(), D, bd, maxiter=5)
+        xo = oracle.stationary_dense_(kind, x0, D, bd, 1.2, maxiter=5)
+        assert np.abs(xs - xo).max() <= 40 * eps * np.abs(xo).max(), kind
 
 
 def test_cg_solve_forwards_a_callback_preconditioner(isb):
