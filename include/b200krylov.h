@@ -487,6 +487,10 @@ B200_API int b200_minres_iter_create(b200_ctx *ctx, const b200_csr *A, const b20
                                      const void *b_dev, const b200_minres_opts *opts, b200_iter **out);
 B200_API int b200_bicgstabl_iter_create(b200_ctx *ctx, const b200_csr *A, const b200_linop *Aop, void *x_dev,
                                         const void *b_dev, const b200_bicgstabl_opts *opts, b200_iter **out);
+/* cg_iterator!(x, A, b, Pl; ...) (src/cg.jl:120-155) with a callback operator and / or a callback preconditioner; the
+ * b200_csr + Identity / Jacobi form with caller-owned CGStateVariables is b200_cg_iter_create. */
+B200_API int b200_cg_iter_create_op(b200_ctx *ctx, const b200_csr *A, const b200_linop *Aop, void *x_dev,
+                                    const void *b_dev, const b200_cg_opts *opts, b200_iter **out);
 B200_API int b200_iter_next(b200_iter *it, int64_t k, b200_result *res, double *resnorm_host, int64_t resnorm_cap);
 B200_API int b200_iter_destroy(b200_iter *it);
 

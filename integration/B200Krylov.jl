@@ -644,6 +644,8 @@ function gmres_iterable!(x::B200Vector{T}, A::Union{B200CSR{T},B200LinearOperato
                 A.ctx.h, csr, a, x.p, b.p, o, r))
     finalizer(iter_finalize, B200Iterable{T}(r[], A.ctx, Result(), x, keep))
 end
+# cg_iterator!(x, A::B200LinearOperator, b, Pl; ...): b200_cg_iter_create_op with Ref{CgOpts} (the CSR + Identity / Jacobi form
+# with CGStateVariables is b200_cg_iter_create).
 # minres_iterable!(x, A, b; ...) and bicgstabl_iterator!(x, A, b, l; ...): same pattern with b200_minres_iter_create
 # (Ref{MinresOpts}) / b200_bicgstabl_iter_create (Ref{BicgstablOpts}).
 function step!(it::B200Iterable, k::Integer = 1)

@@ -190,6 +190,7 @@ SIGNATURES = {
     "b200_gmres_iter_create": (_INT, [_P, _P, C.POINTER(LinOp), _P, _P, C.POINTER(GmresOpts), C.POINTER(_P)]),
     "b200_minres_iter_create": (_INT, [_P, _P, C.POINTER(LinOp), _P, _P, C.POINTER(MinresOpts), C.POINTER(_P)]),
     "b200_bicgstabl_iter_create": (_INT, [_P, _P, C.POINTER(LinOp), _P, _P, C.POINTER(BicgstablOpts), C.POINTER(_P)]),
+    "b200_cg_iter_create_op": (_INT, [_P, _P, C.POINTER(LinOp), _P, _P, C.POINTER(CgOpts), C.POINTER(_P)]),
     "b200_iter_next": (_INT, [_P, _I64, C.POINTER(Result), _P, _I64]),
     "b200_iter_destroy": (_INT, [_P]),
     "b200_minres_solve": (_INT, [_P, _P, _P, _P, C.POINTER(MinresOpts), C.POINTER(Result), _P, _I64]),

@@ -157,57 +157,83 @@ struct CgpUpdateXR {
 struct CgpOutcome {
   int64_t iters, mvps, n_hist;
   double residual, tol;
-  int converged, breakdown;
+  int converged, breakdown, done, pad;
 };
+
+// ---- the driver in resumable pieces (cg_iterator! :120-155 = setup, iterate :43-100 = advance); cgp_run is the one-shot
+// form, the iterator of the C ABI keeps the scratch between calls.
+template <typename T>
+struct CgpLayout {
+  T *u, *r, *c;
+  CgpScal *s;
+  double *hist;
+  int64_t hist_cap;
+};
+inline size_t cgp_vec_bytes(size_t elem, int64_t n) { return ((elem * (size_t)(n > 0 ? n : 1)) + 255) / 256 * 256; }
+template <typename T>
+size_t cgp_ws_bytes(int64_t n, int64_t hist_cap) {
+  return 3 * cgp_vec_bytes(sizeof(T), n) + 512 + ((sizeof(double) * (size_t)(hist_cap > 0 ? hist_cap : 1)) + 255) / 256 * 256;
+}
+template <typename T>
+CgpLayout<T> cgp_layout(void *ws, int64_t n, int64_t hist_cap) {
+  static_assert(sizeof(CgpScal) <= 512, "CgpScal outgrew its slot");
+  const size_t vb = cgp_vec_bytes(sizeof(T), n);
+  CgpLayout<T> L;
+  char *p = (char *)ws;
+  L.u = (T *)p; p += vb;
+  L.r = (T *)p; p += vb;
+  L.c = (T *)p; p += vb;
+  L.s = (CgpScal *)p; p += 512;
+  L.hist = hist_cap > 0 ? (double *)p : nullptr;
+  L.hist_cap = hist_cap > 0 ? hist_cap : 0;
+  return L;
+}
 
 // A: the operator; Pl: preconditioner callback (y = Pl \ x) or nullptr; diag: Jacobi diagonal or nullptr (Identity
 // when both are null).  x, b: n values.
 template <typename T, typename B>
-int cgp_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const T *diag, int64_t n, int64_t n_global, T *x,
-            const T *b, double abstol, double reltol, int64_t maxiter, int initially_zero, int check_every,
-            int64_t hist_cap, double *hist_host, CgpOutcome *out) {
+int cgp_setup(B &be, const typename B::Op *A, bool precond, const CgpLayout<T> &L, int64_t n, int64_t n_global, T *x,
+              const T *b, double abstol, double reltol, int64_t maxiter, int initially_zero, int64_t *mvps0) {
   if (reltol < 0) reltol = sqrt(eps_of<T>());                               // :211
   if (maxiter < 0) maxiter = n_global;                                      // :212
-  if (!hist_host) hist_cap = 0;
-  if (hist_cap > maxiter + 1) hist_cap = maxiter + 1;
-  const size_t vb = ((sizeof(T) * (size_t)(n > 0 ? n : 1)) + 255) / 256 * 256;
-  const size_t hb = ((sizeof(double) * (size_t)(hist_cap > 0 ? hist_cap : 1)) + 255) / 256 * 256;
-  void *ws = nullptr;
-  int st = be.workspace(3 * vb + 512 + hb, &ws);
-  if (st) return st;
-  char *p = (char *)ws;
-  T *u = (T *)p; p += vb;
-  T *r = (T *)p; p += vb;
-  T *c = (T *)p; p += vb;
-  CgpScal *s = (CgpScal *)p; p += 512;
-  double *hist = hist_cap ? (double *)p : nullptr;
-  static_assert(sizeof(CgpScal) <= 512, "CgpScal outgrew its slot");
-  const bool precond = Pl != nullptr || diag != nullptr;
-
   CgpScal h;
   memset(&h, 0, sizeof(h));
   h.abstol = abstol;
   h.reltol = reltol;
   h.maxiter = maxiter;
-  h.hist = hist;
-  h.hist_cap = hist_cap;
+  h.hist = L.hist;
+  h.hist_cap = L.hist_cap;
   h.precond = precond;
-  if ((st = be.to_device(s, &h, sizeof(h)))) return st;
-
-  int64_t mvps = 0;
+  int st;
+  if ((st = be.to_device(L.s, &h, sizeof(h)))) return st;
+  *mvps0 = 0;
   if (!initially_zero) {                                                    // :133-139
-    if ((st = be.apply(A, x, c))) return st;
-    mvps = 1;
+    if ((st = be.apply(A, x, L.c))) return st;
+    *mvps0 = 1;
   }
-  if ((st = be.pass(CgpInit<T>{b, initially_zero ? nullptr : c, r, u, s}, n))) return st;
+  return be.pass(CgpInit<T>{b, initially_zero ? nullptr : L.c, L.r, L.u, L.s}, n);
+}
 
+// up to k more iterations (k < 0: until done)
+template <typename T, typename B>
+int cgp_advance(B &be, const typename B::Op *A, const typename B::Op *Pl, const T *diag, const CgpLayout<T> &L, int64_t n,
+                T *x, int64_t k, int check_every) {
+  int st;
+  T *u = L.u, *r = L.r, *c = L.c;
+  CgpScal *s = L.s;
+  CgpScal h;
+  if ((st = be.to_host(&h, s, sizeof(h)))) return st;
+  if (h.done) return 0;
+  const bool precond = Pl != nullptr || diag != nullptr;
+  const int64_t left = h.maxiter - h.iteration;
+  const int64_t todo = (k < 0 || k > left) ? left : k;
   if (check_every <= 0) check_every = 16;
   int64_t enqueued = 0;
   for (;;) {
     int done = 0;
     if ((st = be.read_flag(&s->done, &done))) return st;
-    if (done || enqueued >= maxiter) break;
-    const int64_t batch = check_every < maxiter - enqueued ? check_every : maxiter - enqueued;
+    if (done || enqueued >= todo) break;
+    const int64_t batch = check_every < todo - enqueued ? check_every : todo - enqueued;
     for (int64_t q = 0; q < batch; ++q) {
       if (precond) {
         if (Pl && (st = be.apply(Pl, r, c))) return st;                                        // L  :79
@@ -222,16 +248,48 @@ int cgp_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const T *d
     }
     enqueued += batch;
   }
-  if ((st = be.to_host(&h, s, sizeof(h)))) return st;
+  return 0;
+}
+
+template <typename T, typename B>
+int cgp_collect(B &be, const CgpLayout<T> &L, int64_t mvps0, double *hist_host, CgpOutcome *out) {
+  int st;
+  CgpScal h;
+  if ((st = be.to_host(&h, L.s, sizeof(h)))) return st;
   out->iters = h.iteration;
-  out->mvps = mvps + h.iteration;
+  out->mvps = mvps0 + h.iteration;
   out->residual = h.residual;
   out->tol = h.tol;
   out->converged = h.residual <= h.tol;                                     // converged() :32
   out->breakdown = h.breakdown;
-  out->n_hist = h.iteration < hist_cap ? h.iteration : hist_cap;
-  if (out->n_hist > 0 && (st = be.to_host(hist_host, hist, sizeof(double) * (size_t)out->n_hist))) return st;
+  out->done = h.done;
+  out->n_hist = h.n_hist < L.hist_cap ? h.n_hist : L.hist_cap;
+  if (hist_host && out->n_hist > 0 && (st = be.to_host(hist_host, L.hist, sizeof(double) * (size_t)out->n_hist))) return st;
   return 0;
+}
+template <typename B>
+int cgp_reset_window(B &be, CgpScal *s) {
+  const long long zero = 0;
+  return be.to_device(&s->n_hist, &zero, sizeof(zero));
+}
+
+template <typename T, typename B>
+int cgp_run(B &be, const typename B::Op *A, const typename B::Op *Pl, const T *diag, int64_t n, int64_t n_global, T *x,
+            const T *b, double abstol, double reltol, int64_t maxiter, int initially_zero, int check_every,
+            int64_t hist_cap, double *hist_host, CgpOutcome *out) {
+  if (maxiter < 0) maxiter = n_global;
+  if (!hist_host) hist_cap = 0;
+  if (hist_cap > maxiter + 1) hist_cap = maxiter + 1;
+  void *ws = nullptr;
+  int st = be.workspace(cgp_ws_bytes<T>(n, hist_cap), &ws);
+  if (st) return st;
+  const CgpLayout<T> L = cgp_layout<T>(ws, n, hist_cap);
+  int64_t mvps0 = 0;
+  if ((st = cgp_setup<T, B>(be, A, Pl != nullptr || diag != nullptr, L, n, n_global, x, b, abstol, reltol, maxiter,
+                            initially_zero, &mvps0)))
+    return st;
+  if ((st = cgp_advance<T, B>(be, A, Pl, diag, L, n, x, -1, check_every))) return st;
+  return cgp_collect<T, B>(be, L, mvps0, hist_host, out);
 }
 
 }  // namespace b200

@@ -5,6 +5,7 @@
 // run between two b200_iter_next calls.  x and b stay the caller's device vectors, as in the reference.
 #include "linop.cuh"
 #include "bicgstabl_core.h"
+#include "cg_core.h"
 #include "gmres_core.h"
 #include "minres_core.h"
 
@@ -12,7 +13,7 @@ using namespace b200;
 
 namespace {
 constexpr int64_t kIterWindow = 4096;   // residuals recorded per b200_iter_next call (as b200_cg_iter_next)
-enum { IT_GMRES = 1, IT_MINRES = 2, IT_BICGSTABL = 3 };
+enum { IT_GMRES = 1, IT_MINRES = 2, IT_BICGSTABL = 3, IT_CG = 4 };
 }  // namespace
 
 struct b200_iter {
@@ -125,6 +126,20 @@ int next_impl(b200_iter *it, int64_t k, b200_result *res, double *resnorm_host, 
     MinresOutcome o;
     memset(&o, 0, sizeof(o));
     if ((st = minres_collect<T, CudaBackend>(be, L, it->mv, window.data(), &o))) return st;
+    const int64_t nh = std::min(o.n_hist, want);
+    for (int64_t i = 0; i < nh; ++i) resnorm_host[i] = window[(size_t)i];
+    fill_result(res, o.iters, o.mvps, o.converged, o.done, o.tol, o.residual, nh);
+    return o.breakdown ? B200_ERR_BREAKDOWN : B200_OK;
+  }
+  if (it->kind == IT_CG) {
+    const CgpLayout<T> L = cgp_layout<T>(it->ws, it->n, kIterWindow);
+    if ((st = cgp_reset_window(be, L.s))) return st;
+    if (k > 0 && (st = cgp_advance<T, CudaBackend>(be, &it->A, it->Pl.fn ? &it->Pl : nullptr, (const T *)it->pl_diag, L, it->n,
+                                                  (T *)it->x, k, 0)))
+      return st;
+    CgpOutcome o;
+    memset(&o, 0, sizeof(o));
+    if ((st = cgp_collect<T, CudaBackend>(be, L, it->mv, window.data(), &o))) return st;
     const int64_t nh = std::min(o.n_hist, want);
     for (int64_t i = 0; i < nh; ++i) resnorm_host[i] = window[(size_t)i];
     fill_result(res, o.iters, o.mvps, o.converged, o.done, o.tol, o.residual, nh);
@@ -248,6 +263,39 @@ int b200_bicgstabl_iter_create(b200_ctx *ctx, const b200_csr *A, const b200_lino
                                              bicgstabl_layout<float>(it->ws, it->n, it->l, kIterWindow), it->n, it->n_global,
                                              (float *)x_dev, (const float *)b_dev, it->l, opts->abstol, opts->reltol,
                                              opts->max_mv_products, opts->initial_zero);
+  if (st != B200_OK) {
+    b200_iter_destroy(it.release());
+    return st;
+  }
+  *out = it.release();
+  return B200_OK;
+}
+
+// cg_iterator!(x, A, b, Pl; ...) for a callback operator and / or a callback preconditioner (reference src/cg.jl:120-155);
+// the CSR + Identity / Jacobi form is b200_cg_iter_create (tuned engine, caller-owned state vectors).
+int b200_cg_iter_create_op(b200_ctx *ctx, const b200_csr *A, const b200_linop *Aop, void *x_dev, const void *b_dev,
+                           const b200_cg_opts *opts, b200_iter **out) {
+  B200_REQUIRE(ctx && x_dev && b_dev && opts && out, "NULL argument");
+  B200_REQUIRE(!opts->fixed_iterations && !opts->variant, "fixed_iterations / variant are not available on this path");
+  std::unique_ptr<b200_iter> it(new b200_iter());
+  it->kind = IT_CG;
+  B200_TRY(set_operator(it.get(), ctx, A, Aop));
+  B200_TRY(set_precond(it.get(), opts->Pl, "Pl", &it->pl_fn, &it->Pl, &it->pl_diag));
+  it->x = x_dev;
+  it->b = b_dev;
+  const bool f64 = it->dtype == B200_F64;
+  B200_TRY(alloc_ws(it.get(), f64 ? cgp_ws_bytes<double>(it->n, kIterWindow) : cgp_ws_bytes<float>(it->n, kIterWindow)));
+  CudaBackend be{ctx};
+  const bool precond = it->Pl.fn != nullptr || it->pl_diag != nullptr;
+  int st;
+  if (f64)
+    st = cgp_setup<double, CudaBackend>(be, &it->A, precond, cgp_layout<double>(it->ws, it->n, kIterWindow), it->n,
+                                        it->n_global, (double *)x_dev, (const double *)b_dev, opts->abstol, opts->reltol,
+                                        opts->maxiter, opts->initially_zero, &it->mv);
+  else
+    st = cgp_setup<float, CudaBackend>(be, &it->A, precond, cgp_layout<float>(it->ws, it->n, kIterWindow), it->n,
+                                       it->n_global, (float *)x_dev, (const float *)b_dev, opts->abstol, opts->reltol,
+                                       opts->maxiter, opts->initially_zero, &it->mv);
   if (st != B200_OK) {
     b200_iter_destroy(it.release());
     return st;

@@ -258,13 +258,19 @@ class CGIterable:
 
 def cg_iterator_(x, A, b, *, abstol=0.0, reltol=None, maxiter=None, statevars=None, Pl=None, initially_zero=False):
     """cg_iterator!(x, A, b, Pl = Identity(); abstol, reltol, maxiter, statevars, initially_zero)
-    -- reference src/cg.jl:120-155."""
-    _check_operator(A)
+    -- reference src/cg.jl:120-155.  A B200CSR with Identity / JacobiPrec gives the tuned iterator (optionally on the
+    caller's CGStateVariables); a B200LinearOperator or a FunctionPrec gives the general one (a KrylovIterable)."""
+    _check_operator(A, linop_ok=True)
     if reltol is None:
         reltol = math.sqrt(_eps(A.dtype))
     if maxiter is None:
         maxiter = A.size(2)
     opts = _lib.CgOpts(abstol, reltol, int(maxiter), int(bool(initially_zero)), 0, precond_to_c(Pl, A), 0, 0)
+    if _is_linop(A) or isinstance(Pl, FunctionPrec):
+        if statevars is not None:
+            raise B200Error("statevars are taken by the tuned iterator only (B200CSR with Identity / JacobiPrec)")
+        keep = [A] + ([Pl] if Pl is not None else []) + ([Pl.op] if isinstance(Pl, FunctionPrec) else [])
+        return KrylovIterable(lib().b200_cg_iter_create_op, x, A, b, opts, keep)
     return CGIterable(x, A, b, opts, statevars)
 
 

@@ -398,7 +398,7 @@ EXPORT int hostsim_bicgstabl(int is_f64, const hostsim_csr *A, const hostsim_csr
 }
 
 // The resumable forms (what csrc/iterables.cu does with the CUDA backend): setup once, then advance `chunk` iterations
-// per call with a fresh history window each time, until done.  kind: 1 gmres, 2 minres, 3 bicgstabl.  The histories of
+// per call with a fresh history window each time, until done.  kind: 1 gmres, 2 minres, 3 bicgstabl, 4 cg.  The histories of
 // the calls are concatenated into hist; calls = number of advance calls made.
 template <typename T>
 static int chunked_impl(int kind, HostBackend &be, const HostCsr *a, const HostCsr *pl, const HostCsr *pr, const T *pl_diag,
@@ -441,6 +441,25 @@ static int chunked_impl(int kind, HostBackend &be, const HostCsr *a, const HostC
       if ((st = b200::minres_reset_window(be, L.s))) return st;
       if ((st = b200::minres_advance<T, HostBackend>(be, a, L, n, x, chunk, 3))) return st;
       if ((st = b200::minres_collect<T, HostBackend>(be, L, mv0, win.data(), &o))) return st;
+      *calls += 1;
+      for (int64_t i = 0; i < o.n_hist && nh < hist_cap; ++i) hist[nh++] = win[(size_t)i];
+      out->iters = o.iters; out->mvps = o.mvps; out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged;
+      out->breakdown = o.breakdown;
+      if (o.done || o.breakdown) break;
+    }
+  } else if (kind == 4) {
+    if ((st = be.workspace(b200::cgp_ws_bytes<T>(n, W), &ws))) return st;
+    const b200::CgpLayout<T> L = b200::cgp_layout<T>(ws, n, W);
+    int64_t mv0 = 0;
+    if ((st = b200::cgp_setup<T, HostBackend>(be, a, pl != nullptr || pl_diag != nullptr, L, n, n_global, x, b, abstol, reltol,
+                                              maxiter, zero, &mv0)))
+      return st;
+    for (;;) {
+      b200::CgpOutcome o;
+      memset(&o, 0, sizeof(o));
+      if ((st = b200::cgp_reset_window(be, L.s))) return st;
+      if ((st = b200::cgp_advance<T, HostBackend>(be, a, pl, pl_diag, L, n, x, chunk, 3))) return st;
+      if ((st = b200::cgp_collect<T, HostBackend>(be, L, mv0, win.data(), &o))) return st;
       *calls += 1;
       for (int64_t i = 0; i < o.n_hist && nh < hist_cap; ++i) hist[nh++] = win[(size_t)i];
       out->iters = o.iters; out->mvps = o.mvps; out->resnorm = o.residual; out->tol = o.tol; out->converged = o.converged;

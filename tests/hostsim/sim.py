@@ -315,7 +315,7 @@ def chunked(kind, x, A, b, chunk, *, Pl=None, Pr=None, pl_diag=None, pr_diag=Non
     hist = np.zeros(cap)
     out, calls = _Out(), C.c_int()
     vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None else None
-    st = lib().hostsim_chunked(C.c_int({"gmres": 1, "minres": 2, "bicgstabl": 3}[kind]), C.c_int(dt == np.float64),
+    st = lib().hostsim_chunked(C.c_int({"gmres": 1, "minres": 2, "bicgstabl": 3, "cg": 4}[kind]), C.c_int(dt == np.float64),
                                C.byref(Ac.c), C.byref(Plc.c) if Plc else None, C.byref(Prc.c) if Prc else None, vp(dl),
                                vp(dr), vp(x), vp(b), vp(sh), C.c_int(l), C.c_int(restart),
                                C.c_int({"mgs": 0, "cgs": 1, "dgks": 2}[orth_meth]), C.c_int(skew_hermitian),

@@ -975,7 +975,7 @@ def test_engine_bicgstabl_general_matches_oracle(oracle, sim, dtype, tol):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_resumable_forms_reproduce_the_one_shot_solves(sim, dtype):
-    """gmres_iterable! / minres_iterable! / bicgstabl_iterator! (setup once, k iterations per call, history window reset at
+    """gmres_iterable! / minres_iterable! / bicgstabl_iterator! / the general cg_iterator! (setup once, k iterations per call, history window reset at
     every call -- the pieces csrc/iterables.cu drives with the CUDA backend) give bit-for-bit the x, the history and the
     counters of the one-shot engines, whatever the chunk size (cycle boundaries, DGKS rounds, the done iteration)."""
     rng = np.random.default_rng(11)
@@ -985,6 +985,8 @@ def test_resumable_forms_reproduce_the_one_shot_solves(sim, dtype):
     S = (0.1 * (R + R.T) + sp.diags(np.where(np.arange(n) % 2 == 0, 1.0, -1.0) * np.linspace(1, 3, n))).tocsr().astype(dtype)
     d = A.diagonal()
     Dinv = sp.diags(1.0 / d.astype(np.float64)).tocsr()
+    Sp = (A + A.T + 8 * sp.eye(n)).tocsr().astype(dtype)          # symmetric positive definite, for cg
+    DinvS = sp.diags(1.0 / Sp.diagonal().astype(np.float64)).tocsr()
     b = rng.standard_normal(n).astype(dtype)
     x0 = rng.standard_normal(n).astype(dtype)
     sh = rng.random(n).astype(dtype)
@@ -992,12 +994,14 @@ def test_resumable_forms_reproduce_the_one_shot_solves(sim, dtype):
         "gmres": sim.gmres_(x0.copy(), A, b, pl_diag=d, Pr=Dinv, restart=6, maxiter=50, orth_meth="dgks"),
         "minres": sim.minres_(x0.copy(), S, b, maxiter=50),
         "bicgstabl": sim.bicgstabl_(x0.copy(), A, b, 2, sh, Pl=Dinv, max_mv_products=60, reltol=1e-13),
+        "cg": sim.cg_(x0.copy(), Sp, b, Pl=DinvS, maxiter=50),
     }
     for chunk in (1, 4, 1000):
         many = {
             "gmres": sim.chunked("gmres", x0.copy(), A, b, chunk, pl_diag=d, Pr=Dinv, restart=6, maxiter=50, orth_meth="dgks"),
             "minres": sim.chunked("minres", x0.copy(), S, b, chunk, maxiter=50),
             "bicgstabl": sim.chunked("bicgstabl", x0.copy(), A, b, chunk, Pl=Dinv, shadow=sh, l=2, maxiter=60, reltol=1e-13),
+            "cg": sim.chunked("cg", x0.copy(), Sp, b, chunk, Pl=DinvS, maxiter=50),
         }
         for name in one:
             (x1, h1), (x2, h2, calls) = one[name], many[name]
@@ -1087,6 +1091,16 @@ def test_python_iterables_with_a_fake_library(monkeypatch):
     cargs = calls[0][1]
     assert calls[0][0] == "b200_minres_iter_create" and cargs[1] is None and isinstance(cargs[2]._obj, L.LinOp)
     assert [r for r in it] == [0.0, 1.0, 2.0] and it.done
+
+    calls.clear()
+    state["maxiter"] = 2
+    it = isb.cg_iterator_(np.zeros(n), op, b)                    # callback operator -> the general CG iterable
+    assert calls[0][0] == "b200_cg_iter_create_op" and isinstance(it, isb.KrylovIterable) and [r for r in it] == [0.0, 1.0]
+    calls.clear()
+    it = isb.cg_iterator_(np.zeros(n), csr, b, Pl=isb.FunctionPrec(n, np.float64, lambda y, x: None, ctx=ctx))
+    assert calls[0][0] == "b200_cg_iter_create_op" and calls[0][1][1].value == 7 and calls[0][1][5]._obj.Pl.kind == 2
+    with pytest.raises(isb.B200Error):
+        isb.cg_iterator_(np.zeros(n), op, b, statevars=object())
 
     calls.clear()
     Pl = isb.FunctionPrec(n, np.float64, lambda y, x: None, ctx=ctx)

@@ -72,3 +72,31 @@ def test_iteration_protocol_and_device_vectors(isb):
     assert np.array_equal(np.asarray(res), h["resnorm"]) and np.array_equal(xd.numpy(), x_ref)
     with pytest.raises(isb.B200Error):
         isb.gmres_iterable_(np.zeros(n), A, b, restart=100)       # restart > 64
+
+
+def test_general_cg_iterable(isb):
+    """cg_iterator! on a callback operator / with a callback preconditioner (b200_cg_iter_create_op): chunked steps reproduce
+    the one-shot general CG engine bit for bit; the tuned iterator (CSR + Jacobi) agrees to rounding."""
+    rng = np.random.default_rng(SEED)
+    n = 3000
+    M = sp.random(n, n, 0.003, random_state=1, format="csc")
+    S = (M + M.T + 8 * sp.eye(n)).tocsc()
+    A = isb.B200CSR.from_scipy(S)
+    op = isb.B200LinearOperator.from_csr(A)
+    jac = isb.JacobiPrec(S.diagonal())
+    Pcb = isb.FunctionPrec(n, np.float64, lambda y, v: jac.ldiv_(y, v))
+    b = rng.standard_normal(n)
+    x_ref, h_ref = isb.cg(op, b, Pl=Pcb, log=True)
+    for chunk in (1, 7, 10 ** 6):
+        for A_it in (A, op):
+            it = isb.cg_iterator_(np.zeros(n), A_it, b, Pl=Pcb, initially_zero=True)
+            assert isinstance(it, isb.KrylovIterable)
+            hist = []
+            while not it.done:
+                hist += it.step(chunk)
+            assert it.iteration == h_ref.iters and it.converged and np.array_equal(np.asarray(hist), h_ref["resnorm"])
+            assert np.array_equal(it.x, x_ref)
+            it.close()
+    it = isb.cg_iterator_(np.zeros(n), A, b, Pl=jac, initially_zero=True)       # tuned iterator
+    res = [r for r in it]
+    assert abs(len(res) - h_ref.iters) <= 1 and np.linalg.norm(it.x - x_ref) <= 1e-8 * np.linalg.norm(x_ref)
