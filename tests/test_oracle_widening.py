@@ -1450,3 +1450,42 @@ def test_engine_svdl_parameter_corners(oracle, sim, method):
         r = sim.svdl(sp.csr_matrix(A), q, nsv=nsv, k=k, j=j, tol=1e-8, reltol=1e-10, maxiter=200, method=method)
         assert r["iters"] == h.iters and r["converged"] and h.isconverged, (nsv, k, j)
         assert np.abs(r["sigma"] - so).max() <= 1e-12 * ex[0] and np.abs(r["sigma"] - ex[:nsv]).max() <= 1e-7 * ex[0]
+
+
+def test_general_engines_randomized(oracle, sim):
+    """twenty random systems (n = 4 .. 120, three densities), random restart / orthogonalisation / l / maxiter / initial
+    guess, Jacobi preconditioner, both summation orders and the multi-GPU finishing form: the general gmres / minres /
+    bicgstabl / cg engines give the oracle's iteration and product counts and its x."""
+    import warnings
+    rng = np.random.default_rng(99)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for trial in range(20):
+            n = int(rng.integers(4, 120))
+            dens = float(rng.choice([0.05, 0.2, 0.6]))
+            R = sp.random(n, n, dens, random_state=int(rng.integers(1 << 30)), format="csr")
+            A = (R + sp.diags(np.abs(R).sum(axis=1).A1 + 1.0)).tocsr()
+            S = (R + R.T + sp.diags(np.abs(R + R.T).sum(axis=1).A1 + 1.0)).tocsr()
+            b, x0, d, sh = rng.standard_normal(n), rng.standard_normal(n), A.diagonal(), rng.random(n)
+            restart = int(rng.integers(1, min(n, 40) + 1))
+            meth = str(rng.choice(["mgs", "cgs", "dgks"]))
+            l = int(rng.integers(1, 9))
+            mi = int(rng.integers(1, 60))
+            iz = bool(rng.integers(0, 2))
+            start = np.zeros(n) if iz else x0
+            kw = dict(order=trial % 2, split=trial % 2)
+            xo, ho = oracle.gmres_(start.copy(), A.tocsc(), b, Pl=oracle.JacobiPrec(d), restart=restart, maxiter=mi, log=True,
+                                   orth_meth=meth, initially_zero=iz)
+            xs, hs = sim.gmres_(start.copy(), A, b, pl_diag=d, restart=restart, maxiter=mi, orth_meth=meth, initially_zero=iz, **kw)
+            assert hs.iters == ho.iters and hs.mvps == ho.mvps and np.allclose(xs, xo, rtol=1e-8, atol=1e-10), ("gmres", trial)
+            xo, ho = oracle.minres_(start.copy(), S.tocsc(), b, maxiter=mi, log=True, initially_zero=iz)
+            xs, hs = sim.minres_(start.copy(), S, b, maxiter=mi, initially_zero=iz, **kw)
+            assert hs.iters == ho.iters and np.allclose(xs, xo, rtol=1e-7, atol=1e-9), ("minres", trial)
+            xo, ho = oracle.bicgstabl_(start.copy(), A.tocsc(), b, l, Pl=oracle.JacobiPrec(d), max_mv_products=mi, log=True,
+                                       initial_zero=iz, r_shadow=sh)
+            xs, hs = sim.bicgstabl_(start.copy(), A, b, l, sh, diag=d, max_mv_products=mi, initial_zero=iz, **kw)
+            assert hs.iters == ho.iters and hs.mvps == ho.mvps and np.allclose(xs, xo, rtol=1e-5, atol=1e-7), ("bicgstabl", trial)
+            xo, ho = oracle.cg_(start.copy(), S.tocsc(), b, Pl=oracle.JacobiPrec(S.diagonal()), maxiter=mi, log=True,
+                                initially_zero=iz)
+            xs, hs = sim.cg_(start.copy(), S, b, diag=S.diagonal(), maxiter=mi, initially_zero=iz, **kw)
+            assert hs.iters == ho.iters and np.allclose(xs, xo, rtol=1e-8, atol=1e-10), ("cg", trial)
