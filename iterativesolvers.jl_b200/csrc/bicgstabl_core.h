@@ -242,11 +242,13 @@ struct BcgMr {
   B200_HD void elem(int64_t i, double *acc) const {
     T u0 = us[i], xv = x[i], r0 = rs[i];
     T su = (T)0, sx = (T)0, sr = (T)0;
-    for (int c = 0; c < l; ++c) {
-      su = su + us[i + (c + 1) * ld] * g[c];                // us[:, 2:end] * gamma :126
-      sx = sx + rs[i + c * ld] * g[c];                      // rs[:, 1:l] * gamma :127
-      sr = sr + rs[i + (c + 1) * ld] * g[c];                // rs[:, 2:end] * gamma :128
-    }
+    B200_UNROLL
+    for (int c = 0; c < kBcMaxL; ++c)                       // (compile-time bound: gamma stays in registers)
+      if (c < l) {
+        su = su + us[i + (c + 1) * ld] * g[c];              // us[:, 2:end] * gamma :126
+        sx = sx + rs[i + c * ld] * g[c];                    // rs[:, 1:l] * gamma :127
+        sr = sr + rs[i + (c + 1) * ld] * g[c];              // rs[:, 2:end] * gamma :128
+      }
     us[i] = u0 - su;
     x[i] = xv + sx;
     r0 = r0 - sr;
