@@ -71,7 +71,14 @@ typedef struct {
   int64_t mvps;         /* history.mvps  (quirks of SURVEY.md section 9 reproduced)               */
   int32_t isconverged;  /* converged(iterable) at exit                                            */
   int32_t status;       /* 0, or B200_ERR_BREAKDOWN if a NaN/breakdown was detected
-                           (b200_cg_iter_next: 1 once done(it) holds)                             */
+                           (b200_cg_iter_next: 1 once done(it) holds).
+                           DEVIATION from the reference, deliberate: a NaN residual norm (initial or
+                           recurrence) ENDS the solve at that iteration with this status.  The
+                           reference's done() (src/cg.jl:36: iteration >= maxiter || residual <= tol)
+                           is false for NaN, so it keeps multiplying NaNs until maxiter (default
+                           size(A,2) iterations); iters / mvps / the :resnorm length therefore differ
+                           from the reference after a breakdown -- x is NaN in both.  Fixed-horizon
+                           runs (opts.fixed_iterations) never stop early.                          */
   double tol;           /* max(reltol*||r0||, abstol)                                             */
   double residual;      /* iterable.residual at exit                                              */
   int64_t n_resnorm;    /* number of :resnorm entries written to the caller's history buffer      */
@@ -561,7 +568,11 @@ B200_API int b200_svdl_op(b200_ctx *ctx, const b200_linop *A, const b200_linop *
  * >= nc columns are reserved for b200_lobpcg_constraint_append, which mirrors update! (:188-206: the Cholesky factor
  * of Y'Y is extended by an identity block -- the appended columns must be orthonormal and orthogonal to Y, as the
  * converged Ritz vectors of a constrained solve are); that is how the nev > blocksize driver (:925-962) deflates
- * the batches it has already computed.  _apply: X <- X - Y (Y'Y \ Y'X) on a column-major block (:212-224). */
+ * the batches it has already computed.  _apply: X <- X - Y (Y'Y \ Y'X) on a column-major block (:212-224).
+ * Errors: _create returns B200_ERR_BREAKDOWN ("PosDefException") when Y'Y is not positive definite.  The pivot rule
+ * is a superset of LAPACK potrf's (!(d > 0), what cholesky! at :181-182 does): a pivot is also rejected when it is
+ * below 4 nc eps of its diagonal entry, i.e. when Y is rank deficient up to rounding -- there potrf's answer depends on
+ * the order of roundings and the accepted factor carries no correct digits. */
 typedef struct b200_lobpcg_constraint b200_lobpcg_constraint;
 B200_API int b200_lobpcg_constraint_create(b200_ctx *ctx, int64_t n_local, const void *Y_dev, int64_t ldy, int nc,
                                            int capacity, int dtype, b200_lobpcg_constraint **out);

@@ -87,7 +87,7 @@ __device__ __forceinline__ void cg_after_init_norm(CgScal *s, double rr) {
   s->iter = 0;
   s->breakdown = !(res == res);
   const bool conv = !s->fixed && (res <= s->tol);
-  s->done = (0 >= s->maxiter) || conv;
+  s->done = (0 >= s->maxiter) || conv || (!s->fixed && s->breakdown);   // NaN ends the solve: see b200_result.status
 }
 
 enum { FIN_NONE = 0, FIN_INIT = 1, FIN_DOT = 2, FIN_NORM = 3, FIN_NORM_PCG = 4, FIN_RHO = 5 };
@@ -375,12 +375,7 @@ struct CgEngine {
       ProfScope prof(ctx, 0);
 #define LAUNCH(L)                                                                                                    \
   do {                                                                                                               \
-    static bool attr_set = false;                                                                                    \
-    if (!attr_set) {                                                                                                 \
-      B200_CUDA(cudaFuncSetAttribute(k_cg_spmv_dot_stream<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                     (int)smem));                                                                    \
-      attr_set = true;                                                                                               \
-    }                                                                                                                \
+    B200_SMEM_ATTR_ONCE(ctx, smem, k_cg_spmv_dot_stream<T, L>);                                                      \
     k_cg_spmv_dot_stream<T, L><<<grid, kStreamThreads, smem, ctx->stream>>>(                                        \
         A->rowptr, A->colind, (const T *)A->vals, xv, n, c, s, ctx->red.partials, ctx->red.ticket, cm);              \
   } while (0)

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,18 @@ void set_error(const char *fmt, ...);
                       cudaGetErrorString(_e), #call);                                            \
       return B200_ERR_CUDA;                                                                      \
     }                                                                                            \
+  } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: raise it once per (kernel
+// instantiation, device) -- a process may hold contexts on several devices (b200_ctx_create(device)); thread-safe.
+#define B200_SMEM_ATTR_ONCE(ctx, bytes, ...)                                                                      \
+  do {                                                                                                            \
+    static std::atomic<unsigned long long> b200_attr_done_{0ull};                                                 \
+    const unsigned long long b200_bit_ = 1ull << ((ctx)->device & 63);                                            \
+    if (!(b200_attr_done_.load(std::memory_order_acquire) & b200_bit_)) {                                         \
+      B200_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));    \
+      b200_attr_done_.fetch_or(b200_bit_, std::memory_order_release);                                             \
+    }                                                                                                             \
   } while (0)
 
 #define B200_NCCL(call)                                                                          \

@@ -904,11 +904,7 @@ struct Lobpcg {
   template <int NR>
   int gram_launch(const T *L, const T *const *Rb) {
     const size_t smem = sizeof(GramSmem<T, NR>);
-    static bool attr_set = false;
-    if (!attr_set) {
-      B200_CUDA(cudaFuncSetAttribute(k_gram<T, NR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
-    }
+    B200_SMEM_ATTR_ONCE(ctx, smem, k_gram<T, NR>);
     k_gram<T, NR><<<grid_gram, kGramThreads, smem, ctx->stream>>>(L, Rb[0], Rb[NR > 1 ? 1 : 0], Rb[NR > 2 ? 2 : 0],
                                                                   Rb[NR > 3 ? 3 : 0], Rb[0] == L ? 1 : 0, n,
                                                                   gram_partials, ctx->red.ticket, d_gram);
@@ -937,14 +933,8 @@ struct Lobpcg {
       ra.blk[0] = X_; ra.blk[1] = R_; ra.blk[2] = AR_;
       ra.blk[3] = with_p ? P_ : X_; ra.blk[4] = with_p ? AP_ : X_;
       ra.n = n;
-      static bool attr_set = false;
-      if (!attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(k_gram_rr_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(RrSmem<2>)));
-        B200_CUDA(cudaFuncSetAttribute(k_gram_rr_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(RrSmem<1>)));
-        attr_set = true;
-      }
+      B200_SMEM_ATTR_ONCE(ctx, sizeof(RrSmem<2>), k_gram_rr_tc<2>);
+      B200_SMEM_ATTR_ONCE(ctx, sizeof(RrSmem<1>), k_gram_rr_tc<1>);
       {
         ProfScope prof(ctx, 1);
         if (with_p)
@@ -972,12 +962,7 @@ struct Lobpcg {
       RrArgs ra;
       for (int b = 0; b < 5; ++b) ra.blk[b] = B_;
       ra.n = n;
-      static bool attr_set = false;
-      if (!attr_set) {
-        B200_CUDA(cudaFuncSetAttribute(k_gram_rr_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(RrSmem<0>)));
-        attr_set = true;
-      }
+      B200_SMEM_ATTR_ONCE(ctx, sizeof(RrSmem<0>), k_gram_rr_tc<0>);
       {
         ProfScope prof(ctx, 1);
         k_gram_rr_tc<0><<<grid_gram, kRrThreads, sizeof(RrSmem<0>), ctx->stream>>>(ra, gram_partials, ctx->red.ticket,

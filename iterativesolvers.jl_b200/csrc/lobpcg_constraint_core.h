@@ -103,12 +103,21 @@ int constraint_update(B &be, const T *Y, int64_t ldy, int nc, const double *coef
 }
 
 // host: upper Cholesky factor U (nc x nc, column-major, ld = nc) of the Hermitian matrix whose upper triangle is in G
-// (column-major); returns 0, or j+1 when the leading minor of order j+1 is not positive definite (PosDefException)
+// (column-major); returns 0, or j+1 when the leading minor of order j+1 is not positive definite (PosDefException).
+// Pivot rule: LAPACK potrf (the reference's cholesky!, src/lobpcg.jl:181-182) rejects a pivot d only when !(d > 0);
+// for a Gram matrix that is singular up to rounding the sign of d is decided by the order of the roundings (FMA
+// contraction), so acceptance there is arbitrary and the accepted factor turns constraint_apply into noise.  This
+// engine rejects every pivot that is not above the rounding level of its own cancellation,
+//     !(d > 4 nc eps G[j][j])      (G[j][j] the diagonal entry before elimination),
+// a superset of potrf's failure set: every input potrf rejects is rejected here, and the additional rejections are
+// Gram matrices whose Cholesky factor carries no correct digits in its last pivot.  Documented in b200krylov.h.
 inline int con_cholesky_upper(double *G, int nc) {
+  const double rel = 4.0 * (double)nc * 2.220446049250313e-16;
   for (int j = 0; j < nc; ++j) {
-    double d = G[j + (size_t)j * nc];
+    const double g0 = G[j + (size_t)j * nc];
+    double d = g0;
     for (int k = 0; k < j; ++k) d -= G[k + (size_t)j * nc] * G[k + (size_t)j * nc];
-    if (!(d > 0.0)) return j + 1;
+    if (!(d > 0.0) || !(d > rel * g0)) return j + 1;
     d = sqrt(d);
     G[j + (size_t)j * nc] = d;
     for (int c = j + 1; c < nc; ++c) {

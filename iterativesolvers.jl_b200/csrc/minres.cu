@@ -319,12 +319,7 @@ int minres_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200_m
         ProfScope prof(ctx, 0);
 #define LAUNCH(L)                                                                                                  \
   do {                                                                                                             \
-    static bool attr_set = false;                                                                                  \
-    if (!attr_set) {                                                                                               \
-      B200_CUDA(cudaFuncSetAttribute(k_mr_spmv_stream<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                                     (int)smem));                                                                  \
-      attr_set = true;                                                                                             \
-    }                                                                                                              \
+    B200_SMEM_ATTR_ONCE(ctx, smem, k_mr_spmv_stream<T, L>);                                                        \
     k_mr_spmv_stream<T, L><<<grid, kStreamThreads, smem, st>>>(A->rowptr, A->colind, (const T *)A->vals, xv,       \
                                                                 v_prev, v_next, n, m, ctx->red.partials,           \
                                                                 ctx->red.ticket, single);                          \

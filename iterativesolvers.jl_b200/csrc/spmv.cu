@@ -86,11 +86,7 @@ int launch_spmv_stream(b200_ctx *ctx, const b200_csr *A, const void *x, void *y)
   const size_t smem = sizeof(StreamSmem<T>);
 #define LAUNCH(L)                                                                                                 \
   do {                                                                                                            \
-    static bool attr_set = false;                                                                                 \
-    if (!attr_set) {                                                                                              \
-      B200_CUDA(cudaFuncSetAttribute(k_spmv_stream<T, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      attr_set = true;                                                                                            \
-    }                                                                                                             \
+    B200_SMEM_ATTR_ONCE(ctx, smem, k_spmv_stream<T, L>);                                                          \
     k_spmv_stream<T, L><<<grid, kStreamThreads, smem, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals,   \
                                                                      xv, A->m_local, (T *)y);                    \
   } while (0)
@@ -134,10 +130,13 @@ template <typename T, int BS>
 int launch_spmm_bs(b200_ctx *ctx, const b200_csr *A, const T *X, int64_t ldx, T *Y, int64_t ldy) {
   const int lpr = pick_lpr(A->avg_row_nnz);
   const int grid = stream_grid(ctx, A->m_local, kThreads / lpr, 4);
+  // no halo buffer (single GPU): column indices >= m_local of a wide operator (n > m, lsqr!/lsmr!/svdl) address the rows
+  // of X behind the first m_local ones -- the same aliasing make_xview does for the vector kernels
+  const T *halo = A->halo ? (const T *)A->halo : X + A->m_local;
+  const int64_t ldh = A->halo ? A->n_halo : ldx;
 #define LAUNCH(L)                                                                                                   \
-  k_spmm<T, L, BS><<<grid, kThreads, 0, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals, X, ldx,           \
-                                                       (const T *)A->halo, A->n_halo, (int)A->m_local, A->m_local, \
-                                                       Y, ldy)
+  k_spmm<T, L, BS><<<grid, kThreads, 0, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals, X, ldx, halo, ldh, \
+                                                       (int)A->m_local, A->m_local, Y, ldy)
   switch (lpr) {
     case 2: LAUNCH(2); break;
     case 4: LAUNCH(4); break;
@@ -187,9 +186,9 @@ int b200_spmv(b200_ctx *ctx, const b200_csr *A, const void *x_dev, void *y_dev) 
 
 int b200_spmm(b200_ctx *ctx, const b200_csr *A, const void *X_dev, int64_t ldx, void *Y_dev, int64_t ldy, int bs) {
   B200_REQUIRE(ctx && A && X_dev && Y_dev && bs >= 1, "bad arguments");
-  B200_REQUIRE(ldx >= A->m_local && ldy >= A->m_local, "leading dimensions too small");
-  B200_REQUIRE(X_dev != Y_dev, "mul!(Y, A, X): Y must not alias X");
   B200_REQUIRE(ctx->world == 1, "block SpMM is single-GPU in this version");
+  B200_REQUIRE(ldx >= A->n_global && ldy >= A->m_local, "leading dimensions too small: X has size(A,2) rows, Y size(A,1)");
+  B200_REQUIRE(X_dev != Y_dev, "mul!(Y, A, X): Y must not alias X");
   if (A->m_local == 0) return B200_OK;
   return A->dtype == B200_F64 ? launch_spmm<double>(ctx, A, (const double *)X_dev, ldx, (double *)Y_dev, ldy, bs)
                               : launch_spmm<float>(ctx, A, (const float *)X_dev, ldx, (float *)Y_dev, ldy, bs);

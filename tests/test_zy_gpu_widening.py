@@ -104,6 +104,14 @@ def test_transpose_and_rectangular_spmv(isb, oracle, shape, density, dtype):
     x, y = rng.standard_normal(n).astype(dtype), rng.standard_normal(m).astype(dtype)
     assert relerr(A @ x, oracle.csc_spmv(O, x)) <= tol
     assert relerr(At @ y, oracle.csc_spmv_adjoint(O, y)) <= tol
+    # block form mul!(Y, A, X) on the same operators (X has size(A,2) rows, Y size(A,1)): wide and tall alike
+    X, Y = rng.standard_normal((n, 3)).astype(dtype), rng.standard_normal((m, 5)).astype(dtype)
+    AX, AtY = A @ np.asfortranarray(X), At @ np.asfortranarray(Y)
+    assert AX.shape == (m, 3) and AtY.shape == (n, 5)
+    for j in range(3):
+        assert relerr(AX[:, j], oracle.csc_spmv(O, X[:, j])) <= tol
+    for j in range(5):
+        assert relerr(AtY[:, j], oracle.csc_spmv_adjoint(O, Y[:, j])) <= tol
 
 
 def test_square_solvers_reject_rectangular_operators(isb):

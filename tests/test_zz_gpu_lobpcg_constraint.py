@@ -1,7 +1,7 @@
 """GPU tests for the LOBPCG constraint (`C` keyword, reference src/lobpcg.jl:144-224, :829) and the nev > blocksize
 driver (:925-962): the constraint passes through the C ABI against the oracle, constrained `lobpcg` against the
 oracle's, and the reference's own property tests (test/lobpcg.jl:213-228, :291-306, :324-342) on the device path.
-(Written after the round's GPU budget was spent: first executed by the round-end GPU run.)"""
+"""
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -38,11 +38,15 @@ def test_constraint_apply_matches_oracle(isb, oracle, dtype, tol):
     cases.case_constraint_apply(oracle, [fn], dtype, tol)
 
 
-def test_constraint_rejects_dependent_basis(isb):
+@pytest.mark.parametrize("n", [64, 40])
+def test_constraint_rejects_dependent_basis(isb, n):
+    """n = 64: Y'Y = 64 [[1,1],[1,1]], sqrt(64) exact, second pivot exactly 0 in any rounding -- LAPACK potrf (the
+    reference's cholesky!, src/lobpcg.jl:181-182) rejects it too.  n = 40: the second pivot is +-7e-15 depending on FMA
+    contraction (potrf's verdict is a coin flip); the engine's relative pivot rule (b200krylov.h) rejects it."""
     ctx = isb.default_context()
-    Y = np.ones((40, 2))
+    Y = np.ones((n, 2))
     with pytest.raises(isb.B200Error) as e:
-        isb.LobpcgConstraint(ctx, 40, np.float64, Y)
+        isb.LobpcgConstraint(ctx, n, np.float64, Y)
     assert "PosDef" in str(e.value)
 
 
@@ -113,9 +117,16 @@ def test_general_engine_equals_tuned_engine_on_the_standard_problem(isb, oracle)
     O = oracle.laplace_matrix(np.float64, 8, 3, base=1)
     A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
     X0 = rng.random((O.n, 4))
-    r1 = isb.lobpcg(A, False, X0, tol=1e-6, maxiter=300)
-    r2 = isb.lobpcg(isb.B200LinearOperator.from_csr(A), False, X0, tol=1e-6, maxiter=300)
-    assert r1.converged and r2.converged and abs(r1.iterations - r2.iterations) <= max(3, r1.iterations // 10)
+    r1 = isb.lobpcg(A, False, X0, tol=1e-6, maxiter=300, log=True)
+    r2 = isb.lobpcg(isb.B200LinearOperator.from_csr(A), False, X0, tol=1e-6, maxiter=300, log=True)
+    assert r1.converged and r2.converged
+    # same recurrence, different summation orders: the first steps agree to rounding ...
+    for (i1, rn1, l1), (i2, rn2, l2) in list(zip(r1.trace, r2.trace))[:12]:
+        assert i1 == i2 and np.abs(l1 - l2).max() <= 1e-8 * np.abs(l2).max()
+        assert np.abs(rn1 - rn2).max() <= 1e-5 * np.abs(rn2).max() + 1e-8
+    # ... while the step at which the triple eigenvalue 0.709 (lambda_2..4 of the 8^3 Laplacian) lets the last residual
+    # under tol is rounding-sensitive (first GPU run: 71 vs 63 iterations), so the count is compared loosely
+    assert abs(r1.iterations - r2.iterations) <= max(5, r1.iterations // 4)
     assert np.abs(np.sort(r1.lam) - np.sort(r2.lam)).max() <= 1e-8
 
 
