@@ -53,19 +53,31 @@ def prof_read(L, ctx):
     return out
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["gmres", "lobpcg", "minres", "bicgstabl", "cg256", "widen", "general"])
-    ap.add_argument("--grid", type=int, default=256)
-    ap.add_argument("--iters", type=int, default=None)
-    ap.add_argument("--orth", default="cgs")
-    ap.add_argument("--reps", type=int, default=2)
-    args = ap.parse_args()
-    import torch
-    torch.cuda.set_device(0)
+class _Clocks:
+    """nvidia-smi clocks / throttle reasons around the LAST (timed) repetition of a config (bench.ClockSampler)."""
+
+    def __init__(self, enabled=True, device=0):
+        self.s, self.device, self.enabled = None, device, enabled
+
+    def start(self):
+        if self.enabled:
+            from bench import ClockSampler
+            self.s = ClockSampler(self.device)
+            self.s.start()
+
+    def stop(self):
+        out = self.s.stop() if self.s else None
+        self.s = None
+        return out
+
+
+def run(which, grid=256, iters=None, orth="cgs", reps=2, ctx=None, clocks=True):
+    """one config on cuda:<ctx.device>; returns the JSON-able record (see the module docstring)."""
+    args = argparse.Namespace(which=which, grid=grid, iters=iters, orth=orth, reps=reps)
     import iterativesolvers_jl_b200 as isb
-    ctx = isb.default_context()
+    ctx = ctx or isb.default_context()
     L = isb.lib()
+    clk = _Clocks(clocks)
     N = args.grid
     n = N ** 3
     nnz = 7 * N ** 3 - 6 * N ** 2
@@ -91,11 +103,14 @@ def main():
             if rep == 1:
                 prof_reset(L, ctx)
             ctx.sync()
+            if rep == args.reps:
+                clk.start()
             t0 = time.perf_counter()
             x, h = isb.gmres_(xd, A, bd, restart=restart, maxiter=iters, orth_meth=args.orth, initially_zero=True,
                               log=True, reltol=0.0)
             ctx.sync()
             dt = time.perf_counter() - t0
+        out["clocks"] = clk.stop()
         pr = prof_read(L, ctx)
         out.update({"solver": f"gmres!(restart=30, orth_meth={args.orth})", "iters": h.niters, "seconds": dt,
                     "iters_per_s": h.niters / dt, "mvps": h.mvps, "resnorm_first_last": [float(h["resnorm"][0]), float(h["resnorm"][-1])],
@@ -110,10 +125,13 @@ def main():
             if rep == 1:
                 prof_reset(L, ctx)
             ctx.sync()
+            if rep == args.reps:
+                clk.start()
             t0 = time.perf_counter()
             x, h = isb.bicgstabl_(xd, A, bd, l, max_mv_products=mv, initial_zero=True, log=True, reltol=0.0, r_shadow=rsh)
             ctx.sync()
             dt = time.perf_counter() - t0
+        out["clocks"] = clk.stop()
         pr = prof_read(L, ctx)
         out.update({"solver": "bicgstabl!(l=2)", "outer_iters": h.niters, "mvps": h.mvps, "seconds": dt,
                     "mv_products_per_s": h.mvps / dt, "profile": pr})
@@ -131,6 +149,8 @@ def main():
             if rep == 1:
                 prof_reset(L, ctx)
             ctx.sync()
+            if rep == args.reps:
+                clk.start()
             t0 = time.perf_counter()
             if args.which == "minres":
                 x, h = isb.minres_(xd, A, bd, maxiter=iters, initially_zero=True, log=True, reltol=0.0)
@@ -138,6 +158,7 @@ def main():
                 x, h = isb.cg_(xd, A, bd, maxiter=iters, initially_zero=True, log=True, reltol=0.0, _fixed_iterations=True)
             ctx.sync()
             dt = time.perf_counter() - t0
+        out["clocks"] = clk.stop()
         pr = prof_read(L, ctx)
         out.update({"solver": args.which, "iters": h.niters, "seconds": dt, "iters_per_s": h.niters / dt,
                     "algorithmic_gb_per_iter": per_it / 1e9, "achieved_gbs": per_it * h.niters / dt / 1e9,
@@ -176,6 +197,8 @@ def main():
                 if rep == 1:
                     prof_reset(L, ctx)
                 ctx.sync()
+                if rep == args.reps:
+                    clk.start()
                 t0 = time.perf_counter()
                 if name == "qmr":
                     x, h = isb.qmr_(xd, A, bd, maxiter=iters, initially_zero=True, log=True, reltol=0.0)
@@ -187,9 +210,10 @@ def main():
                     x, h = isb.idrs_(xd, A, bd, s=s_dim, P=Pd, maxiter=iters, log=True, reltol=0.0)
                 ctx.sync()
                 dt = time.perf_counter() - t0
+            ck = clk.stop()
             pr = prof_read(L, ctx)
             key = "resnorm" if name in ("qmr", "idrs", "lsqr") else "rnorm"
-            res[name] = {"iters": h.iters, "seconds": dt, "iters_per_s": h.iters / dt,
+            res[name] = {"clocks": ck, "iters": h.iters, "seconds": dt, "iters_per_s": h.iters / dt,
                          "algorithmic_gb_per_iter": per_it[name] / 1e9,
                          "achieved_gbs": per_it[name] * h.iters / dt / 1e9,
                          "frac_of_measured_peak": per_it[name] * h.iters / dt / 1e9 / pk,
@@ -231,12 +255,14 @@ def main():
                 for rep in range(args.reps + 1):
                     L.b200_fill(ctx._h, n, 0.0, xd._p, 0)
                     ctx.sync()
+                    if rep == args.reps:
+                        clk.start()
                     t0 = time.perf_counter()
                     h = fn(op)
                     ctx.sync()
                     dt = time.perf_counter() - t0
                 units = h.mvps if name == "bicgstabl" else h.iters
-                entry[kind] = {"units": int(units), "seconds": dt, "units_per_s": units / dt,
+                entry[kind] = {"clocks": clk.stop(), "units": int(units), "seconds": dt, "units_per_s": units / dt,
                                "last_resnorm": float(h["resnorm"][-1]) if len(h["resnorm"]) else None}
                 if per_it:
                     entry[kind]["achieved_gbs_on_tuned_bytes"] = per_it * units / dt / 1e9
@@ -257,19 +283,38 @@ def main():
             if rep == 1:
                 prof_reset(L, ctx)
             ctx.sync()
+            if rep == args.reps:
+                clk.start()
             t0 = time.perf_counter()
             r = isb.lobpcg(A, False, Xd, maxiter=steps, _fixed_iterations=True)
             ctx.sync()
             dt = time.perf_counter() - t0
+            if rep == args.reps:
+                out["clocks"] = clk.stop()
             Xd.free()
         pr = prof_read(L, ctx)
         out.update({"solver": "lobpcg(block=16, fp32, smallest)", "steps": steps, "seconds": dt, "steps_per_s": steps / dt,
                     "lambda_min": float(np.min(r.lam)), "max_resnorm": float(np.max(r.residual_norms)),
                     "algorithmic_gb_per_step_ideal": per_step / 1e9, "achieved_gbs_vs_ideal_bytes": per_step * steps / dt / 1e9,
+                    "frac_of_measured_peak": per_step * steps / dt / 1e9 / pk,
                     "profile": pr})
     if "achieved_gbs" in out:
         out["frac_of_measured_peak"] = out["achieved_gbs"] / pk
-    print(json.dumps(out))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", choices=["gmres", "lobpcg", "minres", "bicgstabl", "cg256", "widen", "general"])
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--iters", type=int, default=None)
+    ap.add_argument("--orth", default="cgs")
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--no-clocks", action="store_true")
+    args = ap.parse_args()
+    import torch
+    torch.cuda.set_device(0)
+    print(json.dumps(run(args.which, args.grid, args.iters, args.orth, args.reps, clocks=not args.no_clocks)))
 
 
 if __name__ == "__main__":

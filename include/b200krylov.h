@@ -115,10 +115,16 @@ B200_API int b200_ctx_profile_read(b200_ctx *ctx, int slot, double *total_ms, in
  *   "spmv_kernel": 0 = auto, 1 = sub-warp-per-row kernel, 2 = TMA-streamed kernel (when the tiles fit)
  *   "snake": 1 (default) = consecutive hot kernels of a solver sweep the rows in alternating directions so
  *           that each starts on the data the previous one touched last (L2 reuse); 0 = always ascending
+ *   "orth_fused": 1 (default) = orthogonalize_and_normalize! (CGS / DGKS) is ONE cooperative launch (dots, update, norm,
+ *           DGKS re-orthogonalisation rounds and the scaling separated by grid-wide barriers) and gmres! keeps H, the
+ *           residual recurrence and the stopping test on the device, enqueueing a whole restart cycle per host
+ *           synchronisation (single-GPU contexts); 0 = three kernels per orthogonalisation, host-side recurrences
  *   "comm": 0 = auto, 1 = NCCL collectives, 2 = NVLink peer-memory collectives fused into the kernels
  *           (multi-GPU contexts; get "peer_ok" tells whether the peer buffers could be mapped)
  *   "lobpcg_mma": 1 (default) = fp32 LOBPCG blocks run the update and the Gram products as 3xTF32 tensor-core
- *           MMAs (fp32-level products, fp32 accumulate); 0 = CUDA-core kernels (always used for fp64) */
+ *           MMAs (fp32-level products, fp32 accumulate), the eight Rayleigh-Ritz Gram products of a step as
+ *           tcgen05.mma with TMEM accumulators; 2 = the same with the legacy mma.sync Gram kernel;
+ *           0 = CUDA-core kernels (always used for fp64) */
 B200_API int b200_ctx_set_option(b200_ctx *ctx, const char *name, int64_t value);
 B200_API int b200_ctx_get_option(const b200_ctx *ctx, const char *name, int64_t *value);
 /* sum over ranks (no-op for world==1); used by hosts for max/sum of small host scalars */
@@ -601,6 +607,12 @@ B200_API int b200_lobpcg_solve_op(b200_ctx *ctx, const b200_linop *A, const b200
                                   double *lambda_host, double *resnorm_host);
 B200_API int b200_lobpcg_constraint_create_b(b200_ctx *ctx, const b200_linop *B, int64_t n_local, const void *Y_dev,
                                              int64_t ldy, int nc, int capacity, int dtype, b200_lobpcg_constraint **out);
+
+/* Test hook: the eight Rayleigh-Ritz Gram products (reference src/lobpcg.jl:586-605) of five row-major n x 16 fp32
+ * device blocks X, R, AR, P, AP through one of the engine's kernels (variant 1: tcgen05.mma with TMEM accumulators,
+ * variant 2: legacy mma.sync); out_host[p * 256 + i * 16 + j], products X'AR, X'R, R'AR, X'AP, X'P, R'P, AR'P, P'AP. */
+B200_API int b200_debug_lobpcg_gram_rr(b200_ctx *ctx, const void *const *blk_dev, int64_t n, int variant,
+                                       double *out_host);
 
 /* Host-side dense helpers used by the engines for their O(blocksize^3) pieces (fp64, column-major,
  * n <= 64): eigen!(Hermitian(A)[, Hermitian(B)]) -- eigenvalues ascending in w, eigenvectors in the

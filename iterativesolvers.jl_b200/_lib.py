@@ -229,6 +229,7 @@ SIGNATURES = {
                                     C.POINTER(LobpcgResult), _P, _P]),
     "b200_lobpcg_constraint_create_b": (_INT, [_P, C.POINTER(LinOp), _I64, _P, _I64, _INT, _INT, _INT, C.POINTER(_P)]),
     "b200_dense_sygv_host": (_INT, [_INT, _P, _P, _P, _P]),
+    "b200_debug_lobpcg_gram_rr": (_INT, [_P, _P, _I64, _INT, _P]),
 }
 
 _lib = None

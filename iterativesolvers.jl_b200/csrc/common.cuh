@@ -98,7 +98,10 @@ struct b200_ctx {
   int *h_flags = nullptr;        // pinned host flags (16 ints)
   int opt_spmv_kernel = 0;       // b200_ctx_set_option("spmv_kernel"): 0 auto, 1 sub-warp per row, 2 TMA stream
   int opt_comm = 0;              // b200_ctx_set_option("comm"): 0 auto (peer memory if mapped), 1 NCCL, 2 peer memory
-  int opt_lobpcg_mma = 1;        // b200_ctx_set_option("lobpcg_mma"): fp32 LOBPCG blocks on the tensor pipe (3xTF32); 0 = SIMT kernels
+  int opt_lobpcg_mma = 1;        // b200_ctx_set_option("lobpcg_mma"): fp32 LOBPCG blocks on the tensor cores (3xTF32): 1 = Rayleigh-Ritz Gram on
+                                 // tcgen05 (TMEM accumulators), 2 = legacy mma.sync Gram, 0 = SIMT kernels
+  int opt_orth_fused = 1;        // b200_ctx_set_option("orth_fused"): 1 = one cooperative launch per CGS/DGKS orthogonalisation and a
+                                 // device-resident GMRES cycle (single GPU); 0 = the three-kernel path with host-side recurrences
   int opt_snake = 1;            // b200_ctx_set_option("snake"): consecutive hot kernels sweep the rows in alternating directions
   // peer-memory collectives (peer.cuh), multi-GPU contexts only
   bool peer_ok = false;
@@ -115,6 +118,7 @@ struct b200_ctx {
   int64_t prof_n[4] = {0, 0, 0, 0};
   void *ws = nullptr;            // grow-only solver workspace (reused across solves: no malloc in the timed path)
   size_t ws_bytes = 0;
+  void *orth_scal = nullptr;     // device GmScal of the op-level orthogonalize_and_normalize! (gmres.cu), allocated on first use
   int in_callback = 0;           // > 0 while an operator / preconditioner callback runs: the workspace belongs to the caller
 };
 

@@ -189,6 +189,7 @@ int b200_ctx_destroy(b200_ctx *c) {
   cudaFree(c->red.ticket);
   cudaFree(c->d_scalars);
   if (c->ws) cudaFree(c->ws);
+  if (c->orth_scal) cudaFree(c->orth_scal);
   for (auto e : c->prof_ev) cudaEventDestroy(e);
   cudaFreeHost(c->h_scalars);
   cudaFreeHost(c->h_flags);
@@ -246,8 +247,12 @@ int b200_ctx_set_option(b200_ctx *c, const char *name, int64_t value) {
     c->opt_snake = value != 0;
     return B200_OK;
   }
+  if (strcmp(name, "orth_fused") == 0) {
+    c->opt_orth_fused = value != 0;
+    return B200_OK;
+  }
   if (strcmp(name, "lobpcg_mma") == 0) {
-    c->opt_lobpcg_mma = value != 0;
+    c->opt_lobpcg_mma = (int)(value < 0 ? 0 : (value > 2 ? 2 : value));
     return B200_OK;
   }
   if (strcmp(name, "comm") == 0) {
@@ -266,6 +271,7 @@ int b200_ctx_get_option(const b200_ctx *c, const char *name, int64_t *value) {
   else if (strcmp(name, "comm") == 0) *value = c->opt_comm;
   else if (strcmp(name, "lobpcg_mma") == 0) *value = c->opt_lobpcg_mma;
   else if (strcmp(name, "snake") == 0) *value = c->opt_snake;
+  else if (strcmp(name, "orth_fused") == 0) *value = c->opt_orth_fused;
   else if (strcmp(name, "peer_ok") == 0) *value = c->peer_ok ? 1 : 0;
   else {
     set_error("unknown option `%s`", name);

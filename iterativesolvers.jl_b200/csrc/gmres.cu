@@ -12,9 +12,12 @@
 //   k_block_axpy : w -= V h ; ||w||^2 fused                                  ((k+2) n-passes)
 //   k_scale_dev  : w *= inv(nrm)                                             (2 n-passes)
 // Algorithmic bytes per CGS step k: (2k+5) * n * V.
+#include <cooperative_groups.h>
+
 #include "blas1.cuh"
 #include "spmv.cuh"
 #include "linop.cuh"
+#include "gmres_core.h"
 
 using namespace b200;
 
@@ -206,6 +209,165 @@ __global__ void k_hessenberg_ldiv(double *__restrict__ H, int ldh, int m, double
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// orthogonalize_and_normalize!(V[:, 1:k], w, h, ClassicalGramSchmidt() / DGKS()) in ONE cooperative launch
+// (reference src/orthogonalize.jl:41-51, :13-39) and, for the GMRES engine, the scalar part of the inner iteration
+// (src/gmres.jl:68-104: H column, null-vector residual recurrence, stopping test, Givens least-squares solve at the end
+// of a cycle) in its finishing thread.  Every scalar lives in the device GmScal (gmres_core.h), so the host neither
+// reads nor decides anything between the launches of a restart cycle:
+//
+//   phase 1  h = V' w: block partial sums of the k dots                                  grid.sync
+//   phase 2  block j sums column j of the partials in a fixed order -> dst[j]            grid.sync
+//   phase 3  w -= V dst, block partial of ||w||^2                                        grid.sync
+//   phase 4  block 0: ||w||; DGKS: projection size and the re-orthogonalisation test (:20-33); when no further round
+//            is needed and do_step: gm_step                                              grid.sync
+//   (DGKS: back to phase 1 with dst = correction while nrm < eta * projection_size)
+//   phase 5  w *= inv(nrm)
+//
+// Every thread sweeps the same rows in phases 1, 3 and 5.  HBM traffic is that of the three separate kernels
+// ((2k+5) n V); what goes away are two launches, the allreduce placeholders and the host round trip.
+// `gate_mask`: the launch is a no-op when (s->flags & gate_mask) != 0 -- GMRES enqueues a whole restart cycle ahead of
+// the device-side stopping test.
+namespace cgx = cooperative_groups;
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads) k_orth_fused(const T *__restrict__ V, int64_t ld, int k, T *w, int64_t n,
+                                                         int dgks, double *partials, GmScal *s, int do_step,
+                                                         int gate_mask) {
+  if (s->flags & gate_mask) return;             // uniform over the grid: nobody reaches a grid.sync
+  cgx::grid_group grid = cgx::this_grid();
+  __shared__ double smem[kThreads / 32][JB];
+  __shared__ double sred[kThreads / 32];
+  __shared__ T sy[kMaxReduceWidth];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t nv = n / VEC;                   // VEC == 2 is only launched when n is even
+  double *dst = s->h;
+  for (int round = 0;; ++round) {
+    // ---- phase 1: dots (register block of JB columns, as k_block_dots)
+    for (int j0 = 0; j0 < k; j0 += JB) {
+      const int jn = min(JB, k - j0);
+      double acc[JB];
+#pragma unroll
+      for (int j = 0; j < JB; ++j) acc[j] = 0.0;
+      for (int64_t iv = blockIdx.x * (int64_t)kThreads + threadIdx.x; iv < nv; iv += (int64_t)gridDim.x * kThreads) {
+        const int64_t i = iv * VEC;
+        T wv[VEC], vv[JB][VEC];
+        ldv<T, VEC>(w + i, wv);
+#pragma unroll
+        for (int j = 0; j < JB; ++j)
+          if (j < jn) ldv<T, VEC>(V + i + (int64_t)(j0 + j) * ld, vv[j]);
+#pragma unroll
+        for (int j = 0; j < JB; ++j)
+          if (j < jn) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) acc[j] += (double)vv[j][e] * (double)wv[e];
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < JB; ++j) acc[j] = warp_sum(acc[j]);
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < JB; ++j) smem[warp][j] = acc[j];
+      }
+      __syncthreads();
+      if (threadIdx.x < jn) {
+        double t = 0.0;
+        for (int wv = 0; wv < kThreads / 32; ++wv) t += smem[wv][threadIdx.x];
+        partials[(size_t)blockIdx.x * kMaxReduceWidth + j0 + threadIdx.x] = t;
+      }
+      __syncthreads();
+    }
+    __threadfence();
+    grid.sync();
+    // ---- phase 2: column j of the partials, summed by block j in slot order (deterministic)
+    for (int j = blockIdx.x; j < k; j += gridDim.x) {
+      double a = 0.0;
+      for (unsigned int b = threadIdx.x; b < gridDim.x; b += kThreads) a += __ldcg(&partials[(size_t)b * kMaxReduceWidth + j]);
+      a = block_sum<kThreads>(a, sred);
+      if (threadIdx.x == 0) dst[j] = a;
+    }
+    __threadfence();
+    grid.sync();
+    // ---- phase 3: w -= V dst ; ||w||^2
+    for (int j = threadIdx.x; j < k; j += kThreads) sy[j] = (T)(-__ldcg(&dst[j]));
+    __syncthreads();
+    double nacc = 0.0;
+    for (int64_t iv = blockIdx.x * (int64_t)kThreads + threadIdx.x; iv < nv; iv += (int64_t)gridDim.x * kThreads) {
+      const int64_t i = iv * VEC;
+      T t[VEC];
+      ldv<T, VEC>(w + i, t);
+      int j = 0;
+      for (; j + JB <= k; j += JB) {
+        T vv[JB][VEC];
+#pragma unroll
+        for (int u = 0; u < JB; ++u) ldv<T, VEC>(V + i + (int64_t)(j + u) * ld, vv[u]);
+#pragma unroll
+        for (int u = 0; u < JB; ++u) {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) t[e] += sy[j + u] * vv[u][e];
+        }
+      }
+      if (j < k) {
+        T vv[JB][VEC];
+#pragma unroll
+        for (int u = 0; u < JB; ++u)
+          if (j + u < k) ldv<T, VEC>(V + i + (int64_t)(j + u) * ld, vv[u]);
+#pragma unroll
+        for (int u = 0; u < JB; ++u)
+          if (j + u < k) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) t[e] += sy[j + u] * vv[u][e];
+          }
+      }
+      stv<T, VEC>(w + i, t);
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) nacc += (double)t[e] * (double)t[e];
+    }
+    nacc = block_sum<kThreads>(nacc, sred);
+    if (threadIdx.x == 0) partials[(size_t)blockIdx.x * kMaxReduceWidth] = nacc;
+    __threadfence();
+    grid.sync();
+    // ---- phase 4: the norm and everything scalar
+    if (blockIdx.x == 0) {
+      double a = 0.0;
+      for (unsigned int b = threadIdx.x; b < gridDim.x; b += kThreads) a += __ldcg(&partials[(size_t)b * kMaxReduceWidth]);
+      a = block_sum<kThreads>(a, sred);
+      if (threadIdx.x == 0) {
+        s->nrm2 = a;
+        s->nrm = sqrt(a);
+        s->k = k;
+        if (dgks) {
+          if (round == 0) gm_dgks_first(s);      // projection_size = norm(h); nrm < eta * projection_size ?  :20-26
+          else gm_dgks_next(s);                  // h .+= correction; projection_size = norm(correction)    :28-31
+        } else {
+          s->reorth = 0;
+        }
+        if (!s->reorth && do_step) gm_step(s);   // src/gmres.jl:68-104
+        __threadfence();
+      }
+    }
+    grid.sync();
+    if (!*(volatile int *)&s->reorth) break;
+    dst = s->corr;
+  }
+  // ---- phase 5: w .*= inv(nrm)  (:36 / :48); nrm == 0 (lucky breakdown) gives the reference's NaNs
+  const T inv = (T)1 / (T)(*(volatile double *)&s->nrm);
+  for (int64_t iv = blockIdx.x * (int64_t)kThreads + threadIdx.x; iv < nv; iv += (int64_t)gridDim.x * kThreads) {
+    const int64_t i = iv * VEC;
+    T t[VEC];
+    ldv<T, VEC>(w + i, t);
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) t[e] = t[e] * inv;
+    stv<T, VEC>(w + i, t);
+  }
+}
+
+__global__ void k_gm_set_beta(GmScal *s, const double *sumsq, int clear_mask) {
+  gm_set_beta(s, sumsq[0]);
+  s->flags &= ~clear_mask;
+}
+
 int gridv(const b200_ctx *ctx, int64_t n) { return stream_grid(ctx, n, kThreads * 2, 8); }
 
 // grid = one full wave of the kernel's real occupancy (grid-stride loops: a partial last wave is pure tail)
@@ -277,6 +439,29 @@ int scale_dev(b200_ctx *ctx, T *w, int64_t n, const double *nrm2_dev) {
   return B200_OK;
 }
 
+// one cooperative launch of k_orth_fused (single-GPU contexts, CGS / DGKS, 1 <= k <= 64)
+template <typename T>
+int orth_fused_launch(b200_ctx *ctx, const T *V, int64_t ld, int k, T *w, int64_t n, int dgks, GmScal *s, int do_step,
+                      int gate_mask) {
+  const bool v2 = can_vec2<T>(n, ld, {V, w});
+  auto kern = v2 ? k_orth_fused<T, 2> : k_orth_fused<T, 1>;
+  static int occ[2][64];                                   // blocks per SM of the two instantiations, per device
+  int &per_sm = occ[v2 ? 1 : 0][ctx->device & 63];
+  if (per_sm == 0) {
+    int q = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, kThreads, 0));
+    per_sm = q < 1 ? 1 : q;
+  }
+  const int grid = stream_grid(ctx, n, kThreads * 2, per_sm);   // <= sm_count * per_sm: all blocks co-resident (grid.sync)
+  double *partials = ctx->red.partials;
+  void *args[] = {(void *)&V, (void *)&ld, (void *)&k, (void *)&w, (void *)&n, (void *)&dgks, (void *)&partials, (void *)&s,
+                  (void *)&do_step, (void *)&gate_mask};
+  ProfScope prof(ctx, 1);
+  B200_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(kThreads), args, 0, ctx->stream));
+  ctx->launches++;
+  return B200_OK;
+}
+
 // orthogonalize_and_normalize!(V[:,1:k], w, h, method): h_host (k doubles) out, returns nrm.
 // Scratch: ctx->d_scalars[0..63] = h, [64..127] = correction, [200] = ||w||^2
 template <typename T>
@@ -285,6 +470,19 @@ int orth_impl(b200_ctx *ctx, int64_t n, const T *V, int64_t ld, int k, T *w, dou
   double *d_h = ctx->d_scalars, *d_c = ctx->d_scalars + 64, *d_n = ctx->d_scalars + 200;
   B200_REQUIRE(k >= 0 && k <= 64, "orthogonalize_and_normalize!: k=%d exceeds 64 basis vectors", k);
   double nrm2 = 0.0;
+  if (ctx->world == 1 && method != B200_ORTH_MGS && k >= 1 && ctx->opt_orth_fused) {
+    // one cooperative launch; h, the correction rounds and the norm stay in a device GmScal until they are read back
+    if (!ctx->orth_scal) B200_CUDA(cudaMalloc(&ctx->orth_scal, sizeof(GmScal)));
+    GmScal *s = (GmScal *)ctx->orth_scal;
+    B200_CUDA(cudaMemsetAsync(&s->flags, 0, sizeof(int), ctx->stream));
+    B200_TRY(orth_fused_launch<T>(ctx, V, ld, k, w, n, method == B200_ORTH_DGKS ? 1 : 0, s, 0, 0));
+    B200_CUDA(cudaMemcpyAsync(ctx->h_scalars, s->h, sizeof(double) * k, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(ctx->h_scalars + 64, &s->nrm, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int j = 0; j < k; ++j) h_host[j] = ctx->h_scalars[j];
+    *nrm_out = ctx->h_scalars[64];
+    return B200_OK;
+  }
   if (method == B200_ORTH_MGS) {
     // reference src/orthogonalize.jl:67-79: k sequential (dot ; axpy) pairs
     for (int i = 0; i < k; ++i) {
@@ -518,6 +716,165 @@ int gmres_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200_gm
   return B200_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// gmres! with a device-resident restart cycle (single GPU, CGS / DGKS): H, the null-vector residual recurrence, the
+// stopping test and the Givens least-squares solve live in a device GmScal (gmres_core.h: gm_step is the scalar part
+// of src/gmres.jl:68-104, run by the finishing thread of k_orth_fused).  The host enqueues expand! + orthogonalize for
+// the whole cycle -- launches behind the point where the cycle closes (restart reached, converged, maxiter) are no-ops
+// gated on s->flags -- and synchronises ONCE per cycle to learn how many columns the solution update takes.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+int gmres_impl_fused(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200_gmres_opts *o, b200_result *res,
+                     double *resnorm_host, int64_t resnorm_cap) {
+  const int64_t n = A->m_local;
+  const int dt = dtype_of<T>::value;
+  const double eps = sizeof(T) == 8 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
+  const double reltol = o->reltol < 0 ? sqrt(eps) : o->reltol;
+  const int64_t maxiter = o->maxiter < 0 ? A->n_global : o->maxiter;
+  const int restart = o->restart > 0 ? o->restart : (int)std::min<int64_t>(20, A->n_global);
+  B200_REQUIRE(restart <= kGmMaxRestart, "restart=%d: this version supports restart <= 64", restart);
+  const int dgks = o->orth_meth == B200_ORTH_DGKS ? 1 : 0;
+  const T *pl = o->Pl.kind == B200_PREC_JACOBI ? (const T *)o->Pl.diag : nullptr;
+  const T *pr = o->Pr.kind == B200_PREC_JACOBI ? (const T *)o->Pr.diag : nullptr;
+  const int64_t hist_cap = resnorm_host ? std::min<int64_t>(resnorm_cap, maxiter) : 0;   // reserve!(history, :resnorm, maxiter) :198
+
+  const size_t vec_bytes = align_up(sizeof(T) * (size_t)std::max<int64_t>(n, 1), 256);
+  const size_t v_bytes = align_up(sizeof(T) * (size_t)std::max<int64_t>(n, 1) * (restart + 1), 256);
+  const size_t s_bytes = align_up(sizeof(GmScal), 256);
+  void *ws = nullptr;
+  B200_TRY(ws_get(ctx, v_bytes + vec_bytes + s_bytes + align_up(sizeof(double) * (size_t)std::max<int64_t>(hist_cap, 1), 256), &ws));
+  T *V = (T *)ws;                                            // n x (restart+1), leading dimension n
+  T *Ax = (T *)((char *)ws + v_bytes);
+  GmScal *s = (GmScal *)((char *)Ax + vec_bytes);
+  double *d_hist = (double *)((char *)s + s_bytes);
+  double *d_n = ctx->d_scalars + 200;
+  auto col = [&](int j) { return V + (int64_t)j * n; };
+  {
+    std::unique_ptr<GmScal> h(new GmScal);
+    memset(h.get(), 0, sizeof(GmScal));
+    for (int i = 0; i < kGmLdh; ++i) h->nullvec[i] = 1.0;                 // ones(T, order+1) :27
+    h->accumulator = h->current = h->beta_res = h->beta = 1.0;
+    h->abstol = o->abstol;
+    h->reltol = reltol;
+    h->maxiter = maxiter;
+    h->hist = hist_cap > 0 ? d_hist : nullptr;
+    h->hist_cap = hist_cap;
+    h->k = 1;
+    h->restart = restart;
+    h->first = 1;
+    B200_CUDA(cudaMemcpyAsync(s, h.get(), sizeof(GmScal), cudaMemcpyHostToDevice, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));                        // h goes out of scope
+  }
+  B200_CUDA(cudaMemsetAsync(V, 0, sizeof(T) * (size_t)n * (restart + 1), ctx->stream));   // zeros(T, n, order+1) :13
+
+  // init! (:235-255) with beta, tol and the first stopping test formed on the device
+  auto init = [&](bool zero, int clear_mask) -> int {
+    T *v0 = col(0);
+    B200_TRY(copy(ctx, n, b, v0, dt));                                   // :241
+    if (!zero) {
+      B200_TRY(spmv(ctx, A, x, Ax));                                     // :245
+      B200_TRY(axpby(ctx, n, -1.0, Ax, 1.0, v0, dt));                    // :246
+    }
+    if (pl) B200_TRY(jacobi_ldiv(ctx, n, pl, v0, v0, dt));               // :249
+    B200_TRY(dot_dev(ctx, n, v0, v0, dt, d_n));                          // :252
+    k_gm_set_beta<<<1, 1, 0, ctx->stream>>>(s, d_n, clear_mask);         // :126-133 / :96-99
+    ctx->launches++;
+    B200_TRY(scale_dev<T>(ctx, v0, n, d_n));                             // :253
+    return B200_OK;
+  };
+  const int kGate = GM_FIN | GM_DONE;
+  // expand! (:285-304); k 1-based: V[:, k+1] = Pl \ (A (Pr \ V[:, k])).  The product is gated, the cheap vector passes are not
+  auto expand = [&](int k) -> int {
+    T *next = col(k), *cur = col(k - 1);
+    if (!pr) {
+      {
+        ProfScope prof(ctx, 0);
+        B200_TRY(spmv_gated(ctx, A, cur, next, &s->flags, kGate));       // :287/:293
+        ctx->launches++;
+      }
+      if (pl) B200_TRY(jacobi_ldiv(ctx, n, pl, next, next, dt));         // :294
+    } else {
+      B200_TRY(jacobi_ldiv(ctx, n, pr, cur, next, dt));                  // :300
+      B200_TRY(spmv_gated(ctx, A, next, Ax, &s->flags, kGate));          // :301
+      ctx->launches++;
+      B200_TRY(copy(ctx, n, Ax, next, dt));                              // :302
+      if (pl) B200_TRY(jacobi_ldiv(ctx, n, pl, next, next, dt));         // :303
+    }
+    return B200_OK;
+  };
+  struct Tail { double current, tol; long long iteration, n_hist; int k, m, flags; } t;
+  auto read_tail = [&]() -> int {
+    // the scalars the host steers by; one small copy each, one synchronisation
+    B200_CUDA(cudaMemcpyAsync(&ctx->h_scalars[0], &s->current, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(&ctx->h_scalars[1], &s->tol, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(&ctx->h_scalars[2], &s->iteration, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(&ctx->h_scalars[3], &s->n_hist, sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(&ctx->h_scalars[4], &s->k, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));   // k, restart, m, flags
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    t.current = ctx->h_scalars[0];
+    t.tol = ctx->h_scalars[1];
+    memcpy(&t.iteration, &ctx->h_scalars[2], sizeof(long long));
+    memcpy(&t.n_hist, &ctx->h_scalars[3], sizeof(long long));
+    int q[4];
+    memcpy(q, &ctx->h_scalars[4], sizeof(q));
+    t.k = q[0];
+    t.m = q[2];
+    t.flags = q[3];
+    return B200_OK;
+  };
+
+  int64_t mv_products = o->initially_zero ? 1 : 0;                        // :122 (sic)
+  B200_TRY(init(o->initially_zero != 0, 0));                              // :126
+  B200_TRY(read_tail());
+  while (!(t.flags & GM_DONE)) {                                          // :59
+    const int64_t before = t.iteration;
+    const int64_t left = maxiter - t.iteration;
+    const int kc = (int)std::min<int64_t>(restart, left);                 // the cycle closes at the latest after kc steps
+    for (int k = 1; k <= kc; ++k) {
+      B200_TRY(expand(k));                                                // :63
+      B200_TRY(orth_fused_launch<T>(ctx, V, n, k, col(k), n, dgks, s, 1, kGate));   // :68-73 + the scalar part of the step
+    }
+    B200_TRY(read_tail());
+    mv_products += t.iteration - before;                                  // :65, for the steps that really ran
+    B200_REQUIRE(t.flags & (GM_FIN | GM_DONE), "internal: GMRES cycle did not close (flags=%d)", t.flags);
+    if (t.flags & GM_FIN) {
+      const int m = t.m;                                                  // update_solution! :273-283 with y = s->rhs
+      if (m > 0) {
+        if (!pr) {
+          B200_TRY(block_axpy<T>(ctx, V, n, m, s->rhs, 1.0, x, x, n, nullptr));       // :275
+        } else {
+          B200_TRY(fill(ctx, n, 0.0, Ax, dt));
+          B200_TRY(block_axpy<T>(ctx, V, n, m, s->rhs, 1.0, Ax, Ax, n, nullptr));     // :280
+          B200_TRY(jacobi_ldiv(ctx, n, pr, Ax, Ax, dt));                               // :281
+          B200_TRY(axpby(ctx, n, 1.0, Ax, 1.0, x, dt));                                // :282
+        }
+      }
+      if (t.flags & GM_REINIT) {                                          // :93 (sic: tested with the old iteration count)
+        B200_TRY(init(false, GM_FIN | GM_REINIT));                        // :96-99
+        mv_products += 1;                                                 // :101
+      }
+    }
+    if (t.flags & GM_BREAKDOWN) break;
+  }
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int64_t n_hist = std::min<int64_t>(t.n_hist, hist_cap);
+  if (resnorm_host && n_hist > 0) {
+    B200_CUDA(cudaMemcpyAsync(resnorm_host, d_hist, sizeof(double) * (size_t)n_hist, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (res) {
+    res->iters = t.iteration;
+    res->mvps = mv_products;                                              // history.mvps = iterable.mv_products :210
+    res->isconverged = t.current <= t.tol;                                // :218
+    res->status = (t.flags & GM_BREAKDOWN) ? B200_ERR_BREAKDOWN : 0;
+    res->tol = t.tol;
+    res->residual = t.current;
+    res->n_resnorm = n_hist;
+  }
+  return B200_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -554,6 +911,10 @@ int b200_gmres_solve(b200_ctx *ctx, const b200_csr *A, void *x_dev, const void *
   B200_REQUIRE(opts->Pr.kind == B200_PREC_IDENTITY || (opts->Pr.kind == B200_PREC_JACOBI && opts->Pr.diag),
                "unsupported preconditioner Pr");
   B200_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->world == 1 && ctx->opt_orth_fused && opts->orth_meth != B200_ORTH_MGS && A->m_local > 0)
+    return A->dtype == B200_F64
+               ? gmres_impl_fused<double>(ctx, A, (double *)x_dev, (const double *)b_dev, opts, res, resnorm_host, resnorm_cap)
+               : gmres_impl_fused<float>(ctx, A, (float *)x_dev, (const float *)b_dev, opts, res, resnorm_host, resnorm_cap);
   return A->dtype == B200_F64
              ? gmres_impl<double>(ctx, A, (double *)x_dev, (const double *)b_dev, opts, res, resnorm_host, resnorm_cap)
              : gmres_impl<float>(ctx, A, (float *)x_dev, (const float *)b_dev, opts, res, resnorm_host, resnorm_cap);

@@ -27,6 +27,7 @@
 #include "blas1.cuh"
 #include "dense_small.h"
 #include "spmv_stream.cuh"
+#include "lobpcg_gram_umma.cuh"
 
 using namespace b200;
 
@@ -937,7 +938,14 @@ struct Lobpcg {
       B200_SMEM_ATTR_ONCE(ctx, sizeof(RrSmem<1>), k_gram_rr_tc<1>);
       {
         ProfScope prof(ctx, 1);
-        if (with_p)
+        if (with_p && ctx->opt_lobpcg_mma == 1) {
+          // steady state: the eight products on tcgen05 (lobpcg_gram_umma.cuh); same output format
+          UmArgs ua;
+          for (int b = 0; b < 5; ++b) ua.blk[b] = ra.blk[b];
+          ua.n = n;
+          B200_SMEM_ATTR_ONCE(ctx, sizeof(UmSmem), k_gram_umma);
+          k_gram_umma<<<grid_gram, kUmThreads, sizeof(UmSmem), ctx->stream>>>(ua, gram_partials, ctx->red.ticket, d_gram);
+        } else if (with_p)
           k_gram_rr_tc<2><<<grid_gram, kRrThreads, sizeof(RrSmem<2>), ctx->stream>>>(ra, gram_partials,
                                                                                      ctx->red.ticket, d_gram);
         else
@@ -1329,6 +1337,35 @@ int b200_lobpcg_solve_constrained(b200_ctx *ctx, const b200_csr *A, void *X_dev,
   return A->dtype == B200_F64
              ? lobpcg_impl<double>(ctx, A, (double *)X_dev, ldx, opts, C, res, lambda_host, resnorm_host)
              : lobpcg_impl<float>(ctx, A, (float *)X_dev, ldx, opts, C, res, lambda_host, resnorm_host);
+}
+
+/* TEST HOOK (tests/test_gpu_lobpcg.py): the eight Rayleigh-Ritz Gram products of five row-major n x 16 fp32 blocks
+ * (X, R, AR, P, AP: device pointers) through one of the engine's kernels -- variant 1: tcgen05 (k_gram_umma),
+ * variant 2: legacy mma.sync (k_gram_rr_tc<2>).  out_host: 8 x 256 doubles, out[p * 256 + i * 16 + j]. */
+int b200_debug_lobpcg_gram_rr(b200_ctx *ctx, const void *const *blk_dev, int64_t n, int variant, double *out_host) {
+  B200_REQUIRE(ctx && blk_dev && out_host && n >= 0 && (variant == 1 || variant == 2), "bad arguments");
+  B200_CUDA(cudaSetDevice(ctx->device));
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (n + RC - 1) / RC));
+  DevBuf part, outd;
+  B200_TRY(part.alloc(sizeof(double) * (size_t)grid * 8 * 256));
+  B200_TRY(outd.alloc(sizeof(double) * 8 * 256));
+  if (variant == 1) {
+    UmArgs ua;
+    for (int b = 0; b < 5; ++b) ua.blk[b] = (const float *)blk_dev[b];
+    ua.n = n;
+    B200_SMEM_ATTR_ONCE(ctx, sizeof(UmSmem), k_gram_umma);
+    k_gram_umma<<<grid, kUmThreads, sizeof(UmSmem), ctx->stream>>>(ua, (double *)part.p, ctx->red.ticket, (double *)outd.p);
+  } else {
+    RrArgs ra;
+    for (int b = 0; b < 5; ++b) ra.blk[b] = (const float *)blk_dev[b];
+    ra.n = n;
+    B200_SMEM_ATTR_ONCE(ctx, sizeof(RrSmem<2>), k_gram_rr_tc<2>);
+    k_gram_rr_tc<2><<<grid, kRrThreads, sizeof(RrSmem<2>), ctx->stream>>>(ra, (double *)part.p, ctx->red.ticket, (double *)outd.p);
+  }
+  B200_LAUNCH_CHECK(ctx);
+  B200_CUDA(cudaMemcpyAsync(out_host, outd.p, sizeof(double) * 8 * 256, cudaMemcpyDeviceToHost, ctx->stream));
+  B200_CUDA(cudaStreamSynchronize(ctx->stream));
+  return B200_OK;
 }
 
 int b200_dense_sygv_host(int n, const double *A, const double *B, double *w, double *Z) {

@@ -12,7 +12,8 @@ constexpr int kThreads = 256;
 template <typename T, int LPR>
 __global__ void __launch_bounds__(kThreads) k_spmv(const int *__restrict__ rowptr, const int *__restrict__ colind,
                                                    const T *__restrict__ vals, XView<T> xv, int64_t m,
-                                                   T *__restrict__ y) {
+                                                   T *__restrict__ y, const int *__restrict__ gate, int gate_mask) {
+  if (gate && (*gate & gate_mask)) return;   // speculatively enqueued launch whose solver has already stopped
   constexpr int ROWS = kThreads / LPR;
   const int sub = threadIdx.x % LPR;
   const int rib = threadIdx.x / LPR;
@@ -73,14 +74,15 @@ struct StoreEpi {
 template <typename T, int LPR>
 __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
     k_spmv_stream(const int *__restrict__ rowptr, const int *__restrict__ colind, const T *__restrict__ vals,
-                  XView<T> xv, int64_t m, T *__restrict__ y) {
+                  XView<T> xv, int64_t m, T *__restrict__ y, const int *__restrict__ gate, int gate_mask) {
+  if (gate && (*gate & gate_mask)) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   StoreEpi<T> epi{y};
   spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, m, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw));
 }
 
 template <typename T>
-int launch_spmv_stream(b200_ctx *ctx, const b200_csr *A, const void *x, void *y) {
+int launch_spmv_stream(b200_ctx *ctx, const b200_csr *A, const void *x, void *y, const int *gate, int gate_mask) {
   XView<T> xv = make_xview<T>(A, x);
   const int grid = stream_grid_size(ctx, A);
   const size_t smem = sizeof(StreamSmem<T>);
@@ -88,7 +90,7 @@ int launch_spmv_stream(b200_ctx *ctx, const b200_csr *A, const void *x, void *y)
   do {                                                                                                            \
     B200_SMEM_ATTR_ONCE(ctx, smem, k_spmv_stream<T, L>);                                                          \
     k_spmv_stream<T, L><<<grid, kStreamThreads, smem, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals,   \
-                                                                     xv, A->m_local, (T *)y);                    \
+                                                                     xv, A->m_local, (T *)y, gate, gate_mask);  \
   } while (0)
   switch (A->stream_lpr) {
     case 1: LAUNCH(1); break;
@@ -104,16 +106,16 @@ int launch_spmv_stream(b200_ctx *ctx, const b200_csr *A, const void *x, void *y)
 }
 
 template <typename T>
-int launch_spmv(b200_ctx *ctx, const b200_csr *A, const void *x, void *y) {
+int launch_spmv(b200_ctx *ctx, const b200_csr *A, const void *x, void *y, const int *gate = nullptr, int gate_mask = 0) {
   if (A->m_local == 0) return B200_OK;
-  if (use_stream(ctx, A)) return launch_spmv_stream<T>(ctx, A, x, y);
+  if (use_stream(ctx, A)) return launch_spmv_stream<T>(ctx, A, x, y, gate, gate_mask);
   XView<T> xv = make_xview<T>(A, x);
   const int lpr = pick_lpr(A->avg_row_nnz);
   const int rows = kThreads / lpr;
   const int grid = stream_grid(ctx, A->m_local, rows, 8);
 #define LAUNCH(L)                                                                                             \
   k_spmv<T, L><<<grid, kThreads, 0, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals, xv, A->m_local, \
-                                                   (T *)y)
+                                                   (T *)y, gate, gate_mask)
   switch (lpr) {
     case 2: LAUNCH(2); break;
     case 4: LAUNCH(4); break;
@@ -173,6 +175,12 @@ namespace b200 {
 int spmv(b200_ctx *ctx, const b200_csr *A, const void *x, void *y) {
   B200_TRY(halo_exchange(ctx, A, x));
   return A->dtype == B200_F64 ? launch_spmv<double>(ctx, A, x, y) : launch_spmv<float>(ctx, A, x, y);
+}
+// single-GPU only: y = A x unless (*gate & gate_mask) != 0 on the device when the kernel starts (launches that a solver
+// enqueues ahead of its own device-side stopping test)
+int spmv_gated(b200_ctx *ctx, const b200_csr *A, const void *x, void *y, const int *gate, int gate_mask) {
+  return A->dtype == B200_F64 ? launch_spmv<double>(ctx, A, x, y, gate, gate_mask)
+                              : launch_spmv<float>(ctx, A, x, y, gate, gate_mask);
 }
 }  // namespace b200
 

@@ -135,16 +135,72 @@ def test_lobpcg_fp32_tensor_pipe_vs_simt(isb, oracle, bs):
         ro = oracle.lobpcg(O, False, X0, maxiter=6, fixed_iterations=True)
         out = {}
         try:
-            for mode in (1, 0):
+            for mode in (1, 2, 0):       # 1: tcgen05 Gram (TMEM accumulators), 2: legacy mma.sync Gram, 0: SIMT
                 assert L.b200_ctx_set_option(ctx._h, b"lobpcg_mma", mode) == 0
                 out[mode] = isb.lobpcg(A, False, X0, maxiter=6, _fixed_iterations=True)
         finally:
             L.b200_ctx_set_option(ctx._h, b"lobpcg_mma", 1)
-        for mode in (1, 0):
+        for mode in (1, 2, 0):
             np.testing.assert_allclose(out[mode].lam, ro.lam, rtol=1e-4)
             np.testing.assert_allclose(out[mode].residual_norms, ro.residual_norms, rtol=5e-3)
         np.testing.assert_allclose(out[1].lam, out[0].lam, rtol=2e-5)
+        np.testing.assert_allclose(out[1].lam, out[2].lam, rtol=2e-5)
         np.testing.assert_allclose(out[1].X.T @ out[1].X, np.eye(bs), atol=2e-5)
+
+
+PRODUCTS = [(0, 2), (0, 1), (1, 2), (0, 4), (0, 3), (1, 3), (2, 3), (3, 4)]     # X'AR X'R R'AR X'AP X'P R'P AR'P P'AP
+
+
+def _gram_rr(isb, blocks, variant):
+    """the engine's Rayleigh-Ritz Gram kernel on five row-major n x 16 fp32 blocks (C-ABI test hook)."""
+    import ctypes as C
+    ctx = isb.default_context()
+    n = blocks[0].shape[0]
+    devs = [isb.DeviceArray.from_numpy(ctx, np.ascontiguousarray(b, dtype=np.float32).reshape(-1)) for b in blocks]
+    ptrs = (C.c_void_p * 5)(*[d.ptr for d in devs])
+    out = np.zeros(8 * 256)
+    isb._lib.check(isb.lib().b200_debug_lobpcg_gram_rr(ctx._h, ptrs, n, variant, out.ctypes.data_as(C.c_void_p)))
+    return out.reshape(8, 16, 16)
+
+
+@pytest.mark.parametrize("n", [8, 64, 200, 64 * 148 * 9 + 37])
+def test_gram_rr_tcgen05_kernel_vs_fp64(isb, n):
+    """k_gram_umma (tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators) against fp64 numpy Gram products and against
+    the legacy mma.sync kernel: one MMA (n = 8), one stage, a ragged tail, and several accumulator hand-overs per CTA.
+    fp32-level accuracy: 2e-6 of ||a_i|| ||b_j||."""
+    rng = np.random.default_rng(SEED + n)
+    blocks = [rng.standard_normal((n, 16)).astype(np.float32) * (1.0 + b) for b in range(5)]
+    got = {v: _gram_rr(isb, blocks, v) for v in (1, 2)}
+    B64 = [b.astype(np.float64) for b in blocks]
+    for p, (l, r) in enumerate(PRODUCTS):
+        ref = B64[l].T @ B64[r]
+        scale = np.linalg.norm(B64[l], axis=0)[:, None] * np.linalg.norm(B64[r], axis=0)[None, :]
+        for v in (1, 2):
+            err = float(np.max(np.abs(got[v][p] - ref) / scale))
+            assert err <= 2e-6, (n, p, v, err, got[v][p][:2, :4], ref[:2, :4])
+
+
+def test_lobpcg_fp32_tcgen05_gram_many_stages(isb, oracle):
+    """n = 64^3: every CTA of the tcgen05 Gram kernel runs ~28 stages of 64 rows, i.e. several accumulator hand-overs
+    between the two TMEM accumulators (lobpcg_gram_umma.cuh: kUmDrain = 8 stages per group).  Against the oracle and
+    against the legacy mma.sync Gram kernel, 5 steps."""
+    L = isb.lib()
+    ctx = isb.default_context()
+    N, bs = 64, 16
+    O = oracle.laplace_matrix(np.float32, N, 3)
+    A = _op(isb, O)
+    X0 = np.random.default_rng(SEED).random((O.n, bs)).astype(np.float32)
+    ro = oracle.lobpcg(O, False, X0, maxiter=5, fixed_iterations=True)
+    out = {}
+    try:
+        for mode in (1, 2):
+            assert L.b200_ctx_set_option(ctx._h, b"lobpcg_mma", mode) == 0
+            out[mode] = isb.lobpcg(A, False, X0, maxiter=5, _fixed_iterations=True)
+    finally:
+        L.b200_ctx_set_option(ctx._h, b"lobpcg_mma", 1)
+    for mode in (1, 2):
+        np.testing.assert_allclose(out[mode].lam, ro.lam, rtol=1e-4)
+    np.testing.assert_allclose(out[1].lam, out[2].lam, rtol=2e-5)
 
 
 def test_lobpcg_256cubed_fp32_properties(isb):

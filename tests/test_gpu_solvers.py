@@ -152,6 +152,33 @@ def test_gmres_advection_vs_oracle(isb, oracle, orth):
     assert np.all(np.diff(h["resnorm"]) <= 1e-12 * h["resnorm"][0])        # test/gmres.jl:25
 
 
+@pytest.mark.parametrize("orth", ["cgs", "dgks"])
+def test_gmres_device_resident_cycle_equals_host_driven_engine(isb, oracle, orth):
+    """option orth_fused: 1 (default) = one cooperative launch per orthogonalisation, H / residual recurrence / stopping
+    test on the device, one host synchronisation per restart cycle; 0 = three kernels per orthogonalisation with the
+    recurrences on the host (the round-1 engine).  Same arithmetic in the same order: histories agree to rounding of the
+    grid-level summation order; counts are identical.  Convergence in the MIDDLE of a cycle exercises the gated
+    (speculatively enqueued) launches behind the stopping point; an odd n the one-row-per-thread instantiation."""
+    L = isb.lib()
+    ctx = isb.default_context()
+    for N, kw in ((16, dict(maxiter=75, reltol=0.0)), (12, dict(maxiter=600, reltol=1e-6)), (11, dict(maxiter=47, reltol=1e-9))):
+        M, O, A, b = _advection(isb, oracle, N)
+        out = {}
+        try:
+            for mode in (1, 0):
+                assert L.b200_ctx_set_option(ctx._h, b"orth_fused", mode) == 0
+                out[mode] = isb.gmres(A, b, restart=20, orth_meth=orth, log=True, **kw)
+        finally:
+            L.b200_ctx_set_option(ctx._h, b"orth_fused", 1)
+        (x1, h1), (x0, h0) = out[1], out[0]
+        assert (h1.niters, h1.mvps, h1.isconverged) == (h0.niters, h0.mvps, h0.isconverged)
+        assert len(h1["resnorm"]) == len(h0["resnorm"]) == h1.niters
+        assert relerr(h1["resnorm"], h0["resnorm"]) <= 1e-10 and relerr(x1, x0) <= 1e-9
+        xo, ho = oracle.gmres(O, b, restart=20, orth_meth=orth, log=True, **kw)
+        assert (h1.niters, h1.mvps, h1.isconverged) == (ho.niters, ho.mvps, ho.isconverged)
+        assert relerr(h1["resnorm"], ho["resnorm"]) <= 1e-8
+
+
 def test_gmres_converges_with_true_residual_and_jacobi(isb, oracle):
     M, O, A, b = _advection(isb, oracle, 12)
     x, h = isb.gmres(A, b, restart=30, orth_meth="dgks", log=True, maxiter=600, reltol=1e-10)
