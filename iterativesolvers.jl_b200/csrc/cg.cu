@@ -106,16 +106,15 @@ __device__ __forceinline__ void cg_apply(int kind, CgScal *s, double total, doub
   }
 }
 
-// called by the single thread that holds the grid-wide sum of this GPU
+// called by the FIRST WARP of the block that holds the grid-wide sum of this GPU (lane 0 has it in `total`)
 __device__ __forceinline__ void cg_finish(int kind, CgScal *s, double total, double *hist, const Comm &cm) {
+  if (cm.mode == COMM_PEER) total = peer_allreduce_sum_warp(cm.pv, total, cm.seq);   // lane q <-> rank q
+  if ((threadIdx.x & 31u) != 0) return;
   if (cm.mode == COMM_NCCL) {   // the host enqueues ncclAllReduce(&s->sum) + k_cg_scalar next
     s->sum = total;
     return;
   }
-  if (cm.mode == COMM_PEER) {
-    peer_allreduce_sum(cm.pv, &total, 1, cm.seq);
-    if (cm.pv.hdr[cm.pv.rank]->error) s->comm_error = 1;
-  }
+  if (cm.mode == COMM_PEER && cm.pv.hdr[cm.pv.rank]->error) s->comm_error = 1;
   cg_apply(kind, s, total, hist);
 }
 
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_init(const T *__restrict__ b, c
   }
   acc = block_sum<kThreads>(acc, smem);
   double total;
-  if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x == 0)
+  if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x < 32)
     cg_finish(FIN_INIT, s, total, nullptr, cm);
 }
 
@@ -233,7 +232,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_spmv_dot(const int *__restrict_
   }
   acc = block_sum<kThreads>(acc, smem);
   double total;
-  if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x == 0)
+  if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x < 32)
     cg_finish(FIN_DOT, s, total, nullptr, cm);
 }
 
@@ -262,7 +261,7 @@ __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
   spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, m, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw), cm.rev != 0);
   const double acc = block_sum<kStreamThreads>(epi.acc, red);
   double total;
-  if (grid_reduce_finish<kStreamThreads>(acc, partials, ticket, red, &total) && threadIdx.x == 0)
+  if (grid_reduce_finish<kStreamThreads>(acc, partials, ticket, red, &total) && threadIdx.x < 32)
     cg_finish(FIN_DOT, s, total, nullptr, cm);
 }
 
@@ -285,7 +284,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_update_r(T *__restrict__ r, con
   }
   acc = block_sum<kThreads>(acc, smem);
   double total;
-  if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x == 0)
+  if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x < 32)
     cg_finish(pcg ? FIN_NORM_PCG : FIN_NORM, s, total, hist, cm);
 }
 
@@ -305,7 +304,7 @@ __global__ void __launch_bounds__(kThreads) k_pcg_precond(const T *__restrict__ 
   }
   acc = block_sum<kThreads>(acc, smem);
   double total;
-  if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x == 0)
+  if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x < 32)
     cg_finish(FIN_RHO, s, total, nullptr, cm);
 }
 

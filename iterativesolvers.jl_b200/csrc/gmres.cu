@@ -231,8 +231,23 @@ __global__ void k_hessenberg_ldiv(double *__restrict__ H, int ldh, int m, double
 // the device-side stopping test.
 namespace cgx = cooperative_groups;
 
+// the scalar sections run in ONE thread: kept out of line so that their locals do not set the register count (and with it
+// the occupancy) of the streaming phases
+__device__ __noinline__ void orth_scalar_section(GmScal *s, int k, int dgks, int round, int do_step, double nrm2) {
+  s->nrm2 = nrm2;
+  s->nrm = sqrt(nrm2);
+  s->k = k;
+  if (dgks) {
+    if (round == 0) gm_dgks_first(s);      // projection_size = norm(h); nrm < eta * projection_size ?  :20-26
+    else gm_dgks_next(s);                  // h .+= correction; projection_size = norm(correction)    :28-31
+  } else {
+    s->reorth = 0;
+  }
+  if (!s->reorth && do_step) gm_step(s);   // src/gmres.jl:68-104
+}
+
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kThreads) k_orth_fused(const T *__restrict__ V, int64_t ld, int k, T *w, int64_t n,
+__global__ void __launch_bounds__(kThreads, 2) k_orth_fused(const T *__restrict__ V, int64_t ld, int k, T *w, int64_t n,
                                                          int dgks, double *partials, GmScal *s, int do_step,
                                                          int gate_mask) {
   if (s->flags & gate_mask) return;             // uniform over the grid: nobody reaches a grid.sync
@@ -334,16 +349,7 @@ __global__ void __launch_bounds__(kThreads) k_orth_fused(const T *__restrict__ V
       for (unsigned int b = threadIdx.x; b < gridDim.x; b += kThreads) a += __ldcg(&partials[(size_t)b * kMaxReduceWidth]);
       a = block_sum<kThreads>(a, sred);
       if (threadIdx.x == 0) {
-        s->nrm2 = a;
-        s->nrm = sqrt(a);
-        s->k = k;
-        if (dgks) {
-          if (round == 0) gm_dgks_first(s);      // projection_size = norm(h); nrm < eta * projection_size ?  :20-26
-          else gm_dgks_next(s);                  // h .+= correction; projection_size = norm(correction)    :28-31
-        } else {
-          s->reorth = 0;
-        }
-        if (!s->reorth && do_step) gm_step(s);   // src/gmres.jl:68-104
+        orth_scalar_section(s, k, dgks, round, do_step, a);
         __threadfence();
       }
     }

@@ -1343,16 +1343,18 @@ int b200_lobpcg_solve_constrained(b200_ctx *ctx, const b200_csr *A, void *X_dev,
  * (X, R, AR, P, AP: device pointers) through one of the engine's kernels -- variant 1: tcgen05 (k_gram_umma),
  * variant 2: legacy mma.sync (k_gram_rr_tc<2>).  out_host: 8 x 256 doubles, out[p * 256 + i * 16 + j]. */
 int b200_debug_lobpcg_gram_rr(b200_ctx *ctx, const void *const *blk_dev, int64_t n, int variant, double *out_host) {
-  B200_REQUIRE(ctx && blk_dev && out_host && n >= 0 && (variant == 1 || variant == 2), "bad arguments");
+  B200_REQUIRE(ctx && blk_dev && out_host && n >= 0 && (variant == 1 || variant == 2 || (variant > 100 && variant < 1000)),
+               "bad arguments");
   B200_CUDA(cudaSetDevice(ctx->device));
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctx->sm_count, (n + RC - 1) / RC));
   DevBuf part, outd;
   B200_TRY(part.alloc(sizeof(double) * (size_t)grid * 8 * 256));
   B200_TRY(outd.alloc(sizeof(double) * 8 * 256));
-  if (variant == 1) {
+  if (variant != 2) {
     UmArgs ua;
     for (int b = 0; b < 5; ++b) ua.blk[b] = (const float *)blk_dev[b];
     ua.n = n;
+    if (variant > 100) ua.drain = variant - 100;    // variant 100 + d: tcgen05 kernel with d stages per accumulator hand-over
     B200_SMEM_ATTR_ONCE(ctx, sizeof(UmSmem), k_gram_umma);
     k_gram_umma<<<grid, kUmThreads, sizeof(UmSmem), ctx->stream>>>(ua, (double *)part.p, ctx->red.ticket, (double *)outd.p);
   } else {

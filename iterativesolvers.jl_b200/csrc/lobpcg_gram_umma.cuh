@@ -7,8 +7,9 @@
 //
 // One MMA per 8 rows.  Every fp32 value a is split a = a_hi + a_lo (both TF32, "3xTF32"); the 8-row slice of the five
 // blocks becomes ONE shared-memory operand of 160 columns  [X_h X_l R_h R_l AR_h AR_l P_h P_l AP_h AP_l]  stored
-// MN-major (K = the 8 rows), of which the MMA reads columns 0..127 as A (left factors X, R, AR, P) and columns 32..159
-// as B (right factors R, AR, P, AP) -- the same bytes serve both operands:
+// K-major (K = the 8 rows; measured with tools/umma_probe.cu: kind::tf32 returns zeros for MN-major operands without
+// swizzle, so the converter warps transpose 4 x 4 register tiles), of which the MMA reads columns 0..127 as A (left
+// factors X, R, AR, P) and columns 32..159 as B (right factors R, AR, P, AP) -- the same bytes serve both operands:
 //
 //        D (128 x 128, TMEM, fp32)  +=  A^T (128 x 8)  *  B (8 x 128)
 //
@@ -17,11 +18,13 @@
 // (B300_MICROARCH "tcgen05 floor"), against 108 cycles of HBM time for the slice (2.5 KB at 23 B/clk/SM): the
 // pass is memory-bound instead of pinned at the legacy mma.sync pipe's ceiling (r1: 0.50 of the HBM peak).
 //
-// Warp roles (448 threads, one CTA per SM, persistent over 64-row stages):
+// Warp roles (512 threads, one CTA per SM, persistent over 64-row stages):
 //   warp 4      producer: cp.async.bulk of the five 64-row block slices into a 4-deep raw ring (mbarrier tx-count)
-//   warps 6-13  converters: raw fp32 -> hi / lo in the UMMA canonical layout (no swizzle, MN-major: a core matrix is
-//               8 K-rows x 16 B; consecutive cores 160 B apart so that both the 128-bit loads of the raw tile and the
-//               128-bit stores of the operand are bank-conflict free), fence.proxy.async, arrive on op_full
+//   warps 6-15  converters: a thread takes 4 rows x 4 columns of one block (4 128-bit loads), splits into hi / lo and
+//               stores the transposed tile in the UMMA canonical K-major layout without swizzle (a core matrix is 8
+//               columns x 16 B = 4 consecutive rows; 8-column groups 160 B apart, the second K half 3216 B behind the
+//               first: with these strides the 128-bit loads and stores are bank-conflict free), fence.proxy.async,
+//               arrive on op_full
 //   warp 5      one thread issues the tcgen05.mma's (8 per stage); tcgen05.commit releases the operand stage and,
 //               every kUmDrain stages, hands the accumulator to the epilogue; two accumulators (2 x 128 TMEM columns)
 //   warps 0-3   epilogue: tcgen05.ld of the needed column blocks (warp w owns TMEM lanes 32w..32w+31 = left block w),
@@ -38,19 +41,20 @@ constexpr int kUmRows = 64;                               // rows per stage = 8 
 constexpr int kUmSteps = kUmRows / 8;
 constexpr int kUmRawStages = 4;
 constexpr int kUmOpStages = 2;
-constexpr int kUmCoreStride = 160;                        // bytes between consecutive 4-column core matrices (SBO)
-constexpr int kUmCores = 40;                              // 5 blocks x (hi, lo) x 4 column quads
-constexpr int kUmStepBytes = kUmCores * kUmCoreStride;    // 6400 B: the operand of one MMA
-constexpr int kUmOpBytes = kUmSteps * kUmStepBytes;       // 51200 B per operand stage
+constexpr int kUmGroupStride = 160;                       // SBO: bytes between consecutive 8-column groups (128 B of data)
+constexpr int kUmGroups = 20;                             // 5 blocks x (hi, lo) x 2 groups of 8 columns
+constexpr int kUmHalfStride = kUmGroups * kUmGroupStride + 16;   // LBO: rows 4..7 of a step start 3216 B behind rows 0..3
+constexpr int kUmStepBytes = 2 * kUmHalfStride;           // 6432 B: the operand of one MMA (K = 8 rows)
+constexpr int kUmOpBytes = kUmSteps * kUmStepBytes;       // 51456 B per operand stage
 constexpr int kUmDrain = 8;                               // stages per accumulator hand-over (512 rows, 64 MMAs)
-constexpr int kUmEpiWarps = 4, kUmConvWarps = 8;
+constexpr int kUmEpiWarps = 4, kUmConvWarps = 10;
 constexpr int kUmProducerWarp = 4, kUmMmaWarp = 5, kUmConvWarp0 = 6;
-constexpr int kUmThreads = (kUmConvWarp0 + kUmConvWarps) * 32;   // 448
+constexpr int kUmThreads = (kUmConvWarp0 + kUmConvWarps) * 32;   // 512
 constexpr int kUmTmemCols = 256;                          // two 128-column accumulators
 
 struct UmSmem {
   alignas(128) float raw[kUmRawStages][5][kUmRows * 16];  // 80 KB
-  alignas(128) unsigned char op[kUmOpStages][kUmOpBytes]; // 100 KB
+  alignas(128) unsigned char op[kUmOpStages][kUmOpBytes]; // 100.5 KB
   alignas(8) unsigned long long raw_full[kUmRawStages], raw_empty[kUmRawStages];
   alignas(8) unsigned long long op_full[kUmOpStages], op_empty[kUmOpStages];
   alignas(8) unsigned long long acc_full[2], acc_empty[2];
@@ -60,20 +64,21 @@ struct UmSmem {
 struct UmArgs {
   const float *blk[5];   // X, R, AR, P, AP
   int64_t n;
+  int drain = kUmDrain;  // stages per accumulator hand-over (tests vary it)
 };
 
 // instruction descriptor (cute::UMMA::InstrDescriptor bit layout): D = F32 [4,6) = 1, A = B = TF32 [7,10) = [10,13) = 2,
-// A and B MN-major (bits 15, 16), N >> 3 in [17,23), M >> 4 in [24,29)
-constexpr uint32_t kUmIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) |
-                              ((128u >> 4) << 24);
+// A and B K-major (bits 15, 16 clear), N >> 3 in [17,23), M >> 4 in [24,29)
+constexpr uint32_t kUmIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
 #ifdef __CUDACC__
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in [0,14), leading byte offset >> 4 in
-// [16,30) (between core matrices along K: unused, K = 8 is a single core), stride byte offset >> 4 in [32,46) (between
-// core matrices along M/N), version 1 in [46,48), layout type 0 = no swizzle in [61,64)
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major without swizzle: start address >> 4 in [0,14),
+// leading byte offset >> 4 in [16,30) (between the two core matrices along K: rows 0..3 / 4..7), stride byte offset >> 4
+// in [32,46) (between 8-column groups along M/N), version 1 in [46,48), layout type 0 = no swizzle in [61,64).
+// Element (column m, row k) of the operand: (m / 8) * SBO + (m % 8) * 16 + (k / 4) * LBO + (k % 4) * 4  (tools/umma_probe.cu)
 __device__ __forceinline__ uint64_t um_desc(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(128u >> 4) << 16) | ((uint64_t)(kUmCoreStride >> 4) << 32) |
-         (1ull << 46);
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(kUmHalfStride >> 4) << 16) |
+         ((uint64_t)(kUmGroupStride >> 4) << 32) | (1ull << 46);
 }
 __device__ __forceinline__ void um_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
   asm volatile(
@@ -147,7 +152,8 @@ __global__ void __launch_bounds__(kUmThreads, 1) k_gram_umma(UmArgs a, double *p
   const int64_t nchunks = (n + kUmRows - 1) / kUmRows;
   // stages this CTA processes: chunks blockIdx.x, blockIdx.x + gridDim.x, ...
   const int nst = (int)((nchunks > (int64_t)blockIdx.x) ? (nchunks - 1 - blockIdx.x) / gridDim.x + 1 : 0);
-  const int ngroups = (nst + kUmDrain - 1) / kUmDrain;
+  const int drain = a.drain;
+  const int ngroups = (nst + drain - 1) / drain;
 
   if (tid == 0) {
     for (int s = 0; s < kUmRawStages; ++s) {
@@ -203,8 +209,8 @@ __global__ void __launch_bounds__(kUmThreads, 1) k_gram_umma(UmArgs a, double *p
       for (int it = 0; it < nst; ++it) {
         const int t = it % kUmOpStages;
         const uint32_t pht = (uint32_t)((it / kUmOpStages) & 1);
-        const int g = it / kUmDrain, ab = g & 1;
-        if (it % kUmDrain == 0) {                       // a new accumulation group: the accumulator must be drained
+        const int g = it / drain, ab = g & 1;
+        if (it % drain == 0) {                       // a new accumulation group: the accumulator must be drained
           um_wait(&sm->acc_empty[ab], (uint32_t)((g >> 1) & 1) ^ 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
@@ -215,45 +221,61 @@ __global__ void __launch_bounds__(kUmThreads, 1) k_gram_umma(UmArgs a, double *p
 #pragma unroll
         for (int ks = 0; ks < kUmSteps; ++ks) {
           const uint32_t o = base + (uint32_t)(ks * kUmStepBytes);
-          um_mma(d, um_desc(o), um_desc(o + 8u * kUmCoreStride), (it % kUmDrain != 0 || ks != 0) ? 1u : 0u);
+          um_mma(d, um_desc(o), um_desc(o + 4u * kUmGroupStride), (it % drain != 0 || ks != 0) ? 1u : 0u);   // B: columns 32..159
         }
         um_commit(&sm->op_empty[t]);                    // arrives when these MMAs have read the operand stage
-        if (it % kUmDrain == kUmDrain - 1 || it == nst - 1) um_commit(&sm->acc_full[ab]);
+        if (it % drain == drain - 1 || it == nst - 1) um_commit(&sm->acc_full[ab]);
       }
     }
   } else if (warp >= kUmConvWarp0) {
     // ------------------------------------------------------------------ converters
-    const int ct = tid - kUmConvWarp0 * 32;             // 0..255: row = ct / 4 (0..63), column quad = ct % 4
-    const int row = ct >> 2, quad = ct & 3;
-    const int ks = row >> 3, kk = row & 7;
-    const int cw = warp - kUmConvWarp0;
-    (void)cw;
+    // thread <-> (block b, 8-row step ks, row half g, column quad q): rows ks*8 + g*4 .. +3, columns q*4 .. +3 of block b
+    const int ct = tid - kUmConvWarp0 * 32;             // 0..319
+    const int b = ct >> 6, ks = (ct >> 3) & 7, g = (ct >> 2) & 1, q = ct & 3;
+    const int row0 = ks * 8 + g * 4;
+    // hi tile of columns q*4.. of block b: operand columns b*32 + q*4 + c -> group b*4 + q/2, row-in-group (q%2)*4 + c;
+    // the lo tile sits 16 columns = 2 groups further
+    const int dst_off = ks * kUmStepBytes + g * kUmHalfStride + (b * 4 + (q >> 1)) * kUmGroupStride + (q & 1) * 64;
     for (int it = 0; it < nst; ++it) {
       const int s = it % kUmRawStages, t = it % kUmOpStages;
       const uint32_t phs = (uint32_t)((it / kUmRawStages) & 1), pht = (uint32_t)((it / kUmOpStages) & 1);
       const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kUmRows;
-      const bool valid = r0 + row < n;
       um_wait(&sm->raw_full[s], phs);
-      float4 x[5];
+      // the two row halves of a quarter-warp read rows of opposite parity (g = 1 swaps its row pairs): no bank conflict
+      float4 v[4];
 #pragma unroll
-      for (int b = 0; b < 5; ++b) {
-        x[b] = *reinterpret_cast<const float4 *>(&sm->raw[s][b][row * 16 + quad * 4]);
-        if (!valid) x[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 4; ++j) {
+        const int jj = j ^ g;
+        v[j] = *reinterpret_cast<const float4 *>(&sm->raw[s][b][(row0 + jj) * 16 + q * 4]);
+        if (!(r0 + row0 + jj < n)) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      // hi / lo of the transposed 4 x 4 tile BEFORE the raw stage is released: the conversions consume the loaded
+      // registers, so every load has completed when lane 0 arrives on raw_empty.  (Releasing right after issuing the loads
+      // let the producer's next bulk copy overwrite the slice under loads still queued behind the operand stores of the
+      // other warps -- measured: wrong Gram blocks as soon as a CTA reuses a raw stage; tools/diag_gram_umma2.py.)
+      uint4 hi[4], lo[4];                               // [column]: its 4 consecutive rows are one 16-byte K chunk
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float xc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 w = g ? v[k ^ 1] : v[k];        // row k of the tile (static register indices)
+          xc[k] = c == 0 ? w.x : (c == 1 ? w.y : (c == 2 ? w.z : w.w));
+        }
+        hi[c].x = um_tf32(xc[0]); hi[c].y = um_tf32(xc[1]); hi[c].z = um_tf32(xc[2]); hi[c].w = um_tf32(xc[3]);
+        lo[c].x = um_tf32(xc[0] - __uint_as_float(hi[c].x));
+        lo[c].y = um_tf32(xc[1] - __uint_as_float(hi[c].y));
+        lo[c].z = um_tf32(xc[2] - __uint_as_float(hi[c].z));
+        lo[c].w = um_tf32(xc[3] - __uint_as_float(hi[c].w));
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm->raw_empty[s]);    // the raw slice is in registers
+      if (lane == 0) mbar_arrive(&sm->raw_empty[s]);    // the slice has been consumed
       um_wait(&sm->op_empty[t], pht ^ 1u);
-      unsigned char *dst = sm->op[t] + ks * kUmStepBytes + kk * 16;
+      unsigned char *dst = sm->op[t] + dst_off;
 #pragma unroll
-      for (int b = 0; b < 5; ++b) {
-        uint4 hi, lo;
-        hi.x = um_tf32(x[b].x); hi.y = um_tf32(x[b].y); hi.z = um_tf32(x[b].z); hi.w = um_tf32(x[b].w);
-        lo.x = um_tf32(x[b].x - __uint_as_float(hi.x));
-        lo.y = um_tf32(x[b].y - __uint_as_float(hi.y));
-        lo.z = um_tf32(x[b].z - __uint_as_float(hi.z));
-        lo.w = um_tf32(x[b].w - __uint_as_float(hi.w));
-        *reinterpret_cast<uint4 *>(dst + (b * 8 + quad) * kUmCoreStride) = hi;
-        *reinterpret_cast<uint4 *>(dst + (b * 8 + 4 + quad) * kUmCoreStride) = lo;
+      for (int c = 0; c < 4; ++c) {
+        *reinterpret_cast<uint4 *>(dst + c * 16) = hi[c];
+        *reinterpret_cast<uint4 *>(dst + c * 16 + 2 * kUmGroupStride) = lo[c];
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the MMA (async proxy)
       __syncwarp();
