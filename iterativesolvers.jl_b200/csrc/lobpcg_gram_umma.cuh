@@ -30,7 +30,15 @@
 //   warps 0-3   epilogue: tcgen05.ld of the needed column blocks (warp w owns TMEM lanes 32w..32w+31 = left block w),
 //               hi/lo column halves summed into 64 fp32 registers per thread; at the end lanes l and l+16 (hi and lo
 //               ROW of the same left column) are combined, per-CTA partials go out in fp64 and the last CTA (ticket)
-//               sums them -- the accumulation inside the tensor core never runs longer than kUmDrain*64 rows.
+//               sums them.
+//
+// Accumulation length.  The tensor core adds each K = 8 product sum to the fp32 accumulator with truncation: a chain of c
+// MMAs biases a positive sum (the diagonals of R'AR, P'AP) by about -c/2 ulp.  Measured (tools/diag_gram_ortho.py) on
+// orthonormal blocks: -2.3e-7 relative with 8 MMAs per hand-over, -2.5e-6 with 64 -- and the legacy mma.sync kernel, whose
+// per-warp chains grow with n, -9e-8 at n = 24^3 but -1.9e-6 at 64^3 (at 256^3 it lets lobpcg drift to NEGATIVE Ritz
+// values of an SPD matrix within 30 steps).  With the hand-over after every stage (kUmDrain = 1: 8 MMAs, then unbiased fp32
+// adds in the epilogue, fp64 across CTAs) the bias is independent of n and `lobpcg` converges where the reference's
+// arithmetic does; 64-MMA chains made the natural run of test_lobpcg_fp32_config5_shape end in a PosDefException.
 #pragma once
 #include "common.cuh"
 #include "spmv_stream.cuh"
@@ -46,7 +54,7 @@ constexpr int kUmGroups = 20;                             // 5 blocks x (hi, lo)
 constexpr int kUmHalfStride = kUmGroups * kUmGroupStride + 16;   // LBO: rows 4..7 of a step start 3216 B behind rows 0..3
 constexpr int kUmStepBytes = 2 * kUmHalfStride;           // 6432 B: the operand of one MMA (K = 8 rows)
 constexpr int kUmOpBytes = kUmSteps * kUmStepBytes;       // 51456 B per operand stage
-constexpr int kUmDrain = 8;                               // stages per accumulator hand-over (512 rows, 64 MMAs)
+constexpr int kUmDrain = 1;                               // stages per accumulator hand-over (64 rows, 8 MMAs): see the note on truncation below
 constexpr int kUmEpiWarps = 4, kUmConvWarps = 10;
 constexpr int kUmProducerWarp = 4, kUmMmaWarp = 5, kUmConvWarp0 = 6;
 constexpr int kUmThreads = (kUmConvWarp0 + kUmConvWarps) * 32;   // 512
