@@ -8,6 +8,9 @@
     cg256     configs[1]: cg! on laplace_matrix(Float64, 256, 3)
     widen     SURVEY 8(f) item 4: qmr!, lsqr!, lsmr!, idrs!(s=8) on laplace_matrix(Float64, N, 3), fixed iteration counts
               (adjoint operator built by the device transpose)
+    scattered y = A x (mul!) on CSR operators WITHOUT stencil structure, 7 nonzeros per row: columns uniform over all n, and
+              columns within a band of +-2^16 around the diagonal -- what the L1/L2 gather of x costs when the x-window argument
+              of the stencil case does not apply
     general   the general (callback-operator) engines of DESIGN sections 11 / 16 next to the tuned ones: cg!, minres! on
               laplace_matrix(Float64, N, 3), gmres!(30, CGS), bicgstabl!(2) on advection_dominated(N); the operator goes
               through the b200_linop interface with the library's own SpMV thunk (no host code inside the iteration)
@@ -133,8 +136,15 @@ def run(which, grid=256, iters=None, orth="cgs", reps=2, ctx=None, clocks=True, 
             dt = time.perf_counter() - t0
         out["clocks"] = clk.stop()
         pr = prof_read(L, ctx)
+        # algorithmic bytes of one outer iteration (reference src/bicgstabl.jl:88-131, every operation reading its operands
+        # once): BiCG part, step j: two dots with r_shadow (2n each), us[:,1:j] update (3jn), rs[:,1:j] update (3jn), x update
+        # (3n), two products; MR part: the Gram pass over rs (l+1)n and the three gemv updates (2l+6)n
+        V = 8
+        spmv_b = nnz * 12 + (n + 1) * 4 + 2 * n * V
+        per_outer = (3 * l * l + 13 * l + 7) * n * V + 2 * l * spmv_b
         out.update({"solver": "bicgstabl!(l=2)", "outer_iters": h.niters, "mvps": h.mvps, "seconds": dt,
-                    "mv_products_per_s": h.mvps / dt, "profile": pr})
+                    "mv_products_per_s": h.mvps / dt, "algorithmic_gb_per_outer_iteration": per_outer / 1e9,
+                    "achieved_gbs": per_outer * h.niters / dt / 1e9, "profile": pr})
     elif args.which in ("minres", "cg256"):
         A = isb.B200CSR.laplacian(N, 3, np.float64, ctx=ctx)
         b = rng.standard_normal(n)
@@ -219,6 +229,56 @@ def run(which, grid=256, iters=None, orth="cgs", reps=2, ctx=None, clocks=True, 
                          "frac_of_measured_peak": per_it[name] * h.iters / dt / 1e9 / pk,
                          "first_last": [float(h[key][0]), float(h[key][-1])], "profile": pr}
         out["solvers"] = res
+    elif args.which == "scattered":
+        V = 8
+        per_row = 7
+        res = {}
+        rowptr = (np.arange(n + 1, dtype=np.int64) * per_row).astype(np.int32)
+        xs = isb.DeviceArray.from_numpy(ctx, rng.standard_normal(n))
+        ys = isb.DeviceArray(ctx, n)
+        for name, band in (("banded_2^16", 1 << 16), ("uniform", None)):
+            rows = np.repeat(np.arange(n, dtype=np.int64), per_row - 1)
+            if band is None:
+                off = rng.integers(0, n, rows.size, dtype=np.int64)
+            else:
+                off = np.clip(rows + rng.integers(-band, band + 1, rows.size, dtype=np.int64), 0, n - 1)
+            cols = np.empty((n, per_row), dtype=np.int32)
+            cols[:, 0] = np.arange(n, dtype=np.int32)
+            cols[:, 1:] = off.reshape(n, per_row - 1)
+            del rows, off
+            cols.sort(axis=1)
+            vals = rng.standard_normal(n * per_row)
+            A = isb.B200CSR.from_csr_slab(rowptr, cols.reshape(-1), vals, n, 0, 0, None, ctx)
+            del cols, vals
+            spmv_b = A.nnz * 12 + (n + 1) * 4 + 2 * n * V
+            reps = args.iters or 50
+            for rep in range(2):
+                if rep == 1:
+                    clk.start()
+                ctx.sync()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    A.mul_(ys, xs)
+                ctx.sync()
+                dt = (time.perf_counter() - t0) / reps
+            res[name] = {"clocks": clk.stop(), "nnz": int(A.nnz), "ms_per_spmv": dt * 1e3,
+                         "algorithmic_gb": spmv_b / 1e9, "achieved_gbs": spmv_b / dt / 1e9,
+                         "frac_of_measured_peak": spmv_b / dt / 1e9 / pk}
+            A.close()
+        # the stencil operator of the same size for comparison
+        A = isb.B200CSR.laplacian(N, 3, np.float64, ctx=ctx)
+        spmv_b = A.nnz * 12 + (n + 1) * 4 + 2 * n * V
+        reps = args.iters or 50
+        for rep in range(2):
+            ctx.sync()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                A.mul_(ys, xs)
+            ctx.sync()
+            dt = (time.perf_counter() - t0) / reps
+        res["laplace_7pt"] = {"nnz": int(A.nnz), "ms_per_spmv": dt * 1e3, "algorithmic_gb": spmv_b / 1e9,
+                              "achieved_gbs": spmv_b / dt / 1e9, "frac_of_measured_peak": spmv_b / dt / 1e9 / pk}
+        out["operators"] = res
     elif args.which == "general":
         V = 8
         spmv_b = nnz * 12 + (n + 1) * 4 + 2 * n * V
@@ -312,7 +372,7 @@ def run(which, grid=256, iters=None, orth="cgs", reps=2, ctx=None, clocks=True, 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["gmres", "lobpcg", "minres", "bicgstabl", "cg256", "widen", "general"])
+    ap.add_argument("which", choices=["gmres", "lobpcg", "minres", "bicgstabl", "cg256", "widen", "general", "scattered"])
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--iters", type=int, default=None)
     ap.add_argument("--orth", default="cgs")

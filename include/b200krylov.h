@@ -119,6 +119,8 @@ B200_API int b200_ctx_profile_read(b200_ctx *ctx, int slot, double *total_ms, in
  *           DGKS re-orthogonalisation rounds and the scaling separated by grid-wide barriers) and gmres! keeps H, the
  *           residual recurrence and the stopping test on the device, enqueueing a whole restart cycle per host
  *           synchronisation (single-GPU contexts); 0 = three kernels per orthogonalisation, host-side recurrences
+ *   "pdl": 1 (default) = the kernels of a cg! iteration are chained with programmatic dependent launch
+ *           (griddepcontrol): the next kernel's blocks are resident when the previous one ends; 0 = plain stream order
  *   "comm": 0 = auto, 1 = NCCL collectives, 2 = NVLink peer-memory collectives fused into the kernels
  *           (multi-GPU contexts; get "peer_ok" tells whether the peer buffers could be mapped)
  *   "lobpcg_mma": 1 (default) = fp32 LOBPCG blocks run the update and the Gram products as 3xTF32 tensor-core

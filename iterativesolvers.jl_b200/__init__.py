@@ -15,7 +15,7 @@ from ._lib import B200Error, lib  # noqa: F401
 from .device import Context, DeviceArray, default_context, pinned_empty  # noqa: F401
 from .operators import B200CSR, B200LinearOperator, FunctionPrec, HaloPlan, Identity, JacobiPrec  # noqa: F401
 from .history import ConvergenceHistory, niters, nprods, nrests  # noqa: F401
-from .generators import laplace_matrix, laplace_csr_slab, advection_dominated, mmread  # noqa: F401
+from .generators import laplace_matrix, laplace_csr_slab, advection_dominated, mmread, matread  # noqa: F401
 from .solvers import (cg, cg_, chebyshev, chebyshev_, gmres, gmres_, minres, minres_, bicgstabl, bicgstabl_, lobpcg,  # noqa: F401
                       LOBPCGResults, orthogonalize_and_normalize_, hessenberg_ldiv_,
                       cg_iterator_, CGIterable, CGStateVariables, KrylovIterable, gmres_iterable_, minres_iterable_,

@@ -173,13 +173,17 @@ __global__ void __launch_bounds__(kThreads) k_bc_gram(const T *__restrict__ rs, 
   __threadfence();
   if (threadIdx.x < NPAIR) out[threadIdx.x] = 0.0;      // pairs with a column >= LC
   __syncthreads();
-  if (threadIdx.x < NPL) {
+  // warp w finishes pairs w, w + 8, ...: its lanes stride over the block slots (fixed order per lane, fixed shuffle tree:
+  // deterministic), instead of NPL threads walking all slots one after the other
+  for (int pr = warp; pr < NPL; pr += kThreads / 32) {
     double sacc = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b)
-      sacc += __ldcg(&partials[(size_t)b * kMaxReduceWidth + threadIdx.x]);
-    int p = 0, k = threadIdx.x;                           // local pair index -> (p, q)
-    while (k >= LC - p) { k -= LC - p; ++p; }
-    out[pair_slot(p, p + k)] = sacc;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) sacc += __ldcg(&partials[(size_t)b * kMaxReduceWidth + pr]);
+    sacc = warp_sum(sacc);
+    if (lane == 0) {
+      int p = 0, k = pr;                                  // local pair index -> (p, q)
+      while (k >= LC - p) { k -= LC - p; ++p; }
+      out[pair_slot(p, p + k)] = sacc;
+    }
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }

@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(kThreads) k_cg_update_u(const T *__restrict__ 
                                                           const CgScal *__restrict__ s, int pcg, int rev,
                                                           const T *r_halo, T *__restrict__ u_halo, int n_halo,
                                                           Comm cm) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (s->done) return;
   const double beta_d = pcg ? s->rho / s->rho_prev
                             : (s->residual * s->residual) / (s->prev_residual * s->prev_residual);
@@ -214,6 +216,8 @@ __global__ void __launch_bounds__(kThreads) k_cg_spmv_dot(const int *__restrict_
                                                           const T *__restrict__ vals, XView<T> xv, int64_t m,
                                                           T *__restrict__ c, CgScal *s, double *partials,
                                                           unsigned int *ticket, Comm cm) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (s->done) return;
   __shared__ double smem[kThreads / 32];
   wait_halo(cm);
@@ -253,6 +257,8 @@ __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
     k_cg_spmv_dot_stream(const int *__restrict__ rowptr, const int *__restrict__ colind, const T *__restrict__ vals,
                          XView<T> xv, int64_t m, T *__restrict__ c, CgScal *s, double *partials,
                          unsigned int *ticket, Comm cm) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (s->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double red[kStreamThreads / 32];
@@ -270,6 +276,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_update_r(T *__restrict__ r, const T *__restrict__ c, int64_t n,
                                                           CgScal *s, double *hist, double *partials,
                                                           unsigned int *ticket, int pcg, Comm cm) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (s->done) return;
   __shared__ double smem[kThreads / 32];
   const T alpha = (T)s->alpha;
@@ -293,6 +301,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads) k_pcg_precond(const T *__restrict__ d, const T *__restrict__ r,
                                                           T *__restrict__ c, int64_t n, CgScal *s, double *partials,
                                                           unsigned int *ticket, Comm cm) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (s->done) return;
   __shared__ double smem[kThreads / 32];
   double acc = 0.0;
@@ -375,8 +385,9 @@ struct CgEngine {
 #define LAUNCH(L)                                                                                                    \
   do {                                                                                                               \
     B200_SMEM_ATTR_ONCE(ctx, smem, k_cg_spmv_dot_stream<T, L>);                                                      \
-    k_cg_spmv_dot_stream<T, L><<<grid, kStreamThreads, smem, ctx->stream>>>(                                        \
-        A->rowptr, A->colind, (const T *)A->vals, xv, n, c, s, ctx->red.partials, ctx->red.ticket, cm);              \
+    B200_CUDA(launch_chained(ctx->opt_pdl != 0, k_cg_spmv_dot_stream<T, L>, dim3(grid), dim3(kStreamThreads), smem,    \
+                             ctx->stream, A->rowptr, A->colind, (const T *)A->vals, xv, n, c, s, ctx->red.partials,  \
+                             ctx->red.ticket, cm));                                                                  \
   } while (0)
       switch (A->stream_lpr) {
         case 1: LAUNCH(1); break;
@@ -390,8 +401,9 @@ struct CgEngine {
     } else {
       ProfScope prof(ctx, 0);
 #define LAUNCH(L)                                                                                               \
-  k_cg_spmv_dot<T, L><<<grid_spmv, kThreads, 0, ctx->stream>>>(A->rowptr, A->colind, (const T *)A->vals, xv, n, \
-                                                               c, s, ctx->red.partials, ctx->red.ticket, cm)
+  B200_CUDA(launch_chained(ctx->opt_pdl != 0, k_cg_spmv_dot<T, L>, dim3(grid_spmv), dim3(kThreads), 0, ctx->stream, \
+                           A->rowptr, A->colind, (const T *)A->vals, xv, n, c, s, ctx->red.partials,             \
+                           ctx->red.ticket, cm))
       switch (lpr) {
         case 2: LAUNCH(2); break;
         case 4: LAUNCH(4); break;
@@ -409,7 +421,8 @@ struct CgEngine {
     cudaStream_t st = ctx->stream;
     const int pcg = jac != nullptr;
     if (pcg) {
-      k_pcg_precond<T><<<grid_vec, kThreads, 0, st>>>(jac, r, c, n, s, ctx->red.partials, ctx->red.ticket, comm());
+      B200_CUDA(launch_chained(ctx->opt_pdl != 0, k_pcg_precond<T>, dim3(grid_vec), dim3(kThreads), 0, st, jac, r, c, n, s,
+                               ctx->red.partials, ctx->red.ticket, comm()));
       B200_LAUNCH_CHECK(ctx);
       B200_TRY(after_reduce(FIN_RHO));
     }
@@ -422,17 +435,17 @@ struct CgEngine {
       hc.halo_mask = fold_halo ? A->recv_mask : 0;
       hc.rev = 0;
       if (mode == COMM_PEER) hc.pv = ctx->peer_view;
-      k_cg_update_u<T><<<grid_vec, kThreads, 0, st>>>(pcg ? c : r, u, x, n, s, pcg, next_sweep(),
-                                                      fold_halo ? (const T *)A->halo_peer : nullptr,
-                                                      fold_halo ? (T *)A->halo : nullptr, fold_halo ? (int)A->n_halo : 0,
-                                                      hc);
+      B200_CUDA(launch_chained(ctx->opt_pdl != 0, k_cg_update_u<T>, dim3(grid_vec), dim3(kThreads), 0, st,
+                               (const T *)(pcg ? c : r), u, x, n, (const CgScal *)s, pcg, next_sweep(),
+                               fold_halo ? (const T *)A->halo_peer : (const T *)nullptr,
+                               fold_halo ? (T *)A->halo : (T *)nullptr, fold_halo ? (int)A->n_halo : 0, hc));
     }
     B200_LAUNCH_CHECK(ctx);
     B200_TRY(spmv_dot());
     {
       ProfScope prof(ctx, 1);
-      k_cg_update_r<T><<<grid_vec, kThreads, 0, st>>>(r, c, n, s, hist, ctx->red.partials, ctx->red.ticket, pcg,
-                                                      comm(false, next_sweep()));
+      B200_CUDA(launch_chained(ctx->opt_pdl != 0, k_cg_update_r<T>, dim3(grid_vec), dim3(kThreads), 0, st, r, (const T *)c, n,
+                               s, hist, ctx->red.partials, ctx->red.ticket, pcg, comm(false, next_sweep())));
     }
     B200_LAUNCH_CHECK(ctx);
     B200_TRY(after_reduce(pcg ? FIN_NORM_PCG : FIN_NORM));

@@ -102,6 +102,7 @@ struct b200_ctx {
                                  // tcgen05 (TMEM accumulators), 2 = legacy mma.sync Gram, 0 = SIMT kernels
   int opt_orth_fused = 1;        // b200_ctx_set_option("orth_fused"): 1 = one cooperative launch per CGS/DGKS orthogonalisation and a
                                  // device-resident GMRES cycle (single GPU); 0 = the three-kernel path with host-side recurrences
+  int opt_pdl = 1;               // b200_ctx_set_option("pdl"): chain the kernels of a CG iteration with programmatic dependent launch
   int opt_snake = 1;            // b200_ctx_set_option("snake"): consecutive hot kernels sweep the rows in alternating directions
   // peer-memory collectives (peer.cuh), multi-GPU contexts only
   bool peer_ok = false;
@@ -225,6 +226,28 @@ __device__ __forceinline__ int ld_stream<int>(const int *p, uint64_t pol) {
   return r;
 }
 
+// Programmatic dependent launch (PDL): consecutive kernels of an iteration are chained so that the blocks of kernel k+1 are
+// already resident (launch latency, prologue) when kernel k ends.  A chained kernel starts with pdl_wait() -- it returns once
+// the preceding grid has completed and flushed -- and then lets ITS successor be scheduled with pdl_launch_dependents().
+// Both are no-ops for launches without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(bool chained, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = chained ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 #endif  // __CUDACC__
 
 // profiling scope: records an event pair around a launch when the context's profiler is on

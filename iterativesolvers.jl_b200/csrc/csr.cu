@@ -801,6 +801,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_halo_push(PushArgs a, const int *__restrict__ idx, const T *__restrict__ x,
                                                    PeerView pv, unsigned long long seq, unsigned int *ticket,
                                                    const int *__restrict__ done_flag) {
+  pdl_wait();
+  pdl_launch_dependents();
   if (done_flag && *done_flag) return;
   const long long n = a.start[a.world];
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
@@ -837,9 +839,11 @@ int b200::halo_push(b200_ctx *ctx, const b200_csr *A, const void *x_dev, unsigne
   const int grid = std::max(1, std::min(ctx->sm_count, (int)((A->n_send + 1023) / 1024)));
   unsigned int *ticket = ctx->red.ticket + 1;   // own counter: must not interfere with a reduction in flight
   if (A->dtype == B200_F64)
-    k_halo_push<double><<<grid, 256, 0, ctx->stream>>>(a, A->send_idx, (const double *)x_dev, ctx->peer_view, seq, ticket, done_flag);
+    B200_CUDA(launch_chained(ctx->opt_pdl != 0, k_halo_push<double>, dim3(grid), dim3(256), 0, ctx->stream, a,
+                             (const int *)A->send_idx, (const double *)x_dev, ctx->peer_view, seq, ticket, done_flag));
   else
-    k_halo_push<float><<<grid, 256, 0, ctx->stream>>>(a, A->send_idx, (const float *)x_dev, ctx->peer_view, seq, ticket, done_flag);
+    B200_CUDA(launch_chained(ctx->opt_pdl != 0, k_halo_push<float>, dim3(grid), dim3(256), 0, ctx->stream, a,
+                             (const int *)A->send_idx, (const float *)x_dev, ctx->peer_view, seq, ticket, done_flag));
   B200_LAUNCH_CHECK(ctx);
   return B200_OK;
 }

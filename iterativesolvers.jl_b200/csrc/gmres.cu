@@ -96,10 +96,11 @@ __global__ void __launch_bounds__(kThreads) k_block_dots(const T *__restrict__ V
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  for (int j = threadIdx.x; j < k; j += kThreads) {
+  for (int j = warp; j < k; j += kThreads / 32) {     // warp per column, lanes stride over the block slots (deterministic)
     double s = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * kMaxReduceWidth + j]);
-    out[j] = s;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(&partials[(size_t)b * kMaxReduceWidth + j]);
+    s = warp_sum(s);
+    if (lane == 0) out[j] = s;
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }

@@ -143,18 +143,39 @@ __global__ void __launch_bounds__(kThreads) k_spmm_rm(const int *__restrict__ ro
     if (row >= m) continue;
     const int b = __ldg(rowptr + row), e = __ldg(rowptr + row + 1);
     T acc[4] = {(T)0, (T)0, (T)0, (T)0};
-    for (int k = b; k < e; ++k) {
-      const int c = ld_stream<int>(colind + k, pol);
-      const T a = ld_stream<T>(vals + k, pol);
-      // local extended index: [0, m) own rows, [m, m + n_halo) rows received from the neighbours
-      const T *xr = (c < m ? X + (int64_t)c * BS : Xhalo + (int64_t)(c - m) * BS) + 4 * sub;
-      if constexpr (sizeof(T) == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(xr));
-        acc[0] += a * t.x; acc[1] += a * t.y; acc[2] += a * t.z; acc[3] += a * t.w;
-      } else {
-        const double2 t0 = __ldg(reinterpret_cast<const double2 *>(xr));
-        const double2 t1 = __ldg(reinterpret_cast<const double2 *>(xr) + 1);
-        acc[0] += a * t0.x; acc[1] += a * t0.y; acc[2] += a * t1.x; acc[3] += a * t1.y;
+    // four nonzeros per round: their column indices, then their four X rows are in flight together (the one-by-one loop
+    // chained index load -> gather -> FMA per nonzero and ran latency-bound at 4.9 TB/s, r1 ncu); the products are added
+    // in the row's storage order, as before
+    for (int k = b; k < e; k += 4) {
+      int c[4];
+      T a[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = k + u < e ? k + u : e - 1;
+        c[u] = ld_stream<int>(colind + kk, pol);
+        a[u] = ld_stream<T>(vals + kk, pol);
+        if (k + u >= e) a[u] = (T)0;
+      }
+      T t[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        // local extended index: [0, m) own rows, [m, m + n_halo) rows received from the neighbours
+        const T *xr = (c[u] < m ? X + (int64_t)c[u] * BS : Xhalo + (int64_t)(c[u] - m) * BS) + 4 * sub;
+        if constexpr (sizeof(T) == 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4 *>(xr));
+          t[u][0] = v.x; t[u][1] = v.y; t[u][2] = v.z; t[u][3] = v.w;
+        } else {
+          const double2 v0 = __ldg(reinterpret_cast<const double2 *>(xr));
+          const double2 v1 = __ldg(reinterpret_cast<const double2 *>(xr) + 1);
+          t[u][0] = v0.x; t[u][1] = v0.y; t[u][2] = v1.x; t[u][3] = v1.y;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (k + u < e) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) acc[q] += a[u] * t[u][q];
+        }
       }
     }
     T *yr = Y + row * BS + 4 * sub;
@@ -469,10 +490,11 @@ __global__ void __launch_bounds__(kThreads) k_update(UpdateArgs a, const T *__re
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (threadIdx.x < BS) {
+  for (int j = warp; j < BS; j += kThreads / 32) {    // warp per column, lanes stride over the block slots (deterministic)
     double s = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * kMaxReduceWidth + threadIdx.x]);
-    norms2[threadIdx.x] = s;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(&partials[(size_t)b * kMaxReduceWidth + j]);
+    s = warp_sum(s);
+    if (lane == 0) norms2[j] = s;
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }
@@ -634,10 +656,11 @@ __global__ void __launch_bounds__(kThreads, 2) k_update_tc(UpdateArgs a, const f
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  if (threadIdx.x < BS) {
+  for (int j = warp; j < BS; j += kThreads / 32) {    // warp per column, lanes stride over the block slots (deterministic)
     double s = 0.0;
-    for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(&partials[(size_t)b * kMaxReduceWidth + threadIdx.x]);
-    norms2[threadIdx.x] = s;
+    for (unsigned int b = lane; b < gridDim.x; b += 32) s += __ldcg(&partials[(size_t)b * kMaxReduceWidth + j]);
+    s = warp_sum(s);
+    if (lane == 0) norms2[j] = s;
   }
   if (threadIdx.x == 0) *ticket = 0u;
 }

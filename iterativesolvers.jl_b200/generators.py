@@ -71,3 +71,33 @@ def mmread(path, base: int = 0):
     nzval = np.empty(max(nnz.value, 1), dtype=np.float64)
     check(lib().b200_mm_read_csc_i64(p, base, nnz.value, _vp(colptr), _vp(rowval), _vp(nzval)))
     return colptr, rowval[: nnz.value], nzval[: nnz.value], (m.value, n.value)
+
+
+def matread(path, problem="Problem", base: int = 0):
+    """MAT.matread(file)["Problem"] of the reference's benchmark/matrixcollection.jl:4-12 -- the MATLAB files of the
+    SuiteSparse (University of Florida) collection: returns (colptr, rowval, nzval, shape, b) with the operator
+    `Problem.A` as SparseMatrixCSC{Float64,Int64} arrays (rows sorted, base = 1 for Julia's indexing; feed them to
+    B200CSR.from_csc_arrays) and the right-hand side `Problem.b[:]` (None when the file has none).  Host-side ingestion,
+    read with scipy.io.loadmat (MATLAB v5 / v7 files, zlib-compressed elements included); v7.3 (HDF5) files are rejected."""
+    import scipy.io as sio
+    import scipy.sparse as sp
+    try:
+        vars_ = sio.loadmat(os.fspath(path), squeeze_me=False, struct_as_record=False)
+    except NotImplementedError as e:            # scipy: "Please use HDF reader for matlab v7.3 files"
+        raise B200Error(f"{path}: MATLAB v7.3 (HDF5) files are not supported: {e}")
+    if problem not in vars_:
+        raise B200Error(f"{path}: no variable `{problem}` (found {sorted(k for k in vars_ if not k.startswith('__'))})")
+    P = vars_[problem]
+    P = P[0, 0] if isinstance(P, np.ndarray) and P.dtype == object else P
+    A = getattr(P, "A", None) if not sp.issparse(P) else P
+    if A is None or not sp.issparse(A):
+        raise B200Error(f"{path}: `{problem}.A` is not a sparse matrix")
+    A = sp.csc_matrix(A, dtype=np.float64)
+    A.sum_duplicates()
+    A.sort_indices()
+    b = getattr(P, "b", None) if not sp.issparse(P) else None
+    if b is not None:
+        b = np.asarray(b.todense() if sp.issparse(b) else b, dtype=np.float64).reshape(-1, order="F")
+    colptr = A.indptr.astype(np.int64) + base
+    rowval = A.indices.astype(np.int64) + base
+    return colptr, rowval, A.data.astype(np.float64), A.shape, b

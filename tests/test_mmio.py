@@ -86,3 +86,28 @@ def test_solve_an_operator_loaded_from_a_matrix_market_file(isb, oracle, tmp_pat
     b = A @ xs
     x, h = isb.cg(A, b, log=True, reltol=1e-12)
     assert h.isconverged and np.linalg.norm(x - xs) <= 1e-9 * np.linalg.norm(xs)
+
+
+def test_matread_suitesparse_layout(isb, tmp_path):
+    """benchmark/matrixcollection.jl:4-12: vars = matread(file); A, b = vars["Problem"]["A"], vars["Problem"]["b"][:].
+    A file written the way the SuiteSparse collection's .mat files are laid out (struct `Problem` with a sparse `A`, a dense
+    `b` and metadata), compressed and uncompressed, comes back as the CSC{Float64,Int64} arrays of A and the vector b."""
+    A = sp.random(40, 40, 0.1, random_state=5, format="csc") + sp.identity(40, format="csc")
+    A = (A + A.T).tocsc()
+    A.sort_indices()
+    b = np.arange(1.0, 41.0).reshape(-1, 1)
+    for compress in (False, True):
+        path = os.path.join(tmp_path, f"ACUSIM_Pres_Poisson_{int(compress)}.mat")
+        sio.savemat(path, {"Problem": {"A": A, "b": b, "name": "ACUSIM/Pres_Poisson", "id": 1}}, do_compression=compress)
+        for base in (0, 1):
+            cp, rv, nz, shape, bb = isb.matread(path, base=base)
+            assert shape == (40, 40) and cp.dtype == rv.dtype == np.int64 and nz.dtype == np.float64
+            assert np.array_equal(cp - base, A.indptr) and np.array_equal(rv - base, A.indices) and np.array_equal(nz, A.data)
+            assert np.array_equal(bb, b[:, 0])
+    path = os.path.join(tmp_path, "no_problem.mat")
+    sio.savemat(path, {"X": np.eye(2)})
+    with pytest.raises(isb.B200Error):
+        isb.matread(path)
+    sio.savemat(path, {"Problem": {"A": np.eye(3)}})
+    with pytest.raises(isb.B200Error):
+        isb.matread(path)

@@ -20,15 +20,14 @@ OUT = os.path.join(ROOT, "profiles")
 # tag -> (substring of the mangled name that selects ONE instantiation, what to show)
 HOT = {
     "cg_k2_spmv_dot_stream_f64": ("k_cg_spmv_dot_streamIdLi8E", "K2 of cg!: c = A u fused with dot(u, c); TMA-bulk streamed CSR"),
-    "cg_k1_update": ("k_cg_update_x_u", "K1 of cg!: x += alpha u_old (deferred), u = r + beta u"),
-    "cg_k3_update_r": ("k_cg_update_r", "K3 of cg!: r -= alpha c fused with ||r||^2"),
-    "gmres_block_dots": ("k_block_dots", "CGS/DGKS block of dots h = V' w"),
-    "gmres_block_axpy": ("k_block_axpy", "CGS/DGKS w -= V h"),
-    "gmres_fused_orth": ("k_orth_fused", "fused cooperative CGS/DGKS orthogonalize_and_normalize!"),
-    "lobpcg_update_tc": ("k_update_tcILi1E", "LOBPCG update (3xTF32 mma.sync)"),
+    "cg_k1_update_u": ("k_cg_update_uId", "K1 of cg!: x += alpha u_old (deferred), u = r + beta u"),
+    "cg_k3_update_r": ("k_cg_update_rId", "K3 of cg!: r -= alpha c fused with ||r||^2 (and the warp-parallel NVLink allreduce)"),
+    "gmres_block_dots": ("k_block_dotsIdLi2E", "CGS/DGKS block of dots h = V' w (three-kernel path)"),
+    "gmres_fused_orth": ("k_orth_fusedIdLi2E", "orthogonalize_and_normalize! CGS/DGKS in one cooperative launch + the GMRES scalar step"),
+    "lobpcg_update_tc": ("k_update_tcILi1E", "LOBPCG update X, P, AX, AP, R (3xTF32 mma.sync)"),
     "lobpcg_gram_tcgen05": ("k_gram_umma", "LOBPCG Rayleigh-Ritz Gram products on tcgen05 (TMEM accumulators)"),
     "lobpcg_gram_legacy": ("k_gram_rr_tcILi2E", "LOBPCG Rayleigh-Ritz Gram products, legacy mma.sync path (kept for comparison)"),
-    "pass_generic": ("k_pass", "the fused-pass kernel of the general (callback-operator) engines"),
+    "pass_generic": ("k_passINS_8QmrWNextIdEE", "the fused-pass kernel of the general engines (one instantiation: QMR's w-recurrence pass)"),
     "spmv_stream_f64": ("k_spmv_streamIdLi8E", "mul!(y, A, x): TMA-bulk streamed CSR SpMV"),
 }
 KEY = re.compile(r"\b(UBLKCP|UTMALDG|UTMASTG|SYNCS|UTC[A-Z]*MMA|UTCBAR|UTCCP|LDTM|STTM|UTCALLOC|HMMA|DFMA|DADD|DMUL|FFMA|"
@@ -88,7 +87,7 @@ def main():
             m = re.search(r"/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", l)
             if m:
                 hist[m.group(1).split(".")[0]] += 1
-        keyl = [l.rstrip() for l in ins if KEY.search(l) and re.search(r"UBLKCP|UTMA|SYNCS|UTC|LDTM|STTM|HMMA|DFMA|ACQBULK|ELECT|REDG", l)]
+        keyl = [l.rstrip() for l in ins if KEY.search(l) and re.search(r"UBLKCP|UTMA|SYNCS|UTC|LDTM|STTM|HMMA|DFMA|ACQBULK|ELECT|REDG|ERRBAR|MEMBAR", l)]
         path = os.path.join(OUT, f"sass_{tag}.txt")
         with open(path, "w") as f:
             f.write(f"# {what}\n# {demangle(n)}\n# cuobjdump -sass libb200krylov.so (sm_100a), {len(ins)} instructions\n")
@@ -97,7 +96,7 @@ def main():
             f.write("\n".join(keyl[:120]) + "\n")
         written.append(path)
     rows = ptxas_table()
-    hot_subs = [v[0].split("I")[0] for v in HOT.values()]
+    hot_subs = [v[0].split("I")[0] if not v[0].startswith("k_pass") else v[0] for v in HOT.values()]
     with open(os.path.join(OUT, "ptxas_table.md"), "w") as f:
         f.write("# `ptxas -v` facts of the hot kernels (sm_100a; from iterativesolvers.jl_b200/csrc/build/*.ptxas.log)\n\n")
         f.write("| file | kernel | registers | static smem B | stack B | spill st B | spill ld B |\n|---|---|---|---|---|---|---|\n")
