@@ -119,8 +119,12 @@ B200_API int b200_ctx_profile_read(b200_ctx *ctx, int slot, double *total_ms, in
  *           DGKS re-orthogonalisation rounds and the scaling separated by grid-wide barriers) and gmres! keeps H, the
  *           residual recurrence and the stopping test on the device, enqueueing a whole restart cycle per host
  *           synchronisation (single-GPU contexts); 0 = three kernels per orthogonalisation, host-side recurrences
- *   "pdl": 1 (default) = the kernels of a cg! iteration are chained with programmatic dependent launch
- *           (griddepcontrol): the next kernel's blocks are resident when the previous one ends; 0 = plain stream order
+ *   "pdl": 1 = the kernels of a cg! iteration are chained with programmatic dependent launch (griddepcontrol): the
+ *           next kernel's blocks are resident when the previous one ends; 0 (default) = plain stream order, which
+ *           measured faster on B200 with this driver (560 vs 520 iterations/s, 512^3 on 2 GPUs)
+ *   "fold_push": 1 (default) = multi-GPU peer-memory cg! with Identity: the kernel that updates r stores r's boundary rows
+ *           into the neighbours' halo segments itself and its finishing block raises the halo flags (one launch less
+ *           per iteration; needs one contiguous row range per neighbour); 0 = separate push kernel
  *   "comm": 0 = auto, 1 = NCCL collectives, 2 = NVLink peer-memory collectives fused into the kernels
  *           (multi-GPU contexts; get "peer_ok" tells whether the peer buffers could be mapped)
  *   "lobpcg_mma": 1 (default) = fp32 LOBPCG blocks run the update and the Gram products as 3xTF32 tensor-core

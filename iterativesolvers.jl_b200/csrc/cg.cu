@@ -64,6 +64,18 @@ struct Comm {
   PeerView pv;
 };
 
+// Peer path, CG with Identity: the boundary rows of the new r go to the neighbours from INSIDE K3 (the rows every rank sends
+// are one contiguous range per neighbour for slabs of banded operators), and the block that finishes the grid reduction
+// raises the halo flags -- one launch (k_halo_push) less per iteration.
+struct PushRanges {
+  int n;                         // 0: nothing to push from this kernel
+  int rank;
+  unsigned int send_mask;
+  unsigned long long seq;        // halo sequence the flags announce
+  long long lo[2], cnt[2];       // local row ranges
+  void *dst[2];                  // their place in the neighbour's halo segment (mapped peer memory)
+};
+
 // bookkeeping after ||r||^2 is known (src/cg.jl:61-62 + done() :36); single thread
 __device__ __forceinline__ void cg_after_norm(CgScal *s, double rr, double *hist, bool pcg) {
   if (!pcg) s->prev_residual = s->residual;
@@ -163,7 +175,6 @@ __global__ void __launch_bounds__(kThreads) k_cg_update_u(const T *__restrict__ 
                                                           const T *r_halo, T *__restrict__ u_halo, int n_halo,
                                                           Comm cm) {
   pdl_wait();
-  pdl_launch_dependents();
   if (s->done) return;
   const double beta_d = pcg ? s->rho / s->rho_prev
                             : (s->residual * s->residual) / (s->prev_residual * s->prev_residual);
@@ -182,6 +193,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_update_u(const T *__restrict__ 
       u[i] = __fadd_rn(r[i], __fmul_rn(beta, ui));
     }
   }
+  pdl_launch_dependents();   // the bulk of this CTA's work is done: let the next kernel's blocks become resident
   // Peer-memory path (CG, Identity): the neighbours pushed the boundary values of r right after their K3 -- one
   // kernel earlier than u exists -- and every GPU forms the halo part of u itself from the same operands
   // (r_halo, beta, previous u_halo): bit-identical to the owner's values, and the NVLink latency of the push is
@@ -217,7 +229,6 @@ __global__ void __launch_bounds__(kThreads) k_cg_spmv_dot(const int *__restrict_
                                                           T *__restrict__ c, CgScal *s, double *partials,
                                                           unsigned int *ticket, Comm cm) {
   pdl_wait();
-  pdl_launch_dependents();
   if (s->done) return;
   __shared__ double smem[kThreads / 32];
   wait_halo(cm);
@@ -234,6 +245,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_spmv_dot(const int *__restrict_
       acc += (double)xv.x[row] * (double)ci;
     }
   }
+  pdl_launch_dependents();
   acc = block_sum<kThreads>(acc, smem);
   double total;
   if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x < 32)
@@ -258,13 +270,13 @@ __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
                          XView<T> xv, int64_t m, T *__restrict__ c, CgScal *s, double *partials,
                          unsigned int *ticket, Comm cm) {
   pdl_wait();
-  pdl_launch_dependents();
   if (s->done) return;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double red[kStreamThreads / 32];
   wait_halo(cm);
   CgDotEpi<T> epi{c, xv.x, 0.0};
   spmv_stream_tiles<T, LPR>(rowptr, colind, vals, xv, m, epi, reinterpret_cast<StreamSmem<T> *>(smem_raw), cm.rev != 0);
+  pdl_launch_dependents();
   const double acc = block_sum<kStreamThreads>(epi.acc, red);
   double total;
   if (grid_reduce_finish<kStreamThreads>(acc, partials, ticket, red, &total) && threadIdx.x < 32)
@@ -275,9 +287,8 @@ __global__ void __launch_bounds__(kStreamThreads, kStreamCtasPerSm)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_cg_update_r(T *__restrict__ r, const T *__restrict__ c, int64_t n,
                                                           CgScal *s, double *hist, double *partials,
-                                                          unsigned int *ticket, int pcg, Comm cm) {
+                                                          unsigned int *ticket, int pcg, Comm cm, PushRanges pr) {
   pdl_wait();
-  pdl_launch_dependents();
   if (s->done) return;
   __shared__ double smem[kThreads / 32];
   const T alpha = (T)s->alpha;
@@ -289,11 +300,25 @@ __global__ void __launch_bounds__(kThreads) k_cg_update_r(T *__restrict__ r, con
     else ri = __fsub_rn(r[i], __fmul_rn(alpha, c[i]));
     r[i] = ri;
     acc += (double)ri * (double)ri;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const long long k = (long long)i - pr.lo[q];
+      if (q < pr.n && k >= 0 && k < pr.cnt[q]) ((T *)pr.dst[q])[k] = ri;   // store to the neighbour's halo segment (NVLink)
+    }
   }
+  pdl_launch_dependents();
   acc = block_sum<kThreads>(acc, smem);
   double total;
-  if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x < 32)
-    cg_finish(pcg ? FIN_NORM_PCG : FIN_NORM, s, total, hist, cm);
+  if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total, pr.n > 0)) {
+    if (pr.n > 0 && threadIdx.x == 0) {
+      // every block fenced its boundary stores at system scope before taking its ticket: the flags may go out (before this
+      // GPU starts waiting for the other ranks' partial sums)
+      __threadfence_system();
+      for (int p = 0; p < cm.pv.world; ++p)
+        if ((pr.send_mask >> p) & 1u) st_release_sys(&cm.pv.hdr[p]->halo_flag[pr.rank], pr.seq);
+    }
+    if (threadIdx.x < 32) cg_finish(pcg ? FIN_NORM_PCG : FIN_NORM, s, total, hist, cm);
+  }
 }
 
 // PCG: c = r ./ d ; rho = dot(c, r)    (src/cg.jl:79-82, Jacobi ldiv!)
@@ -302,7 +327,6 @@ __global__ void __launch_bounds__(kThreads) k_pcg_precond(const T *__restrict__ 
                                                           T *__restrict__ c, int64_t n, CgScal *s, double *partials,
                                                           unsigned int *ticket, Comm cm) {
   pdl_wait();
-  pdl_launch_dependents();
   if (s->done) return;
   __shared__ double smem[kThreads / 32];
   double acc = 0.0;
@@ -312,6 +336,7 @@ __global__ void __launch_bounds__(kThreads) k_pcg_precond(const T *__restrict__ 
     c[i] = ci;
     acc += (double)ci * (double)ri;
   }
+  pdl_launch_dependents();
   acc = block_sum<kThreads>(acc, smem);
   double total;
   if (grid_reduce_finish<kThreads>(acc, partials, ticket, smem, &total) && threadIdx.x < 32)
@@ -332,6 +357,7 @@ struct CgEngine {
   int lpr, grid_vec, grid_spmv;
   int sweep = 0;   // direction of the next hot kernel (toggled per launch when ctx->opt_snake)
   bool fold_halo = false;   // peer path, Identity: r's boundary is pushed after K3 and K1 forms u's halo locally
+  bool fold_push = false;   // ... and K3 itself stores the boundary rows to the neighbours (contiguous send ranges)
 
   int next_sweep() {
     const int d = ctx->opt_snake ? sweep : 0;
@@ -442,14 +468,30 @@ struct CgEngine {
     }
     B200_LAUNCH_CHECK(ctx);
     B200_TRY(spmv_dot());
+    PushRanges pr;
+    memset(&pr, 0, sizeof(pr));
+    if (fold_push) {
+      ctx->halo_seq += 1;
+      pr.rank = ctx->rank;
+      pr.send_mask = A->send_mask;
+      pr.seq = ctx->halo_seq;
+      const size_t vs = sizeof(T);
+      for (int p = 0; p < ctx->world; ++p)
+        if (A->send_count[p] > 0) {
+          pr.lo[pr.n] = A->send_range_lo[p];
+          pr.cnt[pr.n] = A->send_count[p];
+          pr.dst[pr.n] = (char *)ctx->peer_ptr[p] + kPeerHeaderBytes + vs * (size_t)A->peer_dst_offset[p];
+          pr.n += 1;
+        }
+    }
     {
       ProfScope prof(ctx, 1);
       B200_CUDA(launch_chained(ctx->opt_pdl != 0, k_cg_update_r<T>, dim3(grid_vec), dim3(kThreads), 0, st, r, (const T *)c, n,
-                               s, hist, ctx->red.partials, ctx->red.ticket, pcg, comm(false, next_sweep())));
+                               s, hist, ctx->red.partials, ctx->red.ticket, pcg, comm(false, next_sweep()), pr));
     }
     B200_LAUNCH_CHECK(ctx);
     B200_TRY(after_reduce(pcg ? FIN_NORM_PCG : FIN_NORM));
-    return push_r_halo();
+    return fold_push ? B200_OK : push_r_halo();
   }
 
   // boundary values of the new r go to the neighbours now; they are consumed by the next K1
@@ -489,6 +531,17 @@ int cg_setup(CgEngine<T> &e, b200_ctx *ctx, const b200_csr *A, T *x, const T *b,
   e.grid_spmv = stream_grid(ctx, n, kThreads / e.lpr, 8);
   e.fold_halo = e.mode == COMM_PEER && !e.jac && A->halo && A->halo_peer && A->n_halo > 0;
   if (e.fold_halo) B200_CUDA(cudaMemsetAsync(A->halo, 0, sizeof(T) * (size_t)A->n_halo, st));   // u_0 = 0
+  e.fold_push = false;
+  if (e.fold_halo && ctx->opt_fold_push != 0) {      // at most two neighbours, each receiving one contiguous range of rows
+    int peers = 0;
+    bool ranges = true;
+    for (int p = 0; p < ctx->world; ++p)
+      if (A->send_count[p] > 0) {
+        peers += 1;
+        ranges = ranges && (int)A->send_range_lo.size() > p && A->send_range_lo[p] >= 0;
+      }
+    e.fold_push = ranges && peers >= 1 && peers <= 2;
+  }
 
   CgScal h;
   memset(&h, 0, sizeof(h));

@@ -102,7 +102,9 @@ struct b200_ctx {
                                  // tcgen05 (TMEM accumulators), 2 = legacy mma.sync Gram, 0 = SIMT kernels
   int opt_orth_fused = 1;        // b200_ctx_set_option("orth_fused"): 1 = one cooperative launch per CGS/DGKS orthogonalisation and a
                                  // device-resident GMRES cycle (single GPU); 0 = the three-kernel path with host-side recurrences
-  int opt_pdl = 1;               // b200_ctx_set_option("pdl"): chain the kernels of a CG iteration with programmatic dependent launch
+  int opt_fold_push = 1;         // b200_ctx_set_option("fold_push"): peer path, cg! with Identity: K3 stores r's boundary rows to the neighbours itself
+  int opt_pdl = 0;               // b200_ctx_set_option("pdl"): chain the kernels of a CG iteration with programmatic dependent launch
+                                 // (off by default: measured SLOWER, 520 vs 560 it/s at 512^3 on 2 GPUs -- profiles/r2_summary.md)
   int opt_snake = 1;            // b200_ctx_set_option("snake"): consecutive hot kernels sweep the rows in alternating directions
   // peer-memory collectives (peer.cuh), multi-GPU contexts only
   bool peer_ok = false;
@@ -170,11 +172,14 @@ __device__ __forceinline__ double block_sum(double v, double *smem /* >= THREADS
 // receives the total in *total (sum over block slots in index order).
 template <int THREADS>
 __device__ __forceinline__ bool grid_reduce_finish(double block_partial, double *partials, unsigned int *ticket,
-                                                   double *smem, double *total) {
+                                                   double *smem, double *total, bool system_scope = false) {
   __shared__ bool is_last;
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = block_partial;
-    __threadfence();
+    // system_scope: the block also stored to mapped peer memory (boundary values for the neighbours); the barrier inside
+    // block_sum ordered those stores before this fence, which makes them visible to the peers before the ticket is taken
+    if (system_scope) __threadfence_system();
+    else __threadfence();
     const unsigned int t = atomicAdd(ticket, 1u);
     is_last = (t == gridDim.x - 1);
   }
@@ -228,8 +233,10 @@ __device__ __forceinline__ int ld_stream<int>(const int *p, uint64_t pol) {
 
 // Programmatic dependent launch (PDL): consecutive kernels of an iteration are chained so that the blocks of kernel k+1 are
 // already resident (launch latency, prologue) when kernel k ends.  A chained kernel starts with pdl_wait() -- it returns once
-// the preceding grid has completed and flushed -- and then lets ITS successor be scheduled with pdl_launch_dependents().
-// Both are no-ops for launches without the attribute.
+// the preceding grid has completed and flushed -- and lets ITS successor be scheduled with pdl_launch_dependents() when its
+// row loop is done, i.e. while the grid reduction / the allreduce wait of the last block is still in flight (triggering at
+// the start kept the next kernel's blocks resident for the whole kernel and cost 5 % at N = 2).  Both are no-ops for
+// launches without the attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 

@@ -372,6 +372,15 @@ int finish_operator(b200_ctx *ctx, b200_csr *A, const b200_halo_plan *plan) {
     }
     A->send_offset[W] = (int64_t)send_idx.size();
     A->recv_offset[W] = plan->recv_offset[W];
+    A->send_range_lo.assign(W, -1);
+    for (int p = 0; p < W; ++p) {
+      const int64_t cnt = A->send_count[p];
+      if (cnt <= 0) continue;
+      const int *l = send_idx.data() + A->send_offset[p];
+      bool contiguous = true;
+      for (int64_t k = 1; k < cnt && contiguous; ++k) contiguous = l[k] == l[0] + (int)k;
+      if (contiguous) A->send_range_lo[p] = l[0];
+    }
     A->n_send = (int64_t)send_idx.size();
     const size_t vs = dtype_size(A->dtype);
     if (A->n_send) {
@@ -802,7 +811,6 @@ __global__ void __launch_bounds__(256) k_halo_push(PushArgs a, const int *__rest
                                                    PeerView pv, unsigned long long seq, unsigned int *ticket,
                                                    const int *__restrict__ done_flag) {
   pdl_wait();
-  pdl_launch_dependents();
   if (done_flag && *done_flag) return;
   const long long n = a.start[a.world];
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
@@ -810,6 +818,7 @@ __global__ void __launch_bounds__(256) k_halo_push(PushArgs a, const int *__rest
     while (k >= a.start[p + 1]) ++p;
     ((T *)a.dst[p])[k - a.start[p]] = x[idx[k]];      // store to mapped peer memory (NVLink)
   }
+  pdl_launch_dependents();
   __threadfence_system();
   __shared__ bool is_last;
   __syncthreads();

@@ -42,6 +42,8 @@ struct b200_csr {
   bool peer_halo = false;
   void *halo_peer = nullptr;               // = ctx->peer_local + kPeerHeaderBytes
   std::vector<int64_t> peer_dst_offset;    // [peer] element offset of MY values inside the peer's halo segment
+  std::vector<int64_t> send_range_lo;      // [peer] first local row when the rows sent to `peer` are ONE ascending contiguous range
+                                           // (slabs of banded operators), -1 otherwise
   unsigned int recv_mask = 0, send_mask = 0;
   // lazily built analysis of the stationary sweeps (stationary.cu): diagonal positions and dependency levels; the
   // operator is immutable, so the plan stays valid for its lifetime
