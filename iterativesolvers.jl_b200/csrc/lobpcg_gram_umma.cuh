@@ -32,6 +32,11 @@
 //               ROW of the same left column) are combined, per-CTA partials go out in fp64 and the last CTA (ticket)
 //               sums them.
 //
+// Measured alternatives (profiles/r2_summary.md): ncu on this version: DRAM traffic = algorithmic (5.37 GB), shared-memory
+// pipe ~50 % LSU wavefronts (conflict-free) + 40 % tensor-core operand reads, tensor pipe 12 %; 1.39 ms per launch = 0.59 of
+// the HBM peak (legacy mma.sync kernel: 1.62 ms).  Converters reading the blocks straight from global memory (no bulk-copy
+// staging, 4 operand stages) were SLOWER (1.47 ms): the staged version stays.
+//
 // Accumulation length.  The tensor core adds each K = 8 product sum to the fp32 accumulator with truncation: a chain of c
 // MMAs biases a positive sum (the diagonals of R'AR, P'AP) by about -c/2 ulp.  Measured (tools/diag_gram_ortho.py) on
 // orthonormal blocks: -2.3e-7 relative with 8 MMAs per hand-over, -2.5e-6 with 64 -- and the legacy mma.sync kernel, whose
@@ -131,11 +136,9 @@ __device__ __forceinline__ void um_wait(unsigned long long *bar, uint32_t parity
     if (spin > (1u << 24)) __trap();
   }
 }
-__device__ __forceinline__ uint32_t um_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// fp32 -> tf32 bit pattern, round to nearest with ties away from zero (what cvt.rna.tf32.f32 computes for finite values,
+// without the Inf / NaN special-casing ptxas wraps around it: two integer operations instead of about nine instructions)
+__device__ __forceinline__ uint32_t um_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u; }
 
 // product index of (left block lb, right block rb) in the output (order of k_gram_rr_tc<2>), -1 if not needed;
 // left blocks X R AR P = 0..3, right blocks R AR P AP = 0..3
@@ -244,19 +247,25 @@ __global__ void __launch_bounds__(kUmThreads, 1) k_gram_umma(UmArgs a, double *p
     // hi tile of columns q*4.. of block b: operand columns b*32 + q*4 + c -> group b*4 + q/2, row-in-group (q%2)*4 + c;
     // the lo tile sits 16 columns = 2 groups further
     const int dst_off = ks * kUmStepBytes + g * kUmHalfStride + (b * 4 + (q >> 1)) * kUmGroupStride + (q & 1) * 64;
-    for (int it = 0; it < nst; ++it) {
-      const int s = it % kUmRawStages, t = it % kUmOpStages;
-      const uint32_t phs = (uint32_t)((it / kUmRawStages) & 1), pht = (uint32_t)((it / kUmOpStages) & 1);
+    // software pipeline over the stages: the 128-bit loads of stage it + 1 are issued before this thread waits for the
+    // operand slot of stage it, so their latency (and the wait for the producer) hides behind the stores and the fence
+    float4 v[4];
+    auto load_stage = [&](int it) {
+      const int s = it % kUmRawStages;
       const int64_t r0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * kUmRows;
-      um_wait(&sm->raw_full[s], phs);
+      um_wait(&sm->raw_full[s], (uint32_t)((it / kUmRawStages) & 1));
       // the two row halves of a quarter-warp read rows of opposite parity (g = 1 swaps its row pairs): no bank conflict
-      float4 v[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int jj = j ^ g;
         v[j] = *reinterpret_cast<const float4 *>(&sm->raw[s][b][(row0 + jj) * 16 + q * 4]);
         if (!(r0 + row0 + jj < n)) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    };
+    if (nst > 0) load_stage(0);
+    for (int it = 0; it < nst; ++it) {
+      const int s = it % kUmRawStages, t = it % kUmOpStages;
+      const uint32_t pht = (uint32_t)((it / kUmOpStages) & 1);
       // hi / lo of the transposed 4 x 4 tile BEFORE the raw stage is released: the conversions consume the loaded
       // registers, so every load has completed when lane 0 arrives on raw_empty.  (Releasing right after issuing the loads
       // let the producer's next bulk copy overwrite the slice under loads still queued behind the operand stores of the
@@ -278,6 +287,7 @@ __global__ void __launch_bounds__(kUmThreads, 1) k_gram_umma(UmArgs a, double *p
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm->raw_empty[s]);    // the slice has been consumed
+      if (it + 1 < nst) load_stage(it + 1);
       um_wait(&sm->op_empty[t], pht ^ 1u);
       unsigned char *dst = sm->op[t] + dst_off;
 #pragma unroll
