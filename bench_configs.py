@@ -8,6 +8,8 @@
     cg256     configs[1]: cg! on laplace_matrix(Float64, 256, 3)
     widen     SURVEY 8(f) item 4: qmr!, lsqr!, lsmr!, idrs!(s=8) on laplace_matrix(Float64, N, 3), fixed iteration counts
               (adjoint operator built by the device transpose)
+    cg2d      configs[0]: cg! on laplace_matrix(Float64, 128, 2) (n = 16 384), reltol = sqrt(eps): solves/s and microseconds per
+              iteration with the persistent cooperative kernel (default) and with the three-launch streaming iteration
     scattered y = A x (mul!) on CSR operators WITHOUT stencil structure, 7 nonzeros per row: columns uniform over all n, and
               columns within a band of +-2^16 around the diagonal -- what the L1/L2 gather of x costs when the x-window argument
               of the stencil case does not apply
@@ -229,6 +231,36 @@ def run(which, grid=256, iters=None, orth="cgs", reps=2, ctx=None, clocks=True, 
                          "frac_of_measured_peak": per_it[name] * h.iters / dt / 1e9 / pk,
                          "first_last": [float(h[key][0]), float(h[key][-1])], "profile": pr}
         out["solvers"] = res
+    elif args.which == "cg2d":
+        from oracle import oracle as _orc        # generator only (this script is a bench tool, like bench.py's CPU arm)
+        O = _orc.laplace_matrix(np.float64, 128, 2, base=1)
+        A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1, ctx=ctx)
+        b = np.random.default_rng(1234321).standard_normal(O.n)
+        b /= np.linalg.norm(b)
+        bd = isb.DeviceArray.from_numpy(ctx, b)
+        xd = isb.DeviceArray.zeros(ctx, O.n)
+        res = {}
+        solves = args.iters or 200
+        for mode in (1, 0):
+            L.b200_ctx_set_option(ctx._h, b"cg_persistent", mode)
+            for rep in range(2):
+                if rep == 1:
+                    clk.start()
+                ctx.sync()
+                t0 = time.perf_counter()
+                its = 0
+                for _ in range(solves):
+                    L.b200_fill(ctx._h, O.n, 0.0, xd._p, 0)
+                    isb.cg_(xd, A, bd, initially_zero=True)
+                    its += int(isb.cg_.last_result.iters)
+                ctx.sync()
+                dt = time.perf_counter() - t0
+            res["persistent" if mode else "three_launches"] = {
+                "clocks": clk.stop(), "solves_per_s": solves / dt, "iterations_per_solve": its / solves,
+                "us_per_iteration": dt / its * 1e6, "iterations_per_s": its / dt}
+        L.b200_ctx_set_option(ctx._h, b"cg_persistent", 1)
+        out.update({"solver": "cg! 5-pt 2-D Poisson 128^2 fp64 (configs[0])", "n": O.n, "engines": res,
+                    "speedup": res["persistent"]["iterations_per_s"] / res["three_launches"]["iterations_per_s"]})
     elif args.which == "scattered":
         V = 8
         per_row = 7
@@ -372,7 +404,7 @@ def run(which, grid=256, iters=None, orth="cgs", reps=2, ctx=None, clocks=True, 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["gmres", "lobpcg", "minres", "bicgstabl", "cg256", "widen", "general", "scattered"])
+    ap.add_argument("which", choices=["gmres", "lobpcg", "minres", "bicgstabl", "cg256", "widen", "general", "scattered", "cg2d"])
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--iters", type=int, default=None)
     ap.add_argument("--orth", default="cgs")

@@ -122,6 +122,9 @@ B200_API int b200_ctx_profile_read(b200_ctx *ctx, int slot, double *total_ms, in
  *   "pdl": 1 = the kernels of a cg! iteration are chained with programmatic dependent launch (griddepcontrol): the
  *           next kernel's blocks are resident when the previous one ends; 0 (default) = plain stream order, which
  *           measured faster on B200 with this driver (560 vs 520 iterations/s, 512^3 on 2 GPUs)
+ *   "cg_persistent": 1 (default) = cg! on single-GPU operators of at most 2^18 rows runs its whole loop in ONE persistent
+ *           cooperative kernel (grid-wide barriers between the phases of an iteration instead of three launches; same
+ *           recurrence, same operation order); 0 = the streaming three-kernel iteration at every size
  *   "fold_push": 1 (default) = multi-GPU peer-memory cg! with Identity: the kernel that updates r stores r's boundary rows
  *           into the neighbours' halo segments itself and its finishing block raises the halo flags (one launch less
  *           per iteration; needs one contiguous row range per neighbour); 0 = separate push kernel

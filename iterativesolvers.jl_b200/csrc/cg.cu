@@ -22,6 +22,8 @@
 //     4 launches per iteration, no NCCL call, no scalar kernel;
 //   * NCCL: halo = pack kernel + grouped ncclSend/ncclRecv, each sum = ncclAllReduce of one double followed
 //     by a 1-thread bookkeeping kernel.
+#include <cooperative_groups.h>
+
 #include "blas1.cuh"
 #include "spmv_stream.cuh"
 #include "linop.cuh"
@@ -343,6 +345,146 @@ __global__ void __launch_bounds__(kThreads) k_pcg_precond(const T *__restrict__ 
     cg_finish(FIN_RHO, s, total, nullptr, cm);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Small operators: the whole CG loop in ONE persistent cooperative kernel (single GPU, Identity / Jacobi).
+// At config-#1 size (5-point Poisson 128^2, n = 16 384) an iteration is a few microseconds of work and the three launches of
+// the streaming path are the cost; here the phases of an iteration are separated by grid-wide barriers instead:
+//   [PCG: c = r ./ d, rho]  ->  x += alpha_prev u ; u = r + beta u  -> sync ->  c = A u, <u,c>  -> sync ->
+//   r -= alpha c, ||r||^2  -> sync
+// Every block sums the per-block partials itself, in the same order, so all blocks hold identical scalars (alpha, beta,
+// residual, done) without a broadcast; the reference's operation order and the unfused multiply / add of its broadcasts are
+// kept (src/cg.jl:43-66, :72-100), the x update rides one phase behind as in the streaming kernels.
+// ------------------------------------------------------------------------------------------------
+namespace cgx = cooperative_groups;
+constexpr int64_t kPersistMaxRows = 1 << 18;      // above this the TMA-streamed kernels win (vectors no longer L2-resident)
+
+template <int THREADS>
+__device__ __forceinline__ double all_blocks_sum(const double *slots, unsigned int nslots, double *smem, double *bcast) {
+  double a = 0.0;
+  for (unsigned int i = threadIdx.x; i < nslots; i += THREADS) a += __ldcg(&slots[i]);   // same scheme as grid_reduce_finish
+  a = block_sum<THREADS>(a, smem);
+  if (threadIdx.x == 0) *bcast = a;
+  __syncthreads();
+  const double t = *bcast;
+  __syncthreads();
+  return t;
+}
+
+template <typename T, int LPR>
+__global__ void __launch_bounds__(kThreads) k_cg_persistent(const int *__restrict__ rowptr, const int *__restrict__ colind,
+                                                            const T *__restrict__ vals, const T *__restrict__ jac, T *x, T *r,
+                                                            T *u, T *c, int64_t n, CgScal *s, double *hist, double *partials,
+                                                            long long iters) {
+  cgx::grid_group grid = cgx::this_grid();
+  __shared__ double smem[kThreads / 32];
+  __shared__ double bcast;
+  double *pa = partials, *pb = partials + kMaxPartials, *pc = partials + 2 * kMaxPartials;
+  // every block keeps its own copy of the scalars; they evolve identically
+  double residual = s->residual, prev_residual = s->prev_residual, alpha = s->alpha, rho = s->rho, rho_prev = s->rho_prev;
+  const double tol = s->tol;
+  long long iter = s->iter;
+  const long long maxiter = s->maxiter, hist_cap = s->hist_cap;
+  const int fixed = s->fixed, pcg = s->pcg;
+  int done = s->done, breakdown = s->breakdown;
+  double dot_uc = s->dot_uc;
+  const int64_t gstride = (int64_t)gridDim.x * kThreads;
+  constexpr int ROWS = kThreads / LPR;
+  const int sub = threadIdx.x % LPR, rib = threadIdx.x / LPR;
+  XView<T> xv;
+  xv.x = u;
+  xv.halo = u;
+  xv.m = (int)n;
+  for (long long it = 0; it < iters && !done; ++it) {
+    if (pcg) {                                            // c = Pl \ r ; rho = <c, r>   (:79-82)
+      double acc = 0.0;
+      for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += gstride) {
+        const T ri = r[i];
+        const T ci = ri / jac[i];
+        c[i] = ci;
+        acc += (double)ci * (double)ri;
+      }
+      acc = block_sum<kThreads>(acc, smem);
+      if (threadIdx.x == 0) pc[blockIdx.x] = acc;
+      __threadfence();
+      grid.sync();
+      rho_prev = rho;
+      rho = all_blocks_sum<kThreads>(pc, gridDim.x, smem, &bcast);
+    }
+    // x += alpha_prev u (deferred :58) ; u = r + beta u (:50-51 / :85-86)
+    const T beta = (T)(pcg ? rho / rho_prev : (residual * residual) / (prev_residual * prev_residual));
+    const T al = (T)alpha;
+    const bool upd_x = iter > 0;
+    const T *src = pcg ? c : r;
+    for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += gstride) {
+      const T ui = u[i];
+      if constexpr (sizeof(T) == 8) {
+        if (upd_x) x[i] = __dadd_rn(x[i], __dmul_rn(al, ui));
+        u[i] = __dadd_rn(src[i], __dmul_rn(beta, ui));
+      } else {
+        if (upd_x) x[i] = __fadd_rn(x[i], __fmul_rn(al, ui));
+        u[i] = __fadd_rn(src[i], __fmul_rn(beta, ui));
+      }
+    }
+    __threadfence();
+    grid.sync();
+    // c = A u ; <u, c>   (:54-55)
+    {
+      double acc = 0.0;
+      for (int64_t base = (int64_t)blockIdx.x * ROWS; base < n; base += (int64_t)gridDim.x * ROWS) {
+        const int64_t row = base + rib;
+        const bool valid = row < n;
+        const T ci = row_dot<T, LPR>(rowptr, colind, vals, xv, valid ? row : (n - 1), sub);
+        if (valid && sub == 0) {
+          c[row] = ci;
+          acc += (double)u[row] * (double)ci;
+        }
+      }
+      acc = block_sum<kThreads>(acc, smem);
+      if (threadIdx.x == 0) pa[blockIdx.x] = acc;
+    }
+    __threadfence();
+    grid.sync();
+    dot_uc = all_blocks_sum<kThreads>(pa, gridDim.x, smem, &bcast);
+    alpha = pcg ? rho / dot_uc : (residual * residual) / dot_uc;
+    // r -= alpha c ; ||r||   (:59-62 / :94-96)
+    {
+      const T a2 = (T)alpha;
+      double acc = 0.0;
+      for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < n; i += gstride) {
+        T ri;
+        if constexpr (sizeof(T) == 8) ri = __dsub_rn(r[i], __dmul_rn(a2, c[i]));
+        else ri = __fsub_rn(r[i], __fmul_rn(a2, c[i]));
+        r[i] = ri;
+        acc += (double)ri * (double)ri;
+      }
+      acc = block_sum<kThreads>(acc, smem);
+      if (threadIdx.x == 0) pb[blockIdx.x] = acc;
+    }
+    __threadfence();
+    grid.sync();
+    const double rr = all_blocks_sum<kThreads>(pb, gridDim.x, smem, &bcast);
+    if (!pcg) prev_residual = residual;                   // cg_after_norm
+    residual = sqrt(rr);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && hist && iter < hist_cap) hist[iter] = residual;
+    iter += 1;
+    if (!(residual == residual)) breakdown = 1;
+    const bool conv = !fixed && (residual <= tol);
+    done = (iter >= maxiter) || conv || (!fixed && breakdown);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    s->residual = residual;
+    s->prev_residual = prev_residual;
+    s->alpha = alpha;
+    s->dot_uc = dot_uc;
+    s->rho = rho;
+    s->rho_prev = rho_prev;
+    s->iter = iter;
+    s->done = done;
+    s->breakdown = breakdown;
+  }
+}
+
 template <typename T>
 struct CgEngine {
   b200_ctx *ctx;
@@ -358,6 +500,8 @@ struct CgEngine {
   int sweep = 0;   // direction of the next hot kernel (toggled per launch when ctx->opt_snake)
   bool fold_halo = false;   // peer path, Identity: r's boundary is pushed after K3 and K1 forms u's halo locally
   bool fold_push = false;   // ... and K3 itself stores the boundary rows to the neighbours (contiguous send ranges)
+  bool persistent = false;  // small single-GPU operator: the whole loop runs in k_cg_persistent
+  int grid_persist = 0;
 
   int next_sweep() {
     const int d = ctx->opt_snake ? sweep : 0;
@@ -494,6 +638,36 @@ struct CgEngine {
     return fold_push ? B200_OK : push_r_halo();
   }
 
+  // k iterations (fewer if done() comes first): one cooperative launch for small operators, k x iterate() otherwise
+  int iterate_many(int64_t k) {
+    if (!persistent) {
+      for (int64_t i = 0; i < k; ++i) B200_TRY(iterate());
+      return B200_OK;
+    }
+    if (k <= 0) return B200_OK;
+    const int *rp = A->rowptr, *ci = A->colind;
+    const T *va = (const T *)A->vals, *jc = jac;
+    T *x_ = x, *r_ = r, *u_ = u, *c_ = c;
+    int64_t n_ = n;
+    CgScal *s_ = s;
+    double *h_ = hist, *pt = ctx->red.partials;
+    long long kk = k;
+    void *args[] = {(void *)&rp, (void *)&ci, (void *)&va, (void *)&jc, (void *)&x_, (void *)&r_, (void *)&u_, (void *)&c_,
+                    (void *)&n_, (void *)&s_, (void *)&h_, (void *)&pt, (void *)&kk};
+    const void *kern = nullptr;
+    switch (lpr) {
+      case 2: kern = (const void *)k_cg_persistent<T, 2>; break;
+      case 4: kern = (const void *)k_cg_persistent<T, 4>; break;
+      case 8: kern = (const void *)k_cg_persistent<T, 8>; break;
+      case 16: kern = (const void *)k_cg_persistent<T, 16>; break;
+      default: kern = (const void *)k_cg_persistent<T, 32>; break;
+    }
+    ProfScope prof(ctx, 0);
+    B200_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid_persist), dim3(kThreads), args, 0, ctx->stream));
+    ctx->launches++;
+    return B200_OK;
+  }
+
   // boundary values of the new r go to the neighbours now; they are consumed by the next K1
   int push_r_halo() {
     if (!fold_halo) return B200_OK;
@@ -531,6 +705,24 @@ int cg_setup(CgEngine<T> &e, b200_ctx *ctx, const b200_csr *A, T *x, const T *b,
   e.grid_spmv = stream_grid(ctx, n, kThreads / e.lpr, 8);
   e.fold_halo = e.mode == COMM_PEER && !e.jac && A->halo && A->halo_peer && A->n_halo > 0;
   if (e.fold_halo) B200_CUDA(cudaMemsetAsync(A->halo, 0, sizeof(T) * (size_t)A->n_halo, st));   // u_0 = 0
+  e.persistent = false;
+  if (ctx->world == 1 && ctx->opt_cg_persistent != 0 && n > 0 && n <= kPersistMaxRows) {
+    int per_sm = 0;
+    const void *kern = nullptr;
+    switch (e.lpr) {
+      case 2: kern = (const void *)k_cg_persistent<T, 2>; break;
+      case 4: kern = (const void *)k_cg_persistent<T, 4>; break;
+      case 8: kern = (const void *)k_cg_persistent<T, 8>; break;
+      case 16: kern = (const void *)k_cg_persistent<T, 16>; break;
+      default: kern = (const void *)k_cg_persistent<T, 32>; break;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, 0) == cudaSuccess && per_sm >= 1) {
+      const int64_t want = (n + (kThreads / e.lpr) - 1) / (kThreads / e.lpr);          // one SpMV row group per block
+      const int64_t cap = std::min<int64_t>((int64_t)ctx->sm_count * std::min(per_sm, 2), kMaxPartials);
+      e.grid_persist = (int)std::max<int64_t>(1, std::min<int64_t>(want, cap));
+      e.persistent = true;
+    }
+  }
   e.fold_push = false;
   if (e.fold_halo && ctx->opt_fold_push != 0) {      // at most two neighbours, each receiving one contiguous range of rows
     int peers = 0;
@@ -592,8 +784,9 @@ int cg_solve_impl(b200_ctx *ctx, const b200_csr *A, T *x, const T *b, const b200
     B200_CUDA(cudaMemcpyAsync(h_done, &e.s->done, sizeof(int), cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     if (*h_done || enqueued >= maxiter) break;
-    const int64_t batch = std::min<int64_t>(check_every, maxiter - enqueued);
-    for (int64_t i = 0; i < batch; ++i) B200_TRY(e.iterate());
+    // persistent kernel: a launch runs until done() or its iteration budget, so the budget per host check can be large
+    const int64_t batch = std::min<int64_t>(e.persistent ? std::max<int64_t>(check_every, 1024) : check_every, maxiter - enqueued);
+    B200_TRY(e.iterate_many(batch));
     enqueued += batch;
   }
   k_cg_flush_x<T><<<e.grid_vec, kThreads, 0, st>>>(e.u, x, n, e.s);   // x += alpha*u of the last iteration
@@ -670,8 +863,7 @@ int cg_iter_next_impl(CgIterState<T> *it, int64_t k, b200_result *res, double *r
   e.hist = window ? (double *)it->hist.p - start : nullptr;
   k_cg_iter_ctl<<<1, 1, 0, st>>>(e.s, start + window, 0);
   B200_LAUNCH_CHECK(ctx);
-  if (!h.done)
-    for (int64_t i = 0; i < k; ++i) B200_TRY(e.iterate());          // iterate(it) x k  (src/cg.jl:43-66 / :72-100)
+  if (!h.done) B200_TRY(e.iterate_many(k));                         // iterate(it) x k  (src/cg.jl:43-66 / :72-100)
   k_cg_flush_x<T><<<e.grid_vec, kThreads, 0, st>>>(e.u, e.x, e.n, e.s);
   B200_LAUNCH_CHECK(ctx);
   k_cg_iter_ctl<<<1, 1, 0, st>>>(e.s, -1, 1);

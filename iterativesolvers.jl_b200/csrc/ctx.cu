@@ -247,6 +247,10 @@ int b200_ctx_set_option(b200_ctx *c, const char *name, int64_t value) {
     c->opt_snake = value != 0;
     return B200_OK;
   }
+  if (strcmp(name, "cg_persistent") == 0) {
+    c->opt_cg_persistent = value != 0;
+    return B200_OK;
+  }
   if (strcmp(name, "fold_push") == 0) {
     c->opt_fold_push = value != 0;
     return B200_OK;
@@ -282,6 +286,7 @@ int b200_ctx_get_option(const b200_ctx *c, const char *name, int64_t *value) {
   else if (strcmp(name, "orth_fused") == 0) *value = c->opt_orth_fused;
   else if (strcmp(name, "pdl") == 0) *value = c->opt_pdl;
   else if (strcmp(name, "fold_push") == 0) *value = c->opt_fold_push;
+  else if (strcmp(name, "cg_persistent") == 0) *value = c->opt_cg_persistent;
   else if (strcmp(name, "peer_ok") == 0) *value = c->peer_ok ? 1 : 0;
   else {
     set_error("unknown option `%s`", name);

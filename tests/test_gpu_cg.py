@@ -394,3 +394,52 @@ def test_cg_statevars_are_used_and_hold_the_state(isb, oracle):
     assert relerr(sv.c.numpy(), A @ sv.u.numpy()) <= 1e-13
     with pytest.raises(TypeError):
         isb.CGStateVariables(np.zeros(3), np.zeros(3), np.zeros(3))
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 1e-9), (np.float32, 1e-3)])
+def test_cg_persistent_kernel_equals_the_streaming_iteration(isb, oracle, dtype, tol):
+    """Operators of at most 2^18 rows run the whole cg! loop in one cooperative kernel (option cg_persistent, default on);
+    option 0 selects the three-kernel streaming iteration at every size.  Same recurrence and operation order, another
+    grouping of the partial sums: same iteration counts, histories within rounding of each other, both within the stated
+    tolerance of the oracle -- CG and PCG, config #1 (5-point Poisson 128^2), an odd size, maxiter in the middle of a launch,
+    and the iterator form (one step at a time) bit-identical to the one-shot solve."""
+    L = isb.lib()
+    ctx = isb.default_context()
+    rng = np.random.default_rng(SEED + 7)
+    for N, dims in ((128, 2), (23, 3)):
+        O = oracle.laplace_matrix(dtype, N, dims, base=1)
+        A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+        b = rng.standard_normal(O.n).astype(dtype)
+        b /= np.linalg.norm(b)
+        d = (O.diagonal() * (1.0 + 0.5 * rng.random(O.n))).astype(dtype)
+        for kw_d, kw_o in (({}, {}), ({"Pl": isb.JacobiPrec(d)}, {"Pl": oracle.JacobiPrec(d)}), ({"maxiter": 37}, {"maxiter": 37})):
+            out = {}
+            try:
+                for mode in (1, 0):
+                    assert L.b200_ctx_set_option(ctx._h, b"cg_persistent", mode) == 0
+                    out[mode] = isb.cg(A, b, log=True, **kw_d)
+            finally:
+                L.b200_ctx_set_option(ctx._h, b"cg_persistent", 1)
+            (x1, h1), (x0, h0) = out[1], out[0]
+            if dtype == np.float64:
+                assert (h1.niters, h1.mvps, h1.isconverged) == (h0.niters, h0.mvps, h0.isconverged)
+                assert np.max(np.abs(h1["resnorm"] - h0["resnorm"]) / h0["resnorm"]) <= tol
+            else:   # fp32 recurrences drift apart after some tens of iterations (first run: 6e-3 at the end): compare the start
+                assert abs(h1.niters - h0.niters) <= 2 and h1.isconverged == h0.isconverged
+                k = min(30, h1.niters, h0.niters)
+                assert np.max(np.abs(h1["resnorm"][:k] - h0["resnorm"][:k]) / h0["resnorm"][:k]) <= tol
+            if dtype == np.float64:
+                xo, ho = oracle.cg(O, b, log=True, **kw_o)
+                assert h1.niters == ho.niters and h1.isconverged == ho.isconverged
+                assert np.max(np.abs(h1["resnorm"] - ho["resnorm"]) / ho["resnorm"]) <= 1e-10
+                assert np.linalg.norm(x1 - xo) <= 1e-10 * np.linalg.norm(xo)
+    # iterator, one step per call, against the one-shot solve: both run the persistent kernel
+    O = oracle.laplace_matrix(dtype, 16, 3, base=1)
+    A = isb.B200CSR.from_csc_arrays(O.colptr, O.rowval, O.nzval, O.shape, base=1)
+    b = rng.standard_normal(O.n).astype(dtype)
+    xs, hs = isb.cg(A, b, log=True)
+    x = np.zeros(O.n, dtype=dtype)
+    it = isb.cg_iterator_(x, A, b, initially_zero=True)
+    res = [r for r in it]
+    it.close()
+    assert np.array_equal(np.array(res), hs["resnorm"]) and np.array_equal(x, xs)
