@@ -259,7 +259,7 @@ def run(which, grid=256, iters=None, orth="cgs", reps=2, ctx=None, clocks=True, 
                 "clocks": clk.stop(), "solves_per_s": solves / dt, "iterations_per_solve": its / solves,
                 "us_per_iteration": dt / its * 1e6, "iterations_per_s": its / dt}
         L.b200_ctx_set_option(ctx._h, b"cg_persistent", 1)
-        out.update({"solver": "cg! 5-pt 2-D Poisson 128^2 fp64 (configs[0])", "n": O.n, "engines": res,
+        out.update({"solver": "cg! 5-pt 2-D Poisson 128^2 fp64 (configs[0])", "grid": 128, "n": O.n, "nnz": int(A.nnz), "engines": res,
                     "speedup": res["persistent"]["iterations_per_s"] / res["three_launches"]["iterations_per_s"]})
     elif args.which == "scattered":
         V = 8
