@@ -20,6 +20,7 @@ OUT = os.path.join(ROOT, "profiles")
 # tag -> (substring of the mangled name that selects ONE instantiation, what to show)
 HOT = {
     "cg_k2_spmv_dot_stream_f64": ("k_cg_spmv_dot_streamIdLi8E", "K2 of cg!: c = A u fused with dot(u, c); TMA-bulk streamed CSR"),
+    "cg_persistent": ("k_cg_persistentIdLi8E", "cg! for small operators: the whole loop in one persistent cooperative kernel"),
     "cg_k1_update_u": ("k_cg_update_uId", "K1 of cg!: x += alpha u_old (deferred), u = r + beta u"),
     "cg_k3_update_r": ("k_cg_update_rId", "K3 of cg!: r -= alpha c fused with ||r||^2 (and the warp-parallel NVLink allreduce)"),
     "gmres_block_dots": ("k_block_dotsIdLi2E", "CGS/DGKS block of dots h = V' w (three-kernel path)"),
