@@ -922,7 +922,10 @@ struct Lobpcg {
   double *gram_partials, *d_gram;                // device Gram output: 4 * 256 doubles
   T *d_small;                                    // V (3*256) + lambda (16) + U (256)
   int *d_idx;
-  DevBuf scratch, send_blk, halo_blk;              // multi-GPU: packed boundary rows out / halo rows in (n x 16)
+  DevBuf scratch;
+  // multi-GPU: packed boundary rows out / halo rows in (rows x 16), carved from the context workspace: a cudaMalloc / cudaFree
+  // pair per solve costs tens of milliseconds once peer mappings exist (measured: 40 instead of 150 steps/s on 2 GPUs)
+  struct { void *p = nullptr; } send_blk, halo_blk;
   int grid_gram, grid_vec, grid_spmm;
 
   template <int NR>
@@ -1100,8 +1103,10 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
   const size_t blk_bytes = align_up(sizeof(T) * (size_t)n * BS, 256);
   const size_t small_bytes = align_up(sizeof(T) * (3 * 256 + 16 + 256), 256);
   const size_t gram_bytes = sizeof(double) * ((size_t)L.grid_gram * 8 * 256 + 8 * 256 + 64);
+  const size_t send_bytes = ctx->world > 1 ? align_up(sizeof(T) * BS * (size_t)std::max<int64_t>(A->n_send, 1), 256) : 0;
+  const size_t halo_bytes = ctx->world > 1 ? align_up(sizeof(T) * BS * (size_t)std::max<int64_t>(A->n_halo, 1), 256) : 0;
   void *ws = nullptr;
-  B200_TRY(ws_get(ctx, 6 * blk_bytes + small_bytes + gram_bytes + 1024, &ws));
+  B200_TRY(ws_get(ctx, 6 * blk_bytes + small_bytes + align_up(gram_bytes, 256) + send_bytes + halo_bytes + 1024, &ws));
   char *p = (char *)ws;
   L.X = (T *)p; p += blk_bytes;
   L.AX = (T *)p; p += blk_bytes;
@@ -1116,8 +1121,9 @@ int lobpcg_impl(b200_ctx *ctx, const b200_csr *A, T *Xcm, int64_t ldx, const b20
   L.d_idx = (int *)p;
   L.gR = L.gP = L.gAP = nullptr;
   if (ctx->world > 1) {
-    B200_TRY(L.send_blk.alloc(sizeof(T) * BS * (size_t)std::max<int64_t>(A->n_send, 1)));
-    B200_TRY(L.halo_blk.alloc(sizeof(T) * BS * (size_t)std::max<int64_t>(A->n_halo, 1)));
+    char *q = (char *)ws + 6 * blk_bytes + small_bytes + align_up(gram_bytes, 256) + 256;
+    L.send_blk.p = q;
+    L.halo_blk.p = q + send_bytes;
   }
   k_to_rowmajor<T><<<L.grid_vec, kThreads, 0, st>>>(Xcm, L.X, n, sizeX);
   B200_LAUNCH_CHECK(ctx);
