@@ -926,9 +926,9 @@ int b200_cg_solve_host(b200_ctx *ctx, const b200_csr *A, void *x_host, const voi
   B200_TRY(check_cg_args(ctx, A, x_host, b_host, opts));
   B200_CUDA(cudaSetDevice(ctx->device));
   const size_t bytes = dtype_size(A->dtype) * (size_t)A->m_local;
-  DevBuf dx, db;
-  B200_TRY(dx.alloc(bytes));
-  B200_TRY(db.alloc(bytes));
+  struct { void *p; } dx, db;
+  B200_TRY(stage_get(ctx, 0, bytes ? bytes : 16, &dx.p));
+  B200_TRY(stage_get(ctx, 1, bytes ? bytes : 16, &db.p));
   B200_CUDA(cudaMemcpyAsync(db.p, b_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   B200_CUDA(cudaMemcpyAsync(dx.p, x_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   int s = b200_cg_solve(ctx, A, dx.p, db.p, opts, res, resnorm_host, resnorm_cap);

@@ -122,6 +122,8 @@ struct b200_ctx {
   int64_t prof_n[4] = {0, 0, 0, 0};
   void *ws = nullptr;            // grow-only solver workspace (reused across solves: no malloc in the timed path)
   size_t ws_bytes = 0;
+  void *stage[2] = {nullptr, nullptr};   // grow-only device staging of the host-buffer entry points (x, b): no cudaMalloc / cudaFree per solve
+  size_t stage_bytes[2] = {0, 0};
   void *orth_scal = nullptr;     // device GmScal of the op-level orthogonalize_and_normalize! (gmres.cu), allocated on first use
   int in_callback = 0;           // > 0 while an operator / preconditioner callback runs: the workspace belongs to the caller
 };
@@ -311,6 +313,25 @@ inline int ws_get(b200_ctx *ctx, size_t bytes, void **out) {
   return B200_OK;
 }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// grow-only staging buffer `which` (0 / 1) of the context; contents are scratch.  cudaMalloc / cudaFree per call are not an
+// option on multi-GPU contexts: with CUDA-IPC peer mappings each costs tens of milliseconds (profiles/r2_summary.md section 8)
+inline int stage_get(b200_ctx *ctx, int which, size_t bytes, void **out) {
+  if (bytes > ctx->stage_bytes[which]) {
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stage[which]) cudaFree(ctx->stage[which]);
+    ctx->stage[which] = nullptr;
+    ctx->stage_bytes[which] = 0;
+    cudaError_t e = cudaMalloc(&ctx->stage[which], bytes);
+    if (e != cudaSuccess) {
+      set_error("staging cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+      return B200_ERR_ALLOC;
+    }
+    ctx->stage_bytes[which] = bytes;
+  }
+  *out = ctx->stage[which];
+  return B200_OK;
+}
 
 // grid size for streaming kernels: a multiple of the SM count (148 on B200), capped by the work
 inline int stream_grid(const b200_ctx *ctx, int64_t work_items, int items_per_block, int blocks_per_sm) {

@@ -190,6 +190,8 @@ int b200_ctx_destroy(b200_ctx *c) {
   cudaFree(c->d_scalars);
   if (c->ws) cudaFree(c->ws);
   if (c->orth_scal) cudaFree(c->orth_scal);
+  for (int k = 0; k < 2; ++k)
+    if (c->stage[k]) cudaFree(c->stage[k]);
   for (auto e : c->prof_ev) cudaEventDestroy(e);
   cudaFreeHost(c->h_scalars);
   cudaFreeHost(c->h_flags);
