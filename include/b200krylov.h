@@ -195,6 +195,11 @@ B200_API int b200_halo_plan_recv_cols(const b200_halo_plan *plan, int owner, int
 /* tell the plan which of MY rows `peer` needs (global indices, the peer's recv_cols for me) */
 B200_API int b200_halo_plan_set_send(b200_halo_plan *plan, int peer, const int64_t *cols, int64_t count);
 B200_API int64_t b200_halo_plan_send_count(const b200_halo_plan *plan, int peer);
+/* 1 (and *lo_local = first local row) when the rows `peer` asked for are ONE ascending contiguous range of this
+ * rank's slab -- then the CG update kernel stores them straight into the peer's halo (no pack kernel); 0 otherwise
+ * (empty, or scattered: packed and pushed by the halo kernel); -1 on bad arguments.  Slab-partitioned stencils
+ * (the reference's laplace_matrix, test/laplace_matrix.jl:3-19) always give ranges. */
+B200_API int b200_halo_plan_send_range(const b200_halo_plan *plan, int peer, int64_t *lo_local);
 B200_API int64_t b200_halo_plan_n_halo(const b200_halo_plan *plan);
 /* global column -> local extended index ([0,m_local) own rows, [m_local, m_local+n_halo) halo) */
 B200_API int64_t b200_halo_plan_local_index(const b200_halo_plan *plan, int64_t global_col);

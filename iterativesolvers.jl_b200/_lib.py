@@ -157,6 +157,7 @@ SIGNATURES = {
     "b200_halo_plan_recv_cols": (_INT, [_P, _INT, _P]),
     "b200_halo_plan_set_send": (_INT, [_P, _INT, _P, _I64]),
     "b200_halo_plan_send_count": (_I64, [_P, _INT]),
+    "b200_halo_plan_send_range": (_INT, [_P, _INT, C.POINTER(_I64)]),
     "b200_halo_plan_n_halo": (_I64, [_P]),
     "b200_halo_plan_local_index": (_I64, [_P, _I64]),
     "b200_halo_plan_destroy": (_INT, [_P]),

@@ -119,6 +119,15 @@ int64_t b200_halo_plan_send_count(const b200_halo_plan *p, int peer) {
   if (!p || peer < 0 || peer >= p->world) return -1;
   return (int64_t)p->send_cols[peer].size();
 }
+int b200_halo_plan_send_range(const b200_halo_plan *p, int peer, int64_t *lo_local) {
+  if (!p || peer < 0 || peer >= p->world) return -1;
+  const std::vector<int64_t> &c = p->send_cols[peer];
+  if (c.empty()) return 0;
+  for (size_t k = 1; k < c.size(); ++k)
+    if (c[k] != c[0] + (int64_t)k) return 0;
+  if (lo_local) *lo_local = c[0] - p->row_offsets[p->rank];
+  return 1;
+}
 int64_t b200_halo_plan_n_halo(const b200_halo_plan *p) { return p ? (int64_t)p->halo_sorted.size() : -1; }
 int64_t b200_halo_plan_local_index(const b200_halo_plan *p, int64_t c) {
   if (!p) return -1;
@@ -374,12 +383,7 @@ int finish_operator(b200_ctx *ctx, b200_csr *A, const b200_halo_plan *plan) {
     A->recv_offset[W] = plan->recv_offset[W];
     A->send_range_lo.assign(W, -1);
     for (int p = 0; p < W; ++p) {
-      const int64_t cnt = A->send_count[p];
-      if (cnt <= 0) continue;
-      const int *l = send_idx.data() + A->send_offset[p];
-      bool contiguous = true;
-      for (int64_t k = 1; k < cnt && contiguous; ++k) contiguous = l[k] == l[0] + (int)k;
-      if (contiguous) A->send_range_lo[p] = l[0];
+      if (b200_halo_plan_send_range(plan, p, nullptr) == 1) A->send_range_lo[p] = plan->send_cols[p][0] - A->row_begin;
     }
     A->n_send = (int64_t)send_idx.size();
     const size_t vs = dtype_size(A->dtype);

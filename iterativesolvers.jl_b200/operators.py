@@ -89,6 +89,15 @@ class HaloPlan:
     def send_count(self, peer: int) -> int:
         return int(lib().b200_halo_plan_send_count(self._h, peer))
 
+    def send_range(self, peer: int):
+        """first local row when the rows `peer` asked for are one ascending contiguous range (then the CG update kernel
+        stores them straight into the peer's halo), else None."""
+        lo = C.c_int64(-1)
+        r = int(lib().b200_halo_plan_send_range(self._h, peer, C.byref(lo)))
+        if r < 0:
+            raise ValueError("bad peer")
+        return int(lo.value) if r == 1 else None
+
     @property
     def n_halo(self) -> int:
         return int(lib().b200_halo_plan_n_halo(self._h))

@@ -126,6 +126,14 @@ other = 1 - rank
 objs = [None, None]
 dist.all_gather_object(objs, plan.recv_cols(other))
 assert plan.send_count(other) == len(objs[other])
+# z-slabs of a stencil: the rows the peer needs are one contiguous plane -> the fused push of the CG update kernel
+want_lo = (hi - lo) - N * N if rank == 0 else 0
+assert plan.send_range(other) == want_lo and plan.send_count(other) == N * N and plan.send_range(rank) is None
+scat = isb.HaloPlan(rank, world, offs)
+scat.set_send(other, np.array([lo, lo + 2, lo + 3], dtype=np.int64))     # scattered rows: packed push, no range
+assert scat.send_range(other) is None
+scat.set_send(other, np.array([lo + 5, lo + 6, lo + 7], dtype=np.int64))
+assert scat.send_range(other) == 5
 # emulate the halo SpMV on the host: x slab + received halo values, local extended indices
 rng = np.random.default_rng(1234321)
 x_global = rng.standard_normal(n)
